@@ -1,0 +1,215 @@
+/*
+ * gamc_b200.h -- C ABI of the B200-native GAMC hot path (libgamc_b200.so).
+ *
+ * Drop-in boundary for papamarkou/GAMCSampler.jl's per-iteration hot path: evaluation of log-target,
+ * gradient and metric tensor, and the SMMALA / AM transition that consumes them.  Plain pointers and
+ * sizes only; all matrices are COLUMN-MAJOR FP64 (Julia's native layout, so a Julia `Matrix{Float64}` /
+ * `Vector{Float64}` is passed by pointer with no copy on the host side).  The caller owns every host
+ * buffer; the library owns all device memory behind the handle.  One handle = one CUDA device + one
+ * stream; calls on one handle are serialised, different handles are independent.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference repo).
+ * The ccall binding a GAMCSampler.jl maintainer would add is in INTEGRATION.md and
+ * gamcsampler.jl_b200/julia/GAMCSamplerB200.jl.
+ */
+#ifndef GAMC_B200_H
+#define GAMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gamc_ctx* gamc_handle;
+
+/* Error behaviour of the reference: `@assert` -> AssertionError (src/samplers/GAMC.jl:51-67,135-138,168-170),
+ * PosDefException from `chol` (src/samplers/iterate/GAMC.jl:30,94 and the MvNormal constructor behind
+ * set_gmm, src/samplers/GAMC.jl:188), SingularException from `inv` (:26,43). */
+typedef enum {
+  GAMC_OK = 0,
+  GAMC_INVALID_ARG = 1,       /* AssertionError: bad sampler parameter / null pointer / bad size          */
+  GAMC_NONFINITE_INIT = 2,    /* "Log-target not finite: initial value out of support" (GAMC.jl:168-170) */
+  GAMC_NOT_POSDEF = 3,        /* PosDefException / SingularException; pivot via gamc_last_error_string   */
+  GAMC_CUDA_ERROR = 4,
+  GAMC_NCCL_ERROR = 5,
+  GAMC_UNSUPPORTED_SHAPE = 6, /* p outside the compiled kernel range (1..512)                            */
+  GAMC_NOT_READY = 7          /* call order violated (no target / sampler not initialised / no tape)     */
+} gamc_status;
+
+/* Schedules: `update!` functions of src/samplers/GAMC.jl:264-337 (decay formulas src/stats/schedule.jl:1-7). */
+typedef enum {
+  GAMC_SCHED_AM_ONLY = 0,        /* am_only_update!          :264                         */
+  GAMC_SCHED_SMMALA_ONLY = 1,    /* smmala_only_update!      :336                         */
+  GAMC_SCHED_MOD = 2,            /* mod_update!(n=10)        :277   params[0] = n          */
+  GAMC_SCHED_RAND = 3,           /* rand_update!(p=0.5)      :327   params[0] = p          */
+  GAMC_SCHED_COS = 4,            /* cos_update!(a,b,c)       :267   params = a,b,c         */
+  GAMC_SCHED_RAND_EXP_DECAY = 5, /* rand_exp_decay_update!   :287   params = a(10), b(0)   */
+  GAMC_SCHED_RAND_LIN_DECAY = 6, /* rand_lin_decay_update!   :297   params = a(1e-2), b    */
+  GAMC_SCHED_RAND_POW_DECAY = 7, /* rand_pow_decay_update!   :307   params = a(1e-3), b    */
+  GAMC_SCHED_RAND_QUAD_DECAY = 8 /* rand_quad_decay_update!  :317   params = a(1e-5), b    */
+} gamc_schedule;
+
+/* Sampler + tuner + range configuration.  Mirrors `GAMC(; update, transform, driftstep, minorscale, c, t0)`
+ * (src/samplers/GAMC.jl:126-151), `GAMCTuner(smmalatuner, amtuner, totaltuner)` (src/tuners/GAMCTuner.jl:15-23)
+ * with Klara's VanillaMCTuner / AcceptanceRateMCTuner, and `BasicMCRange(nsteps, burnin)`
+ * (examples/logistic_regression/src/GAMC/simulations.jl:57). */
+typedef struct {
+  double driftstep;        /* > 0                                                                  */
+  double minorscale;       /* > 0: covariance scale of the stabilising mixture component           */
+  double c;                /* >= 0: weight of the stabilising component                            */
+  int32_t t0;              /* > 0: first t0 iterations are always SMMALA                           */
+  int32_t schedule;        /* gamc_schedule                                                        */
+  double sched_params[3];  /* NaN = reference default for that schedule                            */
+  int32_t total_tuner_kind;/* 0 = VanillaMCTuner, 1 = AcceptanceRateMCTuner                        */
+  double targetrate;       /* AcceptanceRateMCTuner target (0.35 in the examples)                  */
+  double score_k;          /* logistic_rate_score steepness (Klara default 7)                      */
+  int32_t period;          /* tuner period (Klara default 100)                                     */
+  int32_t verbose_total;   /* VanillaMCTuner(verbose=...) flags: they switch the counters on       */
+  int32_t verbose_smmala;  /*   (src/samplers/iterate/GAMC.jl:4-6,15-17,129-131)                   */
+  int32_t verbose_am;
+  int64_t nsteps;          /* BasicMCRange.nsteps (the `tot` argument of the schedules)            */
+  int64_t burnin;          /* BasicMCRange.burnin                                                  */
+  int32_t am_mode;         /* 0 = literal covariance recursion + Cholesky each AM step,
+                              1 = rank-one Cholesky update of the same recursion (fast path)       */
+  int32_t reserved;
+} gamc_config;
+
+/* Snapshot of the scalar sampler state: fields of MuvGAMCState / GAMCTune that the reference exposes
+ * (src/samplers/GAMC.jl:7-27, src/tuners/GAMCTuner.jl:1-7; read after a run at
+ * examples/logistic_regression/src/GAMC/simulations.jl:85-86). */
+typedef struct {
+  int64_t count;
+  int64_t updatetensorcount;
+  double step;             /* tune.totaltune.step */
+  double sqrttunestep;
+  int64_t total_accepted, total_proposed, total_totproposed;
+  double total_rate;
+  int64_t smmala_accepted, smmala_proposed, smmala_totproposed;
+  int64_t am_accepted, am_proposed, am_totproposed;
+  double smmalafrequency, amfrequency;
+  double logtarget;        /* pstate.logtarget */
+  double ratio;            /* sstate.ratio of the last transition */
+  int32_t presentupdatetensor, pastupdatetensor;
+  int32_t error_flag;      /* 0, or GAMC_NOT_POSDEF raised on device during the run */
+  int32_t error_pivot;     /* 1-based pivot index of the failed factorisation */
+  int64_t error_iteration; /* iteration count at which it was raised */
+  int64_t chain_saved;     /* number of samples currently in the device chain buffer */
+} gamc_state_scalars;
+
+/* Vectors / matrices of the state that can be copied out (gamc_get_array). */
+typedef enum {
+  GAMC_ARR_VALUE = 0,          /* pstate.value            p        */
+  GAMC_ARR_GRADLOGTARGET = 1,  /* pstate.gradlogtarget    p        */
+  GAMC_ARR_TENSORLOGTARGET = 2,/* pstate.tensorlogtarget  p x p    */
+  GAMC_ARR_LASTMEAN = 3,       /* sstate.lastmean         p        */
+  GAMC_ARR_SECONDLASTMEAN = 4, /* sstate.secondlastmean   p        */
+  GAMC_ARR_OLDINVTENSOR = 5,   /* sstate.oldinvtensor     p x p  (G^-1 after SMMALA, AM covariance after AM) */
+  GAMC_ARR_CHOLINVTENSOR = 6,  /* sstate.cholinvtensor    p x p lower (L L' = G^-1)                          */
+  GAMC_ARR_OLDFIRSTTERM = 7,   /* sstate.oldfirstterm     p        */
+  GAMC_ARR_PROPOSED_VALUE = 8  /* sstate.pstate.value     p        */
+} gamc_array_id;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------- */
+gamc_status gamc_create(gamc_handle* out, int32_t device);
+gamc_status gamc_destroy(gamc_handle h);
+const char* gamc_last_error_string(gamc_handle h);
+/* Use the caller's CUDA stream (cudaStream_t passed as void*) instead of the handle's own. */
+gamc_status gamc_set_stream(gamc_handle h, void* cuda_stream);
+gamc_status gamc_sync(gamc_handle h);
+/* "gamc_b200 <version> sm_100a" */
+const char* gamc_version(void);
+
+/* ---- target: Bayesian logistic regression -----------------------------------------------------------
+ * Replaces the user callbacks ploglikelihood / plogprior / pgradlogtarget / ptensorlogtarget of
+ * examples/logistic_regression/src/GAMC/simulations.jl:25-37 and the model data `[lambda, X, y, p]`
+ * (:39-48,69).  X is N x p column-major with leading dimension ldX >= N, y is N (0/1), lambda the prior
+ * VARIANCE.  One H2D copy; the handle keeps the device copy.  In a multi-GPU job each rank passes ITS row
+ * shard and the prior terms are added once after the all-reduce. */
+gamc_status gamc_target_logistic(gamc_handle h, const double* X, int64_t ldX, const double* y,
+                                 int64_t N, int32_t p, double lambda);
+/* Same, for data already on the device (no copy; the caller keeps the buffers alive; ldX must be even
+ * and dX 16-byte aligned for the TMA descriptor). */
+gamc_status gamc_target_logistic_device(gamc_handle h, const double* dX, int64_t ldX, const double* dy,
+                                        int64_t N, int32_t p, double lambda);
+/* Synthetic shard generated on the device: rows [row0, row0+nrows) of the global problem,
+ * X[i,j] = standardised Irwin-Hall(4) from Philox4x32-10 keyed by (seed; i, j), y ~ Bernoulli(sigma(x.theta_true)).
+ * Bit-identical to oracle/logistic.py:synth_logistic for any sharding. */
+gamc_status gamc_target_logistic_synth(gamc_handle h, uint64_t seed, int64_t row0, int64_t nrows, int32_t p,
+                                       const double* theta_true, double lambda);
+/* Copy rows [r0, r0+n) of the device-resident design matrix / labels back (n x p column-major, ld = n). */
+gamc_status gamc_target_read_rows(gamc_handle h, int64_t r0, int64_t n, double* X_out, double* y_out);
+
+/* ---- target evaluation ------------------------------------------------------------------------------
+ * Replace the Klara closures `parameter.logtarget!(pstate)` (call site src/samplers/iterate/GAMC.jl:148)
+ * and `parameter.uptotensorlogtarget!(pstate)` (:20,37; src/samplers/GAMC.jl:163,241).
+ * theta: p host doubles.  logtarget = loglikelihood + logprior; grad: p; G: p x p column-major, full
+ * symmetric.  Any output pointer may be NULL.  In a multi-GPU job every rank calls with the same theta
+ * and receives the all-reduced result. */
+gamc_status gamc_eval_logtarget(gamc_handle h, const double* theta, double* logtarget);
+gamc_status gamc_eval_upto_tensor(gamc_handle h, const double* theta, double* logtarget, double* grad, double* G);
+/* Likelihood-only partial sums of THIS rank's shard, before any all-reduce and without prior terms
+ * (what the rank contributes to the reduction): ll, g_lik[p], G_lik[p x p]. */
+gamc_status gamc_eval_partials(gamc_handle h, const double* theta, double* ll, double* g_lik, double* G_lik);
+
+/* ---- multi-GPU: observations row-sharded, one process per GPU -------------------------
+ * gamc_comm_unique_id fills a 128-byte NCCL unique id on one rank; the host side (torch.distributed /
+ * MPI / Julia Distributed) broadcasts it; every rank then calls gamc_comm_init.  After that, every
+ * target evaluation all-reduces [ll, g_lik, G_lik] (NCCL, sum, in place, on the handle's stream). */
+gamc_status gamc_comm_unique_id(uint8_t id_out[128]);
+gamc_status gamc_comm_init(gamc_handle h, const uint8_t id[128], int32_t nranks, int32_t rank);
+
+/* ---- sampler ----------------------------------------------------------------------------------------
+ * gamc_sampler_init = Klara `initialize!` + `sampler_state` for GAMC (src/samplers/GAMC.jl:157-176,202-228):
+ * evaluates target/gradient/metric at theta0, checks finiteness, factorises the metric, seeds lastmean,
+ * counters and tuner state (tuner_state, :195-200).  Calling it again is `reset!` (:234-260). */
+gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const double* theta0);
+
+/* Random tape for the next n iterations (host arrays): u_sched[n], u_mix[n], z[p x n column-major],
+ * u_acc[n].  Replaces the reference's in-line `rand(Bernoulli(.))`, `rand(proposal)`, `randn(p)`, `rand()`
+ * (src/samplers/GAMC.jl:276-334, src/samplers/iterate/GAMC.jl:35,69,146,158) with host-drawn numbers in
+ * fixed per-iteration slots.  H2D copy. */
+gamc_status gamc_tape_set(gamc_handle h, int64_t n, const double* u_sched, const double* u_mix,
+                          const double* z, const double* u_acc);
+/* Device-generated tape (Philox, throughput mode): same slots, no host traffic. */
+gamc_status gamc_tape_generate(gamc_handle h, int64_t n, uint64_t seed);
+
+/* Enqueue n `iterate!` transitions (src/samplers/iterate/GAMC.jl:1-293) reading the resident tape;
+ * asynchronous.  Samples with iteration index > burnin are appended to the device chain buffer. */
+gamc_status gamc_run(gamc_handle h, int64_t n);
+/* Copy saved samples [first, first+n) out: value is p x n column-major (`chain.value`), accept n bytes
+ * (`chain.diagnosticvalues`, examples/logistic_regression/src/GAMC/simulations.jl:81-82).  Synchronises. */
+gamc_status gamc_chain_get(gamc_handle h, int64_t first, int64_t n, double* value, uint8_t* accept);
+/* Convenience: gamc_tape_set + gamc_run + gamc_chain_get of everything saved during these n iterations
+ * (n_saved_out receives the count).  This is the host-buffer end-to-end call. */
+gamc_status gamc_iterate(gamc_handle h, int64_t n, const double* u_sched, const double* u_mix, const double* z,
+                         const double* u_acc, double* value, uint8_t* accept, int64_t* n_saved_out);
+/* Which branch each of the n tape iterations would take (1 = SMMALA, 0 = AM), from the resident tape and
+ * the current count -- the schedule coin depends only on (i, nsteps, u_sched). */
+gamc_status gamc_peek_kinds(gamc_handle h, int64_t n, uint8_t* kinds_out);
+
+gamc_status gamc_get_state(gamc_handle h, gamc_state_scalars* out);
+gamc_status gamc_get_array(gamc_handle h, int32_t array_id, double* out);
+
+/* ---- measurement hooks ------------------------------------------------------------------------------
+ * With profiling on, every kernel launched by gamc_run / gamc_eval_* is bracketed by CUDA events on the
+ * handle's stream; gamc_profile_get returns launches and summed milliseconds per kernel family. */
+typedef enum {
+  GAMC_K_LOGLIK = 0,     /* log-likelihood only data pass (AM step)              */
+  GAMC_K_LOGLIK_GRAD = 1,/* fused log-likelihood + gradient (+ weights) data pass */
+  GAMC_K_METRIC = 2,     /* X' diag(w) X on FP64 DMMA                             */
+  GAMC_K_REDUCE = 3,     /* deterministic partial reductions                      */
+  GAMC_K_LINALG = 4,     /* Cholesky / solves / proposal / MH accept kernels      */
+  GAMC_K_ALLREDUCE = 5,  /* NCCL all-reduce                                       */
+  GAMC_K_COUNT = 6
+} gamc_kernel_family;
+gamc_status gamc_profile_enable(gamc_handle h, int32_t on);
+gamc_status gamc_profile_get(gamc_handle h, int32_t family, int64_t* launches, double* total_ms);
+gamc_status gamc_profile_reset(gamc_handle h);
+/* Total kernels launched by this handle since creation (for bench.py's gpu_launches). */
+gamc_status gamc_launch_count(gamc_handle h, int64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAMC_B200_H */
