@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- GAMC (AM <-> SMMALA) throughput on the BASELINE.json workload.
+
+  python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K --warmup W   # CPU restatement of the reference, host cores
+
+Workload (BASELINE.json configs[1], "C2"): synthetic Bayesian logistic regression, N = 2^20 observations
+PER GPU, p = 256, FP64, single chain, the sampler configuration shipped with the reference's example
+(examples/logistic_regression/src/GAMC/simulations.jl:50-59: rand_exp_decay_update!(a=10), driftstep 0.02,
+minorscale 0.001, c 0.01, t0 3, AcceptanceRateMCTuner(0.35), period 100).  A "step" is one GAMC `iterate!`
+transition.  Multi-GPU: observations are row-sharded, one process per GPU, one NCCL all-reduce of
+[loglik, gradient, metric] per target evaluation; weak scaling (2^20 rows per GPU), and `value` counts
+shard-iterations per second (= iters/s x n_gpus; at 1 GPU exactly GAMC iters/s on C2).
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 20260101
+LAMBDA = 100.0
+FP64_DMMA_PEAK_TFLOPS_FALLBACK = 37.1   # profiles/r01_fp64_peak.txt (register-only DMMA.8x8x4 loop, this pool's B200)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--logN", type=int, default=20, help="log2 of rows per GPU (default 2^20 = BASELINE C2)")
+    ap.add_argument("--p", type=int, default=256)
+    ap.add_argument("--am-mode", type=int, default=int(os.environ.get("GAMC_AM_MODE", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def bench_config(gamc, nsteps, am_mode):
+    sampler = gamc.GAMC(update=gamc.rand_exp_decay_update(10.0), driftstep=0.02, minorscale=0.001, c=0.01, am_mode=am_mode)
+    tuner = gamc.GAMCTuner(gamc.VanillaMCTuner(), gamc.VanillaMCTuner(), gamc.AcceptanceRateMCTuner(0.35))
+    return sampler, tuner, gamc.BasicMCRange(nsteps=nsteps, burnin=nsteps // 5)
+
+
+def theta_inputs(p):
+    import oracle.logistic as ol   # data definition shared with the checker (host-side NumPy only)
+    tt = ol.synth_theta_true(SEED, p)
+    theta0 = tt + 0.01 * np.random.Generator(np.random.PCG64(SEED + 1)).standard_normal(p)
+    return tt, theta0
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (a NumPy restatement of the reference's Julia path; Julia itself is not in the image)
+# ----------------------------------------------------------------------------------------------------
+def cpu_iteration_costs(X, y, theta0, p, threads_note):
+    """Times real oracle `iterate!` transitions at full N on the host cores, per kind:
+    'am', 'smmala' (one tensor evaluation) and 'smmala_stale' (two: the step after an AM step re-evaluates)."""
+    import oracle as o
+    tgt = o.LogisticTarget(X, y, LAMBDA, reference_shaped=True)   # three X*theta passes, N x p temporary, full gemm
+    nst = 14
+    tuner = o.GAMCTuner(o.VanillaMCTuner(), o.VanillaMCTuner(), o.AcceptanceRateMCTuner(0.35))
+    sam = o.GAMCOracle(tgt, theta0, nst, 0, update="mod_update!", update_params=(4,), driftstep=0.02, minorscale=0.001, c=0.01, tuner=tuner)
+    tape = o.RandomTape(nst, p, seed=3)
+    costs = {"am": [], "smmala": [], "smmala_stale": []}
+    for _ in range(nst):
+        past = sam.pastupdatetensor
+        t0 = time.perf_counter()
+        sam.iterate(tape)
+        dt = time.perf_counter() - t0
+        kind = "am" if sam.last_kind == "am" else ("smmala" if past else "smmala_stale")
+        costs[kind].append(dt)
+    return {k: float(np.mean(v[1:] if len(v) > 1 else v)) for k, v in costs.items() if v}
+
+
+def compose_cpu_rate(costs, kinds):
+    """iters/s of the K-step schedule from per-kind costs (kinds: 1 = SMMALA, 0 = AM)."""
+    total, past = 0.0, False
+    for k in kinds:
+        if k:
+            total += costs["smmala"] if past else costs.get("smmala_stale", costs["smmala"])
+        else:
+            total += costs["am"]
+        past = bool(k)
+    return len(kinds) / total, total
+
+
+def host_kinds(K, seed):
+    """Branch sequence of the K-step job for the device-generated tape is only known to the GPU arm; the CPU
+    arm draws its own schedule uniforms (same distribution: exp(-10 i/K) SMMALA probability)."""
+    import oracle as o
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u = rng.random(K)
+    kinds = np.ones(K, dtype=np.uint8)
+    for i in range(4, K + 1):
+        kinds[i - 1] = u[i - 1] <= o.exp_decay(i, K, 10.0, 0.0)
+    return kinds
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle.logistic as ol
+    N, p = 1 << args.logN, args.p
+    t0 = time.perf_counter()
+    rng = np.random.Generator(np.random.PCG64(SEED))
+    # same shape and distribution as the GPU arm's synthetic data (standardised columns, Bernoulli labels);
+    # generated with NumPy's own generator here because the timing is data-independent
+    X = np.asfortranarray(rng.standard_normal((N, p)))
+    tt, theta0 = theta_inputs(p)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-(X @ tt)))).astype(np.float64)
+    gen_s = time.perf_counter() - t0
+    costs = cpu_iteration_costs(X, y, theta0, p, "")
+    kinds = host_kinds(args.steps, SEED + 2)
+    rate, total = compose_cpu_rate(costs, kinds)
+    cores = os.cpu_count()
+    sample = (f"14 real oracle iterate! transitions (mod_update! n=4) at full N=2^{args.logN}, p={p}, reference-shaped callbacks "
+              f"(3 X*theta passes, N x p temporary, full gemm), per-kind means composed over the K={args.steps}-step exp-decay schedule "
+              f"({int(kinds.sum())} SMMALA / {int(len(kinds) - kinds.sum())} AM)")
+    line = {
+        "impl": "reference", "metric": "gamc_iters_per_sec", "value": rate, "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (NumPy PCG64 N(0,1) design, Bernoulli labels)",
+        "config": {"workload": f"C2: logistic N=2^{args.logN}, p={p}, GAMC exp-decay(a=10), single chain", "rows": N, "p": p},
+        "cpu_baseline": {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample,
+                         "per_kind_seconds": costs, "datagen_s": gen_s},
+        "e2e": {"value": rate, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "Julia/Klara cannot run in this image; this is the NumPy+BLAS restatement (oracle/) on all host cores",
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gamc_b200 as g
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, p = 1 << args.logN, args.p          # rows PER GPU (weak scaling)
+    K, W = args.steps, max(args.warmup, 3)
+    tt, theta0 = theta_inputs(p)
+
+    eng = g.Engine(local)
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    eng.target_logistic_synth(SEED, rank * N, N, p, tt, LAMBDA)   # this rank's row shard, generated on the device
+    if world > 1:
+        from gamc_b200.distributed import init_comm
+        init_comm(eng, rank, world)
+
+    model = g.LogisticModel(synth={"seed": SEED, "N": N * world, "p": p, "theta_true": tt}, lam=LAMBDA)
+
+    def make_job(nsteps, tape=None):
+        sampler, tuner, rng = bench_config(g, nsteps, args.am_mode)
+        return g.BasicMCJob(model, sampler, rng, {"p": theta0}, tuner=tuner, engine=eng, tape=tape, tape_seed=SEED + 7)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: W transitions of a separate short job (both kernel families get exercised)
+    job = make_job(max(W, 8))
+    job.run()
+    # ---- timed region: tape resident on the device, K transitions, device-timed, max over ranks
+    job = make_job(K)
+    eng.tape_generate(K, SEED + 7)
+    kinds = eng.peek_kinds(K)
+    launches0 = eng.launch_count()
+    clocks = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    clocks.start()
+    e0.record(stream)
+    eng.run(K)
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    eng.sync()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    iters_per_sec = K / (ms * 1e-3)
+    st = eng.state()
+    nsave = K - K // 5
+    value, accept = eng.chain_get(0, nsave)
+    ess_min = float(np.min(g.ess(value))) if nsave >= 400 else None
+
+    # ---- per-kernel roofline: same job re-run with CUDA events around every launch (on the launching stream)
+    job = make_job(K)
+    eng.tape_generate(K, SEED + 7)
+    eng.profile_enable(True)
+    eng.profile_reset()
+    kp = min(K, 1200)
+    eng.run(kp)
+    eng.sync()
+    prof = eng.profile_get()
+    eng.profile_enable(False)
+    hbm_peak, hbm_src = measured_peaks()
+    n_ll, ms_ll = prof["loglik"]
+    n_lg, ms_lg = prof["loglik_grad"]
+    n_mt, ms_mt = prof["metric"]
+    bytes_ll = 8.0 * N * p + 8.0 * N + 8.0 * p               # X + y + theta
+    bytes_lg = 8.0 * N * p + 16.0 * N + 16.0 * p             # + weights written (8N) + gradient partials
+    flops_mt = float(N) * p * (p + 1)                        # algorithmic: lower triangle incl. diagonal, FMA = 2
+    roof_ll = {"bound": "hbm", "achieved": bytes_ll / (ms_ll / n_ll * 1e-3) * 1e-9 if n_ll else None, "peak": hbm_peak, "unit": "GB/s",
+               "traffic": None, "kernel": "k_datapass<loglik> (AM step)", "launches": n_ll, "avg_ms": ms_ll / n_ll if n_ll else None,
+               "algorithmic_bytes": bytes_ll, "peak_source": hbm_src}
+    if roof_ll["achieved"]:
+        roof_ll["frac"] = roof_ll["achieved"] / hbm_peak
+    roof_lg = {"bound": "hbm", "achieved": bytes_lg / (ms_lg / n_lg * 1e-3) * 1e-9 if n_lg else None, "peak": hbm_peak, "unit": "GB/s",
+               "kernel": "k_datapass<loglik+grad+weights> (SMMALA step)", "launches": n_lg, "avg_ms": ms_lg / n_lg if n_lg else None,
+               "algorithmic_bytes": bytes_lg}
+    if roof_lg["achieved"]:
+        roof_lg["frac"] = roof_lg["achieved"] / hbm_peak
+    peak64 = FP64_DMMA_PEAK_TFLOPS_FALLBACK
+    roof_mt = {"bound": "tensor", "achieved": flops_mt / (ms_mt / n_mt * 1e-3) * 1e-12 if n_mt else None, "peak": peak64, "unit": "TFLOP/s",
+               "kernel": "k_metric (FP64 DMMA weighted SYRK)", "launches": n_mt, "avg_ms": ms_mt / n_mt if n_mt else None,
+               "algorithmic_flops": flops_mt, "full_gemm_flops": 2.0 * N * p * p,
+               "peak_source": "measured register-only DMMA.8x8x4 loop on this pool's B200 (profiles/r01_fp64_peak.txt); cuBLAS DGEMM 8192^3 = 35.5"}
+    if roof_mt["achieved"]:
+        roof_mt["frac"] = roof_mt["achieved"] / peak64
+    share = {k: v[1] for k, v in prof.items()}
+    tot = sum(share.values()) or 1.0
+    share = {k: round(v / tot, 4) for k, v in share.items()}
+
+    # ---- e2e: the user-facing call with HOST buffers (pinned): tape H2D + K transitions + chain D2H
+    e2e = None
+    if not args.no_e2e:
+        tape = g.RandomTape(K, p, seed=SEED + 9)
+        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+        tape.u_sched, tape.u_mix, tape.u_acc, tape.z = pin(tape.u_sched), pin(tape.u_mix), pin(tape.u_acc), pin(tape.z)
+        job = make_job(K, tape=tape)
+        barrier()
+        t0 = time.perf_counter()
+        job.run()                    # gamc_tape_set (H2D) + gamc_run + sync
+        chain = job.output()         # gamc_chain_get (D2H)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * K / dt, "unit": "shard-iters/s", "iters_per_sec": K / dt, "h2d_bytes_per_step": 8 * (p + 3),
+               "d2h_bytes_per_step": (8 * p + 1) * (K - K // 5) / K, "acceptance": float(chain.diagnosticvalues.mean()),
+               "what": "BasicMCJob.run()+output(): gamc_tape_set(host pinned tape) + gamc_run + gamc_chain_get(host chain); "
+                       "the design matrix is resident (uploaded/generated once per job, as the reference passes it once at job construction)"}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only), bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Xh, yh = eng.read_rows(0, N)      # identical data: read the device-generated shard back
+        costs = cpu_iteration_costs(Xh, yh, theta0, p, "")
+        rate, _ = compose_cpu_rate(costs, kinds)
+        cpu = {"value": rate, "unit": "iters/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"14 real oracle iterate! transitions at full N=2^{args.logN}, p={p} (reference-shaped callbacks), per-kind means "
+                         f"composed over the same K={K}-step branch sequence", "per_kind_seconds": costs}
+        del Xh, yh
+
+    if rank == 0:
+        line = {
+            "metric": "gamc_iters_per_sec", "value": world * iters_per_sec, "unit": "shard-iters/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (Philox4x32-10 keyed by global row/col, generated on device)",
+            "config": {"workload": f"C2: logistic N=2^{args.logN} rows per GPU, p={p}, FP64, GAMC rand_exp_decay(a=10), single chain",
+                       "rows_per_gpu": N, "global_rows": N * world, "p": p, "parallelism": f"row-sharded x{world}, NCCL all-reduce" if world > 1 else "single GPU",
+                       "l2": "inputs (2.1 GB design matrix per pass) larger than L2; no flush needed",
+                       "value_definition": "iters/s x n_gpus (each GPU processes one 2^20-row shard of every iteration)",
+                       "am_mode": args.am_mode, "nsteps": K, "burnin": K // 5},
+            "iters_per_sec": iters_per_sec,
+            "ess_per_sec": (ess_min / (ms * 1e-3)) if ess_min else None, "ess_min": ess_min,
+            "acceptance": float(accept.mean()), "n_smmala": int(kinds.sum()), "n_am": int(K - kinds.sum()),
+            "final_step": st.step, "updatetensorcount": st.updatetensorcount,
+            "gpu_launches": int(launches),
+            "roofline": roof_ll, "roofline_grad": roof_lg, "roofline_metric": roof_mt, "kernel_time_share": share,
+            "clocks": clk, "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,892 @@
+// gamc_abi.cu -- C ABI (include/gamc_b200.h) over the sm_100a kernels.  Host-side orchestration only:
+// buffer ownership, TMA descriptors, the per-iteration launch sequence of GAMC's `iterate!`
+// (reference src/samplers/iterate/GAMC.jl:1-293), NCCL plumbing, profiling events.  No CPU arithmetic
+// on the hot path: every target evaluation and every transition runs in the kernels of datapass.cuh,
+// metric.cuh, sampler.cuh.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <set>
+#include <dlfcn.h>
+
+#include "../../include/gamc_b200.h"
+#include "common.cuh"
+#include "datapass.cuh"
+#include "metric.cuh"
+#include "metric_plan.h"
+#include "sampler.cuh"
+#include "synth.cuh"
+
+using namespace gamc;
+
+// ----------------------------------------------------------------------------------------------------
+// minimal NCCL surface, resolved lazily with dlopen so that single-GPU use needs no NCCL at all
+// ----------------------------------------------------------------------------------------------------
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef void* ncclComm_t;
+typedef int (*fn_ncclGetUniqueId)(NcclUniqueId*);
+typedef int (*fn_ncclCommInitRank)(ncclComm_t*, int, NcclUniqueId, int);
+typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef int (*fn_ncclCommDestroy)(ncclComm_t);
+typedef const char* (*fn_ncclGetErrorString)(int);
+struct NcclApi {
+  void* lib = nullptr;
+  fn_ncclGetUniqueId GetUniqueId = nullptr;
+  fn_ncclCommInitRank CommInitRank = nullptr;
+  fn_ncclAllReduce AllReduce = nullptr;
+  fn_ncclCommDestroy CommDestroy = nullptr;
+  fn_ncclGetErrorString GetErrorString = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+    GetUniqueId = (fn_ncclGetUniqueId)dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (fn_ncclCommInitRank)dlsym(lib, "ncclCommInitRank");
+    AllReduce = (fn_ncclAllReduce)dlsym(lib, "ncclAllReduce");
+    CommDestroy = (fn_ncclCommDestroy)dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (fn_ncclGetErrorString)dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl lacks required symbols"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int NCCL_DOUBLE = 8;  // ncclFloat64
+constexpr int NCCL_SUM = 0;
+
+typedef CUresult (*fn_cuTensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+fn_cuTensorMapEncodeTiled g_encode = nullptr;
+
+constexpr int PROF_POOL = 8192;
+}  // namespace
+
+struct gamc_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+
+  // target
+  long long N = 0; int p = 0; long long ld = 0; double lambda = 1.0;
+  double* dX = nullptr; double* dy = nullptr; bool own_data = false;
+  double* dw = nullptr;
+  // data-pass configuration
+  int dp_rpl = 1, dp_nu = 0, dp_grid = 0, part_g_stride = 0;
+  CUtensorMap mapXA{}, mapXB{}, mapW{};
+  double* part_ll = nullptr; double* part_g = nullptr;
+  // metric
+  MetricLayout layout; MetricPlan* d_plans = nullptr; TaskCoord* d_coords = nullptr;
+  int nkinds = 0, nsplit = 0, ntasks = 0; long long nslabs = 0; double* ws = nullptr;
+  // landing buffer of an evaluation = all-reduce payload [ll, g(p), pad, G(p x p)]
+  double* R = nullptr; int goff = 0;
+  double* theta_eval = nullptr;
+  // sampler
+  bool sampler_ready = false;
+  gamc_config cfg{}; TuneCfg tune{};
+  Bufs B{};
+  double* U = nullptr; double* vecs = nullptr; double* mats = nullptr;
+  long long h_count = 0; bool h_present = true, h_past = false;
+  // tape
+  long long tape_n = 0, tape_pos = 0, tape_cap = 0; int tape_p = 0;
+  double* d_tape = nullptr; std::vector<double> h_usched;
+  long long tape_gen_total = 0;
+  // chain
+  long long chain_cap = 0; double* d_chain = nullptr; unsigned char* d_accept = nullptr;
+  // comm
+  ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
+  // profiling
+  bool prof = false; std::vector<cudaEvent_t> ev0, ev1; std::vector<int> ev_family; int ev_used = 0;
+  long long launches = 0;
+  std::set<const void*> attr_set;   // kernels whose dynamic shared-memory limit was raised on this device
+};
+
+#define CUDA_TRY(h, call)                                                                         \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                             \
+      return GAMC_CUDA_ERROR;                                                                     \
+    }                                                                                             \
+  } while (0)
+
+// Debug aid (GAMC_DEBUG=1): synchronise and report after every launch.
+static bool g_debug = getenv("GAMC_DEBUG") != nullptr;
+#define DEBUG_POINT(h, what)                                                                      \
+  do {                                                                                            \
+    if (g_debug) {                                                                                \
+      cudaError_t e__ = cudaStreamSynchronize((h)->stream);                                       \
+      cudaError_t l__ = cudaGetLastError();                                                       \
+      if (e__ != cudaSuccess || l__ != cudaSuccess)                                               \
+        fprintf(stderr, "[gamc debug] %s: sync=%s last=%s\n", what, cudaGetErrorString(e__), cudaGetErrorString(l__)); \
+    }                                                                                             \
+  } while (0)
+
+#define REQUIRE(h, cond, status, msg)                                                             \
+  do { if (!(cond)) { (h)->err = (msg); return (status); } } while (0)
+
+namespace {
+
+struct ProfScope {
+  gamc_ctx* h; int idx = -1;
+  ProfScope(gamc_ctx* h_, int family) : h(h_) {
+    h->launches += 1;
+    if (h->prof && h->ev_used < PROF_POOL) {
+      idx = h->ev_used++;
+      h->ev_family[idx] = family;
+      cudaEventRecord(h->ev0[idx], h->stream);
+    }
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(h->ev1[idx], h->stream); }
+};
+
+gamc_status ensure_attr(gamc_ctx* h, const void* kern, size_t bytes) {
+  if (h->attr_set.count(kern)) return GAMC_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return GAMC_CUDA_ERROR; }
+  h->attr_set.insert(kern);
+  return GAMC_OK;
+}
+
+bool ensure_encode(gamc_ctx* h) {
+  if (g_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn) { h->err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  g_encode = (fn_cuTensorMapEncodeTiled)fn;
+  return true;
+}
+
+gamc_status make_map_2d(gamc_ctx* h, CUtensorMap* map, const double* base, long long N, int p, long long ld, int box_rows, int box_cols) {
+  if (!ensure_encode(h)) return GAMC_CUDA_ERROR;
+  cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)p};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled(2d) failed with code " + std::to_string((int)r); return GAMC_CUDA_ERROR; }
+  return GAMC_OK;
+}
+
+gamc_status make_map_1d(gamc_ctx* h, CUtensorMap* map, const double* base, long long N, int box) {
+  if (!ensure_encode(h)) return GAMC_CUDA_ERROR;
+  cuuint64_t dims[1] = {(cuuint64_t)N};
+  cuuint64_t strides[1] = {8};  // unused for rank 1
+  cuuint32_t bx[1] = {(cuuint32_t)box};
+  cuuint32_t es[1] = {1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 1, (void*)base, dims, strides, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled(1d) failed with code " + std::to_string((int)r); return GAMC_CUDA_ERROR; }
+  return GAMC_OK;
+}
+
+void free_target(gamc_ctx* h) {
+  if (h->own_data) { cudaFree(h->dX); cudaFree(h->dy); }
+  h->dX = h->dy = nullptr; h->own_data = false;
+  cudaFree(h->dw); h->dw = nullptr;
+  cudaFree(h->part_ll); cudaFree(h->part_g); h->part_ll = h->part_g = nullptr;
+  cudaFree(h->d_plans); cudaFree(h->d_coords); cudaFree(h->ws); h->d_plans = nullptr; h->d_coords = nullptr; h->ws = nullptr;
+  cudaFree(h->R); h->R = nullptr; cudaFree(h->theta_eval); h->theta_eval = nullptr;
+}
+
+void free_sampler(gamc_ctx* h) {
+  cudaFree(h->B.st); cudaFree(h->U); cudaFree(h->vecs); cudaFree(h->mats);
+  cudaFree(h->d_chain); cudaFree(h->d_accept);
+  h->B = Bufs{}; h->U = h->vecs = h->mats = nullptr; h->d_chain = nullptr; h->d_accept = nullptr;
+  h->sampler_ready = false;
+}
+
+// ---- data-pass dispatch -----------------------------------------------------------------------------
+template <int NU, int RPL, bool GRAD>
+gamc_status launch_dp_t(gamc_ctx* h, const double* theta) {
+  auto kern = k_datapass<NU, RPL, GRAD>;
+  { gamc_status s = ensure_attr(h, (const void*)kern, sizeof(DataPassSmem)); if (s != GAMC_OK) return s; }
+  ProfScope ps(h, GRAD ? GAMC_K_LOGLIK_GRAD : GAMC_K_LOGLIK);
+  DEBUG_POINT(h, "before datapass");
+  kern<<<h->dp_grid, DP_THREADS, sizeof(DataPassSmem), h->stream>>>(h->mapXA, h->dy, theta, h->p, h->N, h->dw, h->part_ll,
+                                                                    h->part_g, h->part_g_stride);
+  CUDA_TRY(h, cudaGetLastError());
+  DEBUG_POINT(h, "after datapass");
+  return GAMC_OK;
+}
+
+template <int RPL, bool GRAD>
+gamc_status launch_dp_nu(gamc_ctx* h, const double* theta) {
+  switch (h->dp_nu) {
+    case 1: return launch_dp_t<1, RPL, GRAD>(h, theta);
+    case 2: return launch_dp_t<2, RPL, GRAD>(h, theta);
+    case 3: return launch_dp_t<3, RPL, GRAD>(h, theta);
+    case 4: return launch_dp_t<4, RPL, GRAD>(h, theta);
+    case 5: return launch_dp_t<5, RPL, GRAD>(h, theta);
+    case 6: return launch_dp_t<6, RPL, GRAD>(h, theta);
+    case 7: return launch_dp_t<7, RPL, GRAD>(h, theta);
+    case 8: return launch_dp_t<8, RPL, GRAD>(h, theta);
+    default: h->err = "unsupported number of column units"; return GAMC_UNSUPPORTED_SHAPE;
+  }
+}
+
+gamc_status launch_datapass(gamc_ctx* h, const double* theta, bool grad) {
+  if (h->dp_rpl == 2) return grad ? launch_dp_nu<2, true>(h, theta) : launch_dp_nu<2, false>(h, theta);
+  return grad ? launch_dp_nu<1, true>(h, theta) : launch_dp_nu<1, false>(h, theta);
+}
+
+gamc_status launch_metric(gamc_ctx* h) {
+  { gamc_status s = ensure_attr(h, (const void*)k_metric, sizeof(MetricSmem)); if (s != GAMC_OK) return s; }
+  ProfScope ps(h, GAMC_K_METRIC);
+  k_metric<<<h->nkinds * h->nsplit, MT_THREADS, sizeof(MetricSmem), h->stream>>>(h->mapXB, h->mapW, h->d_plans, h->nkinds, h->nsplit,
+                                                                               h->nslabs, h->ws, h->ntasks);
+  CUDA_TRY(h, cudaGetLastError());
+  return GAMC_OK;
+}
+
+// level: 0 = ll, 1 = ll + grad, 2 = ll + grad + metric
+gamc_status launch_reduce(gamc_ctx* h, int level) {
+  ProfScope ps(h, GAMC_K_REDUCE);
+  const int nblk = (level >= 2 ? h->ntasks * 4 : 0) + 1;
+  k_reduce<<<nblk, 256, 0, h->stream>>>(h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, h->dp_grid, level >= 1,
+                                        level >= 2 ? h->ws : nullptr, h->d_coords, h->ntasks, h->nsplit);
+  CUDA_TRY(h, cudaGetLastError());
+  return GAMC_OK;
+}
+
+// Likelihood partial sums at a device-resident theta into the landing buffer R, then (multi-GPU) all-reduce.
+gamc_status eval_device(gamc_ctx* h, const double* d_theta, int level, bool allreduce) {
+  gamc_status s = launch_datapass(h, d_theta, level >= 1);
+  if (s != GAMC_OK) return s;
+  if (level >= 2) { s = launch_metric(h); if (s != GAMC_OK) return s; }
+  s = launch_reduce(h, level);
+  if (s != GAMC_OK) return s;
+  if (allreduce && h->comm) {
+    ProfScope ps(h, GAMC_K_ALLREDUCE);
+    const size_t count = level == 0 ? 1 : (level == 1 ? (size_t)(1 + h->p) : (size_t)h->goff + (size_t)h->p * h->p);
+    int r = g_nccl.AllReduce(h->R, h->R, count, NCCL_DOUBLE, NCCL_SUM, h->comm, h->stream);
+    if (r != 0) { h->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return GAMC_NCCL_ERROR; }
+  }
+  return GAMC_OK;
+}
+
+// prior terms for the standalone evaluation entry points
+__global__ void __launch_bounds__(256) k_eval_finish(double* R, int goff, const double* theta, int p, double lambda, int level) {
+  __shared__ double red[40];
+  if (level == 0) {
+    const double lp = log_prior(theta, p, lambda, red);
+    if (threadIdx.x == 0) R[0] += lp;
+  } else if (level == 1) {
+    const double lp = log_prior(theta, p, lambda, red);
+    for (int i = threadIdx.x; i < p; i += blockDim.x) R[1 + i] -= theta[i] / lambda;
+    if (threadIdx.x == 0) R[0] += lp;
+  } else {
+    const double lt = add_prior(R, goff, theta, p, lambda, red);
+    if (threadIdx.x == 0) R[0] = lt;
+  }
+}
+
+gamc_status setup_target(gamc_ctx* h) {
+  const int p = h->p;
+  REQUIRE(h, p >= 1 && p <= 512, GAMC_UNSUPPORTED_SHAPE, "p must be in 1..512");
+  REQUIRE(h, (h->ld % 2) == 0 && ((uintptr_t)h->dX % 16) == 0, GAMC_INVALID_ARG, "device X must be 16-byte aligned with an even leading dimension");
+  const char* env = getenv("GAMC_DP_RPL");
+  h->dp_rpl = (env && atoi(env) == 2 && p <= 256) ? 2 : 1;
+  const int CU = 64 / h->dp_rpl, RB = 32 * h->dp_rpl;
+  h->dp_nu = (p + CU - 1) / CU;
+  h->part_g_stride = h->dp_nu * CU;
+  const long long nrb = (h->N + RB - 1) / RB;
+  h->dp_grid = (int)std::min<long long>(nrb, h->num_sms);
+  if (h->dp_grid < 1) h->dp_grid = 1;
+  gamc_status s = make_map_2d(h, &h->mapXA, h->dX, h->N, p, h->ld, RB, CU);
+  if (s != GAMC_OK) return s;
+  s = make_map_2d(h, &h->mapXB, h->dX, h->N, p, h->ld, MT_SLAB, MT_BLK);
+  if (s != GAMC_OK) return s;
+  CUDA_TRY(h, cudaMalloc(&h->dw, sizeof(double) * (size_t)(h->N + 64)));
+  CUDA_TRY(h, cudaMemsetAsync(h->dw, 0, sizeof(double) * (size_t)(h->N + 64), h->stream));
+  s = make_map_1d(h, &h->mapW, h->dw, h->N, MT_SLAB);
+  if (s != GAMC_OK) return s;
+  CUDA_TRY(h, cudaMalloc(&h->part_ll, sizeof(double) * h->dp_grid));
+  CUDA_TRY(h, cudaMalloc(&h->part_g, sizeof(double) * (size_t)h->dp_grid * h->part_g_stride));
+  // metric layout
+  h->layout = build_metric_layout(p);
+  h->nkinds = (int)h->layout.plans.size();
+  h->ntasks = (int)h->layout.coords.size();
+  h->nslabs = (h->N + MT_SLAB - 1) / MT_SLAB;
+  h->nsplit = (int)std::max<long long>(1, std::min<long long>(h->num_sms / h->nkinds, h->nslabs));
+  CUDA_TRY(h, cudaMalloc(&h->d_plans, sizeof(MetricPlan) * h->nkinds));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_plans, h->layout.plans.data(), sizeof(MetricPlan) * h->nkinds, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMalloc(&h->d_coords, sizeof(TaskCoord) * h->ntasks));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_coords, h->layout.coords.data(), sizeof(TaskCoord) * h->ntasks, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMalloc(&h->ws, sizeof(double) * (size_t)h->nsplit * h->ntasks * MT_BLK * MT_BLK));
+  h->goff = (1 + p + 1) & ~1;  // G starts 16-byte aligned
+  CUDA_TRY(h, cudaMalloc(&h->R, sizeof(double) * ((size_t)h->goff + (size_t)p * p)));
+  CUDA_TRY(h, cudaMemsetAsync(h->R, 0, sizeof(double) * ((size_t)h->goff + (size_t)p * p), h->stream));
+  CUDA_TRY(h, cudaMalloc(&h->theta_eval, sizeof(double) * p));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GAMC_OK;
+}
+
+gamc_status check_device_error(gamc_ctx* h) {
+  if (!h->sampler_ready && !h->B.st) return GAMC_OK;
+  DevState st;
+  CUDA_TRY(h, cudaMemcpyAsync(&st, h->B.st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (st.error_flag == GAMC_NONFINITE_INIT) {
+    h->err = "Log-target, gradient or tensor of log-target not finite: initial values out of support";
+    return GAMC_NONFINITE_INIT;
+  }
+  if (st.error_flag == GAMC_NOT_POSDEF) {
+    h->err = "matrix is not positive definite; Cholesky factorization failed at pivot " + std::to_string(st.error_pivot) +
+             " (iteration " + std::to_string(st.error_iter) + ")";
+    return GAMC_NOT_POSDEF;
+  }
+  return GAMC_OK;
+}
+
+// `rand(Bernoulli(prob))` decisions of the nine schedules (src/samplers/GAMC.jl:264-337, src/stats/schedule.jl:1-7)
+bool schedule_decision(const gamc_config& c, long long i, long long tot, double u) {
+  auto par = [&](int k, double dflt) { return std::isnan(c.sched_params[k]) ? dflt : c.sched_params[k]; };
+  const double di = (double)i, dt = (double)tot;
+  switch (c.schedule) {
+    case GAMC_SCHED_AM_ONLY: return false;
+    case GAMC_SCHED_SMMALA_ONLY: return true;
+    case GAMC_SCHED_MOD: { long long n = (long long)par(0, 10.0); return n > 0 && (i % n) == 0; }
+    case GAMC_SCHED_RAND: return u <= par(0, 0.5);
+    case GAMC_SCHED_COS: { double a = par(0, 10.0), b = par(1, 0.2), cc = par(2, 0.2); return u <= b * cos(a * di * M_PI / dt) + cc; }
+    case GAMC_SCHED_RAND_EXP_DECAY: { double a = par(0, 10.0), b = par(1, 0.0); return u <= (1 - b) * exp(-a * di / dt) + b; }
+    case GAMC_SCHED_RAND_LIN_DECAY: { double a = par(0, 1e-2), b = par(1, 0.0); return u <= (1 - b) * (1 / (1 + a * di)) + b; }
+    case GAMC_SCHED_RAND_POW_DECAY: { double a = par(0, 1e-3), b = par(1, 0.0); return u <= (1 - b) * pow(a, di / dt) + b; }
+    case GAMC_SCHED_RAND_QUAD_DECAY: { double a = par(0, 1e-5), b = par(1, 0.0); return u <= (1 - b) * (1 / (1 + a * (di * di))) + b; }
+    default: return true;
+  }
+}
+
+template <typename K, typename... Args>
+gamc_status launch_step(gamc_ctx* h, K kern, Args... args) {
+  const size_t smem = step_smem_bytes(h->p);
+  ProfScope ps(h, GAMC_K_LINALG);
+  kern<<<1, LA_THREADS, smem, h->stream>>>(args...);
+  CUDA_TRY(h, cudaGetLastError());
+  return GAMC_OK;
+}
+
+gamc_status set_step_attrs(gamc_ctx* h) {
+  const int smem = (int)step_smem_bytes(512);   // sized for the largest supported p so the attribute is set once
+  const void* ks[] = {(const void*)k_sampler_init, (const void*)k_smmala_pre, (const void*)k_smmala_post, (const void*)k_am_pre, (const void*)k_am_post};
+  for (const void* k : ks) { gamc_status s = ensure_attr(h, k, smem); if (s != GAMC_OK) return s; }
+  return GAMC_OK;
+}
+
+// sstate.oldinvtensor = inv(G) of the current point, into B.C (and W = Lm^-1 into B.W)
+gamc_status launch_inverse(gamc_ctx* h, bool write_C = true) {
+  const int p = h->p;
+  {
+    ProfScope ps(h, GAMC_K_LINALG);
+    const int warps_per_block = 8;
+    k_triinv<<<(p + warps_per_block - 1) / warps_per_block, 256, 0, h->stream>>>(h->B.st, h->B.U, h->B.Ustride, h->B.rdiagU, p, h->B.W);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  if (write_C) {
+    ProfScope ps(h, GAMC_K_LINALG);
+    dim3 grid((p + 15) / 16, (p + 15) / 16);
+    k_wtw<<<grid, 256, 0, h->stream>>>(h->B.W, p, h->B.C);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  return GAMC_OK;
+}
+
+gamc_status ensure_tape(gamc_ctx* h, long long n) {
+  if (n <= h->tape_cap && h->tape_p == h->p) return GAMC_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_tape);
+  h->d_tape = nullptr; h->tape_cap = 0;
+  CUDA_TRY(h, cudaMalloc(&h->d_tape, sizeof(double) * (size_t)n * (3 + h->p)));
+  h->tape_cap = n; h->tape_p = h->p;
+  return GAMC_OK;
+}
+
+void bind_tape(gamc_ctx* h) {
+  const long long n = h->tape_cap;
+  h->B.tape_usched = h->d_tape;
+  h->B.tape_umix = h->d_tape + n;
+  h->B.tape_uacc = h->d_tape + 2 * n;
+  h->B.tape_z = h->d_tape + 3 * n;
+}
+
+}  // namespace
+
+// ====================================================================================================
+// C ABI
+// ====================================================================================================
+extern "C" {
+
+const char* gamc_version(void) { return "gamc_b200 0.1.0 sm_100a"; }
+
+gamc_status gamc_create(gamc_handle* out, int32_t device) {
+  if (!out) return GAMC_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return GAMC_CUDA_ERROR;  // no CPU fallback: fail loudly
+  if (device < 0 || device >= ndev) return GAMC_INVALID_ARG;
+  gamc_ctx* h = new gamc_ctx();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return GAMC_CUDA_ERROR; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return GAMC_CUDA_ERROR; }
+  if (prop.major != 10) { delete h; return GAMC_CUDA_ERROR; }  // sm_100a code only
+  h->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return GAMC_CUDA_ERROR; }
+  h->ev0.resize(PROF_POOL); h->ev1.resize(PROF_POOL); h->ev_family.resize(PROF_POOL);
+  *out = h;
+  return GAMC_OK;
+}
+
+gamc_status gamc_destroy(gamc_handle h) {
+  if (!h) return GAMC_INVALID_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  free_sampler(h);
+  free_target(h);
+  cudaFree(h->d_tape);
+  if (h->prof || h->ev_used) for (int i = 0; i < PROF_POOL; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return GAMC_OK;
+}
+
+const char* gamc_last_error_string(gamc_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+gamc_status gamc_set_stream(gamc_handle h, void* cuda_stream) {
+  if (!h) return GAMC_INVALID_ARG;
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)cuda_stream;
+  h->own_stream = false;
+  return GAMC_OK;
+}
+
+gamc_status gamc_sync(gamc_handle h) {
+  if (!h) return GAMC_INVALID_ARG;
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->B.st) return check_device_error(h);
+  return GAMC_OK;
+}
+
+// ---- targets ----------------------------------------------------------------------------------------
+gamc_status gamc_target_logistic(gamc_handle h, const double* X, int64_t ldX, const double* y, int64_t N, int32_t p, double lambda) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, X && y && N >= 1 && p >= 1 && ldX >= N && lambda > 0, GAMC_INVALID_ARG, "gamc_target_logistic: bad argument");
+  REQUIRE(h, p <= 512, GAMC_UNSUPPORTED_SHAPE, "p must be in 1..512");
+  cudaSetDevice(h->device);
+  free_sampler(h); free_target(h);
+  h->N = N; h->p = p; h->lambda = lambda;
+  h->ld = (N + 15) & ~15LL;   // re-pitched: 128-byte aligned columns
+  CUDA_TRY(h, cudaMalloc(&h->dX, sizeof(double) * (size_t)h->ld * p));
+  CUDA_TRY(h, cudaMalloc(&h->dy, sizeof(double) * (size_t)h->ld));
+  h->own_data = true;
+  CUDA_TRY(h, cudaMemcpy2DAsync(h->dX, sizeof(double) * h->ld, X, sizeof(double) * ldX, sizeof(double) * N, p, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->dy, y, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
+  return setup_target(h);
+}
+
+gamc_status gamc_target_logistic_device(gamc_handle h, const double* dX, int64_t ldX, const double* dy, int64_t N, int32_t p, double lambda) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, dX && dy && N >= 1 && p >= 1 && ldX >= N && lambda > 0, GAMC_INVALID_ARG, "gamc_target_logistic_device: bad argument");
+  cudaSetDevice(h->device);
+  free_sampler(h); free_target(h);
+  h->N = N; h->p = p; h->lambda = lambda; h->ld = ldX;
+  h->dX = const_cast<double*>(dX); h->dy = const_cast<double*>(dy); h->own_data = false;
+  return setup_target(h);
+}
+
+gamc_status gamc_target_logistic_synth(gamc_handle h, uint64_t seed, int64_t row0, int64_t nrows, int32_t p, const double* theta_true, double lambda) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, theta_true && nrows >= 1 && row0 >= 0 && p >= 1 && lambda > 0, GAMC_INVALID_ARG, "gamc_target_logistic_synth: bad argument");
+  REQUIRE(h, p <= 512, GAMC_UNSUPPORTED_SHAPE, "p must be in 1..512");
+  cudaSetDevice(h->device);
+  free_sampler(h); free_target(h);
+  h->N = nrows; h->p = p; h->lambda = lambda;
+  h->ld = (nrows + 15) & ~15LL;
+  CUDA_TRY(h, cudaMalloc(&h->dX, sizeof(double) * (size_t)h->ld * p));
+  CUDA_TRY(h, cudaMalloc(&h->dy, sizeof(double) * (size_t)h->ld));
+  h->own_data = true;
+  double* d_tt = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d_tt, sizeof(double) * p));
+  CUDA_TRY(h, cudaMemcpyAsync(d_tt, theta_true, sizeof(double) * p, cudaMemcpyHostToDevice, h->stream));
+  {
+    dim3 grid((unsigned)((nrows + 255) / 256), (unsigned)std::min(p, 64));
+    k_synth_X<<<grid, 256, 0, h->stream>>>(h->dX, h->ld, row0, nrows, p, seed);
+    CUDA_TRY(h, cudaGetLastError());
+    k_synth_y<<<(unsigned)((nrows + 255) / 256), 256, 0, h->stream>>>(h->dX, h->ld, row0, nrows, p, d_tt, seed, h->dy);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 2;
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_tt);
+  return setup_target(h);
+}
+
+gamc_status gamc_target_read_rows(gamc_handle h, int64_t r0, int64_t n, double* X_out, double* y_out) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->dX, GAMC_NOT_READY, "no target");
+  REQUIRE(h, r0 >= 0 && n >= 1 && r0 + n <= h->N, GAMC_INVALID_ARG, "row range out of bounds");
+  cudaSetDevice(h->device);
+  if (X_out) CUDA_TRY(h, cudaMemcpy2DAsync(X_out, sizeof(double) * n, h->dX + r0, sizeof(double) * h->ld, sizeof(double) * n, h->p, cudaMemcpyDeviceToHost, h->stream));
+  if (y_out) CUDA_TRY(h, cudaMemcpyAsync(y_out, h->dy + r0, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GAMC_OK;
+}
+
+// ---- evaluation -------------------------------------------------------------------------------------
+static gamc_status eval_host(gamc_handle h, const double* theta, int level, bool reduce_and_prior, double* lt, double* grad, double* G) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->dX, GAMC_NOT_READY, "no target: call gamc_target_* first");
+  REQUIRE(h, theta, GAMC_INVALID_ARG, "theta is null");
+  cudaSetDevice(h->device);
+  const int p = h->p;
+  CUDA_TRY(h, cudaMemcpyAsync(h->theta_eval, theta, sizeof(double) * p, cudaMemcpyHostToDevice, h->stream));
+  gamc_status s = eval_device(h, h->theta_eval, level, reduce_and_prior);
+  if (s != GAMC_OK) return s;
+  if (reduce_and_prior) {
+    ProfScope ps(h, GAMC_K_LINALG);
+    k_eval_finish<<<1, 256, 0, h->stream>>>(h->R, h->goff, h->theta_eval, p, h->lambda, level);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  if (lt) CUDA_TRY(h, cudaMemcpyAsync(lt, h->R, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (grad && level >= 1) CUDA_TRY(h, cudaMemcpyAsync(grad, h->R + 1, sizeof(double) * p, cudaMemcpyDeviceToHost, h->stream));
+  if (G && level >= 2) CUDA_TRY(h, cudaMemcpyAsync(G, h->R + h->goff, sizeof(double) * (size_t)p * p, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GAMC_OK;
+}
+
+gamc_status gamc_eval_logtarget(gamc_handle h, const double* theta, double* logtarget) {
+  return eval_host(h, theta, 0, true, logtarget, nullptr, nullptr);
+}
+gamc_status gamc_eval_upto_tensor(gamc_handle h, const double* theta, double* logtarget, double* grad, double* G) {
+  return eval_host(h, theta, 2, true, logtarget, grad, G);
+}
+gamc_status gamc_eval_partials(gamc_handle h, const double* theta, double* ll, double* g_lik, double* G_lik) {
+  return eval_host(h, theta, G_lik ? 2 : (g_lik ? 1 : 0), false, ll, g_lik, G_lik);
+}
+
+// ---- communicator -----------------------------------------------------------------------------------
+gamc_status gamc_comm_unique_id(uint8_t id_out[128]) {
+  std::string err;
+  if (!id_out || !g_nccl.load(err)) return GAMC_NCCL_ERROR;
+  NcclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return GAMC_NCCL_ERROR;
+  memcpy(id_out, id.internal, 128);
+  return GAMC_OK;
+}
+
+gamc_status gamc_comm_init(gamc_handle h, const uint8_t id[128], int32_t nranks, int32_t rank) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, id && nranks >= 1 && rank >= 0 && rank < nranks, GAMC_INVALID_ARG, "gamc_comm_init: bad argument");
+  if (!g_nccl.load(h->err)) return GAMC_NCCL_ERROR;
+  cudaSetDevice(h->device);
+  NcclUniqueId uid;
+  memcpy(uid.internal, id, 128);
+  int r = g_nccl.CommInitRank(&h->comm, nranks, uid, rank);
+  if (r != 0) { h->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); h->comm = nullptr; return GAMC_NCCL_ERROR; }
+  h->nranks = nranks; h->rank = rank;
+  return GAMC_OK;
+}
+
+// ---- sampler ----------------------------------------------------------------------------------------
+gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const double* theta0) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->dX, GAMC_NOT_READY, "no target: call gamc_target_* first");
+  REQUIRE(h, cfg && theta0, GAMC_INVALID_ARG, "null argument");
+  // GAMC inner constructor asserts (src/samplers/GAMC.jl:135-138)
+  REQUIRE(h, cfg->driftstep > 0, GAMC_INVALID_ARG, "Drift step is not positive");
+  REQUIRE(h, cfg->minorscale > 0, GAMC_INVALID_ARG, "Constant minorscale must be positive");
+  REQUIRE(h, cfg->c >= 0, GAMC_INVALID_ARG, "Constant c must be non-negative");
+  REQUIRE(h, cfg->t0 > 0, GAMC_INVALID_ARG, "t0 is not positive");
+  REQUIRE(h, cfg->schedule >= 0 && cfg->schedule <= GAMC_SCHED_RAND_QUAD_DECAY, GAMC_INVALID_ARG, "unknown schedule");
+  REQUIRE(h, cfg->period >= 1 && cfg->nsteps >= 1 && cfg->burnin >= 0, GAMC_INVALID_ARG, "bad period / nsteps / burnin");
+  REQUIRE(h, cfg->am_mode == 0 || cfg->am_mode == 1, GAMC_INVALID_ARG, "am_mode must be 0 or 1");
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  DEBUG_POINT(h, "sampler_init entry");
+  free_sampler(h);
+  DEBUG_POINT(h, "sampler_init after free_sampler");
+  const int p = h->p;
+  h->cfg = *cfg;
+  TuneCfg& T = h->tune;
+  T = TuneCfg{};
+  T.is_accrate = cfg->total_tuner_kind == 1;
+  const bool tuner_verbose = cfg->verbose_total || cfg->verbose_smmala || cfg->verbose_am;   // GAMCTuner.jl:22-23
+  T.tuning = tuner_verbose || T.is_accrate;
+  T.count_total = cfg->verbose_total || T.is_accrate;
+  T.verbose_sm = cfg->verbose_smmala; T.verbose_am = cfg->verbose_am;
+  T.period = cfg->period; T.burnin = cfg->burnin;
+  T.targetrate = cfg->targetrate; T.score_k = cfg->score_k;
+  T.minorscale = cfg->minorscale; T.sqrtminorscale = sqrt(cfg->minorscale); T.c = cfg->c;
+  T.lambda = h->lambda; T.p = p; T.am_mode = cfg->am_mode;
+
+  Bufs& B = h->B;
+  B = Bufs{};
+  CUDA_TRY(h, cudaMalloc(&B.st, sizeof(DevState)));
+  const size_t pp = (size_t)p * p;
+  CUDA_TRY(h, cudaMalloc(&h->mats, sizeof(double) * pp * 7));
+  CUDA_TRY(h, cudaMemsetAsync(h->mats, 0, sizeof(double) * pp * 7, h->stream));
+  B.Gs = h->mats; B.Gstride = pp;
+  B.U = h->mats + 2 * pp; B.Ustride = pp;
+  B.C = h->mats + 4 * pp; B.Lc = h->mats + 5 * pp; B.W = h->mats + 6 * pp;
+  CUDA_TRY(h, cudaMalloc(&h->vecs, sizeof(double) * (size_t)p * 12));
+  CUDA_TRY(h, cudaMemsetAsync(h->vecs, 0, sizeof(double) * (size_t)p * 12, h->stream));
+  double* v = h->vecs;
+  B.gs = v; v += 2 * p; B.rdiagU = v; v += 2 * p; B.fterm = v; v += 2 * p;
+  B.theta = v; v += p; B.theta_prop = v; v += p; B.mu = v; v += p; B.lastmean = v; v += p; B.secondlastmean = v; v += p; B.rdiagL = v;
+  B.R = h->R; B.goff = h->goff;
+  h->chain_cap = std::max<long long>(0, cfg->nsteps - cfg->burnin);
+  if (h->chain_cap > 0) {
+    CUDA_TRY(h, cudaMalloc(&h->d_chain, sizeof(double) * (size_t)h->chain_cap * p));
+    CUDA_TRY(h, cudaMalloc(&h->d_accept, (size_t)h->chain_cap));
+  }
+  B.chain_value = h->d_chain; B.chain_accept = h->d_accept; B.chain_cap = h->chain_cap;
+  if (h->d_tape && h->tape_p == p) bind_tape(h);
+
+  // tuner_state (src/samplers/GAMC.jl:195-200): BasicMCTune(step, 0, 0, period) seeds totproposed with the period
+  DevState st{};
+  st.step = cfg->driftstep; st.sqrtstep = sqrt(cfg->driftstep);
+  st.tot_totprop = cfg->period; st.sm_totprop = cfg->period; st.am_totprop = cfg->period;
+  st.tot_rate = st.sm_rate = st.am_rate = NAN; st.smfreq = st.amfreq = NAN; st.ratio = NAN;
+  CUDA_TRY(h, cudaMemcpyAsync(B.st, &st, sizeof(DevState), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(B.theta, theta0, sizeof(double) * p, cudaMemcpyHostToDevice, h->stream));
+  DEBUG_POINT(h, "sampler_init after allocs");
+  gamc_status s = set_step_attrs(h);
+  if (s != GAMC_OK) return s;
+  DEBUG_POINT(h, "sampler_init after attrs");
+  // initialize! (:157-176): first evaluation of target + gradient + metric at theta0
+  s = eval_device(h, B.theta, 2, true);
+  if (s != GAMC_OK) return s;
+  s = launch_step(h, k_sampler_init, B, T);
+  if (s != GAMC_OK) return s;
+  h->h_count = 0; h->h_present = true; h->h_past = false;   // MuvGAMCState outer ctor (:117-118)
+  h->tape_n = 0; h->tape_pos = 0;
+  h->sampler_ready = true;
+  return check_device_error(h);
+}
+
+gamc_status gamc_tape_set(gamc_handle h, int64_t n, const double* u_sched, const double* u_mix, const double* z, const double* u_acc) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->dX, GAMC_NOT_READY, "no target");
+  REQUIRE(h, n >= 1 && u_sched && u_mix && z && u_acc, GAMC_INVALID_ARG, "gamc_tape_set: bad argument");
+  cudaSetDevice(h->device);
+  gamc_status s = ensure_tape(h, n);
+  if (s != GAMC_OK) return s;
+  bind_tape(h);
+  const long long cap = h->tape_cap;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_tape, u_sched, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_tape + cap, u_mix, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_tape + 2 * cap, u_acc, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_tape + 3 * cap, z, sizeof(double) * (size_t)n * h->p, cudaMemcpyHostToDevice, h->stream));
+  h->h_usched.assign(u_sched, u_sched + n);
+  h->tape_n = n; h->tape_pos = 0;
+  return GAMC_OK;
+}
+
+gamc_status gamc_tape_generate(gamc_handle h, int64_t n, uint64_t seed) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->dX, GAMC_NOT_READY, "no target");
+  REQUIRE(h, n >= 1, GAMC_INVALID_ARG, "gamc_tape_generate: n < 1");
+  cudaSetDevice(h->device);
+  gamc_status s = ensure_tape(h, n);
+  if (s != GAMC_OK) return s;
+  bind_tape(h);
+  const long long cap = h->tape_cap;
+  const int pairs = (h->p + 1) / 2;
+  const long long total = n * (long long)(pairs + 1);
+  k_tape_generate<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(n, h->p, seed, h->tape_gen_total, h->d_tape, h->d_tape + cap,
+                                                                       h->d_tape + 2 * cap, h->d_tape + 3 * cap);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
+  h->tape_gen_total += n;
+  h->h_usched.resize(n);
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_usched.data(), h->d_tape, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->tape_n = n; h->tape_pos = 0;
+  return GAMC_OK;
+}
+
+gamc_status gamc_peek_kinds(gamc_handle h, int64_t n, uint8_t* kinds_out) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->sampler_ready, GAMC_NOT_READY, "sampler not initialised");
+  REQUIRE(h, kinds_out && n >= 0 && h->tape_pos + n <= h->tape_n, GAMC_INVALID_ARG, "gamc_peek_kinds: tape too short");
+  bool present = h->h_present;
+  for (long long k = 0; k < n; ++k) {
+    const long long t = h->h_count + k + 1;
+    if (t > h->cfg.t0) present = schedule_decision(h->cfg, t, h->cfg.nsteps, h->h_usched[h->tape_pos + k]);
+    kinds_out[k] = present ? 1 : 0;
+  }
+  return GAMC_OK;
+}
+
+gamc_status gamc_run(gamc_handle h, int64_t n) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->sampler_ready, GAMC_NOT_READY, "sampler not initialised");
+  REQUIRE(h, n >= 0 && h->tape_pos + n <= h->tape_n, GAMC_NOT_READY, "random tape exhausted: call gamc_tape_set / gamc_tape_generate");
+  cudaSetDevice(h->device);
+  Bufs& B = h->B;
+  const TuneCfg& T = h->tune;
+  gamc_status s;
+  for (long long k = 0; k < n; ++k) {
+    const long long t = ++h->h_count;                                                    // iterate/GAMC.jl:2
+    const long long ti = h->tape_pos++;
+    if (t > h->cfg.t0) h->h_present = schedule_decision(h->cfg, t, h->cfg.nsteps, h->h_usched[ti]);   // :8-10
+    if (h->h_present) {                                                                  // :12
+      const int refactor = h->h_past ? 0 : 1;
+      if (refactor) { s = eval_device(h, B.theta, 2, true); if (s != GAMC_OK) return s; }  // :20
+      s = launch_step(h, k_smmala_pre, B, T, ti, refactor); if (s != GAMC_OK) return s;
+      s = eval_device(h, B.theta_prop, 2, true); if (s != GAMC_OK) return s;             // :37
+      s = launch_step(h, k_smmala_post, B, T, ti); if (s != GAMC_OK) return s;
+    } else {                                                                             // :128
+      if (h->h_past) { s = launch_inverse(h); if (s != GAMC_OK) return s; }              // oldinvtensor = inv(G) seeds the recursion
+      s = launch_step(h, k_am_pre, B, T, ti); if (s != GAMC_OK) return s;
+      s = eval_device(h, B.theta_prop, 0, true); if (s != GAMC_OK) return s;             // :148
+      s = launch_step(h, k_am_post, B, T, ti); if (s != GAMC_OK) return s;
+    }
+    h->h_past = h->h_present;                                                            // :197
+  }
+  return GAMC_OK;
+}
+
+gamc_status gamc_chain_get(gamc_handle h, int64_t first, int64_t n, double* value, uint8_t* accept) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->sampler_ready, GAMC_NOT_READY, "sampler not initialised");
+  cudaSetDevice(h->device);
+  gamc_status s = check_device_error(h);   // synchronises
+  if (s != GAMC_OK) return s;
+  REQUIRE(h, first >= 0 && n >= 0 && first + n <= h->chain_cap, GAMC_INVALID_ARG, "chain range out of bounds");
+  if (n == 0) return GAMC_OK;
+  if (value) CUDA_TRY(h, cudaMemcpyAsync(value, h->d_chain + (size_t)first * h->p, sizeof(double) * (size_t)n * h->p, cudaMemcpyDeviceToHost, h->stream));
+  if (accept) CUDA_TRY(h, cudaMemcpyAsync(accept, h->d_accept + first, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GAMC_OK;
+}
+
+gamc_status gamc_iterate(gamc_handle h, int64_t n, const double* u_sched, const double* u_mix, const double* z, const double* u_acc,
+                         double* value, uint8_t* accept, int64_t* n_saved_out) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->sampler_ready, GAMC_NOT_READY, "sampler not initialised");
+  gamc_status s = gamc_tape_set(h, n, u_sched, u_mix, z, u_acc);
+  if (s != GAMC_OK) return s;
+  const long long before = std::max<long long>(0, std::min<long long>(h->h_count - h->cfg.burnin, h->chain_cap));
+  s = gamc_run(h, n);
+  if (s != GAMC_OK) return s;
+  const long long after = std::max<long long>(0, std::min<long long>(h->h_count - h->cfg.burnin, h->chain_cap));
+  s = gamc_chain_get(h, before, after - before, value, accept);
+  if (n_saved_out) *n_saved_out = after - before;
+  return s;
+}
+
+gamc_status gamc_get_state(gamc_handle h, gamc_state_scalars* out) {
+  if (!h || !out) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->B.st, GAMC_NOT_READY, "sampler not initialised");
+  cudaSetDevice(h->device);
+  DevState st;
+  CUDA_TRY(h, cudaMemcpyAsync(&st, h->B.st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  out->count = st.count; out->updatetensorcount = st.updatetensorcount;
+  out->step = st.step; out->sqrttunestep = st.sqrtstep;
+  out->total_accepted = st.tot_acc; out->total_proposed = st.tot_prop; out->total_totproposed = st.tot_totprop; out->total_rate = st.tot_rate;
+  out->smmala_accepted = st.sm_acc; out->smmala_proposed = st.sm_prop; out->smmala_totproposed = st.sm_totprop;
+  out->am_accepted = st.am_acc; out->am_proposed = st.am_prop; out->am_totproposed = st.am_totprop;
+  out->smmalafrequency = st.smfreq; out->amfrequency = st.amfreq;
+  out->logtarget = st.logtarget; out->ratio = st.ratio;
+  out->presentupdatetensor = h->h_present; out->pastupdatetensor = h->h_past;
+  out->error_flag = st.error_flag; out->error_pivot = st.error_pivot; out->error_iteration = st.error_iter;
+  out->chain_saved = st.chain_saved;
+  return GAMC_OK;
+}
+
+gamc_status gamc_get_array(gamc_handle h, int32_t array_id, double* out) {
+  if (!h || !out) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->sampler_ready, GAMC_NOT_READY, "sampler not initialised");
+  cudaSetDevice(h->device);
+  const int p = h->p; const size_t pp = (size_t)p * p;
+  Bufs& B = h->B;
+  DevState st;
+  CUDA_TRY(h, cudaMemcpyAsync(&st, B.st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  const int cur = st.cur;
+  const double* src = nullptr; size_t n = p;
+  switch (array_id) {
+    case GAMC_ARR_VALUE: src = B.theta; break;
+    case GAMC_ARR_GRADLOGTARGET: src = B.gs + (size_t)cur * p; break;
+    case GAMC_ARR_TENSORLOGTARGET: src = B.Gs + (size_t)cur * pp; n = pp; break;
+    case GAMC_ARR_LASTMEAN: src = B.lastmean; break;
+    case GAMC_ARR_SECONDLASTMEAN: src = B.secondlastmean; break;
+    case GAMC_ARR_OLDFIRSTTERM: src = B.fterm + (size_t)cur * p; break;
+    case GAMC_ARR_PROPOSED_VALUE: src = B.theta_prop; break;
+    case GAMC_ARR_OLDINVTENSOR:
+      if (h->h_past || h->h_count == 0) { gamc_status s = launch_inverse(h); if (s != GAMC_OK) return s; }
+      src = B.C; n = pp; break;
+    case GAMC_ARR_CHOLINVTENSOR: {
+      // L = U^-T: L(a,b) = W(p-1-b, p-1-a) with W = Lm^-1 (M space); data movement only on the host
+      gamc_status s = launch_inverse(h, false); if (s != GAMC_OK) return s;
+      std::vector<double> W(pp);
+      CUDA_TRY(h, cudaMemcpyAsync(W.data(), B.W, sizeof(double) * pp, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      for (int b = 0; b < p; ++b) for (int a = 0; a < p; ++a) out[a + (size_t)b * p] = (a >= b) ? W[(size_t)(p - 1 - b) + (size_t)(p - 1 - a) * p] : 0.0;
+      return GAMC_OK;
+    }
+    default: h->err = "unknown array id"; return GAMC_INVALID_ARG;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(out, src, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GAMC_OK;
+}
+
+// ---- measurement ------------------------------------------------------------------------------------
+gamc_status gamc_profile_enable(gamc_handle h, int32_t on) {
+  if (!h) return GAMC_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (on && !h->ev0[0]) {
+    for (int i = 0; i < PROF_POOL; ++i) { CUDA_TRY(h, cudaEventCreate(&h->ev0[i])); CUDA_TRY(h, cudaEventCreate(&h->ev1[i])); }
+  }
+  h->prof = on != 0;
+  return GAMC_OK;
+}
+
+gamc_status gamc_profile_reset(gamc_handle h) {
+  if (!h) return GAMC_INVALID_ARG;
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->ev_used = 0;
+  return GAMC_OK;
+}
+
+gamc_status gamc_profile_get(gamc_handle h, int32_t family, int64_t* launches, double* total_ms) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, family >= 0 && family < GAMC_K_COUNT, GAMC_INVALID_ARG, "bad kernel family");
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  long long cnt = 0; double ms = 0.0;
+  for (int i = 0; i < h->ev_used; ++i) {
+    if (h->ev_family[i] != family) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, h->ev0[i], h->ev1[i]) == cudaSuccess) { ms += t; cnt += 1; }
+  }
+  if (launches) *launches = cnt;
+  if (total_ms) *total_ms = ms;
+  return GAMC_OK;
+}
+
+gamc_status gamc_launch_count(gamc_handle h, int64_t* out) {
+  if (!h || !out) return GAMC_INVALID_ARG;
+  *out = h->launches;
+  return GAMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+// metric.cuh -- Kernel B: Fisher metric partials  G_lik = X' diag(w) X  on the FP64 tensor cores.
+//
+// Replaces `broadcast(*, r.*(1-r), X)' * X` of examples/logistic_regression/src/GAMC/simulations.jl:36
+// (an N x p temporary followed by a full, symmetry-unaware dgemm) by a weighted SYRK that only forms the
+// lower triangle, in 32 x 32 "tasks" (column block bi x column block bj, bi >= bj), one task per warp,
+// 4 x 4 DMMA.8x8x4 accumulator tiles per task held in registers for the whole K (row) range of the CTA.
+//
+// Operand layout: the K dimension of the contraction is the observation index i, which is the
+// CONTIGUOUS dimension of column-major X, so both MMA operands (A = X' "row-major", B = X "col-major")
+// are read straight out of the same shared-memory slab: a TMA box of 36 rows x 32 columns per column
+// block.  36 (= 4 mod 16 in units of 8-byte bank pairs) makes the fragment loads -- 8 columns x 4 rows
+// per half-warp -- conflict-free without swizzling; rows beyond N are zero-filled by TMA.
+// Work split: grid = nkinds x nsplit CTAs; a "kind" owns up to 12 tasks and the <= MAXS column blocks they
+// touch (plan built on the host, metric_plan.h); split s processes row slabs s, s+nsplit, ...; partial
+// tiles go to a workspace and are summed in fixed split order by k_reduce (deterministic).
+// Compute-bound: algorithmic flops = N p (p+1); the 8x8 tiles above the diagonal of diagonal tasks are skipped.
+#pragma once
+#include "common.cuh"
+
+namespace gamc {
+
+constexpr int MT_SLAB = 36;                  // rows per slab (K-extent per stage)
+constexpr int MT_BLK = 32;                   // columns per block
+constexpr int MT_MAXS = 8;                   // max column blocks resident per CTA
+constexpr int MT_MAXT = 12;                  // tasks (consumer warps) per CTA
+constexpr int MT_THREADS = (MT_MAXT + 1) * 32;
+constexpr int MT_NSTAGE = 3;
+constexpr int MT_SLOT_DOUBLES = MT_SLAB * MT_BLK;  // 1152 doubles = 9216 B
+
+struct MetricPlan {
+  int nslots;
+  int ntasks;
+  int slot_block[MT_MAXS];
+  int task_sa[MT_MAXT];   // slot holding column block bi (rows of the output task)
+  int task_sb[MT_MAXT];   // slot holding column block bj (columns of the output task)
+  int task_id[MT_MAXT];   // global task index (position in the workspace)
+  int task_diag[MT_MAXT];
+};
+
+struct MetricSmem {
+  alignas(128) double slab[MT_NSTAGE][MT_MAXS][MT_SLOT_DOUBLES];
+  alignas(128) double w[MT_NSTAGE][48];
+  alignas(8) uint64_t full_bar[MT_NSTAGE];
+  alignas(8) uint64_t empty_bar[MT_NSTAGE];
+  MetricPlan plan;
+};
+
+template <bool DIAG>
+__device__ __forceinline__ void metric_slab(const double* __restrict__ A, const double* __restrict__ B,
+                                            const double* __restrict__ wv, int lane, double (&acc)[4][4][2]) {
+  const int g = lane >> 2, c = lane & 3;
+  const double* ap = A + g * MT_SLAB + c;
+  const double* bp = B + g * MT_SLAB + c;
+#pragma unroll
+  for (int k4 = 0; k4 < MT_SLAB / 4; ++k4) {
+    const double wk = wv[k4 * 4 + c];
+    double a[4], b[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      a[t] = ap[t * 8 * MT_SLAB + k4 * 4] * wk;
+      b[t] = bp[t * 8 * MT_SLAB + k4 * 4];
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        if (!DIAG || mt >= nt) dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+  }
+}
+
+__global__ void __launch_bounds__(MT_THREADS, 1)
+k_metric(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+         const MetricPlan* __restrict__ plans, int nkinds, int nsplit, long long nslabs,
+         double* __restrict__ ws, int ntasks_total) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MetricSmem& S = *reinterpret_cast<MetricSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kind = blockIdx.x % nkinds, split = blockIdx.x / nkinds;
+
+  {
+    const int* src = reinterpret_cast<const int*>(&plans[kind]);
+    int* dst = reinterpret_cast<int*>(&S.plan);
+    for (int i = tid; i < (int)(sizeof(MetricPlan) / sizeof(int)); i += MT_THREADS) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    const int nt = plans[kind].ntasks;   // only warps that own a task take part in the empty-barrier protocol
+    for (int s = 0; s < MT_NSTAGE; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], nt); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int nslots = S.plan.nslots, ntasks = S.plan.ntasks;
+
+  if (warp == MT_MAXT) {
+    if (lane == 0) {
+      tma_prefetch_desc(&mapX);
+      tma_prefetch_desc(&mapW);
+      unsigned it = 0;
+      for (long long slab = split; slab < nslabs; slab += nsplit, ++it) {
+        const unsigned st = it % MT_NSTAGE, round = it / MT_NSTAGE;
+        mbar_wait(&S.empty_bar[st], (round & 1) ^ 1);
+        mbar_arrive_expect_tx(&S.full_bar[st], (uint32_t)(nslots * MT_SLOT_DOUBLES * 8 + MT_SLAB * 8));
+        for (int s = 0; s < nslots; ++s)
+          tma_load_2d(S.slab[st][s], &mapX, &S.full_bar[st], (int)(slab * MT_SLAB), S.plan.slot_block[s] * MT_BLK);
+        tma_load_1d(S.w[st], &mapW, &S.full_bar[st], (int)(slab * MT_SLAB));
+      }
+    }
+    return;
+  }
+
+  // consumer warps (one task each); surplus warps of a partially filled kind retire
+  if (warp >= ntasks) return;
+  const int sa = S.plan.task_sa[warp], sb = S.plan.task_sb[warp];
+  const bool diag = S.plan.task_diag[warp] != 0;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  unsigned it = 0;
+  for (long long slab = split; slab < nslabs; slab += nsplit, ++it) {
+    const unsigned st = it % MT_NSTAGE, round = it / MT_NSTAGE;
+    mbar_wait(&S.full_bar[st], round & 1);
+    if (diag) metric_slab<true>(S.slab[st][sa], S.slab[st][sb], S.w[st], lane, acc);
+    else      metric_slab<false>(S.slab[st][sa], S.slab[st][sb], S.w[st], lane, acc);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.empty_bar[st]);
+  }
+
+  {
+    // partial tile -> workspace [split][task][32 x 32 row-major]
+    double* out = ws + ((size_t)split * ntasks_total + S.plan.task_id[warp]) * (MT_BLK * MT_BLK);
+    const int g = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        double2 v = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        *reinterpret_cast<double2*>(&out[(mt * 8 + g) * MT_BLK + nt * 8 + 2 * c]) = v;
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_reduce: deterministic second stage.  Sums per-CTA log-likelihood / gradient partials of Kernel A and
+// the per-split metric tiles of Kernel B in a fixed order into the packed evaluation buffer
+//   E = [ ll, g(0..p-1), pad, G(p x p column-major, both triangles written, exactly symmetric) ]
+// (the "landing buffer"), which is also the all-reduce payload in multi-GPU jobs.
+// ---------------------------------------------------------------------------------------------------
+struct TaskCoord { int bi, bj; };
+
+__global__ void __launch_bounds__(256)
+k_reduce(double* __restrict__ E, int p, int goff,
+         const double* __restrict__ part_ll, const double* __restrict__ part_g, int part_g_stride, int nparts,
+         int want_grad, const double* __restrict__ ws, const TaskCoord* __restrict__ coords, int ntasks, int nsplit) {
+  const int nblk_tensor = ws ? ntasks * 4 : 0;  // 256 threads per block, 1024 elements per task
+  if ((int)blockIdx.x < nblk_tensor) {
+    const int task = blockIdx.x >> 2;
+    const int e = ((blockIdx.x & 3) << 8) + threadIdx.x;   // element within the 32x32 tile, row-major
+    const int r = e >> 5, c = e & 31;
+    const int bi = coords[task].bi, bj = coords[task].bj;
+    if (bi == bj && r < c) return;
+    const int gi = bi * MT_BLK + r, gj = bj * MT_BLK + c;
+    if (gi >= p || gj >= p) return;
+    double s = 0.0;
+    const double* src = ws + (size_t)task * (MT_BLK * MT_BLK) + e;
+    for (int k = 0; k < nsplit; ++k) s += src[(size_t)k * ntasks * (MT_BLK * MT_BLK)];
+    double* G = E + goff;
+    G[gi + (size_t)gj * p] = s;
+    G[gj + (size_t)gi * p] = s;
+    return;
+  }
+  // last block: scalar + gradient
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    double s = 0.0;
+    for (int k = lane; k < nparts; k += 32) s += part_ll[k];
+    s = warp_sum(s);
+    if (lane == 0) E[0] = s;
+  }
+  if (want_grad) {
+    for (int j = threadIdx.x; j < p; j += blockDim.x) {
+      double s = 0.0;
+      for (int k = 0; k < nparts; ++k) s += part_g[(size_t)k * part_g_stride + j];
+      E[1 + j] = s;
+    }
+  }
+}
+
+}  // namespace gamc

@@ -1,0 +1,434 @@
+// sampler.cuh -- the arithmetic body of GAMC's `iterate!` (reference src/samplers/iterate/GAMC.jl:1-293)
+// as single-CTA step kernels around the data-pass kernels.  The host knows the branch sequence in advance
+// (the schedule coin depends only on (i, nsteps, u_sched), src/samplers/GAMC.jl:264-337), so it enqueues
+//     SMMALA:  [eval(theta) if stale] k_smmala_pre  -> eval(theta*) -> k_smmala_post
+//     AM:      [G^-1 from U if previous step was SMMALA] k_am_pre -> loglik(theta*) -> k_am_post
+// without ever synchronising; accept/reject, state swap, running means, tuner and chain output are decided
+// on the device.
+#pragma once
+#include "common.cuh"
+#include "linalg.cuh"
+
+namespace gamc {
+
+struct Bufs {
+  DevState* st;
+  double* R; int goff;                   // landing buffer of an evaluation = all-reduce payload: [ll, g(p), pad, G(p x p)]
+  double* Gs; size_t Gstride;            // Gs[slot]: p x p  pstate.tensorlogtarget of the point held in the slot
+  double* gs;                            // [2][p]           pstate.gradlogtarget
+  double* U; size_t Ustride;             // U[slot]: p x p, upper triangle = reverse Cholesky factor of G[slot]
+  double* rdiagU;                        // [2][p] reciprocal diagonal (M-space order)
+  double* fterm;                         // [2][p] G^-1 grad ("firstterm")
+  double* theta; double* theta_prop; double* mu; double* lastmean; double* secondlastmean;
+  double* C;                             // p x p  sstate.oldinvtensor while in AM mode (AM covariance)
+  double* Lc;                            // p x p  lower Cholesky factor of eps*C (am_mode 0) / of C (am_mode 1)
+  double* rdiagL;                        // p
+  double* W;                             // p x p  scratch: triangular inverse
+  double* chain_value; unsigned char* chain_accept; long long chain_cap;
+  const double* tape_usched; const double* tape_umix; const double* tape_z; const double* tape_uacc;
+};
+
+// shared memory of the step kernels: 4 vectors of p doubles + reduction scratch + LA scratch
+struct StepSmem {
+  double* v0; double* v1; double* v2; double* v3; double* red;
+  LaScratch la;
+};
+__host__ __device__ inline size_t step_smem_bytes(int p) {
+  const int pp = (p + 3) & ~3;
+  return sizeof(double) * (4 * (size_t)pp + 40) + la_scratch_bytes(p);
+}
+__device__ inline StepSmem step_smem_carve(unsigned char* base, int p) {
+  StepSmem s;
+  const int pp = (p + 3) & ~3;
+  double* d = reinterpret_cast<double*>(base);
+  s.v0 = d; s.v1 = d + pp; s.v2 = d + 2 * pp; s.v3 = d + 3 * pp; s.red = d + 4 * pp;
+  s.la = la_scratch_carve(reinterpret_cast<unsigned char*>(d + 4 * pp + 40), p);
+  return s;
+}
+
+__device__ __forceinline__ void raise_error(DevState* st, int code, int pivot) {
+  if (threadIdx.x == 0 && st->error_flag == 0) {
+    st->error_flag = code; st->error_pivot = pivot; st->error_iter = st->count;
+  }
+}
+
+// plogprior of examples/logistic_regression/src/GAMC/simulations.jl:30; all threads get the value.
+__device__ inline double log_prior(const double* theta, int p, double lambda, double* red) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) s = fma(theta[i], theta[i], s);
+  s = block_sum(s, red);
+  return -0.5 * (s / lambda + p * log(2.0 * 3.14159265358979323846 * lambda));
+}
+
+// Add the prior terms to a freshly reduced evaluation slot (after the all-reduce, once):
+//   ll += logprior, g -= theta/lambda, G_ii += 1/lambda   (simulations.jl:30,32,36).  Returns the log-target.
+__device__ inline double add_prior(double* E, int goff, const double* theta, int p, double lambda, double* red) {
+  const double lp = log_prior(theta, p, lambda, red);
+  for (int i = threadIdx.x; i < p; i += blockDim.x) {
+    E[1 + i] -= theta[i] / lambda;
+    E[goff + (size_t)i * p + i] += 1.0 / lambda;
+  }
+  __syncthreads();
+  return E[0] + lp;
+}
+
+// all-finite check of [g, G] of a slot; returns 1 if everything is finite
+__device__ inline int slot_finite(const double* E, int goff, int p, double* red) {
+  double bad = 0.0;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) if (!isfinite(E[1 + i])) bad = 1.0;
+  const size_t n = (size_t)p * p;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) if (!isfinite(E[goff + i])) bad = 1.0;
+  return block_sum(bad, red) == 0.0;
+}
+
+// Move the landed evaluation (prior already added) into a slot and factor its metric:
+// Gs[slot] <- G, gs[slot] <- g, U[slot] <- reverse Cholesky of G, fterm[slot] <- G^-1 g.
+// Returns 0 on success, the failed (M-space, 1-based) pivot otherwise.
+__device__ inline int factor_slot(const Bufs& B, int slot, int p, StepSmem& S) {
+  const double* G = B.R + B.goff;
+  const double* g = B.R + 1;
+  double* U = B.U + (size_t)slot * B.Ustride;
+  double* Gd = B.Gs + (size_t)slot * B.Gstride;
+  // copy G; its (natural) upper triangle = M-space lower triangle goes to the factor buffer
+  const size_t n = (size_t)p * p;
+  for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
+    const int i = (int)(e % p), j = (int)(e / p);
+    const double v = G[e];
+    Gd[e] = v;
+    if (i <= j) U[e] = v;
+  }
+  for (int i = threadIdx.x; i < p; i += blockDim.x) B.gs[(size_t)slot * p + i] = g[i];
+  __syncthreads();
+  MatView<true> V{U, p, p};
+  int bad = 0;
+  const double sl = chol_blocked<true>(V, B.rdiagU + (size_t)slot * p, S.la, &bad);
+  if (bad) return bad;
+  if (threadIdx.x == 0) B.st->sumlog[slot] = sl;
+  // firstterm = G^-1 g = Lm^-T (Lm^-1 g')   in M space
+  for (int i = threadIdx.x; i < p; i += blockDim.x) S.v3[i] = g[p - 1 - i];
+  __syncthreads();
+  trsv_lower<true>(V, B.rdiagU + (size_t)slot * p, S.v3, S.la);
+  trsv_lower_t<true>(V, B.rdiagU + (size_t)slot * p, S.v3, S.la);
+  for (int i = threadIdx.x; i < p; i += blockDim.x) B.fterm[(size_t)slot * p + i] = S.v3[p - 1 - i];
+  __syncthreads();
+  return 0;
+}
+
+// Bookkeeping shared by both branches: running means (iterate/GAMC.jl:193-197), burn-in tuning (:199-292),
+// chain output (Klara run loop: save when count > burnin).
+__device__ inline void step_tail(const Bufs& B, const TuneCfg& T, int accepted) {
+  DevState* st = B.st;
+  const int p = T.p;
+  const long long t = st->count;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) {
+    const double lm = B.lastmean[i];
+    B.secondlastmean[i] = lm;                                           // :193
+    B.lastmean[i] = ((double)(t - 1) * lm + B.theta[i]) / (double)t;    // recursive_mean! :195
+  }
+  if (t > T.burnin) {
+    const long long pos = st->chain_saved;
+    if (pos < B.chain_cap) {
+      for (int i = threadIdx.x; i < p; i += blockDim.x) B.chain_value[(size_t)pos * p + i] = B.theta[i];
+      if (threadIdx.x == 0) B.chain_accept[pos] = (unsigned char)accepted;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->last_accept = accepted;
+    if (t > T.burnin && st->chain_saved < B.chain_cap) st->chain_saved += 1;
+    if (T.tuning) {
+      if (st->tot_totprop <= T.burnin && (st->tot_prop % T.period) == 0) {
+        if (T.count_total) st->tot_rate = (double)st->tot_acc / (double)st->tot_prop;       // rate! :205
+        if (T.verbose_sm) {
+          st->smfreq = (double)st->sm_prop / (double)st->tot_prop;
+          st->sm_rate = (double)st->sm_acc / (double)st->sm_prop;
+        }
+        if (T.verbose_am) {
+          st->amfreq = (double)st->am_prop / (double)st->tot_prop;
+          st->am_rate = (double)st->am_acc / (double)st->am_prop;
+        }
+        if (T.is_accrate) {                                                                  // tune! :270-273
+          st->step *= 2.0 / (1.0 + exp(-T.score_k * (st->tot_rate - T.targetrate)));
+          st->sqrtstep = sqrt(st->step);
+        }
+        if (T.verbose_sm) { st->sm_totprop += st->sm_prop; st->sm_prop = 0; st->sm_acc = 0; st->sm_rate = nan(""); }
+        if (T.verbose_am) { st->am_totprop += st->am_prop; st->am_prop = 0; st->am_acc = 0; st->am_rate = nan(""); }
+        st->tot_totprop += st->tot_prop;                                                     // :283
+        st->tot_prop = 0;
+        if (T.count_total) { st->tot_acc = 0; st->tot_rate = nan(""); }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Initialisation: `initialize!` + `sampler_state` (src/samplers/GAMC.jl:157-228) after eval(theta0) into slot 0.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LA_THREADS, 1) k_sampler_init(Bufs B, TuneCfg T) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StepSmem S = step_smem_carve(smem_raw, T.p);
+  DevState* st = B.st;
+  const int p = T.p;
+  const double lt = add_prior(B.R, B.goff, B.theta, p, T.lambda, S.red);
+  const int fin = slot_finite(B.R, B.goff, p, S.red) && isfinite(lt);
+  if (!fin) { raise_error(st, 2 /*GAMC_NONFINITE_INIT*/, 0); return; }
+  const int bad = factor_slot(B, 0, p, S);
+  if (bad) { raise_error(st, 3 /*GAMC_NOT_POSDEF*/, p + 1 - bad); return; }
+  for (int i = threadIdx.x; i < p; i += blockDim.x) B.lastmean[i] = B.theta[i];   // GAMC.jl:218
+  if (threadIdx.x == 0) { st->logtarget = lt; st->cur = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SMMALA branch, part 1 (iterate/GAMC.jl:2-35): counters, optional re-factorisation at theta, proposal.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LA_THREADS, 1) k_smmala_pre(Bufs B, TuneCfg T, long long tape_idx, int refactor) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StepSmem S = step_smem_carve(smem_raw, T.p);
+  DevState* st = B.st;
+  const int p = T.p;
+  if (st->error_flag) return;
+  const int cur = st->cur;
+  if (threadIdx.x == 0) {
+    st->count += 1;                                   // :2
+    if (T.tuning) st->tot_prop += 1;                  // :4-6
+    st->updatetensorcount += 1;                       // :13
+    if (T.verbose_sm) st->sm_prop += 1;               // :15-17
+  }
+  if (refactor) {                                     // :19-31 (previous step was AM: grad/metric stale)
+    const double lt = add_prior(B.R, B.goff, B.theta, p, T.lambda, S.red);
+    if (threadIdx.x == 0) st->logtarget = lt;
+    const int bad = factor_slot(B, cur, p, S);
+    if (bad) { raise_error(st, 3, p + 1 - bad); return; }
+  }
+  __syncthreads();
+  const double eps = st->step, sq = st->sqrtstep;
+  // y' = Lm^-T z'  (cholinvtensor * randn(p), :35)
+  const double* z = B.tape_z + (size_t)tape_idx * p;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) S.v0[i] = z[p - 1 - i];
+  __syncthreads();
+  MatView<true> V{B.U + (size_t)cur * B.Ustride, p, p};
+  trsv_lower_t<true>(V, B.rdiagU + (size_t)cur * p, S.v0, S.la);
+  for (int i = threadIdx.x; i < p; i += blockDim.x) {
+    const double m = B.theta[i] + 0.5 * eps * B.fterm[(size_t)cur * p + i];   // :33
+    B.mu[i] = m;
+    B.theta_prop[i] = m + sq * S.v0[p - 1 - i];                                // :35
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SMMALA branch, part 2 (iterate/GAMC.jl:37-127 + tail): ratio, accept/reject, state swap.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LA_THREADS, 1) k_smmala_post(Bufs B, TuneCfg T, long long tape_idx) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StepSmem S = step_smem_carve(smem_raw, T.p);
+  DevState* st = B.st;
+  const int p = T.p;
+  if (st->error_flag) return;
+  const int cur = st->cur, prop = 1 - cur;
+  const double* Gc = B.Gs + (size_t)cur * B.Gstride;
+  const double* Gp = B.Gs + (size_t)prop * B.Gstride;
+  const double eps = st->step;
+  const double lt_p = add_prior(B.R, B.goff, B.theta_prop, p, T.lambda, S.red);
+  int ok = slot_finite(B.R, B.goff, p, S.red) && isfinite(lt_p);
+  double ratio = -INFINITY;
+  if (ok) {
+    const int bad = factor_slot(B, prop, p, S);      // newinvtensor / newfirstterm (:43,56) via one factorisation
+    if (bad) { raise_error(st, 3, p + 1 - bad); return; }
+    // d = theta* - mu ; q1 = d' G d / eps                                              (:47-54)
+    for (int i = threadIdx.x; i < p; i += blockDim.x) S.v0[i] = B.theta_prop[i] - B.mu[i];
+    __syncthreads();
+    symv_full(Gc, p, p, S.v0, S.v1);
+    __syncthreads();
+    double q1 = 0.0;
+    for (int i = threadIdx.x; i < p; i += blockDim.x) q1 = fma(S.v0[i], S.v1[i], q1);
+    q1 = block_sum(q1, S.red);
+    // mu* = theta* + eps/2 f* ; d2 = theta - mu* ; q2 = d2' G* d2 / eps                 (:58-67)
+    for (int i = threadIdx.x; i < p; i += blockDim.x) {
+      const double ms = B.theta_prop[i] + 0.5 * eps * B.fterm[(size_t)prop * p + i];
+      S.v2[i] = B.theta[i] - ms;
+    }
+    __syncthreads();
+    symv_full(Gp, p, p, S.v2, S.v1);
+    __syncthreads();
+    double q2 = 0.0;
+    for (int i = threadIdx.x; i < p; i += blockDim.x) q2 = fma(S.v2[i], S.v1[i], q2);
+    q2 = block_sum(q2, S.red);
+    const double plog = p * log(eps);
+    const double ld_old = plog - 2.0 * st->sumlog[cur];   // logdet(eps * G^-1)
+    const double ld_new = plog - 2.0 * st->sumlog[prop];
+    ratio = lt_p - st->logtarget;                                                       // :45
+    ratio += 0.5 * (ld_old + q1 / eps);
+    ratio -= 0.5 * (ld_new + q2 / eps);
+  }
+  const double u = B.tape_uacc[tape_idx];
+  const int accept = (ratio > 0.0) || (ratio > log(u));                                 // :69
+  __syncthreads();
+  if (accept) {
+    for (int i = threadIdx.x; i < p; i += blockDim.x) B.theta[i] = B.theta_prop[i];     // :70
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->ratio = ratio;
+    if (accept) {
+      st->logtarget = lt_p;                                                             // :98
+      st->cur = prop;                          // grad, tensor, invtensor, chol, firstterm swap (:72-96)
+      if (T.count_total) st->tot_acc += 1;                                              // :114-116
+      if (T.verbose_sm) st->sm_acc += 1;
+    }
+  }
+  __syncthreads();
+  step_tail(B, T, accept);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AM branch, part 1 (iterate/GAMC.jl:128-146): covariance recursion, proposal from the two-component GMM.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre(Bufs B, TuneCfg T, long long tape_idx) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StepSmem S = step_smem_carve(smem_raw, T.p);
+  DevState* st = B.st;
+  const int p = T.p;
+  if (st->error_flag) return;
+  if (threadIdx.x == 0) {
+    st->count += 1;
+    if (T.tuning) st->tot_prop += 1;
+    if (T.verbose_am) st->am_prop += 1;               // :129-131
+  }
+  __syncthreads();
+  const long long t = st->count;
+  const double k = (double)(t - 2);
+  const double eps = st->step;
+  // Klara covariance!(C, C, k, x, lastmean, secondlastmean)  (:133-140), then Hermitian (:142):
+  //   C = ((k-1) C + k m2 m2' - (k+1) m1 m1' + x x')/k
+  for (int i = threadIdx.x; i < p; i += blockDim.x) { S.v0[i] = B.theta[i]; S.v1[i] = B.lastmean[i]; S.v2[i] = B.secondlastmean[i]; }
+  __syncthreads();
+  const size_t n = (size_t)p * p;
+  for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
+    const int i = (int)(e % p), j = (int)(e / p);
+    if (i >= j) {
+      const double c = ((k - 1.0) * B.C[e] + k * (S.v2[i] * S.v2[j]) - (k + 1.0) * (S.v1[i] * S.v1[j]) + S.v0[i] * S.v0[j]) / k;
+      B.C[e] = c;
+      B.C[(size_t)j + (size_t)i * p] = c;
+      B.Lc[e] = eps * c;                              // MvNormal(theta, eps*C) -> Cholesky (set_gmm, GAMC.jl:188)
+    }
+  }
+  __syncthreads();
+  MatView<false> V{B.Lc, p, p};
+  int bad = 0;
+  chol_blocked<false>(V, B.rdiagL, S.la, &bad);
+  if (bad) { raise_error(st, 3, bad); return; }
+  const double* z = B.tape_z + (size_t)tape_idx * p;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) S.v3[i] = z[i];
+  __syncthreads();
+  const double umix = B.tape_umix[tape_idx];
+  if (umix <= 1.0 - T.c) {                            // rand(MixtureModel): core component (:146)
+    trmv_lower(B.Lc, p, p, S.v3, S.v1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < p; i += blockDim.x) B.theta_prop[i] = S.v0[i] + S.v1[i];
+  } else {
+    for (int i = threadIdx.x; i < p; i += blockDim.x) B.theta_prop[i] = S.v0[i] + T.sqrtminorscale * S.v3[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AM branch, part 2 (iterate/GAMC.jl:148-191 + tail).  The two GMM log-densities (:152,156) use the same
+// covariance with the roles of theta and theta* exchanged; d -> -d gives bit-identical quadratic forms and
+// log-sum-exp, so they cancel exactly and the device omits them (the oracle evaluates both literally and
+// tests/test_oracle_sampler.py asserts the cancellation is exact).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, long long tape_idx) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StepSmem S = step_smem_carve(smem_raw, T.p);
+  DevState* st = B.st;
+  const int p = T.p;
+  if (st->error_flag) return;
+  const double lt_p = B.R[0] + log_prior(B.theta_prop, p, T.lambda, S.red);
+  double ratio = isfinite(lt_p) ? (lt_p - st->logtarget) : -INFINITY;                   // :150
+  const double u = B.tape_uacc[tape_idx];
+  const int accept = (ratio > 0.0) || (ratio > log(u));                                 // :158
+  __syncthreads();
+  if (accept) {
+    for (int i = threadIdx.x; i < p; i += blockDim.x) B.theta[i] = B.theta_prop[i];     // :159
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->ratio = ratio;
+    if (accept) {
+      st->logtarget = lt_p;                                                             // :161
+      if (T.count_total) st->tot_acc += 1;
+      if (T.verbose_am) st->am_acc += 1;
+    }
+  }
+  __syncthreads();
+  step_tail(B, T, accept);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SMMALA -> AM hand-over: sstate.oldinvtensor = inv(G) seeds the AM covariance recursion
+// (iterate/GAMC.jl:26,92,133).  W = Lm^-1 (M space, one column per warp, column-oriented substitution with
+// one-step-ahead prefetch), then inv(G) = W' W.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TI_MAXR = 16;  // rows per lane: p <= 512
+
+__global__ void __launch_bounds__(256) k_triinv(const DevState* st, const double* Ubase, size_t Ustride,
+                                                const double* rdiagBase, int p, double* W) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int j = warp;
+  if (j >= p) return;
+  const int cur = st->cur;
+  MatView<true> L{const_cast<double*>(Ubase) + (size_t)cur * Ustride, p, p};
+  const double* rd = rdiagBase + (size_t)cur * p;
+  // lane owns rows i = j + lane + 32 s
+  double b[TI_MAXR];
+#pragma unroll
+  for (int s = 0; s < TI_MAXR; ++s) b[s] = 0.0;
+  if (lane == 0) b[0] = 1.0;
+  double* Wc = W + (size_t)j * p;
+  for (int i = lane; i < j; i += 32) Wc[i] = 0.0;
+  double nxt[TI_MAXR];
+#pragma unroll
+  for (int s = 0; s < TI_MAXR; ++s) { const int i = j + lane + 32 * s; nxt[s] = (i > j && i < p) ? L(i, j) : 0.0; }
+  for (int k = j; k < p; ++k) {
+    double colv[TI_MAXR];
+#pragma unroll
+    for (int s = 0; s < TI_MAXR; ++s) colv[s] = nxt[s];
+    if (k + 1 < p) {
+#pragma unroll
+      for (int s = 0; s < TI_MAXR; ++s) { const int i = j + lane + 32 * s; nxt[s] = (i > k + 1 && i < p) ? L(i, k + 1) : 0.0; }
+    }
+    // owner of row k: lane (k-j)%32, register (k-j)/32
+    const int ol = (k - j) & 31, os = (k - j) >> 5;
+    double bk = 0.0;
+#pragma unroll
+    for (int s = 0; s < TI_MAXR; ++s) if (s == os) bk = b[s];
+    const double wk = __shfl_sync(0xffffffffu, bk, ol) * rd[k];
+    if (lane == ol) Wc[k] = wk;
+#pragma unroll
+    for (int s = 0; s < TI_MAXR; ++s) b[s] = fma(-colv[s], wk, b[s]);
+  }
+}
+
+// C(natural) = inv(G):  Cm(a,b) = sum_{k >= max(a,b)} W[k][a] W[k][b];  C[p-1-a][p-1-b] = Cm(a,b).
+__global__ void __launch_bounds__(256) k_wtw(const double* __restrict__ W, int p, double* __restrict__ C) {
+  __shared__ double sa[16][17], sb[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int a0 = blockIdx.x * 16, b0 = blockIdx.y * 16;
+  if (b0 > a0) return;  // lower tiles only; mirrored on output
+  double acc = 0.0;
+  for (int k0 = a0; k0 < p; k0 += 16) {   // k >= max(a,b) >= a0 (W is lower triangular: zero above)
+    const int k = k0 + tx;   // tx runs along k: coalesced column reads of W
+    sa[tx][ty] = (k < p && a0 + ty < p) ? W[(size_t)k + (size_t)(a0 + ty) * p] : 0.0;
+    sb[tx][ty] = (k < p && b0 + ty < p) ? W[(size_t)k + (size_t)(b0 + ty) * p] : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) acc = fma(sa[kk][ty], sb[kk][tx], acc);
+    __syncthreads();
+  }
+  const int a = a0 + ty, b = b0 + tx;
+  if (a < p && b < p) {
+    C[(size_t)(p - 1 - a) + (size_t)(p - 1 - b) * p] = acc;
+    C[(size_t)(p - 1 - b) + (size_t)(p - 1 - a) * p] = acc;
+  }
+}
+
+}  // namespace gamc

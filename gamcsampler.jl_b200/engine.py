@@ -1,0 +1,187 @@
+"""Engine: one C-ABI handle (= one B200 + one CUDA stream) as a Python object.  Pure marshalling -- every
+method is one call into libgamc_b200.so; arrays are NumPy float64, matrices column-major (Fortran order),
+the layout of Julia's `Matrix{Float64}`."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _f64(a, order="F"):
+    return np.require(np.asarray(a, dtype=np.float64), dtype=np.float64, requirements=[order + "_CONTIGUOUS", "ALIGNED"])
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = L.load()
+        self.h = C.c_void_p()
+        st = self.lib.gamc_create(C.byref(self.h), int(device))
+        if st != L.GAMC_OK:
+            raise L.CudaError(f"gamc_create(device={device}) failed with status {st}: no usable sm_100 CUDA device "
+                              "(the product has no CPU fallback)")
+        self.device = int(device)
+        self.p = None
+        self.N = None
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.gamc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        L.check(st, self.h)
+
+    def version(self):
+        return self.lib.gamc_version().decode()
+
+    def sync(self):
+        self._ck(self.lib.gamc_sync(self.h))
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(self.lib.gamc_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    # -- target
+    def target_logistic(self, X, y, lam):
+        X = _f64(X, "F")
+        y = _f64(y, "C").ravel()
+        N, p = X.shape
+        assert y.shape[0] == N
+        self._ck(self.lib.gamc_target_logistic(self.h, L.dptr(X), N, L.dptr(y), N, p, float(lam)))
+        self.N, self.p = N, p
+
+    def target_logistic_device(self, dX_ptr: int, ldX: int, dy_ptr: int, N: int, p: int, lam: float):
+        self._ck(self.lib.gamc_target_logistic_device(self.h, C.c_void_p(dX_ptr), ldX, C.c_void_p(dy_ptr), N, p, float(lam)))
+        self.N, self.p = N, p
+
+    def target_logistic_synth(self, seed, row0, nrows, p, theta_true, lam):
+        tt = _f64(theta_true, "C").ravel()
+        assert tt.shape[0] == p
+        self._ck(self.lib.gamc_target_logistic_synth(self.h, int(seed), int(row0), int(nrows), int(p), L.dptr(tt), float(lam)))
+        self.N, self.p = int(nrows), int(p)
+
+    def read_rows(self, r0, n):
+        X = np.empty((n, self.p), dtype=np.float64, order="F")
+        y = np.empty(n, dtype=np.float64)
+        self._ck(self.lib.gamc_target_read_rows(self.h, int(r0), int(n), L.dptr(X), L.dptr(y)))
+        return X, y
+
+    # -- evaluation
+    def eval_logtarget(self, theta):
+        th = _f64(theta, "C").ravel()
+        out = C.c_double()
+        self._ck(self.lib.gamc_eval_logtarget(self.h, L.dptr(th), C.byref(out)))
+        return out.value
+
+    def eval_upto_tensor(self, theta):
+        th = _f64(theta, "C").ravel()
+        lt = C.c_double()
+        g = np.empty(self.p)
+        G = np.empty((self.p, self.p), order="F")
+        self._ck(self.lib.gamc_eval_upto_tensor(self.h, L.dptr(th), C.byref(lt), L.dptr(g), L.dptr(G)))
+        return lt.value, g, G
+
+    def eval_partials(self, theta, want_grad=True, want_tensor=True):
+        th = _f64(theta, "C").ravel()
+        ll = C.c_double()
+        g = np.empty(self.p) if (want_grad or want_tensor) else None
+        G = np.empty((self.p, self.p), order="F") if want_tensor else None
+        self._ck(self.lib.gamc_eval_partials(self.h, L.dptr(th), C.byref(ll), L.dptr(g), L.dptr(G)))
+        return ll.value, g, G
+
+    # -- communicator
+    @staticmethod
+    def comm_unique_id():
+        lib = L.load()
+        buf = np.zeros(128, dtype=np.uint8)
+        L.check(lib.gamc_comm_unique_id(L.u8ptr(buf)))
+        return buf
+
+    def comm_init(self, uid, nranks, rank):
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        self._ck(self.lib.gamc_comm_init(self.h, L.u8ptr(uid), int(nranks), int(rank)))
+
+    # -- sampler
+    def sampler_init(self, cfg: L.Config, theta0):
+        th = _f64(theta0, "C").ravel()
+        assert th.shape[0] == self.p
+        self._cfg = cfg
+        self._ck(self.lib.gamc_sampler_init(self.h, C.byref(cfg), L.dptr(th)))
+
+    def tape_set(self, u_sched, u_mix, z, u_acc):
+        """z is (n, p) C-order == p x n column-major."""
+        us, um, ua = _f64(u_sched, "C"), _f64(u_mix, "C"), _f64(u_acc, "C")
+        zz = _f64(z, "C")
+        n = us.shape[0]
+        assert zz.shape == (n, self.p)
+        self._ck(self.lib.gamc_tape_set(self.h, n, L.dptr(us), L.dptr(um), L.dptr(zz), L.dptr(ua)))
+
+    def tape_generate(self, n, seed):
+        self._ck(self.lib.gamc_tape_generate(self.h, int(n), int(seed)))
+
+    def run(self, n):
+        self._ck(self.lib.gamc_run(self.h, int(n)))
+
+    def chain_get(self, first, n):
+        value = np.empty((self.p, n), dtype=np.float64, order="F")
+        accept = np.empty(n, dtype=np.uint8)
+        self._ck(self.lib.gamc_chain_get(self.h, int(first), int(n), L.dptr(value), L.u8ptr(accept)))
+        return value, accept.astype(bool)
+
+    def iterate(self, u_sched, u_mix, z, u_acc):
+        us, um, ua = _f64(u_sched, "C"), _f64(u_mix, "C"), _f64(u_acc, "C")
+        zz = _f64(z, "C")
+        n = us.shape[0]
+        value = np.empty((self.p, n), dtype=np.float64, order="F")
+        accept = np.empty(n, dtype=np.uint8)
+        nsaved = C.c_int64()
+        self._ck(self.lib.gamc_iterate(self.h, n, L.dptr(us), L.dptr(um), L.dptr(zz), L.dptr(ua), L.dptr(value),
+                                       L.u8ptr(accept), C.byref(nsaved)))
+        k = nsaved.value
+        return value[:, :k], accept[:k].astype(bool)
+
+    def peek_kinds(self, n):
+        out = np.empty(n, dtype=np.uint8)
+        self._ck(self.lib.gamc_peek_kinds(self.h, int(n), L.u8ptr(out)))
+        return out
+
+    def state(self) -> L.StateScalars:
+        st = L.StateScalars()
+        self._ck(self.lib.gamc_get_state(self.h, C.byref(st)))
+        return st
+
+    def array(self, array_id):
+        is_mat = array_id in (L.ARR_TENSORLOGTARGET, L.ARR_OLDINVTENSOR, L.ARR_CHOLINVTENSOR)
+        out = np.empty(self.p * self.p if is_mat else self.p, dtype=np.float64)
+        self._ck(self.lib.gamc_get_array(self.h, int(array_id), L.dptr(out)))
+        return out.reshape((self.p, self.p), order="F") if is_mat else out
+
+    # -- measurement
+    def profile_enable(self, on=True):
+        self._ck(self.lib.gamc_profile_enable(self.h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._ck(self.lib.gamc_profile_reset(self.h))
+
+    def profile_get(self):
+        out = {}
+        for fam, name in enumerate(L.KERNEL_FAMILIES):
+            n = C.c_int64()
+            ms = C.c_double()
+            self._ck(self.lib.gamc_profile_get(self.h, fam, C.byref(n), C.byref(ms)))
+            out[name] = (n.value, ms.value)
+        return out
+
+    def launch_count(self):
+        n = C.c_int64()
+        self._ck(self.lib.gamc_launch_count(self.h, C.byref(n)))
+        return n.value

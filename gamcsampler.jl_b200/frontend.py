@@ -1,0 +1,326 @@
+"""Host-side mirror of GAMCSampler.jl's public API for the hot path (Python stand-in for the Julia
+front-end in julia/GAMCSamplerB200.jl; Julia is not available in this image).
+
+Same names, keyword arguments, defaults and error behaviour as the reference:
+  GAMC(update, transform, driftstep, minorscale, c, t0)                 src/samplers/GAMC.jl:126-151
+  GAMCTuner(smmalatuner, amtuner, totaltuner)                           src/tuners/GAMCTuner.jl:15-23
+  VanillaMCTuner / AcceptanceRateMCTuner / logistic_rate_score          Klara.jl (restated)
+  nine schedules (Julia's trailing `!` dropped) and four decay functions src/samplers/GAMC.jl:264-337, src/stats/schedule.jl:1-7
+  BasicMCRange / BasicMCJob / run / output / acceptance                 Klara.jl call sites in
+                                                                        examples/logistic_regression/src/GAMC/simulations.jl:39-95
+All arithmetic happens in the CUDA library; this module only builds the C config struct, draws the host
+random tape and marshals arrays.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+from .engine import Engine
+
+__all__ = [
+    "GAMC", "GAMCTuner", "GAMCTune", "BasicMCTune", "VanillaMCTuner", "AcceptanceRateMCTuner", "logistic_rate_score",
+    "am_only_update", "smmala_only_update", "mod_update", "rand_update", "cos_update", "rand_exp_decay_update",
+    "rand_lin_decay_update", "rand_pow_decay_update", "rand_quad_decay_update",
+    "exp_decay", "lin_decay", "pow_decay", "quad_decay",
+    "BasicMCRange", "LogisticModel", "BasicMCJob", "Chain", "run", "output", "acceptance", "RandomTape",
+]
+
+
+# ------------------------------------------------------------------ decay functions (src/stats/schedule.jl:1-7)
+def exp_decay(i, tot, a=10.0, b=0.0):
+    return (1 - b) * math.exp(-a * i / tot) + b
+
+
+def lin_decay(i, tot, a=1e-3, b=0.0):
+    return (1 - b) * (1 / (1 + a * i)) + b
+
+
+def pow_decay(i, tot, a=1e-3, b=0.0):
+    return (1 - b) * (a ** (i / tot)) + b
+
+
+def quad_decay(i, tot, a=1e-3, b=0.0):
+    return (1 - b) * (1 / (1 + a * i * i)) + b
+
+
+# ------------------------------------------------------------------ schedules (src/samplers/GAMC.jl:264-337)
+@dataclass(frozen=True)
+class Schedule:
+    """A schedule `update!` with its trailing parameters bound, e.g. the reference's
+    `(sstate, pstate, i, tot) -> rand_exp_decay_update!(sstate, pstate, i, tot, 10.)`."""
+    kind: int
+    params: tuple = ()
+    name: str = ""
+
+
+def am_only_update():
+    return Schedule(0, (), "am_only_update!")
+
+
+def smmala_only_update():
+    return Schedule(1, (), "smmala_only_update!")
+
+
+def mod_update(n=10):
+    return Schedule(2, (float(n),), "mod_update!")
+
+
+def rand_update(p=0.5):
+    return Schedule(3, (float(p),), "rand_update!")
+
+
+def cos_update(a=10.0, b=0.2, c=0.2):
+    return Schedule(4, (float(a), float(b), float(c)), "cos_update!")
+
+
+def rand_exp_decay_update(a=10.0, b=0.0):
+    return Schedule(5, (float(a), float(b)), "rand_exp_decay_update!")
+
+
+def rand_lin_decay_update(a=1e-2, b=0.0):
+    return Schedule(6, (float(a), float(b)), "rand_lin_decay_update!")
+
+
+def rand_pow_decay_update(a=1e-3, b=0.0):
+    return Schedule(7, (float(a), float(b)), "rand_pow_decay_update!")
+
+
+def rand_quad_decay_update(a=1e-5, b=0.0):
+    return Schedule(8, (float(a), float(b)), "rand_quad_decay_update!")
+
+
+# ------------------------------------------------------------------ tuners
+def logistic_rate_score(x, k=7.0):
+    return 2.0 / (1.0 + math.exp(-k * x))
+
+
+@dataclass
+class VanillaMCTuner:
+    period: int = 100
+    verbose: bool = False
+
+
+@dataclass
+class AcceptanceRateMCTuner:
+    targetrate: float = 0.35
+    score_k: float = 7.0        # score = x -> logistic_rate_score(x, score_k)
+    period: int = 100
+    verbose: bool = False
+
+
+@dataclass
+class GAMCTuner:
+    smmalatuner: VanillaMCTuner = field(default_factory=VanillaMCTuner)
+    amtuner: VanillaMCTuner = field(default_factory=VanillaMCTuner)
+    totaltuner: object = field(default_factory=VanillaMCTuner)
+
+    @property
+    def verbose(self):
+        return bool(self.totaltuner.verbose or self.smmalatuner.verbose or self.amtuner.verbose)
+
+    def __repr__(self):
+        return "GAMCTuner"
+
+
+@dataclass
+class BasicMCTune:
+    step: float = float("nan")
+    accepted: int = 0
+    proposed: int = 0
+    totproposed: int = 0
+    rate: float = float("nan")
+
+
+@dataclass
+class GAMCTune:
+    smmalatune: BasicMCTune
+    amtune: BasicMCTune
+    totaltune: BasicMCTune
+    smmalafrequency: float = float("nan")
+    amfrequency: float = float("nan")
+
+
+# ------------------------------------------------------------------ sampler
+class GAMC:
+    """`GAMC(; update=rand_update!, transform=nothing, driftstep=1., minorscale=1., c=0.05, t0=3)`."""
+
+    def __init__(self, update: Optional[Schedule] = None, transform=None, driftstep=1.0, minorscale=1.0, c=0.05, t0=3,
+                 am_mode=0):
+        assert driftstep > 0, "Drift step is not positive"
+        assert 0 < minorscale, f"Constant minorscale must be positive, got {minorscale}"
+        assert 0 <= c, "Constant c must be non-negative"
+        assert t0 > 0, "t0 is not positive"
+        if transform is not None:
+            raise NotImplementedError("transform (e.g. softabs) is a SURVEY.md 8(f) 'next' row; the logistic path uses none "
+                                      "(examples/logistic_regression/src/GAMC/simulations.jl:50-55)")
+        self.update = update if update is not None else rand_update()
+        self.transform = transform
+        self.driftstep, self.minorscale, self.c, self.t0 = float(driftstep), float(minorscale), float(c), int(t0)
+        self.am_mode = int(am_mode)
+
+    def __repr__(self):
+        return (f"GAMC sampler: drift step = {self.driftstep}, scaling of stabilizing covariance = {self.minorscale}, "
+                f"weight of stabilizing mixture component = {self.c}")
+
+
+@dataclass
+class BasicMCRange:
+    nsteps: int
+    burnin: int = 0
+
+
+@dataclass
+class LogisticModel:
+    """`likelihood_model([Hyperparameter(:λ), Data(:X), Data(:y), p])` of the logistic example with its
+    closed-form callbacks (examples/logistic_regression/src/GAMC/simulations.jl:25-48)."""
+    X: Optional[np.ndarray] = None
+    y: Optional[np.ndarray] = None
+    lam: float = 100.0
+    synth: Optional[dict] = None   # {"seed":..., "N":..., "p":..., "theta_true":..., "row0": 0, "nrows": N}
+
+
+class RandomTape:
+    """Host-drawn normals and uniforms in fixed per-iteration slots."""
+
+    def __init__(self, nsteps, p, seed=0):
+        rng = np.random.Generator(np.random.PCG64(seed))
+        self.u_sched = rng.random(nsteps)
+        self.u_mix = rng.random(nsteps)
+        self.u_acc = rng.random(nsteps)
+        self.u_acc[self.u_acc == 0.0] = np.finfo(np.float64).tiny
+        self.z = rng.standard_normal((nsteps, p))
+
+
+def make_config(sampler: GAMC, tuner: GAMCTuner, mcrange: BasicMCRange) -> L.Config:
+    cfg = L.Config()
+    cfg.driftstep, cfg.minorscale, cfg.c, cfg.t0 = sampler.driftstep, sampler.minorscale, sampler.c, sampler.t0
+    cfg.schedule = sampler.update.kind
+    pr = list(sampler.update.params) + [float("nan")] * 3
+    for i in range(3):
+        cfg.sched_params[i] = pr[i]
+    tt = tuner.totaltuner
+    cfg.total_tuner_kind = 1 if isinstance(tt, AcceptanceRateMCTuner) else 0
+    cfg.targetrate = getattr(tt, "targetrate", float("nan"))
+    cfg.score_k = getattr(tt, "score_k", 7.0)
+    cfg.period = int(tt.period)
+    cfg.verbose_total = int(bool(tt.verbose))
+    cfg.verbose_smmala = int(bool(tuner.smmalatuner.verbose))
+    cfg.verbose_am = int(bool(tuner.amtuner.verbose))
+    cfg.nsteps, cfg.burnin = int(mcrange.nsteps), int(mcrange.burnin)
+    cfg.am_mode = sampler.am_mode
+    return cfg
+
+
+@dataclass
+class Chain:
+    value: np.ndarray              # p x nsamples (chain.value)
+    diagnosticvalues: np.ndarray   # 1 x nsamples Bool (:accept)
+
+
+class _SState:
+    """View of job.sstate with the fields the examples read (simulations.jl:85-86)."""
+
+    def __init__(self, eng: Engine):
+        self._eng = eng
+
+    def _refresh(self):
+        return self._eng.state()
+
+    @property
+    def tune(self):
+        s = self._refresh()
+        return GAMCTune(
+            BasicMCTune(float("nan"), s.smmala_accepted, s.smmala_proposed, s.smmala_totproposed),
+            BasicMCTune(float("nan"), s.am_accepted, s.am_proposed, s.am_totproposed),
+            BasicMCTune(s.step, s.total_accepted, s.total_proposed, s.total_totproposed, s.total_rate),
+            s.smmalafrequency, s.amfrequency)
+
+    @property
+    def updatetensorcount(self):
+        return self._refresh().updatetensorcount
+
+    @property
+    def count(self):
+        return self._refresh().count
+
+    @property
+    def sqrttunestep(self):
+        return self._refresh().sqrttunestep
+
+    @property
+    def ratio(self):
+        return self._refresh().ratio
+
+    def __getattr__(self, name):
+        ids = {"lastmean": L.ARR_LASTMEAN, "secondlastmean": L.ARR_SECONDLASTMEAN, "oldinvtensor": L.ARR_OLDINVTENSOR,
+               "cholinvtensor": L.ARR_CHOLINVTENSOR, "oldfirstterm": L.ARR_OLDFIRSTTERM}
+        if name in ids:
+            return self._eng.array(ids[name])
+        raise AttributeError(name)
+
+
+class BasicMCJob:
+    """`BasicMCJob(model, sampler, mcrange, v0, tuner=..., outopts=...)` (simulations.jl:71) for the GAMC sampler
+    on one B200 (device=...) or on this rank's row shard of a multi-GPU job (comm=(uid, nranks, rank))."""
+
+    def __init__(self, model: LogisticModel, sampler: GAMC, mcrange: BasicMCRange, v0, tuner: Optional[GAMCTuner] = None,
+                 outopts=None, device=0, tape: Optional[RandomTape] = None, tape_seed=0, comm=None, engine: Optional[Engine] = None):
+        self.model, self.sampler, self.range = model, sampler, mcrange
+        self.tuner = tuner if tuner is not None else GAMCTuner()
+        self.outopts = outopts or {"monitor": ["value"], "diagnostics": ["accept"]}
+        self.engine = engine if engine is not None else Engine(device)
+        eng = self.engine
+        if engine is None:
+            if model.synth is not None:
+                s = model.synth
+                eng.target_logistic_synth(s["seed"], s.get("row0", 0), s.get("nrows", s["N"]), s["p"], s["theta_true"], model.lam)
+            else:
+                eng.target_logistic(model.X, model.y, model.lam)
+        if comm is not None:
+            eng.comm_init(*comm)
+        theta0 = np.asarray(v0["p"] if isinstance(v0, dict) else v0, dtype=np.float64)
+        self.cfg = make_config(sampler, self.tuner, mcrange)
+        eng.sampler_init(self.cfg, theta0)          # initialize! + sampler_state
+        self.tape = tape
+        self.tape_seed = tape_seed
+        self.sstate = _SState(eng)
+        self._done = 0
+
+    def run(self, chunk=None):
+        """Klara `run(job)`: nsteps transitions; samples after burn-in stay on the device until `output`."""
+        n = self.range.nsteps - self._done
+        eng = self.engine
+        if self.tape is not None:
+            t = self.tape
+            lo, hi = self._done, self._done + n
+            eng.tape_set(t.u_sched[lo:hi], t.u_mix[lo:hi], t.z[lo:hi], t.u_acc[lo:hi])
+        else:
+            eng.tape_generate(n, self.tape_seed)
+        eng.run(n)
+        eng.sync()
+        self._done += n
+        return self
+
+    def output(self) -> Chain:
+        nsave = max(0, self.range.nsteps - self.range.burnin)
+        value, accept = self.engine.chain_get(0, nsave)
+        return Chain(value, accept.reshape(1, -1))
+
+
+def run(job: BasicMCJob):
+    return job.run()
+
+
+def output(job: BasicMCJob) -> Chain:
+    return job.output()
+
+
+def acceptance(chain_or_diag) -> float:
+    """Klara `acceptance(chain)` / `acceptance(::Matrix{Bool})`: mean of the :accept diagnostic."""
+    d = chain_or_diag.diagnosticvalues if isinstance(chain_or_diag, Chain) else chain_or_diag
+    return float(np.mean(np.asarray(d, dtype=bool)))

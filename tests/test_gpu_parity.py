@@ -1,0 +1,150 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Tolerance: 1e-10 norm-wise relative error in FP64 (BASELINE.json north star) for log-target, gradient and
+metric; trajectories on a shared random tape must agree step for step (identical accept decisions)."""
+import numpy as np
+import pytest
+
+from util import relerr, example_config
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def _oracle():
+    import oracle
+    return oracle
+
+
+@pytest.mark.parametrize("N,p", [(200, 4), (1000, 37), (33, 1), (5000, 256), (4097, 300), (777, 512), (36 * 50 + 1, 64)])
+def test_eval_parity(engine, N, p):
+    o = _oracle()
+    X, y, tt = o.synth_logistic(20260101, N, p)
+    rng = np.random.default_rng(7)
+    theta = tt + 0.05 * rng.standard_normal(p)
+    engine.target_logistic(X, y, 100.0)
+    lt, g, G = engine.eval_upto_tensor(theta)
+    tgt = o.LogisticTarget(X, y, 100.0)
+    lt0, g0, G0 = tgt.uptotensorlogtarget(theta)
+    assert abs(lt - lt0) <= TOL * abs(lt0)
+    assert relerr(g, g0) <= TOL
+    assert relerr(G, G0) <= TOL
+    assert np.array_equal(G, G.T)  # exactly symmetric by construction
+    assert abs(engine.eval_logtarget(theta) - lt0) <= TOL * abs(lt0)
+    # likelihood-only partials (what a rank contributes to the all-reduce)
+    ll, gl, Gl = engine.eval_partials(theta)
+    ll0, gl0, Gl0 = o.logistic_partials(theta, X, y)
+    assert abs(ll - ll0) <= TOL * abs(ll0)
+    assert relerr(gl, gl0) <= TOL and relerr(Gl, Gl0) <= TOL
+
+
+def test_eval_deterministic(engine):
+    o = _oracle()
+    X, y, tt = o.synth_logistic(3, 3000, 100)
+    engine.target_logistic(X, y, 100.0)
+    a = engine.eval_upto_tensor(tt)
+    b = engine.eval_upto_tensor(tt)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_eval_extreme_eta(engine):
+    """|eta| beyond the overflow point of the reference's naive log(1+exp(eta)) must stay finite."""
+    o = _oracle()
+    X, y, tt = o.synth_logistic(5, 500, 8)
+    theta = 400.0 * np.ones(8)
+    engine.target_logistic(X, y, 100.0)
+    lt, g, G = engine.eval_upto_tensor(theta)
+    lt0, g0, G0 = o.LogisticTarget(X, y, 100.0).uptotensorlogtarget(theta)
+    assert np.isfinite(lt) and abs(lt - lt0) <= 1e-10 * abs(lt0)
+    assert relerr(g, g0) <= 1e-10 and relerr(G, G0) <= 1e-9
+
+
+@pytest.mark.parametrize("N,p,row0", [(1000, 20, 0), (513, 7, 100000)])
+def test_synth_bitexact(engine, N, p, row0):
+    o = _oracle()
+    tt = o.logistic.synth_theta_true(11, p)
+    X, y, _ = o.synth_logistic(11, row0 + N, p, row0=row0, nrows=N, theta_true=tt)
+    engine.target_logistic_synth(11, row0, N, p, tt, 100.0)
+    Xd, yd = engine.read_rows(0, N)
+    assert np.array_equal(Xd, X)
+    assert np.array_equal(yd, y)
+
+
+def _run_both(gamc, engine, N, p, nsteps, burnin, seed, am_mode=0, update=None, theta_scale=0.05, verbose=False):
+    o = _oracle()
+    X, y, tt = o.synth_logistic(20260101 + p, N, p)
+    rng = np.random.default_rng(seed)
+    theta0 = tt + theta_scale * rng.standard_normal(p)
+    sampler, tuner, rng_ = example_config(gamc, nsteps, burnin, am_mode=am_mode, update=update, verbose=verbose)
+    tape = gamc.RandomTape(nsteps, p, seed=seed + 1)
+    engine.target_logistic(X, y, 100.0)
+    job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, rng_, {"p": theta0}, tuner=tuner, tape=tape, engine=engine)
+    job.run()
+    chain = job.output()
+    # oracle on the same tape
+    otape = o.RandomTape(nsteps, p, seed=seed + 1)
+    assert np.array_equal(otape.z, tape.z)
+    otuner = o.GAMCTuner(o.VanillaMCTuner(verbose=verbose), o.VanillaMCTuner(verbose=verbose), o.AcceptanceRateMCTuner(0.35, verbose=verbose))
+    osam = o.GAMCOracle(o.LogisticTarget(X, y, 100.0), theta0, nsteps, burnin, update=sampler.update.name,
+                        update_params=sampler.update.params, driftstep=0.02, minorscale=0.001, c=0.01, tuner=otuner)
+    v, a, k = osam.run(otape)
+    return job, chain, osam, v, a, k
+
+
+@pytest.mark.parametrize("N,p,nsteps", [(200, 4, 3000), (500, 33, 1200), (2000, 64, 1000)])
+def test_trajectory_parity(gamc, engine, N, p, nsteps):
+    """Same host-drawn normals and uniforms => step-for-step agreement for >= 1000 iterations."""
+    burnin = nsteps // 5
+    job, chain, osam, v, a, k = _run_both(gamc, engine, N, p, nsteps, burnin, seed=42)
+    assert chain.value.shape == v.shape
+    assert np.array_equal(chain.diagnosticvalues.ravel(), a), "accept/reject decisions diverged"
+    assert relerr(chain.value, v) <= 1e-8
+    st = job.engine.state()
+    assert st.count == nsteps == osam.count
+    assert st.updatetensorcount == osam.updatetensorcount
+    assert abs(st.step - osam.tune.totaltune.step) <= 1e-12 * osam.tune.totaltune.step
+    assert st.total_totproposed == osam.tune.totaltune.totproposed
+    assert relerr(job.engine.array(3), osam.lastmean) <= 1e-9   # lastmean
+
+
+def test_trajectory_parity_verbose_counters(gamc, engine):
+    job, chain, osam, v, a, k = _run_both(gamc, engine, 300, 6, 1500, 500, seed=5, verbose=True)
+    assert np.array_equal(chain.diagnosticvalues.ravel(), a)
+    st = job.engine.state()
+    assert (st.smmala_totproposed, st.am_totproposed) == (osam.tune.smmalatune.totproposed, osam.tune.amtune.totproposed)
+    assert (st.smmala_proposed, st.am_proposed) == (osam.tune.smmalatune.proposed, osam.tune.amtune.proposed)
+
+
+@pytest.mark.parametrize("update", ["smmala_only_update", "am_only_update", "mod_update", "rand_update", "cos_update",
+                                    "rand_lin_decay_update", "rand_pow_decay_update", "rand_quad_decay_update"])
+def test_schedules_parity(gamc, engine, update):
+    sched = getattr(gamc, update)()
+    job, chain, osam, v, a, k = _run_both(gamc, engine, 250, 5, 400, 100, seed=9, update=sched)
+    assert np.array_equal(chain.diagnosticvalues.ravel(), a)
+    assert relerr(chain.value, v) <= 1e-8
+    assert job.engine.state().updatetensorcount == osam.updatetensorcount
+
+
+def test_state_arrays_parity(gamc, engine):
+    """oldinvtensor / cholinvtensor / firstterm (one reverse Cholesky on the device) against the reference's
+    literal inv + chol route in the oracle."""
+    job, chain, osam, v, a, k = _run_both(gamc, engine, 400, 12, 40, 0, seed=3, update=gamc.smmala_only_update())
+    eng = job.engine
+    assert relerr(eng.array(5), osam.oldinvtensor) <= 1e-9
+    assert relerr(eng.array(6), osam.cholinvtensor) <= 1e-9
+    assert relerr(eng.array(7), osam.oldfirstterm) <= 1e-9
+    assert relerr(eng.array(2), osam.G) <= 1e-10
+    assert relerr(eng.array(1), osam.grad) <= 1e-10
+
+
+def test_errors(gamc, engine):
+    o = _oracle()
+    X, y, tt = o.synth_logistic(1, 100, 3)
+    engine.target_logistic(X, y, 100.0)
+    with pytest.raises(AssertionError):
+        gamc.GAMC(driftstep=-1.0)
+    sampler, tuner, rng_ = example_config(gamc, 10, 0)
+    with pytest.raises(AssertionError):   # non-finite initial value (GAMC.jl:168-170)
+        gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, rng_, {"p": np.array([np.nan, 0.0, 0.0])}, tuner=tuner, engine=engine)
+    with pytest.raises(gamc._lib.UnsupportedShape):
+        engine.target_logistic(np.zeros((10, 513)), np.zeros(10), 100.0)
