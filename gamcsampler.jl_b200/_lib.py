@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgamc_b200.so")
+LIB_PATH = os.environ.get("GAMC_LIB", os.path.join(_HERE, "libgamc_b200.so"))   # GAMC_LIB: debug builds only
 
 GAMC_OK, GAMC_INVALID_ARG, GAMC_NONFINITE_INIT, GAMC_NOT_POSDEF, GAMC_CUDA_ERROR, GAMC_NCCL_ERROR, \
     GAMC_UNSUPPORTED_SHAPE, GAMC_NOT_READY = range(8)

@@ -91,7 +91,8 @@ struct gamc_ctx {
   bool sampler_ready = false;
   gamc_config cfg{}; TuneCfg tune{};
   Bufs B{};
-  double* U = nullptr; double* vecs = nullptr; double* mats = nullptr;
+  double* vecs = nullptr; double* mats = nullptr; DevState* d_state = nullptr;
+  unsigned char* arena = nullptr; size_t arena_bytes = 0;   // [state | vecs | R | mats]: the L2-persisting working set of the step kernels
   long long h_count = 0; bool h_present = true, h_past = false;
   // tape
   long long tape_n = 0, tape_pos = 0, tape_cap = 0; int tape_p = 0;
@@ -196,14 +197,34 @@ void free_target(gamc_ctx* h) {
   cudaFree(h->dw); h->dw = nullptr;
   cudaFree(h->part_ll); cudaFree(h->part_g); h->part_ll = h->part_g = nullptr;
   cudaFree(h->d_plans); cudaFree(h->d_coords); cudaFree(h->ws); h->d_plans = nullptr; h->d_coords = nullptr; h->ws = nullptr;
-  cudaFree(h->R); h->R = nullptr; cudaFree(h->theta_eval); h->theta_eval = nullptr;
+  cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0; h->R = nullptr; h->vecs = h->mats = nullptr; h->d_state = nullptr;
+  cudaFree(h->theta_eval); h->theta_eval = nullptr;
 }
 
 void free_sampler(gamc_ctx* h) {
-  cudaFree(h->B.st); cudaFree(h->U); cudaFree(h->vecs); cudaFree(h->mats);
   cudaFree(h->d_chain); cudaFree(h->d_accept);
-  h->B = Bufs{}; h->U = h->vecs = h->mats = nullptr; h->d_chain = nullptr; h->d_accept = nullptr;
+  h->B = Bufs{}; h->d_chain = nullptr; h->d_accept = nullptr;
   h->sampler_ready = false;
+}
+
+// Keep the step kernels' working set (state, vectors, landing buffer, p x p matrices: a few MB) resident in
+// the persisting part of L2: every data pass streams the 2 GB design matrix through L2 and would otherwise
+// evict it, leaving the single-CTA linear-algebra kernels bound by DRAM latency.
+void apply_l2_policy(gamc_ctx* h) {
+  if (!h->arena) return;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return;
+  if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
+  const size_t want = std::min<size_t>(h->arena_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, std::max<size_t>(want * 2, 8u << 20)));
+  cudaStreamAttrValue attr{};
+  attr.accessPolicyWindow.base_ptr = h->arena;
+  attr.accessPolicyWindow.num_bytes = want;
+  attr.accessPolicyWindow.hitRatio = 1.0f;
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+  cudaGetLastError();   // best effort: a refusal only costs performance
 }
 
 // ---- data-pass dispatch -----------------------------------------------------------------------------
@@ -325,15 +346,27 @@ gamc_status setup_target(gamc_ctx* h) {
   CUDA_TRY(h, cudaMemcpyAsync(h->d_coords, h->layout.coords.data(), sizeof(TaskCoord) * h->ntasks, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMalloc(&h->ws, sizeof(double) * (size_t)h->nsplit * h->ntasks * MT_BLK * MT_BLK));
   h->goff = (1 + p + 1) & ~1;  // G starts 16-byte aligned
-  CUDA_TRY(h, cudaMalloc(&h->R, sizeof(double) * ((size_t)h->goff + (size_t)p * p)));
-  CUDA_TRY(h, cudaMemsetAsync(h->R, 0, sizeof(double) * ((size_t)h->goff + (size_t)p * p), h->stream));
+  {
+    const size_t pp = (size_t)p * p;
+    const size_t n_state = 64, n_vecs = ((size_t)12 * p + 15) & ~(size_t)15, n_R = ((size_t)h->goff + pp + 15) & ~(size_t)15, n_mats = 7 * pp;
+    h->arena_bytes = sizeof(double) * (n_state + n_vecs + n_R + n_mats);
+    CUDA_TRY(h, cudaMalloc(&h->arena, h->arena_bytes));
+    CUDA_TRY(h, cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
+    double* base = reinterpret_cast<double*>(h->arena);
+    static_assert(sizeof(DevState) <= 64 * sizeof(double), "DevState must fit its arena slot");
+    h->d_state = reinterpret_cast<DevState*>(base);
+    h->vecs = base + n_state;
+    h->R = h->vecs + n_vecs;
+    h->mats = h->R + n_R;
+    apply_l2_policy(h);
+  }
   CUDA_TRY(h, cudaMalloc(&h->theta_eval, sizeof(double) * p));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return GAMC_OK;
 }
 
 gamc_status check_device_error(gamc_ctx* h) {
-  if (!h->sampler_ready && !h->B.st) return GAMC_OK;
+  if (!h->B.st) return GAMC_OK;
   DevState st;
   CUDA_TRY(h, cudaMemcpyAsync(&st, h->B.st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -378,8 +411,10 @@ gamc_status launch_step(gamc_ctx* h, K kern, Args... args) {
 
 gamc_status set_step_attrs(gamc_ctx* h) {
   const int smem = (int)step_smem_bytes(512);   // sized for the largest supported p so the attribute is set once
-  const void* ks[] = {(const void*)k_sampler_init, (const void*)k_smmala_pre, (const void*)k_smmala_post, (const void*)k_am_pre, (const void*)k_am_post};
+  const void* ks[] = {(const void*)k_sampler_init, (const void*)k_smmala_pre, (const void*)k_smmala_post, (const void*)k_am_pre,
+                      (const void*)k_am_post};
   for (const void* k : ks) { gamc_status s = ensure_attr(h, k, smem); if (s != GAMC_OK) return s; }
+  { gamc_status s = ensure_attr(h, (const void*)k_am_pre_r1, am_r1_smem_bytes(512, 1)); if (s != GAMC_OK) return s; }
   return GAMC_OK;
 }
 
@@ -398,6 +433,17 @@ gamc_status launch_inverse(gamc_ctx* h, bool write_C = true) {
     k_wtw<<<grid, 256, 0, h->stream>>>(h->B.W, p, h->B.C);
     CUDA_TRY(h, cudaGetLastError());
   }
+  return GAMC_OK;
+}
+
+// am_mode 1 hand-over: B.Lc = chol(inv(G)) = U^-T of the current point
+gamc_status launch_seed_factor(gamc_ctx* h) {
+  gamc_status s = launch_inverse(h, false);
+  if (s != GAMC_OK) return s;
+  ProfScope ps(h, GAMC_K_LINALG);
+  const int p = h->p;
+  k_w_to_l<<<std::min(1024, (p * p + 255) / 256), 256, 0, h->stream>>>(h->B.W, p, h->B.Lc, h->B.rdiagL);
+  CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
 }
 
@@ -470,6 +516,7 @@ gamc_status gamc_set_stream(gamc_handle h, void* cuda_stream) {
   if (h->own_stream) cudaStreamDestroy(h->stream);
   h->stream = (cudaStream_t)cuda_stream;
   h->own_stream = false;
+  apply_l2_policy(h);
   return GAMC_OK;
 }
 
@@ -635,14 +682,12 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
 
   Bufs& B = h->B;
   B = Bufs{};
-  CUDA_TRY(h, cudaMalloc(&B.st, sizeof(DevState)));
+  B.st = h->d_state;
   const size_t pp = (size_t)p * p;
-  CUDA_TRY(h, cudaMalloc(&h->mats, sizeof(double) * pp * 7));
   CUDA_TRY(h, cudaMemsetAsync(h->mats, 0, sizeof(double) * pp * 7, h->stream));
   B.Gs = h->mats; B.Gstride = pp;
   B.U = h->mats + 2 * pp; B.Ustride = pp;
   B.C = h->mats + 4 * pp; B.Lc = h->mats + 5 * pp; B.W = h->mats + 6 * pp;
-  CUDA_TRY(h, cudaMalloc(&h->vecs, sizeof(double) * (size_t)p * 12));
   CUDA_TRY(h, cudaMemsetAsync(h->vecs, 0, sizeof(double) * (size_t)p * 12, h->stream));
   double* v = h->vecs;
   B.gs = v; v += 2 * p; B.rdiagU = v; v += 2 * p; B.fterm = v; v += 2 * p;
@@ -751,8 +796,18 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
       s = eval_device(h, B.theta_prop, 2, true); if (s != GAMC_OK) return s;             // :37
       s = launch_step(h, k_smmala_post, B, T, ti); if (s != GAMC_OK) return s;
     } else {                                                                             // :128
-      if (h->h_past) { s = launch_inverse(h); if (s != GAMC_OK) return s; }              // oldinvtensor = inv(G) seeds the recursion
-      s = launch_step(h, k_am_pre, B, T, ti); if (s != GAMC_OK) return s;
+      if (T.am_mode == 1) {
+        if (h->h_past) { s = launch_seed_factor(h); if (s != GAMC_OK) return s; }        // chol(oldinvtensor) = U^-T seeds the update
+        {
+          const int nbuf = am_r1_nbuf(h->p);
+          ProfScope ps(h, GAMC_K_LINALG);
+          k_am_pre_r1<<<1, LA_THREADS, am_r1_smem_bytes(h->p, nbuf), h->stream>>>(B, T, ti, nbuf);
+          CUDA_TRY(h, cudaGetLastError());
+        }
+      } else {
+        if (h->h_past) { s = launch_inverse(h); if (s != GAMC_OK) return s; }            // oldinvtensor = inv(G) seeds the recursion
+        s = launch_step(h, k_am_pre, B, T, ti); if (s != GAMC_OK) return s;
+      }
       s = eval_device(h, B.theta_prop, 0, true); if (s != GAMC_OK) return s;             // :148
       s = launch_step(h, k_am_post, B, T, ti); if (s != GAMC_OK) return s;
     }
@@ -831,6 +886,10 @@ gamc_status gamc_get_array(gamc_handle h, int32_t array_id, double* out) {
     case GAMC_ARR_PROPOSED_VALUE: src = B.theta_prop; break;
     case GAMC_ARR_OLDINVTENSOR:
       if (h->h_past || h->h_count == 0) { gamc_status s = launch_inverse(h); if (s != GAMC_OK) return s; }
+      else if (h->tune.am_mode == 1) {   // AM covariance is kept in factored form: C = L L'
+        k_llt<<<std::min(1024, (p * p + 255) / 256), 256, 0, h->stream>>>(B.Lc, p, B.C);
+        CUDA_TRY(h, cudaGetLastError());
+      }
       src = B.C; n = pp; break;
     case GAMC_ARR_CHOLINVTENSOR: {
       // L = U^-T: L(a,b) = W(p-1-b, p-1-a) with W = Lm^-1 (M space); data movement only on the host

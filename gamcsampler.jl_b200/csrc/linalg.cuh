@@ -17,7 +17,7 @@
 
 namespace gamc {
 
-constexpr int LA_THREADS = 1024;
+constexpr int LA_THREADS = 512;   // 128 registers per thread: the 32-wide row fragments stay in registers
 constexpr int LA_NB = 32;
 constexpr int LA_DLD = 33;  // padded leading dimension of the 32 x 32 diagonal block in shared memory
 
@@ -70,8 +70,8 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, LaScratch S, int* 
     const int nb = min(LA_NB, p - kb);
     const int m = p - kb - nb;
     // (a) diagonal block -> shared
-    {
-      const int r = tid & 31, c = tid >> 5;
+    for (int e = tid; e < LA_NB * LA_NB; e += LA_THREADS) {
+      const int r = e & 31, c = e >> 5;
       if (r < nb && c < nb && r >= c) S.D[r * LA_DLD + c] = A(kb + r, kb + c);
     }
     __syncthreads();
@@ -103,11 +103,11 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, LaScratch S, int* 
     __syncthreads();
     if (S.flag[0]) break;
     // write back the factored diagonal block and the reciprocal diagonal
-    {
-      const int r = tid & 31, c = tid >> 5;
+    for (int e = tid; e < LA_NB * LA_NB; e += LA_THREADS) {
+      const int r = e & 31, c = e >> 5;
       if (r < nb && c < nb && r >= c) A(kb + r, kb + c) = S.D[r * LA_DLD + c];
-      if (tid < nb) rdiag[kb + tid] = S.rd[tid];
     }
+    if (tid < nb) rdiag[kb + tid] = S.rd[tid];
     if (m > 0) {
       // (c) panel solve: row i = kb+nb+t, x = a Lkk^-T, one row per thread
       for (int t = tid; t < m; t += LA_THREADS) {
@@ -200,8 +200,8 @@ __device__ void trsv_lower(MatView<REV> L, const double* rdiag, double* b, LaScr
   const int p = L.p;
   for (int kb = 0; kb < p; kb += LA_NB) {
     const int nb = min(LA_NB, p - kb);
-    {
-      const int r = tid & 31, c = tid >> 5;
+    for (int e = tid; e < LA_NB * LA_NB; e += LA_THREADS) {
+      const int r = e & 31, c = e >> 5;
       if (r < nb && c < nb && r > c) S.D[r * LA_DLD + c] = L(kb + r, kb + c);
     }
     __syncthreads();
@@ -238,8 +238,8 @@ __device__ void trsv_lower_t(MatView<REV> L, const double* rdiag, double* b, LaS
   for (int blk = nblk - 1; blk >= 0; --blk) {
     const int kb = blk * LA_NB;
     const int nb = min(LA_NB, p - kb);
-    {
-      const int r = tid & 31, c = tid >> 5;
+    for (int e = tid; e < LA_NB * LA_NB; e += LA_THREADS) {
+      const int r = e & 31, c = e >> 5;
       if (r < nb && c < nb && r > c) S.D[r * LA_DLD + c] = L(kb + r, kb + c);
     }
     __syncthreads();

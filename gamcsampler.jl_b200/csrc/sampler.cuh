@@ -331,6 +331,207 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre(Bufs B, TuneCfg T, lon
 }
 
 // ---------------------------------------------------------------------------------------------------
+// AM branch, part 1, fast path (am_mode = 1).  With m1 = (k m2 + x)/(k+1) (how lastmean is maintained,
+// iterate/GAMC.jl:193-195) Klara's three-term recursion is algebraically the rank-one update
+//     C_k = ((k-1)/k) C_{k-1} + u u',   u = (x - m2)/sqrt(k+1),
+// so the factor the proposal needs is  chol(C_k) = (a L) chol(I + w w'),  a = sqrt((k-1)/k), (a L) w = u,
+// and chol(I + w w') has the closed form (s_j = 1 + sum_{i<j} w_i^2)
+//     K_jj = sqrt(s_{j+1}/s_j),   K_ij = w_i w_j / sqrt(s_j s_{j+1})  (i > j),
+// which gives, with the running partial products P_ij = sum_{k<=j} a L_ik w_k (the same quantity the forward
+// substitution for w needs),
+//     L'_ij = a L_ij K_jj + g_j (u_i - P_ij),   g_j = w_j / sqrt(s_j s_{j+1}).
+// One ascending sweep over 32-column panels does the triangular solve, the prefix sums, the O(p^2) update and
+// the proposal product L' z: no sqrt/divide on a dependent chain, L read once and written once.  Panels are
+// staged in shared memory with cp.async (double-buffered) so the single CTA is bound by throughput, not by
+// memory latency.  B.Lc holds chol(C) (unscaled by eps; the proposal is theta + sqrt(eps) L z).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__host__ __device__ inline size_t am_r1_smem_bytes(int p, int nbuf) {
+  const int pp = (p + 3) & ~3;
+  return sizeof(double) * ((size_t)nbuf * 32 * pp + 2 * (size_t)pp + 4 * 32 + 2 * 32 * 33 + 32 + 64);
+}
+__host__ __device__ inline int am_r1_nbuf(int p) { return am_r1_smem_bytes(p, 2) <= 200 * 1024 ? 2 : 1; }
+
+__global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, long long tape_idx, int nbuf) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  DevState* st = B.st;
+  const int p = T.p, pp = (p + 3) & ~3;
+  if (st->error_flag) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* panel = reinterpret_cast<double*>(smem_raw);          // [nbuf][32][pp]  (column-major: element (row, jj) at jj*pp + row)
+  double* zs = panel + (size_t)nbuf * 32 * pp;                   // z
+  double* bw = zs + 2 * (size_t)pp;                              // per-block: w[32], Kd[32], g[32], sigma
+  double* Ls = bw + 4 * 32;                                      // [32][33] a*L of the diagonal block (transposed scratch)
+  double* Ts = Ls + 32 * 33;                                     // [32][33] residuals u_i - P_ij of the diagonal block
+  double* accd = Ts + 32 * 33;                                   // [32] proposal-product contributions of the diagonal block
+  int* flag = reinterpret_cast<int*>(accd + 32);
+  if (tid == 0) {
+    st->count += 1;
+    if (T.tuning) st->tot_prop += 1;
+    if (T.verbose_am) st->am_prop += 1;
+    flag[0] = 0;
+  }
+  const int nblk = (p + 31) >> 5;
+  // cp.async staging of panel b by the threads [t0, t0 + nt) (each thread waits for its own groups)
+  auto issue_panel = [&](int b, int t, int nt) {
+    const int j0 = b << 5, nb = min(32, p - j0), rows = p - j0;
+    double* dst = panel + (size_t)(b % nbuf) * 32 * pp;
+    const double* src = B.Lc + (size_t)j0 + (size_t)j0 * p;
+    if ((p & 1) == 0) {   // 16-byte copies: column starts are 16-byte aligned when p is even (j0 is a multiple of 32)
+      for (int jj = 0; jj < nb; ++jj)
+        for (int r = 2 * t; r < rows; r += 2 * nt) cp_async16(dst + (size_t)jj * pp + r, src + (size_t)jj * p + r);
+    } else {
+      for (int jj = 0; jj < nb; ++jj)
+        for (int r = t; r < rows; r += nt) cp_async8(dst + (size_t)jj * pp + r, src + (size_t)jj * p + r);
+    }
+  };
+  issue_panel(0, tid, LA_THREADS);
+  cp_async_commit();
+  __syncthreads();
+  const long long t = st->count;
+  const double k = (double)(t - 2);
+  if (!(k > 1.0)) { cp_async_wait<0>(); raise_error(st, 3, 1); return; }    // C_1 = u u' has rank one: the reference's chol throws
+  const double alpha = sqrt((k - 1.0) / k), beta = 1.0 / sqrt(k + 1.0), ralpha = 1.0 / alpha;
+  const double* z = B.tape_z + (size_t)tape_idx * p;
+  const int i = tid;
+  double th = 0.0, ui = 0.0, P = 0.0, acc = 0.0, rdv = 0.0;
+  if (i < p) {
+    th = B.theta[i];
+    ui = (th - B.secondlastmean[i]) * beta;
+    rdv = B.rdiagL[i] * ralpha;          // 1 / (a L_ii)
+    zs[i] = z[i];
+  }
+  double sigma = 1.0;                     // s_{j0}: carried by every thread identically
+  for (int b = 0; b < nblk; ++b) {
+    const int j0 = b << 5, nb = min(32, p - j0);
+    cp_async_wait<0>();
+    __syncthreads();                      // panel b has landed; everybody is done with block b-1
+    const double* pan = panel + (size_t)(b % nbuf) * 32 * pp;
+    if (warp == b) {
+      // ---- diagonal block (one warp, lane = row j0+lane): forward substitution for w.
+      // Dependent chain per column = mul -> shfl -> fma.  The residual after column jj is exactly
+      // u_i - P_i,jj, the factor the update needs: park it (and a*L) in transposed scratch for the helpers.
+      double lrow[32];
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        lrow[jj] = (jj <= lane && jj < nb && i < p) ? alpha * pan[(size_t)jj * pp + lane] : 0.0;
+        Ls[jj * 33 + lane] = lrow[jj];
+      }
+      double res = ui - P, wmine = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        if (jj < nb) {
+          const double wj = __shfl_sync(0xffffffffu, res * rdv, jj);          // w_j = (u_j - P_j)/(a L_jj)
+          if (lane == jj) wmine = wj;
+          res = fma(-lrow[jj], wj, res);                                      // lrow[jj] = 0 for jj > lane
+          Ts[jj * 33 + lane] = res;
+        }
+      }
+      P = ui - res;
+      // prefix sums s_j and the closed-form factor entries, one column per lane (no serial sqrt/divide)
+      double sc = wmine * wmine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const double n = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += n; }
+      const double incl = sigma + sc, excl = incl - wmine * wmine;
+      const double rs = rsqrt(excl * incl);
+      bw[lane] = wmine; bw[32 + lane] = incl * rs; bw[64 + lane] = wmine * rs;
+      const double snew = __shfl_sync(0xffffffffu, incl, nb - 1);
+      if (lane == 0) bw[96] = snew;
+    } else if (nbuf > 1 && b + 1 < nblk) {
+      // ---- meanwhile the other warps stage the next panel
+      const int t2 = (warp < b ? warp : warp - 1) * 32 + lane;
+      issue_panel(b + 1, t2, LA_THREADS - 32);
+    }
+    cp_async_commit();
+    __syncthreads();
+    sigma = bw[96];
+    if (i >= j0 + 32 && i < p) {
+      // ---- rows below the diagonal block: one thread per row, residual res = u_i - P_i carried in a register
+      const double* prow = pan + (i - j0);
+      double* out = B.Lc + (size_t)i + (size_t)j0 * p;
+      double res = ui - P, a0 = 0.0, a1 = 0.0;
+      if (nb == 32) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const double l = alpha * prow[(size_t)jj * pp];
+          res = fma(-l, bw[jj], res);
+          const double ln = fma(l, bw[32 + jj], bw[64 + jj] * res);
+          out[(size_t)jj * p] = ln;
+          if (jj & 1) a1 = fma(ln, zs[j0 + jj], a1); else a0 = fma(ln, zs[j0 + jj], a0);
+        }
+      } else {
+        for (int jj = 0; jj < nb; ++jj) {
+          const double l = alpha * prow[(size_t)jj * pp];
+          res = fma(-l, bw[jj], res);
+          const double ln = fma(l, bw[32 + jj], bw[64 + jj] * res);
+          out[(size_t)jj * p] = ln;
+          a0 = fma(ln, zs[j0 + jj], a0);
+        }
+      }
+      P = ui - res;
+      acc += a0 + a1;
+    } else if (warp <= b) {
+      // ---- meanwhile the warps that own no rows below update the diagonal block itself:
+      // row r per warp, lane = column:  L'_rj = l K_jj + g_j (u_r - P_rj) for j <= r, independent per element.
+      for (int r = warp; r < nb; r += b + 1) {
+        const int gi = j0 + r;
+        double contrib = 0.0;
+        if (lane <= r && lane < nb) {
+          const double ln = fma(Ls[lane * 33 + r], bw[32 + lane], bw[64 + lane] * Ts[lane * 33 + r]);
+          B.Lc[(size_t)gi + (size_t)(j0 + lane) * p] = ln;
+          contrib = ln * zs[j0 + lane];
+          if (lane == r) B.rdiagL[gi] = 1.0 / ln;
+        }
+        contrib = warp_sum(contrib);
+        if (lane == 0) accd[r] = contrib;
+      }
+    }
+    __syncthreads();
+    if (warp == b && i < p) acc += accd[lane];
+    if (nbuf == 1 && b + 1 < nblk) issue_panel(b + 1, tid, LA_THREADS);
+  }
+  const int fin = isfinite(sigma) ? 0 : 1;
+  if (__syncthreads_or(fin)) { raise_error(st, 3, 1); return; }
+  if (i < p) {
+    const double umix = B.tape_umix[tape_idx];
+    if (umix <= 1.0 - T.c) B.theta_prop[i] = th + st->sqrtstep * acc;       // core component  N(theta, eps C)
+    else B.theta_prop[i] = th + T.sqrtminorscale * zs[i];                   // stabilising component
+  }
+}
+
+// chol(inv(G)) = U^-T as a natural-order lower factor:  L(a,b) = W(p-1-b, p-1-a), W = Lm^-1 (k_triinv).
+__global__ void __launch_bounds__(256) k_w_to_l(const double* __restrict__ W, int p, double* __restrict__ L, double* __restrict__ rdiagL) {
+  const size_t n = (size_t)p * p;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int a = (int)(e % p), b = (int)(e / p);
+    const double v = (a >= b) ? W[(size_t)(p - 1 - b) + (size_t)(p - 1 - a) * p] : 0.0;
+    L[e] = v;
+    if (a == b) rdiagL[a] = 1.0 / v;
+  }
+}
+
+// C = s * L L' (state read-out of sstate.oldinvtensor in am_mode 1); one thread per entry.
+__global__ void __launch_bounds__(256) k_llt(const double* __restrict__ L, int p, double* __restrict__ C) {
+  const size_t n = (size_t)p * p;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int a = (int)(e % p), b = (int)(e / p);
+    const int m = min(a, b);
+    double s = 0.0;
+    for (int k = 0; k <= m; ++k) s = fma(L[(size_t)a + (size_t)k * p], L[(size_t)b + (size_t)k * p], s);
+    C[e] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // AM branch, part 2 (iterate/GAMC.jl:148-191 + tail).  The two GMM log-densities (:152,156) use the same
 // covariance with the roles of theta and theta* exchanged; d -> -d gives bit-identical quadratic forms and
 // log-sum-exp, so they cancel exactly and the device omits them (the oracle evaluates both literally and

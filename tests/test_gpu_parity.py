@@ -91,11 +91,13 @@ def _run_both(gamc, engine, N, p, nsteps, burnin, seed, am_mode=0, update=None, 
     return job, chain, osam, v, a, k
 
 
-@pytest.mark.parametrize("N,p,nsteps", [(200, 4, 3000), (500, 33, 1200), (2000, 64, 1000)])
-def test_trajectory_parity(gamc, engine, N, p, nsteps):
-    """Same host-drawn normals and uniforms => step-for-step agreement for >= 1000 iterations."""
+@pytest.mark.parametrize("am_mode", [0, 1])
+@pytest.mark.parametrize("N,p,nsteps", [(200, 4, 3000), (500, 33, 1200), (2000, 64, 1000), (3000, 130, 1000)])
+def test_trajectory_parity(gamc, engine, N, p, nsteps, am_mode):
+    """Same host-drawn normals and uniforms => step-for-step agreement for >= 1000 iterations.
+    am_mode 0 = literal covariance recursion + Cholesky per AM step; 1 = rank-one Cholesky update (fast path)."""
     burnin = nsteps // 5
-    job, chain, osam, v, a, k = _run_both(gamc, engine, N, p, nsteps, burnin, seed=42)
+    job, chain, osam, v, a, k = _run_both(gamc, engine, N, p, nsteps, burnin, seed=42, am_mode=am_mode)
     assert chain.value.shape == v.shape
     assert np.array_equal(chain.diagnosticvalues.ravel(), a), "accept/reject decisions diverged"
     assert relerr(chain.value, v) <= 1e-8
@@ -135,6 +137,15 @@ def test_state_arrays_parity(gamc, engine):
     assert relerr(eng.array(7), osam.oldfirstterm) <= 1e-9
     assert relerr(eng.array(2), osam.G) <= 1e-10
     assert relerr(eng.array(1), osam.grad) <= 1e-10
+
+
+@pytest.mark.parametrize("am_mode", [0, 1])
+def test_am_covariance_readout(gamc, engine, am_mode):
+    """sstate.oldinvtensor after a run that ends in AM steps = the Haario covariance recursion seeded with inv(G)."""
+    job, chain, osam, v, a, k = _run_both(gamc, engine, 400, 9, 60, 0, seed=4, am_mode=am_mode, update=gamc.mod_update(7))
+    assert osam.last_kind == "am"
+    assert np.array_equal(chain.diagnosticvalues.ravel(), a)
+    assert relerr(job.engine.array(5), osam.oldinvtensor) <= 1e-9
 
 
 def test_errors(gamc, engine):
