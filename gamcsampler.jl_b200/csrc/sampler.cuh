@@ -479,10 +479,11 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, 
       }
       P = ui - res;
       acc += a0 + a1;
-    } else if (warp <= b) {
-      // ---- meanwhile the warps that own no rows below update the diagonal block itself:
-      // row r per warp, lane = column:  L'_rj = l K_jj + g_j (u_r - P_rj) for j <= r, independent per element.
-      for (int r = warp; r < nb; r += b + 1) {
+    }
+    {
+      // ---- the diagonal block itself, spread over all warps (row r per warp, lane = column):
+      // L'_rj = l K_jj + g_j (u_r - P_rj) for j <= r, independent per element.
+      for (int r = warp; r < nb; r += LA_THREADS / 32) {
         const int gi = j0 + r;
         double contrib = 0.0;
         if (lane <= r && lane < nb) {

@@ -1,0 +1,137 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol, the front-end
+builds the right config, product-side statistics agree with the oracle, and the multi-process (gloo, world_size 2)
+sharding path reduces to the single-process result."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as o
+from util import relerr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "gamc_b200.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gamc_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(gamc):
+    lib = gamc._lib.load()
+    syms = _declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"libgamc_b200.so does not export {s}"
+        assert s in gamc._lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert set(gamc._lib.SIGNATURES) == set(syms)
+    assert lib.gamc_version().decode().endswith("sm_100a")
+
+
+def test_struct_layouts_match_the_header(gamc, tmp_path):
+    """Compile the header with gcc (plain C: the ABI must not need C++) and compare struct sizes / offsets with ctypes."""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gamc_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(gamc_config), sizeof(gamc_state_scalars), '
+                   'offsetof(gamc_config, nsteps), offsetof(gamc_config, am_mode), offsetof(gamc_state_scalars, chain_saved));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    C, S = gamc._lib.Config, gamc._lib.StateScalars
+    assert [int(x) for x in out] == [ctypes.sizeof(C), ctypes.sizeof(S), C.nsteps.offset, C.am_mode.offset, S.chain_saved.offset]
+
+
+def test_no_cpu_fallback(gamc):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(gamc._lib.CudaError):
+        gamc.Engine(0)
+
+
+def test_frontend_config_mirrors_reference_defaults(gamc):
+    s = gamc.GAMC()
+    assert (s.driftstep, s.minorscale, s.c, s.t0, s.update.name) == (1.0, 1.0, 0.05, 3, "rand_update!")
+    for bad in (dict(driftstep=0.0), dict(minorscale=0.0), dict(c=-0.1), dict(t0=0)):
+        with pytest.raises(AssertionError):
+            gamc.GAMC(**bad)
+    tuner = gamc.GAMCTuner(gamc.VanillaMCTuner(), gamc.VanillaMCTuner(verbose=True), gamc.AcceptanceRateMCTuner(0.35))
+    assert tuner.verbose and repr(tuner) == "GAMCTuner"
+    cfg = gamc.frontend.make_config(gamc.GAMC(update=gamc.rand_exp_decay_update(10.0), driftstep=0.02, minorscale=0.001, c=0.01), tuner,
+                                    gamc.BasicMCRange(110000, 10000))
+    assert (cfg.schedule, cfg.sched_params[0], cfg.total_tuner_kind, cfg.targetrate, cfg.score_k, cfg.period) == (5, 10.0, 1, 0.35, 7.0, 100)
+    assert (cfg.nsteps, cfg.burnin, cfg.verbose_am, cfg.verbose_smmala) == (110000, 10000, 1, 0)
+    assert "drift step = 0.02" in repr(gamc.GAMC(driftstep=0.02))
+    # decay functions of the front-end are the reference's (src/stats/schedule.jl:1-7)
+    for f in ("exp_decay", "lin_decay", "pow_decay", "quad_decay"):
+        assert getattr(gamc, f)(7, 90) == getattr(o, f)(7, 90)
+
+
+def test_product_stats_match_oracle(gamc):
+    rng = np.random.default_rng(0)
+    x = np.cumsum(rng.standard_normal((3, 5000)), axis=1) * 0.01 + rng.standard_normal((3, 5000))
+    assert relerr(gamc.ess(x), o.ess(x, maxlag=4999)) < 1e-8
+    s = gamc.summary(x, rng.random(5000) < 0.3, 2.0)
+    assert s["efficiency"] == pytest.approx(s["ess"].min() / 2.0)
+
+
+def test_shard_rows_partition():
+    from gamc_b200.distributed import shard_rows
+    for N, w in ((10, 3), (1 << 20, 8), (7, 8)):
+        edges = [shard_rows(N, w, r) for r in range(w)]
+        assert edges[0][0] == 0 and edges[-1][1] == N
+        assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
+        assert max(b - a for a, b in edges) - min(b - a for a, b in edges) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, ROOT)
+    import oracle as oo
+    from gamc_b200.distributed import shard_rows, broadcast_unique_id
+    N, p = 2001, 6
+    tt = oo.logistic.synth_theta_true(9, p)
+    r0, r1 = shard_rows(N, world, rank)
+    X, y, _ = oo.synth_logistic(9, N, p, row0=r0, nrows=r1 - r0, theta_true=tt)      # this rank's shard only
+    ll, g, G = oo.logistic_partials(tt, X, y)
+    buf = torch.from_numpy(np.concatenate([[ll], g, G.ravel()]))
+    dist.all_reduce(buf)                                                            # the data-path collective (sum)
+
+    class FakeEngine:                                                               # unique-id plumbing without NCCL
+        @staticmethod
+        def comm_unique_id():
+            return np.arange(128, dtype=np.uint8)
+    uid = broadcast_unique_id(FakeEngine, rank, world)
+    q.put((rank, buf.numpy().copy(), uid.copy()))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_reduce_matches_whole():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    N, p = 2001, 6
+    X, y, tt = o.synth_logistic(9, N, p)
+    ll, g, G = o.logistic_partials(tt, X, y)
+    whole = np.concatenate([[ll], g, G.ravel()])
+    for rank, buf, uid in res:
+        assert relerr(buf, whole) < 1e-12
+        assert np.array_equal(uid, np.arange(128, dtype=np.uint8))
+    assert np.array_equal(res[0][1], res[1][1])      # every rank holds the bit-identical reduced payload
