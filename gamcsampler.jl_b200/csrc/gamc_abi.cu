@@ -83,7 +83,8 @@ struct gamc_ctx {
   double* part_ll = nullptr; double* part_g = nullptr;
   // metric
   MetricLayout layout; MetricPlan* d_plans = nullptr; TaskCoord* d_coords = nullptr;
-  int nkinds = 0, nsplit = 0, ntasks = 0; long long nslabs = 0; double* ws = nullptr;
+  int nkinds = 0, ntasks = 0, metric_grid = 0; long long nslabs = 0; double* ws = nullptr; int* d_ints = nullptr;
+  int *d_cta_kind = nullptr, *d_cta_split = nullptr, *d_kind_nsplit = nullptr, *d_task_nsplit = nullptr;
   // landing buffer of an evaluation = all-reduce payload [ll, g(p), pad, G(p x p)]
   double* R = nullptr; int goff = 0;
   double* theta_eval = nullptr;
@@ -196,7 +197,7 @@ void free_target(gamc_ctx* h) {
   h->dX = h->dy = nullptr; h->own_data = false;
   cudaFree(h->dw); h->dw = nullptr;
   cudaFree(h->part_ll); cudaFree(h->part_g); h->part_ll = h->part_g = nullptr;
-  cudaFree(h->d_plans); cudaFree(h->d_coords); cudaFree(h->ws); h->d_plans = nullptr; h->d_coords = nullptr; h->ws = nullptr;
+  cudaFree(h->d_plans); cudaFree(h->d_coords); cudaFree(h->ws); cudaFree(h->d_ints); h->d_plans = nullptr; h->d_coords = nullptr; h->ws = nullptr; h->d_ints = nullptr;
   cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0; h->R = nullptr; h->vecs = h->mats = nullptr; h->d_state = nullptr;
   cudaFree(h->theta_eval); h->theta_eval = nullptr;
 }
@@ -264,8 +265,8 @@ gamc_status launch_datapass(gamc_ctx* h, const double* theta, bool grad) {
 gamc_status launch_metric(gamc_ctx* h) {
   { gamc_status s = ensure_attr(h, (const void*)k_metric, sizeof(MetricSmem)); if (s != GAMC_OK) return s; }
   ProfScope ps(h, GAMC_K_METRIC);
-  k_metric<<<h->nkinds * h->nsplit, MT_THREADS, sizeof(MetricSmem), h->stream>>>(h->mapXB, h->mapW, h->d_plans, h->nkinds, h->nsplit,
-                                                                               h->nslabs, h->ws, h->ntasks);
+  k_metric<<<h->metric_grid, MT_THREADS, sizeof(MetricSmem), h->stream>>>(h->mapXB, h->mapW, h->d_plans, h->d_cta_kind, h->d_cta_split,
+                                                                        h->d_kind_nsplit, h->nslabs, h->ws, h->layout.max_nsplit);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
 }
@@ -275,7 +276,7 @@ gamc_status launch_reduce(gamc_ctx* h, int level) {
   ProfScope ps(h, GAMC_K_REDUCE);
   const int nblk = (level >= 2 ? h->ntasks * 4 : 0) + 1;
   k_reduce<<<nblk, 256, 0, h->stream>>>(h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, h->dp_grid, level >= 1,
-                                        level >= 2 ? h->ws : nullptr, h->d_coords, h->ntasks, h->nsplit);
+                                        level >= 2 ? h->ws : nullptr, h->d_coords, h->ntasks, h->d_task_nsplit, h->layout.max_nsplit);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
 }
@@ -339,12 +340,22 @@ gamc_status setup_target(gamc_ctx* h) {
   h->nkinds = (int)h->layout.plans.size();
   h->ntasks = (int)h->layout.coords.size();
   h->nslabs = (h->N + MT_SLAB - 1) / MT_SLAB;
-  h->nsplit = (int)std::max<long long>(1, std::min<long long>(h->num_sms / h->nkinds, h->nslabs));
+  assign_splits(h->layout, std::max(h->num_sms, h->nkinds), h->nslabs);
+  h->metric_grid = (int)h->layout.cta_kind.size();
+  {
+    std::vector<int> ints;
+    auto push = [&](const std::vector<int>& v) { size_t off = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); return off; };
+    const size_t o1 = push(h->layout.cta_kind), o2 = push(h->layout.cta_split), o3 = push(h->layout.kind_nsplit), o4 = push(h->layout.task_nsplit);
+    CUDA_TRY(h, cudaMalloc(&h->d_ints, sizeof(int) * ints.size()));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_ints, ints.data(), sizeof(int) * ints.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->d_cta_kind = h->d_ints + o1; h->d_cta_split = h->d_ints + o2; h->d_kind_nsplit = h->d_ints + o3; h->d_task_nsplit = h->d_ints + o4;
+  }
   CUDA_TRY(h, cudaMalloc(&h->d_plans, sizeof(MetricPlan) * h->nkinds));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_plans, h->layout.plans.data(), sizeof(MetricPlan) * h->nkinds, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMalloc(&h->d_coords, sizeof(TaskCoord) * h->ntasks));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_coords, h->layout.coords.data(), sizeof(TaskCoord) * h->ntasks, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaMalloc(&h->ws, sizeof(double) * (size_t)h->nsplit * h->ntasks * MT_BLK * MT_BLK));
+  CUDA_TRY(h, cudaMalloc(&h->ws, sizeof(double) * (size_t)h->layout.max_nsplit * h->ntasks * MT_BLK * MT_BLK));
   h->goff = (1 + p + 1) & ~1;  // G starts 16-byte aligned
   {
     const size_t pp = (size_t)p * p;

@@ -70,12 +70,12 @@ __device__ __forceinline__ void metric_slab(const double* __restrict__ A, const 
 
 __global__ void __launch_bounds__(MT_THREADS, 1)
 k_metric(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
-         const MetricPlan* __restrict__ plans, int nkinds, int nsplit, long long nslabs,
-         double* __restrict__ ws, int ntasks_total) {
+         const MetricPlan* __restrict__ plans, const int* __restrict__ cta_kind, const int* __restrict__ cta_split,
+         const int* __restrict__ kind_nsplit, long long nslabs, double* __restrict__ ws, int max_nsplit) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   MetricSmem& S = *reinterpret_cast<MetricSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kind = blockIdx.x % nkinds, split = blockIdx.x / nkinds;
+  const int kind = cta_kind[blockIdx.x], split = cta_split[blockIdx.x], nsplit = kind_nsplit[kind];
 
   {
     const int* src = reinterpret_cast<const int*>(&plans[kind]);
@@ -128,8 +128,8 @@ k_metric(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
   }
 
   {
-    // partial tile -> workspace [split][task][32 x 32 row-major]
-    double* out = ws + ((size_t)split * ntasks_total + S.plan.task_id[warp]) * (MT_BLK * MT_BLK);
+    // partial tile -> workspace [task][split][32 x 32 row-major]
+    double* out = ws + ((size_t)S.plan.task_id[warp] * max_nsplit + split) * (MT_BLK * MT_BLK);
     const int g = lane >> 2, c = lane & 3;
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
@@ -152,7 +152,8 @@ struct TaskCoord { int bi, bj; };
 __global__ void __launch_bounds__(256)
 k_reduce(double* __restrict__ E, int p, int goff,
          const double* __restrict__ part_ll, const double* __restrict__ part_g, int part_g_stride, int nparts,
-         int want_grad, const double* __restrict__ ws, const TaskCoord* __restrict__ coords, int ntasks, int nsplit) {
+         int want_grad, const double* __restrict__ ws, const TaskCoord* __restrict__ coords, int ntasks,
+         const int* __restrict__ task_nsplit, int max_nsplit) {
   const int nblk_tensor = ws ? ntasks * 4 : 0;  // 256 threads per block, 1024 elements per task
   if ((int)blockIdx.x < nblk_tensor) {
     const int task = blockIdx.x >> 2;
@@ -163,8 +164,9 @@ k_reduce(double* __restrict__ E, int p, int goff,
     const int gi = bi * MT_BLK + r, gj = bj * MT_BLK + c;
     if (gi >= p || gj >= p) return;
     double s = 0.0;
-    const double* src = ws + (size_t)task * (MT_BLK * MT_BLK) + e;
-    for (int k = 0; k < nsplit; ++k) s += src[(size_t)k * ntasks * (MT_BLK * MT_BLK)];
+    const double* src = ws + (size_t)task * max_nsplit * (MT_BLK * MT_BLK) + e;
+    const int nsplit = task_nsplit[task];
+    for (int k = 0; k < nsplit; ++k) s += src[(size_t)k * (MT_BLK * MT_BLK)];
     double* G = E + goff;
     G[gi + (size_t)gj * p] = s;
     G[gj + (size_t)gi * p] = s;
