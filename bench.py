@@ -38,12 +38,13 @@ FP64_DMMA_PEAK_TFLOPS_FALLBACK = 37.1   # profiles/r01_fp64_peak.txt (register-o
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--logN", type=int, default=20, help="log2 of rows per GPU (default 2^20 = BASELINE C2)")
     ap.add_argument("--p", type=int, default=256)
-    ap.add_argument("--am-mode", type=int, default=int(os.environ.get("GAMC_AM_MODE", "0")))
+    ap.add_argument("--am-mode", type=int, default=int(os.environ.get("GAMC_AM_MODE", "1")),
+                    help="1 = rank-one Cholesky update per AM step (default), 0 = literal covariance recursion + Cholesky")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -192,7 +193,8 @@ def run_reference(args):
         "impl": "reference", "metric": "gamc_iters_per_sec", "value": rate, "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (NumPy PCG64 N(0,1) design, Bernoulli labels)",
-        "config": {"workload": f"C2: logistic N=2^{args.logN}, p={p}, GAMC exp-decay(a=10), single chain", "rows": N, "p": p},
+        "config": {"workload": f"C2: logistic N=2^{args.logN} rows per GPU, p={p}, FP64, GAMC rand_exp_decay(a=10), single chain", "rows_per_gpu": N, "p": p,
+                   "value_definition": "iters/s x n_gpus (weak scaling: the CPU arm is timed on one 2^20-row shard; a CPU job on n_gpus shards is n_gpus times slower per iteration)"},
         "cpu_baseline": {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample,
                          "per_kind_seconds": costs, "datagen_s": gen_s},
         "e2e": {"value": rate, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -324,7 +326,7 @@ def run_ours(args):
             t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": world * K / dt, "unit": "shard-iters/s", "iters_per_sec": K / dt, "h2d_bytes_per_step": 8 * (p + 3),
+        e2e = {"value": world * K / dt, "unit": "iters/s", "iters_per_sec": K / dt, "h2d_bytes_per_step": 8 * (p + 3),
                "d2h_bytes_per_step": (8 * p + 1) * (K - K // 5) / K, "acceptance": float(chain.diagnosticvalues.mean()),
                "what": "BasicMCJob.run()+output(): gamc_tape_set(host pinned tape) + gamc_run + gamc_chain_get(host chain); "
                        "the design matrix is resident (uploaded/generated once per job, as the reference passes it once at job construction)"}
@@ -342,7 +344,7 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": "gamc_iters_per_sec", "value": world * iters_per_sec, "unit": "shard-iters/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": "gamc_iters_per_sec", "value": world * iters_per_sec, "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (Philox4x32-10 keyed by global row/col, generated on device)",
             "config": {"workload": f"C2: logistic N=2^{args.logN} rows per GPU, p={p}, FP64, GAMC rand_exp_decay(a=10), single chain",

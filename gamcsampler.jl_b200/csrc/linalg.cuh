@@ -75,29 +75,37 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, LaScratch S, int* 
       if (r < nb && c < nb && r >= c) S.D[r * LA_DLD + c] = A(kb + r, kb + c);
     }
     __syncthreads();
-    // (b) factor the diagonal block with warp 0 (left-looking, lane = row)
+    // (b) factor the diagonal block with warp 0: right-looking, lane = row, the row lives in registers; the
+    //     freshly scaled column is broadcast through shared memory.  Dependent chain per column:
+    //     shfl -> rsqrt -> mul -> (sts/lds) -> fma; no divide, no sqrt, the logarithms are taken in parallel afterwards.
     if (warp == 0) {
       const int r = lane;
+      double a[LA_NB];
+#pragma unroll
+      for (int c = 0; c < LA_NB; ++c) a[c] = (c <= r && r < nb && c < nb) ? S.D[r * LA_DLD + c] : 0.0;
       int bad = 0;
-      for (int j = 0; j < nb; ++j) {
-        double s0 = (r >= j && r < nb) ? S.D[r * LA_DLD + j] : 0.0, s1 = 0.0;
-        if (r >= j && r < nb) {
-          int k = 0;
-          for (; k + 1 < j; k += 2) {
-            s0 = fma(-S.D[r * LA_DLD + k], S.D[j * LA_DLD + k], s0);
-            s1 = fma(-S.D[r * LA_DLD + k + 1], S.D[j * LA_DLD + k + 1], s1);
-          }
-          if (k < j) s0 = fma(-S.D[r * LA_DLD + k], S.D[j * LA_DLD + k], s0);
+      double* colbuf = S.rd;   // LA_NB doubles, reused as the reciprocal diagonal at the end
+      double myrd = 0.0;
+#pragma unroll
+      for (int j = 0; j < LA_NB; ++j) {
+        if (j < nb) {
+          const double djj = __shfl_sync(0xffffffffu, a[j], j);
+          if (!(djj > 0.0) || !isfinite(djj)) { if (!bad) bad = kb + j + 1; }
+          const double rdv = rsqrt(djj);
+          const double l = a[j] * rdv;               // lane j: sqrt(d_jj); lanes > j: l_ij; lanes < j: 0
+          a[j] = l;
+          if (r == j) myrd = rdv;
+          colbuf[r] = l;
+          __syncwarp();
+#pragma unroll
+          for (int c = j + 1; c < LA_NB; ++c) a[c] = fma(-l, colbuf[c], a[c]);   // a[c] is zero (and stays unused) for c > r
+          __syncwarp();
         }
-        const double s = s0 + s1;
-        const double djj = __shfl_sync(0xffffffffu, s, j);
-        if (!(djj > 0.0) || !isfinite(djj)) { bad = kb + j + 1; break; }
-        const double d = sqrt(djj);
-        const double rdv = 1.0 / d;
-        if (r == j) { S.D[r * LA_DLD + j] = d; S.rd[j] = rdv; sumlog += log(d); }
-        else if (r > j && r < nb) S.D[r * LA_DLD + j] = s * rdv;
-        __syncwarp();
       }
+#pragma unroll
+      for (int c = 0; c < LA_NB; ++c) if (c <= r && r < nb && c < nb) S.D[r * LA_DLD + c] = a[c];
+      __syncwarp();
+      if (r < nb) { S.rd[r] = myrd; sumlog -= log(myrd); }
       if (bad && lane == 0) S.flag[0] = bad;
     }
     __syncthreads();
@@ -118,13 +126,10 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, LaScratch S, int* 
 #pragma unroll
         for (int c = 0; c < LA_NB; ++c) {
           if (c < nb) {
-            double s0 = x[c], s1 = 0.0;
+            const double xc = x[c] * S.rd[c];
+            x[c] = xc;
 #pragma unroll
-            for (int k = 0; k < c; ++k) {
-              if (k & 1) s1 = fma(-x[k], S.D[c * LA_DLD + k], s1);
-              else s0 = fma(-x[k], S.D[c * LA_DLD + k], s0);
-            }
-            x[c] = (s0 + s1) * S.rd[c];
+            for (int k = c + 1; k < LA_NB; ++k) if (k < nb) x[k] = fma(-xc, S.D[k * LA_DLD + c], x[k]);
           }
         }
 #pragma unroll
