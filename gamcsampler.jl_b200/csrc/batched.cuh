@@ -1,0 +1,513 @@
+// batched.cuh -- batched-chains GAMC for small parameter dimension (p <= 32): many independent chains, ONE
+// persistent kernel launch for a whole run.  Each CTA owns one chain; its complete sampler state (theta, gradient,
+// metric, inverse metric, Cholesky factors, AM covariance, running means, tuner) lives in shared memory; the whole
+// `iterate!` loop of the reference (src/samplers/iterate/GAMC.jl:1-293) -- schedule coin, SMMALA or AM branch, target
+// evaluation, optional `transform` (Klara softabs), dense algebra, accept/reject, means, burn-in tuning, chain output --
+// runs inside the kernel, so there is no launch or synchronisation per iteration.
+//
+// Targets evaluated in the kernel:
+//   TARGET_MVT  multivariate-t target of examples/t_distribution/src/GAMC/simulations.jl:17-33 (closed-form gradient and
+//               Hessian in place of the reference's ForwardDiff sweep; tensor = -Hessian, then softabs(., alpha), :39)
+//   TARGET_RV   Keplerian radial-velocity target of examples/radial_velocity/src/*.jl (stat_model.jl:18-63), epochs spread
+//               over the CTA's threads, derivatives by second-order forward-mode dual numbers through the Kepler solver
+// Warp 0 (lane = coordinate) does the small dense algebra; matrices are row-major with an odd leading dimension.
+// Random numbers: a host tape (parity tests) or Philox4x32-10 keyed by (chain, iteration) (throughput mode).
+#pragma once
+#include "common.cuh"
+#include "synth.cuh"
+
+namespace gamc {
+
+constexpr int BT_MAXP = 32;
+
+struct BatchedCfg {
+  int p, ld;                    // dimension, leading dimension (odd)
+  int nchains;
+  int target;                   // 0 = mvt, 1 = rv
+  int transform;                // 0 = none, 1 = softabs
+  double softabs_alpha;
+  // sampler / tuner / range (same meaning as gamc_config)
+  double driftstep, minorscale, sqrtminorscale, c;
+  int t0, schedule; double sp0, sp1, sp2;
+  int tuning, count_total, is_accrate, verbose_sm, verbose_am, period;
+  long long nsteps, burnin;
+  double targetrate, score_k;
+  // mvt target
+  double nu, logconst; const double* Sinv;   // n x n row-major == column-major (symmetric)
+  // rv target
+  const double* rv_t; const double* rv_obs; const double* rv_sig; long long rv_n; int rv_npl;
+  // tape (may be null -> Philox with `seed`)
+  const double* tape_usched; const double* tape_umix; const double* tape_uacc; const double* tape_z;   // [chain][t] / [chain][t][p]
+  long long tape_len;           // iterations per chain on the tape
+  unsigned long long seed;
+  // output
+  double* chain_value; unsigned char* chain_accept; long long chain_cap;   // [chain][cap][p], [chain][cap]
+  double* blob; int blob_doubles;                                        // persistent per-chain state
+};
+
+// ---- per-chain state layout in shared memory (doubles) ------------------------------------------------------------
+enum { BV_THETA = 0, BV_PROP, BV_GC, BV_GP, BV_FC, BV_FP, BV_MU, BV_M1, BV_M2, BV_Z, BV_T1, BV_T2, BV_NVEC };
+enum { BM_GC = 0, BM_IC, BM_LC, BM_GP, BM_IP, BM_LP, BM_LAM, BM_W, BM_NMAT };
+enum { BS_LT = 0, BS_LTP, BS_LDC, BS_LDP, BS_STEP, BS_SQSTEP, BS_RATIO, BS_COUNT, BS_UPD, BS_TACC, BS_TPROP, BS_TTOT, BS_TRATE,
+       BS_SMACC, BS_SMPROP, BS_SMTOT, BS_AMACC, BS_AMPROP, BS_AMTOT, BS_PAST, BS_PRESENT, BS_ERR, BS_SAVED, BS_NSCAL = 24 };
+
+__host__ __device__ inline int bt_blob_doubles(int p, int ld) { return BS_NSCAL + BV_NVEC * BT_MAXP + BM_NMAT * p * ld; }
+
+struct BState {
+  double* s; double* v; double* m; int p, ld;
+  __device__ double* vec(int k) const { return v + k * BT_MAXP; }
+  __device__ double* mat(int k) const { return m + (size_t)k * p * ld; }
+};
+
+// =====================================================================================================
+// warp-level small dense algebra (all 32 lanes call; lane = row; p <= 32)
+// =====================================================================================================
+// in-place lower Cholesky; returns sum log L_ii, NaN on failure (uniform across the warp)
+__device__ inline double w_chol(double* A, int p, int ld, int lane) {
+  double slog = 0.0;
+  bool bad = false;
+  for (int j = 0; j < p; ++j) {
+    const double d = A[j * ld + j];
+    if (!(d > 0.0) || !isfinite(d)) { bad = true; break; }
+    const double rd = rsqrt(d);
+    slog += 0.5 * log(d);
+    if (lane == j) A[j * ld + j] = d * rd;
+    else if (lane > j && lane < p) A[lane * ld + j] *= rd;
+    __syncwarp();
+    if (lane > j && lane < p) {
+      const double lij = A[lane * ld + j];
+      for (int c = j + 1; c <= lane; ++c) A[lane * ld + c] = fma(-lij, A[c * ld + j], A[lane * ld + c]);
+    }
+    __syncwarp();
+  }
+  return bad ? nan("") : slog;
+}
+
+// Inv = (L L')^-1, lane j computes column j with two substitutions; W = p x ld scratch. Result symmetric (averaged).
+__device__ inline void w_inv_from_chol(const double* L, double* Inv, double* W, int p, int ld, int lane) {
+  if (lane < p) {
+    const int j = lane;
+    for (int i = 0; i < p; ++i) {            // L y = e_j
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s = fma(-L[i * ld + k], W[k * ld + j], s);
+      W[i * ld + j] = s / L[i * ld + i];
+    }
+    for (int i = p - 1; i >= 0; --i) {       // L' x = y
+      double s = W[i * ld + j];
+      for (int k = i + 1; k < p; ++k) s = fma(-L[k * ld + i], Inv[k * ld + j], s);
+      Inv[i * ld + j] = s / L[i * ld + i];
+    }
+  }
+  __syncwarp();
+  if (lane < p) for (int c = 0; c < lane; ++c) { const double a = 0.5 * (Inv[lane * ld + c] + Inv[c * ld + lane]); Inv[lane * ld + c] = a; Inv[c * ld + lane] = a; }
+  __syncwarp();
+}
+
+// y = A x (A p x p row-major, x/y length p); lane = row
+__device__ inline void w_matvec(const double* A, const double* x, double* y, int p, int ld, int lane) {
+  if (lane < p) {
+    double s = 0.0;
+    for (int j = 0; j < p; ++j) s = fma(A[lane * ld + j], x[j], s);
+    y[lane] = s;
+  }
+  __syncwarp();
+}
+// y = L x with L lower
+__device__ inline void w_trmv_lower(const double* L, const double* x, double* y, int p, int ld, int lane) {
+  if (lane < p) {
+    double s = 0.0;
+    for (int j = 0; j <= lane; ++j) s = fma(L[lane * ld + j], x[j], s);
+    y[lane] = s;
+  }
+  __syncwarp();
+}
+__device__ inline double w_dot(const double* a, const double* b, int p, int lane) {
+  double s = (lane < p) ? a[lane] * b[lane] : 0.0;
+  return warp_sum(s);
+}
+
+// Cyclic Jacobi eigen-decomposition of the symmetric matrix A (destroyed: eigenvalues end on its diagonal), Q = vectors.
+__device__ inline void w_jacobi(double* A, double* Q, int p, int ld, int lane) {
+  if (lane < p) for (int j = 0; j < p; ++j) Q[lane * ld + j] = (lane == j) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    if (lane < p) { for (int j = 0; j < p; ++j) { const double a = A[lane * ld + j]; if (j != lane) off = fma(a, a, off); else dg = a * a; } }
+    off = warp_sum(off); dg = warp_sum(dg);
+    if (off <= 1e-30 * dg || off == 0.0) break;
+    for (int pp = 0; pp < p - 1; ++pp) {
+      for (int qq = pp + 1; qq < p; ++qq) {
+        const double apq = A[pp * ld + qq];
+        if (apq == 0.0) continue;
+        const double app = A[pp * ld + pp], aqq = A[qq * ld + qq];
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+        const double c = rsqrt(fma(t, t, 1.0)), s = t * c;
+        __syncwarp();
+        if (lane < p) {
+          const int k = lane;
+          if (k != pp && k != qq) {
+            const double akp = A[k * ld + pp], akq = A[k * ld + qq];
+            const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+            A[k * ld + pp] = np_; A[pp * ld + k] = np_;
+            A[k * ld + qq] = nq_; A[qq * ld + k] = nq_;
+          }
+          const double qkp = Q[k * ld + pp], qkq = Q[k * ld + qq];
+          Q[k * ld + pp] = c * qkp - s * qkq;
+          Q[k * ld + qq] = s * qkp + c * qkq;
+        }
+        if (lane == 0) {
+          A[pp * ld + pp] = app - t * apq;
+          A[qq * ld + qq] = aqq + t * apq;
+          A[pp * ld + qq] = 0.0; A[qq * ld + pp] = 0.0;
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// Klara softabs: G <- Q diag(lam coth(alpha lam)) Q'; also Inv <- Q diag(1/f) Q' and returns logdet(G) = sum log f.
+// A holds the input (destroyed), Q scratch, outputs to G and Inv.
+__device__ inline double w_softabs(double* A, double* Q, double* G, double* Inv, double alpha, int p, int ld, int lane, double* fbuf) {
+  w_jacobi(A, Q, p, ld, lane);
+  double lf = 0.0;
+  if (lane < p) {
+    const double lam = A[lane * ld + lane];
+    const double x = alpha * lam;
+    const double f = (fabs(x) < 1e-8) ? 1.0 / alpha : lam / tanh(x);
+    fbuf[lane] = f;
+    lf = log(f);
+  }
+  lf = warp_sum(lf);
+  __syncwarp();
+  if (lane < p) {
+    for (int j = 0; j <= lane; ++j) {
+      double g = 0.0, iv = 0.0;
+      for (int k = 0; k < p; ++k) { const double qq = Q[lane * ld + k] * Q[j * ld + k]; g = fma(qq, fbuf[k], g); iv += qq / fbuf[k]; }
+      G[lane * ld + j] = g; G[j * ld + lane] = g;
+      Inv[lane * ld + j] = iv; Inv[j * ld + lane] = iv;
+    }
+  }
+  __syncwarp();
+  return lf;
+}
+
+// =====================================================================================================
+// targets
+// =====================================================================================================
+// multivariate t: lt = logconst - (nu+n)/2 log1p(q/nu), q = x'Sinv x; grad = -a v; tensor(-H) = a (Sinv - 2 v v'/(nu+q)), a = (nu+n)/(nu+q)
+__device__ inline double mvt_eval(const BatchedCfg& C, const double* x, double* g, double* H, double* vtmp, int level, int lane) {
+  const int p = C.p, ld = C.ld;
+  double vi = 0.0;
+  if (lane < p) for (int j = 0; j < p; ++j) vi = fma(C.Sinv[lane * p + j], x[j], vi);
+  const double q = warp_sum(lane < p ? vi * x[lane] : 0.0);
+  const double lt = C.logconst - 0.5 * (C.nu + p) * log1p(q / C.nu);
+  if (level >= 1) {
+    const double a = (C.nu + p) / (C.nu + q);
+    if (lane < p) { g[lane] = -a * vi; vtmp[lane] = vi; }
+    __syncwarp();
+    if (level >= 2 && lane < p) {
+      const double cc = 2.0 / (C.nu + q);
+      for (int j = 0; j < p; ++j) H[lane * ld + j] = a * (C.Sinv[lane * p + j] - cc * vi * vtmp[j]);
+    }
+    __syncwarp();
+  }
+  return lt;
+}
+
+// ---- second-order forward-mode dual numbers for the RV target (value, NP first and NP(NP+1)/2 second derivatives) -------
+template <int NP>
+struct Dual2 {
+  static constexpr int NH = NP * (NP + 1) / 2;
+  double v; double g[NP]; double h[NH];
+  __device__ static int hidx(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+};
+template <int NP> __device__ inline Dual2<NP> d_const(double c) { Dual2<NP> r; r.v = c; for (int i = 0; i < NP; ++i) r.g[i] = 0; for (int i = 0; i < Dual2<NP>::NH; ++i) r.h[i] = 0; return r; }
+template <int NP> __device__ inline Dual2<NP> d_var(double c, int k) { Dual2<NP> r = d_const<NP>(c); r.g[k] = 1.0; return r; }
+// y = f(x) with f' = f1, f'' = f2
+template <int NP> __device__ inline Dual2<NP> d_unary(const Dual2<NP>& x, double f0, double f1, double f2) {
+  Dual2<NP> r; r.v = f0;
+  for (int i = 0; i < NP; ++i) r.g[i] = f1 * x.g[i];
+  int k = 0;
+  for (int i = 0; i < NP; ++i) for (int j = 0; j <= i; ++j, ++k) r.h[k] = fma(f1, x.h[k], f2 * x.g[i] * x.g[j]);
+  return r;
+}
+template <int NP> __device__ inline Dual2<NP> operator+(const Dual2<NP>& a, const Dual2<NP>& b) { Dual2<NP> r; r.v = a.v + b.v; for (int i = 0; i < NP; ++i) r.g[i] = a.g[i] + b.g[i]; for (int i = 0; i < Dual2<NP>::NH; ++i) r.h[i] = a.h[i] + b.h[i]; return r; }
+template <int NP> __device__ inline Dual2<NP> operator-(const Dual2<NP>& a, const Dual2<NP>& b) { Dual2<NP> r; r.v = a.v - b.v; for (int i = 0; i < NP; ++i) r.g[i] = a.g[i] - b.g[i]; for (int i = 0; i < Dual2<NP>::NH; ++i) r.h[i] = a.h[i] - b.h[i]; return r; }
+template <int NP> __device__ inline Dual2<NP> operator*(const Dual2<NP>& a, const Dual2<NP>& b) {
+  Dual2<NP> r; r.v = a.v * b.v;
+  for (int i = 0; i < NP; ++i) r.g[i] = fma(a.v, b.g[i], b.v * a.g[i]);
+  int k = 0;
+  for (int i = 0; i < NP; ++i) for (int j = 0; j <= i; ++j, ++k) r.h[k] = a.v * b.h[k] + b.v * a.h[k] + a.g[i] * b.g[j] + a.g[j] * b.g[i];
+  return r;
+}
+template <int NP> __device__ inline Dual2<NP> operator*(double c, const Dual2<NP>& a) { Dual2<NP> r; r.v = c * a.v; for (int i = 0; i < NP; ++i) r.g[i] = c * a.g[i]; for (int i = 0; i < Dual2<NP>::NH; ++i) r.h[i] = c * a.h[i]; return r; }
+template <int NP> __device__ inline Dual2<NP> operator+(const Dual2<NP>& a, double c) { Dual2<NP> r = a; r.v += c; return r; }
+template <int NP> __device__ inline Dual2<NP> operator-(double c, const Dual2<NP>& a) { Dual2<NP> r; r.v = c - a.v; for (int i = 0; i < NP; ++i) r.g[i] = -a.g[i]; for (int i = 0; i < Dual2<NP>::NH; ++i) r.h[i] = -a.h[i]; return r; }
+template <int NP> __device__ inline Dual2<NP> d_recip(const Dual2<NP>& x) { const double r = 1.0 / x.v; return d_unary(x, r, -r * r, 2.0 * r * r * r); }
+template <int NP> __device__ inline Dual2<NP> operator/(const Dual2<NP>& a, const Dual2<NP>& b) { return a * d_recip(b); }
+template <int NP> __device__ inline Dual2<NP> d_sin(const Dual2<NP>& x) { double s, c; sincos(x.v, &s, &c); return d_unary(x, s, c, -s); }
+template <int NP> __device__ inline Dual2<NP> d_cos(const Dual2<NP>& x) { double s, c; sincos(x.v, &s, &c); return d_unary(x, c, -s, -c); }
+template <int NP> __device__ inline Dual2<NP> d_sqrt(const Dual2<NP>& x) { const double s = sqrt(x.v); return d_unary(x, s, 0.5 / s, -0.25 / (s * x.v)); }
+template <int NP> __device__ inline Dual2<NP> d_exp(const Dual2<NP>& x) { const double e = exp(x.v); return d_unary(x, e, e, e); }
+// atan2(y, x): via u = y/x is singular at x = 0; use the gradient of atan2 directly: d = (x dy - y dx)/(x^2+y^2)
+template <int NP> __device__ inline Dual2<NP> d_atan2(const Dual2<NP>& y, const Dual2<NP>& x) {
+  const Dual2<NP> r2 = x * x + y * y;
+  const Dual2<NP> ir2 = d_recip(r2);
+  const Dual2<NP> ay = x * ir2;              // d atan2 / dy
+  const Dual2<NP> ax = (-1.0) * (y * ir2);   // d atan2 / dx
+  Dual2<NP> r; r.v = atan2(y.v, x.v);
+  for (int i = 0; i < NP; ++i) r.g[i] = fma(ay.v, y.g[i], ax.v * x.g[i]);
+  int k = 0;
+  for (int i = 0; i < NP; ++i) for (int j = 0; j <= i; ++j, ++k)
+    r.h[k] = ay.v * y.h[k] + ax.v * x.h[k] + ay.g[j] * y.g[i] + ax.g[j] * x.g[i];
+  return r;
+}
+
+}  // namespace gamc
+
+namespace gamc {
+
+// =====================================================================================================
+// the persistent batched-chains kernel
+// =====================================================================================================
+__device__ inline bool bt_schedule(const BatchedCfg& C, long long i, double u) {
+  const double di = (double)i, dt = (double)C.nsteps;
+  auto par = [](double v, double d) { return isnan(v) ? d : v; };
+  switch (C.schedule) {
+    case 0: return false;
+    case 1: return true;
+    case 2: { const long long n = (long long)par(C.sp0, 10.0); return n > 0 && (i % n) == 0; }
+    case 3: return u <= par(C.sp0, 0.5);
+    case 4: return u <= par(C.sp1, 0.2) * cos(par(C.sp0, 10.0) * di * 3.14159265358979323846 / dt) + par(C.sp2, 0.2);
+    case 5: { const double b = par(C.sp1, 0.0); return u <= (1 - b) * exp(-par(C.sp0, 10.0) * di / dt) + b; }
+    case 6: { const double b = par(C.sp1, 0.0); return u <= (1 - b) * (1 / (1 + par(C.sp0, 1e-2) * di)) + b; }
+    case 7: { const double b = par(C.sp1, 0.0); return u <= (1 - b) * pow(par(C.sp0, 1e-3), di / dt) + b; }
+    case 8: { const double b = par(C.sp1, 0.0); return u <= (1 - b) * (1 / (1 + par(C.sp0, 1e-5) * (di * di))) + b; }
+    default: return true;
+  }
+}
+
+// random numbers of (chain, iteration t): u_sched, u_mix, u_acc broadcast; z[p] into smem (warp 0)
+__device__ inline void bt_draw(const BatchedCfg& C, int chain, long long t, long long tape_pos, double* z, double& us, double& um, double& ua, int lane) {
+  const int p = C.p;
+  if (C.tape_z) {
+    const size_t o = (size_t)chain * C.tape_len + tape_pos;
+    us = C.tape_usched[o]; um = C.tape_umix[o]; ua = C.tape_uacc[o];
+    if (lane < p) z[lane] = C.tape_z[o * p + lane];
+  } else {
+    const Philox4 r = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)chain, 0x51u, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
+    const Philox4 r2 = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)chain, 0x52u, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
+    us = philox_u53(r.x, r.y); um = philox_u53(r.z, r.w); ua = philox_u53(r2.x, r2.y);
+    if (ua <= 0.0) ua = 1.0 / 9007199254740992.0;
+    if (lane < p) {
+      const Philox4 q = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)chain, 0x100u + (uint32_t)lane, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
+      double u1 = philox_u53(q.x, q.y); const double u2 = philox_u53(q.z, q.w);
+      if (u1 <= 0.0) u1 = 1.0 / 9007199254740992.0;
+      double sn, cs; sincospi(2.0 * u2, &sn, &cs);
+      z[lane] = sqrt(-2.0 * log(u1)) * cs;
+    }
+  }
+  __syncwarp();
+}
+
+// Target evaluation by warp 0 (mvt).  level: 0 = log-target, 2 = up to tensor.  On level 2 the point's slot
+// (G, Inv, L, grad, firstterm, logdet of Inv) is filled: `transform`, inverse, Cholesky of the inverse, G^-1 grad --
+// the reference's :20-30 / :37-56 sequence for one point.  Returns the log-target; *ok = 0 if anything is non-finite / not PD.
+__device__ inline double bt_eval_point(const BatchedCfg& C, const BState& S, const double* x, int level, int gslot, int islot, int lslot,
+                                       int gradv, int ftermv, int ldscal, int lane, int* ok) {
+  const int p = C.p, ld = C.ld;
+  double* W = S.mat(BM_W);
+  double* G = S.mat(gslot); double* Inv = S.mat(islot); double* L = S.mat(lslot);
+  double* g = S.vec(gradv);
+  *ok = 1;
+  double lt = mvt_eval(C, x, g, (level >= 2) ? W : nullptr, S.vec(BV_T1), level >= 2 ? 2 : 0, lane);
+  if (!isfinite(lt)) { *ok = 0; return lt; }
+  if (level < 2) return lt;
+  double logdetG;
+  if (C.transform == 1) {
+    // W holds tensor = -Hessian; softabs -> G, Inv (L used as the eigenvector scratch)
+    logdetG = w_softabs(W, L, G, Inv, C.softabs_alpha, p, ld, lane, S.vec(BV_T2));
+  } else {
+    if (lane < p) for (int j = 0; j < p; ++j) { G[lane * ld + j] = W[lane * ld + j]; L[lane * ld + j] = W[lane * ld + j]; }
+    __syncwarp();
+    const double sl = w_chol(L, p, ld, lane);           // G = Lg Lg'
+    if (isnan(sl)) { *ok = 0; return lt; }
+    logdetG = 2.0 * sl;
+    w_inv_from_chol(L, Inv, W, p, ld, lane);
+  }
+  if (!isfinite(logdetG)) { *ok = 0; return lt; }
+  // cholinvtensor = chol(Hermitian(inv))'  (lower)
+  if (lane < p) for (int j = 0; j < p; ++j) L[lane * ld + j] = (j <= lane) ? Inv[lane * ld + j] : 0.0;
+  __syncwarp();
+  const double sl2 = w_chol(L, p, ld, lane);
+  if (isnan(sl2)) { *ok = 0; return lt; }
+  w_matvec(Inv, g, S.vec(ftermv), p, ld, lane);         // firstterm = inv * grad
+  if (lane == 0) S.s[ldscal] = -logdetG;                 // logdet(inv(G))
+  __syncwarp();
+  return lt;
+}
+
+__device__ inline void bt_tail(const BatchedCfg& C, const BState& S, int chain, int accepted, int lane) {
+  const int p = C.p;
+  double* s = S.s;
+  const long long t = (long long)s[BS_COUNT];
+  if (lane < p) {
+    const double lm = S.vec(BV_M1)[lane];
+    S.vec(BV_M2)[lane] = lm;
+    S.vec(BV_M1)[lane] = ((double)(t - 1) * lm + S.vec(BV_THETA)[lane]) / (double)t;
+  }
+  if (t > C.burnin) {
+    const long long pos = (long long)s[BS_SAVED];
+    if (pos < C.chain_cap) {
+      if (C.chain_value && lane < p) C.chain_value[((size_t)chain * C.chain_cap + pos) * p + lane] = S.vec(BV_THETA)[lane];
+      if (C.chain_accept && lane == 0) C.chain_accept[(size_t)chain * C.chain_cap + pos] = (unsigned char)accepted;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    if (t > C.burnin && s[BS_SAVED] < (double)C.chain_cap) s[BS_SAVED] += 1.0;
+    if (C.tuning) {
+      if ((long long)s[BS_TTOT] <= C.burnin && ((long long)s[BS_TPROP] % C.period) == 0) {
+        if (C.count_total) s[BS_TRATE] = s[BS_TACC] / s[BS_TPROP];
+        if (C.is_accrate) { s[BS_STEP] *= 2.0 / (1.0 + exp(-C.score_k * (s[BS_TRATE] - C.targetrate))); s[BS_SQSTEP] = sqrt(s[BS_STEP]); }
+        if (C.verbose_sm) { s[BS_SMTOT] += s[BS_SMPROP]; s[BS_SMPROP] = 0; s[BS_SMACC] = 0; }
+        if (C.verbose_am) { s[BS_AMTOT] += s[BS_AMPROP]; s[BS_AMPROP] = 0; s[BS_AMACC] = 0; }
+        s[BS_TTOT] += s[BS_TPROP]; s[BS_TPROP] = 0;
+        if (C.count_total) { s[BS_TACC] = 0; s[BS_TRATE] = nan(""); }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// mode: 0 = run n_iters transitions, 1 = initialise (initialize! + sampler_state) from theta0 [p x nchains]
+__global__ void __launch_bounds__(32) k_batched_gamc(BatchedCfg C, int mode, long long n_iters, const double* __restrict__ theta0) {
+  extern __shared__ __align__(16) double bsm[];
+  const int chain = blockIdx.x, lane = threadIdx.x;
+  if (chain >= C.nchains) return;
+  const int p = C.p, ld = C.ld;
+  BState S{bsm, bsm + BS_NSCAL, bsm + BS_NSCAL + BV_NVEC * BT_MAXP, p, ld};
+  double* s = S.s;
+  double* blob = C.blob + (size_t)chain * C.blob_doubles;
+  if (mode == 1) {
+    for (int i = lane; i < C.blob_doubles; i += 32) bsm[i] = 0.0;
+    __syncwarp();
+    if (lane < p) { S.vec(BV_THETA)[lane] = theta0[(size_t)chain * p + lane]; S.vec(BV_M1)[lane] = S.vec(BV_THETA)[lane]; }
+    __syncwarp();
+    int ok;
+    const double lt = bt_eval_point(C, S, S.vec(BV_THETA), 2, BM_GC, BM_IC, BM_LC, BV_GC, BV_FC, BS_LDC, lane, &ok);
+    if (lane == 0) {
+      s[BS_LT] = lt; s[BS_STEP] = C.driftstep; s[BS_SQSTEP] = sqrt(C.driftstep);
+      s[BS_TTOT] = C.period; s[BS_SMTOT] = C.period; s[BS_AMTOT] = C.period; s[BS_TRATE] = nan("");
+      s[BS_PRESENT] = 1.0; s[BS_PAST] = 0.0; s[BS_ERR] = ok ? 0.0 : 2.0;   // GAMC_NONFINITE_INIT / not PD at the initial point
+    }
+    __syncwarp();
+    for (int i = lane; i < C.blob_doubles; i += 32) blob[i] = bsm[i];
+    return;
+  }
+  for (int i = lane; i < C.blob_doubles; i += 32) bsm[i] = blob[i];
+  __syncwarp();
+  double* theta = S.vec(BV_THETA); double* prop = S.vec(BV_PROP); double* z = S.vec(BV_Z);
+  for (long long it = 0; it < n_iters; ++it) {
+    if (s[BS_ERR] != 0.0) break;
+    const long long t = (long long)s[BS_COUNT] + 1;
+    double us, um, ua;
+    bt_draw(C, chain, t, it, z, us, um, ua, lane);
+    bool present = s[BS_PRESENT] != 0.0;
+    if (t > C.t0) present = bt_schedule(C, t, us);                                 // iterate/GAMC.jl:8-10
+    const bool past = s[BS_PAST] != 0.0;
+    __syncwarp();
+    if (lane == 0) {
+      s[BS_COUNT] = (double)t;
+      if (C.tuning) s[BS_TPROP] += 1.0;
+      s[BS_PRESENT] = present ? 1.0 : 0.0;
+    }
+    const double eps = s[BS_STEP], sq = s[BS_SQSTEP];
+    int accept = 0;
+    if (present) {                                                                 // ---- SMMALA branch (:12-127)
+      if (lane == 0) { s[BS_UPD] += 1.0; if (C.verbose_sm) s[BS_SMPROP] += 1.0; }
+      int ok = 1;
+      if (!past) {                                                                 // :19-31
+        const double lt = bt_eval_point(C, S, theta, 2, BM_GC, BM_IC, BM_LC, BV_GC, BV_FC, BS_LDC, lane, &ok);
+        if (lane == 0) s[BS_LT] = lt;
+        if (!ok) { if (lane == 0) s[BS_ERR] = 3.0; __syncwarp(); break; }
+      }
+      __syncwarp();
+      if (lane < p) S.vec(BV_MU)[lane] = theta[lane] + 0.5 * eps * S.vec(BV_FC)[lane];       // :33
+      __syncwarp();
+      w_trmv_lower(S.mat(BM_LC), z, S.vec(BV_T1), p, ld, lane);
+      if (lane < p) prop[lane] = S.vec(BV_MU)[lane] + sq * S.vec(BV_T1)[lane];               // :35
+      __syncwarp();
+      const double lt_p = bt_eval_point(C, S, prop, 2, BM_GP, BM_IP, BM_LP, BV_GP, BV_FP, BS_LDP, lane, &ok);   // :37-43,56
+      double ratio = -INFINITY;
+      if (ok) {
+        // ratio (:45-67): logdet(eps*inv) = p log eps + logdet(inv)
+        if (lane < p) S.vec(BV_T1)[lane] = prop[lane] - S.vec(BV_MU)[lane];
+        __syncwarp();
+        w_matvec(S.mat(BM_GC), S.vec(BV_T1), S.vec(BV_T2), p, ld, lane);
+        const double q1 = w_dot(S.vec(BV_T1), S.vec(BV_T2), p, lane);
+        if (lane < p) S.vec(BV_T1)[lane] = theta[lane] - (prop[lane] + 0.5 * eps * S.vec(BV_FP)[lane]);
+        __syncwarp();
+        w_matvec(S.mat(BM_GP), S.vec(BV_T1), S.vec(BV_T2), p, ld, lane);
+        const double q2 = w_dot(S.vec(BV_T1), S.vec(BV_T2), p, lane);
+        const double plog = p * log(eps);
+        ratio = lt_p - s[BS_LT];
+        ratio += 0.5 * ((plog + s[BS_LDC]) + q1 / eps);
+        ratio -= 0.5 * ((plog + s[BS_LDP]) + q2 / eps);
+      }
+      accept = (ratio > 0.0) || (ratio > log(ua));                                 // :69
+      __syncwarp();
+      if (accept) {
+        // copy the proposal slot into the current slot (:70-98)
+        for (int e = lane; e < p * ld; e += 32) { S.mat(BM_GC)[e] = S.mat(BM_GP)[e]; S.mat(BM_IC)[e] = S.mat(BM_IP)[e]; S.mat(BM_LC)[e] = S.mat(BM_LP)[e]; }
+        if (lane < p) { theta[lane] = prop[lane]; S.vec(BV_GC)[lane] = S.vec(BV_GP)[lane]; S.vec(BV_FC)[lane] = S.vec(BV_FP)[lane]; }
+        if (lane == 0) { s[BS_LT] = lt_p; s[BS_LDC] = s[BS_LDP]; if (C.count_total) s[BS_TACC] += 1.0; if (C.verbose_sm) s[BS_SMACC] += 1.0; }
+      }
+      if (lane == 0) s[BS_RATIO] = ratio;
+      __syncwarp();
+    } else {                                                                       // ---- AM branch (:128-191)
+      if (lane == 0 && C.verbose_am) s[BS_AMPROP] += 1.0;
+      const double k = (double)(t - 2);
+      double* Cm = S.mat(BM_IC);                                                   // sstate.oldinvtensor
+      double* Lam = S.mat(BM_LAM);
+      if (lane < p) {                                                              // covariance! (:133-140) + Hermitian (:142)
+        const double xi = theta[lane], m1i = S.vec(BV_M1)[lane], m2i = S.vec(BV_M2)[lane];
+        for (int j = 0; j <= lane; ++j) {
+          const double cij = ((k - 1.0) * Cm[lane * ld + j] + k * (m2i * S.vec(BV_M2)[j]) - (k + 1.0) * (m1i * S.vec(BV_M1)[j]) + xi * theta[j]) / k;
+          Lam[lane * ld + j] = eps * cij;
+          S.mat(BM_W)[lane * ld + j] = cij;
+        }
+      }
+      __syncwarp();
+      if (lane < p) for (int j = 0; j <= lane; ++j) { const double cij = S.mat(BM_W)[lane * ld + j]; Cm[lane * ld + j] = cij; Cm[j * ld + lane] = cij; }
+      __syncwarp();
+      const double sl = w_chol(Lam, p, ld, lane);                                  // MvNormal(theta, eps*C) (set_gmm, GAMC.jl:188)
+      if (isnan(sl)) { if (lane == 0) s[BS_ERR] = 3.0; __syncwarp(); break; }
+      if (um <= 1.0 - C.c) {                                                       // :146 core component
+        w_trmv_lower(Lam, z, S.vec(BV_T1), p, ld, lane);
+        if (lane < p) prop[lane] = theta[lane] + S.vec(BV_T1)[lane];
+      } else if (lane < p) prop[lane] = theta[lane] + C.sqrtminorscale * z[lane];
+      __syncwarp();
+      int ok;
+      const double lt_p = bt_eval_point(C, S, prop, 0, BM_GP, BM_IP, BM_LP, BV_GP, BV_FP, BS_LDP, lane, &ok);   // :148
+      const double ratio = ok ? (lt_p - s[BS_LT]) : -INFINITY;                     // GMM terms cancel exactly (:150-156)
+      accept = (ratio > 0.0) || (ratio > log(ua));                                 // :158
+      __syncwarp();
+      if (accept) {
+        if (lane < p) theta[lane] = prop[lane];
+        if (lane == 0) { s[BS_LT] = lt_p; if (C.count_total) s[BS_TACC] += 1.0; if (C.verbose_am) s[BS_AMACC] += 1.0; }
+      }
+      if (lane == 0) s[BS_RATIO] = ratio;
+      __syncwarp();
+    }
+    if (lane == 0) s[BS_PAST] = present ? 1.0 : 0.0;                               // :197
+    __syncwarp();
+    bt_tail(C, S, chain, accept, lane);
+  }
+  __syncwarp();
+  for (int i = lane; i < C.blob_doubles; i += 32) blob[i] = bsm[i];
+}
+
+}  // namespace gamc

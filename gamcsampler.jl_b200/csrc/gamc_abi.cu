@@ -19,6 +19,7 @@
 #include "metric_plan.h"
 #include "sampler.cuh"
 #include "synth.cuh"
+#include "batched.cuh"
 
 using namespace gamc;
 
@@ -101,6 +102,9 @@ struct gamc_ctx {
   long long tape_gen_total = 0;
   // chain
   long long chain_cap = 0; double* d_chain = nullptr; unsigned char* d_accept = nullptr;
+  // batched chains
+  BatchedCfg bcfg{}; bool batched_target = false, batched_ready = false; double* d_Sinv = nullptr; double* d_blob = nullptr;
+  double* d_bchain = nullptr; unsigned char* d_baccept = nullptr; double* d_btape = nullptr; long long btape_doubles = 0;
   // comm
   ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
   // profiling
@@ -482,6 +486,7 @@ void bind_tape(gamc_ctx* h) {
 // C ABI
 // ====================================================================================================
 extern "C" {
+static void free_batched(gamc_ctx* h);
 
 const char* gamc_version(void) { return "gamc_b200 0.1.0 sm_100a"; }
 
@@ -511,6 +516,8 @@ gamc_status gamc_destroy(gamc_handle h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   free_sampler(h);
   free_target(h);
+  free_batched(h);
+  cudaFree(h->d_Sinv);
   cudaFree(h->d_tape);
   if (h->prof || h->ev_used) for (int i = 0; i < PROF_POOL; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -919,6 +926,156 @@ gamc_status gamc_get_array(gamc_handle h, int32_t array_id, double* out) {
 }
 
 // ---- measurement ------------------------------------------------------------------------------------
+// ---- batched chains ---------------------------------------------------------------------------------
+static void free_batched(gamc_ctx* h) {
+  cudaFree(h->d_blob); cudaFree(h->d_bchain); cudaFree(h->d_baccept); cudaFree(h->d_btape);
+  h->d_blob = nullptr; h->d_bchain = nullptr; h->d_baccept = nullptr; h->d_btape = nullptr; h->btape_doubles = 0;
+  h->batched_ready = false;
+}
+
+gamc_status gamc_batched_target_mvt(gamc_handle h, int32_t n, double nu, const double* Sinv, double logconst) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, Sinv && n >= 1 && nu > 0, GAMC_INVALID_ARG, "gamc_batched_target_mvt: bad argument");
+  REQUIRE(h, n <= BT_MAXP, GAMC_UNSUPPORTED_SHAPE, "batched chains support p <= 32");
+  cudaSetDevice(h->device);
+  free_batched(h);
+  cudaFree(h->d_Sinv); h->d_Sinv = nullptr;
+  CUDA_TRY(h, cudaMalloc(&h->d_Sinv, sizeof(double) * n * n));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_Sinv, Sinv, sizeof(double) * n * n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->bcfg = BatchedCfg{};
+  h->bcfg.p = n; h->bcfg.ld = (n & 1) ? n : n + 1; h->bcfg.target = 0;
+  h->bcfg.nu = nu; h->bcfg.logconst = logconst; h->bcfg.Sinv = h->d_Sinv;
+  h->batched_target = true;
+  return GAMC_OK;
+}
+
+static gamc_status launch_batched(gamc_ctx* h, int mode, long long n, const double* d_theta0) {
+  const size_t smem = sizeof(double) * h->bcfg.blob_doubles;
+  { gamc_status s = ensure_attr(h, (const void*)k_batched_gamc, 200 * 1024); if (s != GAMC_OK) return s; }
+  ProfScope ps(h, GAMC_K_LINALG);
+  k_batched_gamc<<<h->bcfg.nchains, 32, smem, h->stream>>>(h->bcfg, mode, n, d_theta0);
+  CUDA_TRY(h, cudaGetLastError());
+  return GAMC_OK;
+}
+
+gamc_status gamc_batched_init(gamc_handle h, const gamc_config* cfg, int32_t nchains, const double* theta0, int32_t transform, double softabs_alpha) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->batched_target, GAMC_NOT_READY, "no batched target: call gamc_batched_target_* first");
+  REQUIRE(h, cfg && theta0 && nchains >= 1, GAMC_INVALID_ARG, "null argument");
+  REQUIRE(h, cfg->driftstep > 0, GAMC_INVALID_ARG, "Drift step is not positive");
+  REQUIRE(h, cfg->minorscale > 0, GAMC_INVALID_ARG, "Constant minorscale must be positive");
+  REQUIRE(h, cfg->c >= 0, GAMC_INVALID_ARG, "Constant c must be non-negative");
+  REQUIRE(h, cfg->t0 > 0, GAMC_INVALID_ARG, "t0 is not positive");
+  REQUIRE(h, cfg->schedule >= 0 && cfg->schedule <= GAMC_SCHED_RAND_QUAD_DECAY, GAMC_INVALID_ARG, "unknown schedule");
+  REQUIRE(h, cfg->period >= 1 && cfg->nsteps >= 1 && cfg->burnin >= 0, GAMC_INVALID_ARG, "bad period / nsteps / burnin");
+  REQUIRE(h, transform == 0 || transform == 1, GAMC_INVALID_ARG, "transform must be 0 (none) or 1 (softabs)");
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  free_batched(h);
+  BatchedCfg& C = h->bcfg;
+  const int p = C.p;
+  C.nchains = nchains; C.transform = transform; C.softabs_alpha = softabs_alpha;
+  C.driftstep = cfg->driftstep; C.minorscale = cfg->minorscale; C.sqrtminorscale = sqrt(cfg->minorscale); C.c = cfg->c;
+  C.t0 = cfg->t0; C.schedule = cfg->schedule; C.sp0 = cfg->sched_params[0]; C.sp1 = cfg->sched_params[1]; C.sp2 = cfg->sched_params[2];
+  C.is_accrate = cfg->total_tuner_kind == 1;
+  C.tuning = (cfg->verbose_total || cfg->verbose_smmala || cfg->verbose_am || C.is_accrate) ? 1 : 0;
+  C.count_total = (cfg->verbose_total || C.is_accrate) ? 1 : 0;
+  C.verbose_sm = cfg->verbose_smmala; C.verbose_am = cfg->verbose_am; C.period = cfg->period;
+  C.nsteps = cfg->nsteps; C.burnin = cfg->burnin; C.targetrate = cfg->targetrate; C.score_k = cfg->score_k;
+  C.blob_doubles = bt_blob_doubles(p, C.ld);
+  C.chain_cap = std::max<long long>(0, cfg->nsteps - cfg->burnin);
+  CUDA_TRY(h, cudaMalloc(&h->d_blob, sizeof(double) * (size_t)nchains * C.blob_doubles));
+  if (C.chain_cap > 0) {
+    CUDA_TRY(h, cudaMalloc(&h->d_bchain, sizeof(double) * (size_t)nchains * C.chain_cap * p));
+    CUDA_TRY(h, cudaMalloc(&h->d_baccept, (size_t)nchains * C.chain_cap));
+  }
+  C.blob = h->d_blob; C.chain_value = h->d_bchain; C.chain_accept = h->d_baccept;
+  C.tape_usched = C.tape_umix = C.tape_uacc = C.tape_z = nullptr; C.tape_len = 0; C.seed = 0;
+  double* d_t0 = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d_t0, sizeof(double) * (size_t)nchains * p));
+  CUDA_TRY(h, cudaMemcpyAsync(d_t0, theta0, sizeof(double) * (size_t)nchains * p, cudaMemcpyHostToDevice, h->stream));
+  gamc_status s = launch_batched(h, 1, 0, d_t0);
+  if (s != GAMC_OK) { cudaFree(d_t0); return s; }
+  // initial-point check (src/samplers/GAMC.jl:168-170) for every chain
+  std::vector<double> err(nchains);
+  cudaError_t e = cudaMemcpy2DAsync(err.data(), sizeof(double), h->d_blob + BS_ERR, sizeof(double) * C.blob_doubles, sizeof(double), nchains,
+                                    cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_t0);
+  if (e != cudaSuccess) { h->err = std::string("batched init: ") + cudaGetErrorString(e); return GAMC_CUDA_ERROR; }
+  for (int c = 0; c < nchains; ++c)
+    if (err[c] != 0.0) { h->err = "Log-target, gradient or tensor not finite / not positive definite at the initial value of chain " + std::to_string(c); return GAMC_NONFINITE_INIT; }
+  h->batched_ready = true;
+  return GAMC_OK;
+}
+
+gamc_status gamc_batched_run(gamc_handle h, int64_t n, uint64_t seed, const double* u_sched, const double* u_mix, const double* z, const double* u_acc) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->batched_ready, GAMC_NOT_READY, "batched sampler not initialised");
+  REQUIRE(h, n >= 0, GAMC_INVALID_ARG, "n < 0");
+  cudaSetDevice(h->device);
+  BatchedCfg& C = h->bcfg;
+  const bool tape = u_sched || u_mix || z || u_acc;
+  if (tape) {
+    REQUIRE(h, u_sched && u_mix && z && u_acc, GAMC_INVALID_ARG, "either all tape pointers or none");
+    const long long per = (long long)C.nchains * n;
+    const long long need = per * (3 + C.p);
+    if (need > h->btape_doubles) {
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      cudaFree(h->d_btape); h->d_btape = nullptr; h->btape_doubles = 0;
+      CUDA_TRY(h, cudaMalloc(&h->d_btape, sizeof(double) * need));
+      h->btape_doubles = need;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_btape, u_sched, sizeof(double) * per, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_btape + per, u_mix, sizeof(double) * per, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_btape + 2 * per, u_acc, sizeof(double) * per, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_btape + 3 * per, z, sizeof(double) * per * C.p, cudaMemcpyHostToDevice, h->stream));
+    C.tape_usched = h->d_btape; C.tape_umix = h->d_btape + per; C.tape_uacc = h->d_btape + 2 * per; C.tape_z = h->d_btape + 3 * per;
+    C.tape_len = n;
+  } else {
+    C.tape_usched = C.tape_umix = C.tape_uacc = C.tape_z = nullptr; C.tape_len = 0;
+  }
+  C.seed = seed;
+  return launch_batched(h, 0, n, nullptr);
+}
+
+gamc_status gamc_batched_chain_get(gamc_handle h, int32_t chain_first, int32_t nchains, double* value, uint8_t* accept) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->batched_ready, GAMC_NOT_READY, "batched sampler not initialised");
+  const BatchedCfg& C = h->bcfg;
+  REQUIRE(h, chain_first >= 0 && nchains >= 0 && chain_first + nchains <= C.nchains, GAMC_INVALID_ARG, "chain range out of bounds");
+  cudaSetDevice(h->device);
+  if (nchains == 0 || C.chain_cap == 0) { CUDA_TRY(h, cudaStreamSynchronize(h->stream)); return GAMC_OK; }
+  if (value) CUDA_TRY(h, cudaMemcpyAsync(value, h->d_bchain + (size_t)chain_first * C.chain_cap * C.p, sizeof(double) * (size_t)nchains * C.chain_cap * C.p, cudaMemcpyDeviceToHost, h->stream));
+  if (accept) CUDA_TRY(h, cudaMemcpyAsync(accept, h->d_baccept + (size_t)chain_first * C.chain_cap, (size_t)nchains * C.chain_cap, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GAMC_OK;
+}
+
+gamc_status gamc_batched_get_state(gamc_handle h, int32_t chain, gamc_state_scalars* out, double* theta) {
+  if (!h || !out) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->batched_ready, GAMC_NOT_READY, "batched sampler not initialised");
+  const BatchedCfg& C = h->bcfg;
+  REQUIRE(h, chain >= 0 && chain < C.nchains, GAMC_INVALID_ARG, "chain out of range");
+  cudaSetDevice(h->device);
+  std::vector<double> b(BS_NSCAL + BT_MAXP);
+  CUDA_TRY(h, cudaMemcpyAsync(b.data(), h->d_blob + (size_t)chain * C.blob_doubles, sizeof(double) * (BS_NSCAL + BT_MAXP), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  memset(out, 0, sizeof(*out));
+  out->count = (int64_t)b[BS_COUNT]; out->updatetensorcount = (int64_t)b[BS_UPD];
+  out->step = b[BS_STEP]; out->sqrttunestep = b[BS_SQSTEP];
+  out->total_accepted = (int64_t)b[BS_TACC]; out->total_proposed = (int64_t)b[BS_TPROP]; out->total_totproposed = (int64_t)b[BS_TTOT]; out->total_rate = b[BS_TRATE];
+  out->smmala_accepted = (int64_t)b[BS_SMACC]; out->smmala_proposed = (int64_t)b[BS_SMPROP]; out->smmala_totproposed = (int64_t)b[BS_SMTOT];
+  out->am_accepted = (int64_t)b[BS_AMACC]; out->am_proposed = (int64_t)b[BS_AMPROP]; out->am_totproposed = (int64_t)b[BS_AMTOT];
+  out->smmalafrequency = NAN; out->amfrequency = NAN;
+  out->logtarget = b[BS_LT]; out->ratio = b[BS_RATIO];
+  out->presentupdatetensor = b[BS_PRESENT] != 0.0; out->pastupdatetensor = b[BS_PAST] != 0.0;
+  out->error_flag = (int32_t)b[BS_ERR]; out->chain_saved = (int64_t)b[BS_SAVED];
+  if (theta) memcpy(theta, b.data() + BS_NSCAL + BV_THETA * BT_MAXP, sizeof(double) * C.p);
+  return GAMC_OK;
+}
+
 gamc_status gamc_profile_enable(gamc_handle h, int32_t on) {
   if (!h) return GAMC_INVALID_ARG;
   cudaSetDevice(h->device);

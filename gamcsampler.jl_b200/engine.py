@@ -165,6 +165,43 @@ class Engine:
         self._ck(self.lib.gamc_get_array(self.h, int(array_id), L.dptr(out)))
         return out.reshape((self.p, self.p), order="F") if is_mat else out
 
+    # -- batched chains (small p)
+    def batched_target_mvt(self, Sinv, nu, logconst):
+        S = _f64(Sinv, "C")
+        n = S.shape[0]
+        self._ck(self.lib.gamc_batched_target_mvt(self.h, n, float(nu), L.dptr(S), float(logconst)))
+        self.bp = n
+
+    def batched_init(self, cfg: L.Config, theta0, transform=0, softabs_alpha=1000.0):
+        """theta0: (nchains, p) array (row c = initial value of chain c)."""
+        th = _f64(theta0, "C")
+        assert th.ndim == 2 and th.shape[1] == self.bp
+        self.bn = th.shape[0]
+        self.bcap = max(0, int(cfg.nsteps) - int(cfg.burnin))
+        self._ck(self.lib.gamc_batched_init(self.h, C.byref(cfg), self.bn, L.dptr(th), int(transform), float(softabs_alpha)))
+
+    def batched_run(self, n, seed=0, tape=None):
+        """tape: None (device Philox) or dict with u_sched/u_mix/u_acc of shape (nchains, n) and z of shape (nchains, n, p)."""
+        if tape is None:
+            self._ck(self.lib.gamc_batched_run(self.h, int(n), int(seed), None, None, None, None))
+        else:
+            us, um, ua, z = (_f64(tape[k], "C") for k in ("u_sched", "u_mix", "u_acc", "z"))
+            assert us.shape == (self.bn, n) and z.shape == (self.bn, n, self.bp)
+            self._ck(self.lib.gamc_batched_run(self.h, int(n), int(seed), L.dptr(us), L.dptr(um), L.dptr(z), L.dptr(ua)))
+
+    def batched_chain_get(self, first=0, nchains=None):
+        nchains = self.bn - first if nchains is None else nchains
+        value = np.empty((nchains, self.bcap, self.bp), dtype=np.float64)
+        accept = np.empty((nchains, self.bcap), dtype=np.uint8)
+        self._ck(self.lib.gamc_batched_chain_get(self.h, int(first), int(nchains), L.dptr(value), L.u8ptr(accept)))
+        return value, accept.astype(bool)
+
+    def batched_state(self, chain):
+        st = L.StateScalars()
+        th = np.empty(self.bp)
+        self._ck(self.lib.gamc_batched_get_state(self.h, int(chain), C.byref(st), L.dptr(th)))
+        return st, th
+
     # -- measurement
     def profile_enable(self, on=True):
         self._ck(self.lib.gamc_profile_enable(self.h, 1 if on else 0))

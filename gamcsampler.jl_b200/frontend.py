@@ -28,6 +28,7 @@ __all__ = [
     "rand_lin_decay_update", "rand_pow_decay_update", "rand_quad_decay_update",
     "exp_decay", "lin_decay", "pow_decay", "quad_decay",
     "BasicMCRange", "LogisticModel", "BasicMCJob", "Chain", "run", "output", "acceptance", "RandomTape",
+    "softabs", "Softabs", "MvTModel", "BatchedMCJob", "BatchedRandomTape",
 ]
 
 
@@ -145,6 +146,17 @@ class GAMCTune:
     amfrequency: float = float("nan")
 
 
+# ------------------------------------------------------------------ metric transform
+@dataclass(frozen=True)
+class Softabs:
+    """`transform = H -> softabs(H, alpha)` (Klara softabs; examples/t_distribution/src/GAMC/simulations.jl:39)."""
+    alpha: float = 1000.0
+
+
+def softabs(alpha=1000.0):
+    return Softabs(float(alpha))
+
+
 # ------------------------------------------------------------------ sampler
 class GAMC:
     """`GAMC(; update=rand_update!, transform=nothing, driftstep=1., minorscale=1., c=0.05, t0=3)`."""
@@ -155,9 +167,9 @@ class GAMC:
         assert 0 < minorscale, f"Constant minorscale must be positive, got {minorscale}"
         assert 0 <= c, "Constant c must be non-negative"
         assert t0 > 0, "t0 is not positive"
-        if transform is not None:
-            raise NotImplementedError("transform (e.g. softabs) is a SURVEY.md 8(f) 'next' row; the logistic path uses none "
-                                      "(examples/logistic_regression/src/GAMC/simulations.jl:50-55)")
+        if transform is not None and not isinstance(transform, Softabs):
+            raise NotImplementedError("only transform=softabs(alpha) (Klara softabs, examples/t_distribution/src/GAMC/simulations.jl:39) "
+                                      "is available on the device; arbitrary host callbacks are not")
         self.update = update if update is not None else rand_update()
         self.transform = transform
         self.driftstep, self.minorscale, self.c, self.t0 = float(driftstep), float(minorscale), float(c), int(t0)
@@ -324,3 +336,71 @@ def acceptance(chain_or_diag) -> float:
     """Klara `acceptance(chain)` / `acceptance(::Matrix{Bool})`: mean of the :accept diagnostic."""
     d = chain_or_diag.diagnosticvalues if isinstance(chain_or_diag, Chain) else chain_or_diag
     return float(np.mean(np.asarray(d, dtype=bool)))
+
+
+# ------------------------------------------------------------------ batched chains (small p)
+@dataclass
+class MvTModel:
+    """`plogtarget(p, v) = logpdf(MvTDist(nu, zeros(n), (nu-2)*Sigma/nu), p)` with Sigma_ij = c^|i-j|
+    (examples/t_distribution/src/GAMC/simulations.jl:17-33).  Model constants (inverse scale matrix, normalising
+    constant) are set up once on the host; every evaluation happens in the kernel."""
+    n: int = 20
+    nu: float = 30.0
+    c: float = 0.9
+
+    def constants(self):
+        idx = np.arange(self.n)
+        Sigma_t = (self.nu - 2.0) * (self.c ** np.abs(idx[:, None] - idx[None, :])) / self.nu
+        Sinv = np.linalg.inv(Sigma_t)
+        Sinv = 0.5 * (Sinv + Sinv.T)
+        _, logdet = np.linalg.slogdet(Sigma_t)
+        logconst = (math.lgamma((self.nu + self.n) / 2.0) - math.lgamma(self.nu / 2.0) - 0.5 * self.n * math.log(self.nu * math.pi) - 0.5 * logdet)
+        return Sinv, logconst
+
+
+class BatchedRandomTape:
+    """Per-chain host tapes: chain c uses RandomTape(nsteps, p, seed + c)."""
+
+    def __init__(self, nchains, nsteps, p, seed=0):
+        tapes = [RandomTape(nsteps, p, seed + c) for c in range(nchains)]
+        self.u_sched = np.stack([t.u_sched for t in tapes])
+        self.u_mix = np.stack([t.u_mix for t in tapes])
+        self.u_acc = np.stack([t.u_acc for t in tapes])
+        self.z = np.stack([t.z for t in tapes])
+
+
+class BatchedMCJob:
+    """The reference's `while i <= nchains ... BasicMCJob(...); run(job)` loop (examples/t_distribution/src/GAMC/simulations.jl:56-79)
+    as ONE persistent kernel: every chain is an independent GAMC job with its own initial value v0s[c]."""
+
+    def __init__(self, model: MvTModel, sampler: GAMC, mcrange: BasicMCRange, v0s, tuner: Optional[GAMCTuner] = None, device=0,
+                 tape: Optional[BatchedRandomTape] = None, seed=0, engine: Optional[Engine] = None):
+        self.model, self.sampler, self.range = model, sampler, mcrange
+        self.tuner = tuner if tuner is not None else GAMCTuner()
+        self.engine = engine if engine is not None else Engine(device)
+        Sinv, logconst = model.constants()
+        self.engine.batched_target_mvt(Sinv, model.nu, logconst)
+        self.cfg = make_config(sampler, self.tuner, mcrange)
+        tr = sampler.transform
+        self.engine.batched_init(self.cfg, np.asarray(v0s, dtype=np.float64), 1 if isinstance(tr, Softabs) else 0,
+                                 tr.alpha if isinstance(tr, Softabs) else 0.0)
+        self.tape, self.seed = tape, seed
+        self._done = 0
+
+    def run(self):
+        n = self.range.nsteps - self._done
+        if self.tape is not None:
+            lo, hi = self._done, self._done + n
+            t = self.tape
+            self.engine.batched_run(n, self.seed, {"u_sched": t.u_sched[:, lo:hi], "u_mix": t.u_mix[:, lo:hi], "u_acc": t.u_acc[:, lo:hi],
+                                                   "z": t.z[:, lo:hi]})
+        else:
+            self.engine.batched_run(n, self.seed)
+        self.engine.sync()
+        self._done += n
+        return self
+
+    def output(self):
+        """List of Chain objects (value p x nsamples, as `chain.value` of the reference)."""
+        value, accept = self.engine.batched_chain_get()
+        return [Chain(np.ascontiguousarray(value[c].T), accept[c].reshape(1, -1)) for c in range(value.shape[0])]

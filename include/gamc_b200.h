@@ -191,6 +191,26 @@ gamc_status gamc_peek_kinds(gamc_handle h, int64_t n, uint8_t* kinds_out);
 gamc_status gamc_get_state(gamc_handle h, gamc_state_scalars* out);
 gamc_status gamc_get_array(gamc_handle h, int32_t array_id, double* out);
 
+
+/* ---- batched chains (small p): many independent chains, one persistent kernel per run -----------------------------
+ * Replaces the reference's sequential `while i <= nchains ... run(job)` loops (examples/t_distribution/src/GAMC/simulations.jl:56-79)
+ * and, per chain, the same `iterate!` as above -- with the target evaluated inside the kernel.
+ * gamc_batched_target_mvt: the target of examples/t_distribution/src/GAMC/simulations.jl:17-33,
+ *   logpdf(MvTDist(nu, 0, Sigma_t), x) = logconst - (nu+n)/2 log1p(x' Sinv x / nu); Sinv = inv(Sigma_t) (n x n, symmetric),
+ *   gradient and tensor (= -Hessian) in closed form (the reference uses ForwardDiff, :33).
+ * transform: 0 = none, 1 = Klara softabs(H, alpha) (`transform=H -> softabs(H, 1000.)`, :39).
+ * theta0: p x nchains column-major.  Chains are independent: in a multi-GPU job every rank simply owns its own chains. */
+gamc_status gamc_batched_target_mvt(gamc_handle h, int32_t n, double nu, const double* Sinv, double logconst);
+gamc_status gamc_batched_init(gamc_handle h, const gamc_config* cfg, int32_t nchains, const double* theta0,
+                              int32_t transform, double softabs_alpha);
+/* n transitions of every chain.  Tape pointers may all be NULL (device Philox keyed by (seed, chain, iteration));
+ * otherwise u_sched/u_mix/u_acc are [nchains][n] and z is [nchains][n][p] (C order). */
+gamc_status gamc_batched_run(gamc_handle h, int64_t n, uint64_t seed, const double* u_sched, const double* u_mix,
+                             const double* z, const double* u_acc);
+/* value: [nchains][cap][p] doubles with cap = nsteps - burnin (sample s of chain c at value[(c*cap + s)*p]); accept [nchains][cap]. */
+gamc_status gamc_batched_chain_get(gamc_handle h, int32_t chain_first, int32_t nchains, double* value, uint8_t* accept);
+gamc_status gamc_batched_get_state(gamc_handle h, int32_t chain, gamc_state_scalars* out, double* theta);
+
 /* ---- measurement hooks ------------------------------------------------------------------------------
  * With profiling on, every kernel launched by gamc_run / gamc_eval_* is bracketed by CUDA events on the
  * handle's stream; gamc_profile_get returns launches and summed milliseconds per kernel family. */
