@@ -108,6 +108,7 @@ SIGNATURES = {
     "gamc_get_state": (C.c_int, [_H, C.POINTER(StateScalars)]),
     "gamc_get_array": (C.c_int, [_H, C.c_int32, _DP]),
     "gamc_batched_target_mvt": (C.c_int, [_H, C.c_int32, C.c_double, _DP, C.c_double]),
+    "gamc_batched_target_rv": (C.c_int, [_H, _DP, _DP, _DP, C.c_int64, C.c_int32]),
     "gamc_batched_init": (C.c_int, [_H, C.POINTER(Config), C.c_int32, _DP, C.c_int32, C.c_double]),
     "gamc_batched_run": (C.c_int, [_H, C.c_int64, C.c_uint64, _DP, _DP, _DP, _DP]),
     "gamc_batched_chain_get": (C.c_int, [_H, C.c_int32, C.c_int32, _DP, _U8P]),

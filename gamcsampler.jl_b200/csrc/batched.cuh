@@ -35,7 +35,7 @@ struct BatchedCfg {
   // mvt target
   double nu, logconst; const double* Sinv;   // n x n row-major == column-major (symmetric)
   // rv target
-  const double* rv_t; const double* rv_obs; const double* rv_sig; long long rv_n; int rv_npl;
+  const double* rv_t; const double* rv_obs; const double* rv_sig; long long rv_n; int rv_npl; double rv_lognorm;
   // tape (may be null -> Philox with `seed`)
   const double* tape_usched; const double* tape_umix; const double* tape_uacc; const double* tape_z;   // [chain][t] / [chain][t][p]
   long long tape_len;           // iterations per chain on the tape
@@ -244,6 +244,7 @@ template <int NP> __device__ inline Dual2<NP> operator*(const Dual2<NP>& a, cons
 }
 template <int NP> __device__ inline Dual2<NP> operator*(double c, const Dual2<NP>& a) { Dual2<NP> r; r.v = c * a.v; for (int i = 0; i < NP; ++i) r.g[i] = c * a.g[i]; for (int i = 0; i < Dual2<NP>::NH; ++i) r.h[i] = c * a.h[i]; return r; }
 template <int NP> __device__ inline Dual2<NP> operator+(const Dual2<NP>& a, double c) { Dual2<NP> r = a; r.v += c; return r; }
+template <int NP> __device__ inline Dual2<NP> operator+(double c, const Dual2<NP>& a) { Dual2<NP> r = a; r.v += c; return r; }
 template <int NP> __device__ inline Dual2<NP> operator-(double c, const Dual2<NP>& a) { Dual2<NP> r; r.v = c - a.v; for (int i = 0; i < NP; ++i) r.g[i] = -a.g[i]; for (int i = 0; i < Dual2<NP>::NH; ++i) r.h[i] = -a.h[i]; return r; }
 template <int NP> __device__ inline Dual2<NP> d_recip(const Dual2<NP>& x) { const double r = 1.0 / x.v; return d_unary(x, r, -r * r, 2.0 * r * r * r); }
 template <int NP> __device__ inline Dual2<NP> operator/(const Dual2<NP>& a, const Dual2<NP>& b) { return a * d_recip(b); }
@@ -263,6 +264,170 @@ template <int NP> __device__ inline Dual2<NP> d_atan2(const Dual2<NP>& y, const 
   for (int i = 0; i < NP; ++i) for (int j = 0; j <= i; ++j, ++k)
     r.h[k] = ay.v * y.h[k] + ax.v * x.h[k] + ay.g[j] * y.g[i] + ax.g[j] * x.g[i];
   return r;
+}
+
+}  // namespace gamc
+
+namespace gamc {
+
+// =====================================================================================================
+// Keplerian radial-velocity target (examples/radial_velocity/src/*.jl), block-cooperative over epochs
+// =====================================================================================================
+// calc_ecc_anom_itterative_laguerre (kepler_eqn.jl:43-56): Danby guess (:18-23) + Laguerre n = 5 (:30-40), M reduced mod 2 pi
+__device__ inline double rv_kepler(double M, double ecc) {
+  const double twopi = 6.283185307179586476925286766559;
+  M = M - twopi * floor(M / twopi);
+  double E = (M < 3.14159265358979323846) ? M + 0.85 * ecc : M - 0.85 * ecc;
+  for (int it = 0; it < 60; ++it) {
+    double sE, cE; sincos(E, &sE, &cE);
+    const double es = ecc * sE, ec = ecc * cE;
+    const double F = (E - es) - M, Fp = 1.0 - ec, Fpp = es;
+    const double root = sqrt(fabs(4.0 * (4.0 * Fp * Fp - 5.0 * F * Fpp)));
+    const double denom = (Fp > 0.0) ? Fp + root : Fp - root;
+    const double En = E - 5.0 * F / denom;
+    const bool done = fabs(En - E) < 1e-14;
+    E = En;
+    if (done) break;
+  }
+  return E;
+}
+
+// velocity of one planet, plain doubles (rv_model_keplerian.jl:9-37)
+__device__ inline double rv_planet(const double* th, double t) {
+  const double P = exp(th[0]) - 1.0, K = exp(th[1]) - 1.0, h = th[2], k = th[3];
+  const double ecc = sqrt(h * h + k * k), w = atan2(k, h);
+  const double n = 6.283185307179586476925286766559 / P;
+  const double M = t * n - (th[4] - w), lam = w + M;
+  const double E = rv_kepler(M, ecc);
+  double sE, cE; sincos(E, &sE, &cE);
+  const double j = sqrt((1.0 - ecc) * (1.0 + ecc));
+  const double pe = ecc * sE, q = ecc * cE;
+  return K * j / (1.0 - q) * (cos(lam + pe) - k * q / (1.0 + j));
+}
+
+// Phi(theta1, h, k, wpM0; t) = velocity / K with exact first and second derivatives: the eccentric anomaly is solved in
+// plain doubles and refined by two Newton steps in dual arithmetic (implicit differentiation of Kepler's equation).
+__device__ inline Dual2<4> rv_phi_dual(const double* th, double t) {
+  typedef Dual2<4> D;
+  const double twopi = 6.283185307179586476925286766559;
+  const D P = d_exp(d_var<4>(th[0], 0)) + (-1.0);
+  const D h = d_var<4>(th[2], 1), k = d_var<4>(th[3], 2), wm = d_var<4>(th[4], 3);
+  const D ecc = d_sqrt(h * h + k * k);
+  const D w = d_atan2(k, h);
+  const D n = twopi * d_recip(P);
+  D M = t * n - wm + w;
+  const D lam = w + M;
+  const double E0 = rv_kepler(M.v, ecc.v);
+  M.v = M.v - twopi * floor(M.v / twopi);
+  D E = d_const<4>(E0);
+#pragma unroll 1
+  for (int it = 0; it < 2; ++it) E = E - (E - ecc * d_sin(E) - M) / (1.0 - ecc * d_cos(E));
+  const D sE = d_sin(E), cE = d_cos(E);
+  const D q = ecc * cE;
+  const D j = d_sqrt((1.0 - ecc) * (1.0 + ecc));
+  return j * d_recip(1.0 - q) * (d_cos(lam + ecc * sE) - k * q * d_recip(j + 1.0));
+}
+
+constexpr int RV_MAXP = 11;
+constexpr int RV_MAXRED = 1 + RV_MAXP + RV_MAXP * (RV_MAXP + 1) / 2;   // 78
+
+// Per-thread partial sums over this thread's epochs.  level 0: acc[0] = sum r^2/s^2 (chi-square).
+// level 2: also acc[1+a] = sum r z_a / s^2 and acc[1+p+idx(a,b)] = sum (z_a z_b + r z_ab)/s^2 (lower triangle, row-major).
+template <int NPL>
+__device__ inline void rv_partial(const BatchedCfg& C, const double* th, int level, int tid, int nt, double* acc) {
+  constexpr int p = 5 * NPL + 1;
+  constexpr int NR = 1 + p + p * (p + 1) / 2;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) acc[i] = 0.0;
+  for (long long e = tid; e < C.rv_n; e += nt) {
+    const double t = C.rv_t[e], o = C.rv_obs[e], sg = C.rv_sig[e];
+    const double is2 = 1.0 / (sg * sg);
+    if (level < 2) {
+      double z = th[5 * NPL];
+#pragma unroll
+      for (int pl = 0; pl < NPL; ++pl) z += rv_planet(th + 5 * pl, t);
+      const double r = z - o;
+      acc[0] = fma(r * r, is2, acc[0]);
+    } else {
+      double za[p];
+      double zab[NPL][15];       // per planet: second derivatives over (theta1, theta2, h, k, wpM0), lower triangle
+      double z = th[5 * NPL];
+      za[5 * NPL] = 1.0;
+#pragma unroll
+      for (int pl = 0; pl < NPL; ++pl) {
+        const Dual2<4> phi = rv_phi_dual(th + 5 * pl, t);
+        const double Kp = exp(th[5 * pl + 1]), K = Kp - 1.0;     // K' = K'' = exp(theta2)
+        z = fma(K, phi.v, z);
+        // local order: 0 = theta1, 1 = theta2 (K), 2 = h, 3 = k, 4 = wpM0;  phi's variables: 0 = theta1, 1 = h, 2 = k, 3 = wpM0
+        const int map[5] = {0, -1, 1, 2, 3};
+#pragma unroll
+        for (int a = 0; a < 5; ++a) za[5 * pl + a] = (a == 1) ? Kp * phi.v : K * phi.g[map[a]];
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+          for (int b = 0; b <= a; ++b) {
+            double v;
+            if (a == 1 && b == 1) v = Kp * phi.v;
+            else if (a == 1) v = Kp * phi.g[map[b]];
+            else if (b == 1) v = Kp * phi.g[map[a]];
+            else v = K * phi.h[Dual2<4>::hidx(map[a], map[b])];
+            zab[pl][a * (a + 1) / 2 + b] = v;
+          }
+      }
+      const double r = z - o;
+      acc[0] = fma(r * r, is2, acc[0]);
+      const double ris2 = r * is2;
+#pragma unroll
+      for (int a = 0; a < p; ++a) acc[1 + a] = fma(ris2, za[a], acc[1 + a]);
+#pragma unroll
+      for (int a = 0; a < p; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          double v = za[a] * za[b] * is2;
+          if (a < 5 * NPL && (a / 5) == (b / 5)) { const int la = a % 5, lb = b % 5; v = fma(ris2, zab[a / 5][la * (la + 1) / 2 + lb], v); }
+          acc[1 + p + a * (a + 1) / 2 + b] += v;
+        }
+    }
+  }
+}
+
+// Block-wide RV evaluation; called by ALL threads of the CTA.  Results (level 2): lt returned to every thread,
+// g (length p) and H = tensor = -Hessian of the log-target (p x ld) written by warp 0.  red = RV_MAXRED * nwarps doubles.
+template <int NPL>
+__device__ inline double rv_eval_block(const BatchedCfg& C, const double* x, double* g, double* H, int level, double* red, double* bcast) {
+  constexpr int p = 5 * NPL + 1;
+  constexpr int NR = 1 + p + p * (p + 1) / 2;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  bool valid = true;
+#pragma unroll
+  for (int pl = 0; pl < NPL; ++pl) { const double h = x[5 * pl + 2], k = x[5 * pl + 3]; if (!(h * h + k * k < 1.0)) valid = false; }   // is_valid, rv_model_param.jl:83-96
+  if (!valid) return -INFINITY;                                                     // stat_model.jl:21
+  double acc[NR];
+  rv_partial<NPL>(C, x, level, tid, nt, acc);
+  const int nred = (level >= 2) ? NR : 1;
+  for (int i = 0; i < nred; ++i) { const double v = warp_sum(acc[i]); if (lane == 0) red[warp * RV_MAXRED + i] = v; }
+  __syncthreads();
+  if (warp == 0) {
+    for (int i = lane; i < nred; i += 32) { double s = 0.0; for (int w2 = 0; w2 < nw; ++w2) s += red[w2 * RV_MAXRED + i]; red[i] = s; }
+    __syncwarp();
+    if (lane == 0) {
+      // log-likelihood normalisation (stat_model.jl:27-35) and modified-Jeffreys prior (:39-61; log prior = const - sum(theta_P + theta_K))
+      double lognorm = C.rv_lognorm;
+      double lp = -2.0 * log(6.283185307179586476925286766559);
+      for (int pl = 0; pl < NPL; ++pl) lp -= x[5 * pl] + x[5 * pl + 1] + 2.0 * log(log1p(10000.0));
+      bcast[0] = -0.5 * red[0] + lognorm + lp;
+    }
+    if (level >= 2) {
+      if (lane < p) {
+        double gv = -red[1 + lane];
+        if (lane < 5 * NPL && (lane % 5) < 2) gv -= 1.0;          // d logprior / d theta_P, theta_K
+        g[lane] = gv;
+        for (int b = 0; b <= lane; ++b) { const double v = red[1 + p + lane * (lane + 1) / 2 + b]; H[lane * C.ld + b] = v; H[b * C.ld + lane] = v; }
+      }
+    }
+  }
+  __syncthreads();
+  return bcast[0];
 }
 
 }  // namespace gamc
@@ -315,15 +480,34 @@ __device__ inline void bt_draw(const BatchedCfg& C, int chain, long long t, long
 // Target evaluation by warp 0 (mvt).  level: 0 = log-target, 2 = up to tensor.  On level 2 the point's slot
 // (G, Inv, L, grad, firstterm, logdet of Inv) is filled: `transform`, inverse, Cholesky of the inverse, G^-1 grad --
 // the reference's :20-30 / :37-56 sequence for one point.  Returns the log-target; *ok = 0 if anything is non-finite / not PD.
-__device__ inline double bt_eval_point(const BatchedCfg& C, const BState& S, const double* x, int level, int gslot, int islot, int lslot,
+struct BtWork { double* red; double* bcast; int* cmd; };
+
+// master side of the block-cooperative RV evaluation: wake the worker warps, evaluate together
+template <int NPL>
+__device__ inline double rv_eval_master(const BatchedCfg& C, const BState& S, const BtWork& Wk, int xvec, int gradv, double* H, int level, int lane) {
+  if (lane == 0) { Wk.cmd[0] = level + 1; Wk.cmd[1] = xvec; }
+  __syncthreads();                                   // barrier A: releases the workers
+  return rv_eval_block<NPL>(C, S.vec(xvec), S.vec(gradv), H, level, Wk.red, Wk.bcast);
+}
+
+template <int TGT>
+__device__ inline double bt_eval_point(const BatchedCfg& C, const BState& S, const BtWork& Wk, int xvec, int level, int gslot, int islot, int lslot,
                                        int gradv, int ftermv, int ldscal, int lane, int* ok) {
+  const double* x = S.vec(xvec);
   const int p = C.p, ld = C.ld;
   double* W = S.mat(BM_W);
   double* G = S.mat(gslot); double* Inv = S.mat(islot); double* L = S.mat(lslot);
   double* g = S.vec(gradv);
   *ok = 1;
-  double lt = mvt_eval(C, x, g, (level >= 2) ? W : nullptr, S.vec(BV_T1), level >= 2 ? 2 : 0, lane);
+  double lt;
+  if (TGT == 0) lt = mvt_eval(C, x, g, (level >= 2) ? W : nullptr, S.vec(BV_T1), level >= 2 ? 2 : 0, lane);
+  else lt = rv_eval_master<(TGT == 2 ? 2 : 1)>(C, S, Wk, xvec, gradv, W, level >= 2 ? 2 : 0, lane);
   if (!isfinite(lt)) { *ok = 0; return lt; }
+  if (level >= 2) {   // finite gradient / tensor (initialize! asserts, GAMC.jl:168-170; otherwise a rejection)
+    double bad = 0.0;
+    if (lane < p) { if (!isfinite(g[lane])) bad = 1.0; for (int j = 0; j < p; ++j) if (!isfinite(W[lane * ld + j])) bad = 1.0; }
+    if (warp_sum(bad) != 0.0) { *ok = 0; return lt; }
+  }
   if (level < 2) return lt;
   double logdetG;
   if (C.transform == 1) {
@@ -383,21 +567,41 @@ __device__ inline void bt_tail(const BatchedCfg& C, const BState& S, int chain, 
 }
 
 // mode: 0 = run n_iters transitions, 1 = initialise (initialize! + sampler_state) from theta0 [p x nchains]
-__global__ void __launch_bounds__(32) k_batched_gamc(BatchedCfg C, int mode, long long n_iters, const double* __restrict__ theta0) {
+__host__ __device__ inline size_t bt_smem_bytes(int blob_doubles, int nthreads) {
+  return sizeof(double) * ((size_t)blob_doubles + (size_t)RV_MAXRED * (nthreads / 32) + 8);
+}
+
+template <int TGT>
+__global__ void __launch_bounds__(TGT == 0 ? 32 : 128) k_batched_gamc(BatchedCfg C, int mode, long long n_iters, const double* __restrict__ theta0) {
   extern __shared__ __align__(16) double bsm[];
-  const int chain = blockIdx.x, lane = threadIdx.x;
+  const int chain = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (chain >= C.nchains) return;
   const int p = C.p, ld = C.ld;
   BState S{bsm, bsm + BS_NSCAL, bsm + BS_NSCAL + BV_NVEC * BT_MAXP, p, ld};
   double* s = S.s;
   double* blob = C.blob + (size_t)chain * C.blob_doubles;
+  BtWork Wk;
+  Wk.red = bsm + C.blob_doubles;
+  Wk.bcast = Wk.red + RV_MAXRED * (blockDim.x >> 5);
+  Wk.cmd = reinterpret_cast<int*>(Wk.bcast + 4);
+  if (TGT != 0 && warp != 0) {
+    // worker warps: wait for an evaluation request from warp 0, take part in it, repeat
+    while (true) {
+      __syncthreads();                               // barrier A
+      const int c = Wk.cmd[0];
+      if (c == 0) break;
+      rv_eval_block<(TGT == 2 ? 2 : 1)>(C, S.vec(Wk.cmd[1]), nullptr, nullptr, c - 1, Wk.red, Wk.bcast);
+    }
+    return;
+  }
+  auto release_workers = [&]() { if (TGT != 0) { if (lane == 0) Wk.cmd[0] = 0; __syncthreads(); } };
   if (mode == 1) {
     for (int i = lane; i < C.blob_doubles; i += 32) bsm[i] = 0.0;
     __syncwarp();
     if (lane < p) { S.vec(BV_THETA)[lane] = theta0[(size_t)chain * p + lane]; S.vec(BV_M1)[lane] = S.vec(BV_THETA)[lane]; }
     __syncwarp();
     int ok;
-    const double lt = bt_eval_point(C, S, S.vec(BV_THETA), 2, BM_GC, BM_IC, BM_LC, BV_GC, BV_FC, BS_LDC, lane, &ok);
+    const double lt = bt_eval_point<TGT>(C, S, Wk, BV_THETA, 2, BM_GC, BM_IC, BM_LC, BV_GC, BV_FC, BS_LDC, lane, &ok);
     if (lane == 0) {
       s[BS_LT] = lt; s[BS_STEP] = C.driftstep; s[BS_SQSTEP] = sqrt(C.driftstep);
       s[BS_TTOT] = C.period; s[BS_SMTOT] = C.period; s[BS_AMTOT] = C.period; s[BS_TRATE] = nan("");
@@ -405,6 +609,7 @@ __global__ void __launch_bounds__(32) k_batched_gamc(BatchedCfg C, int mode, lon
     }
     __syncwarp();
     for (int i = lane; i < C.blob_doubles; i += 32) blob[i] = bsm[i];
+    release_workers();
     return;
   }
   for (int i = lane; i < C.blob_doubles; i += 32) bsm[i] = blob[i];
@@ -430,7 +635,7 @@ __global__ void __launch_bounds__(32) k_batched_gamc(BatchedCfg C, int mode, lon
       if (lane == 0) { s[BS_UPD] += 1.0; if (C.verbose_sm) s[BS_SMPROP] += 1.0; }
       int ok = 1;
       if (!past) {                                                                 // :19-31
-        const double lt = bt_eval_point(C, S, theta, 2, BM_GC, BM_IC, BM_LC, BV_GC, BV_FC, BS_LDC, lane, &ok);
+        const double lt = bt_eval_point<TGT>(C, S, Wk, BV_THETA, 2, BM_GC, BM_IC, BM_LC, BV_GC, BV_FC, BS_LDC, lane, &ok);
         if (lane == 0) s[BS_LT] = lt;
         if (!ok) { if (lane == 0) s[BS_ERR] = 3.0; __syncwarp(); break; }
       }
@@ -440,7 +645,7 @@ __global__ void __launch_bounds__(32) k_batched_gamc(BatchedCfg C, int mode, lon
       w_trmv_lower(S.mat(BM_LC), z, S.vec(BV_T1), p, ld, lane);
       if (lane < p) prop[lane] = S.vec(BV_MU)[lane] + sq * S.vec(BV_T1)[lane];               // :35
       __syncwarp();
-      const double lt_p = bt_eval_point(C, S, prop, 2, BM_GP, BM_IP, BM_LP, BV_GP, BV_FP, BS_LDP, lane, &ok);   // :37-43,56
+      const double lt_p = bt_eval_point<TGT>(C, S, Wk, BV_PROP, 2, BM_GP, BM_IP, BM_LP, BV_GP, BV_FP, BS_LDP, lane, &ok);   // :37-43,56
       double ratio = -INFINITY;
       if (ok) {
         // ratio (:45-67): logdet(eps*inv) = p log eps + logdet(inv)
@@ -491,7 +696,7 @@ __global__ void __launch_bounds__(32) k_batched_gamc(BatchedCfg C, int mode, lon
       } else if (lane < p) prop[lane] = theta[lane] + C.sqrtminorscale * z[lane];
       __syncwarp();
       int ok;
-      const double lt_p = bt_eval_point(C, S, prop, 0, BM_GP, BM_IP, BM_LP, BV_GP, BV_FP, BS_LDP, lane, &ok);   // :148
+      const double lt_p = bt_eval_point<TGT>(C, S, Wk, BV_PROP, 0, BM_GP, BM_IP, BM_LP, BV_GP, BV_FP, BS_LDP, lane, &ok);   // :148
       const double ratio = ok ? (lt_p - s[BS_LT]) : -INFINITY;                     // GMM terms cancel exactly (:150-156)
       accept = (ratio > 0.0) || (ratio > log(ua));                                 // :158
       __syncwarp();
@@ -508,6 +713,7 @@ __global__ void __launch_bounds__(32) k_batched_gamc(BatchedCfg C, int mode, lon
   }
   __syncwarp();
   for (int i = lane; i < C.blob_doubles; i += 32) blob[i] = bsm[i];
+  release_workers();
 }
 
 }  // namespace gamc

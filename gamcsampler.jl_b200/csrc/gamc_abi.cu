@@ -950,13 +950,45 @@ gamc_status gamc_batched_target_mvt(gamc_handle h, int32_t n, double nu, const d
   return GAMC_OK;
 }
 
-static gamc_status launch_batched(gamc_ctx* h, int mode, long long n, const double* d_theta0) {
-  const size_t smem = sizeof(double) * h->bcfg.blob_doubles;
-  { gamc_status s = ensure_attr(h, (const void*)k_batched_gamc, 200 * 1024); if (s != GAMC_OK) return s; }
+gamc_status gamc_batched_target_rv(gamc_handle h, const double* t, const double* obs, const double* sigma, int64_t N, int32_t nplanets) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, t && obs && sigma && N >= 1, GAMC_INVALID_ARG, "gamc_batched_target_rv: bad argument");
+  REQUIRE(h, nplanets == 1 || nplanets == 2, GAMC_UNSUPPORTED_SHAPE, "radial-velocity target supports 1 or 2 planets");
+  cudaSetDevice(h->device);
+  free_batched(h);
+  cudaFree(h->d_Sinv); h->d_Sinv = nullptr;        // reused as the [t | obs | sigma] buffer
+  CUDA_TRY(h, cudaMalloc(&h->d_Sinv, sizeof(double) * 3 * (size_t)N));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_Sinv, t, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_Sinv + N, obs, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_Sinv + 2 * N, sigma, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  double lognorm = -0.5 * (double)N * log(2.0 * M_PI);          // stat_model.jl:27,33 (data constants, summed once on the host)
+  for (int64_t i = 0; i < N; ++i) lognorm -= 0.5 * log(sigma[i] * sigma[i]);
+  h->bcfg = BatchedCfg{};
+  h->bcfg.p = 5 * nplanets + 1; h->bcfg.ld = (h->bcfg.p & 1) ? h->bcfg.p : h->bcfg.p + 1; h->bcfg.target = 1;
+  h->bcfg.rv_t = h->d_Sinv; h->bcfg.rv_obs = h->d_Sinv + N; h->bcfg.rv_sig = h->d_Sinv + 2 * N; h->bcfg.rv_n = N; h->bcfg.rv_npl = nplanets;
+  h->bcfg.rv_lognorm = lognorm;
+  h->batched_target = true;
+  return GAMC_OK;
+}
+
+}  // extern "C"
+
+template <int TGT>
+static gamc_status launch_batched_t(gamc_ctx* h, int mode, long long n, const double* d_theta0) {
+  const int nt = (TGT == 0) ? 32 : 128;
+  const size_t smem = bt_smem_bytes(h->bcfg.blob_doubles, nt);
+  { gamc_status s = ensure_attr(h, (const void*)k_batched_gamc<TGT>, 200 * 1024); if (s != GAMC_OK) return s; }
   ProfScope ps(h, GAMC_K_LINALG);
-  k_batched_gamc<<<h->bcfg.nchains, 32, smem, h->stream>>>(h->bcfg, mode, n, d_theta0);
+  k_batched_gamc<TGT><<<h->bcfg.nchains, nt, smem, h->stream>>>(h->bcfg, mode, n, d_theta0);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
+}
+extern "C" {
+
+static gamc_status launch_batched(gamc_ctx* h, int mode, long long n, const double* d_theta0) {
+  if (h->bcfg.target == 0) return launch_batched_t<0>(h, mode, n, d_theta0);
+  return h->bcfg.rv_npl == 2 ? launch_batched_t<2>(h, mode, n, d_theta0) : launch_batched_t<1>(h, mode, n, d_theta0);
 }
 
 gamc_status gamc_batched_init(gamc_handle h, const gamc_config* cfg, int32_t nchains, const double* theta0, int32_t transform, double softabs_alpha) {

@@ -172,6 +172,12 @@ class Engine:
         self._ck(self.lib.gamc_batched_target_mvt(self.h, n, float(nu), L.dptr(S), float(logconst)))
         self.bp = n
 
+    def batched_target_rv(self, t, obs, sigma, nplanets=1):
+        t, obs, sigma = (_f64(a, "C").ravel() for a in (t, obs, sigma))
+        assert t.shape == obs.shape == sigma.shape
+        self._ck(self.lib.gamc_batched_target_rv(self.h, L.dptr(t), L.dptr(obs), L.dptr(sigma), t.shape[0], int(nplanets)))
+        self.bp = 5 * int(nplanets) + 1
+
     def batched_init(self, cfg: L.Config, theta0, transform=0, softabs_alpha=1000.0):
         """theta0: (nchains, p) array (row c = initial value of chain c)."""
         th = _f64(theta0, "C")

@@ -28,7 +28,7 @@ __all__ = [
     "rand_lin_decay_update", "rand_pow_decay_update", "rand_quad_decay_update",
     "exp_decay", "lin_decay", "pow_decay", "quad_decay",
     "BasicMCRange", "LogisticModel", "BasicMCJob", "Chain", "run", "output", "acceptance", "RandomTape",
-    "softabs", "Softabs", "MvTModel", "BatchedMCJob", "BatchedRandomTape",
+    "softabs", "Softabs", "MvTModel", "RVModel", "BatchedMCJob", "BatchedRandomTape",
 ]
 
 
@@ -358,6 +358,16 @@ class MvTModel:
         return Sinv, logconst
 
 
+@dataclass
+class RVModel:
+    """Keplerian radial-velocity model of examples/radial_velocity/src (stat_model.jl:18-63): data = epochs t, observed
+    velocities obs, uncertainties sigma_obs (set_times / set_obs / set_sigma_obs); nplanets in {1, 2}."""
+    times: np.ndarray
+    obs: np.ndarray
+    sigma_obs: np.ndarray
+    nplanets: int = 1
+
+
 class BatchedRandomTape:
     """Per-chain host tapes: chain c uses RandomTape(nsteps, p, seed + c)."""
 
@@ -373,13 +383,16 @@ class BatchedMCJob:
     """The reference's `while i <= nchains ... BasicMCJob(...); run(job)` loop (examples/t_distribution/src/GAMC/simulations.jl:56-79)
     as ONE persistent kernel: every chain is an independent GAMC job with its own initial value v0s[c]."""
 
-    def __init__(self, model: MvTModel, sampler: GAMC, mcrange: BasicMCRange, v0s, tuner: Optional[GAMCTuner] = None, device=0,
+    def __init__(self, model, sampler: GAMC, mcrange: BasicMCRange, v0s, tuner: Optional[GAMCTuner] = None, device=0,
                  tape: Optional[BatchedRandomTape] = None, seed=0, engine: Optional[Engine] = None):
         self.model, self.sampler, self.range = model, sampler, mcrange
         self.tuner = tuner if tuner is not None else GAMCTuner()
         self.engine = engine if engine is not None else Engine(device)
-        Sinv, logconst = model.constants()
-        self.engine.batched_target_mvt(Sinv, model.nu, logconst)
+        if isinstance(model, RVModel):
+            self.engine.batched_target_rv(model.times, model.obs, model.sigma_obs, model.nplanets)
+        else:
+            Sinv, logconst = model.constants()
+            self.engine.batched_target_mvt(Sinv, model.nu, logconst)
         self.cfg = make_config(sampler, self.tuner, mcrange)
         tr = sampler.transform
         self.engine.batched_init(self.cfg, np.asarray(v0s, dtype=np.float64), 1 if isinstance(tr, Softabs) else 0,

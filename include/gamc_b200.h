@@ -201,6 +201,11 @@ gamc_status gamc_get_array(gamc_handle h, int32_t array_id, double* out);
  * transform: 0 = none, 1 = Klara softabs(H, alpha) (`transform=H -> softabs(H, 1000.)`, :39).
  * theta0: p x nchains column-major.  Chains are independent: in a multi-GPU job every rank simply owns its own chains. */
 gamc_status gamc_batched_target_mvt(gamc_handle h, int32_t n, double nu, const double* Sinv, double logconst);
+/* gamc_batched_target_rv: the Keplerian radial-velocity target of examples/radial_velocity/src/stat_model.jl:18-63
+ * (calc_model_rv rv_model_keplerian.jl:9-51, Kepler solver kepler_eqn.jl:18-56, parameter packing rv_model_param.jl:45-96):
+ * theta = [log1p(P), log1p(K), e cos w, e sin w, w + M0] per planet + offset; t, obs, sigma: N epochs.  Gradient and
+ * tensor (= -Hessian) by second-order forward-mode dual numbers in the kernel (the reference uses ForwardDiff, order 2). */
+gamc_status gamc_batched_target_rv(gamc_handle h, const double* t, const double* obs, const double* sigma, int64_t N, int32_t nplanets);
 gamc_status gamc_batched_init(gamc_handle h, const gamc_config* cfg, int32_t nchains, const double* theta0,
                               int32_t transform, double softabs_alpha);
 /* n transitions of every chain.  Tape pointers may all be NULL (device Philox keyed by (seed, chain, iteration));

@@ -168,3 +168,137 @@ class RVModel:
 
     def logtarget(self, theta):
         return self.loglikelihood(theta) + self.logprior(theta)
+
+
+# ------------------------------------------------------------------ second-order forward-mode duals (vectorised over epochs)
+class Dual2:
+    """value v (N,), gradient g (N, m), Hessian h (N, m, m) of a scalar function of m variables, per epoch.
+    Stands in for the reference's ForwardDiff sweep (Klara `DiffOptions(mode=:forward, order=2)`,
+    examples/radial_velocity/src/one_planet/GAMC/simulations.jl:37)."""
+
+    def __init__(self, v, g, h):
+        self.v, self.g, self.h = v, g, h
+
+    @staticmethod
+    def const(c, N, m):
+        return Dual2(np.full(N, float(c)) if np.isscalar(c) else np.asarray(c, dtype=np.float64), np.zeros((N, m)), np.zeros((N, m, m)))
+
+    @staticmethod
+    def var(c, k, N, m):
+        d = Dual2.const(c, N, m)
+        d.g[:, k] = 1.0
+        return d
+
+    def _lift(self, o):
+        return o if isinstance(o, Dual2) else Dual2.const(o, self.v.shape[0], self.g.shape[1])
+
+    def unary(self, f0, f1, f2):
+        gg = self.g[:, :, None] * self.g[:, None, :]
+        return Dual2(f0, f1[:, None] * self.g, f1[:, None, None] * self.h + f2[:, None, None] * gg)
+
+    def __add__(self, o):
+        o = self._lift(o)
+        return Dual2(self.v + o.v, self.g + o.g, self.h + o.h)
+    __radd__ = __add__
+
+    def __neg__(self):
+        return Dual2(-self.v, -self.g, -self.h)
+
+    def __sub__(self, o):
+        return self + (-self._lift(o))
+
+    def __rsub__(self, o):
+        return self._lift(o) - self
+
+    def __mul__(self, o):
+        o = self._lift(o)
+        cross = self.g[:, :, None] * o.g[:, None, :]
+        return Dual2(self.v * o.v, self.v[:, None] * o.g + o.v[:, None] * self.g,
+                     self.v[:, None, None] * o.h + o.v[:, None, None] * self.h + cross + cross.transpose(0, 2, 1))
+    __rmul__ = __mul__
+
+    def recip(self):
+        r = 1.0 / self.v
+        return self.unary(r, -r * r, 2 * r ** 3)
+
+    def __truediv__(self, o):
+        return self * self._lift(o).recip()
+
+    def __rtruediv__(self, o):
+        return self._lift(o) * self.recip()
+
+
+def d_sin(x):
+    return x.unary(np.sin(x.v), np.cos(x.v), -np.sin(x.v))
+
+
+def d_cos(x):
+    return x.unary(np.cos(x.v), -np.sin(x.v), -np.cos(x.v))
+
+
+def d_sqrt(x):
+    s = np.sqrt(x.v)
+    return x.unary(s, 0.5 / s, -0.25 / (s * x.v))
+
+
+def d_exp(x):
+    e = np.exp(x.v)
+    return x.unary(e, e, e)
+
+
+def d_atan2(y, x):
+    r2 = x * x + y * y
+    ay, ax = x / r2, -(y / r2)
+    out = Dual2(np.arctan2(y.v, x.v), ay.v[:, None] * y.g + ax.v[:, None] * x.g,
+                ay.v[:, None, None] * y.h + ax.v[:, None, None] * x.h + y.g[:, :, None] * ay.g[:, None, :] + x.g[:, :, None] * ax.g[:, None, :])
+    out.h = 0.5 * (out.h + out.h.transpose(0, 2, 1))
+    return out
+
+
+def _rv_uptotensor(self, theta):
+    """(logtarget, gradient, tensor = -Hessian) of the RV target with exact derivatives: forward-mode duals over the whole
+    expression of rv_model_keplerian.jl:9-51; the eccentric anomaly is solved in plain floating point and then refined by
+    two dual Newton steps (implicit differentiation of Kepler's equation; the reference differentiates through its Laguerre
+    iterations, which converge to the same derivatives)."""
+    theta = np.asarray(theta, dtype=np.float64)
+    m = len(theta)
+    if not self.is_valid(theta):
+        return -math.inf, np.full(m, np.nan), np.full((m, m), np.nan)
+    N = self.t.shape[0]
+    npl = self.num_planets(theta)
+    z = Dual2.var(theta[5 * npl], 5 * npl, N, m)                  # offset C
+    for pl in range(npl):
+        b = 5 * pl
+        P = d_exp(Dual2.var(theta[b], b, N, m)) - 1.0
+        K = d_exp(Dual2.var(theta[b + 1], b + 1, N, m)) - 1.0
+        h = Dual2.var(theta[b + 2], b + 2, N, m)
+        k = Dual2.var(theta[b + 3], b + 3, N, m)
+        wm = Dual2.var(theta[b + 4], b + 4, N, m)
+        ecc = d_sqrt(h * h + k * k)
+        w = d_atan2(k, h)
+        n = (2.0 * math.pi) / P
+        M = n * Dual2.const(self.t, N, m) - wm + w                # M = t n - M0, M0 = wpM0 - w
+        lam = w + M
+        E0 = kepler_laguerre(M.v, float(ecc.v[0]), tol=1e-14)
+        Mred = Dual2(np.mod(M.v, 2.0 * math.pi), M.g, M.h)
+        E = Dual2.const(E0, N, m)
+        for _ in range(2):
+            E = E - (E - ecc * d_sin(E) - Mred) / (1.0 - ecc * d_cos(E))
+        pp_, q = ecc * d_sin(E), ecc * d_cos(E)
+        j = d_sqrt((1.0 - ecc) * (1.0 + ecc))
+        z = z + K * j / (1.0 - q) * (d_cos(lam + pp_) - k * q / (1.0 + j))
+    s2 = self.s ** 2
+    r = z - Dual2.const(self.o, N, m)
+    chi = r * r
+    ll = -0.5 * float(np.sum(chi.v / s2)) - 0.5 * N * math.log(2 * math.pi) - 0.5 * float(np.sum(np.log(s2)))
+    g = -0.5 * np.sum(chi.g / s2[:, None], axis=0)
+    H = -0.5 * np.sum(chi.h / s2[:, None, None], axis=0)
+    lp = self.logprior(theta)
+    for pl in range(npl):                                          # log prior = const - sum(theta_P + theta_K): linear
+        g[5 * pl] -= 1.0
+        g[5 * pl + 1] -= 1.0
+    G = -H
+    return ll + lp, g, 0.5 * (G + G.T)
+
+
+RVModel.uptotensorlogtarget = _rv_uptotensor

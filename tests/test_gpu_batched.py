@@ -61,3 +61,75 @@ def test_batched_philox_mode_statistics(gamc, engine):
     assert np.all(np.abs(pooled.std(axis=1) - 1.0) < 0.25)
     # distinct chains got distinct random streams
     assert not np.array_equal(chains[0].value, chains[1].value)
+
+
+def _rv_perturb_scale(npl):
+    """make_param_perturb_scale, examples/radial_velocity/src/utils_ex.jl:23-46."""
+    return np.array([0.0001, 0.01, 0.05, 0.05, np.pi * 0.01] * npl + [0.3])
+
+
+@pytest.mark.parametrize("name,npl,nchains,nsteps", [("one_planet", 1, 4, 500), ("two_planets", 2, 2, 300)])
+def test_batched_rv_target_parity(gamc, engine, name, npl, nchains, nsteps):
+    """Radial-velocity example on the data shipped with the reference (tests/golden/rv_fixtures.json): in-kernel dual-number
+    gradient / Hessian + softabs against the NumPy dual-number oracle, chain by chain on shared tapes."""
+    import json
+    import os
+    import oracle as o
+    from oracle import targets as T
+    with open(os.path.join(os.path.dirname(__file__), "golden", "rv_fixtures.json")) as f:
+        d = json.load(f)[name]
+    p = 5 * npl + 1
+    truth = np.array(d["theta_true"])
+    rng = np.random.default_rng(21)
+    v0s = truth + 0.01 * _rv_perturb_scale(npl) * rng.standard_normal((nchains, p))     # one_planet/GAMC/simulations.jl:63
+    burnin = nsteps // 5
+    sched = gamc.rand_exp_decay_update(10.0)
+    sampler = gamc.GAMC(update=sched, transform=gamc.softabs(1000.0), driftstep=0.02, minorscale=0.001, c=0.01)
+    tuner = gamc.GAMCTuner(gamc.VanillaMCTuner(), gamc.VanillaMCTuner(), gamc.AcceptanceRateMCTuner(0.35))
+    tape = gamc.BatchedRandomTape(nchains, nsteps, p, seed=300)
+    model = gamc.RVModel(np.array(d["t"]), np.array(d["rv"]), np.array(d["sigma"]), nplanets=npl)
+    job = gamc.BatchedMCJob(model, sampler, gamc.BasicMCRange(nsteps, burnin), v0s, tuner=tuner, tape=tape, engine=engine)
+    job.run()
+    chains = job.output()
+    om = T.RVModel(d["t"], d["rv"], d["sigma"])
+    for c in range(nchains):
+        otuner = o.GAMCTuner(o.VanillaMCTuner(), o.VanillaMCTuner(), o.AcceptanceRateMCTuner(0.35))
+        sam = o.GAMCOracle(om, v0s[c], nsteps, burnin, update=sched.name, update_params=sched.params, transform=lambda H: T.softabs(H, 1000.0),
+                           driftstep=0.02, minorscale=0.001, c=0.01, tuner=otuner)
+        v, a, k = sam.run(o.RandomTape(nsteps, p, seed=300 + c))
+        assert np.array_equal(chains[c].diagnosticvalues.ravel(), a), f"chain {c}: accept/reject decisions diverged"
+        # tolerance: the softabs metric of this target has condition number 1e6 (one planet) to 1e8 (two planets), so
+        # rounding differences between the Jacobi (device) and LAPACK (oracle) eigen-decompositions are amplified accordingly
+        assert relerr(chains[c].value, v) <= (1e-6 if npl == 1 else 2e-5)
+        st, th = engine.batched_state(c)
+        assert st.updatetensorcount == sam.updatetensorcount and st.count == nsteps
+
+
+def test_batched_rv_many_epochs_derivatives(gamc, engine):
+    """Synthetic epochs (N = 20000, data_generation.jl:11-33 recipe): one SMMALA step from the truth must reproduce the
+    oracle's log-target after the step, i.e. the block-cooperative reduction over epochs is exact to FP64 rounding."""
+    import oracle as o
+    from oracle import targets as T
+    rng = np.random.default_rng(5)
+    N = 20000
+    t = np.sort(rng.uniform(0.0, 730.5, N))
+    truth = T.make_param_true_ex1()
+    sig = 2.0 * np.ones(N)
+    obs = T.RVModel(t, np.zeros(N), sig).model_rv(truth) + 2.0 * rng.standard_normal(N)
+    nsteps = 12
+    sampler = gamc.GAMC(update=gamc.smmala_only_update(), transform=gamc.softabs(1000.0), driftstep=0.02, minorscale=0.001, c=0.01)
+    tuner = gamc.GAMCTuner(gamc.VanillaMCTuner(), gamc.VanillaMCTuner(), gamc.AcceptanceRateMCTuner(0.35))
+    v0s = truth + 1e-5 * _rv_perturb_scale(1) * rng.standard_normal((2, 6))
+    tape = gamc.BatchedRandomTape(2, nsteps, 6, seed=9)
+    job = gamc.BatchedMCJob(gamc.RVModel(t, obs, sig, 1), sampler, gamc.BasicMCRange(nsteps, 0), v0s, tuner=tuner, tape=tape, engine=engine)
+    job.run()
+    chains = job.output()
+    om = T.RVModel(t, obs, sig)
+    for c in range(2):
+        sam = o.GAMCOracle(om, v0s[c], nsteps, 0, update="smmala_only_update!", transform=lambda H: T.softabs(H, 1000.0), driftstep=0.02,
+                           minorscale=0.001, c=0.01, tuner=o.GAMCTuner(o.VanillaMCTuner(), o.VanillaMCTuner(), o.AcceptanceRateMCTuner(0.35)))
+        v, a, _ = sam.run(o.RandomTape(nsteps, 6, seed=9 + c))
+        assert np.array_equal(chains[c].diagnosticvalues.ravel(), a)
+        assert relerr(chains[c].value, v) <= 1e-6
+        st, _ = engine.batched_state(c)
+        assert abs(st.logtarget - sam.logtarget) <= 1e-9 * abs(sam.logtarget)

@@ -79,3 +79,19 @@ def test_rv_truth_vectors_and_validity():
     th[2], th[3] = 0.8, 0.7                      # h^2 + k^2 >= 1  => -Inf (stat_model.jl:21)
     m = T.RVModel([0.0, 1.0], [0.0, 0.0], [2.0, 2.0])
     assert m.loglikelihood(th) == -math.inf and m.logtarget(th) == -math.inf
+
+
+def test_rv_dual_number_derivatives_match_finite_differences():
+    """Exact (dual-number) gradient and tensor of the RV log-target against central differences of the plain restatement."""
+    with open(os.path.join(GOLD, "rv_fixtures.json")) as f:
+        d = json.load(f)["one_planet"]
+    m = T.RVModel(d["t"], d["rv"], d["sigma"])
+    th = np.array(d["theta_true"]) + 0.01 * np.array([0.0001, 0.01, 0.05, 0.05, 0.03, 0.3])
+    lt, g, G = m.uptotensorlogtarget(th)
+    assert lt == pytest.approx(m.logtarget(th), rel=1e-13)
+    h = 1e-6
+    fd = np.array([(m.logtarget(th + h * e) - m.logtarget(th - h * e)) / (2 * h) for e in np.eye(6)])
+    assert relerr(g, fd) < 1e-6
+    H = np.array([(m.uptotensorlogtarget(th + h * e)[1] - m.uptotensorlogtarget(th - h * e)[1]) / (2 * h) for e in np.eye(6)])
+    assert relerr(G, -H) < 1e-6
+    assert np.array_equal(G, G.T)

@@ -1,0 +1,63 @@
+"""Throughput of the batched-chains kernel on the reference's t-distribution example scaled out to many chains
+(BASELINE.json configs[3] family; d <= 32 here -- d = 1024 needs the dense large-p batched path).
+  python tools/bench_batched.py [--n 20] [--chains 4096] [--steps 2000]
+Prints one JSON line: chain-iterations per second (device-timed, Philox tape generated in the kernel) and the CPU oracle's rate."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gamc_b200 as g  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=20)
+    ap.add_argument("--chains", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--cpu-steps", type=int, default=1500)
+    a = ap.parse_args()
+    import torch
+    rng = np.random.default_rng(0)
+    v0s = 2.0 * rng.standard_normal((a.chains, a.n))
+    sampler = g.GAMC(update=g.rand_exp_decay_update(10.0), transform=g.softabs(1000.0), driftstep=0.02, minorscale=0.001, c=0.01)
+    tuner = g.GAMCTuner(g.VanillaMCTuner(), g.VanillaMCTuner(), g.AcceptanceRateMCTuner(0.35))
+    eng = g.Engine(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    rngk = g.BasicMCRange(a.steps, a.steps // 5)
+    job = g.BatchedMCJob(g.MvTModel(n=a.n), sampler, g.BasicMCRange(50, 0), v0s, tuner=tuner, seed=1, engine=eng)
+    job.run()                                           # warm-up
+    job = g.BatchedMCJob(g.MvTModel(n=a.n), sampler, rngk, v0s, tuner=tuner, seed=1, engine=eng)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    eng.batched_run(a.steps, 1)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    chains = job.output()
+    acc = float(np.mean([c.diagnosticvalues.mean() for c in chains]))
+    # CPU oracle: one chain
+    import oracle as o
+    from oracle import targets as T
+    tgt = T.TTarget(n=a.n, nu=30.0)
+    sam = o.GAMCOracle(tgt, v0s[0], a.cpu_steps, 0, update="rand_exp_decay_update!", update_params=(10.0, 0.0), transform=lambda H: T.softabs(H, 1000.0),
+                       driftstep=0.02, minorscale=0.001, c=0.01, tuner=o.GAMCTuner(o.VanillaMCTuner(), o.VanillaMCTuner(), o.AcceptanceRateMCTuner(0.35)))
+    t0 = time.perf_counter()
+    sam.run(o.RandomTape(a.cpu_steps, a.n, seed=1))
+    cpu = a.cpu_steps / (time.perf_counter() - t0)
+    print(json.dumps({"metric": "gamc_chain_iters_per_sec", "value": a.chains * a.steps / (ms * 1e-3), "unit": "chain-iters/s", "n_gpus": 1,
+                      "config": {"workload": f"t-distribution example, n={a.n}, nu=30, softabs(1000), {a.chains} chains, GAMC rand_exp_decay(a=10)"},
+                      "ms_total": ms, "steps": a.steps, "acceptance": acc, "dtype": "f64",
+                      "cpu_baseline": {"value": cpu, "unit": "chain-iters/s", "cores": 1, "kind": "port", "sample": f"{a.cpu_steps} oracle transitions of one chain"}}))
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
