@@ -20,9 +20,13 @@ def main():
     ap.add_argument("--chains", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--cpu-steps", type=int, default=1500)
+    ap.add_argument("--workload", default="t", choices=["t", "rv"])
+    ap.add_argument("--logN", type=int, default=18, help="rv: log2 of the number of epochs")
     a = ap.parse_args()
     import torch
     rng = np.random.default_rng(0)
+    if a.workload == "rv":
+        return main_rv(a, rng, torch)
     v0s = 2.0 * rng.standard_normal((a.chains, a.n))
     sampler = g.GAMC(update=g.rand_exp_decay_update(10.0), transform=g.softabs(1000.0), driftstep=0.02, minorscale=0.001, c=0.01)
     tuner = g.GAMCTuner(g.VanillaMCTuner(), g.VanillaMCTuner(), g.AcceptanceRateMCTuner(0.35))
@@ -56,6 +60,54 @@ def main():
                       "config": {"workload": f"t-distribution example, n={a.n}, nu=30, softabs(1000), {a.chains} chains, GAMC rand_exp_decay(a=10)"},
                       "ms_total": ms, "steps": a.steps, "acceptance": acc, "dtype": "f64",
                       "cpu_baseline": {"value": cpu, "unit": "chain-iters/s", "cores": 1, "kind": "port", "sample": f"{a.cpu_steps} oracle transitions of one chain"}}))
+    eng.close()
+
+
+def main_rv(a, rng, torch):
+    """BASELINE.json configs[4]: Keplerian RV model on synthetic observations (N = 2^18 epochs), one planet, many chains."""
+    import oracle as o
+    from oracle import targets as T
+    N = 1 << a.logN
+    truth = T.make_param_true_ex1()
+    t = np.sort(rng.uniform(0.0, 730.5, N))                   # one_planet/data_generation.jl:16-18
+    sig = 2.0 * np.ones(N)                                    # :20-21
+    obs = T.RVModel(t, np.zeros(N), sig).model_rv(truth) + 2.0 * rng.standard_normal(N)   # :26
+    scale = np.array([0.0001, 0.01, 0.05, 0.05, np.pi * 0.01, 0.3])
+    v0s = truth + 0.01 * scale * rng.standard_normal((a.chains, 6)) / np.sqrt(N / 50.0)
+    sampler = g.GAMC(update=g.rand_exp_decay_update(10.0), transform=g.softabs(1000.0), driftstep=0.02, minorscale=0.001, c=0.01)
+    tuner = g.GAMCTuner(g.VanillaMCTuner(), g.VanillaMCTuner(), g.AcceptanceRateMCTuner(0.35))
+    eng = g.Engine(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    model = g.RVModel(t, obs, sig, 1)
+    job = g.BatchedMCJob(model, sampler, g.BasicMCRange(8, 0), v0s, tuner=tuner, seed=1, engine=eng)
+    job.run()
+    job = g.BatchedMCJob(model, sampler, g.BasicMCRange(a.steps, a.steps // 5), v0s, tuner=tuner, seed=1, engine=eng)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    eng.batched_run(a.steps, 1)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    chains = job.output()
+    acc = float(np.mean([c.diagnosticvalues.mean() for c in chains]))
+    st, _ = eng.batched_state(0)
+    # CPU oracle, one chain, a few transitions at full N
+    om = T.RVModel(t, obs, sig)
+    ncpu = 12
+    sam = o.GAMCOracle(om, v0s[0], ncpu, 0, update="mod_update!", update_params=(4,), transform=lambda H: T.softabs(H, 1000.0), driftstep=0.02,
+                       minorscale=0.001, c=0.01, tuner=o.GAMCTuner(o.VanillaMCTuner(), o.VanillaMCTuner(), o.AcceptanceRateMCTuner(0.35)))
+    t0 = time.perf_counter()
+    sam.run(o.RandomTape(ncpu, 6, seed=1))
+    cpu = ncpu / (time.perf_counter() - t0)
+    print(json.dumps({"metric": "gamc_chain_iters_per_sec", "value": a.chains * a.steps / (ms * 1e-3), "unit": "chain-iters/s", "n_gpus": 1,
+                      "config": {"workload": f"radial-velocity example, one planet, N=2^{a.logN} epochs, softabs(1000), {a.chains} chains, GAMC rand_exp_decay(a=10)"},
+                      "ms_total": ms, "steps": a.steps, "acceptance": acc, "n_smmala_chain0": int(st.updatetensorcount), "dtype": "f64",
+                      "epoch_evals_per_sec": a.chains * a.steps * N / (ms * 1e-3),
+                      "cpu_baseline": {"value": cpu, "unit": "chain-iters/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": f"{ncpu} oracle transitions (mod_update! n=4: 6 SMMALA / 6 AM) of one chain at full N"}}))
     eng.close()
 
 
