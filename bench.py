@@ -124,7 +124,7 @@ def theta_inputs(p):
 # ----------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (a NumPy restatement of the reference's Julia path; Julia itself is not in the image)
 # ----------------------------------------------------------------------------------------------------
-def cpu_iteration_costs(X, y, theta0, p, threads_note):
+def cpu_iteration_costs(X, y, theta0, p):
     """Times real oracle `iterate!` transitions at full N on the host cores, per kind:
     'am', 'smmala' (one tensor evaluation) and 'smmala_stale' (two: the step after an AM step re-evaluates)."""
     import oracle as o
@@ -182,7 +182,7 @@ def run_reference(args):
     tt, theta0 = theta_inputs(p)
     y = (rng.random(N) < 1.0 / (1.0 + np.exp(-(X @ tt)))).astype(np.float64)
     gen_s = time.perf_counter() - t0
-    costs = cpu_iteration_costs(X, y, theta0, p, "")
+    costs = cpu_iteration_costs(X, y, theta0, p)
     kinds = host_kinds(args.steps, SEED + 2)
     rate, total = compose_cpu_rate(costs, kinds)
     cores = os.cpu_count()
@@ -338,7 +338,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         Xh, yh = eng.read_rows(0, N)      # identical data: read the device-generated shard back
-        costs = cpu_iteration_costs(Xh, yh, theta0, p, "")
+        costs = cpu_iteration_costs(Xh, yh, theta0, p)
         rate, _ = compose_cpu_rate(costs, kinds)
         cpu = {"value": rate, "unit": "iters/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"14 real oracle iterate! transitions at full N=2^{args.logN}, p={p} (reference-shaped callbacks), per-kind means "

@@ -12,7 +12,7 @@ from . import _lib
 from .engine import Engine
 from .frontend import *  # noqa: F401,F403
 from .frontend import __all__ as _fe_all
-from .stats import ess, mcvar_imse, summary  # noqa: F401
+from .stats import ess, mcvar_imse, summary, write_chain_csv, write_run_csvs, table  # noqa: F401
 
-__all__ = ["Engine", "ess", "mcvar_imse", "summary"] + list(_fe_all)
+__all__ = ["Engine", "ess", "mcvar_imse", "summary", "write_chain_csv", "write_run_csvs", "table"] + list(_fe_all)
 __version__ = "0.1.0"

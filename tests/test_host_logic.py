@@ -135,3 +135,22 @@ def test_gloo_world2_sharded_reduce_matches_whole():
         assert relerr(buf, whole) < 1e-12
         assert np.array_equal(uid, np.arange(128, dtype=np.uint8))
     assert np.array_equal(res[0][1], res[1][1])      # every rank holds the bit-identical reduced payload
+
+
+def test_csv_pipeline_roundtrip(gamc, tmp_path):
+    """chainNN.csv / diagnosticsNN.csv / times.csv / summary.* in the reference's formats
+    (examples/logistic_regression/src/GAMC/simulations.jl:81-95, GAMC/table.jl:21-53)."""
+    rng = np.random.default_rng(1)
+    d = str(tmp_path)
+    chains = [rng.standard_normal((4, 800)) for _ in range(3)]
+    accs = [rng.random(800) < 0.3 for _ in range(3)]
+    for i in range(3):
+        gamc.write_chain_csv(d, i + 1, chains[i], accs[i])
+    gamc.write_run_csvs(d, [1.0, 2.0, 3.0], [0.1, 0.2, 0.3], [10, 11, 12])
+    res = gamc.table(d, 3)
+    assert res["rate"] == pytest.approx(np.mean([a.mean() for a in accs]))
+    assert relerr(res["ess"], np.mean([gamc.ess(c) for c in chains], axis=0)) < 1e-12
+    assert res["time"] == 2.0 and res["efficiency"] == pytest.approx(res["ess"].min() / 2.0)
+    assert np.array_equal(np.loadtxt(os.path.join(d, "chain02.csv"), delimiter=","), chains[1])
+    assert open(os.path.join(d, "diagnostics01.csv")).readline().strip() in ("true", "false")
+    assert len(open(os.path.join(d, "summary.txt")).read().split(" & ")) == 1 + 4 + 2
