@@ -92,7 +92,7 @@ def _run_both(gamc, engine, N, p, nsteps, burnin, seed, am_mode=0, update=None, 
 
 
 @pytest.mark.parametrize("am_mode", [0, 1])
-@pytest.mark.parametrize("N,p,nsteps", [(200, 4, 3000), (500, 33, 1200), (2000, 64, 1000), (3000, 130, 1000)])
+@pytest.mark.parametrize("N,p,nsteps", [(200, 4, 3000), (500, 33, 1200), (2000, 64, 1000), (3000, 130, 1000), (6000, 256, 300), (4000, 512, 120)])
 def test_trajectory_parity(gamc, engine, N, p, nsteps, am_mode):
     """Same host-drawn normals and uniforms => step-for-step agreement for >= 1000 iterations.
     am_mode 0 = literal covariance recursion + Cholesky per AM step; 1 = rank-one Cholesky update (fast path)."""
@@ -159,3 +159,24 @@ def test_errors(gamc, engine):
         gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, rng_, {"p": np.array([np.nan, 0.0, 0.0])}, tuner=tuner, engine=engine)
     with pytest.raises(gamc._lib.UnsupportedShape):
         engine.target_logistic(np.zeros((10, 513)), np.zeros(10), 100.0)
+
+
+@pytest.mark.parametrize("am_mode", [0, 1])
+def test_am_before_enough_history_raises_posdef(gamc, engine, am_mode):
+    """t0 = 1 lets an AM step run at t = 2/3, where Klara's covariance recursion has k = 0/1 and the proposal covariance
+    is not positive definite: the reference throws from the MvNormal constructor (set_gmm, GAMC.jl:188); here the device
+    raises GAMC_NOT_POSDEF, reported at the next synchronising call."""
+    import oracle as o
+    X, y, tt = o.synth_logistic(2, 200, 4)
+    engine.target_logistic(X, y, 100.0)
+    sampler = gamc.GAMC(update=gamc.am_only_update(), driftstep=0.02, minorscale=0.001, c=0.01, t0=1, am_mode=am_mode)
+    tuner = gamc.GAMCTuner(gamc.VanillaMCTuner(), gamc.VanillaMCTuner(), gamc.AcceptanceRateMCTuner(0.35))
+    job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, gamc.BasicMCRange(10, 0), {"p": tt}, tuner=tuner,
+                          tape=gamc.RandomTape(10, 4, seed=1), engine=engine)
+    with pytest.raises(gamc._lib.PosDefError):
+        job.run()
+    # the oracle (the reference's semantics) fails at the same place
+    osam = o.GAMCOracle(o.LogisticTarget(X, y, 100.0), tt, 10, 0, update="am_only_update!", driftstep=0.02, minorscale=0.001, c=0.01, t0=1)
+    with pytest.raises((o.sampler.NotPosDef, ZeroDivisionError, FloatingPointError, np.linalg.LinAlgError)):
+        with np.errstate(all="ignore"):
+            osam.run(o.RandomTape(10, 4, seed=1))
