@@ -115,8 +115,7 @@ def bench_config(gamc, nsteps, am_mode):
 
 
 def theta_inputs(p):
-    import oracle.logistic as ol   # data definition shared with the checker (host-side NumPy only)
-    tt = ol.synth_theta_true(SEED, p)
+    tt = np.random.Generator(np.random.PCG64(SEED)).standard_normal(p) / np.sqrt(p)   # == gamc_b200.synth_theta_true(SEED, p)
     theta0 = tt + 0.01 * np.random.Generator(np.random.PCG64(SEED + 1)).standard_normal(p)
     return tt, theta0
 
@@ -172,7 +171,6 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle.logistic as ol
     N, p = 1 << args.logN, args.p
     t0 = time.perf_counter()
     rng = np.random.Generator(np.random.PCG64(SEED))

@@ -58,7 +58,7 @@ class Config(C.Structure):
         ("t0", C.c_int32), ("schedule", C.c_int32), ("sched_params", C.c_double * 3),
         ("total_tuner_kind", C.c_int32), ("targetrate", C.c_double), ("score_k", C.c_double),
         ("period", C.c_int32), ("verbose_total", C.c_int32), ("verbose_smmala", C.c_int32), ("verbose_am", C.c_int32),
-        ("nsteps", C.c_int64), ("burnin", C.c_int64), ("am_mode", C.c_int32), ("reserved", C.c_int32),
+        ("nsteps", C.c_int64), ("burnin", C.c_int64), ("am_mode", C.c_int32), ("sampler_kind", C.c_int32),
     ]
 
 

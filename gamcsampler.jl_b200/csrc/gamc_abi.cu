@@ -679,6 +679,7 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   REQUIRE(h, cfg->schedule >= 0 && cfg->schedule <= GAMC_SCHED_RAND_QUAD_DECAY, GAMC_INVALID_ARG, "unknown schedule");
   REQUIRE(h, cfg->period >= 1 && cfg->nsteps >= 1 && cfg->burnin >= 0, GAMC_INVALID_ARG, "bad period / nsteps / burnin");
   REQUIRE(h, cfg->am_mode == 0 || cfg->am_mode == 1, GAMC_INVALID_ARG, "am_mode must be 0 or 1");
+  REQUIRE(h, cfg->sampler_kind == 0 || cfg->sampler_kind == 1, GAMC_INVALID_ARG, "sampler_kind must be 0 (GAMC) or 1 (MALA)");
   cudaSetDevice(h->device);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   DEBUG_POINT(h, "sampler_init entry");
@@ -730,11 +731,20 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   gamc_status s = set_step_attrs(h);
   if (s != GAMC_OK) return s;
   DEBUG_POINT(h, "sampler_init after attrs");
-  // initialize! (:157-176): first evaluation of target + gradient + metric at theta0
-  s = eval_device(h, B.theta, 2, true);
-  if (s != GAMC_OK) return s;
-  s = launch_step(h, k_sampler_init, B, T);
-  if (s != GAMC_OK) return s;
+  if (cfg->sampler_kind == 1) {
+    // MALA: log-target + gradient only
+    s = eval_device(h, B.theta, 1, true);
+    if (s != GAMC_OK) return s;
+    ProfScope ps(h, GAMC_K_LINALG);
+    k_mala_init<<<1, 256, 0, h->stream>>>(B, T);
+    CUDA_TRY(h, cudaGetLastError());
+  } else {
+    // initialize! (:157-176): first evaluation of target + gradient + metric at theta0
+    s = eval_device(h, B.theta, 2, true);
+    if (s != GAMC_OK) return s;
+    s = launch_step(h, k_sampler_init, B, T);
+    if (s != GAMC_OK) return s;
+  }
   h->h_count = 0; h->h_present = true; h->h_past = false;   // MuvGAMCState outer ctor (:117-118)
   h->tape_n = 0; h->tape_pos = 0;
   h->sampler_ready = true;
@@ -786,6 +796,7 @@ gamc_status gamc_peek_kinds(gamc_handle h, int64_t n, uint8_t* kinds_out) {
   if (!h) return GAMC_INVALID_ARG;
   REQUIRE(h, h->sampler_ready, GAMC_NOT_READY, "sampler not initialised");
   REQUIRE(h, kinds_out && n >= 0 && h->tape_pos + n <= h->tape_n, GAMC_INVALID_ARG, "gamc_peek_kinds: tape too short");
+  if (h->cfg.sampler_kind == 1) { for (long long k = 0; k < n; ++k) kinds_out[k] = 2; return GAMC_OK; }   // MALA steps
   bool present = h->h_present;
   for (long long k = 0; k < n; ++k) {
     const long long t = h->h_count + k + 1;
@@ -803,6 +814,16 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
   Bufs& B = h->B;
   const TuneCfg& T = h->tune;
   gamc_status s;
+  if (h->cfg.sampler_kind == 1) {   // MALA: pre -> fused log-lik + gradient pass -> post
+    for (long long k = 0; k < n; ++k) {
+      ++h->h_count;
+      const long long ti = h->tape_pos++;
+      { ProfScope ps(h, GAMC_K_LINALG); k_mala_pre<<<1, 256, 0, h->stream>>>(B, T, ti); CUDA_TRY(h, cudaGetLastError()); }
+      s = eval_device(h, B.theta_prop, 1, true); if (s != GAMC_OK) return s;
+      { ProfScope ps(h, GAMC_K_LINALG); k_mala_post<<<1, 256, 0, h->stream>>>(B, T, ti); CUDA_TRY(h, cudaGetLastError()); }
+    }
+    return GAMC_OK;
+  }
   for (long long k = 0; k < n; ++k) {
     const long long t = ++h->h_count;                                                    // iterate/GAMC.jl:2
     const long long ti = h->tape_pos++;

@@ -566,6 +566,78 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, lo
 }
 
 // ---------------------------------------------------------------------------------------------------
+// MALA (identity metric): Klara's comparison sampler, the baseline of the reference's efficiency tables
+// (examples/logistic_regression/src/MALA/simulations.jl:37-41, examples/logistic_regression/src/table.jl:9-17).  Needs only
+// the fused log-likelihood + gradient pass (no metric, no factorisation):
+//   mu = theta + eps/2 grad;  theta* = mu + sqrt(eps) z;  mu* = theta* + eps/2 grad*
+//   log alpha = lt* - lt + |theta* - mu|^2/(2 eps) - |theta - mu*|^2/(2 eps)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mala_init(Bufs B, TuneCfg T) {
+  __shared__ double red[40];
+  DevState* st = B.st;
+  const int p = T.p;
+  const double lp = log_prior(B.theta, p, T.lambda, red);
+  double bad = 0.0;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) {
+    const double g = B.R[1 + i] - B.theta[i] / T.lambda;
+    B.gs[i] = g;
+    B.lastmean[i] = B.theta[i];
+    if (!isfinite(g)) bad = 1.0;
+  }
+  bad = block_sum(bad, red);
+  const double lt = B.R[0] + lp;
+  if (threadIdx.x == 0) {
+    st->logtarget = lt; st->cur = 0;
+    if (bad != 0.0 || !isfinite(lt)) { st->error_flag = 2; st->error_iter = 0; }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_mala_pre(Bufs B, TuneCfg T, long long tape_idx) {
+  DevState* st = B.st;
+  const int p = T.p;
+  if (st->error_flag) return;
+  if (threadIdx.x == 0) { st->count += 1; if (T.tuning) st->tot_prop += 1; }
+  const double eps = st->step, sq = st->sqrtstep;
+  const double* z = B.tape_z + (size_t)tape_idx * p;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) {
+    const double m = B.theta[i] + 0.5 * eps * B.gs[i];
+    B.mu[i] = m;
+    B.theta_prop[i] = m + sq * z[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_mala_post(Bufs B, TuneCfg T, long long tape_idx) {
+  __shared__ double red[40];
+  DevState* st = B.st;
+  const int p = T.p;
+  if (st->error_flag) return;
+  const double eps = st->step;
+  const double lt_p = B.R[0] + log_prior(B.theta_prop, p, T.lambda, red);
+  double q1 = 0.0, q2 = 0.0, bad = 0.0;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) {
+    const double gp = B.R[1 + i] - B.theta_prop[i] / T.lambda;
+    B.gs[p + i] = gp;                                     // proposal-slot gradient
+    if (!isfinite(gp)) bad = 1.0;
+    const double d1 = B.theta_prop[i] - B.mu[i];
+    const double d2 = B.theta[i] - (B.theta_prop[i] + 0.5 * eps * gp);
+    q1 = fma(d1, d1, q1); q2 = fma(d2, d2, q2);
+  }
+  q1 = block_sum(q1, red); q2 = block_sum(q2, red); bad = block_sum(bad, red);
+  double ratio = -INFINITY;
+  if (bad == 0.0 && isfinite(lt_p)) ratio = lt_p - st->logtarget + q1 / (2.0 * eps) - q2 / (2.0 * eps);
+  const int accept = (ratio > 0.0) || (ratio > log(B.tape_uacc[tape_idx]));
+  __syncthreads();
+  if (accept) for (int i = threadIdx.x; i < p; i += blockDim.x) { B.theta[i] = B.theta_prop[i]; B.gs[i] = B.gs[p + i]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->ratio = ratio;
+    if (accept) { st->logtarget = lt_p; if (T.count_total) st->tot_acc += 1; }
+  }
+  __syncthreads();
+  step_tail(B, T, accept);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // SMMALA -> AM hand-over: sstate.oldinvtensor = inv(G) seeds the AM covariance recursion
 // (iterate/GAMC.jl:26,92,133).  W = Lm^-1 (M space, one column per warp, column-oriented substitution with
 // one-step-ahead prefetch), then inv(G) = W' W.

@@ -23,12 +23,12 @@ from . import _lib as L
 from .engine import Engine
 
 __all__ = [
-    "GAMC", "GAMCTuner", "GAMCTune", "BasicMCTune", "VanillaMCTuner", "AcceptanceRateMCTuner", "logistic_rate_score",
+    "MALA", "GAMC", "GAMCTuner", "GAMCTune", "BasicMCTune", "VanillaMCTuner", "AcceptanceRateMCTuner", "logistic_rate_score",
     "am_only_update", "smmala_only_update", "mod_update", "rand_update", "cos_update", "rand_exp_decay_update",
     "rand_lin_decay_update", "rand_pow_decay_update", "rand_quad_decay_update",
     "exp_decay", "lin_decay", "pow_decay", "quad_decay",
     "BasicMCRange", "LogisticModel", "BasicMCJob", "Chain", "run", "output", "acceptance", "RandomTape",
-    "softabs", "Softabs", "MvTModel", "RVModel", "BatchedMCJob", "BatchedRandomTape",
+    "synth_theta_true", "softabs", "Softabs", "MvTModel", "RVModel", "BatchedMCJob", "BatchedRandomTape",
 ]
 
 
@@ -180,6 +180,19 @@ class GAMC:
                 f"weight of stabilizing mixture component = {self.c}")
 
 
+class MALA:
+    """Klara's `MALA(driftstep)` (examples/logistic_regression/src/MALA/simulations.jl:37), the baseline the reference's
+    efficiency tables are normalised by (examples/logistic_regression/src/table.jl:9-17).  Use with a plain tuner, e.g.
+    `AcceptanceRateMCTuner(0.574, score_k=3.)` (:41)."""
+
+    def __init__(self, driftstep=1.0):
+        assert driftstep > 0, "Drift step is not positive"
+        self.driftstep = float(driftstep)
+
+    def __repr__(self):
+        return f"MALA sampler: drift step = {self.driftstep}"
+
+
 @dataclass
 class BasicMCRange:
     nsteps: int
@@ -196,6 +209,11 @@ class LogisticModel:
     synth: Optional[dict] = None   # {"seed":..., "N":..., "p":..., "theta_true":..., "row0": 0, "nrows": N}
 
 
+def synth_theta_true(seed, p):
+    """theta_true[j] ~ N(0, 1/p) of the synthetic logistic workloads: NumPy Generator(PCG64(seed))."""
+    return np.random.Generator(np.random.PCG64(seed)).standard_normal(p) / np.sqrt(p)
+
+
 class RandomTape:
     """Host-drawn normals and uniforms in fixed per-iteration slots."""
 
@@ -208,7 +226,21 @@ class RandomTape:
         self.z = rng.standard_normal((nsteps, p))
 
 
-def make_config(sampler: GAMC, tuner: GAMCTuner, mcrange: BasicMCRange) -> L.Config:
+def make_config(sampler, tuner, mcrange: BasicMCRange) -> L.Config:
+    if isinstance(sampler, MALA):
+        tt = tuner if not isinstance(tuner, GAMCTuner) else tuner.totaltuner
+        cfg = L.Config()
+        cfg.driftstep, cfg.minorscale, cfg.c, cfg.t0, cfg.schedule = sampler.driftstep, 1.0, 0.0, 1, 1
+        for i in range(3):
+            cfg.sched_params[i] = float("nan")
+        cfg.total_tuner_kind = 1 if isinstance(tt, AcceptanceRateMCTuner) else 0
+        cfg.targetrate = getattr(tt, "targetrate", float("nan"))
+        cfg.score_k = getattr(tt, "score_k", 7.0)
+        cfg.period = int(tt.period)
+        cfg.verbose_total = int(bool(tt.verbose))
+        cfg.nsteps, cfg.burnin = int(mcrange.nsteps), int(mcrange.burnin)
+        cfg.sampler_kind = 1
+        return cfg
     cfg = L.Config()
     cfg.driftstep, cfg.minorscale, cfg.c, cfg.t0 = sampler.driftstep, sampler.minorscale, sampler.c, sampler.t0
     cfg.schedule = sampler.update.kind

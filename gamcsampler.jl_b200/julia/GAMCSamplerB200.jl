@@ -112,7 +112,7 @@ struct CConfig
   targetrate::Cdouble; score_k::Cdouble
   period::Int32; verbose_total::Int32; verbose_smmala::Int32; verbose_am::Int32
   nsteps::Int64; burnin::Int64
-  am_mode::Int32; reserved::Int32
+  am_mode::Int32; sampler_kind::Int32
 end
 struct CState
   count::Int64; updatetensorcount::Int64; step::Cdouble; sqrttunestep::Cdouble

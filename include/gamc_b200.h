@@ -72,7 +72,8 @@ typedef struct {
   int64_t burnin;          /* BasicMCRange.burnin                                                  */
   int32_t am_mode;         /* 0 = literal covariance recursion + Cholesky each AM step,
                               1 = rank-one Cholesky update of the same recursion (fast path)       */
-  int32_t reserved;
+  int32_t sampler_kind;    /* 0 = GAMC, 1 = MALA (Klara's comparison sampler, examples/logistic_regression/src/MALA/simulations.jl:37;
+                              identity metric: only driftstep, the total tuner and the range are used)          */
 } gamc_config;
 
 /* Snapshot of the scalar sampler state: fields of MuvGAMCState / GAMCTune that the reference exposes

@@ -18,7 +18,7 @@ from .logistic import (  # noqa: F401
     logistic_partials, LogisticTarget, synth_logistic,
 )
 from .sampler import (  # noqa: F401
-    GAMCOracle, RandomTape, BasicMCTune, VanillaMCTuner, AcceptanceRateMCTuner, GAMCTuner,
+    GAMCOracle, MALAOracle, RandomTape, BasicMCTune, VanillaMCTuner, AcceptanceRateMCTuner, GAMCTuner,
     logistic_rate_score, covariance_update, recursive_mean, gmm_logpdf,
     exp_decay, lin_decay, pow_decay, quad_decay, SCHEDULES, schedule_probability,
 )

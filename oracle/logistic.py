@@ -103,6 +103,13 @@ class LogisticTarget:
     def logtarget(self, theta):
         return ploglikelihood(theta, self.X, self.y) + plogprior(theta, self.lam)
 
+    def uptogradlogtarget(self, theta):
+        """Klara closure `parameter.uptogradlogtarget!` (what MALA calls): log-target and gradient."""
+        if self.reference_shaped:
+            return (ploglikelihood(theta, self.X, self.y) + plogprior(theta, self.lam), pgradlogtarget(theta, self.X, self.y, self.lam))
+        ll, g, _ = logistic_partials(theta, self.X, self.y, want_tensor=False)
+        return ll + plogprior(theta, self.lam), g - theta / self.lam
+
     def uptotensorlogtarget(self, theta):
         if self.reference_shaped:
             lt = ploglikelihood(theta, self.X, self.y) + plogprior(theta, self.lam)

@@ -23,7 +23,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 __all__ = [
-    "RandomTape", "BasicMCTune", "VanillaMCTuner", "AcceptanceRateMCTuner", "GAMCTuner", "GAMCTune",
+    "MALAOracle", "RandomTape", "BasicMCTune", "VanillaMCTuner", "AcceptanceRateMCTuner", "GAMCTuner", "GAMCTune",
     "logistic_rate_score", "covariance_update", "recursive_mean", "gmm_logpdf", "GAMCOracle",
     "exp_decay", "lin_decay", "pow_decay", "quad_decay", "SCHEDULES", "schedule_probability",
 ]
@@ -442,3 +442,71 @@ def _logdet(A):
     if sign <= 0:
         raise NotPosDef("logdet of a matrix with non-positive determinant")
     return float(ld)
+
+
+class MALAOracle:
+    """Klara's MALA sampler (the baseline of the reference's efficiency tables: `MALA(0.02)` with
+    `AcceptanceRateMCTuner(0.574, score=x->logistic_rate_score(x, 3.))`, examples/logistic_regression/src/MALA/simulations.jl:37-41).
+    Klara.jl is not vendored; restated from the published algorithm (Roberts & Tweedie 1996):
+        mu = theta + eps/2 grad(theta);  theta* = mu + sqrt(eps) z;  mu* = theta* + eps/2 grad(theta*)
+        log alpha = lt* - lt + |theta* - mu|^2/(2 eps) - |theta - mu*|^2/(2 eps)
+    Tuning (every `period` proposals while totproposed <= burnin) as for the total tuner of GAMC.  `target` needs
+    `.uptogradlogtarget(theta) -> (lt, grad)`."""
+
+    def __init__(self, target, theta0, nsteps, burnin=0, driftstep=1.0, tuner=None):
+        assert driftstep > 0, "Drift step is not positive"
+        self.target, self.nsteps, self.burnin = target, int(nsteps), int(burnin)
+        self.tuner = tuner if tuner is not None else VanillaMCTuner()
+        self.theta = np.array(theta0, dtype=np.float64)
+        self.p = self.theta.shape[0]
+        self.logtarget, self.grad = target.uptogradlogtarget(self.theta)
+        assert math.isfinite(self.logtarget) and np.all(np.isfinite(self.grad)), "initial values out of support"
+        self.tune = BasicMCTune(float(driftstep), 0, 0, self.tuner.period)
+        self.sqrttunestep = math.sqrt(driftstep)
+        self.count = 0
+
+    @property
+    def _tuning(self):
+        return self.tuner.verbose or isinstance(self.tuner, AcceptanceRateMCTuner)
+
+    def iterate(self, tape):
+        self.count += 1
+        t = self.count
+        if self._tuning:
+            self.tune.proposed += 1
+        eps = self.tune.step
+        mu = self.theta + 0.5 * eps * self.grad
+        prop = mu + self.sqrttunestep * tape.z[t - 1]
+        lt_p, g_p = self.target.uptogradlogtarget(prop)
+        if math.isfinite(lt_p) and np.all(np.isfinite(g_p)):
+            mu_p = prop + 0.5 * eps * g_p
+            d1, d2 = prop - mu, self.theta - mu_p
+            ratio = lt_p - self.logtarget + float(d1 @ d1) / (2 * eps) - float(d2 @ d2) / (2 * eps)
+        else:
+            ratio = -math.inf
+        acc = ratio > 0 or ratio > math.log(tape.u_acc[t - 1])
+        if acc:
+            self.theta, self.logtarget, self.grad = prop.copy(), lt_p, g_p
+            if self._tuning:
+                self.tune.accepted += 1
+        if self._tuning:
+            tt = self.tune
+            if tt.totproposed <= self.burnin and tt.proposed % self.tuner.period == 0:
+                tt.rate = tt.accepted / tt.proposed
+                if isinstance(self.tuner, AcceptanceRateMCTuner):
+                    tt.step *= self.tuner.score(tt.rate - self.tuner.targetrate)
+                    self.sqrttunestep = math.sqrt(tt.step)
+                tt.totproposed += tt.proposed
+                tt.proposed, tt.accepted, tt.rate = 0, 0, float("nan")
+        return acc
+
+    def run(self, tape):
+        nsave = max(0, self.nsteps - self.burnin)
+        value = np.empty((self.p, nsave))
+        accept = np.empty(nsave, dtype=bool)
+        for i in range(1, self.nsteps + 1):
+            acc = self.iterate(tape)
+            if i > self.burnin:
+                value[:, i - self.burnin - 1] = self.theta
+                accept[i - self.burnin - 1] = acc
+        return value, accept

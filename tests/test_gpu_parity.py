@@ -180,3 +180,25 @@ def test_am_before_enough_history_raises_posdef(gamc, engine, am_mode):
     with pytest.raises((o.sampler.NotPosDef, ZeroDivisionError, FloatingPointError, np.linalg.LinAlgError)):
         with np.errstate(all="ignore"):
             osam.run(o.RandomTape(10, 4, seed=1))
+
+
+@pytest.mark.parametrize("N,p,nsteps", [(300, 5, 2000), (3000, 100, 600)])
+def test_mala_trajectory_parity(gamc, engine, N, p, nsteps):
+    """Klara's MALA (the baseline of the reference's efficiency tables) on the fused log-lik + gradient pass."""
+    import oracle as o
+    X, y, tt = o.synth_logistic(77, N, p)
+    theta0 = tt + 0.05 * np.random.default_rng(1).standard_normal(p)
+    burnin = nsteps // 4
+    engine.target_logistic(X, y, 100.0)
+    tuner = gamc.AcceptanceRateMCTuner(0.574, score_k=3.0)          # MALA/simulations.jl:41
+    tape = gamc.RandomTape(nsteps, p, seed=12)
+    job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), gamc.MALA(0.02), gamc.BasicMCRange(nsteps, burnin), {"p": theta0}, tuner=tuner,
+                          tape=tape, engine=engine)
+    job.run()
+    chain = job.output()
+    osam = o.MALAOracle(o.LogisticTarget(X, y, 100.0), theta0, nsteps, burnin, driftstep=0.02, tuner=o.AcceptanceRateMCTuner(0.574, score_k=3.0))
+    v, a = osam.run(o.RandomTape(nsteps, p, seed=12))
+    assert np.array_equal(chain.diagnosticvalues.ravel(), a)
+    assert relerr(chain.value, v) <= 1e-9
+    st = job.engine.state()
+    assert abs(st.step - osam.tune.step) <= 1e-12 * osam.tune.step and st.count == nsteps
