@@ -43,8 +43,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--logN", type=int, default=20, help="log2 of rows per GPU (default 2^20 = BASELINE C2)")
     ap.add_argument("--p", type=int, default=256)
-    ap.add_argument("--am-mode", type=int, default=int(os.environ.get("GAMC_AM_MODE", "1")),
-                    help="1 = rank-one Cholesky update per AM step (default), 0 = literal covariance recursion + Cholesky")
+    ap.add_argument("--am-mode", type=int, default=int(os.environ.get("GAMC_AM_MODE", "2")),
+                    help="2 = rank-one Cholesky update, computed speculatively for both outcomes while the data pass runs (default; bit-identical to 1); "
+                         "1 = rank-one update on the critical path; 0 = literal covariance recursion + Cholesky")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

@@ -46,8 +46,10 @@ struct BatchedCfg {
 };
 
 // ---- per-chain state layout in shared memory (doubles) ------------------------------------------------------------
-enum { BV_THETA = 0, BV_PROP, BV_GC, BV_GP, BV_FC, BV_FP, BV_MU, BV_M1, BV_M2, BV_Z, BV_T1, BV_T2, BV_NVEC };
-enum { BM_GC = 0, BM_IC, BM_LC, BM_GP, BM_IP, BM_LP, BM_LAM, BM_W, BM_NMAT };
+enum { BV_THETA = 0, BV_PROP, BV_GC, BV_GP, BV_FC, BV_FP, BV_MU, BV_M1, BV_M2, BV_Z, BV_T1, BV_T2, BV_ROT0, BV_ROT1, BV_ROT2, BV_NVEC };   // T2, ROT0..2 are contiguous: softabs scratch
+// The evaluation scratch W aliases the proposal-slot metric (the Jacobi input is dead once its eigenvalues are saved) and the
+// AM factor aliases the proposal-slot factor (never live together): 6 matrices per chain instead of 8.
+enum { BM_GC = 0, BM_IC, BM_LC, BM_GP, BM_IP, BM_LP, BM_NMAT, BM_LAM = BM_LP, BM_W = BM_GP };
 enum { BS_LT = 0, BS_LTP, BS_LDC, BS_LDP, BS_STEP, BS_SQSTEP, BS_RATIO, BS_COUNT, BS_UPD, BS_TACC, BS_TPROP, BS_TTOT, BS_TRATE,
        BS_SMACC, BS_SMPROP, BS_SMTOT, BS_AMACC, BS_AMPROP, BS_AMTOT, BS_PAST, BS_PRESENT, BS_ERR, BS_SAVED, BS_NSCAL = 24 };
 
@@ -83,17 +85,17 @@ __device__ inline double w_chol(double* A, int p, int ld, int lane) {
   return bad ? nan("") : slog;
 }
 
-// Inv = (L L')^-1, lane j computes column j with two substitutions; W = p x ld scratch. Result symmetric (averaged).
-__device__ inline void w_inv_from_chol(const double* L, double* Inv, double* W, int p, int ld, int lane) {
+// Inv = (L L')^-1, lane j computes column j with two substitutions, in place in Inv.  Result symmetric (averaged).
+__device__ inline void w_inv_from_chol(const double* L, double* Inv, int p, int ld, int lane) {
   if (lane < p) {
     const int j = lane;
     for (int i = 0; i < p; ++i) {            // L y = e_j
       double s = (i == j) ? 1.0 : 0.0;
-      for (int k = 0; k < i; ++k) s = fma(-L[i * ld + k], W[k * ld + j], s);
-      W[i * ld + j] = s / L[i * ld + i];
+      for (int k = 0; k < i; ++k) s = fma(-L[i * ld + k], Inv[k * ld + j], s);
+      Inv[i * ld + j] = s / L[i * ld + i];
     }
     for (int i = p - 1; i >= 0; --i) {       // L' x = y
-      double s = W[i * ld + j];
+      double s = Inv[i * ld + j];
       for (int k = i + 1; k < p; ++k) s = fma(-L[k * ld + i], Inv[k * ld + j], s);
       Inv[i * ld + j] = s / L[i * ld + i];
     }
@@ -126,57 +128,79 @@ __device__ inline double w_dot(const double* a, const double* b, int p, int lane
   return warp_sum(s);
 }
 
-// Cyclic Jacobi eigen-decomposition of the symmetric matrix A (destroyed: eigenvalues end on its diagonal), Q = vectors.
-__device__ inline void w_jacobi(double* A, double* Q, int p, int ld, int lane) {
+// Jacobi eigen-decomposition of the symmetric matrix A (destroyed: eigenvalues end on its diagonal), Q = vectors.
+// Parallel (round-robin tournament) ordering: each step rotates p/2 DISJOINT index pairs at once -- lanes k < p/2 compute
+// the rotation of pair k, then A <- A J (lane = row), A <- J' A (lane = column), Q <- Q J (lane = row), all conflict-free.
+// rot = 3 * 16 doubles of shared scratch (cos, sin, pair indices).
+__device__ inline void w_jacobi(double* A, double* Q, int p, int ld, int lane, double* rot) {
   if (lane < p) for (int j = 0; j < p; ++j) Q[lane * ld + j] = (lane == j) ? 1.0 : 0.0;
   __syncwarp();
-  for (int sweep = 0; sweep < 30; ++sweep) {
+  if (p < 2) return;
+  const int m = (p + 1) & ~1;            // players (one dummy if p is odd)
+  const int half = m >> 1;
+  double* rc = rot; double* rs = rot + 16; int* rp = reinterpret_cast<int*>(rot + 32);   // rp[2k], rp[2k+1] = pair k
+  for (int sweep = 0; sweep < 40; ++sweep) {
     double off = 0.0, dg = 0.0;
     if (lane < p) { for (int j = 0; j < p; ++j) { const double a = A[lane * ld + j]; if (j != lane) off = fma(a, a, off); else dg = a * a; } }
     off = warp_sum(off); dg = warp_sum(dg);
-    if (off <= 1e-30 * dg || off == 0.0) break;
-    for (int pp = 0; pp < p - 1; ++pp) {
-      for (int qq = pp + 1; qq < p; ++qq) {
-        const double apq = A[pp * ld + qq];
-        if (apq == 0.0) continue;
-        const double app = A[pp * ld + pp], aqq = A[qq * ld + qq];
-        const double theta = (aqq - app) / (2.0 * apq);
-        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-        const double c = rsqrt(fma(t, t, 1.0)), s = t * c;
-        __syncwarp();
-        if (lane < p) {
-          const int k = lane;
-          if (k != pp && k != qq) {
-            const double akp = A[k * ld + pp], akq = A[k * ld + qq];
-            const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
-            A[k * ld + pp] = np_; A[pp * ld + k] = np_;
-            A[k * ld + qq] = nq_; A[qq * ld + k] = nq_;
+    if (off <= 1e-27 * dg || off == 0.0) break;   // |offdiag|_F <= 3e-14 |diag|_F: rounding level for p <= 32
+    for (int step = 0; step < m - 1; ++step) {
+      // round-robin: player 0 fixed, the others rotate; pair k = (pos(k), pos(m-1-k))
+      if (lane < half) {
+        auto pos = [&](int k) { return k == 0 ? 0 : 1 + ((k - 1 + step) % (m - 1)); };
+        int a = pos(lane), b = pos(m - 1 - lane);
+        if (a > b) { const int t = a; a = b; b = t; }
+        double c = 1.0, sn = 0.0;
+        if (b < p) {
+          const double apq = A[a * ld + b];
+          if (apq != 0.0) {
+            const double theta = (A[b * ld + b] - A[a * ld + a]) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+            c = rsqrt(fma(t, t, 1.0)); sn = t * c;
           }
-          const double qkp = Q[k * ld + pp], qkq = Q[k * ld + qq];
-          Q[k * ld + pp] = c * qkp - s * qkq;
-          Q[k * ld + qq] = s * qkp + c * qkq;
         }
-        if (lane == 0) {
-          A[pp * ld + pp] = app - t * apq;
-          A[qq * ld + qq] = aqq + t * apq;
-          A[pp * ld + qq] = 0.0; A[qq * ld + pp] = 0.0;
-        }
-        __syncwarp();
+        rc[lane] = c; rs[lane] = sn; rp[2 * lane] = a; rp[2 * lane + 1] = (b < p) ? b : -1;
       }
+      __syncwarp();
+      if (lane < p) {                     // A <- A J and Q <- Q J: lane = row
+        for (int k = 0; k < half; ++k) {
+          const int a = rp[2 * k], b = rp[2 * k + 1];
+          if (b < 0) continue;
+          const double c = rc[k], sn = rs[k];
+          const double x = A[lane * ld + a], y = A[lane * ld + b];
+          A[lane * ld + a] = c * x - sn * y; A[lane * ld + b] = sn * x + c * y;
+          const double qx = Q[lane * ld + a], qy = Q[lane * ld + b];
+          Q[lane * ld + a] = c * qx - sn * qy; Q[lane * ld + b] = sn * qx + c * qy;
+        }
+      }
+      __syncwarp();
+      if (lane < p) {                     // A <- J' A: lane = column
+        for (int k = 0; k < half; ++k) {
+          const int a = rp[2 * k], b = rp[2 * k + 1];
+          if (b < 0) continue;
+          const double c = rc[k], sn = rs[k];
+          const double x = A[a * ld + lane], y = A[b * ld + lane];
+          A[a * ld + lane] = c * x - sn * y; A[b * ld + lane] = sn * x + c * y;
+        }
+      }
+      __syncwarp();
     }
   }
+  // exact symmetry / clean-up is not needed: only the diagonal (eigenvalues) and Q are used
 }
 
 // Klara softabs: G <- Q diag(lam coth(alpha lam)) Q'; also Inv <- Q diag(1/f) Q' and returns logdet(G) = sum log f.
 // A holds the input (destroyed), Q scratch, outputs to G and Inv.
 __device__ inline double w_softabs(double* A, double* Q, double* G, double* Inv, double alpha, int p, int ld, int lane, double* fbuf) {
-  w_jacobi(A, Q, p, ld, lane);
+  double* finv = fbuf + 32 + 48;   // fbuf: [f(32) | rotation scratch (48) | 1/f (32)] = T2, ROT0, ROT1, ROT2
+  w_jacobi(A, Q, p, ld, lane, fbuf + 32);
   double lf = 0.0;
   if (lane < p) {
     const double lam = A[lane * ld + lane];
     const double x = alpha * lam;
     const double f = (fabs(x) < 1e-8) ? 1.0 / alpha : lam / tanh(x);
     fbuf[lane] = f;
+    finv[lane] = 1.0 / f;
     lf = log(f);
   }
   lf = warp_sum(lf);
@@ -184,7 +208,7 @@ __device__ inline double w_softabs(double* A, double* Q, double* G, double* Inv,
   if (lane < p) {
     for (int j = 0; j <= lane; ++j) {
       double g = 0.0, iv = 0.0;
-      for (int k = 0; k < p; ++k) { const double qq = Q[lane * ld + k] * Q[j * ld + k]; g = fma(qq, fbuf[k], g); iv += qq / fbuf[k]; }
+      for (int k = 0; k < p; ++k) { const double qq = Q[lane * ld + k] * Q[j * ld + k]; g = fma(qq, fbuf[k], g); iv = fma(qq, finv[k], iv); }
       G[lane * ld + j] = g; G[j * ld + lane] = g;
       Inv[lane * ld + j] = iv; Inv[j * ld + lane] = iv;
     }
@@ -519,7 +543,7 @@ __device__ inline double bt_eval_point(const BatchedCfg& C, const BState& S, con
     const double sl = w_chol(L, p, ld, lane);           // G = Lg Lg'
     if (isnan(sl)) { *ok = 0; return lt; }
     logdetG = 2.0 * sl;
-    w_inv_from_chol(L, Inv, W, p, ld, lane);
+    w_inv_from_chol(L, Inv, p, ld, lane);
   }
   if (!isfinite(logdetG)) { *ok = 0; return lt; }
   // cholinvtensor = chol(Hermitian(inv))'  (lower)

@@ -31,6 +31,8 @@ struct DevState {
   long long chain_saved;
   double sumlog[2];   // sum_i log U_ii of the factor in each slot
   double mix_scratch;
+  int lcur;           // which of the three AM factor buffers holds chol(C) (am_mode 2 rotates them; otherwise 0)
+  int spec_err[2];    // speculative factor update of outcome 0 (accept) / 1 (reject) failed
 };
 
 // Tuner / range constants handed to the step kernels by value.

@@ -72,6 +72,7 @@ struct gamc_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t side = nullptr; cudaEvent_t ev_main = nullptr, ev_side = nullptr;   // am_mode 2: speculative factor updates overlap the data pass
   std::string err;
 
   // target
@@ -79,7 +80,7 @@ struct gamc_ctx {
   double* dX = nullptr; double* dy = nullptr; bool own_data = false;
   double* dw = nullptr;
   // data-pass configuration
-  int dp_rpl = 1, dp_nu = 0, dp_grid = 0, part_g_stride = 0;
+  int dp_rpl = 1, dp_nu = 0, dp_grid = 0, dp_grid_now = 0, part_g_stride = 0;   // dp_grid_now: grid of the current evaluation (am_mode 2 leaves SMs free)
   CUtensorMap mapXA{}, mapXB{}, mapW{};
   double* part_ll = nullptr; double* part_g = nullptr;
   // metric
@@ -95,7 +96,7 @@ struct gamc_ctx {
   Bufs B{};
   double* vecs = nullptr; double* mats = nullptr; DevState* d_state = nullptr;
   unsigned char* arena = nullptr; size_t arena_bytes = 0;   // [state | vecs | R | mats]: the L2-persisting working set of the step kernels
-  long long h_count = 0; bool h_present = true, h_past = false;
+  long long h_count = 0; bool h_present = true, h_past = false, spec_ready = false;
   // tape
   long long tape_n = 0, tape_pos = 0, tape_cap = 0; int tape_p = 0;
   double* d_tape = nullptr; std::vector<double> h_usched;
@@ -235,11 +236,12 @@ void apply_l2_policy(gamc_ctx* h) {
 // ---- data-pass dispatch -----------------------------------------------------------------------------
 template <int NU, int RPL, bool GRAD>
 gamc_status launch_dp_t(gamc_ctx* h, const double* theta) {
+  const int grid = h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid;
   auto kern = k_datapass<NU, RPL, GRAD>;
   { gamc_status s = ensure_attr(h, (const void*)kern, sizeof(DataPassSmem)); if (s != GAMC_OK) return s; }
   ProfScope ps(h, GRAD ? GAMC_K_LOGLIK_GRAD : GAMC_K_LOGLIK);
   DEBUG_POINT(h, "before datapass");
-  kern<<<h->dp_grid, DP_THREADS, sizeof(DataPassSmem), h->stream>>>(h->mapXA, h->dy, theta, h->p, h->N, h->dw, h->part_ll,
+  kern<<<grid, DP_THREADS, sizeof(DataPassSmem), h->stream>>>(h->mapXA, h->dy, theta, h->p, h->N, h->dw, h->part_ll,
                                                                     h->part_g, h->part_g_stride);
   CUDA_TRY(h, cudaGetLastError());
   DEBUG_POINT(h, "after datapass");
@@ -279,7 +281,7 @@ gamc_status launch_metric(gamc_ctx* h) {
 gamc_status launch_reduce(gamc_ctx* h, int level) {
   ProfScope ps(h, GAMC_K_REDUCE);
   const int nblk = (level >= 2 ? h->ntasks * 4 : 0) + 1;
-  k_reduce<<<nblk, 256, 0, h->stream>>>(h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, h->dp_grid, level >= 1,
+  k_reduce<<<nblk, 256, 0, h->stream>>>(h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid, level >= 1,
                                         level >= 2 ? h->ws : nullptr, h->d_coords, h->ntasks, h->d_task_nsplit, h->layout.max_nsplit);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
@@ -363,7 +365,7 @@ gamc_status setup_target(gamc_ctx* h) {
   h->goff = (1 + p + 1) & ~1;  // G starts 16-byte aligned
   {
     const size_t pp = (size_t)p * p;
-    const size_t n_state = 64, n_vecs = ((size_t)12 * p + 15) & ~(size_t)15, n_R = ((size_t)h->goff + pp + 15) & ~(size_t)15, n_mats = 7 * pp;
+    const size_t n_state = 64, n_vecs = ((size_t)16 * p + 15) & ~(size_t)15, n_R = ((size_t)h->goff + pp + 15) & ~(size_t)15, n_mats = 9 * pp;
     h->arena_bytes = sizeof(double) * (n_state + n_vecs + n_R + n_mats);
     CUDA_TRY(h, cudaMalloc(&h->arena, h->arena_bytes));
     CUDA_TRY(h, cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
@@ -457,7 +459,7 @@ gamc_status launch_seed_factor(gamc_ctx* h) {
   if (s != GAMC_OK) return s;
   ProfScope ps(h, GAMC_K_LINALG);
   const int p = h->p;
-  k_w_to_l<<<std::min(1024, (p * p + 255) / 256), 256, 0, h->stream>>>(h->B.W, p, h->B.Lc, h->B.rdiagL);
+  k_w_to_l<<<std::min(1024, (p * p + 255) / 256), 256, 0, h->stream>>>(h->B.st, h->B.W, p, h->B.Lc, h->B.rdiagL);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
 }
@@ -504,6 +506,8 @@ gamc_status gamc_create(gamc_handle* out, int32_t device) {
   if (prop.major != 10) { delete h; return GAMC_CUDA_ERROR; }  // sm_100a code only
   h->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return GAMC_CUDA_ERROR; }
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess) { delete h; return GAMC_CUDA_ERROR; }
   h->ev0.resize(PROF_POOL); h->ev1.resize(PROF_POOL); h->ev_family.resize(PROF_POOL);
   *out = h;
   return GAMC_OK;
@@ -521,6 +525,7 @@ gamc_status gamc_destroy(gamc_handle h) {
   cudaFree(h->d_tape);
   if (h->prof || h->ev_used) for (int i = 0; i < PROF_POOL; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
   if (h->own_stream) cudaStreamDestroy(h->stream);
+  cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_main); cudaEventDestroy(h->ev_side);
   delete h;
   return GAMC_OK;
 }
@@ -678,7 +683,7 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   REQUIRE(h, cfg->t0 > 0, GAMC_INVALID_ARG, "t0 is not positive");
   REQUIRE(h, cfg->schedule >= 0 && cfg->schedule <= GAMC_SCHED_RAND_QUAD_DECAY, GAMC_INVALID_ARG, "unknown schedule");
   REQUIRE(h, cfg->period >= 1 && cfg->nsteps >= 1 && cfg->burnin >= 0, GAMC_INVALID_ARG, "bad period / nsteps / burnin");
-  REQUIRE(h, cfg->am_mode == 0 || cfg->am_mode == 1, GAMC_INVALID_ARG, "am_mode must be 0 or 1");
+  REQUIRE(h, cfg->am_mode >= 0 && cfg->am_mode <= 2, GAMC_INVALID_ARG, "am_mode must be 0, 1 or 2");
   REQUIRE(h, cfg->sampler_kind == 0 || cfg->sampler_kind == 1, GAMC_INVALID_ARG, "sampler_kind must be 0 (GAMC) or 1 (MALA)");
   cudaSetDevice(h->device);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -703,14 +708,14 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   B = Bufs{};
   B.st = h->d_state;
   const size_t pp = (size_t)p * p;
-  CUDA_TRY(h, cudaMemsetAsync(h->mats, 0, sizeof(double) * pp * 7, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->mats, 0, sizeof(double) * pp * 9, h->stream));
   B.Gs = h->mats; B.Gstride = pp;
   B.U = h->mats + 2 * pp; B.Ustride = pp;
-  B.C = h->mats + 4 * pp; B.Lc = h->mats + 5 * pp; B.W = h->mats + 6 * pp;
-  CUDA_TRY(h, cudaMemsetAsync(h->vecs, 0, sizeof(double) * (size_t)p * 12, h->stream));
+  B.C = h->mats + 4 * pp; B.W = h->mats + 5 * pp; B.Lc = h->mats + 6 * pp; B.Lstride = pp;   // Lc: three buffers (am_mode 2 rotates them)
+  CUDA_TRY(h, cudaMemsetAsync(h->vecs, 0, sizeof(double) * (size_t)p * 16, h->stream));
   double* v = h->vecs;
   B.gs = v; v += 2 * p; B.rdiagU = v; v += 2 * p; B.fterm = v; v += 2 * p;
-  B.theta = v; v += p; B.theta_prop = v; v += p; B.mu = v; v += p; B.lastmean = v; v += p; B.secondlastmean = v; v += p; B.rdiagL = v;
+  B.theta = v; v += p; B.theta_prop = v; v += p; B.mu = v; v += p; B.lastmean = v; v += p; B.secondlastmean = v; v += p; B.rdiagL = v; v += 3 * p; B.accbuf = v;
   B.R = h->R; B.goff = h->goff;
   h->chain_cap = std::max<long long>(0, cfg->nsteps - cfg->burnin);
   if (h->chain_cap > 0) {
@@ -745,7 +750,7 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
     s = launch_step(h, k_sampler_init, B, T);
     if (s != GAMC_OK) return s;
   }
-  h->h_count = 0; h->h_present = true; h->h_past = false;   // MuvGAMCState outer ctor (:117-118)
+  h->h_count = 0; h->h_present = true; h->h_past = false; h->spec_ready = false;   // MuvGAMCState outer ctor (:117-118)
   h->tape_n = 0; h->tape_pos = 0;
   h->sampler_ready = true;
   return check_device_error(h);
@@ -824,31 +829,63 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
     }
     return GAMC_OK;
   }
+  // branch sequence of these n iterations (the schedule coin depends only on (i, nsteps, u_sched))
+  std::vector<unsigned char> kinds(n);
+  {
+    bool pr = h->h_present;
+    for (long long k = 0; k < n; ++k) {
+      const long long t = h->h_count + k + 1;
+      if (t > h->cfg.t0) pr = schedule_decision(h->cfg, t, h->cfg.nsteps, h->h_usched[h->tape_pos + k]);
+      kinds[k] = pr ? 1 : 0;
+    }
+  }
   for (long long k = 0; k < n; ++k) {
-    const long long t = ++h->h_count;                                                    // iterate/GAMC.jl:2
+    ++h->h_count;                                                                        // iterate/GAMC.jl:2
     const long long ti = h->tape_pos++;
-    if (t > h->cfg.t0) h->h_present = schedule_decision(h->cfg, t, h->cfg.nsteps, h->h_usched[ti]);   // :8-10
+    h->h_present = kinds[k] != 0;                                                        // :8-10
     if (h->h_present) {                                                                  // :12
+      h->spec_ready = false;
       const int refactor = h->h_past ? 0 : 1;
       if (refactor) { s = eval_device(h, B.theta, 2, true); if (s != GAMC_OK) return s; }  // :20
       s = launch_step(h, k_smmala_pre, B, T, ti, refactor); if (s != GAMC_OK) return s;
       s = eval_device(h, B.theta_prop, 2, true); if (s != GAMC_OK) return s;             // :37
       s = launch_step(h, k_smmala_post, B, T, ti); if (s != GAMC_OK) return s;
     } else {                                                                             // :128
-      if (T.am_mode == 1) {
-        if (h->h_past) { s = launch_seed_factor(h); if (s != GAMC_OK) return s; }        // chol(oldinvtensor) = U^-T seeds the update
-        {
+      const bool next_am = (T.am_mode == 2) && (k + 1 < n) && !kinds[k + 1];            // next step is AM too: speculate
+      if (T.am_mode >= 1) {
+        if (!h->spec_ready) {
+          if (h->h_past) { s = launch_seed_factor(h); if (s != GAMC_OK) return s; }      // chol(oldinvtensor) = U^-T seeds the update
           const int nbuf = am_r1_nbuf(h->p);
           ProfScope ps(h, GAMC_K_LINALG);
-          k_am_pre_r1<<<1, LA_THREADS, am_r1_smem_bytes(h->p, nbuf), h->stream>>>(B, T, ti, nbuf);
+          k_am_pre_r1<<<1, LA_THREADS, am_r1_smem_bytes(h->p, nbuf), h->stream>>>(B, T, ti, nbuf, 0);
           CUDA_TRY(h, cudaGetLastError());
-        }
+        }   // else: the previous k_am_post selected the speculative factor and wrote the proposal
       } else {
         if (h->h_past) { s = launch_inverse(h); if (s != GAMC_OK) return s; }            // oldinvtensor = inv(G) seeds the recursion
         s = launch_step(h, k_am_pre, B, T, ti); if (s != GAMC_OK) return s;
       }
-      s = eval_device(h, B.theta_prop, 0, true); if (s != GAMC_OK) return s;             // :148
-      s = launch_step(h, k_am_post, B, T, ti); if (s != GAMC_OK) return s;
+      if (next_am) {
+        // both outcomes of this step's accept/reject -> next step's factor, on the side stream, while the data pass runs
+        CUDA_TRY(h, cudaEventRecord(h->ev_main, h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->side, h->ev_main, 0));
+        const int nbuf = am_r1_nbuf(h->p);
+        h->launches += 1;
+        k_am_pre_r1<<<2, LA_THREADS, am_r1_smem_bytes(h->p, nbuf), h->side>>>(B, T, ti + 1, nbuf, 1);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaEventRecord(h->ev_side, h->side));
+        h->dp_grid_now = std::max(1, h->dp_grid - 2);                                    // leave two SMs to the speculative CTAs
+      }
+      s = eval_device(h, B.theta_prop, 0, true);                                         // :148
+      h->dp_grid_now = 0;
+      if (s != GAMC_OK) return s;
+      if (next_am) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_side, 0));
+      {
+        const size_t smem = step_smem_bytes(h->p);
+        ProfScope ps(h, GAMC_K_LINALG);
+        k_am_post<<<1, LA_THREADS, smem, h->stream>>>(B, T, ti, next_am ? 1 : 0);
+        CUDA_TRY(h, cudaGetLastError());
+      }
+      h->spec_ready = next_am;
     }
     h->h_past = h->h_present;                                                            // :197
   }
@@ -925,8 +962,8 @@ gamc_status gamc_get_array(gamc_handle h, int32_t array_id, double* out) {
     case GAMC_ARR_PROPOSED_VALUE: src = B.theta_prop; break;
     case GAMC_ARR_OLDINVTENSOR:
       if (h->h_past || h->h_count == 0) { gamc_status s = launch_inverse(h); if (s != GAMC_OK) return s; }
-      else if (h->tune.am_mode == 1) {   // AM covariance is kept in factored form: C = L L'
-        k_llt<<<std::min(1024, (p * p + 255) / 256), 256, 0, h->stream>>>(B.Lc, p, B.C);
+      else if (h->tune.am_mode >= 1) {   // AM covariance is kept in factored form: C = L L'
+        k_llt<<<std::min(1024, (p * p + 255) / 256), 256, 0, h->stream>>>(B.Lc + (size_t)st.lcur * B.Lstride, p, B.C);
         CUDA_TRY(h, cudaGetLastError());
       }
       src = B.C; n = pp; break;

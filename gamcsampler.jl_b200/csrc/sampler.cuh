@@ -22,7 +22,9 @@ struct Bufs {
   double* theta; double* theta_prop; double* mu; double* lastmean; double* secondlastmean;
   double* C;                             // p x p  sstate.oldinvtensor while in AM mode (AM covariance)
   double* Lc;                            // p x p  lower Cholesky factor of eps*C (am_mode 0) / of C (am_mode 1)
-  double* rdiagL;                        // p
+  double* rdiagL;                        // p  (am_mode 2: three buffers of p, like Lc)
+  double* accbuf;                        // [2][p] unscaled proposal products L' z of the two speculative outcomes (am_mode 2)
+  size_t Lstride;                        // p*p: distance between the AM factor buffers
   double* W;                             // p x p  scratch: triangular inverse
   double* chain_value; unsigned char* chain_accept; long long chain_cap;
   const double* tape_usched; const double* tape_umix; const double* tape_z; const double* tape_uacc;
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre(Bufs B, TuneCfg T, lon
       const double c = ((k - 1.0) * B.C[e] + k * (S.v2[i] * S.v2[j]) - (k + 1.0) * (S.v1[i] * S.v1[j]) + S.v0[i] * S.v0[j]) / k;
       B.C[e] = c;
       B.C[(size_t)j + (size_t)i * p] = c;
-      B.Lc[e] = eps * c;                              // MvNormal(theta, eps*C) -> Cholesky (set_gmm, GAMC.jl:188)
+      B.Lc[e] = eps * c;                              // MvNormal(theta, eps*C) -> Cholesky (set_gmm, GAMC.jl:188); am_mode 0 uses buffer 0 only
     }
   }
   __syncthreads();
@@ -361,12 +363,25 @@ __host__ __device__ inline size_t am_r1_smem_bytes(int p, int nbuf) {
 }
 __host__ __device__ inline int am_r1_nbuf(int p) { return am_r1_smem_bytes(p, 2) <= 200 * 1024 ? 2 : 1; }
 
-__global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, long long tape_idx, int nbuf) {
+// spec = 0: the step itself (in place on the current factor buffer; bumps the counters; writes the proposal).
+// spec = 1 (am_mode 2): SPECULATIVE update for the NEXT AM step, launched on a side stream while the data pass of the
+// current step runs: CTA o in {0, 1} assumes the current proposal is accepted (o = 0) or rejected (o = 1), reads the
+// current factor, writes the updated factor to buffer (lcur + 1 + o) % 3 and the unscaled product L' z to accbuf[o];
+// k_am_post picks the outcome that happened.  Same arithmetic as spec = 0, so the chain is bit-identical.
+__global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, long long tape_idx, int nbuf, int spec) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   DevState* st = B.st;
   const int p = T.p, pp = (p + 3) & ~3;
   if (st->error_flag) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int outcome = spec ? (int)blockIdx.x : 0;
+  const int lcur = st->lcur;
+  const double* Lin = B.Lc + (size_t)lcur * B.Lstride;
+  double* Lout = spec ? B.Lc + (size_t)((lcur + 1 + outcome) % 3) * B.Lstride : B.Lc + (size_t)lcur * B.Lstride;
+  const double* rdin = B.rdiagL + (size_t)lcur * p;
+  double* rdout = spec ? B.rdiagL + (size_t)((lcur + 1 + outcome) % 3) * p : B.rdiagL + (size_t)lcur * p;
+  const double* xsrc = (spec && outcome == 0) ? B.theta_prop : B.theta;          // the state the next step would start from
+  const double* m2src = spec ? B.lastmean : B.secondlastmean;                     // secondlastmean of the NEXT step = lastmean now
   double* panel = reinterpret_cast<double*>(smem_raw);          // [nbuf][32][pp]  (column-major: element (row, jj) at jj*pp + row)
   double* zs = panel + (size_t)nbuf * 32 * pp;                   // z
   double* bw = zs + 2 * (size_t)pp;                              // per-block: w[32], Kd[32], g[32], sigma
@@ -375,9 +390,11 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, 
   double* accd = Ts + 32 * 33;                                   // [32] proposal-product contributions of the diagonal block
   int* flag = reinterpret_cast<int*>(accd + 32);
   if (tid == 0) {
-    st->count += 1;
-    if (T.tuning) st->tot_prop += 1;
-    if (T.verbose_am) st->am_prop += 1;
+    if (!spec) {
+      st->count += 1;
+      if (T.tuning) st->tot_prop += 1;
+      if (T.verbose_am) st->am_prop += 1;
+    }
     flag[0] = 0;
   }
   const int nblk = (p + 31) >> 5;
@@ -385,7 +402,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, 
   auto issue_panel = [&](int b, int t, int nt) {
     const int j0 = b << 5, nb = min(32, p - j0), rows = p - j0;
     double* dst = panel + (size_t)(b % nbuf) * 32 * pp;
-    const double* src = B.Lc + (size_t)j0 + (size_t)j0 * p;
+    const double* src = Lin + (size_t)j0 + (size_t)j0 * p;
     if ((p & 1) == 0) {   // 16-byte copies: column starts are 16-byte aligned when p is even (j0 is a multiple of 32)
       for (int jj = 0; jj < nb; ++jj)
         for (int r = 2 * t; r < rows; r += 2 * nt) cp_async16(dst + (size_t)jj * pp + r, src + (size_t)jj * p + r);
@@ -397,17 +414,21 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, 
   issue_panel(0, tid, LA_THREADS);
   cp_async_commit();
   __syncthreads();
-  const long long t = st->count;
+  const long long t = st->count + (spec ? 1 : 0);                             // iteration the update belongs to
   const double k = (double)(t - 2);
-  if (!(k > 1.0)) { cp_async_wait<0>(); raise_error(st, 3, 1); return; }    // C_1 = u u' has rank one: the reference's chol throws
+  if (!(k > 1.0)) {                                                            // C_1 = u u' has rank one: the reference's chol throws
+    cp_async_wait<0>();
+    if (spec) { if (tid == 0) st->spec_err[outcome] = 1; } else raise_error(st, 3, 1);
+    return;
+  }
   const double alpha = sqrt((k - 1.0) / k), beta = 1.0 / sqrt(k + 1.0), ralpha = 1.0 / alpha;
   const double* z = B.tape_z + (size_t)tape_idx * p;
   const int i = tid;
   double th = 0.0, ui = 0.0, P = 0.0, acc = 0.0, rdv = 0.0;
   if (i < p) {
-    th = B.theta[i];
-    ui = (th - B.secondlastmean[i]) * beta;
-    rdv = B.rdiagL[i] * ralpha;          // 1 / (a L_ii)
+    th = xsrc[i];
+    ui = (th - m2src[i]) * beta;
+    rdv = rdin[i] * ralpha;              // 1 / (a L_ii)
     zs[i] = z[i];
   }
   double sigma = 1.0;                     // s_{j0}: carried by every thread identically
@@ -457,7 +478,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, 
     if (i >= j0 + 32 && i < p) {
       // ---- rows below the diagonal block: one thread per row, residual res = u_i - P_i carried in a register
       const double* prow = pan + (i - j0);
-      double* out = B.Lc + (size_t)i + (size_t)j0 * p;
+      double* out = Lout + (size_t)i + (size_t)j0 * p;
       double res = ui - P, a0 = 0.0, a1 = 0.0;
       if (nb == 32) {
 #pragma unroll
@@ -488,9 +509,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, 
         double contrib = 0.0;
         if (lane <= r && lane < nb) {
           const double ln = fma(Ls[lane * 33 + r], bw[32 + lane], bw[64 + lane] * Ts[lane * 33 + r]);
-          B.Lc[(size_t)gi + (size_t)(j0 + lane) * p] = ln;
+          Lout[(size_t)gi + (size_t)(j0 + lane) * p] = ln;
           contrib = ln * zs[j0 + lane];
-          if (lane == r) B.rdiagL[gi] = 1.0 / ln;
+          if (lane == r) rdout[gi] = 1.0 / ln;
         }
         contrib = warp_sum(contrib);
         if (lane == 0) accd[r] = contrib;
@@ -501,7 +522,15 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, 
     if (nbuf == 1 && b + 1 < nblk) issue_panel(b + 1, tid, LA_THREADS);
   }
   const int fin = isfinite(sigma) ? 0 : 1;
-  if (__syncthreads_or(fin)) { raise_error(st, 3, 1); return; }
+  if (__syncthreads_or(fin)) {
+    if (spec) { if (tid == 0) st->spec_err[outcome] = 1; } else raise_error(st, 3, 1);
+    return;
+  }
+  if (spec) {
+    if (i < p) B.accbuf[(size_t)outcome * p + i] = acc;                     // scaled by sqrt(eps) once the outcome is known
+    if (tid == 0) st->spec_err[outcome] = 0;
+    return;
+  }
   if (i < p) {
     const double umix = B.tape_umix[tape_idx];
     if (umix <= 1.0 - T.c) B.theta_prop[i] = th + st->sqrtstep * acc;       // core component  N(theta, eps C)
@@ -510,7 +539,8 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, 
 }
 
 // chol(inv(G)) = U^-T as a natural-order lower factor:  L(a,b) = W(p-1-b, p-1-a), W = Lm^-1 (k_triinv).
-__global__ void __launch_bounds__(256) k_w_to_l(const double* __restrict__ W, int p, double* __restrict__ L, double* __restrict__ rdiagL) {
+__global__ void __launch_bounds__(256) k_w_to_l(DevState* st, const double* __restrict__ W, int p, double* __restrict__ L, double* __restrict__ rdiagL) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->lcur = 0;       // the seeded factor lives in buffer 0
   const size_t n = (size_t)p * p;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
     const int a = (int)(e % p), b = (int)(e / p);
@@ -538,7 +568,10 @@ __global__ void __launch_bounds__(256) k_llt(const double* __restrict__ L, int p
 // log-sum-exp, so they cancel exactly and the device omits them (the oracle evaluates both literally and
 // tests/test_oracle_sampler.py asserts the cancellation is exact).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, long long tape_idx) {
+// next_spec = 1 (am_mode 2): the next step is an AM step whose factor update was computed speculatively for both outcomes
+// while the data pass ran; after the decision this kernel selects the factor buffer of the outcome that happened and
+// performs the head of the next `iterate!` (counters, proposal) so that the next data pass can start immediately.
+__global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, long long tape_idx, int next_spec) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StepSmem S = step_smem_carve(smem_raw, T.p);
   DevState* st = B.st;
@@ -563,6 +596,25 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, lo
   }
   __syncthreads();
   step_tail(B, T, accept);
+  if (next_spec) {
+    __syncthreads();
+    const int o = accept ? 0 : 1;
+    if (st->spec_err[o]) { raise_error(st, 3, 1); return; }
+    const long long tn = tape_idx + 1;
+    const double umix = B.tape_umix[tn];
+    const double* z = B.tape_z + (size_t)tn * p;
+    const double sq = st->sqrtstep;                                           // after this step's tuning, as the next iterate! sees it
+    for (int i = threadIdx.x; i < p; i += blockDim.x) {
+      const double th = B.theta[i];
+      B.theta_prop[i] = (umix <= 1.0 - T.c) ? th + sq * B.accbuf[(size_t)o * p + i] : th + T.sqrtminorscale * z[i];
+    }
+    if (threadIdx.x == 0) {
+      st->lcur = (st->lcur + 1 + o) % 3;
+      st->count += 1;                                                         // head of the next iterate! (iterate/GAMC.jl:2-6,129-131)
+      if (T.tuning) st->tot_prop += 1;
+      if (T.verbose_am) st->am_prop += 1;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -71,7 +71,9 @@ typedef struct {
   int64_t nsteps;          /* BasicMCRange.nsteps (the `tot` argument of the schedules)            */
   int64_t burnin;          /* BasicMCRange.burnin                                                  */
   int32_t am_mode;         /* 0 = literal covariance recursion + Cholesky each AM step,
-                              1 = rank-one Cholesky update of the same recursion (fast path)       */
+                              1 = rank-one Cholesky update of the same recursion (fast path),
+                              2 = as 1, computed for both accept/reject outcomes on a side stream while
+                                  the data pass runs (bit-identical chain, shorter critical path)  */
   int32_t sampler_kind;    /* 0 = GAMC, 1 = MALA (Klara's comparison sampler, examples/logistic_regression/src/MALA/simulations.jl:37;
                               identity metric: only driftstep, the total tuner and the range are used)          */
 } gamc_config;

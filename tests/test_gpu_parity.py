@@ -91,11 +91,12 @@ def _run_both(gamc, engine, N, p, nsteps, burnin, seed, am_mode=0, update=None, 
     return job, chain, osam, v, a, k
 
 
-@pytest.mark.parametrize("am_mode", [0, 1])
+@pytest.mark.parametrize("am_mode", [0, 1, 2])
 @pytest.mark.parametrize("N,p,nsteps", [(200, 4, 3000), (500, 33, 1200), (2000, 64, 1000), (3000, 130, 1000), (6000, 256, 300), (4000, 512, 120)])
 def test_trajectory_parity(gamc, engine, N, p, nsteps, am_mode):
     """Same host-drawn normals and uniforms => step-for-step agreement for >= 1000 iterations.
-    am_mode 0 = literal covariance recursion + Cholesky per AM step; 1 = rank-one Cholesky update (fast path)."""
+    am_mode 0 = literal covariance recursion + Cholesky per AM step; 1 = rank-one Cholesky update (fast path);
+    2 = the same update computed speculatively for both accept/reject outcomes while the data pass runs."""
     burnin = nsteps // 5
     job, chain, osam, v, a, k = _run_both(gamc, engine, N, p, nsteps, burnin, seed=42, am_mode=am_mode)
     assert chain.value.shape == v.shape
@@ -139,7 +140,7 @@ def test_state_arrays_parity(gamc, engine):
     assert relerr(eng.array(1), osam.grad) <= 1e-10
 
 
-@pytest.mark.parametrize("am_mode", [0, 1])
+@pytest.mark.parametrize("am_mode", [0, 1, 2])
 def test_am_covariance_readout(gamc, engine, am_mode):
     """sstate.oldinvtensor after a run that ends in AM steps = the Haario covariance recursion seeded with inv(G)."""
     job, chain, osam, v, a, k = _run_both(gamc, engine, 400, 9, 60, 0, seed=4, am_mode=am_mode, update=gamc.mod_update(7))
@@ -161,7 +162,7 @@ def test_errors(gamc, engine):
         engine.target_logistic(np.zeros((10, 513)), np.zeros(10), 100.0)
 
 
-@pytest.mark.parametrize("am_mode", [0, 1])
+@pytest.mark.parametrize("am_mode", [0, 1, 2])
 def test_am_before_enough_history_raises_posdef(gamc, engine, am_mode):
     """t0 = 1 lets an AM step run at t = 2/3, where Klara's covariance recursion has k = 0/1 and the proposal covariance
     is not positive definite: the reference throws from the MvNormal constructor (set_gmm, GAMC.jl:188); here the device
@@ -202,3 +203,23 @@ def test_mala_trajectory_parity(gamc, engine, N, p, nsteps):
     assert relerr(chain.value, v) <= 1e-9
     st = job.engine.state()
     assert abs(st.step - osam.tune.step) <= 1e-12 * osam.tune.step and st.count == nsteps
+
+
+def test_speculative_am_is_bitwise_identical(gamc, engine):
+    """am_mode 2 overlaps the factor update with the data pass; it must not change a single bit of the chain."""
+    import oracle as o
+    X, y, tt = o.synth_logistic(5, 5000, 96)
+    theta0 = tt + 0.05 * np.random.default_rng(2).standard_normal(96)
+    nsteps = 700
+    engine.target_logistic(X, y, 100.0)
+    out = []
+    for mode in (1, 2):
+        sampler, tuner, rng_ = example_config(gamc, nsteps, 100, am_mode=mode, verbose=True)
+        job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, rng_, {"p": theta0}, tuner=tuner, tape=gamc.RandomTape(nsteps, 96, seed=4), engine=engine)
+        job.run()
+        st = engine.state()
+        out.append((job.output(), st.step, st.am_totproposed, st.total_totproposed, engine.array(5)))
+    assert np.array_equal(out[0][0].value, out[1][0].value)
+    assert np.array_equal(out[0][0].diagnosticvalues, out[1][0].diagnosticvalues)
+    assert out[0][1:4] == out[1][1:4]
+    assert np.array_equal(out[0][4], out[1][4])
