@@ -64,7 +64,7 @@ typedef CUresult (*fn_cuTensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType,
                                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 fn_cuTensorMapEncodeTiled g_encode = nullptr;
 
-constexpr int PROF_POOL = 8192;
+constexpr int PROF_POOL = 32768;
 }  // namespace
 
 struct gamc_ctx {
