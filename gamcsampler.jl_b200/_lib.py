@@ -111,6 +111,7 @@ SIGNATURES = {
     "gamc_batched_target_rv": (C.c_int, [_H, _DP, _DP, _DP, C.c_int64, C.c_int32]),
     "gamc_batched_init": (C.c_int, [_H, C.POINTER(Config), C.c_int32, _DP, C.c_int32, C.c_double]),
     "gamc_batched_run": (C.c_int, [_H, C.c_int64, C.c_uint64, _DP, _DP, _DP, _DP]),
+    "gamc_batched_set_chain_offset": (C.c_int, [_H, C.c_int64]),
     "gamc_batched_chain_get": (C.c_int, [_H, C.c_int32, C.c_int32, _DP, _U8P]),
     "gamc_batched_get_state": (C.c_int, [_H, C.c_int32, C.POINTER(StateScalars), _DP]),
     "gamc_profile_enable": (C.c_int, [_H, C.c_int32]),

@@ -23,6 +23,7 @@ constexpr int BT_MAXP = 32;
 struct BatchedCfg {
   int p, ld;                    // dimension, leading dimension (odd)
   int nchains;
+  long long chain_offset;       // global index of this rank's first chain (keys the Philox streams; chains are sharded across ranks)
   int target;                   // 0 = mvt, 1 = rv
   int transform;                // 0 = none, 1 = softabs
   double softabs_alpha;
@@ -144,49 +145,59 @@ __device__ inline void w_jacobi(double* A, double* Q, int p, int ld, int lane, d
     if (lane < p) { for (int j = 0; j < p; ++j) { const double a = A[lane * ld + j]; if (j != lane) off = fma(a, a, off); else dg = a * a; } }
     off = warp_sum(off); dg = warp_sum(dg);
     if (off <= 1e-27 * dg || off == 0.0) break;   // |offdiag|_F <= 3e-14 |diag|_F: rounding level for p <= 32
+    // round-robin positions of this lane's pair, advanced incrementally (player 0 fixed, players 1..m-1 rotate)
+    int ra = (lane == 0) ? 0 : lane, rb = m - 1 - lane;          // step 0: pair k = (k, m-1-k); values in 1..m-1 rotate by +1 mod (m-1)
     for (int step = 0; step < m - 1; ++step) {
-      // round-robin: player 0 fixed, the others rotate; pair k = (pos(k), pos(m-1-k))
       if (lane < half) {
-        auto pos = [&](int k) { return k == 0 ? 0 : 1 + ((k - 1 + step) % (m - 1)); };
-        int a = pos(lane), b = pos(m - 1 - lane);
+        int a = ra, b = rb;
         if (a > b) { const int t = a; a = b; b = t; }
         double c = 1.0, sn = 0.0;
         if (b < p) {
           const double apq = A[a * ld + b];
-          if (apq != 0.0) {
-            const double theta = (A[b * ld + b] - A[a * ld + a]) / (2.0 * apq);
-            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+          const double app = A[a * ld + a], aqq = A[b * ld + b];
+          // skip rotations that cannot change the diagonal at working precision
+          if (fabs(apq) > 1e-19 * (fabs(app) + fabs(aqq))) {
+            // t = tan(phi) = sgn(d) h / (|d| + sqrt(d^2 + h^2)), d = aqq - app, h = 2 apq   (one rsqrt, one divide)
+            const double d = aqq - app, h2 = 2.0 * apq;
+            const double q = fma(d, d, h2 * h2);
+            const double r = q * rsqrt(q);
+            const double t = (d >= 0.0 ? h2 : -h2) / (fabs(d) + r);
             c = rsqrt(fma(t, t, 1.0)); sn = t * c;
           }
         }
-        rc[lane] = c; rs[lane] = sn; rp[2 * lane] = a; rp[2 * lane + 1] = (b < p) ? b : -1;
+        rc[lane] = c; rs[lane] = sn; rp[2 * lane] = a; rp[2 * lane + 1] = (b < p && sn != 0.0) ? b : -1;
+        // next step's pair
+        if (lane != 0) ra = (ra == m - 1) ? 1 : ra + 1;
+        rb = (rb == m - 1) ? 1 : rb + 1;
       }
       __syncwarp();
       if (lane < p) {                     // A <- A J and Q <- Q J: lane = row
+        double* Ar = A + lane * ld; double* Qr = Q + lane * ld;
         for (int k = 0; k < half; ++k) {
-          const int a = rp[2 * k], b = rp[2 * k + 1];
+          const int b = rp[2 * k + 1];
           if (b < 0) continue;
+          const int a = rp[2 * k];
           const double c = rc[k], sn = rs[k];
-          const double x = A[lane * ld + a], y = A[lane * ld + b];
-          A[lane * ld + a] = c * x - sn * y; A[lane * ld + b] = sn * x + c * y;
-          const double qx = Q[lane * ld + a], qy = Q[lane * ld + b];
-          Q[lane * ld + a] = c * qx - sn * qy; Q[lane * ld + b] = sn * qx + c * qy;
+          const double x = Ar[a], y = Ar[b];
+          Ar[a] = c * x - sn * y; Ar[b] = fma(sn, x, c * y);
+          const double qx = Qr[a], qy = Qr[b];
+          Qr[a] = c * qx - sn * qy; Qr[b] = fma(sn, qx, c * qy);
         }
       }
       __syncwarp();
       if (lane < p) {                     // A <- J' A: lane = column
         for (int k = 0; k < half; ++k) {
-          const int a = rp[2 * k], b = rp[2 * k + 1];
+          const int b = rp[2 * k + 1];
           if (b < 0) continue;
+          const int a = rp[2 * k];
           const double c = rc[k], sn = rs[k];
           const double x = A[a * ld + lane], y = A[b * ld + lane];
-          A[a * ld + lane] = c * x - sn * y; A[b * ld + lane] = sn * x + c * y;
+          A[a * ld + lane] = c * x - sn * y; A[b * ld + lane] = fma(sn, x, c * y);
         }
       }
       __syncwarp();
     }
   }
-  // exact symmetry / clean-up is not needed: only the diagonal (eigenvalues) and Q are used
 }
 
 // Klara softabs: G <- Q diag(lam coth(alpha lam)) Q'; also Inv <- Q diag(1/f) Q' and returns logdet(G) = sum log f.
@@ -481,17 +492,18 @@ __device__ inline bool bt_schedule(const BatchedCfg& C, long long i, double u) {
 // random numbers of (chain, iteration t): u_sched, u_mix, u_acc broadcast; z[p] into smem (warp 0)
 __device__ inline void bt_draw(const BatchedCfg& C, int chain, long long t, long long tape_pos, double* z, double& us, double& um, double& ua, int lane) {
   const int p = C.p;
+  const uint32_t gchain = (uint32_t)(C.chain_offset + chain);
   if (C.tape_z) {
     const size_t o = (size_t)chain * C.tape_len + tape_pos;
     us = C.tape_usched[o]; um = C.tape_umix[o]; ua = C.tape_uacc[o];
     if (lane < p) z[lane] = C.tape_z[o * p + lane];
   } else {
-    const Philox4 r = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)chain, 0x51u, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
-    const Philox4 r2 = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)chain, 0x52u, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
+    const Philox4 r = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 0x51u, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
+    const Philox4 r2 = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 0x52u, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
     us = philox_u53(r.x, r.y); um = philox_u53(r.z, r.w); ua = philox_u53(r2.x, r2.y);
     if (ua <= 0.0) ua = 1.0 / 9007199254740992.0;
     if (lane < p) {
-      const Philox4 q = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)chain, 0x100u + (uint32_t)lane, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
+      const Philox4 q = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 0x100u + (uint32_t)lane, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
       double u1 = philox_u53(q.x, q.y); const double u2 = philox_u53(q.z, q.w);
       if (u1 <= 0.0) u1 = 1.0 / 9007199254740992.0;
       double sn, cs; sincospi(2.0 * u2, &sn, &cs);

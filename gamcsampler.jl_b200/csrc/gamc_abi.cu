@@ -104,7 +104,7 @@ struct gamc_ctx {
   // chain
   long long chain_cap = 0; double* d_chain = nullptr; unsigned char* d_accept = nullptr;
   // batched chains
-  BatchedCfg bcfg{}; bool batched_target = false, batched_ready = false; double* d_Sinv = nullptr; double* d_blob = nullptr;
+  BatchedCfg bcfg{}; long long bcfg_chain_offset = 0; bool batched_target = false, batched_ready = false; double* d_Sinv = nullptr; double* d_blob = nullptr;
   double* d_bchain = nullptr; unsigned char* d_baccept = nullptr; double* d_btape = nullptr; long long btape_doubles = 0;
   // comm
   ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
@@ -1065,7 +1065,7 @@ gamc_status gamc_batched_init(gamc_handle h, const gamc_config* cfg, int32_t nch
   free_batched(h);
   BatchedCfg& C = h->bcfg;
   const int p = C.p;
-  C.nchains = nchains; C.transform = transform; C.softabs_alpha = softabs_alpha;
+  C.nchains = nchains; C.chain_offset = h->bcfg_chain_offset; C.transform = transform; C.softabs_alpha = softabs_alpha;
   C.driftstep = cfg->driftstep; C.minorscale = cfg->minorscale; C.sqrtminorscale = sqrt(cfg->minorscale); C.c = cfg->c;
   C.t0 = cfg->t0; C.schedule = cfg->schedule; C.sp0 = cfg->sched_params[0]; C.sp1 = cfg->sched_params[1]; C.sp2 = cfg->sched_params[2];
   C.is_accrate = cfg->total_tuner_kind == 1;
@@ -1128,6 +1128,14 @@ gamc_status gamc_batched_run(gamc_handle h, int64_t n, uint64_t seed, const doub
   }
   C.seed = seed;
   return launch_batched(h, 0, n, nullptr);
+}
+
+gamc_status gamc_batched_set_chain_offset(gamc_handle h, int64_t chain_offset) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, chain_offset >= 0, GAMC_INVALID_ARG, "chain_offset < 0");
+  h->bcfg_chain_offset = chain_offset;
+  h->bcfg.chain_offset = chain_offset;
+  return GAMC_OK;
 }
 
 gamc_status gamc_batched_chain_get(gamc_handle h, int32_t chain_first, int32_t nchains, double* value, uint8_t* accept) {

@@ -34,3 +34,8 @@ def allreduce_partials_host(parts):
     g = sum(p[1] for p in parts) if parts[0][1] is not None else None
     G = sum(p[2] for p in parts) if parts[0][2] is not None else None
     return ll, g, G
+
+
+def shard_chains(nchains: int, world: int, rank: int):
+    """Block of independent chains [c0, c1) owned by `rank` (chains shard trivially, no collective)."""
+    return shard_rows(nchains, world, rank)

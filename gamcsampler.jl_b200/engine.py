@@ -178,6 +178,9 @@ class Engine:
         self._ck(self.lib.gamc_batched_target_rv(self.h, L.dptr(t), L.dptr(obs), L.dptr(sigma), t.shape[0], int(nplanets)))
         self.bp = 5 * int(nplanets) + 1
 
+    def batched_set_chain_offset(self, offset):
+        self._ck(self.lib.gamc_batched_set_chain_offset(self.h, int(offset)))
+
     def batched_init(self, cfg: L.Config, theta0, transform=0, softabs_alpha=1000.0):
         """theta0: (nchains, p) array (row c = initial value of chain c)."""
         th = _f64(theta0, "C")

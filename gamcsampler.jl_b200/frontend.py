@@ -416,7 +416,7 @@ class BatchedMCJob:
     as ONE persistent kernel: every chain is an independent GAMC job with its own initial value v0s[c]."""
 
     def __init__(self, model, sampler: GAMC, mcrange: BasicMCRange, v0s, tuner: Optional[GAMCTuner] = None, device=0,
-                 tape: Optional[BatchedRandomTape] = None, seed=0, engine: Optional[Engine] = None):
+                 tape: Optional[BatchedRandomTape] = None, seed=0, engine: Optional[Engine] = None, chain_offset=0):
         self.model, self.sampler, self.range = model, sampler, mcrange
         self.tuner = tuner if tuner is not None else GAMCTuner()
         self.engine = engine if engine is not None else Engine(device)
@@ -426,6 +426,7 @@ class BatchedMCJob:
             Sinv, logconst = model.constants()
             self.engine.batched_target_mvt(Sinv, model.nu, logconst)
         self.cfg = make_config(sampler, self.tuner, mcrange)
+        self.engine.batched_set_chain_offset(chain_offset)     # this rank's first chain in a chains-sharded multi-GPU job
         tr = sampler.transform
         self.engine.batched_init(self.cfg, np.asarray(v0s, dtype=np.float64), 1 if isinstance(tr, Softabs) else 0,
                                  tr.alpha if isinstance(tr, Softabs) else 0.0)

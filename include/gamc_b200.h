@@ -216,6 +216,9 @@ gamc_status gamc_batched_init(gamc_handle h, const gamc_config* cfg, int32_t nch
 gamc_status gamc_batched_run(gamc_handle h, int64_t n, uint64_t seed, const double* u_sched, const double* u_mix,
                              const double* z, const double* u_acc);
 /* value: [nchains][cap][p] doubles with cap = nsteps - burnin (sample s of chain c at value[(c*cap + s)*p]); accept [nchains][cap]. */
+/* Multi-GPU: chains are independent, every rank owns a block of them; the global index of this rank's first chain keys the
+ * device random streams so that ranks draw distinct numbers.  Call before gamc_batched_init (default 0). */
+gamc_status gamc_batched_set_chain_offset(gamc_handle h, int64_t chain_offset);
 gamc_status gamc_batched_chain_get(gamc_handle h, int32_t chain_first, int32_t nchains, double* value, uint8_t* accept);
 gamc_status gamc_batched_get_state(gamc_handle h, int32_t chain, gamc_state_scalars* out, double* theta);
 
