@@ -309,58 +309,149 @@ namespace gamc {
 // Keplerian radial-velocity target (examples/radial_velocity/src/*.jl), block-cooperative over epochs
 // =====================================================================================================
 // calc_ecc_anom_itterative_laguerre (kepler_eqn.jl:43-56): Danby guess (:18-23) + Laguerre n = 5 (:30-40), M reduced mod 2 pi
-__device__ inline double rv_kepler(double M, double ecc) {
+// Returns E and its sine / cosine.  One full sincos at the starting guess; the later (small) Laguerre corrections update
+// (sin E, cos E) by the angle-addition formulas with a short Taylor series for the correction angle.
+__device__ inline double rv_kepler_sc(double M, double ecc, double& sE, double& cE) {
   const double twopi = 6.283185307179586476925286766559;
-  M = M - twopi * floor(M / twopi);
+  M = M - twopi * floor(M * (1.0 / twopi));
   double E = (M < 3.14159265358979323846) ? M + 0.85 * ecc : M - 0.85 * ecc;
+  sincos(E, &sE, &cE);
   for (int it = 0; it < 60; ++it) {
-    double sE, cE; sincos(E, &sE, &cE);
     const double es = ecc * sE, ec = ecc * cE;
     const double F = (E - es) - M, Fp = 1.0 - ec, Fpp = es;
     const double root = sqrt(fabs(4.0 * (4.0 * Fp * Fp - 5.0 * F * Fpp)));
     const double denom = (Fp > 0.0) ? Fp + root : Fp - root;
-    const double En = E - 5.0 * F / denom;
-    const bool done = fabs(En - E) < 1e-14;
-    E = En;
-    if (done) break;
+    const double d = -5.0 * F / denom;             // E_new = E + d
+    E += d;
+    if (fabs(d) <= 0.1) {
+      const double d2 = d * d;
+      const double sd = d * (1.0 - d2 * (1.0 / 6.0) * (1.0 - d2 * (1.0 / 20.0) * (1.0 - d2 * (1.0 / 42.0) * (1.0 - d2 * (1.0 / 72.0)))));
+      const double cd = 1.0 - d2 * 0.5 * (1.0 - d2 * (1.0 / 12.0) * (1.0 - d2 * (1.0 / 30.0) * (1.0 - d2 * (1.0 / 56.0) * (1.0 - d2 * (1.0 / 90.0)))));
+      const double sn = sE * cd + cE * sd;
+      cE = cE * cd - sE * sd;
+      sE = sn;
+    } else {
+      sincos(E, &sE, &cE);
+    }
+    if (fabs(d) < 1e-10) break;                    // reference: 1e-8 (kepler_eqn.jl:43); Laguerre converges cubically
   }
   return E;
 }
+__device__ inline double rv_kepler(double M, double ecc) { double s, c; return rv_kepler_sc(M, ecc, s, c); }
 
-// velocity of one planet, plain doubles (rv_model_keplerian.jl:9-37)
-__device__ inline double rv_planet(const double* th, double t) {
-  const double P = exp(th[0]) - 1.0, K = exp(th[1]) - 1.0, h = th[2], k = th[3];
-  const double ecc = sqrt(h * h + k * k), w = atan2(k, h);
-  const double n = 6.283185307179586476925286766559 / P;
-  const double M = t * n - (th[4] - w), lam = w + M;
-  const double E = rv_kepler(M, ecc);
-  double sE, cE; sincos(E, &sE, &cE);
-  const double j = sqrt((1.0 - ecc) * (1.0 + ecc));
-  const double pe = ecc * sE, q = ecc * cE;
-  return K * j / (1.0 - q) * (cos(lam + pe) - k * q / (1.0 + j));
+// The same solver for U independent epochs at once: the per-epoch work is one long dependent chain (sincos -> sqrt ->
+// divide -> update), so a thread that interleaves several epochs hides most of that latency (instruction-level parallelism).
+template <int U>
+__device__ inline void rv_kepler_sc_batch(const double (&Min)[U], double ecc, double (&sE)[U], double (&cE)[U]) {
+  const double twopi = 6.283185307179586476925286766559;
+  double M[U], E[U];
+  bool done[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    M[u] = Min[u] - twopi * floor(Min[u] * (1.0 / twopi));
+    E[u] = (M[u] < 3.14159265358979323846) ? M[u] + 0.85 * ecc : M[u] - 0.85 * ecc;
+    sincos(E[u], &sE[u], &cE[u]);
+    done[u] = false;
+  }
+  for (int it = 0; it < 60; ++it) {
+    // branch-free across the U epochs so that their dependent chains interleave; converged epochs take a zero step
+    bool all = true, big = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double es = ecc * sE[u], ec = ecc * cE[u];
+      const double F = (E[u] - es) - M[u], Fp = 1.0 - ec, Fpp = es;
+      const double root = sqrt(fabs(4.0 * (4.0 * Fp * Fp - 5.0 * F * Fpp)));
+      const double denom = (Fp > 0.0) ? Fp + root : Fp - root;
+      double d = -5.0 * F / denom;
+      d = done[u] ? 0.0 : d;
+      E[u] += d;
+      const double d2 = d * d;
+      const double sd = d * (1.0 - d2 * (1.0 / 6.0) * (1.0 - d2 * (1.0 / 20.0) * (1.0 - d2 * (1.0 / 42.0) * (1.0 - d2 * (1.0 / 72.0)))));
+      const double cd = 1.0 - d2 * 0.5 * (1.0 - d2 * (1.0 / 12.0) * (1.0 - d2 * (1.0 / 30.0) * (1.0 - d2 * (1.0 / 56.0) * (1.0 - d2 * (1.0 / 90.0)))));
+      const double sn = sE[u] * cd + cE[u] * sd;
+      cE[u] = cE[u] * cd - sE[u] * sd;
+      sE[u] = sn;
+      big = big || (fabs(d) > 0.1);
+      done[u] = done[u] || (fabs(d) < 1e-10);
+      all = all && done[u];
+    }
+    if (big) {                                     // rare (first step from a poor guess): the series is not accurate enough
+#pragma unroll
+      for (int u = 0; u < U; ++u) sincos(E[u], &sE[u], &cE[u]);
+    }
+    if (all) break;
+  }
 }
 
-// Phi(theta1, h, k, wpM0; t) = velocity / K with exact first and second derivatives: the eccentric anomaly is solved in
-// plain doubles and refined by two Newton steps in dual arithmetic (implicit differentiation of Kepler's equation).
-__device__ inline Dual2<4> rv_phi_dual(const double* th, double t) {
+// Quantities of one planet that do not depend on the epoch (rv_model_keplerian.jl:15-19,31-33), computed once per
+// evaluation and shared through shared memory: plain values, and (for level 2) their second-order duals over the
+// planet's nonlinear parameters (theta1 = log1p P, h, k, w + M0).
+struct RvPlain { double K, Kp, k, ecc, w, n, j, rj1, wm, pad; };
+struct RvDual { Dual2<4> ecc, w, n, j, rj1; };
+constexpr int RV_CONST_DOUBLES = 2 * ((int)(sizeof(RvPlain) + sizeof(RvDual)) / 8);   // two planets
+
+__device__ inline void rv_planet_constants(const double* th, RvPlain* pc, RvDual* dc, int level) {
   typedef Dual2<4> D;
   const double twopi = 6.283185307179586476925286766559;
-  const D P = d_exp(d_var<4>(th[0], 0)) + (-1.0);
-  const D h = d_var<4>(th[2], 1), k = d_var<4>(th[3], 2), wm = d_var<4>(th[4], 3);
-  const D ecc = d_sqrt(h * h + k * k);
-  const D w = d_atan2(k, h);
-  const D n = twopi * d_recip(P);
-  D M = t * n - wm + w;
-  const D lam = w + M;
-  const double E0 = rv_kepler(M.v, ecc.v);
-  M.v = M.v - twopi * floor(M.v / twopi);
-  D E = d_const<4>(E0);
-#pragma unroll 1
-  for (int it = 0; it < 2; ++it) E = E - (E - ecc * d_sin(E) - M) / (1.0 - ecc * d_cos(E));
-  const D sE = d_sin(E), cE = d_cos(E);
-  const D q = ecc * cE;
-  const D j = d_sqrt((1.0 - ecc) * (1.0 + ecc));
-  return j * d_recip(1.0 - q) * (d_cos(lam + ecc * sE) - k * q * d_recip(j + 1.0));
+  const double P = exp(th[0]) - 1.0, Kp = exp(th[1]), h = th[2], k = th[3];
+  const double ecc = sqrt(h * h + k * k), w = atan2(k, h);
+  const double j = sqrt((1.0 - ecc) * (1.0 + ecc));
+  pc->K = Kp - 1.0; pc->Kp = Kp; pc->k = k; pc->ecc = ecc; pc->w = w; pc->n = twopi / P; pc->j = j; pc->rj1 = 1.0 / (1.0 + j); pc->wm = th[4];
+  if (level >= 2) {
+    const D Pd = d_exp(d_var<4>(th[0], 0)) + (-1.0);
+    const D hd = d_var<4>(h, 1), kd = d_var<4>(k, 2);
+    const D ed = d_sqrt(hd * hd + kd * kd);
+    dc->ecc = ed;
+    dc->w = d_atan2(kd, hd);
+    dc->n = twopi * d_recip(Pd);
+    const D jd = d_sqrt((1.0 - ed) * (1.0 + ed));
+    dc->j = jd;
+    dc->rj1 = d_recip(jd + 1.0);
+  }
+}
+
+// velocity of one planet at epoch t, plain doubles (rv_model_keplerian.jl:20-35)
+__device__ inline double rv_planet(const RvPlain& c, double t) {
+  const double M = t * c.n - (c.wm - c.w), lam = c.w + M;
+  double sE, cE;
+  rv_kepler_sc(M, c.ecc, sE, cE);
+  const double pe = c.ecc * sE, q = c.ecc * cE;
+  return c.K * c.j / (1.0 - q) * (cos(lam + pe) - c.k * q * c.rj1);
+}
+
+// Phi(theta1, h, k, wpM0; t) = velocity / K with exact first and second derivatives.  The eccentric anomaly is solved in
+// plain doubles; its derivatives follow from implicit differentiation of Kepler's equation E - e sin E = M:
+//   D E_i = M_i + s e_i,                                   D = 1 - e cos E, s = sin E, c = cos E
+//   D E_ij = M_ij + s e_ij + c (E_j e_i + E_i e_j) - e s E_i E_j
+// (the reference differentiates through its Laguerre iterations, which converge to the same derivatives).
+__device__ inline Dual2<4> rv_phi_dual(const RvPlain& pc, const RvDual& dc, double kval, double t) {
+  typedef Dual2<4> D;
+  const double twopi = 6.283185307179586476925286766559;
+  D M = t * dc.n + dc.w;                 // M = t n - (wpM0 - w)
+  M.v -= pc.wm; M.g[3] -= 1.0;
+  const D lam = dc.w + M;
+  (void)twopi;
+  double s, c;
+  const double E0 = rv_kepler_sc(M.v, pc.ecc, s, c);
+  const double rD = 1.0 / (1.0 - pc.ecc * c);
+  D E; E.v = E0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) E.g[i] = (M.g[i] + s * dc.ecc.g[i]) * rD;
+  {
+    int kk = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j, ++kk)
+        E.h[kk] = (M.h[kk] + s * dc.ecc.h[kk] + c * (E.g[j] * dc.ecc.g[i] + E.g[i] * dc.ecc.g[j]) - pc.ecc * s * E.g[i] * E.g[j]) * rD;
+  }
+  const D sE = d_unary(E, s, c, -s), cE = d_unary(E, c, -s, -c);
+  const D q = dc.ecc * cE;
+  const D arg = lam + dc.ecc * sE;
+  double sa, ca; sincos(arg.v, &sa, &ca);
+  const D cosarg = d_unary(arg, ca, -sa, -ca);
+  const D kd = d_var<4>(kval, 2);
+  return dc.j * d_recip(1.0 - q) * (cosarg - kd * q * dc.rj1);
 }
 
 constexpr int RV_MAXP = 11;
@@ -369,29 +460,59 @@ constexpr int RV_MAXRED = 1 + RV_MAXP + RV_MAXP * (RV_MAXP + 1) / 2;   // 78
 // Per-thread partial sums over this thread's epochs.  level 0: acc[0] = sum r^2/s^2 (chi-square).
 // level 2: also acc[1+a] = sum r z_a / s^2 and acc[1+p+idx(a,b)] = sum (z_a z_b + r z_ab)/s^2 (lower triangle, row-major).
 template <int NPL>
-__device__ inline void rv_partial(const BatchedCfg& C, const double* th, int level, int tid, int nt, double* acc) {
+__device__ inline void rv_partial(const BatchedCfg& C, const double* th, const RvPlain* pc, const RvDual* dc, int level, int tid, int nt, double* acc) {
   constexpr int p = 5 * NPL + 1;
   constexpr int NR = 1 + p + p * (p + 1) / 2;
 #pragma unroll
   for (int i = 0; i < NR; ++i) acc[i] = 0.0;
-  for (long long e = tid; e < C.rv_n; e += nt) {
+  const double offset = th[5 * NPL];
+  long long e0 = tid;
+  if (level < 2) {
+    // log-target only (AM steps): four independent epochs per trip
+    constexpr int U = 4;
+    for (; e0 + (long long)(U - 1) * nt < C.rv_n; e0 += (long long)U * nt) {
+      double t[U], z[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { t[u] = C.rv_t[e0 + (long long)u * nt]; z[u] = offset; }
+#pragma unroll
+      for (int pl = 0; pl < NPL; ++pl) {
+        const RvPlain& c = pc[pl];
+        double M[U], sE[U], cE[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) M[u] = t[u] * c.n - (c.wm - c.w);
+        rv_kepler_sc_batch<U>(M, c.ecc, sE, cE);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const double pe = c.ecc * sE[u], q = c.ecc * cE[u];
+          z[u] += c.K * c.j / (1.0 - q) * (cos(c.w + M[u] + pe) - c.k * q * c.rj1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double sg = C.rv_sig[e0 + (long long)u * nt];
+        const double r = z[u] - C.rv_obs[e0 + (long long)u * nt];
+        acc[0] = fma(r * r, 1.0 / (sg * sg), acc[0]);
+      }
+    }
+  }
+  for (long long e = e0; e < C.rv_n; e += nt) {
     const double t = C.rv_t[e], o = C.rv_obs[e], sg = C.rv_sig[e];
     const double is2 = 1.0 / (sg * sg);
     if (level < 2) {
-      double z = th[5 * NPL];
+      double z = offset;
 #pragma unroll
-      for (int pl = 0; pl < NPL; ++pl) z += rv_planet(th + 5 * pl, t);
+      for (int pl = 0; pl < NPL; ++pl) z += rv_planet(pc[pl], t);
       const double r = z - o;
       acc[0] = fma(r * r, is2, acc[0]);
     } else {
       double za[p];
       double zab[NPL][15];       // per planet: second derivatives over (theta1, theta2, h, k, wpM0), lower triangle
-      double z = th[5 * NPL];
+      double z = offset;
       za[5 * NPL] = 1.0;
 #pragma unroll
       for (int pl = 0; pl < NPL; ++pl) {
-        const Dual2<4> phi = rv_phi_dual(th + 5 * pl, t);
-        const double Kp = exp(th[5 * pl + 1]), K = Kp - 1.0;     // K' = K'' = exp(theta2)
+        const Dual2<4> phi = rv_phi_dual(pc[pl], dc[pl], pc[pl].k, t);
+        const double Kp = pc[pl].Kp, K = pc[pl].K;                // K' = K'' = exp(theta2)
         z = fma(K, phi.v, z);
         // local order: 0 = theta1, 1 = theta2 (K), 2 = h, 3 = k, 4 = wpM0;  phi's variables: 0 = theta1, 1 = h, 2 = k, 3 = wpM0
         const int map[5] = {0, -1, 1, 2, 3};
@@ -429,7 +550,7 @@ __device__ inline void rv_partial(const BatchedCfg& C, const double* th, int lev
 // Block-wide RV evaluation; called by ALL threads of the CTA.  Results (level 2): lt returned to every thread,
 // g (length p) and H = tensor = -Hessian of the log-target (p x ld) written by warp 0.  red = RV_MAXRED * nwarps doubles.
 template <int NPL>
-__device__ inline double rv_eval_block(const BatchedCfg& C, const double* x, double* g, double* H, int level, double* red, double* bcast) {
+__device__ inline double rv_eval_block(const BatchedCfg& C, const double* x, double* g, double* H, int level, double* red, double* bcast, double* rvconst) {
   constexpr int p = 5 * NPL + 1;
   constexpr int NR = 1 + p + p * (p + 1) / 2;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
@@ -437,8 +558,12 @@ __device__ inline double rv_eval_block(const BatchedCfg& C, const double* x, dou
 #pragma unroll
   for (int pl = 0; pl < NPL; ++pl) { const double h = x[5 * pl + 2], k = x[5 * pl + 3]; if (!(h * h + k * k < 1.0)) valid = false; }   // is_valid, rv_model_param.jl:83-96
   if (!valid) return -INFINITY;                                                     // stat_model.jl:21
+  RvPlain* pc = reinterpret_cast<RvPlain*>(rvconst);
+  RvDual* dc = reinterpret_cast<RvDual*>(rvconst + 2 * (sizeof(RvPlain) / 8));
+  if (tid < NPL) rv_planet_constants(x + 5 * tid, pc + tid, dc + tid, level);
+  __syncthreads();
   double acc[NR];
-  rv_partial<NPL>(C, x, level, tid, nt, acc);
+  rv_partial<NPL>(C, x, pc, dc, level, tid, nt, acc);
   const int nred = (level >= 2) ? NR : 1;
   for (int i = 0; i < nred; ++i) { const double v = warp_sum(acc[i]); if (lane == 0) red[warp * RV_MAXRED + i] = v; }
   __syncthreads();
@@ -516,14 +641,14 @@ __device__ inline void bt_draw(const BatchedCfg& C, int chain, long long t, long
 // Target evaluation by warp 0 (mvt).  level: 0 = log-target, 2 = up to tensor.  On level 2 the point's slot
 // (G, Inv, L, grad, firstterm, logdet of Inv) is filled: `transform`, inverse, Cholesky of the inverse, G^-1 grad --
 // the reference's :20-30 / :37-56 sequence for one point.  Returns the log-target; *ok = 0 if anything is non-finite / not PD.
-struct BtWork { double* red; double* bcast; int* cmd; };
+struct BtWork { double* red; double* bcast; int* cmd; double* rvconst; };
 
 // master side of the block-cooperative RV evaluation: wake the worker warps, evaluate together
 template <int NPL>
 __device__ inline double rv_eval_master(const BatchedCfg& C, const BState& S, const BtWork& Wk, int xvec, int gradv, double* H, int level, int lane) {
   if (lane == 0) { Wk.cmd[0] = level + 1; Wk.cmd[1] = xvec; }
   __syncthreads();                                   // barrier A: releases the workers
-  return rv_eval_block<NPL>(C, S.vec(xvec), S.vec(gradv), H, level, Wk.red, Wk.bcast);
+  return rv_eval_block<NPL>(C, S.vec(xvec), S.vec(gradv), H, level, Wk.red, Wk.bcast, Wk.rvconst);
 }
 
 template <int TGT>
@@ -604,7 +729,7 @@ __device__ inline void bt_tail(const BatchedCfg& C, const BState& S, int chain, 
 
 // mode: 0 = run n_iters transitions, 1 = initialise (initialize! + sampler_state) from theta0 [p x nchains]
 __host__ __device__ inline size_t bt_smem_bytes(int blob_doubles, int nthreads) {
-  return sizeof(double) * ((size_t)blob_doubles + (size_t)RV_MAXRED * (nthreads / 32) + 8);
+  return sizeof(double) * ((size_t)blob_doubles + (size_t)RV_MAXRED * (nthreads / 32) + 8 + (nthreads > 32 ? RV_CONST_DOUBLES : 0));
 }
 
 template <int TGT>
@@ -620,13 +745,14 @@ __global__ void __launch_bounds__(TGT == 0 ? 32 : 128) k_batched_gamc(BatchedCfg
   Wk.red = bsm + C.blob_doubles;
   Wk.bcast = Wk.red + RV_MAXRED * (blockDim.x >> 5);
   Wk.cmd = reinterpret_cast<int*>(Wk.bcast + 4);
+  Wk.rvconst = Wk.bcast + 8;
   if (TGT != 0 && warp != 0) {
     // worker warps: wait for an evaluation request from warp 0, take part in it, repeat
     while (true) {
       __syncthreads();                               // barrier A
       const int c = Wk.cmd[0];
       if (c == 0) break;
-      rv_eval_block<(TGT == 2 ? 2 : 1)>(C, S.vec(Wk.cmd[1]), nullptr, nullptr, c - 1, Wk.red, Wk.bcast);
+      rv_eval_block<(TGT == 2 ? 2 : 1)>(C, S.vec(Wk.cmd[1]), nullptr, nullptr, c - 1, Wk.red, Wk.bcast, Wk.rvconst);
     }
     return;
   }

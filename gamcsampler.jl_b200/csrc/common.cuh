@@ -7,6 +7,25 @@
 
 namespace gamc {
 
+// Phase clocks (debug builds only, -DGAMC_PHASE_CLOCKS): thread 0 accumulates clock64 deltas between PHASE() marks of
+// the single-CTA step kernels; read back with gamc_debug_phases().  Compiled out of the product library.
+#ifdef GAMC_PHASE_CLOCKS
+__device__ long long g_phase_acc[64];
+__device__ long long g_phase_cnt[64];
+__device__ long long g_phase_last;
+#define GAMC_PHASE_BEGIN() do { __syncthreads(); if (threadIdx.x == 0) g_phase_last = clock64(); } while (0)
+#define GAMC_PHASE(k) do { __syncthreads(); if (threadIdx.x == 0) { const long long now_ = clock64(); \
+    g_phase_acc[k] += now_ - g_phase_last; g_phase_cnt[k] += 1; g_phase_last = now_; } } while (0)
+// per-warp variant (no barrier): GAMC_WCLK_BEGIN(t) then GAMC_WCLK(t, k) from one lane of the warp being timed
+#define GAMC_WCLK_BEGIN(t) long long t = clock64()
+#define GAMC_WCLK(t, k) do { if ((threadIdx.x & 31) == 0) { const long long now_ = clock64(); g_phase_acc[k] += now_ - t; g_phase_cnt[k] += 1; t = now_; } } while (0)
+#else
+#define GAMC_PHASE_BEGIN() do { } while (0)
+#define GAMC_PHASE(k) do { } while (0)
+#define GAMC_WCLK_BEGIN(t) do { } while (0)
+#define GAMC_WCLK(t, k) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // Device-resident sampler state: the scalar fields of MuvGAMCState / GAMCTune
 // (reference src/samplers/GAMC.jl:7-27, src/tuners/GAMCTuner.jl:1-7).

@@ -365,7 +365,7 @@ gamc_status setup_target(gamc_ctx* h) {
   h->goff = (1 + p + 1) & ~1;  // G starts 16-byte aligned
   {
     const size_t pp = (size_t)p * p;
-    const size_t n_state = 64, n_vecs = ((size_t)16 * p + 15) & ~(size_t)15, n_R = ((size_t)h->goff + pp + 15) & ~(size_t)15, n_mats = 9 * pp;
+    const size_t n_state = 64, n_vecs = ((size_t)16 * p + 15) & ~(size_t)15, n_R = ((size_t)h->goff + pp + 15) & ~(size_t)15, n_mats = 9 * pp + 2 * la_invd_doubles(p);
     h->arena_bytes = sizeof(double) * (n_state + n_vecs + n_R + n_mats);
     CUDA_TRY(h, cudaMalloc(&h->arena, h->arena_bytes));
     CUDA_TRY(h, cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
@@ -708,9 +708,10 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   B = Bufs{};
   B.st = h->d_state;
   const size_t pp = (size_t)p * p;
-  CUDA_TRY(h, cudaMemsetAsync(h->mats, 0, sizeof(double) * pp * 9, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->mats, 0, sizeof(double) * (pp * 9 + 2 * la_invd_doubles(p)), h->stream));
   B.Gs = h->mats; B.Gstride = pp;
   B.U = h->mats + 2 * pp; B.Ustride = pp;
+  B.invU = h->mats + 9 * pp; B.invUstride = la_invd_doubles(p);
   B.C = h->mats + 4 * pp; B.W = h->mats + 5 * pp; B.Lc = h->mats + 6 * pp; B.Lstride = pp;   // Lc: three buffers (am_mode 2 rotates them)
   CUDA_TRY(h, cudaMemsetAsync(h->vecs, 0, sizeof(double) * (size_t)p * 16, h->stream));
   double* v = h->vecs;
@@ -1213,5 +1214,20 @@ gamc_status gamc_launch_count(gamc_handle h, int64_t* out) {
   *out = h->launches;
   return GAMC_OK;
 }
+
+#ifdef GAMC_PHASE_CLOCKS
+// Debug build only (make dbg): accumulated clock64 deltas / hit counts of the PHASE() marks; reset = 1 clears them.
+int gamc_debug_phases(long long* acc, long long* cnt, int reset) {
+  cudaDeviceSynchronize();
+  if (acc) cudaMemcpyFromSymbol(acc, gamc::g_phase_acc, sizeof(long long) * 64);
+  if (cnt) cudaMemcpyFromSymbol(cnt, gamc::g_phase_cnt, sizeof(long long) * 64);
+  if (reset) {
+    long long z[64] = {0};
+    cudaMemcpyToSymbol(gamc::g_phase_acc, z, sizeof(z));
+    cudaMemcpyToSymbol(gamc::g_phase_cnt, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 }  // extern "C"

@@ -20,6 +20,10 @@ namespace gamc {
 constexpr int LA_THREADS = 512;   // 128 registers per thread: the 32-wide row fragments stay in registers
 constexpr int LA_NB = 32;
 constexpr int LA_DLD = 33;  // padded leading dimension of the 32 x 32 diagonal block in shared memory
+constexpr int LA_YLD = 36;  // leading dimension of the inverted diagonal block in shared memory (16-byte aligned rows)
+constexpr int LA_INVD_STRIDE = 2 * LA_NB * LA_NB;   // doubles per diagonal block in the global inverse buffer (two layouts)
+
+__host__ __device__ inline size_t la_invd_doubles(int p) { return (size_t)((p + LA_NB - 1) / LA_NB) * LA_INVD_STRIDE; }
 
 template <bool REV>
 struct MatView {
@@ -30,159 +34,295 @@ struct MatView {
   }
 };
 
-// Shared-memory scratch for the factorisation: D (diagonal block), rd (reciprocal diagonal of the block),
-// P (panel, k-major: P[c * pld + t]), flag.
+// Shared-memory scratch of the factorisation and the triangular solves.
 struct LaScratch {
-  double* D;      // LA_NB * LA_DLD
-  double* rd;     // LA_NB
-  double* P;      // LA_NB * pld
-  int* flag;      // 2 ints
+  double* D;      // LA_NB * LA_DLD   diagonal block before factorisation, row r at D[r * LA_DLD]
+  double* LT;     // LA_NB * LA_DLD   its factor by columns, LT[j * LA_DLD + r] = Lkk(r, j)
+  double* Y;      // LA_NB * LA_YLD   its inverse, Y[k * LA_YLD + c] = (Lkk^-1)(c, k)
+  double* rd;     // LA_NB            reciprocal diagonal of the block
+  double* xs;     // LA_NB            block solution of the triangular solves
+  double* P;      // LA_NB * pld      panel, k-major: P[c * pld + t]
+  int* flag;      // [0] failed pivot, [1] number of factored columns published to the inverter warp (monotone)
   int pld;
 };
 
 __host__ __device__ inline size_t la_scratch_bytes(int p) {
   const int pld = ((p + 3) & ~3) + 4;
-  return sizeof(double) * (LA_NB * LA_DLD + LA_NB + (size_t)LA_NB * pld) + 16;
+  return sizeof(double) * (2 * LA_NB * LA_DLD + LA_NB * LA_YLD + 2 * LA_NB + (size_t)LA_NB * pld) + 16;
 }
 
 __device__ inline LaScratch la_scratch_carve(unsigned char* base, int p) {
   LaScratch s;
   s.pld = ((p + 3) & ~3) + 4;
-  s.D = reinterpret_cast<double*>(base);
-  s.rd = s.D + LA_NB * LA_DLD;
-  s.P = s.rd + LA_NB;
-  s.flag = reinterpret_cast<int*>(s.P + (size_t)LA_NB * s.pld);
+  s.Y = reinterpret_cast<double*>(base);          // first: keeps the 16-byte alignment the double2 reads need
+  s.P = s.Y + LA_NB * LA_YLD;
+  s.D = s.P + (size_t)LA_NB * s.pld;
+  s.LT = s.D + LA_NB * LA_DLD;
+  s.rd = s.LT + LA_NB * LA_DLD;
+  s.xs = s.rd + LA_NB;
+  s.flag = reinterpret_cast<int*>(s.xs + LA_NB);
   return s;
 }
 
-// In-place blocked right-looking Cholesky of the lower triangle (M space) of A: A = Lm Lm'.
-// Also writes rdiag[i] = 1 / Lm_ii (M-space order, shared or global) and returns sum_i log Lm_ii.
-// On a non-positive pivot returns NaN and sets *fail_pivot = 1-based M-space pivot index (else 0).
+__device__ __forceinline__ void la_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void la_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Warp roles of chol_blocked (16 warps).  Scheduler partition 0 (warps 0, 4, 8, 12) is kept free of trailing-update
+// work so that the serial column chain of warp 0 is not slowed down by FP64 pipe contention.
+constexpr int LA_TEAM = 128;                                   // warps 0, 4, 8, 12: diagonal-block update; warp 0: column chain
+constexpr int LA_NTRAIL = LA_THREADS - LA_TEAM - 32;           // 11 warps: trailing update + panel load; warp 1: inverter
+__device__ __forceinline__ bool la_is_team(int warp) { return (warp & 3) == 0; }
+__device__ __forceinline__ int la_trail_index(int warp, int lane) {   // dense index 0..LA_NTRAIL-1 of a trailing thread
+  // warps 2,3 -> 0,1; 5,6,7 -> 2,3,4; 9,10,11 -> 5,6,7; 13,14,15 -> 8,9,10
+  const int w = warp - 1 - (warp >> 2) - 1;
+  return w * 32 + lane;
+}
+
+// In-place blocked right-looking Cholesky of the lower triangle (M space) of A: A = Lm Lm', one CTA, software-pipelined:
+// in pass `it` the team updates diagonal block `it` with panel it-1, warp 0 factors it column by column (row per lane,
+// in registers; dependent chain per column: shfl -> rsqrt -> mul -> sts/lds -> fma, no divide, no sqrt) while warp 1
+// inverts the factor one column behind (lane j solves Lkk y = e_j), and the other eleven warps apply the rest of the
+// rank-32 trailing update of panel it-1 and then stage the raw panel `it` in shared memory.  The panel solve is a small
+// GEMM with the inverted diagonal block (no per-row dependent chains).
+// Also writes rdiag[i] = 1 / Lm_ii (M-space order, global), the inverted diagonal blocks (invd, may be null; both
+// layouts [j*32+i] and [i*32+j], for the coalesced block solves of trsv_lower / trsv_lower_t) and returns
+// sum_i log Lm_ii.  On a non-positive pivot returns NaN and sets *fail_pivot = 1-based M-space pivot (else 0).
 // Must be called by all LA_THREADS threads.
 template <bool REV>
-__device__ double chol_blocked(MatView<REV> A, double* rdiag, LaScratch S, int* fail_pivot) {
+__device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaScratch S, int* fail_pivot) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p = A.p;
-  double sumlog = 0.0;  // meaningful in thread 0 of warp 0; broadcast at the end
-  if (tid == 0) { S.flag[0] = 0; }
+  const int nblk = (p + LA_NB - 1) / LA_NB;
+  double sumlog = 0.0;  // lane-local partial in warp 0; reduced at the end
+  volatile int* vflag = S.flag;
+  if (tid == 0) { S.flag[0] = 0; S.flag[1] = 0; }
   __syncthreads();
-  for (int kb = 0; kb < p; kb += LA_NB) {
-    const int nb = min(LA_NB, p - kb);
-    const int m = p - kb - nb;
-    // (a) diagonal block -> shared
-    for (int e = tid; e < LA_NB * LA_NB; e += LA_THREADS) {
-      const int r = e & 31, c = e >> 5;
-      if (r < nb && c < nb && r >= c) S.D[r * LA_DLD + c] = A(kb + r, kb + c);
-    }
-    __syncthreads();
-    // (b) factor the diagonal block with warp 0: right-looking, lane = row, the row lives in registers; the
-    //     freshly scaled column is broadcast through shared memory.  Dependent chain per column:
-    //     shfl -> rsqrt -> mul -> (sts/lds) -> fma; no divide, no sqrt, the logarithms are taken in parallel afterwards.
-    if (warp == 0) {
-      const int r = lane;
-      double a[LA_NB];
+  for (int it = 0; it < nblk; ++it) {
+    const int kn = it * LA_NB;                       // first row / column of diagonal block `it`
+    const int nbn = min(LA_NB, p - kn);
+    const int mprev = p - kn;                        // rows of panel it-1 (= trailing size), when it > 0
+    const int mnext = p - kn - nbn;                  // rows of panel it
+    if (la_is_team(warp)) {
+      // ---- team: diagonal block `it` = A(block) - Pn Pn' (Pn = first 32 rows of the solved panel it-1), 8 columns per warp
+      const int c0 = (warp >> 2) * 8;
+      GAMC_WCLK_BEGIN(w0);
+      double av[8];
 #pragma unroll
-      for (int c = 0; c < LA_NB; ++c) a[c] = (c <= r && r < nb && c < nb) ? S.D[r * LA_DLD + c] : 0.0;
-      int bad = 0;
-      double* colbuf = S.rd;   // LA_NB doubles, reused as the reciprocal diagonal at the end
-      double myrd = 0.0;
+      for (int b = 0; b < 8; ++b) { const int c = c0 + b; av[b] = (c <= lane && lane < nbn) ? A(kn + lane, kn + c) : 0.0; }
+      if (it > 0) {
+        double sacc[8];
 #pragma unroll
-      for (int j = 0; j < LA_NB; ++j) {
-        if (j < nb) {
-          const double djj = __shfl_sync(0xffffffffu, a[j], j);
-          if (!(djj > 0.0) || !isfinite(djj)) { if (!bad) bad = kb + j + 1; }
-          const double rdv = rsqrt(djj);
-          const double l = a[j] * rdv;               // lane j: sqrt(d_jj); lanes > j: l_ij; lanes < j: 0
-          a[j] = l;
-          if (r == j) myrd = rdv;
-          colbuf[r] = l;
-          __syncwarp();
-#pragma unroll
-          for (int c = j + 1; c < LA_NB; ++c) a[c] = fma(-l, colbuf[c], a[c]);   // a[c] is zero (and stays unused) for c > r
-          __syncwarp();
+        for (int b = 0; b < 8; ++b) sacc[b] = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < LA_NB; ++k) {
+          const double pr = S.P[k * S.pld + lane];
+          const double2 q0 = *reinterpret_cast<const double2*>(&S.P[k * S.pld + c0]);
+          const double2 q1 = *reinterpret_cast<const double2*>(&S.P[k * S.pld + c0 + 2]);
+          const double2 q2 = *reinterpret_cast<const double2*>(&S.P[k * S.pld + c0 + 4]);
+          const double2 q3 = *reinterpret_cast<const double2*>(&S.P[k * S.pld + c0 + 6]);
+          sacc[0] = fma(pr, q0.x, sacc[0]); sacc[1] = fma(pr, q0.y, sacc[1]);
+          sacc[2] = fma(pr, q1.x, sacc[2]); sacc[3] = fma(pr, q1.y, sacc[3]);
+          sacc[4] = fma(pr, q2.x, sacc[4]); sacc[5] = fma(pr, q2.y, sacc[5]);
+          sacc[6] = fma(pr, q3.x, sacc[6]); sacc[7] = fma(pr, q3.y, sacc[7]);
         }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) av[b] -= sacc[b];
       }
 #pragma unroll
-      for (int c = 0; c < LA_NB; ++c) if (c <= r && r < nb && c < nb) S.D[r * LA_DLD + c] = a[c];
-      __syncwarp();
-      if (r < nb) { S.rd[r] = myrd; sumlog -= log(myrd); }
-      if (bad && lane == 0) S.flag[0] = bad;
-    }
-    __syncthreads();
-    if (S.flag[0]) break;
-    // write back the factored diagonal block and the reciprocal diagonal
-    for (int e = tid; e < LA_NB * LA_NB; e += LA_THREADS) {
-      const int r = e & 31, c = e >> 5;
-      if (r < nb && c < nb && r >= c) A(kb + r, kb + c) = S.D[r * LA_DLD + c];
-    }
-    if (tid < nb) rdiag[kb + tid] = S.rd[tid];
-    if (m > 0) {
-      // (c) panel solve: row i = kb+nb+t, x = a Lkk^-T, one row per thread
-      for (int t = tid; t < m; t += LA_THREADS) {
-        const int i = kb + nb + t;
-        double x[LA_NB];
+      for (int b = 0; b < 8; ++b) { const int c = c0 + b; S.D[lane * LA_DLD + c] = (c <= lane && lane < nbn) ? av[b] : 0.0; }
+      la_bar_sync(1, LA_TEAM);
+      if (it > 0) la_bar_arrive(2, LA_TEAM + LA_NTRAIL);       // the team no longer reads the solved panel
+      if (warp == 0) {
+        GAMC_WCLK(w0, 52);
+        // ---- column chain
+        const int r = lane;
+        double a[LA_NB];
 #pragma unroll
-        for (int c = 0; c < LA_NB; ++c) x[c] = (c < nb) ? A(i, kb + c) : 0.0;
+        for (int c = 0; c < LA_NB; ++c) a[c] = S.D[r * LA_DLD + c];
+        int bad = 0;
+        double myrd = 0.0;
 #pragma unroll
-        for (int c = 0; c < LA_NB; ++c) {
-          if (c < nb) {
-            const double xc = x[c] * S.rd[c];
-            x[c] = xc;
+        for (int j = 0; j < LA_NB; ++j) {
+          if (j < nbn) {
+            const double djj = __shfl_sync(0xffffffffu, a[j], j);
+            if (!(djj > 0.0) || !isfinite(djj)) { if (!bad) bad = kn + j + 1; }
+            const double rdv = rsqrt(djj);
+            const double l = a[j] * rdv;             // lane j: sqrt(d_jj); lanes > j: l_ij; lanes < j: 0
+            a[j] = l;
+            if (r == j) { myrd = rdv; S.rd[j] = rdv; }
+            S.LT[j * LA_DLD + r] = l;
+            __syncwarp();
+            if (r == 0) vflag[1] = it * LA_NB + j + 1;   // column j visible to the inverter (shared stores of a warp retire in order)
 #pragma unroll
-            for (int k = c + 1; k < LA_NB; ++k) if (k < nb) x[k] = fma(-xc, S.D[k * LA_DLD + c], x[k]);
+            for (int c = j + 1; c < LA_NB; ++c) a[c] = fma(-l, S.LT[j * LA_DLD + c], a[c]);   // a[c] stays unused for c > r
           }
         }
+        GAMC_WCLK(w0, 53);
+        // publish the factor to global memory
 #pragma unroll
-        for (int c = 0; c < LA_NB; ++c) {
-          if (c < nb) { A(i, kb + c) = x[c]; }
-          S.P[c * S.pld + t] = x[c];
+        for (int c = 0; c < LA_NB; ++c) if (c <= r && r < nbn) A(kn + r, kn + c) = a[c];
+        if (r < nbn) { rdiag[kn + r] = myrd; sumlog -= log(myrd); }
+        if (bad && lane == 0) S.flag[0] = bad;
+        GAMC_WCLK(w0, 54);
+      }
+    } else if (warp == 1) {
+      GAMC_WCLK_BEGIN(w1);
+      // ---- inverter: column `lane` of Lkk^-1 by forward substitution on e_lane, one column behind the chain
+      const int r = lane;
+      double y[LA_NB];
+#pragma unroll
+      for (int i = 0; i < LA_NB; ++i) y[i] = (i == r && r < nbn) ? 1.0 : 0.0;
+#pragma unroll
+      for (int i = 0; i < LA_NB; ++i) {
+        if (i < nbn) {
+          while (vflag[1] < it * LA_NB + i + 1) { }
+          asm volatile("" ::: "memory");
+          const double yi = y[i] * S.rd[i];
+          y[i] = yi;
+#pragma unroll
+          for (int k = i + 1; k < LA_NB; ++k) if (k < nbn) y[k] = fma(-S.LT[i * LA_DLD + k], yi, y[k]);
         }
       }
-      // zero the padding rows of the panel so that 4x4 micro-tiles may over-read
-      for (int t = m + tid; t < ((m + 3) & ~3); t += LA_THREADS)
-        for (int c = 0; c < LA_NB; ++c) S.P[c * S.pld + t] = 0.0;
-      __syncthreads();
-      // (d) trailing update A22 -= P P' (lower triangle), 4 x 4 register micro-tiles
-      const int mt = (m + 3) >> 2;
-      const int ntile = mt * (mt + 1) / 2;
-      for (int q = tid; q < ntile; q += LA_THREADS) {
-        // decode column-major triangular index: column tj, row ti >= tj
-        int tj = (int)(((2.0 * mt + 1.0) - sqrt((2.0 * mt + 1.0) * (2.0 * mt + 1.0) - 8.0 * (double)q)) * 0.5);
-        if (tj < 0) tj = 0;
-        while (tj > 0 && tj * mt - tj * (tj - 1) / 2 > q) --tj;
-        while ((tj + 1) * mt - (tj + 1) * tj / 2 <= q) ++tj;
-        const int ti = tj + (q - (tj * mt - tj * (tj - 1) / 2));
-        double acc[4][4];
+      // Y[k = r][c = i] = inv(c = i, k = r): lane r owns row r of the k-major shared copy
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+      for (int i = 0; i < LA_NB; i += 2) *reinterpret_cast<double2*>(&S.Y[r * LA_YLD + i]) = make_double2(y[i], y[i + 1]);
+      if (invd) {
+        double* gB = invd + (size_t)it * LA_INVD_STRIDE + LA_NB * LA_NB;   // layout B: [i * 32 + j] = inv(i, j)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-        const double* pa = S.P + 4 * ti;
-        const double* pb = S.P + 4 * tj;
+        for (int i = 0; i < LA_NB; ++i) gB[i * LA_NB + r] = y[i];
+        __syncwarp();
+        double* gA = invd + (size_t)it * LA_INVD_STRIDE;                   // layout A: [j * 32 + i] = inv(i, j)
+#pragma unroll
+        for (int j = 0; j < LA_NB; ++j) gA[j * LA_NB + r] = S.Y[j * LA_YLD + r];
+      }
+      GAMC_WCLK(w1, 55);
+    } else {
+      const int tt = la_trail_index(warp, lane);
+      GAMC_WCLK_BEGIN(w2);
+      if (it > 0) {
+        // ---- trailing update A22 -= P P' (lower triangle) with panel it-1 on the FP64 tensor cores: one 32 x 32
+        //      output block (4 x 4 DMMA m8n8k4 tiles, 8 k-steps) per warp task, minus block (0,0) = diagonal block
+        //      `it` (the team's).  Fragments come straight from the k-major panel (conflict-free for pld = 4 mod 16).
+        const int nb32 = (mprev + LA_NB - 1) / LA_NB;
+        const int ntask = nb32 * (nb32 + 1) / 2;
+        const int tw = tt >> 5;                                  // dense trailing-warp index 0..10
+        const int fr = lane >> 2, fk = lane & 3;
+        for (int q = 1 + tw; q < ntask; q += LA_NTRAIL / 32) {
+          // column-major triangular index -> (bi >= bj)
+          int bj = 0, rem = q;
+          while (rem >= nb32 - bj) { rem -= nb32 - bj; ++bj; }
+          const int bi = bj + rem;
+          double acc[4][4][2];
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+          const double* pa = S.P + 32 * bi + fr + (size_t)fk * S.pld;
+          const double* pb = S.P + 32 * bj + fr + (size_t)fk * S.pld;
+#pragma unroll 2
+          for (int k4 = 0; k4 < LA_NB / 4; ++k4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) { af[mi] = pa[(size_t)(4 * k4) * S.pld + 8 * mi]; bf[mi] = pb[(size_t)(4 * k4) * S.pld + 8 * mi]; }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+          }
+          const int i0 = kn + 32 * bi + fr, j0 = kn + 32 * bj + 2 * fk;
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) {
+            double old[4][2];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int i = i0 + 8 * mi, j = j0 + 8 * ni + e;
+                old[ni][e] = (i < p && j < p && i >= j) ? A(i, j) : 0.0;
+              }
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int i = i0 + 8 * mi, j = j0 + 8 * ni + e;
+                if (i < p && j < p && i >= j) A(i, j) = old[ni][e] - acc[mi][ni][e];
+              }
+          }
+        }
+        la_bar_sync(2, LA_TEAM + LA_NTRAIL);         // every reader of the solved panel it-1 is done (and its updates are visible)
+        if (warp == 2) GAMC_WCLK(w2, 56);
+      }
+      // ---- raw panel `it` -> shared, one row per thread (32 independent coalesced loads), zero padding rows
+      if (mnext > 0) {
+        const int mt4 = ((mnext + 3) >> 2) * 4;
+        for (int t = tt; t < mt4; t += LA_NTRAIL) {
+          double x[LA_NB];
+          if (t < mnext) {
+#pragma unroll
+            for (int c = 0; c < LA_NB; ++c) x[c] = A(kn + LA_NB + t, kn + c);
+          } else {
+#pragma unroll
+            for (int c = 0; c < LA_NB; ++c) x[c] = 0.0;
+          }
+#pragma unroll
+          for (int c = 0; c < LA_NB; ++c) S.P[c * S.pld + t] = x[c];
+        }
+      }
+      if (warp == 2) GAMC_WCLK(w2, 57);
+    }
+    __syncthreads();
+    if (REV) GAMC_PHASE(48);
+    if (S.flag[0]) break;
+    if (mnext > 0) {
+      // ---- panel solve X = P Lkk^-T as a GEMM with the inverted block: 4 x 8 register tiles, in place after a barrier
+      //      (one pass for p <= 512 + 32, the supported range: a second pass would read rows the first one overwrote)
+      const int mt = (mnext + 3) >> 2;
+      const int q = tid;
+      const int tr = q % mt, tc = q / mt;            // row group, column group (0..3)
+      const bool act = q < 4 * mt;
+      double acc[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+      if (act) {
+        const double* pa = S.P + 4 * tr;
+        const double* py = S.Y + 8 * tc;
+        const int kend = 8 * tc + 8;                 // inv(c, k) = 0 for k > c
 #pragma unroll 4
-        for (int c = 0; c < LA_NB; ++c) {
-          const double2 a01 = *reinterpret_cast<const double2*>(pa + c * S.pld);
-          const double2 a23 = *reinterpret_cast<const double2*>(pa + c * S.pld + 2);
-          const double2 b01 = *reinterpret_cast<const double2*>(pb + c * S.pld);
-          const double2 b23 = *reinterpret_cast<const double2*>(pb + c * S.pld + 2);
+        for (int k = 0; k < kend; ++k) {
+          const double2 a01 = *reinterpret_cast<const double2*>(pa + k * S.pld);
+          const double2 a23 = *reinterpret_cast<const double2*>(pa + k * S.pld + 2);
           const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-          const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+          double yv[8];
+#pragma unroll
+          for (int b = 0; b < 8; b += 2) {
+            const double2 t2 = *reinterpret_cast<const double2*>(py + k * LA_YLD + b);
+            yv[b] = t2.x; yv[b + 1] = t2.y;
+          }
 #pragma unroll
           for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+            for (int b = 0; b < 8; ++b) acc[a][b] = fma(av[a], yv[b], acc[a][b]);
         }
-        const int i0 = kb + nb + 4 * ti, j0 = kb + nb + 4 * tj;
+      }
+      __syncthreads();
+      if (act) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+        for (int b = 0; b < 8; ++b) {
+          const int c = 8 * tc + b;
+          *reinterpret_cast<double2*>(&S.P[c * S.pld + 4 * tr]) = make_double2(acc[0][b], acc[1][b]);
+          *reinterpret_cast<double2*>(&S.P[c * S.pld + 4 * tr + 2]) = make_double2(acc[2][b], acc[3][b]);
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
-            const int i = i0 + a, j = j0 + b;
-            if (i < p && j < p && i >= j) A(i, j) -= acc[a][b];
+            const int t = 4 * tr + a;
+            if (t < mnext) A(kn + LA_NB + t, kn + c) = acc[a][b];
           }
+        }
       }
+      __syncthreads();
+      if (REV) GAMC_PHASE(49);
     }
-    __syncthreads();
   }
   // broadcast result (each lane of warp 0 holds the logs of "its" diagonal entries)
   __syncthreads();
@@ -198,93 +338,157 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, LaScratch S, int* 
   return bad ? nan("") : out;
 }
 
-// Forward substitution Lm x = b in place on b (shared memory, M-space order), rdiag = 1/Lm_ii.
+// Forward substitution Lm x = b in place on b (shared memory, M-space order).  invd = the inverted diagonal blocks
+// written by chol_blocked.  Right-looking by block column: the last warp solves the diagonal block as a 32 x 32
+// matrix-vector product with the stored inverse while threads 0..479 already hold "their" row of the block column in
+// registers (prefetched one step ahead), so one step costs two barriers and no exposed L2 round trip.
 template <bool REV>
-__device__ void trsv_lower(MatView<REV> L, const double* rdiag, double* b, LaScratch S) {
+__device__ void trsv_lower(MatView<REV> L, const double* invd, double* b, LaScratch S) {
+  constexpr int RT = LA_THREADS - 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool solver = warp == (LA_THREADS / 32 - 1);
   const int p = L.p;
-  for (int kb = 0; kb < p; kb += LA_NB) {
+  const int nblk = (p + LA_NB - 1) / LA_NB;
+  double reg[LA_NB];     // solver warp: row `lane` of the inverted block; others: row kb+32+tid of the block column
+  auto prefetch = [&](int blk) {
+    const int kb = blk * LA_NB;
+    if (solver) {
+      const double* gA = invd + (size_t)blk * LA_INVD_STRIDE;
+#pragma unroll
+      for (int j = 0; j < LA_NB; ++j) reg[j] = gA[j * LA_NB + lane];
+    } else {
+      const int i = kb + LA_NB + tid;
+      if (i < p) {
+#pragma unroll
+        for (int c = 0; c < LA_NB; ++c) reg[c] = L(i, kb + c);
+      }
+    }
+  };
+  prefetch(0);
+  __syncthreads();
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int kb = blk * LA_NB;
     const int nb = min(LA_NB, p - kb);
-    for (int e = tid; e < LA_NB * LA_NB; e += LA_THREADS) {
-      const int r = e & 31, c = e >> 5;
-      if (r < nb && c < nb && r > c) S.D[r * LA_DLD + c] = L(kb + r, kb + c);
+    if (solver) {
+      double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+#pragma unroll
+      for (int j = 0; j < LA_NB; j += 4) {
+        if (j < nb) x0 = fma(reg[j], b[kb + j], x0);
+        if (j + 1 < nb) x1 = fma(reg[j + 1], b[kb + j + 1], x1);
+        if (j + 2 < nb) x2 = fma(reg[j + 2], b[kb + j + 2], x2);
+        if (j + 3 < nb) x3 = fma(reg[j + 3], b[kb + j + 3], x3);
+      }
+      const double x = (x0 + x1) + (x2 + x3);
+      __syncwarp();
+      if (lane < nb) { b[kb + lane] = x; S.xs[lane] = x; }
     }
     __syncthreads();
-    if (warp == 0) {
-      double br = (lane < nb) ? b[kb + lane] : 0.0;
-      const double rdv = (lane < nb) ? rdiag[kb + lane] : 0.0;
-      for (int j = 0; j < nb; ++j) {
-        const double xj = __shfl_sync(0xffffffffu, br * rdv, j);
-        if (lane == j) br = xj;
-        else if (lane > j && lane < nb) br = fma(-S.D[lane * LA_DLD + j], xj, br);
+    if (!solver) {
+      const int i = kb + LA_NB + tid;
+      if (i < p) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int c = 0; c < LA_NB; c += 4) {
+          s0 = fma(reg[c], S.xs[c], s0); s1 = fma(reg[c + 1], S.xs[c + 1], s1);
+          s2 = fma(reg[c + 2], S.xs[c + 2], s2); s3 = fma(reg[c + 3], S.xs[c + 3], s3);
+        }
+        b[i] -= (s0 + s1) + (s2 + s3);
       }
-      if (lane < nb) { b[kb + lane] = br; S.rd[lane] = br; }
-    }
-    __syncthreads();
-    for (int i = kb + nb + tid; i < p; i += LA_THREADS) {
-      double s0 = b[i], s1 = 0.0;
-#pragma unroll 8
-      for (int c = 0; c < nb; c += 2) {
-        s0 = fma(-L(i, kb + c), S.rd[c], s0);
-        if (c + 1 < nb) s1 = fma(-L(i, kb + c + 1), S.rd[c + 1], s1);
+      for (int i2 = i + RT; i2 < p; i2 += RT) {     // p > 512 only
+        double s = 0.0;
+        for (int c = 0; c < LA_NB; ++c) s = fma(L(i2, kb + c), S.xs[c], s);
+        b[i2] -= s;
       }
-      b[i] = s0 + s1;
     }
+    if (blk + 1 < nblk) prefetch(blk + 1);
     __syncthreads();
   }
 }
 
-// Backward substitution Lm' x = b in place on b (shared memory, M-space order).
+// Backward substitution Lm' x = b in place on b (shared memory, M-space order); same scheme, blocks in descending order,
+// thread j < kb holds column j of the block row.
 template <bool REV>
-__device__ void trsv_lower_t(MatView<REV> L, const double* rdiag, double* b, LaScratch S) {
+__device__ void trsv_lower_t(MatView<REV> L, const double* invd, double* b, LaScratch S) {
+  constexpr int RT = LA_THREADS - 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool solver = warp == (LA_THREADS / 32 - 1);
   const int p = L.p;
   const int nblk = (p + LA_NB - 1) / LA_NB;
+  double reg[LA_NB];     // solver warp: column `lane` of the inverted block; others: column tid of the block row
+  auto prefetch = [&](int blk) {
+    const int kb = blk * LA_NB;
+    const int nb = min(LA_NB, p - kb);
+    if (solver) {
+      const double* gB = invd + (size_t)blk * LA_INVD_STRIDE + LA_NB * LA_NB;
+#pragma unroll
+      for (int i = 0; i < LA_NB; ++i) reg[i] = gB[i * LA_NB + lane];
+    } else if (tid < kb) {
+#pragma unroll
+      for (int c = 0; c < LA_NB; ++c) reg[c] = (c < nb) ? L(kb + c, tid) : 0.0;
+    }
+  };
+  prefetch(nblk - 1);
+  __syncthreads();
   for (int blk = nblk - 1; blk >= 0; --blk) {
     const int kb = blk * LA_NB;
     const int nb = min(LA_NB, p - kb);
-    for (int e = tid; e < LA_NB * LA_NB; e += LA_THREADS) {
-      const int r = e & 31, c = e >> 5;
-      if (r < nb && c < nb && r > c) S.D[r * LA_DLD + c] = L(kb + r, kb + c);
+    if (solver) {
+      double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+#pragma unroll
+      for (int i = 0; i < LA_NB; i += 4) {
+        if (i < nb) x0 = fma(reg[i], b[kb + i], x0);
+        if (i + 1 < nb) x1 = fma(reg[i + 1], b[kb + i + 1], x1);
+        if (i + 2 < nb) x2 = fma(reg[i + 2], b[kb + i + 2], x2);
+        if (i + 3 < nb) x3 = fma(reg[i + 3], b[kb + i + 3], x3);
+      }
+      const double x = (x0 + x1) + (x2 + x3);
+      __syncwarp();
+      if (lane < nb) { b[kb + lane] = x; S.xs[lane] = x; }
+      if (lane >= nb) S.xs[lane] = 0.0;
     }
     __syncthreads();
-    if (warp == 0) {
-      // solve Lkk' x = b: x_j = (b_j - sum_{i>j} L_ij x_i) / L_jj, j descending; lane = j
-      double bj = (lane < nb) ? b[kb + lane] : 0.0;
-      const double rdv = (lane < nb) ? rdiag[kb + lane] : 0.0;
-      for (int i = nb - 1; i >= 0; --i) {
-        const double xi = __shfl_sync(0xffffffffu, bj * rdv, i);
-        if (lane == i) bj = xi;
-        else if (lane < i) bj = fma(-S.D[i * LA_DLD + lane], xi, bj);
+    if (!solver) {
+      if (tid < kb) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int c = 0; c < LA_NB; c += 4) {
+          s0 = fma(reg[c], S.xs[c], s0); s1 = fma(reg[c + 1], S.xs[c + 1], s1);
+          s2 = fma(reg[c + 2], S.xs[c + 2], s2); s3 = fma(reg[c + 3], S.xs[c + 3], s3);
+        }
+        b[tid] -= (s0 + s1) + (s2 + s3);
       }
-      if (lane < nb) { b[kb + lane] = bj; S.rd[lane] = bj; }
-    }
-    __syncthreads();
-    for (int j = tid; j < kb; j += LA_THREADS) {
-      double s0 = b[j], s1 = 0.0;
-#pragma unroll 8
-      for (int c = 0; c < nb; c += 2) {
-        s0 = fma(-L(kb + c, j), S.rd[c], s0);
-        if (c + 1 < nb) s1 = fma(-L(kb + c + 1, j), S.rd[c + 1], s1);
+      for (int j2 = tid + RT; j2 < kb; j2 += RT) {  // p > 512 only
+        double s = 0.0;
+        for (int c = 0; c < nb; ++c) s = fma(L(kb + c, j2), S.xs[c], s);
+        b[j2] -= s;
       }
-      b[j] = s0 + s1;
     }
+    if (blk > 0) prefetch(blk - 1);
     __syncthreads();
   }
 }
 
-// y = A x for a full symmetric p x p column-major matrix (natural order), x and y in shared memory.
-__device__ inline void symv_full(const double* __restrict__ A, int ld, int p, const double* x, double* y) {
-  for (int i = threadIdx.x; i < p; i += blockDim.x) {
-    double s0 = 0.0, s1 = 0.0;
-    int j = 0;
-    for (; j + 1 < p; j += 2) {
-      s0 = fma(A[(size_t)i + (size_t)j * ld], x[j], s0);
-      s1 = fma(A[(size_t)i + (size_t)(j + 1) * ld], x[j + 1], s1);
-    }
-    if (j < p) s0 = fma(A[(size_t)i + (size_t)j * ld], x[j], s0);
-    y[i] = s0 + s1;
+// Streaming helper for the p x p passes of the step kernels: U independent loads in flight per thread (the single CTA
+// is L2-latency bound, not bandwidth bound), then f(e, value) on each.
+template <int U, typename F>
+__device__ __forceinline__ void flat_stream(const double* src, int n, F f) {
+  for (int base = 0; base < n; base += U * (int)blockDim.x) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int e = base + u * (int)blockDim.x + (int)threadIdx.x; v[u] = (e < n) ? src[e] : 0.0; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int e = base + u * (int)blockDim.x + (int)threadIdx.x; if (e < n) f(e, v[u]); }
   }
+}
+
+// x' A x for a full p x p column-major matrix, x in shared memory; `red` = block_sum scratch.  All threads get the value.
+__device__ inline double quad_form(const double* A, int p, const double* x, double* red) {
+  double q = 0.0;
+  flat_stream<16>(A, p * p, [&](int e, double v) {
+    const int j = e / p, i = e - j * p;
+    q = fma(v * x[i], x[j], q);
+  });
+  return block_sum(q, red);
 }
 
 // y = L x for a lower-triangular column-major L (natural order); x, y in shared memory.

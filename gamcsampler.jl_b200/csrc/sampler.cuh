@@ -18,6 +18,7 @@ struct Bufs {
   double* gs;                            // [2][p]           pstate.gradlogtarget
   double* U; size_t Ustride;             // U[slot]: p x p, upper triangle = reverse Cholesky factor of G[slot]
   double* rdiagU;                        // [2][p] reciprocal diagonal (M-space order)
+  double* invU; size_t invUstride;       // [2][la_invd_doubles(p)] inverted 32 x 32 diagonal blocks of the factor (block solves)
   double* fterm;                         // [2][p] G^-1 grad ("firstterm")
   double* theta; double* theta_prop; double* mu; double* lastmean; double* secondlastmean;
   double* C;                             // p x p  sstate.oldinvtensor while in AM mode (AM covariance)
@@ -74,45 +75,48 @@ __device__ inline double add_prior(double* E, int goff, const double* theta, int
   return E[0] + lp;
 }
 
-// all-finite check of [g, G] of a slot; returns 1 if everything is finite
-__device__ inline int slot_finite(const double* E, int goff, int p, double* red) {
+// all-finite check of the gradient of a landed evaluation (the metric is checked while factor_slot copies it)
+__device__ inline int grad_finite(const double* E, int p, double* red) {
   double bad = 0.0;
   for (int i = threadIdx.x; i < p; i += blockDim.x) if (!isfinite(E[1 + i])) bad = 1.0;
-  const size_t n = (size_t)p * p;
-  for (size_t i = threadIdx.x; i < n; i += blockDim.x) if (!isfinite(E[goff + i])) bad = 1.0;
   return block_sum(bad, red) == 0.0;
 }
 
 // Move the landed evaluation (prior already added) into a slot and factor its metric:
 // Gs[slot] <- G, gs[slot] <- g, U[slot] <- reverse Cholesky of G, fterm[slot] <- G^-1 g.
-// Returns 0 on success, the failed (M-space, 1-based) pivot otherwise.
+// Returns 0 on success, the failed (M-space, 1-based) pivot, or -1 if G has a non-finite entry.
 __device__ inline int factor_slot(const Bufs& B, int slot, int p, StepSmem& S) {
   const double* G = B.R + B.goff;
   const double* g = B.R + 1;
   double* U = B.U + (size_t)slot * B.Ustride;
   double* Gd = B.Gs + (size_t)slot * B.Gstride;
-  // copy G; its (natural) upper triangle = M-space lower triangle goes to the factor buffer
-  const size_t n = (size_t)p * p;
-  for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
-    const int i = (int)(e % p), j = (int)(e / p);
-    const double v = G[e];
+  double* invd = B.invU + (size_t)slot * B.invUstride;
+  // one pass over G: copy, finite check; its (natural) upper triangle = M-space lower triangle goes to the factor buffer
+  double nonfinite = 0.0;
+  flat_stream<16>(G, p * p, [&](int e, double v) {
+    const int j = e / p, i = e - j * p;
     Gd[e] = v;
     if (i <= j) U[e] = v;
-  }
+    if (!isfinite(v)) nonfinite = 1.0;
+  });
   for (int i = threadIdx.x; i < p; i += blockDim.x) B.gs[(size_t)slot * p + i] = g[i];
-  __syncthreads();
+  if (block_sum(nonfinite, S.red) != 0.0) return -1;
+  GAMC_PHASE(16);
   MatView<true> V{U, p, p};
   int bad = 0;
-  const double sl = chol_blocked<true>(V, B.rdiagU + (size_t)slot * p, S.la, &bad);
+  const double sl = chol_blocked<true>(V, B.rdiagU + (size_t)slot * p, invd, S.la, &bad);
+  GAMC_PHASE(17);
   if (bad) return bad;
   if (threadIdx.x == 0) B.st->sumlog[slot] = sl;
   // firstterm = G^-1 g = Lm^-T (Lm^-1 g')   in M space
   for (int i = threadIdx.x; i < p; i += blockDim.x) S.v3[i] = g[p - 1 - i];
   __syncthreads();
-  trsv_lower<true>(V, B.rdiagU + (size_t)slot * p, S.v3, S.la);
-  trsv_lower_t<true>(V, B.rdiagU + (size_t)slot * p, S.v3, S.la);
+  trsv_lower<true>(V, invd, S.v3, S.la);
+  GAMC_PHASE(18);
+  trsv_lower_t<true>(V, invd, S.v3, S.la);
   for (int i = threadIdx.x; i < p; i += blockDim.x) B.fterm[(size_t)slot * p + i] = S.v3[p - 1 - i];
   __syncthreads();
+  GAMC_PHASE(19);
   return 0;
 }
 
@@ -172,9 +176,10 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_sampler_init(Bufs B, TuneCfg 
   DevState* st = B.st;
   const int p = T.p;
   const double lt = add_prior(B.R, B.goff, B.theta, p, T.lambda, S.red);
-  const int fin = slot_finite(B.R, B.goff, p, S.red) && isfinite(lt);
+  const int fin = grad_finite(B.R, p, S.red) && isfinite(lt);
   if (!fin) { raise_error(st, 2 /*GAMC_NONFINITE_INIT*/, 0); return; }
   const int bad = factor_slot(B, 0, p, S);
+  if (bad < 0) { raise_error(st, 2 /*GAMC_NONFINITE_INIT*/, 0); return; }
   if (bad) { raise_error(st, 3 /*GAMC_NOT_POSDEF*/, p + 1 - bad); return; }
   for (int i = threadIdx.x; i < p; i += blockDim.x) B.lastmean[i] = B.theta[i];   // GAMC.jl:218
   if (threadIdx.x == 0) { st->logtarget = lt; st->cur = 0; }
@@ -196,25 +201,28 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_smmala_pre(Bufs B, TuneCfg T,
     st->updatetensorcount += 1;                       // :13
     if (T.verbose_sm) st->sm_prop += 1;               // :15-17
   }
+  GAMC_PHASE_BEGIN();
   if (refactor) {                                     // :19-31 (previous step was AM: grad/metric stale)
     const double lt = add_prior(B.R, B.goff, B.theta, p, T.lambda, S.red);
     if (threadIdx.x == 0) st->logtarget = lt;
     const int bad = factor_slot(B, cur, p, S);
-    if (bad) { raise_error(st, 3, p + 1 - bad); return; }
+    if (bad) { raise_error(st, 3, bad < 0 ? 0 : p + 1 - bad); return; }
   }
   __syncthreads();
+  GAMC_PHASE(refactor ? 32 : 33);
   const double eps = st->step, sq = st->sqrtstep;
   // y' = Lm^-T z'  (cholinvtensor * randn(p), :35)
   const double* z = B.tape_z + (size_t)tape_idx * p;
   for (int i = threadIdx.x; i < p; i += blockDim.x) S.v0[i] = z[p - 1 - i];
   __syncthreads();
   MatView<true> V{B.U + (size_t)cur * B.Ustride, p, p};
-  trsv_lower_t<true>(V, B.rdiagU + (size_t)cur * p, S.v0, S.la);
+  trsv_lower_t<true>(V, B.invU + (size_t)cur * B.invUstride, S.v0, S.la);
   for (int i = threadIdx.x; i < p; i += blockDim.x) {
     const double m = B.theta[i] + 0.5 * eps * B.fterm[(size_t)cur * p + i];   // :33
     B.mu[i] = m;
     B.theta_prop[i] = m + sq * S.v0[p - 1 - i];                                // :35
   }
+  GAMC_PHASE(34);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -230,31 +238,31 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_smmala_post(Bufs B, TuneCfg T
   const double* Gc = B.Gs + (size_t)cur * B.Gstride;
   const double* Gp = B.Gs + (size_t)prop * B.Gstride;
   const double eps = st->step;
+  GAMC_PHASE_BEGIN();
   const double lt_p = add_prior(B.R, B.goff, B.theta_prop, p, T.lambda, S.red);
-  int ok = slot_finite(B.R, B.goff, p, S.red) && isfinite(lt_p);
+  GAMC_PHASE(0);
+  int ok = grad_finite(B.R, p, S.red) && isfinite(lt_p);
+  GAMC_PHASE(1);
   double ratio = -INFINITY;
+  int bad = 0;
+  if (ok) bad = factor_slot(B, prop, p, S);          // newinvtensor / newfirstterm (:43,56) via one factorisation
+  if (bad > 0) { raise_error(st, 3, p + 1 - bad); return; }
+  if (bad < 0) ok = 0;                               // non-finite metric at the proposal: reject
   if (ok) {
-    const int bad = factor_slot(B, prop, p, S);      // newinvtensor / newfirstterm (:43,56) via one factorisation
-    if (bad) { raise_error(st, 3, p + 1 - bad); return; }
+    GAMC_PHASE(2);
     // d = theta* - mu ; q1 = d' G d / eps                                              (:47-54)
     for (int i = threadIdx.x; i < p; i += blockDim.x) S.v0[i] = B.theta_prop[i] - B.mu[i];
     __syncthreads();
-    symv_full(Gc, p, p, S.v0, S.v1);
-    __syncthreads();
-    double q1 = 0.0;
-    for (int i = threadIdx.x; i < p; i += blockDim.x) q1 = fma(S.v0[i], S.v1[i], q1);
-    q1 = block_sum(q1, S.red);
+    const double q1 = quad_form(Gc, p, S.v0, S.red);
+    GAMC_PHASE(3);
     // mu* = theta* + eps/2 f* ; d2 = theta - mu* ; q2 = d2' G* d2 / eps                 (:58-67)
     for (int i = threadIdx.x; i < p; i += blockDim.x) {
       const double ms = B.theta_prop[i] + 0.5 * eps * B.fterm[(size_t)prop * p + i];
       S.v2[i] = B.theta[i] - ms;
     }
     __syncthreads();
-    symv_full(Gp, p, p, S.v2, S.v1);
-    __syncthreads();
-    double q2 = 0.0;
-    for (int i = threadIdx.x; i < p; i += blockDim.x) q2 = fma(S.v2[i], S.v1[i], q2);
-    q2 = block_sum(q2, S.red);
+    const double q2 = quad_form(Gp, p, S.v2, S.red);
+    GAMC_PHASE(4);
     const double plog = p * log(eps);
     const double ld_old = plog - 2.0 * st->sumlog[cur];   // logdet(eps * G^-1)
     const double ld_new = plog - 2.0 * st->sumlog[prop];
@@ -280,6 +288,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_smmala_post(Bufs B, TuneCfg T
   }
   __syncthreads();
   step_tail(B, T, accept);
+  GAMC_PHASE(5);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -317,7 +326,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre(Bufs B, TuneCfg T, lon
   __syncthreads();
   MatView<false> V{B.Lc, p, p};
   int bad = 0;
-  chol_blocked<false>(V, B.rdiagL, S.la, &bad);
+  chol_blocked<false>(V, B.rdiagL, nullptr, S.la, &bad);
   if (bad) { raise_error(st, 3, bad); return; }
   const double* z = B.tape_z + (size_t)tape_idx * p;
   for (int i = threadIdx.x; i < p; i += blockDim.x) S.v3[i] = z[i];
