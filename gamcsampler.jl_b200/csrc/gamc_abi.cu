@@ -365,7 +365,7 @@ gamc_status setup_target(gamc_ctx* h) {
   h->goff = (1 + p + 1) & ~1;  // G starts 16-byte aligned
   {
     const size_t pp = (size_t)p * p;
-    const size_t n_state = 64, n_vecs = ((size_t)16 * p + 15) & ~(size_t)15, n_R = ((size_t)h->goff + pp + 15) & ~(size_t)15, n_mats = 9 * pp + 2 * la_invd_doubles(p);
+    const size_t n_state = 64, n_vecs = ((size_t)20 * p + 16 + 15) & ~(size_t)15, n_R = ((size_t)h->goff + pp + 15) & ~(size_t)15, n_mats = 9 * pp + 2 * la_invd_doubles(p);
     h->arena_bytes = sizeof(double) * (n_state + n_vecs + n_R + n_mats);
     CUDA_TRY(h, cudaMalloc(&h->arena, h->arena_bytes));
     CUDA_TRY(h, cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
@@ -415,6 +415,14 @@ bool schedule_decision(const gamc_config& c, long long i, long long tot, double 
     case GAMC_SCHED_RAND_QUAD_DECAY: { double a = par(0, 1e-5), b = par(1, 0.0); return u <= (1 - b) * (1 / (1 + a * (di * di))) + b; }
     default: return true;
   }
+}
+
+// move a landed level-2 evaluation into its slot (mode 0 initial point, 1 current point, 2 proposal)
+gamc_status launch_land(gamc_ctx* h, int mode) {
+  ProfScope ps(h, GAMC_K_LINALG);
+  k_land<<<h->p, LAND_THREADS, 0, h->stream>>>(h->B, h->tune, mode);
+  CUDA_TRY(h, cudaGetLastError());
+  return GAMC_OK;
 }
 
 template <typename K, typename... Args>
@@ -713,10 +721,10 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   B.U = h->mats + 2 * pp; B.Ustride = pp;
   B.invU = h->mats + 9 * pp; B.invUstride = la_invd_doubles(p);
   B.C = h->mats + 4 * pp; B.W = h->mats + 5 * pp; B.Lc = h->mats + 6 * pp; B.Lstride = pp;   // Lc: three buffers (am_mode 2 rotates them)
-  CUDA_TRY(h, cudaMemsetAsync(h->vecs, 0, sizeof(double) * (size_t)p * 16, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->vecs, 0, sizeof(double) * ((size_t)p * 20 + 16), h->stream));
   double* v = h->vecs;
   B.gs = v; v += 2 * p; B.rdiagU = v; v += 2 * p; B.fterm = v; v += 2 * p;
-  B.theta = v; v += p; B.theta_prop = v; v += p; B.mu = v; v += p; B.lastmean = v; v += p; B.secondlastmean = v; v += p; B.rdiagL = v; v += 3 * p; B.accbuf = v;
+  B.theta = v; v += p; B.theta_prop = v; v += p; B.mu = v; v += p; B.lastmean = v; v += p; B.secondlastmean = v; v += p; B.rdiagL = v; v += 3 * p; B.accbuf = v; v += 2 * p; B.land = v;
   B.R = h->R; B.goff = h->goff;
   h->chain_cap = std::max<long long>(0, cfg->nsteps - cfg->burnin);
   if (h->chain_cap > 0) {
@@ -747,6 +755,8 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   } else {
     // initialize! (:157-176): first evaluation of target + gradient + metric at theta0
     s = eval_device(h, B.theta, 2, true);
+    if (s != GAMC_OK) return s;
+    s = launch_land(h, 0);
     if (s != GAMC_OK) return s;
     s = launch_step(h, k_sampler_init, B, T);
     if (s != GAMC_OK) return s;
@@ -847,9 +857,13 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
     if (h->h_present) {                                                                  // :12
       h->spec_ready = false;
       const int refactor = h->h_past ? 0 : 1;
-      if (refactor) { s = eval_device(h, B.theta, 2, true); if (s != GAMC_OK) return s; }  // :20
+      if (refactor) {                                                                    // :20
+        s = eval_device(h, B.theta, 2, true); if (s != GAMC_OK) return s;
+        s = launch_land(h, 1); if (s != GAMC_OK) return s;
+      }
       s = launch_step(h, k_smmala_pre, B, T, ti, refactor); if (s != GAMC_OK) return s;
       s = eval_device(h, B.theta_prop, 2, true); if (s != GAMC_OK) return s;             // :37
+      s = launch_land(h, 2); if (s != GAMC_OK) return s;
       s = launch_step(h, k_smmala_post, B, T, ti); if (s != GAMC_OK) return s;
     } else {                                                                             // :128
       const bool next_am = (T.am_mode == 2) && (k + 1 < n) && !kinds[k + 1];            // next step is AM too: speculate

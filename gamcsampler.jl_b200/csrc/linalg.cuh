@@ -36,19 +36,20 @@ struct MatView {
 
 // Shared-memory scratch of the factorisation and the triangular solves.
 struct LaScratch {
-  double* D;      // LA_NB * LA_DLD   diagonal block before factorisation, row r at D[r * LA_DLD]
-  double* LT;     // LA_NB * LA_DLD   its factor by columns, LT[j * LA_DLD + r] = Lkk(r, j)
-  double* Y;      // LA_NB * LA_YLD   its inverse, Y[k * LA_YLD + c] = (Lkk^-1)(c, k)
-  double* rd;     // LA_NB            reciprocal diagonal of the block
-  double* xs;     // LA_NB            block solution of the triangular solves
-  double* P;      // LA_NB * pld      panel, k-major: P[c * pld + t]
-  int* flag;      // [0] failed pivot, [1] number of factored columns published to the inverter warp (monotone)
+  double* D;      // LA_NB * LA_DLD      diagonal block before factorisation, row r at D[r * LA_DLD]
+  double* Dn;     // 2 * LA_NB * LA_DLD  staged copies of the next diagonal block (written by the trailing update)
+  double* LT;     // LA_NB * LA_DLD      its factor by columns, LT[j * LA_DLD + r] = Lkk(r, j)
+  double* Y;      // LA_NB * LA_YLD      its inverse by rows, Y[c * LA_YLD + k] = (Lkk^-1)(c, k)
+  double* rd;     // LA_NB               reciprocal diagonal of the block
+  double* xs;     // LA_NB               block solution of the triangular solves
+  double* P;      // LA_NB * pld         solved panel, k-major: P[c * pld + t]
+  int* flag;      // [0] failed pivot, [1] factored columns published by the chain warp, [2] inverse rows published (monotone)
   int pld;
 };
 
 __host__ __device__ inline size_t la_scratch_bytes(int p) {
   const int pld = ((p + 3) & ~3) + 4;
-  return sizeof(double) * (2 * LA_NB * LA_DLD + LA_NB * LA_YLD + 2 * LA_NB + (size_t)LA_NB * pld) + 16;
+  return sizeof(double) * (4 * LA_NB * LA_DLD + LA_NB * LA_YLD + 2 * LA_NB + (size_t)LA_NB * pld) + 16;
 }
 
 __device__ inline LaScratch la_scratch_carve(unsigned char* base, int p) {
@@ -57,7 +58,8 @@ __device__ inline LaScratch la_scratch_carve(unsigned char* base, int p) {
   s.Y = reinterpret_cast<double*>(base);          // first: keeps the 16-byte alignment the double2 reads need
   s.P = s.Y + LA_NB * LA_YLD;
   s.D = s.P + (size_t)LA_NB * s.pld;
-  s.LT = s.D + LA_NB * LA_DLD;
+  s.Dn = s.D + LA_NB * LA_DLD;
+  s.LT = s.Dn + 2 * LA_NB * LA_DLD;
   s.rd = s.LT + LA_NB * LA_DLD;
   s.xs = s.rd + LA_NB;
   s.flag = reinterpret_cast<int*>(s.xs + LA_NB);
@@ -66,24 +68,27 @@ __device__ inline LaScratch la_scratch_carve(unsigned char* base, int p) {
 
 __device__ __forceinline__ void la_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void la_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void la_spin_until(volatile int* flag, int target) {
+  while (*flag < target) __nanosleep(40);
+  asm volatile("" ::: "memory");
+}
 
 // Warp roles of chol_blocked (16 warps).  Scheduler partition 0 (warps 0, 4, 8, 12) is kept free of trailing-update
 // work so that the serial column chain of warp 0 is not slowed down by FP64 pipe contention.
-constexpr int LA_TEAM = 128;                                   // warps 0, 4, 8, 12: diagonal-block update; warp 0: column chain
-constexpr int LA_NTRAIL = LA_THREADS - LA_TEAM - 32;           // 11 warps: trailing update + panel load; warp 1: inverter
+constexpr int LA_TEAM = 128;                                   // warps 0, 4, 8, 12: diagonal-block update; warp 0: chain; warp 4: inverter
+constexpr int LA_NTRAIL = LA_THREADS - LA_TEAM;                // 12 warps: trailing update + panel solve
 __device__ __forceinline__ bool la_is_team(int warp) { return (warp & 3) == 0; }
-__device__ __forceinline__ int la_trail_index(int warp, int lane) {   // dense index 0..LA_NTRAIL-1 of a trailing thread
-  // warps 2,3 -> 0,1; 5,6,7 -> 2,3,4; 9,10,11 -> 5,6,7; 13,14,15 -> 8,9,10
-  const int w = warp - 1 - (warp >> 2) - 1;
-  return w * 32 + lane;
-}
+__device__ __forceinline__ int la_trail_index(int warp, int lane) { return (warp - 1 - (warp >> 2)) * 32 + lane; }   // dense 0..383
 
-// In-place blocked right-looking Cholesky of the lower triangle (M space) of A: A = Lm Lm', one CTA, software-pipelined:
-// in pass `it` the team updates diagonal block `it` with panel it-1, warp 0 factors it column by column (row per lane,
-// in registers; dependent chain per column: shfl -> rsqrt -> mul -> sts/lds -> fma, no divide, no sqrt) while warp 1
-// inverts the factor one column behind (lane j solves Lkk y = e_j), and the other eleven warps apply the rest of the
-// rank-32 trailing update of panel it-1 and then stage the raw panel `it` in shared memory.  The panel solve is a small
-// GEMM with the inverted diagonal block (no per-row dependent chains).
+// In-place blocked right-looking Cholesky of the lower triangle (M space) of A: A = Lm Lm', one CTA, software-pipelined
+// at column granularity.  In pass `it`:
+//   team (warps 0,4,8,12)  diagonal block `it` -= Pn Pn' (Pn = first 32 rows of the solved panel it-1)
+//   warp 0                 factors it column by column (row per lane, in registers; dependent chain per column:
+//                          shfl -> rsqrt -> mul -> sts/lds -> fma, no divide, no sqrt) and publishes each column
+//   warp 4                 inverts the factor one column behind (lane j solves Lkk y = e_j) and publishes each row
+//   the other 12 warps     rank-32 trailing update with panel it-1 on the FP64 tensor cores (DMMA m8n8k4), then the
+//                          panel solve X = A_panel Lkk^-T, one row per thread, one column behind the inverter
+// so the serial column chain is the only thing on the critical path of a pass.
 // Also writes rdiag[i] = 1 / Lm_ii (M-space order, global), the inverted diagonal blocks (invd, may be null; both
 // layouts [j*32+i] and [i*32+j], for the coalesced block solves of trsv_lower / trsv_lower_t) and returns
 // sum_i log Lm_ii.  On a non-positive pivot returns NaN and sets *fail_pivot = 1-based M-space pivot (else 0).
@@ -93,9 +98,8 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaSc
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p = A.p;
   const int nblk = (p + LA_NB - 1) / LA_NB;
-  double sumlog = 0.0;  // lane-local partial in warp 0; reduced at the end
   volatile int* vflag = S.flag;
-  if (tid == 0) { S.flag[0] = 0; S.flag[1] = 0; }
+  if (tid == 0) { S.flag[0] = 0; S.flag[1] = 0; S.flag[2] = 0; }
   __syncthreads();
   for (int it = 0; it < nblk; ++it) {
     const int kn = it * LA_NB;                       // first row / column of diagonal block `it`
@@ -103,12 +107,19 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaSc
     const int mprev = p - kn;                        // rows of panel it-1 (= trailing size), when it > 0
     const int mnext = p - kn - nbn;                  // rows of panel it
     if (la_is_team(warp)) {
-      // ---- team: diagonal block `it` = A(block) - Pn Pn' (Pn = first 32 rows of the solved panel it-1), 8 columns per warp
+      // ---- team: diagonal block `it` = A(block) - Pn Pn', 8 columns per warp.  From pass 2 on the block comes from
+      //      the shared staging copy the trailing update of the previous pass left (no L2 round trip).
       const int c0 = (warp >> 2) * 8;
       GAMC_WCLK_BEGIN(w0);
       double av[8];
+      if (it >= 2) {
+        const double* Ds = S.Dn + (it & 1) * LA_NB * LA_DLD;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) { const int c = c0 + b; av[b] = (c <= lane && lane < nbn) ? A(kn + lane, kn + c) : 0.0; }
+        for (int b = 0; b < 8; ++b) av[b] = Ds[lane * LA_DLD + c0 + b];
+      } else {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { const int c = c0 + b; av[b] = (c <= lane && lane < nbn) ? A(kn + lane, kn + c) : 0.0; }
+      }
       if (it > 0) {
         double sacc[8];
 #pragma unroll
@@ -131,7 +142,7 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaSc
 #pragma unroll
       for (int b = 0; b < 8; ++b) { const int c = c0 + b; S.D[lane * LA_DLD + c] = (c <= lane && lane < nbn) ? av[b] : 0.0; }
       la_bar_sync(1, LA_TEAM);
-      if (it > 0) la_bar_arrive(2, LA_TEAM + LA_NTRAIL);       // the team no longer reads the solved panel
+      if (it > 0) la_bar_arrive(2, LA_THREADS);                // the team no longer reads the solved panel it-1
       if (warp == 0) {
         GAMC_WCLK(w0, 52);
         // ---- column chain
@@ -151,51 +162,51 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaSc
             a[j] = l;
             if (r == j) { myrd = rdv; S.rd[j] = rdv; }
             S.LT[j * LA_DLD + r] = l;
+            if (j + 1 < LA_NB) {                     // next pivot column first, through a shuffle (shortest dependent path)
+              const double ln = __shfl_sync(0xffffffffu, l, j + 1);
+              a[j + 1] = fma(-l, ln, a[j + 1]);
+            }
             __syncwarp();
             if (r == 0) vflag[1] = it * LA_NB + j + 1;   // column j visible to the inverter (shared stores of a warp retire in order)
 #pragma unroll
-            for (int c = j + 1; c < LA_NB; ++c) a[c] = fma(-l, S.LT[j * LA_DLD + c], a[c]);   // a[c] stays unused for c > r
+            for (int c = j + 2; c < LA_NB; ++c) a[c] = fma(-l, S.LT[j * LA_DLD + c], a[c]);   // a[c] stays unused for c > r
           }
         }
         GAMC_WCLK(w0, 53);
         // publish the factor to global memory
 #pragma unroll
         for (int c = 0; c < LA_NB; ++c) if (c <= r && r < nbn) A(kn + r, kn + c) = a[c];
-        if (r < nbn) { rdiag[kn + r] = myrd; sumlog -= log(myrd); }
+        if (r < nbn) rdiag[kn + r] = myrd;
         if (bad && lane == 0) S.flag[0] = bad;
         GAMC_WCLK(w0, 54);
-      }
-    } else if (warp == 1) {
-      GAMC_WCLK_BEGIN(w1);
-      // ---- inverter: column `lane` of Lkk^-1 by forward substitution on e_lane, one column behind the chain
-      const int r = lane;
-      double y[LA_NB];
+      } else if (warp == 4) {
+        // ---- inverter: column `lane` of Lkk^-1 by forward substitution on e_lane, one column behind the chain;
+        //      after step i every lane holds inv(i, lane): row i of the inverse is published for the panel solve
+        const int r = lane;
+        double y[LA_NB];
 #pragma unroll
-      for (int i = 0; i < LA_NB; ++i) y[i] = (i == r && r < nbn) ? 1.0 : 0.0;
+        for (int i = 0; i < LA_NB; ++i) y[i] = (i == r && r < nbn) ? 1.0 : 0.0;
 #pragma unroll
-      for (int i = 0; i < LA_NB; ++i) {
-        if (i < nbn) {
-          while (vflag[1] < it * LA_NB + i + 1) { }
-          asm volatile("" ::: "memory");
-          const double yi = y[i] * S.rd[i];
-          y[i] = yi;
+        for (int i = 0; i < LA_NB; ++i) {
+          if (i < nbn) {
+            la_spin_until(vflag + 1, it * LA_NB + i + 1);
+            const double yi = y[i] * S.rd[i];
+            y[i] = yi;
+            S.Y[i * LA_YLD + r] = yi;
+            __syncwarp();
+            if (r == 0) vflag[2] = it * LA_NB + i + 1;
 #pragma unroll
-          for (int k = i + 1; k < LA_NB; ++k) if (k < nbn) y[k] = fma(-S.LT[i * LA_DLD + k], yi, y[k]);
+            for (int k = i + 1; k < LA_NB; ++k) if (k < nbn) y[k] = fma(-S.LT[i * LA_DLD + k], yi, y[k]);
+          }
         }
+        if (invd) {
+          double* gB = invd + (size_t)it * LA_INVD_STRIDE + LA_NB * LA_NB;   // layout B: [i * 32 + j] = inv(i, j)
+          double* gA = invd + (size_t)it * LA_INVD_STRIDE;                   // layout A: [j * 32 + i] = inv(i, j)
+#pragma unroll
+          for (int i = 0; i < LA_NB; ++i) { gB[i * LA_NB + r] = y[i]; gA[r * LA_NB + i] = y[i]; }
+        }
+        GAMC_WCLK(w0, 55);
       }
-      // Y[k = r][c = i] = inv(c = i, k = r): lane r owns row r of the k-major shared copy
-#pragma unroll
-      for (int i = 0; i < LA_NB; i += 2) *reinterpret_cast<double2*>(&S.Y[r * LA_YLD + i]) = make_double2(y[i], y[i + 1]);
-      if (invd) {
-        double* gB = invd + (size_t)it * LA_INVD_STRIDE + LA_NB * LA_NB;   // layout B: [i * 32 + j] = inv(i, j)
-#pragma unroll
-        for (int i = 0; i < LA_NB; ++i) gB[i * LA_NB + r] = y[i];
-        __syncwarp();
-        double* gA = invd + (size_t)it * LA_INVD_STRIDE;                   // layout A: [j * 32 + i] = inv(i, j)
-#pragma unroll
-        for (int j = 0; j < LA_NB; ++j) gA[j * LA_NB + r] = S.Y[j * LA_YLD + r];
-      }
-      GAMC_WCLK(w1, 55);
     } else {
       const int tt = la_trail_index(warp, lane);
       GAMC_WCLK_BEGIN(w2);
@@ -203,15 +214,18 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaSc
         // ---- trailing update A22 -= P P' (lower triangle) with panel it-1 on the FP64 tensor cores: one 32 x 32
         //      output block (4 x 4 DMMA m8n8k4 tiles, 8 k-steps) per warp task, minus block (0,0) = diagonal block
         //      `it` (the team's).  Fragments come straight from the k-major panel (conflict-free for pld = 4 mod 16).
+        //      Block (1,1), the next diagonal block, is also staged in shared memory for the team's next pass.
         const int nb32 = (mprev + LA_NB - 1) / LA_NB;
         const int ntask = nb32 * (nb32 + 1) / 2;
-        const int tw = tt >> 5;                                  // dense trailing-warp index 0..10
+        const int tw = tt >> 5;                                  // dense trailing-warp index 0..11
         const int fr = lane >> 2, fk = lane & 3;
+        double* Dst = S.Dn + ((it + 1) & 1) * LA_NB * LA_DLD;
         for (int q = 1 + tw; q < ntask; q += LA_NTRAIL / 32) {
           // column-major triangular index -> (bi >= bj)
           int bj = 0, rem = q;
           while (rem >= nb32 - bj) { rem -= nb32 - bj; ++bj; }
           const int bi = bj + rem;
+          const bool stage = (bi == 1 && bj == 1);
           double acc[4][4][2];
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi)
@@ -245,94 +259,48 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaSc
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int i = i0 + 8 * mi, j = j0 + 8 * ni + e;
-                if (i < p && j < p && i >= j) A(i, j) = old[ni][e] - acc[mi][ni][e];
+                const double v = old[ni][e] - acc[mi][ni][e];
+                if (i < p && j < p && i >= j) A(i, j) = v;
+                if (stage) Dst[(fr + 8 * mi) * LA_DLD + 2 * fk + 8 * ni + e] = (i < p && j < p && i >= j) ? v : 0.0;
               }
           }
         }
-        la_bar_sync(2, LA_TEAM + LA_NTRAIL);         // every reader of the solved panel it-1 is done (and its updates are visible)
-        if (warp == 2) GAMC_WCLK(w2, 56);
+        la_bar_sync(2, LA_THREADS);                  // every reader of the solved panel it-1 is done
+        if (warp == 1) GAMC_WCLK(w2, 56);
       }
-      // ---- raw panel `it` -> shared, one row per thread (32 independent coalesced loads), zero padding rows
-      if (mnext > 0) {
-        const int mt4 = ((mnext + 3) >> 2) * 4;
-        for (int t = tt; t < mt4; t += LA_NTRAIL) {
-          double x[LA_NB];
-          if (t < mnext) {
+      // ---- panel solve X = A_panel Lkk^-T, one row per thread held in registers, column c as soon as the inverter
+      //      has published row c of the inverse:  X(t, c) = sum_{k <= c} A_panel(t, k) inv(c, k)
+      for (int t = tt; t < mnext; t += LA_NTRAIL) {
+        double x[LA_NB];
 #pragma unroll
-            for (int c = 0; c < LA_NB; ++c) x[c] = A(kn + LA_NB + t, kn + c);
-          } else {
+        for (int c = 0; c < LA_NB; ++c) x[c] = A(kn + LA_NB + t, kn + c);
 #pragma unroll
-            for (int c = 0; c < LA_NB; ++c) x[c] = 0.0;
+        for (int c = 0; c < LA_NB; ++c) {
+          la_spin_until(vflag + 2, it * LA_NB + c + 1);
+          const double* yr = S.Y + c * LA_YLD;
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int k = 0; k <= c; k += 2) {
+            const double2 y2 = *reinterpret_cast<const double2*>(yr + k);
+            s0 = fma(x[k], y2.x, s0);
+            if (k + 1 <= c) s1 = fma(x[k + 1], y2.y, s1);
           }
-#pragma unroll
-          for (int c = 0; c < LA_NB; ++c) S.P[c * S.pld + t] = x[c];
+          const double xc = s0 + s1;
+          S.P[c * S.pld + t] = xc;
+          A(kn + LA_NB + t, kn + c) = xc;
         }
       }
-      if (warp == 2) GAMC_WCLK(w2, 57);
+      if (warp == 1) GAMC_WCLK(w2, 57);
     }
     __syncthreads();
     if (REV) GAMC_PHASE(48);
     if (S.flag[0]) break;
-    if (mnext > 0) {
-      // ---- panel solve X = P Lkk^-T as a GEMM with the inverted block: 4 x 8 register tiles, in place after a barrier
-      //      (one pass for p <= 512 + 32, the supported range: a second pass would read rows the first one overwrote)
-      const int mt = (mnext + 3) >> 2;
-      const int q = tid;
-      const int tr = q % mt, tc = q / mt;            // row group, column group (0..3)
-      const bool act = q < 4 * mt;
-      double acc[4][8];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
-      if (act) {
-        const double* pa = S.P + 4 * tr;
-        const double* py = S.Y + 8 * tc;
-        const int kend = 8 * tc + 8;                 // inv(c, k) = 0 for k > c
-#pragma unroll 4
-        for (int k = 0; k < kend; ++k) {
-          const double2 a01 = *reinterpret_cast<const double2*>(pa + k * S.pld);
-          const double2 a23 = *reinterpret_cast<const double2*>(pa + k * S.pld + 2);
-          const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-          double yv[8];
-#pragma unroll
-          for (int b = 0; b < 8; b += 2) {
-            const double2 t2 = *reinterpret_cast<const double2*>(py + k * LA_YLD + b);
-            yv[b] = t2.x; yv[b + 1] = t2.y;
-          }
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 8; ++b) acc[a][b] = fma(av[a], yv[b], acc[a][b]);
-        }
-      }
-      __syncthreads();
-      if (act) {
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const int c = 8 * tc + b;
-          *reinterpret_cast<double2*>(&S.P[c * S.pld + 4 * tr]) = make_double2(acc[0][b], acc[1][b]);
-          *reinterpret_cast<double2*>(&S.P[c * S.pld + 4 * tr + 2]) = make_double2(acc[2][b], acc[3][b]);
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const int t = 4 * tr + a;
-            if (t < mnext) A(kn + LA_NB + t, kn + c) = acc[a][b];
-          }
-        }
-      }
-      __syncthreads();
-      if (REV) GAMC_PHASE(49);
-    }
   }
-  // broadcast result (each lane of warp 0 holds the logs of "its" diagonal entries)
-  __syncthreads();
-  if (warp == 0) {
-    sumlog = warp_sum(sumlog);
-    if (lane == 0) S.D[0] = sumlog;
-  }
-  __syncthreads();
+  // sum_i log Lm_ii = -sum_i log rdiag_i, in parallel at the end (keeps the logarithm off the column chain)
   const int bad = S.flag[0];
-  const double out = S.D[0];
+  double sl = 0.0;
+  if (!bad) for (int i = tid; i < p; i += LA_THREADS) sl -= log(rdiag[i]);
+  const double out = block_sum(sl, S.D);
   __syncthreads();
   if (fail_pivot) *fail_pivot = bad;
   return bad ? nan("") : out;

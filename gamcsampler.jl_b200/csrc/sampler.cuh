@@ -20,6 +20,7 @@ struct Bufs {
   double* rdiagU;                        // [2][p] reciprocal diagonal (M-space order)
   double* invU; size_t invUstride;       // [2][la_invd_doubles(p)] inverted 32 x 32 diagonal blocks of the factor (block solves)
   double* fterm;                         // [2][p] G^-1 grad ("firstterm")
+  double* land;                          // [3p + 8] k_land output: per-column non-finite flags, q1 and q2 partials; [3p] log-target, [3p+1] gradient flag
   double* theta; double* theta_prop; double* mu; double* lastmean; double* secondlastmean;
   double* C;                             // p x p  sstate.oldinvtensor while in AM mode (AM covariance)
   double* Lc;                            // p x p  lower Cholesky factor of eps*C (am_mode 0) / of C (am_mode 1)
@@ -75,32 +76,82 @@ __device__ inline double add_prior(double* E, int goff, const double* theta, int
   return E[0] + lp;
 }
 
-// all-finite check of the gradient of a landed evaluation (the metric is checked while factor_slot copies it)
-__device__ inline int grad_finite(const double* E, int p, double* red) {
-  double bad = 0.0;
-  for (int i = threadIdx.x; i < p; i += blockDim.x) if (!isfinite(E[1 + i])) bad = 1.0;
-  return block_sum(bad, red) == 0.0;
+// ---------------------------------------------------------------------------------------------------
+// k_land: move a landed (and, multi-GPU, all-reduced) level-2 evaluation R = [ll, g, G] into an evaluation slot, on the
+// whole GPU (one CTA per column) instead of inside the single-CTA step kernels:
+//   Gs[slot] <- G + I/lambda, U[slot] <- its upper triangle (the input of the reverse Cholesky), gs[slot] <- g - theta/lambda,
+//   land[3p] <- ll + logprior(theta)                         (prior terms of simulations.jl:30,32,36, added once, after the reduction)
+// and the O(p^2) pieces of the SMMALA acceptance ratio that do not depend on the factorisation (mode 2 only):
+//   land[p + j]  = d_j sum_i d_i G(theta)_ij,   d = theta* - mu                (iterate/GAMC.jl:47-54)
+//   land[2p + j] = a_j sum_i a_i G(theta*)_ij,  a = theta - theta*             (:60-67, see k_smmala_post)
+// land[j] = 1 if column j of G has a non-finite entry.  Column partials are summed in a fixed order by the consumer.
+// mode: 0 = initial point (slot 0), 1 = re-evaluation of the current point (slot cur), 2 = proposal (slot 1 - cur).
+// ---------------------------------------------------------------------------------------------------
+constexpr int LAND_THREADS = 128;
+__global__ void __launch_bounds__(LAND_THREADS) k_land(Bufs B, TuneCfg T, int mode) {
+  __shared__ double red[40];
+  DevState* st = B.st;
+  if (st->error_flag) return;
+  const int p = T.p, j = blockIdx.x;
+  const int cur = st->cur;
+  const int slot = mode == 0 ? 0 : (mode == 1 ? cur : 1 - cur);
+  const double* G = B.R + B.goff + (size_t)j * p;
+  const double* Gc = B.Gs + (size_t)cur * B.Gstride + (size_t)j * p;
+  double* Gd = B.Gs + (size_t)slot * B.Gstride + (size_t)j * p;
+  double* U = B.U + (size_t)slot * B.Ustride + (size_t)j * p;
+  const double ilam = 1.0 / T.lambda;
+  double nf = 0.0, q1 = 0.0, q2 = 0.0;
+  for (int i = threadIdx.x; i < p; i += LAND_THREADS) {
+    double v = G[i];
+    if (i == j) v += ilam;
+    Gd[i] = v;
+    if (i <= j) U[i] = v;
+    if (!isfinite(v)) nf = 1.0;
+    if (mode == 2) {
+      const double tp = B.theta_prop[i];
+      q1 += (tp - B.mu[i]) * Gc[i];
+      q2 += (B.theta[i] - tp) * v;
+    }
+  }
+  nf = block_sum(nf, red);
+  if (mode == 2) {
+    q1 = block_sum(q1, red);
+    q2 = block_sum(q2, red);
+    if (threadIdx.x == 0) {
+      const double tp = B.theta_prop[j];
+      B.land[p + j] = q1 * (tp - B.mu[j]);
+      B.land[2 * p + j] = q2 * (B.theta[j] - tp);
+    }
+  }
+  if (threadIdx.x == 0) B.land[j] = nf != 0.0 ? 1.0 : 0.0;
+  if (j == 0) {
+    const double* th = mode == 2 ? B.theta_prop : B.theta;
+    double gnf = 0.0;
+    for (int i = threadIdx.x; i < p; i += LAND_THREADS) {
+      const double g = B.R[1 + i] - th[i] * ilam;
+      B.gs[(size_t)slot * p + i] = g;
+      if (!isfinite(g)) gnf = 1.0;
+    }
+    gnf = block_sum(gnf, red);
+    const double lp = log_prior(th, p, T.lambda, red);
+    if (threadIdx.x == 0) { B.land[3 * p] = B.R[0] + lp; B.land[3 * p + 1] = gnf; }
+  }
 }
 
-// Move the landed evaluation (prior already added) into a slot and factor its metric:
-// Gs[slot] <- G, gs[slot] <- g, U[slot] <- reverse Cholesky of G, fterm[slot] <- G^-1 g.
-// Returns 0 on success, the failed (M-space, 1-based) pivot, or -1 if G has a non-finite entry.
+// all threads: 1 if the landed evaluation (k_land) is finite everywhere
+__device__ inline int landed_finite(const Bufs& B, int p, double* red) {
+  double bad = 0.0;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) bad += B.land[i];
+  bad = block_sum(bad, red);
+  return bad == 0.0 && B.land[3 * p + 1] == 0.0 && isfinite(B.land[3 * p]);
+}
+
+// Factor the metric k_land left in a slot: U[slot] <- reverse Cholesky of G (in place), fterm[slot] <- G^-1 g.
+// Returns 0 on success, the failed (M-space, 1-based) pivot otherwise.
 __device__ inline int factor_slot(const Bufs& B, int slot, int p, StepSmem& S) {
-  const double* G = B.R + B.goff;
-  const double* g = B.R + 1;
   double* U = B.U + (size_t)slot * B.Ustride;
-  double* Gd = B.Gs + (size_t)slot * B.Gstride;
+  const double* g = B.gs + (size_t)slot * p;
   double* invd = B.invU + (size_t)slot * B.invUstride;
-  // one pass over G: copy, finite check; its (natural) upper triangle = M-space lower triangle goes to the factor buffer
-  double nonfinite = 0.0;
-  flat_stream<16>(G, p * p, [&](int e, double v) {
-    const int j = e / p, i = e - j * p;
-    Gd[e] = v;
-    if (i <= j) U[e] = v;
-    if (!isfinite(v)) nonfinite = 1.0;
-  });
-  for (int i = threadIdx.x; i < p; i += blockDim.x) B.gs[(size_t)slot * p + i] = g[i];
-  if (block_sum(nonfinite, S.red) != 0.0) return -1;
   GAMC_PHASE(16);
   MatView<true> V{U, p, p};
   int bad = 0;
@@ -175,11 +226,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_sampler_init(Bufs B, TuneCfg 
   StepSmem S = step_smem_carve(smem_raw, T.p);
   DevState* st = B.st;
   const int p = T.p;
-  const double lt = add_prior(B.R, B.goff, B.theta, p, T.lambda, S.red);
-  const int fin = grad_finite(B.R, p, S.red) && isfinite(lt);
-  if (!fin) { raise_error(st, 2 /*GAMC_NONFINITE_INIT*/, 0); return; }
+  const double lt = B.land[3 * p];                  // k_land(mode 0) ran on the evaluation at theta0
+  if (!landed_finite(B, p, S.red)) { raise_error(st, 2 /*GAMC_NONFINITE_INIT*/, 0); return; }
   const int bad = factor_slot(B, 0, p, S);
-  if (bad < 0) { raise_error(st, 2 /*GAMC_NONFINITE_INIT*/, 0); return; }
   if (bad) { raise_error(st, 3 /*GAMC_NOT_POSDEF*/, p + 1 - bad); return; }
   for (int i = threadIdx.x; i < p; i += blockDim.x) B.lastmean[i] = B.theta[i];   // GAMC.jl:218
   if (threadIdx.x == 0) { st->logtarget = lt; st->cur = 0; }
@@ -203,10 +252,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_smmala_pre(Bufs B, TuneCfg T,
   }
   GAMC_PHASE_BEGIN();
   if (refactor) {                                     // :19-31 (previous step was AM: grad/metric stale)
-    const double lt = add_prior(B.R, B.goff, B.theta, p, T.lambda, S.red);
-    if (threadIdx.x == 0) st->logtarget = lt;
+    if (threadIdx.x == 0) st->logtarget = B.land[3 * p];   // k_land(mode 1) ran on the re-evaluation at theta
     const int bad = factor_slot(B, cur, p, S);
-    if (bad) { raise_error(st, 3, bad < 0 ? 0 : p + 1 - bad); return; }
+    if (bad) { raise_error(st, 3, p + 1 - bad); return; }
   }
   __syncthreads();
   GAMC_PHASE(refactor ? 32 : 33);
@@ -235,33 +283,33 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_smmala_post(Bufs B, TuneCfg T
   const int p = T.p;
   if (st->error_flag) return;
   const int cur = st->cur, prop = 1 - cur;
-  const double* Gc = B.Gs + (size_t)cur * B.Gstride;
-  const double* Gp = B.Gs + (size_t)prop * B.Gstride;
   const double eps = st->step;
   GAMC_PHASE_BEGIN();
-  const double lt_p = add_prior(B.R, B.goff, B.theta_prop, p, T.lambda, S.red);
-  GAMC_PHASE(0);
-  int ok = grad_finite(B.R, p, S.red) && isfinite(lt_p);
+  const double lt_p = B.land[3 * p];                 // k_land(mode 2) ran on the evaluation at theta*
+  int ok = landed_finite(B, p, S.red);               // non-finite target / gradient / metric at the proposal: reject
   GAMC_PHASE(1);
   double ratio = -INFINITY;
   int bad = 0;
   if (ok) bad = factor_slot(B, prop, p, S);          // newinvtensor / newfirstterm (:43,56) via one factorisation
   if (bad > 0) { raise_error(st, 3, p + 1 - bad); return; }
-  if (bad < 0) ok = 0;                               // non-finite metric at the proposal: reject
   if (ok) {
     GAMC_PHASE(2);
-    // d = theta* - mu ; q1 = d' G d / eps                                              (:47-54)
-    for (int i = threadIdx.x; i < p; i += blockDim.x) S.v0[i] = B.theta_prop[i] - B.mu[i];
-    __syncthreads();
-    const double q1 = quad_form(Gc, p, S.v0, S.red);
-    GAMC_PHASE(3);
-    // mu* = theta* + eps/2 f* ; d2 = theta - mu* ; q2 = d2' G* d2 / eps                 (:58-67)
+    // q1 = d' G d, d = theta* - mu (:47-54): column partials from k_land, summed in a fixed order
+    double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0;
     for (int i = threadIdx.x; i < p; i += blockDim.x) {
-      const double ms = B.theta_prop[i] + 0.5 * eps * B.fterm[(size_t)prop * p + i];
-      S.v2[i] = B.theta[i] - ms;
+      t1 += B.land[p + i];
+      t2 += B.land[2 * p + i];
+      // mu* = theta* + eps/2 f*, d2 = theta - mu* = a - eps/2 f* with a = theta - theta*; since G* f* = g*:
+      //   q2 = d2' G* d2 = a' G* a - eps a' g* + eps^2/4 f*' g*                         (:58-67)
+      const double gp = B.gs[(size_t)prop * p + i];
+      t3 = fma(B.theta[i] - B.theta_prop[i], gp, t3);
+      t4 = fma(B.fterm[(size_t)prop * p + i], gp, t4);
     }
-    __syncthreads();
-    const double q2 = quad_form(Gp, p, S.v2, S.red);
+    const double q1 = block_sum(t1, S.red);
+    const double aGa = block_sum(t2, S.red);
+    const double ag = block_sum(t3, S.red);
+    const double fg = block_sum(t4, S.red);
+    const double q2 = aGa - eps * ag + 0.25 * eps * eps * fg;
     GAMC_PHASE(4);
     const double plog = p * log(eps);
     const double ld_old = plog - 2.0 * st->sumlog[cur];   // logdet(eps * G^-1)

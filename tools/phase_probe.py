@@ -14,12 +14,12 @@ import gamc_b200 as g  # noqa: E402
 from gamc_b200 import _lib  # noqa: E402
 
 NAMES = {
-    0: "post: add_prior", 1: "post: grad finite", 2: "post: (after factor_slot)", 3: "post: symv+dot #1", 4: "post: symv+dot #2",
-    5: "post: accept+tail", 16: "factor: copy G,g + finite", 17: "factor: chol epilogue", 18: "factor: trsv_lower", 19: "factor: trsv_lower_t",
+    1: "post: landed finite", 2: "post: (after factor_slot)", 4: "post: ratio sums",
+    5: "post: accept+tail", 16: "factor: entry", 17: "factor: chol epilogue", 18: "factor: trsv_lower", 19: "factor: trsv_lower_t",
     32: "pre(refactor): prior+factor tail", 33: "pre(no refactor): entry", 34: "pre: trsv_t + proposal",
-    48: "chol: pass (chain | trailing + panel load)", 49: "chol: panel GEMM",
-    52: "  warp0: team update of the diagonal block", 53: "  warp0: column chain", 54: "  warp0: publish", 55: "  warp1: inverter (whole pass)",
-    56: "  warp2: trailing tiles + barrier", 57: "  warp2: raw panel load",
+    48: "chol: pass",
+    52: "  warp0: team update of the diagonal block", 53: "  warp0: column chain", 54: "  warp0: publish", 55: "  warp4: inverter (whole pass)",
+    56: "  warp1: trailing tasks + barrier", 57: "  warp1: panel solve (pipelined)",
 }
 
 
