@@ -288,9 +288,11 @@ gamc_status launch_reduce(gamc_ctx* h, int level) {
 }
 
 // Likelihood partial sums at a device-resident theta into the landing buffer R, then (multi-GPU) all-reduce.
-gamc_status eval_device(gamc_ctx* h, const double* d_theta, int level, bool allreduce) {
+// skip_reduce (level 0, single GPU only): leave the per-CTA partials for k_am_post to sum.
+gamc_status eval_device(gamc_ctx* h, const double* d_theta, int level, bool allreduce, bool skip_reduce = false) {
   gamc_status s = launch_datapass(h, d_theta, level >= 1);
   if (s != GAMC_OK) return s;
+  if (skip_reduce && level == 0 && !h->comm) return GAMC_OK;
   if (level >= 2) { s = launch_metric(h); if (s != GAMC_OK) return s; }
   s = launch_reduce(h, level);
   if (s != GAMC_OK) return s;
@@ -890,14 +892,15 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
         CUDA_TRY(h, cudaEventRecord(h->ev_side, h->side));
         h->dp_grid_now = std::max(1, h->dp_grid - 2);                                    // leave two SMs to the speculative CTAs
       }
-      s = eval_device(h, B.theta_prop, 0, true);                                         // :148
+      const int nparts_post = h->comm ? 0 : (h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid);
+      s = eval_device(h, B.theta_prop, 0, true, true);                                   // :148
       h->dp_grid_now = 0;
       if (s != GAMC_OK) return s;
       if (next_am) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_side, 0));
       {
         const size_t smem = step_smem_bytes(h->p);
         ProfScope ps(h, GAMC_K_LINALG);
-        k_am_post<<<1, LA_THREADS, smem, h->stream>>>(B, T, ti, next_am ? 1 : 0);
+        k_am_post<<<1, LA_THREADS, smem, h->stream>>>(B, T, ti, next_am ? 1 : 0, h->part_ll, nparts_post);
         CUDA_TRY(h, cudaGetLastError());
       }
       h->spec_ready = next_am;

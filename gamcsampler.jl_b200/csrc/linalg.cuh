@@ -173,12 +173,7 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaSc
           }
         }
         GAMC_WCLK(w0, 53);
-        // publish the factor to global memory
-#pragma unroll
-        for (int c = 0; c < LA_NB; ++c) if (c <= r && r < nbn) A(kn + r, kn + c) = a[c];
-        if (r < nbn) rdiag[kn + r] = myrd;
         if (bad && lane == 0) S.flag[0] = bad;
-        GAMC_WCLK(w0, 54);
       } else if (warp == 4) {
         // ---- inverter: column `lane` of Lkk^-1 by forward substitution on e_lane, one column behind the chain;
         //      after step i every lane holds inv(i, lane): row i of the inverse is published for the panel solve
@@ -199,13 +194,23 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaSc
             for (int k = i + 1; k < LA_NB; ++k) if (k < nbn) y[k] = fma(-S.LT[i * LA_DLD + k], yi, y[k]);
           }
         }
-        if (invd) {
-          double* gB = invd + (size_t)it * LA_INVD_STRIDE + LA_NB * LA_NB;   // layout B: [i * 32 + j] = inv(i, j)
-          double* gA = invd + (size_t)it * LA_INVD_STRIDE;                   // layout A: [j * 32 + i] = inv(i, j)
-#pragma unroll
-          for (int i = 0; i < LA_NB; ++i) { gB[i * LA_NB + r] = y[i]; gA[r * LA_NB + i] = y[i]; }
-        }
         GAMC_WCLK(w0, 55);
+      } else if (warp == 8) {
+        // ---- publisher of the factor: column j of the diagonal block to global memory as soon as the chain releases it
+        for (int j = 0; j < nbn; ++j) {
+          la_spin_until(vflag + 1, it * LA_NB + j + 1);
+          if (lane >= j && lane < nbn) A(kn + lane, kn + j) = S.LT[j * LA_DLD + lane];
+        }
+        if (lane < nbn) rdiag[kn + lane] = S.rd[lane];
+      } else if (invd) {
+        // ---- publisher of the inverse (warp 12): row i in layout B as the inverter releases it, layout A at the end
+        double* gB = invd + (size_t)it * LA_INVD_STRIDE + LA_NB * LA_NB;   // layout B: [i * 32 + j] = inv(i, j)
+        double* gA = invd + (size_t)it * LA_INVD_STRIDE;                   // layout A: [j * 32 + i] = inv(i, j)
+        for (int i = 0; i < nbn; ++i) {
+          la_spin_until(vflag + 2, it * LA_NB + i + 1);
+          gB[i * LA_NB + lane] = S.Y[i * LA_YLD + lane];
+        }
+        for (int j = 0; j < nbn; ++j) gA[j * LA_NB + lane] = (lane < nbn) ? S.Y[lane * LA_YLD + j] : 0.0;
       }
     } else {
       const int tt = la_trail_index(warp, lane);
@@ -268,26 +273,46 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaSc
         la_bar_sync(2, LA_THREADS);                  // every reader of the solved panel it-1 is done
         if (warp == 1) GAMC_WCLK(w2, 56);
       }
-      // ---- panel solve X = A_panel Lkk^-T, one row per thread held in registers, column c as soon as the inverter
-      //      has published row c of the inverse:  X(t, c) = sum_{k <= c} A_panel(t, k) inv(c, k)
-      for (int t = tt; t < mnext; t += LA_NTRAIL) {
-        double x[LA_NB];
+      // ---- panel solve X = A_panel Lkk^-T on the tensor cores: X(t, c) = sum_{k <= c} A_panel(t, k) inv(c, k).
+      //      One 8-row block per warp task; A fragments straight from global memory (issued before waiting for the
+      //      inverter), B fragments from the shared inverse (conflict-free for LA_YLD = 36); k-blocks above the
+      //      diagonal of the inverse are skipped.
+      if (mnext > 0) {
+        const int fr = lane >> 2, fk = lane & 3;
+        const int nrb = (mnext + 7) >> 3;
+        constexpr int NW = LA_NTRAIL / 32;
+        for (int rb0 = tt >> 5; rb0 < nrb; rb0 += 3 * NW) {       // three row blocks per warp in flight: one L2 round trip
+          double af[3][LA_NB / 4];
 #pragma unroll
-        for (int c = 0; c < LA_NB; ++c) x[c] = A(kn + LA_NB + t, kn + c);
+          for (int s3 = 0; s3 < 3; ++s3) {
+            const int t = 8 * (rb0 + s3 * NW) + fr;
 #pragma unroll
-        for (int c = 0; c < LA_NB; ++c) {
-          la_spin_until(vflag + 2, it * LA_NB + c + 1);
-          const double* yr = S.Y + c * LA_YLD;
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int k = 0; k <= c; k += 2) {
-            const double2 y2 = *reinterpret_cast<const double2*>(yr + k);
-            s0 = fma(x[k], y2.x, s0);
-            if (k + 1 <= c) s1 = fma(x[k + 1], y2.y, s1);
+            for (int k4 = 0; k4 < LA_NB / 4; ++k4) af[s3][k4] = (t < mnext) ? A(kn + LA_NB + t, kn + 4 * k4 + fk) : 0.0;
           }
-          const double xc = s0 + s1;
-          S.P[c * S.pld + t] = xc;
-          A(kn + LA_NB + t, kn + c) = xc;
+          la_spin_until(vflag + 2, it * LA_NB + nbn);
+#pragma unroll
+          for (int s3 = 0; s3 < 3; ++s3) {
+            const int rb = rb0 + s3 * NW;
+            if (rb < nrb) {
+              const int t = 8 * rb + fr;
+              double acc[4][2];
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni) { acc[ni][0] = 0.0; acc[ni][1] = 0.0; }
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int k4 = 0; k4 <= 2 * ni + 1; ++k4)
+                  dmma_8x8x4(acc[ni][0], acc[ni][1], af[s3][k4], S.Y[(8 * ni + fr) * LA_YLD + 4 * k4 + fk]);
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int c = 8 * ni + 2 * fk + e;
+                  S.P[c * S.pld + t] = acc[ni][e];
+                  if (t < mnext) A(kn + LA_NB + t, kn + c) = acc[ni][e];
+                }
+            }
+          }
         }
       }
       if (warp == 1) GAMC_WCLK(w2, 57);

@@ -628,13 +628,26 @@ __global__ void __launch_bounds__(256) k_llt(const double* __restrict__ L, int p
 // next_spec = 1 (am_mode 2): the next step is an AM step whose factor update was computed speculatively for both outcomes
 // while the data pass ran; after the decision this kernel selects the factor buffer of the outcome that happened and
 // performs the head of the next `iterate!` (counters, proposal) so that the next data pass can start immediately.
-__global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, long long tape_idx, int next_spec) {
+// part_ll / nparts: single-GPU jobs skip k_reduce for the log-likelihood-only evaluation and sum the per-CTA partials of
+// the data pass here, in k_reduce's order (bitwise the same value); nparts = 0 reads the (all-)reduced R[0].
+__global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, long long tape_idx, int next_spec,
+                                                           const double* __restrict__ part_ll, int nparts) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StepSmem S = step_smem_carve(smem_raw, T.p);
   DevState* st = B.st;
   const int p = T.p;
   if (st->error_flag) return;
-  const double lt_p = B.R[0] + log_prior(B.theta_prop, p, T.lambda, S.red);
+  if (nparts > 0) {
+    if (threadIdx.x < 32) {
+      double s = 0.0;
+      for (int k = threadIdx.x; k < nparts; k += 32) s += part_ll[k];
+      s = warp_sum(s);
+      if (threadIdx.x == 0) S.red[39] = s;
+    }
+    __syncthreads();
+  }
+  const double ll_p = nparts > 0 ? S.red[39] : B.R[0];
+  const double lt_p = ll_p + log_prior(B.theta_prop, p, T.lambda, S.red);
   double ratio = isfinite(lt_p) ? (lt_p - st->logtarget) : -INFINITY;                   // :150
   const double u = B.tape_uacc[tape_idx];
   const int accept = (ratio > 0.0) || (ratio > log(u));                                 // :158
