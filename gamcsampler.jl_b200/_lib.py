@@ -98,6 +98,7 @@ SIGNATURES = {
     "gamc_eval_partials": (C.c_int, [_H, _DP, _DP, _DP, _DP]),
     "gamc_comm_unique_id": (C.c_int, [_U8P]),
     "gamc_comm_init": (C.c_int, [_H, _U8P, C.c_int32, C.c_int32]),
+    "gamc_comm_peer_path": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "gamc_sampler_init": (C.c_int, [_H, C.POINTER(Config), _DP]),
     "gamc_tape_set": (C.c_int, [_H, C.c_int64, _DP, _DP, _DP, _DP]),
     "gamc_tape_generate": (C.c_int, [_H, C.c_int64, C.c_uint64]),

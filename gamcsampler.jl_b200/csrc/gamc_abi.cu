@@ -32,6 +32,7 @@ typedef void* ncclComm_t;
 typedef int (*fn_ncclGetUniqueId)(NcclUniqueId*);
 typedef int (*fn_ncclCommInitRank)(ncclComm_t*, int, NcclUniqueId, int);
 typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef int (*fn_ncclAllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
 typedef int (*fn_ncclCommDestroy)(ncclComm_t);
 typedef const char* (*fn_ncclGetErrorString)(int);
 struct NcclApi {
@@ -39,6 +40,7 @@ struct NcclApi {
   fn_ncclGetUniqueId GetUniqueId = nullptr;
   fn_ncclCommInitRank CommInitRank = nullptr;
   fn_ncclAllReduce AllReduce = nullptr;
+  fn_ncclAllGather AllGather = nullptr;
   fn_ncclCommDestroy CommDestroy = nullptr;
   fn_ncclGetErrorString GetErrorString = nullptr;
   bool load(std::string& err) {
@@ -49,6 +51,7 @@ struct NcclApi {
     GetUniqueId = (fn_ncclGetUniqueId)dlsym(lib, "ncclGetUniqueId");
     CommInitRank = (fn_ncclCommInitRank)dlsym(lib, "ncclCommInitRank");
     AllReduce = (fn_ncclAllReduce)dlsym(lib, "ncclAllReduce");
+    AllGather = (fn_ncclAllGather)dlsym(lib, "ncclAllGather");
     CommDestroy = (fn_ncclCommDestroy)dlsym(lib, "ncclCommDestroy");
     GetErrorString = (fn_ncclGetErrorString)dlsym(lib, "ncclGetErrorString");
     if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl lacks required symbols"; return false; }
@@ -108,6 +111,8 @@ struct gamc_ctx {
   double* d_bchain = nullptr; unsigned char* d_baccept = nullptr; double* d_btape = nullptr; long long btape_doubles = 0;
   // comm
   ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
+  // peer mailboxes (NVLink peer memory, CUDA IPC): scalar all-reduce of the AM step without NCCL or k_reduce
+  PeerMail* mbox = nullptr; PeerMail** d_peers = nullptr; void* peer_ptr[32] = {nullptr}; bool p2p_ready = false; unsigned long long p2p_seq = 0;
   // profiling
   bool prof = false; std::vector<cudaEvent_t> ev0, ev1; std::vector<int> ev_family; int ev_used = 0;
   long long launches = 0;
@@ -292,7 +297,7 @@ gamc_status launch_reduce(gamc_ctx* h, int level) {
 gamc_status eval_device(gamc_ctx* h, const double* d_theta, int level, bool allreduce, bool skip_reduce = false) {
   gamc_status s = launch_datapass(h, d_theta, level >= 1);
   if (s != GAMC_OK) return s;
-  if (skip_reduce && level == 0 && !h->comm) return GAMC_OK;
+  if (skip_reduce && level == 0 && (!h->comm || h->p2p_ready)) return GAMC_OK;
   if (level >= 2) { s = launch_metric(h); if (s != GAMC_OK) return s; }
   s = launch_reduce(h, level);
   if (s != GAMC_OK) return s;
@@ -397,6 +402,10 @@ gamc_status check_device_error(gamc_ctx* h) {
     h->err = "matrix is not positive definite; Cholesky factorization failed at pivot " + std::to_string(st.error_pivot) +
              " (iteration " + std::to_string(st.error_iter) + ")";
     return GAMC_NOT_POSDEF;
+  }
+  if (st.error_flag == GAMC_NCCL_ERROR) {
+    h->err = "peer all-reduce timed out waiting for rank " + std::to_string(st.error_pivot) + " (iteration " + std::to_string(st.error_iter) + ")";
+    return GAMC_NCCL_ERROR;
   }
   return GAMC_OK;
 }
@@ -528,6 +537,8 @@ gamc_status gamc_destroy(gamc_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (int r = 0; r < h->nranks && r < 32; ++r) if (h->peer_ptr[r] && r != h->rank) cudaIpcCloseMemHandle(h->peer_ptr[r]);
+  cudaFree(h->mbox); cudaFree(h->d_peers);
   free_sampler(h);
   free_target(h);
   free_batched(h);
@@ -668,6 +679,55 @@ gamc_status gamc_comm_unique_id(uint8_t id_out[128]) {
   return GAMC_OK;
 }
 
+// Map every rank's mailbox array into this process (CUDA IPC over NVLink peer memory).  The handles travel through one
+// ncclAllGather; the gather also orders every rank's zero-fill before any peer write.  GAMC_NO_P2P=1 disables the path.
+static void setup_peer_mailboxes(gamc_ctx* h) {
+  h->p2p_ready = false;
+  if (getenv("GAMC_NO_P2P") || h->nranks < 2 || h->nranks > 32 || !g_nccl.AllGather) return;
+  const int n = h->nranks;
+  unsigned char* d_handles = nullptr;
+  std::vector<cudaIpcMemHandle_t> handles(n);
+  bool ok = cudaMalloc(&h->mbox, sizeof(PeerMail) * 2 * n) == cudaSuccess &&
+            cudaMemsetAsync(h->mbox, 0, sizeof(PeerMail) * 2 * n, h->stream) == cudaSuccess &&
+            cudaMalloc(&d_handles, sizeof(cudaIpcMemHandle_t) * n) == cudaSuccess &&
+            cudaIpcGetMemHandle(&handles[h->rank], h->mbox) == cudaSuccess &&
+            cudaMemcpyAsync(d_handles + sizeof(cudaIpcMemHandle_t) * h->rank, &handles[h->rank], sizeof(cudaIpcMemHandle_t),
+                            cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
+  // every rank must take part in the gather, whatever happened above (a rank that failed contributes zeros)
+  if (d_handles) {
+    const int r = g_nccl.AllGather(d_handles + sizeof(cudaIpcMemHandle_t) * h->rank, d_handles, sizeof(cudaIpcMemHandle_t), 0 /*ncclChar*/,
+                                   h->comm, h->stream);
+    ok = ok && r == 0 && cudaMemcpyAsync(handles.data(), d_handles, sizeof(cudaIpcMemHandle_t) * n, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
+  } else {
+    ok = false;
+  }
+  ok = cudaStreamSynchronize(h->stream) == cudaSuccess && ok;
+  cudaFree(d_handles);
+  std::vector<PeerMail*> peers(n, nullptr);
+  for (int r = 0; ok && r < n; ++r) {
+    if (r == h->rank) { peers[r] = h->mbox; h->peer_ptr[r] = h->mbox; continue; }
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+    h->peer_ptr[r] = ptr; peers[r] = (PeerMail*)ptr;
+  }
+  ok = ok && cudaMalloc(&h->d_peers, sizeof(PeerMail*) * n) == cudaSuccess &&
+       cudaMemcpy(h->d_peers, peers.data(), sizeof(PeerMail*) * n, cudaMemcpyHostToDevice) == cudaSuccess;
+  cudaGetLastError();
+  // all ranks must agree: a one-element all-reduce of the local verdict (min over ranks)
+  double* d_ok = nullptr;
+  if (cudaMalloc(&d_ok, sizeof(double)) == cudaSuccess) {
+    const double v = ok ? 1.0 : 0.0;
+    double all = 0.0;
+    cudaMemcpyAsync(d_ok, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    const int r = g_nccl.AllReduce(d_ok, d_ok, 1, NCCL_DOUBLE, 3 /*ncclMin*/, h->comm, h->stream);
+    cudaMemcpyAsync(&all, d_ok, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_ok);
+    h->p2p_ready = (r == 0 && all == 1.0);
+  }
+  h->p2p_seq = 0;
+}
+
 gamc_status gamc_comm_init(gamc_handle h, const uint8_t id[128], int32_t nranks, int32_t rank) {
   if (!h) return GAMC_INVALID_ARG;
   REQUIRE(h, id && nranks >= 1 && rank >= 0 && rank < nranks, GAMC_INVALID_ARG, "gamc_comm_init: bad argument");
@@ -678,6 +738,13 @@ gamc_status gamc_comm_init(gamc_handle h, const uint8_t id[128], int32_t nranks,
   int r = g_nccl.CommInitRank(&h->comm, nranks, uid, rank);
   if (r != 0) { h->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); h->comm = nullptr; return GAMC_NCCL_ERROR; }
   h->nranks = nranks; h->rank = rank;
+  setup_peer_mailboxes(h);   // optional fast path; falls back to NCCL for the scalar too when it cannot be set up
+  return GAMC_OK;
+}
+
+gamc_status gamc_comm_peer_path(gamc_handle h, int32_t* active) {
+  if (!h || !active) return GAMC_INVALID_ARG;
+  *active = h->p2p_ready ? 1 : 0;
   return GAMC_OK;
 }
 
@@ -892,7 +959,10 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
         CUDA_TRY(h, cudaEventRecord(h->ev_side, h->side));
         h->dp_grid_now = std::max(1, h->dp_grid - 2);                                    // leave two SMs to the speculative CTAs
       }
-      const int nparts_post = h->comm ? 0 : (h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid);
+      const bool local_sum = !h->comm || h->p2p_ready;
+      const int nparts_post = local_sum ? (h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid) : 0;
+      PeerArgs pa{};
+      if (h->comm && h->p2p_ready) { pa.peers = h->d_peers; pa.nranks = h->nranks; pa.rank = h->rank; pa.seq = ++h->p2p_seq; }
       s = eval_device(h, B.theta_prop, 0, true, true);                                   // :148
       h->dp_grid_now = 0;
       if (s != GAMC_OK) return s;
@@ -900,7 +970,7 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
       {
         const size_t smem = step_smem_bytes(h->p);
         ProfScope ps(h, GAMC_K_LINALG);
-        k_am_post<<<1, LA_THREADS, smem, h->stream>>>(B, T, ti, next_am ? 1 : 0, h->part_ll, nparts_post);
+        k_am_post<<<1, LA_THREADS, smem, h->stream>>>(B, T, ti, next_am ? 1 : 0, h->part_ll, nparts_post, pa);
         CUDA_TRY(h, cudaGetLastError());
       }
       h->spec_ready = next_am;

@@ -11,6 +11,10 @@
 
 namespace gamc {
 
+// One mailbox slot of the peer all-reduce (see k_am_post) and the per-launch arguments of that path.
+struct PeerMail { double val; unsigned long long seq; };
+struct PeerArgs { PeerMail* const* peers; int nranks; int rank; unsigned long long seq; };
+
 struct Bufs {
   DevState* st;
   double* R; int goff;                   // landing buffer of an evaluation = all-reduce payload: [ll, g(p), pad, G(p x p)]
@@ -628,10 +632,14 @@ __global__ void __launch_bounds__(256) k_llt(const double* __restrict__ L, int p
 // next_spec = 1 (am_mode 2): the next step is an AM step whose factor update was computed speculatively for both outcomes
 // while the data pass ran; after the decision this kernel selects the factor buffer of the outcome that happened and
 // performs the head of the next `iterate!` (counters, proposal) so that the next data pass can start immediately.
-// part_ll / nparts: single-GPU jobs skip k_reduce for the log-likelihood-only evaluation and sum the per-CTA partials of
-// the data pass here, in k_reduce's order (bitwise the same value); nparts = 0 reads the (all-)reduced R[0].
+// part_ll / nparts: the per-CTA log-likelihood partials of the data pass are summed here, in k_reduce's order (bitwise the
+// same value), so the AM step launches neither k_reduce nor NCCL; nparts = 0 reads the (all-)reduced R[0] instead.
+// pa (multi-GPU): one-shot all-reduce of that scalar over NVLink peer memory -- every rank stores (value, sequence number)
+// into its slot of every peer's mailbox, waits until its own mailbox holds this step's sequence number from every rank,
+// and adds the values in rank order: the same bits on every rank.  Slots alternate with the parity of the sequence
+// number (a rank can be at most one step ahead of the slowest one).
 __global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, long long tape_idx, int next_spec,
-                                                           const double* __restrict__ part_ll, int nparts) {
+                                                           const double* __restrict__ part_ll, int nparts, PeerArgs pa) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StepSmem S = step_smem_carve(smem_raw, T.p);
   DevState* st = B.st;
@@ -645,6 +653,33 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, lo
       if (threadIdx.x == 0) S.red[39] = s;
     }
     __syncthreads();
+    if (pa.nranks > 1) {
+      const double mine = S.red[39];
+      const int par = (int)(pa.seq & 1ull);
+      if ((int)threadIdx.x < pa.nranks) {
+        volatile PeerMail* dst = pa.peers[threadIdx.x] + par * pa.nranks + pa.rank;
+        dst->val = mine;
+        __threadfence_system();
+        dst->seq = pa.seq;
+        volatile PeerMail* src = pa.peers[pa.rank] + par * pa.nranks + threadIdx.x;
+        const long long t0 = clock64();
+        bool got = true;
+        while (src->seq != pa.seq) {
+          if (clock64() - t0 > 6000000000ll) { got = false; break; }   // ~3 s: a peer died
+          __nanosleep(100);
+        }
+        __threadfence_system();
+        S.red[threadIdx.x] = got ? src->val : nan("");
+        if (!got && st->error_flag == 0) { st->error_flag = 5 /*GAMC_NCCL_ERROR*/; st->error_pivot = threadIdx.x; st->error_iter = st->count; }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int r = 0; r < pa.nranks; ++r) s += S.red[r];
+        S.red[39] = s;
+      }
+      __syncthreads();
+    }
   }
   const double ll_p = nparts > 0 ? S.red[39] : B.R[0];
   const double lt_p = ll_p + log_prior(B.theta_prop, p, T.lambda, S.red);

@@ -110,6 +110,12 @@ class Engine:
         uid = np.ascontiguousarray(uid, dtype=np.uint8)
         self._ck(self.lib.gamc_comm_init(self.h, L.u8ptr(uid), int(nranks), int(rank)))
 
+    def comm_peer_path(self):
+        """True if the scalar all-reduce of AM steps runs over the NVLink peer mailboxes (else NCCL)."""
+        out = C.c_int32(0)
+        self._ck(self.lib.gamc_comm_peer_path(self.h, C.byref(out)))
+        return bool(out.value)
+
     # -- sampler
     def sampler_init(self, cfg: L.Config, theta0):
         th = _f64(theta0, "C").ravel()

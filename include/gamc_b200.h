@@ -158,9 +158,15 @@ gamc_status gamc_eval_partials(gamc_handle h, const double* theta, double* ll, d
 /* ---- multi-GPU: observations row-sharded, one process per GPU -------------------------
  * gamc_comm_unique_id fills a 128-byte NCCL unique id on one rank; the host side (torch.distributed /
  * MPI / Julia Distributed) broadcasts it; every rank then calls gamc_comm_init.  After that, every
- * target evaluation all-reduces [ll, g_lik, G_lik] (NCCL, sum, in place, on the handle's stream). */
+ * target evaluation all-reduces [ll, g_lik, G_lik] (NCCL, sum, in place, on the handle's stream).
+ * gamc_comm_init also maps a small mailbox of every peer through CUDA IPC (NVLink peer memory): the scalar
+ * log-likelihood of an adaptive-Metropolis step is then all-reduced inside the accept/reject kernel itself
+ * (one-shot: every rank writes its partial to every peer, sums in rank order) instead of through NCCL.
+ * gamc_comm_peer_path reports whether that path is active (1) or NCCL carries the scalar too (0; e.g.
+ * GAMC_NO_P2P=1, no peer access, more than 32 ranks). */
 gamc_status gamc_comm_unique_id(uint8_t id_out[128]);
 gamc_status gamc_comm_init(gamc_handle h, const uint8_t id[128], int32_t nranks, int32_t rank);
+gamc_status gamc_comm_peer_path(gamc_handle h, int32_t* active);
 
 /* ---- sampler ----------------------------------------------------------------------------------------
  * gamc_sampler_init = Klara `initialize!` + `sampler_state` for GAMC (src/samplers/GAMC.jl:157-176,202-228):

@@ -62,7 +62,8 @@ def main():
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"MULTIGPU_CHECK world={world} {'PASS' if flag.item() == 1 else 'FAIL'} relerr_G={relerr(G, G0):.2e} relerr_g={relerr(grad, g0):.2e}")
+        print(f"MULTIGPU_CHECK world={world} {'PASS' if flag.item() == 1 else 'FAIL'} relerr_G={relerr(G, G0):.2e} relerr_g={relerr(grad, g0):.2e} "
+              f"am_scalar_allreduce={'peer-mailbox' if eng.comm_peer_path() else 'nccl'}")
     eng.close()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)
