@@ -385,8 +385,10 @@ def run_ours(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (Philox4x32-10 keyed by global row/col, generated on device)",
             "config": {"workload": f"C2: logistic N=2^{args.logN} rows per GPU, p={p}, FP64, GAMC rand_exp_decay(a=10), single chain",
-                       "rows_per_gpu": N, "global_rows": N * world, "p": p, "parallelism": (f"row-sharded x{world}, NCCL all-reduce of [ll, grad, metric]; AM-step scalar over "
-                                       + ("NVLink peer mailboxes inside k_am_post" if eng.comm_peer_path() else "NCCL")) if world > 1 else "single GPU",
+                       "rows_per_gpu": N, "global_rows": N * world, "p": p, "parallelism": (f"row-sharded x{world}; [ll, grad, metric] of SMMALA steps summed over "
+                                       + ("NVLink peer memory inside k_land" if eng.comm_peer_path() & 2 else "NCCL all-reduce")
+                                       + "; AM-step scalar over "
+                                       + ("NVLink peer mailboxes inside k_am_post" if eng.comm_peer_path() & 1 else "NCCL")) if world > 1 else "single GPU",
                        "l2": "inputs (2.1 GB design matrix per pass) larger than L2; no flush needed",
                        "value_definition": "iters/s x n_gpus (each GPU processes one 2^20-row shard of every iteration)",
                        "am_mode": args.am_mode, "nsteps": K, "burnin": K // 5},

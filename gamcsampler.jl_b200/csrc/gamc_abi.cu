@@ -113,6 +113,9 @@ struct gamc_ctx {
   ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
   // peer mailboxes (NVLink peer memory, CUDA IPC): scalar all-reduce of the AM step without NCCL or k_reduce
   PeerMail* mbox = nullptr; PeerMail** d_peers = nullptr; void* peer_ptr[32] = {nullptr}; bool p2p_ready = false; unsigned long long p2p_seq = 0;
+  // peer landing: two reduced-evaluation buffers per rank, mapped by every peer; k_land sums them over NVLink (no NCCL on the step path)
+  double* xR = nullptr; size_t xR_stride = 0; int xR_p = 0; double** d_peerR = nullptr; void* peerR_ptr[32] = {nullptr}; bool land_p2p = false;
+  unsigned long long land_seq = 0;
   // profiling
   bool prof = false; std::vector<cudaEvent_t> ev0, ev1; std::vector<int> ev_family; int ev_used = 0;
   long long launches = 0;
@@ -212,6 +215,112 @@ void free_target(gamc_ctx* h) {
   cudaFree(h->theta_eval); h->theta_eval = nullptr;
 }
 
+void free_peer_landing(gamc_ctx* h) {
+  for (int r = 0; r < h->nranks && r < 32; ++r) if (h->peerR_ptr[r] && r != h->rank) cudaIpcCloseMemHandle(h->peerR_ptr[r]);
+  for (int r = 0; r < 32; ++r) h->peerR_ptr[r] = nullptr;
+  cudaFree(h->xR); cudaFree(h->d_peerR);
+  h->xR = nullptr; h->d_peerR = nullptr; h->land_p2p = false; h->xR_p = 0;
+}
+
+// Collective (every rank calls it from gamc_sampler_init): allocate this rank's two reduced-evaluation buffers and map every
+// peer's pair (CUDA IPC).  Leaves land_p2p = false (NCCL path) unless it worked on every rank.
+void setup_peer_landing(gamc_ctx* h) {
+  if (!h->comm || !h->p2p_ready || getenv("GAMC_NO_P2P_LAND")) { h->land_p2p = false; return; }
+  if (h->land_p2p && h->xR_p == h->p) return;
+  free_peer_landing(h);
+  const int n = h->nranks, p = h->p;
+  h->xR_stride = ((size_t)h->goff + (size_t)p * p + 15) & ~(size_t)15;
+  unsigned char* d_handles = nullptr;
+  std::vector<cudaIpcMemHandle_t> handles(n);
+  bool ok = cudaMalloc(&h->xR, sizeof(double) * 2 * h->xR_stride) == cudaSuccess &&
+            cudaMemsetAsync(h->xR, 0, sizeof(double) * 2 * h->xR_stride, h->stream) == cudaSuccess &&
+            cudaMalloc(&d_handles, sizeof(cudaIpcMemHandle_t) * n) == cudaSuccess &&
+            cudaIpcGetMemHandle(&handles[h->rank], h->xR) == cudaSuccess &&
+            cudaMemcpyAsync(d_handles + sizeof(cudaIpcMemHandle_t) * h->rank, &handles[h->rank], sizeof(cudaIpcMemHandle_t),
+                            cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
+  if (d_handles) {
+    const int r = g_nccl.AllGather(d_handles + sizeof(cudaIpcMemHandle_t) * h->rank, d_handles, sizeof(cudaIpcMemHandle_t), 0 /*ncclChar*/,
+                                   h->comm, h->stream);
+    ok = ok && r == 0 && cudaMemcpyAsync(handles.data(), d_handles, sizeof(cudaIpcMemHandle_t) * n, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
+  } else {
+    ok = false;
+  }
+  ok = cudaStreamSynchronize(h->stream) == cudaSuccess && ok;
+  cudaFree(d_handles);
+  std::vector<double*> peers(n, nullptr);
+  for (int r = 0; ok && r < n; ++r) {
+    if (r == h->rank) { peers[r] = h->xR; h->peerR_ptr[r] = h->xR; continue; }
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+    h->peerR_ptr[r] = ptr; peers[r] = (double*)ptr;
+  }
+  ok = ok && cudaMalloc(&h->d_peerR, sizeof(double*) * n) == cudaSuccess &&
+       cudaMemcpy(h->d_peerR, peers.data(), sizeof(double*) * n, cudaMemcpyHostToDevice) == cudaSuccess;
+  cudaGetLastError();
+  double* d_ok = nullptr;
+  bool all_ok = false;
+  if (cudaMalloc(&d_ok, sizeof(double)) == cudaSuccess) {
+    const double v = ok ? 1.0 : 0.0;
+    double all = 0.0;
+    cudaMemcpyAsync(d_ok, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    const int r = g_nccl.AllReduce(d_ok, d_ok, 1, NCCL_DOUBLE, 3 /*ncclMin*/, h->comm, h->stream);
+    cudaMemcpyAsync(&all, d_ok, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_ok);
+    all_ok = (r == 0 && all == 1.0);
+  }
+  h->land_p2p = all_ok; h->xR_p = p;
+}
+
+// Map every rank's mailbox array into this process (CUDA IPC over NVLink peer memory).  The handles travel through one
+// ncclAllGather; the gather also orders every rank's zero-fill before any peer write.  GAMC_NO_P2P=1 disables the path.
+void setup_peer_mailboxes(gamc_ctx* h) {
+  h->p2p_ready = false;
+  if (getenv("GAMC_NO_P2P") || h->nranks < 2 || h->nranks > 32 || !g_nccl.AllGather) return;
+  const int n = h->nranks;
+  unsigned char* d_handles = nullptr;
+  std::vector<cudaIpcMemHandle_t> handles(n);
+  bool ok = cudaMalloc(&h->mbox, sizeof(PeerMail) * 4 * n) == cudaSuccess &&     // [0,2n): AM scalars, [2n,4n): landing flags
+            cudaMemsetAsync(h->mbox, 0, sizeof(PeerMail) * 4 * n, h->stream) == cudaSuccess &&
+            cudaMalloc(&d_handles, sizeof(cudaIpcMemHandle_t) * n) == cudaSuccess &&
+            cudaIpcGetMemHandle(&handles[h->rank], h->mbox) == cudaSuccess &&
+            cudaMemcpyAsync(d_handles + sizeof(cudaIpcMemHandle_t) * h->rank, &handles[h->rank], sizeof(cudaIpcMemHandle_t),
+                            cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
+  // every rank must take part in the gather, whatever happened above (a rank that failed contributes zeros)
+  if (d_handles) {
+    const int r = g_nccl.AllGather(d_handles + sizeof(cudaIpcMemHandle_t) * h->rank, d_handles, sizeof(cudaIpcMemHandle_t), 0 /*ncclChar*/,
+                                   h->comm, h->stream);
+    ok = ok && r == 0 && cudaMemcpyAsync(handles.data(), d_handles, sizeof(cudaIpcMemHandle_t) * n, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
+  } else {
+    ok = false;
+  }
+  ok = cudaStreamSynchronize(h->stream) == cudaSuccess && ok;
+  cudaFree(d_handles);
+  std::vector<PeerMail*> peers(n, nullptr);
+  for (int r = 0; ok && r < n; ++r) {
+    if (r == h->rank) { peers[r] = h->mbox; h->peer_ptr[r] = h->mbox; continue; }
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+    h->peer_ptr[r] = ptr; peers[r] = (PeerMail*)ptr;
+  }
+  ok = ok && cudaMalloc(&h->d_peers, sizeof(PeerMail*) * n) == cudaSuccess &&
+       cudaMemcpy(h->d_peers, peers.data(), sizeof(PeerMail*) * n, cudaMemcpyHostToDevice) == cudaSuccess;
+  cudaGetLastError();
+  // all ranks must agree: a one-element all-reduce of the local verdict (min over ranks)
+  double* d_ok = nullptr;
+  if (cudaMalloc(&d_ok, sizeof(double)) == cudaSuccess) {
+    const double v = ok ? 1.0 : 0.0;
+    double all = 0.0;
+    cudaMemcpyAsync(d_ok, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    const int r = g_nccl.AllReduce(d_ok, d_ok, 1, NCCL_DOUBLE, 3 /*ncclMin*/, h->comm, h->stream);
+    cudaMemcpyAsync(&all, d_ok, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_ok);
+    h->p2p_ready = (r == 0 && all == 1.0);
+  }
+  h->p2p_seq = 0;
+}
+
 void free_sampler(gamc_ctx* h) {
   cudaFree(h->d_chain); cudaFree(h->d_accept);
   h->B = Bufs{}; h->d_chain = nullptr; h->d_accept = nullptr;
@@ -283,10 +392,10 @@ gamc_status launch_metric(gamc_ctx* h) {
 }
 
 // level: 0 = ll, 1 = ll + grad, 2 = ll + grad + metric
-gamc_status launch_reduce(gamc_ctx* h, int level) {
+gamc_status launch_reduce(gamc_ctx* h, int level, double* E = nullptr) {
   ProfScope ps(h, GAMC_K_REDUCE);
   const int nblk = (level >= 2 ? h->ntasks * 4 : 0) + 1;
-  k_reduce<<<nblk, 256, 0, h->stream>>>(h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid, level >= 1,
+  k_reduce<<<nblk, 256, 0, h->stream>>>(E ? E : h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid, level >= 1,
                                         level >= 2 ? h->ws : nullptr, h->d_coords, h->ntasks, h->d_task_nsplit, h->layout.max_nsplit);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
@@ -431,7 +540,35 @@ bool schedule_decision(const gamc_config& c, long long i, long long tot, double 
 // move a landed level-2 evaluation into its slot (mode 0 initial point, 1 current point, 2 proposal)
 gamc_status launch_land(gamc_ctx* h, int mode) {
   ProfScope ps(h, GAMC_K_LINALG);
-  k_land<<<h->p, LAND_THREADS, 0, h->stream>>>(h->B, h->tune, mode);
+  k_land<<<h->p, LAND_THREADS, 0, h->stream>>>(h->B, h->tune, mode, LandPeer{});
+  CUDA_TRY(h, cudaGetLastError());
+  return GAMC_OK;
+}
+
+// Level-2 evaluation at a device-resident theta, landed into its slot.  With peer landing the reduced buffers stay where
+// they are and k_land adds them up over NVLink; otherwise NCCL all-reduces R first.
+gamc_status eval_and_land(gamc_ctx* h, const double* d_theta, int mode) {
+  if (!h->land_p2p) {
+    gamc_status s = eval_device(h, d_theta, 2, true);
+    if (s != GAMC_OK) return s;
+    return launch_land(h, mode);
+  }
+  gamc_status s = launch_datapass(h, d_theta, true);
+  if (s != GAMC_OK) return s;
+  s = launch_metric(h);
+  if (s != GAMC_OK) return s;
+  const unsigned long long seq = ++h->land_seq;
+  const size_t roff = (size_t)(seq & 1ull) * h->xR_stride;
+  s = launch_reduce(h, 2, h->xR + roff);
+  if (s != GAMC_OK) return s;
+  {
+    ProfScope ps(h, GAMC_K_ALLREDUCE);
+    k_peer_flag<<<1, 32, 0, h->stream>>>(h->d_peers, h->nranks, h->rank, seq);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  ProfScope ps(h, GAMC_K_LINALG);
+  LandPeer lp{h->d_peerR, h->d_peers, h->nranks, h->rank, seq, roff};
+  k_land<<<h->p, LAND_THREADS, 0, h->stream>>>(h->B, h->tune, mode, lp);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
 }
@@ -539,6 +676,7 @@ gamc_status gamc_destroy(gamc_handle h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (int r = 0; r < h->nranks && r < 32; ++r) if (h->peer_ptr[r] && r != h->rank) cudaIpcCloseMemHandle(h->peer_ptr[r]);
   cudaFree(h->mbox); cudaFree(h->d_peers);
+  free_peer_landing(h);
   free_sampler(h);
   free_target(h);
   free_batched(h);
@@ -679,55 +817,6 @@ gamc_status gamc_comm_unique_id(uint8_t id_out[128]) {
   return GAMC_OK;
 }
 
-// Map every rank's mailbox array into this process (CUDA IPC over NVLink peer memory).  The handles travel through one
-// ncclAllGather; the gather also orders every rank's zero-fill before any peer write.  GAMC_NO_P2P=1 disables the path.
-static void setup_peer_mailboxes(gamc_ctx* h) {
-  h->p2p_ready = false;
-  if (getenv("GAMC_NO_P2P") || h->nranks < 2 || h->nranks > 32 || !g_nccl.AllGather) return;
-  const int n = h->nranks;
-  unsigned char* d_handles = nullptr;
-  std::vector<cudaIpcMemHandle_t> handles(n);
-  bool ok = cudaMalloc(&h->mbox, sizeof(PeerMail) * 2 * n) == cudaSuccess &&
-            cudaMemsetAsync(h->mbox, 0, sizeof(PeerMail) * 2 * n, h->stream) == cudaSuccess &&
-            cudaMalloc(&d_handles, sizeof(cudaIpcMemHandle_t) * n) == cudaSuccess &&
-            cudaIpcGetMemHandle(&handles[h->rank], h->mbox) == cudaSuccess &&
-            cudaMemcpyAsync(d_handles + sizeof(cudaIpcMemHandle_t) * h->rank, &handles[h->rank], sizeof(cudaIpcMemHandle_t),
-                            cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
-  // every rank must take part in the gather, whatever happened above (a rank that failed contributes zeros)
-  if (d_handles) {
-    const int r = g_nccl.AllGather(d_handles + sizeof(cudaIpcMemHandle_t) * h->rank, d_handles, sizeof(cudaIpcMemHandle_t), 0 /*ncclChar*/,
-                                   h->comm, h->stream);
-    ok = ok && r == 0 && cudaMemcpyAsync(handles.data(), d_handles, sizeof(cudaIpcMemHandle_t) * n, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
-  } else {
-    ok = false;
-  }
-  ok = cudaStreamSynchronize(h->stream) == cudaSuccess && ok;
-  cudaFree(d_handles);
-  std::vector<PeerMail*> peers(n, nullptr);
-  for (int r = 0; ok && r < n; ++r) {
-    if (r == h->rank) { peers[r] = h->mbox; h->peer_ptr[r] = h->mbox; continue; }
-    void* ptr = nullptr;
-    if (cudaIpcOpenMemHandle(&ptr, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
-    h->peer_ptr[r] = ptr; peers[r] = (PeerMail*)ptr;
-  }
-  ok = ok && cudaMalloc(&h->d_peers, sizeof(PeerMail*) * n) == cudaSuccess &&
-       cudaMemcpy(h->d_peers, peers.data(), sizeof(PeerMail*) * n, cudaMemcpyHostToDevice) == cudaSuccess;
-  cudaGetLastError();
-  // all ranks must agree: a one-element all-reduce of the local verdict (min over ranks)
-  double* d_ok = nullptr;
-  if (cudaMalloc(&d_ok, sizeof(double)) == cudaSuccess) {
-    const double v = ok ? 1.0 : 0.0;
-    double all = 0.0;
-    cudaMemcpyAsync(d_ok, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream);
-    const int r = g_nccl.AllReduce(d_ok, d_ok, 1, NCCL_DOUBLE, 3 /*ncclMin*/, h->comm, h->stream);
-    cudaMemcpyAsync(&all, d_ok, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    cudaStreamSynchronize(h->stream);
-    cudaFree(d_ok);
-    h->p2p_ready = (r == 0 && all == 1.0);
-  }
-  h->p2p_seq = 0;
-}
-
 gamc_status gamc_comm_init(gamc_handle h, const uint8_t id[128], int32_t nranks, int32_t rank) {
   if (!h) return GAMC_INVALID_ARG;
   REQUIRE(h, id && nranks >= 1 && rank >= 0 && rank < nranks, GAMC_INVALID_ARG, "gamc_comm_init: bad argument");
@@ -744,7 +833,7 @@ gamc_status gamc_comm_init(gamc_handle h, const uint8_t id[128], int32_t nranks,
 
 gamc_status gamc_comm_peer_path(gamc_handle h, int32_t* active) {
   if (!h || !active) return GAMC_INVALID_ARG;
-  *active = h->p2p_ready ? 1 : 0;
+  *active = (h->p2p_ready ? 1 : 0) | (h->land_p2p ? 2 : 0);   // bit 0: AM-step scalar, bit 1: gradient/metric landing
   return GAMC_OK;
 }
 
@@ -823,9 +912,8 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
     CUDA_TRY(h, cudaGetLastError());
   } else {
     // initialize! (:157-176): first evaluation of target + gradient + metric at theta0
-    s = eval_device(h, B.theta, 2, true);
-    if (s != GAMC_OK) return s;
-    s = launch_land(h, 0);
+    setup_peer_landing(h);
+    s = eval_and_land(h, B.theta, 0);
     if (s != GAMC_OK) return s;
     s = launch_step(h, k_sampler_init, B, T);
     if (s != GAMC_OK) return s;
@@ -927,12 +1015,10 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
       h->spec_ready = false;
       const int refactor = h->h_past ? 0 : 1;
       if (refactor) {                                                                    // :20
-        s = eval_device(h, B.theta, 2, true); if (s != GAMC_OK) return s;
-        s = launch_land(h, 1); if (s != GAMC_OK) return s;
+        s = eval_and_land(h, B.theta, 1); if (s != GAMC_OK) return s;
       }
       s = launch_step(h, k_smmala_pre, B, T, ti, refactor); if (s != GAMC_OK) return s;
-      s = eval_device(h, B.theta_prop, 2, true); if (s != GAMC_OK) return s;             // :37
-      s = launch_land(h, 2); if (s != GAMC_OK) return s;
+      s = eval_and_land(h, B.theta_prop, 2); if (s != GAMC_OK) return s;                 // :37
       s = launch_step(h, k_smmala_post, B, T, ti); if (s != GAMC_OK) return s;
     } else {                                                                             // :128
       const bool next_am = (T.am_mode == 2) && (k + 1 < n) && !kinds[k + 1];            // next step is AM too: speculate

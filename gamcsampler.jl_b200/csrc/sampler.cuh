@@ -14,6 +14,18 @@ namespace gamc {
 // One mailbox slot of the peer all-reduce (see k_am_post) and the per-launch arguments of that path.
 struct PeerMail { double val; unsigned long long seq; };
 struct PeerArgs { PeerMail* const* peers; int nranks; int rank; unsigned long long seq; };
+// Peer landing (see k_land): peerR[r] = rank r's pair of reduced evaluation buffers, roff = offset of this evaluation's buffer.
+struct LandPeer { double* const* peerR; PeerMail* const* peers; int nranks; int rank; unsigned long long seq; size_t roff; };
+__device__ __forceinline__ double ld_peer(const double* q) { return *reinterpret_cast<const volatile double*>(q); }
+
+// After k_reduce: tell every peer that this rank's reduced evaluation `seq` is in place (mailbox slots 2n .. 4n).
+__global__ void k_peer_flag(PeerMail* const* peers, int nranks, int rank, unsigned long long seq) {
+  if ((int)threadIdx.x < nranks) {
+    __threadfence_system();
+    volatile PeerMail* dst = peers[threadIdx.x] + 2 * nranks + (int)(seq & 1ull) * nranks + rank;
+    dst->seq = seq;
+  }
+}
 
 struct Bufs {
   DevState* st;
@@ -91,22 +103,44 @@ __device__ inline double add_prior(double* E, int goff, const double* theta, int
 // land[j] = 1 if column j of G has a non-finite entry.  Column partials are summed in a fixed order by the consumer.
 // mode: 0 = initial point (slot 0), 1 = re-evaluation of the current point (slot cur), 2 = proposal (slot 1 - cur).
 // ---------------------------------------------------------------------------------------------------
+// Multi-GPU with peer landing (lp.nranks > 1): the kernel IS the all-reduce -- it waits for every rank's "reduced" flag
+// and adds the ranks' buffers in rank order while landing them (loads over NVLink peer memory; identical bits on every
+// rank; no NCCL call and no second pass over the payload).
 constexpr int LAND_THREADS = 128;
-__global__ void __launch_bounds__(LAND_THREADS) k_land(Bufs B, TuneCfg T, int mode) {
+__global__ void __launch_bounds__(LAND_THREADS) k_land(Bufs B, TuneCfg T, int mode, LandPeer lp) {
   __shared__ double red[40];
   DevState* st = B.st;
   if (st->error_flag) return;
   const int p = T.p, j = blockIdx.x;
+  const int nr = lp.nranks > 1 ? lp.nranks : 1;
+  if (nr > 1) {
+    if ((int)threadIdx.x < nr) {
+      volatile PeerMail* src = lp.peers[lp.rank] + 2 * nr + (int)(lp.seq & 1ull) * nr + threadIdx.x;
+      const long long t0 = clock64();
+      while (src->seq != lp.seq) {
+        if (clock64() - t0 > 6000000000ll) {          // ~3 s: a peer died
+          if (st->error_flag == 0) { st->error_flag = 5 /*GAMC_NCCL_ERROR*/; st->error_pivot = threadIdx.x; st->error_iter = st->count; }
+          break;
+        }
+        __nanosleep(100);
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+  }
   const int cur = st->cur;
   const int slot = mode == 0 ? 0 : (mode == 1 ? cur : 1 - cur);
   const double* G = B.R + B.goff + (size_t)j * p;
+  const size_t poff = lp.roff + B.goff + (size_t)j * p;
   const double* Gc = B.Gs + (size_t)cur * B.Gstride + (size_t)j * p;
   double* Gd = B.Gs + (size_t)slot * B.Gstride + (size_t)j * p;
   double* U = B.U + (size_t)slot * B.Ustride + (size_t)j * p;
   const double ilam = 1.0 / T.lambda;
   double nf = 0.0, q1 = 0.0, q2 = 0.0;
   for (int i = threadIdx.x; i < p; i += LAND_THREADS) {
-    double v = G[i];
+    double v;
+    if (nr > 1) { v = 0.0; for (int r = 0; r < nr; ++r) v += ld_peer(lp.peerR[r] + poff + i); }
+    else v = G[i];
     if (i == j) v += ilam;
     Gd[i] = v;
     if (i <= j) U[i] = v;
@@ -132,13 +166,21 @@ __global__ void __launch_bounds__(LAND_THREADS) k_land(Bufs B, TuneCfg T, int mo
     const double* th = mode == 2 ? B.theta_prop : B.theta;
     double gnf = 0.0;
     for (int i = threadIdx.x; i < p; i += LAND_THREADS) {
-      const double g = B.R[1 + i] - th[i] * ilam;
+      double gl;
+      if (nr > 1) { gl = 0.0; for (int r = 0; r < nr; ++r) gl += ld_peer(lp.peerR[r] + lp.roff + 1 + i); }
+      else gl = B.R[1 + i];
+      const double g = gl - th[i] * ilam;
       B.gs[(size_t)slot * p + i] = g;
       if (!isfinite(g)) gnf = 1.0;
     }
     gnf = block_sum(gnf, red);
-    const double lp = log_prior(th, p, T.lambda, red);
-    if (threadIdx.x == 0) { B.land[3 * p] = B.R[0] + lp; B.land[3 * p + 1] = gnf; }
+    const double lpr = log_prior(th, p, T.lambda, red);
+    if (threadIdx.x == 0) {
+      double ll;
+      if (nr > 1) { ll = 0.0; for (int r = 0; r < nr; ++r) ll += ld_peer(lp.peerR[r] + lp.roff); }
+      else ll = B.R[0];
+      B.land[3 * p] = ll + lpr; B.land[3 * p + 1] = gnf;
+    }
   }
 }
 

@@ -111,10 +111,11 @@ class Engine:
         self._ck(self.lib.gamc_comm_init(self.h, L.u8ptr(uid), int(nranks), int(rank)))
 
     def comm_peer_path(self):
-        """True if the scalar all-reduce of AM steps runs over the NVLink peer mailboxes (else NCCL)."""
+        """Bit mask of the reductions that run over NVLink peer memory instead of NCCL: 1 = the scalar of AM steps
+        (inside k_am_post), 2 = the gradient/metric payload of SMMALA steps (inside k_land; known after sampler_init)."""
         out = C.c_int32(0)
         self._ck(self.lib.gamc_comm_peer_path(self.h, C.byref(out)))
-        return bool(out.value)
+        return int(out.value)
 
     # -- sampler
     def sampler_init(self, cfg: L.Config, theta0):

@@ -161,9 +161,12 @@ gamc_status gamc_eval_partials(gamc_handle h, const double* theta, double* ll, d
  * target evaluation all-reduces [ll, g_lik, G_lik] (NCCL, sum, in place, on the handle's stream).
  * gamc_comm_init also maps a small mailbox of every peer through CUDA IPC (NVLink peer memory): the scalar
  * log-likelihood of an adaptive-Metropolis step is then all-reduced inside the accept/reject kernel itself
- * (one-shot: every rank writes its partial to every peer, sums in rank order) instead of through NCCL.
- * gamc_comm_peer_path reports whether that path is active (1) or NCCL carries the scalar too (0; e.g.
- * GAMC_NO_P2P=1, no peer access, more than 32 ranks). */
+ * (one-shot: every rank writes its partial to every peer, sums in rank order) instead of through NCCL; and
+ * gamc_sampler_init maps every peer's pair of reduced-evaluation buffers, so the [ll, g, G] payload of
+ * SMMALA steps is summed over the ranks by the landing kernel itself (loads over NVLink, rank order).
+ * gamc_comm_peer_path reports which of the two is active: bit 0 = AM scalar, bit 1 = SMMALA payload
+ * (0 = NCCL carries both; e.g. GAMC_NO_P2P=1, GAMC_NO_P2P_LAND=1, no peer access, more than 32 ranks).
+ * The standalone gamc_eval_* entry points always use NCCL. */
 gamc_status gamc_comm_unique_id(uint8_t id_out[128]);
 gamc_status gamc_comm_init(gamc_handle h, const uint8_t id[128], int32_t nranks, int32_t rank);
 gamc_status gamc_comm_peer_path(gamc_handle h, int32_t* active);

@@ -63,7 +63,8 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"MULTIGPU_CHECK world={world} {'PASS' if flag.item() == 1 else 'FAIL'} relerr_G={relerr(G, G0):.2e} relerr_g={relerr(grad, g0):.2e} "
-              f"am_scalar_allreduce={'peer-mailbox' if eng.comm_peer_path() else 'nccl'}")
+              f"am_scalar_allreduce={'peer-mailbox' if eng.comm_peer_path() & 1 else 'nccl'} "
+              f"metric_allreduce={'peer-landing' if eng.comm_peer_path() & 2 else 'nccl'}")
     eng.close()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)
