@@ -140,6 +140,19 @@ def test_state_arrays_parity(gamc, engine):
     assert relerr(eng.array(1), osam.grad) <= 1e-10
 
 
+@pytest.mark.parametrize("N,p,nsteps", [(400, 12, 25), (3000, 130, 12), (6000, 256, 9)])
+def test_smmala_ratio_parity(gamc, engine, N, p, nsteps):
+    """sstate.ratio of the last SMMALA transition (iterate/GAMC.jl:45-67).  The device forms the proposal-side quadratic
+    form as a'G*a - eps a'grad* + eps^2/4 f*'grad* (a = theta - theta*, f* = G*^-1 grad*) from the column partials of
+    k_land instead of the reference's literal (theta - mu*)'G*(theta - mu*); both must agree to rounding."""
+    job, chain, osam, v, a, k = _run_both(gamc, engine, N, p, nsteps, 0, seed=21, update=gamc.smmala_only_update())
+    st = job.engine.state()
+    assert np.array_equal(chain.diagnosticvalues.ravel(), a)
+    assert np.isfinite(osam.ratio)
+    assert abs(st.ratio - osam.ratio) <= 1e-9 * max(1.0, abs(osam.ratio))
+    assert abs(st.logtarget - osam.logtarget) <= 1e-10 * abs(osam.logtarget)
+
+
 @pytest.mark.parametrize("am_mode", [0, 1, 2])
 def test_am_covariance_readout(gamc, engine, am_mode):
     """sstate.oldinvtensor after a run that ends in AM steps = the Haario covariance recursion seeded with inv(G)."""
