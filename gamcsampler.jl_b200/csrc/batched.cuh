@@ -733,7 +733,10 @@ __host__ __device__ inline size_t bt_smem_bytes(int blob_doubles, int nthreads) 
 }
 
 template <int TGT>
-__global__ void __launch_bounds__(TGT == 0 ? 32 : 128) k_batched_gamc(BatchedCfg C, int mode, long long n_iters, const double* __restrict__ theta0) {
+#ifndef GAMC_RV_MINBLOCKS
+#define GAMC_RV_MINBLOCKS 4     // resident CTAs per SM the RV kernels are compiled for: 128 registers (spills) but twice the warps of the uncapped build; measured 51.9 k (2 CTAs/SM) -> 60.9 k (3) -> 70.9 k (4) chain-iterations/s on C5
+#endif
+__global__ void __launch_bounds__(TGT == 0 ? 32 : 128, TGT == 0 ? 1 : GAMC_RV_MINBLOCKS) k_batched_gamc(BatchedCfg C, int mode, long long n_iters, const double* __restrict__ theta0) {
   extern __shared__ __align__(16) double bsm[];
   const int chain = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (chain >= C.nchains) return;

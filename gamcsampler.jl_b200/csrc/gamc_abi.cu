@@ -588,6 +588,7 @@ gamc_status set_step_attrs(gamc_ctx* h) {
                       (const void*)k_am_post};
   for (const void* k : ks) { gamc_status s = ensure_attr(h, k, smem); if (s != GAMC_OK) return s; }
   { gamc_status s = ensure_attr(h, (const void*)k_am_pre_r1, am_r1_smem_bytes(512, 1)); if (s != GAMC_OK) return s; }
+  { gamc_status s = ensure_attr(h, (const void*)k_triinv, triinv_smem_bytes(512)); if (s != GAMC_OK) return s; }
   return GAMC_OK;
 }
 
@@ -596,8 +597,8 @@ gamc_status launch_inverse(gamc_ctx* h, bool write_C = true) {
   const int p = h->p;
   {
     ProfScope ps(h, GAMC_K_LINALG);
-    const int warps_per_block = 8;
-    k_triinv<<<(p + warps_per_block - 1) / warps_per_block, 256, 0, h->stream>>>(h->B.st, h->B.U, h->B.Ustride, h->B.rdiagU, p, h->B.W);
+    const size_t smem = triinv_smem_bytes(p);
+    k_triinv<<<(p + 31) / 32, 256, smem, h->stream>>>(h->B.st, h->B.U, h->B.Ustride, h->B.invU, h->B.invUstride, p, h->B.W);
     CUDA_TRY(h, cudaGetLastError());
   }
   if (write_C) {

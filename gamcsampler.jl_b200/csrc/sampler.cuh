@@ -838,46 +838,102 @@ __global__ void __launch_bounds__(256) k_mala_post(Bufs B, TuneCfg T, long long 
 
 // ---------------------------------------------------------------------------------------------------
 // SMMALA -> AM hand-over: sstate.oldinvtensor = inv(G) seeds the AM covariance recursion
-// (iterate/GAMC.jl:26,92,133).  W = Lm^-1 (M space, one column per warp, column-oriented substitution with
-// one-step-ahead prefetch), then inv(G) = W' W.
+// (iterate/GAMC.jl:26,92,133).  W = Lm^-1 (M space), then inv(G) = W' W.
+// Blocked by 32: one CTA per block column J, W_JJ = Y_J (the inverted diagonal blocks chol_blocked left behind) and
+//   W_IJ = -Y_I * sum_{K=J}^{I-1} L_IK W_KJ     for I = J+1 ..,
+// every product on the FP64 tensor cores (8 warps x 2 DMMA 8x8 tiles); block column J of W stays in shared memory and
+// the next L block is fetched into registers while the current one is multiplied.
 // ---------------------------------------------------------------------------------------------------
-constexpr int TI_MAXR = 16;  // rows per lane: p <= 512
+constexpr int TI_LD = 36;                 // leading dimension of the 32 x 32 operand tiles in shared memory (4 mod 16: conflict-free fragments)
+constexpr int TI_TILE = 32 * TI_LD;
+__host__ __device__ inline size_t triinv_smem_bytes(int p) { return sizeof(double) * (size_t)((p + 31) / 32 + 3) * TI_TILE; }
 
 __global__ void __launch_bounds__(256) k_triinv(const DevState* st, const double* Ubase, size_t Ustride,
-                                                const double* rdiagBase, int p, double* W) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int j = warp;
-  if (j >= p) return;
+                                                const double* invBase, size_t invStride, int p, double* W) {
+  extern __shared__ __align__(16) double ti_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nblk = (p + 31) / 32, J = blockIdx.x;
   const int cur = st->cur;
   MatView<true> L{const_cast<double*>(Ubase) + (size_t)cur * Ustride, p, p};
-  const double* rd = rdiagBase + (size_t)cur * p;
-  // lane owns rows i = j + lane + 32 s
-  double b[TI_MAXR];
+  const double* invd = invBase + (size_t)cur * invStride;
+  double* Wsm = ti_smem;                          // [I - J][k][n]: block (I, J) of W, row k, column n
+  double* Asm = ti_smem + (size_t)nblk * TI_TILE; // [k][r]: current left operand (L_IK or Y_I), column k, row r
+  double* Ssm = Asm + TI_TILE;                    // [k][n]: S = sum_K L_IK W_KJ
+  const int fr = lane >> 2, fk = lane & 3;
+  const int mi = warp >> 1, n0 = (warp & 1) * 2;  // this warp's tiles: (mi, n0) and (mi, n0 + 1)
+  // W_JJ = Y_J: layout A of invd is [j * 32 + i] = inv(i, j)
+  for (int e = tid; e < 1024; e += 256) {
+    const int i = e & 31, j = e >> 5;
+    const double v = invd[(size_t)J * LA_INVD_STRIDE + j * 32 + i];
+    Wsm[i * TI_LD + j] = v;
+    const int gi = 32 * J + i, gj = 32 * J + j;
+    if (gi < p && gj < p) W[(size_t)gi + (size_t)gj * p] = v;
+  }
+  double pre[4];
+  auto fetch_L = [&](int I, int K) {              // L_IK -> registers, element (r, k) with r = e % 32 (coalesced along rows)
 #pragma unroll
-  for (int s = 0; s < TI_MAXR; ++s) b[s] = 0.0;
-  if (lane == 0) b[0] = 1.0;
-  double* Wc = W + (size_t)j * p;
-  for (int i = lane; i < j; i += 32) Wc[i] = 0.0;
-  double nxt[TI_MAXR];
-#pragma unroll
-  for (int s = 0; s < TI_MAXR; ++s) { const int i = j + lane + 32 * s; nxt[s] = (i > j && i < p) ? L(i, j) : 0.0; }
-  for (int k = j; k < p; ++k) {
-    double colv[TI_MAXR];
-#pragma unroll
-    for (int s = 0; s < TI_MAXR; ++s) colv[s] = nxt[s];
-    if (k + 1 < p) {
-#pragma unroll
-      for (int s = 0; s < TI_MAXR; ++s) { const int i = j + lane + 32 * s; nxt[s] = (i > k + 1 && i < p) ? L(i, k + 1) : 0.0; }
+    for (int u = 0; u < 4; ++u) {
+      const int e = tid + 256 * u, r = e & 31, k = e >> 5;
+      const int gi = 32 * I + r, gj = 32 * K + k;
+      pre[u] = (gi < p && gj < p) ? L(gi, gj) : 0.0;
     }
-    // owner of row k: lane (k-j)%32, register (k-j)/32
-    const int ol = (k - j) & 31, os = (k - j) >> 5;
-    double bk = 0.0;
+  };
+  auto fetch_Y = [&](int I) {                     // Y_I as a left operand: A[r = i][k = j] = inv(i, j)
 #pragma unroll
-    for (int s = 0; s < TI_MAXR; ++s) if (s == os) bk = b[s];
-    const double wk = __shfl_sync(0xffffffffu, bk, ol) * rd[k];
-    if (lane == ol) Wc[k] = wk;
+    for (int u = 0; u < 4; ++u) { const int e = tid + 256 * u; pre[u] = invd[(size_t)I * LA_INVD_STRIDE + e]; }   // e = j * 32 + i
+  };
+  auto stage = [&]() {
 #pragma unroll
-    for (int s = 0; s < TI_MAXR; ++s) b[s] = fma(-colv[s], wk, b[s]);
+    for (int u = 0; u < 4; ++u) { const int e = tid + 256 * u, r = e & 31, k = e >> 5; Asm[k * TI_LD + r] = pre[u]; }
+  };
+  if (J + 1 < nblk) fetch_L(J + 1, J);
+  __syncthreads();
+  for (int I = J + 1; I < nblk; ++I) {
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int K = J; K < I; ++K) {
+      stage();                                    // L_IK (fetched earlier) -> shared
+      __syncthreads();
+      if (K + 1 < I) fetch_L(I, K + 1); else fetch_Y(I);
+      const double* Bm = Wsm + (size_t)(K - J) * TI_TILE;
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const double af = Asm[(4 * k4 + fk) * TI_LD + 8 * mi + fr];
+        const double b0 = Bm[(4 * k4 + fk) * TI_LD + 8 * n0 + fr];
+        const double b1 = Bm[(4 * k4 + fk) * TI_LD + 8 * (n0 + 1) + fr];
+        dmma_8x8x4(acc[0][0], acc[0][1], af, b0);
+        dmma_8x8x4(acc[1][0], acc[1][1], af, b1);
+      }
+      __syncthreads();
+    }
+    // S -> shared as a right operand, Y_I -> shared as the left one
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) Ssm[(8 * mi + fr) * TI_LD + 8 * (n0 + t) + 2 * fk + e] = acc[t][e];
+    stage();
+    __syncthreads();
+    if (I + 1 < nblk) fetch_L(I + 1, J);
+    double out[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+      const double af = Asm[(4 * k4 + fk) * TI_LD + 8 * mi + fr];
+      const double b0 = Ssm[(4 * k4 + fk) * TI_LD + 8 * n0 + fr];
+      const double b1 = Ssm[(4 * k4 + fk) * TI_LD + 8 * (n0 + 1) + fr];
+      dmma_8x8x4(out[0][0], out[0][1], af, b0);
+      dmma_8x8x4(out[1][0], out[1][1], af, b1);
+    }
+    double* Wb = Wsm + (size_t)(I - J) * TI_TILE;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = 8 * mi + fr, c = 8 * (n0 + t) + 2 * fk + e;
+        const double v = -out[t][e];
+        Wb[r * TI_LD + c] = v;
+        const int gi = 32 * I + r, gj = 32 * J + c;
+        if (gi < p && gj < p) W[(size_t)gi + (size_t)gj * p] = v;
+      }
+    __syncthreads();
   }
 }
 
