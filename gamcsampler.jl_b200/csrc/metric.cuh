@@ -166,7 +166,13 @@ k_reduce(double* __restrict__ E, int p, int goff,
     double s = 0.0;
     const double* src = ws + (size_t)task * max_nsplit * (MT_BLK * MT_BLK) + e;
     const int nsplit = task_nsplit[task];
-    for (int k = 0; k < nsplit; ++k) s += src[(size_t)k * (MT_BLK * MT_BLK)];
+    int k = 0;
+    for (; k + 4 <= nsplit; k += 4) {           // four independent loads in flight, added in split order (deterministic)
+      const double v0 = src[(size_t)k * (MT_BLK * MT_BLK)], v1 = src[(size_t)(k + 1) * (MT_BLK * MT_BLK)];
+      const double v2 = src[(size_t)(k + 2) * (MT_BLK * MT_BLK)], v3 = src[(size_t)(k + 3) * (MT_BLK * MT_BLK)];
+      s += v0; s += v1; s += v2; s += v3;
+    }
+    for (; k < nsplit; ++k) s += src[(size_t)k * (MT_BLK * MT_BLK)];
     double* G = E + goff;
     G[gi + (size_t)gj * p] = s;
     G[gj + (size_t)gi * p] = s;
@@ -183,7 +189,15 @@ k_reduce(double* __restrict__ E, int p, int goff,
   if (want_grad) {
     for (int j = threadIdx.x; j < p; j += blockDim.x) {
       double s = 0.0;
-      for (int k = 0; k < nparts; ++k) s += part_g[(size_t)k * part_g_stride + j];
+      int k = 0;
+      for (; k + 8 <= nparts; k += 8) {         // eight independent loads in flight, added in CTA order (deterministic)
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = part_g[(size_t)(k + u) * part_g_stride + j];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+      }
+      for (; k < nparts; ++k) s += part_g[(size_t)k * part_g_stride + j];
       E[1 + j] = s;
     }
   }
