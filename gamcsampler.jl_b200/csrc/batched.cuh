@@ -468,8 +468,11 @@ __device__ inline void rv_partial(const BatchedCfg& C, const double* th, const R
   const double offset = th[5 * NPL];
   long long e0 = tid;
   if (level < 2) {
-    // log-target only (AM steps): four independent epochs per trip
-    constexpr int U = 4;
+    // log-target only (AM steps): GAMC_RV_BATCH independent epochs per trip
+#ifndef GAMC_RV_BATCH
+#define GAMC_RV_BATCH 2     // measured at 4 CTAs/SM on C5: 1 -> 82.7 k, 2 -> 83.2 k, 4 -> 71.0 k chain-iterations/s
+#endif
+    constexpr int U = GAMC_RV_BATCH;
     for (; e0 + (long long)(U - 1) * nt < C.rv_n; e0 += (long long)U * nt) {
       double t[U], z[U];
 #pragma unroll

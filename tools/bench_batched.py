@@ -115,6 +115,11 @@ def main_rv(a, rng, torch):
     chains = job.output()
     acc = float(np.mean([c.diagnosticvalues.mean() for c in chains]))
     st, _ = eng.batched_state(0)
+    if a.cpu_steps == 0:     # --cpu-steps 0: device measurement only
+        print(json.dumps({"metric": "gamc_chain_iters_per_sec", "value": a.chains * a.steps / (ms * 1e-3), "unit": "chain-iters/s", "n_gpus": 1,
+                          "ms_total": ms, "steps": a.steps, "acceptance": acc, "epoch_evals_per_sec": a.chains * a.steps * N / (ms * 1e-3)}))
+        eng.close()
+        return
     # CPU oracle, one chain, a few transitions at full N
     om = T.RVModel(t, obs, sig)
     ncpu = 12
