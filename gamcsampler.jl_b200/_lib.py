@@ -92,6 +92,7 @@ SIGNATURES = {
     "gamc_target_logistic": (C.c_int, [_H, _DP, C.c_int64, _DP, C.c_int64, C.c_int32, C.c_double]),
     "gamc_target_logistic_device": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_double]),
     "gamc_target_logistic_synth": (C.c_int, [_H, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, _DP, C.c_double]),
+    "gamc_target_callback": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p]),
     "gamc_target_read_rows": (C.c_int, [_H, C.c_int64, C.c_int64, _DP, _DP]),
     "gamc_eval_logtarget": (C.c_int, [_H, _DP, _DP]),
     "gamc_eval_upto_tensor": (C.c_int, [_H, _DP, _DP, _DP, _DP]),
@@ -122,6 +123,11 @@ SIGNATURES = {
 }
 
 _lib = None
+
+
+# gamc_target_fn of include/gamc_b200.h
+TARGET_FN = C.CFUNCTYPE(C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                        C.POINTER(C.c_double), C.c_void_p)
 
 
 def load():

@@ -116,6 +116,9 @@ struct gamc_ctx {
   // peer landing: two reduced-evaluation buffers per rank, mapped by every peer; k_land sums them over NVLink (no NCCL on the step path)
   double* xR = nullptr; size_t xR_stride = 0; int xR_p = 0; double** d_peerR = nullptr; void* peerR_ptr[32] = {nullptr}; bool land_p2p = false;
   unsigned long long land_seq = 0;
+  // generic target: the host evaluates the model (gamc_target_callback)
+  long long launches_cb = 0;
+  gamc_target_fn cb = nullptr; void* cb_user = nullptr; double* cb_theta = nullptr; double* cb_R = nullptr;
   // profiling
   bool prof = false; std::vector<cudaEvent_t> ev0, ev1; std::vector<int> ev_family; int ev_used = 0;
   long long launches = 0;
@@ -213,6 +216,7 @@ void free_target(gamc_ctx* h) {
   cudaFree(h->d_plans); cudaFree(h->d_coords); cudaFree(h->ws); cudaFree(h->d_ints); h->d_plans = nullptr; h->d_coords = nullptr; h->ws = nullptr; h->d_ints = nullptr;
   cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0; h->R = nullptr; h->vecs = h->mats = nullptr; h->d_state = nullptr;
   cudaFree(h->theta_eval); h->theta_eval = nullptr;
+  cudaFreeHost(h->cb_theta); cudaFreeHost(h->cb_R); h->cb_theta = h->cb_R = nullptr; h->cb = nullptr; h->cb_user = nullptr;
 }
 
 void free_peer_landing(gamc_ctx* h) {
@@ -402,8 +406,24 @@ gamc_status launch_reduce(gamc_ctx* h, int level, double* E = nullptr) {
 }
 
 // Likelihood partial sums at a device-resident theta into the landing buffer R, then (multi-GPU) all-reduce.
+// Generic target: fetch theta, let the host evaluate, upload [lt, g, G] into the landing buffer (one round trip).
+gamc_status eval_callback(gamc_ctx* h, const double* d_theta, int level) {
+  const int p = h->p;
+  CUDA_TRY(h, cudaMemcpyAsync(h->cb_theta, d_theta, sizeof(double) * p, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  double lt = NAN;
+  const int rc = h->cb(h->cb_theta, p, level, &lt, h->cb_R + 1, h->cb_R + h->goff, h->cb_user);
+  if (rc != 0) { h->err = "target callback returned " + std::to_string(rc); return GAMC_INVALID_ARG; }
+  h->cb_R[0] = lt;
+  const size_t count = level == 0 ? 1 : (level == 1 ? (size_t)(1 + p) : (size_t)h->goff + (size_t)p * p);
+  CUDA_TRY(h, cudaMemcpyAsync(h->R, h->cb_R, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
+  h->launches_cb += 1;
+  return GAMC_OK;
+}
+
 // skip_reduce (level 0, single GPU only): leave the per-CTA partials for k_am_post to sum.
 gamc_status eval_device(gamc_ctx* h, const double* d_theta, int level, bool allreduce, bool skip_reduce = false) {
+  if (h->cb) return eval_callback(h, d_theta, level);
   gamc_status s = launch_datapass(h, d_theta, level >= 1);
   if (s != GAMC_OK) return s;
   if (skip_reduce && level == 0 && (!h->comm || h->p2p_ready)) return GAMC_OK;
@@ -433,6 +453,29 @@ __global__ void __launch_bounds__(256) k_eval_finish(double* R, int goff, const 
     const double lt = add_prior(R, goff, theta, p, lambda, red);
     if (threadIdx.x == 0) R[0] = lt;
   }
+}
+
+// Working set of the step kernels: [state | vectors | landing buffer R | p x p matrices], plus the evaluation point.
+gamc_status alloc_arena(gamc_ctx* h) {
+  const int p = h->p;
+  h->goff = (1 + p + 1) & ~1;  // G starts 16-byte aligned
+  {
+    const size_t pp = (size_t)p * p;
+    const size_t n_state = 64, n_vecs = ((size_t)20 * p + 16 + 15) & ~(size_t)15, n_R = ((size_t)h->goff + pp + 15) & ~(size_t)15, n_mats = 9 * pp + 2 * la_invd_doubles(p);
+    h->arena_bytes = sizeof(double) * (n_state + n_vecs + n_R + n_mats);
+    CUDA_TRY(h, cudaMalloc(&h->arena, h->arena_bytes));
+    CUDA_TRY(h, cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
+    double* base = reinterpret_cast<double*>(h->arena);
+    static_assert(sizeof(DevState) <= 64 * sizeof(double), "DevState must fit its arena slot");
+    h->d_state = reinterpret_cast<DevState*>(base);
+    h->vecs = base + n_state;
+    h->R = h->vecs + n_vecs;
+    h->mats = h->R + n_R;
+    apply_l2_policy(h);
+  }
+  CUDA_TRY(h, cudaMalloc(&h->theta_eval, sizeof(double) * p));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GAMC_OK;
 }
 
 gamc_status setup_target(gamc_ctx* h) {
@@ -478,25 +521,9 @@ gamc_status setup_target(gamc_ctx* h) {
   CUDA_TRY(h, cudaMalloc(&h->d_coords, sizeof(TaskCoord) * h->ntasks));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_coords, h->layout.coords.data(), sizeof(TaskCoord) * h->ntasks, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMalloc(&h->ws, sizeof(double) * (size_t)h->layout.max_nsplit * h->ntasks * MT_BLK * MT_BLK));
-  h->goff = (1 + p + 1) & ~1;  // G starts 16-byte aligned
-  {
-    const size_t pp = (size_t)p * p;
-    const size_t n_state = 64, n_vecs = ((size_t)20 * p + 16 + 15) & ~(size_t)15, n_R = ((size_t)h->goff + pp + 15) & ~(size_t)15, n_mats = 9 * pp + 2 * la_invd_doubles(p);
-    h->arena_bytes = sizeof(double) * (n_state + n_vecs + n_R + n_mats);
-    CUDA_TRY(h, cudaMalloc(&h->arena, h->arena_bytes));
-    CUDA_TRY(h, cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
-    double* base = reinterpret_cast<double*>(h->arena);
-    static_assert(sizeof(DevState) <= 64 * sizeof(double), "DevState must fit its arena slot");
-    h->d_state = reinterpret_cast<DevState*>(base);
-    h->vecs = base + n_state;
-    h->R = h->vecs + n_vecs;
-    h->mats = h->R + n_R;
-    apply_l2_policy(h);
-  }
-  CUDA_TRY(h, cudaMalloc(&h->theta_eval, sizeof(double) * p));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  return GAMC_OK;
+  return alloc_arena(h);
 }
+
 
 gamc_status check_device_error(gamc_ctx* h) {
   if (!h->B.st) return GAMC_OK;
@@ -765,6 +792,21 @@ gamc_status gamc_target_logistic_synth(gamc_handle h, uint64_t seed, int64_t row
   return setup_target(h);
 }
 
+gamc_status gamc_target_callback(gamc_handle h, int32_t p, gamc_target_fn fn, void* user) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, fn && p >= 1, GAMC_INVALID_ARG, "gamc_target_callback: bad argument");
+  REQUIRE(h, p <= 512, GAMC_UNSUPPORTED_SHAPE, "p must be in 1..512");
+  cudaSetDevice(h->device);
+  free_sampler(h); free_target(h);
+  h->N = 0; h->p = p; h->lambda = -1.0;   // lambda <= 0: the step kernels add no prior terms (the host's values are complete)
+  h->goff = (1 + p + 1) & ~1;
+  CUDA_TRY(h, cudaMallocHost(&h->cb_theta, sizeof(double) * p));
+  CUDA_TRY(h, cudaMallocHost(&h->cb_R, sizeof(double) * ((size_t)h->goff + (size_t)p * p)));
+  memset(h->cb_R, 0, sizeof(double) * ((size_t)h->goff + (size_t)p * p));
+  h->cb = fn; h->cb_user = user;
+  return alloc_arena(h);
+}
+
 gamc_status gamc_target_read_rows(gamc_handle h, int64_t r0, int64_t n, double* X_out, double* y_out) {
   if (!h) return GAMC_INVALID_ARG;
   REQUIRE(h, h->dX, GAMC_NOT_READY, "no target");
@@ -779,14 +821,14 @@ gamc_status gamc_target_read_rows(gamc_handle h, int64_t r0, int64_t n, double* 
 // ---- evaluation -------------------------------------------------------------------------------------
 static gamc_status eval_host(gamc_handle h, const double* theta, int level, bool reduce_and_prior, double* lt, double* grad, double* G) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->dX, GAMC_NOT_READY, "no target: call gamc_target_* first");
+  REQUIRE(h, h->dX || h->cb, GAMC_NOT_READY, "no target: call gamc_target_* first");
   REQUIRE(h, theta, GAMC_INVALID_ARG, "theta is null");
   cudaSetDevice(h->device);
   const int p = h->p;
   CUDA_TRY(h, cudaMemcpyAsync(h->theta_eval, theta, sizeof(double) * p, cudaMemcpyHostToDevice, h->stream));
   gamc_status s = eval_device(h, h->theta_eval, level, reduce_and_prior);
   if (s != GAMC_OK) return s;
-  if (reduce_and_prior) {
+  if (reduce_and_prior && !h->cb) {
     ProfScope ps(h, GAMC_K_LINALG);
     k_eval_finish<<<1, 256, 0, h->stream>>>(h->R, h->goff, h->theta_eval, p, h->lambda, level);
     CUDA_TRY(h, cudaGetLastError());
@@ -841,7 +883,7 @@ gamc_status gamc_comm_peer_path(gamc_handle h, int32_t* active) {
 // ---- sampler ----------------------------------------------------------------------------------------
 gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const double* theta0) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->dX, GAMC_NOT_READY, "no target: call gamc_target_* first");
+  REQUIRE(h, h->dX || h->cb, GAMC_NOT_READY, "no target: call gamc_target_* first");
   REQUIRE(h, cfg && theta0, GAMC_INVALID_ARG, "null argument");
   // GAMC inner constructor asserts (src/samplers/GAMC.jl:135-138)
   REQUIRE(h, cfg->driftstep > 0, GAMC_INVALID_ARG, "Drift step is not positive");
@@ -927,7 +969,7 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
 
 gamc_status gamc_tape_set(gamc_handle h, int64_t n, const double* u_sched, const double* u_mix, const double* z, const double* u_acc) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->dX, GAMC_NOT_READY, "no target");
+  REQUIRE(h, h->dX || h->cb, GAMC_NOT_READY, "no target");
   REQUIRE(h, n >= 1 && u_sched && u_mix && z && u_acc, GAMC_INVALID_ARG, "gamc_tape_set: bad argument");
   cudaSetDevice(h->device);
   gamc_status s = ensure_tape(h, n);
@@ -945,7 +987,7 @@ gamc_status gamc_tape_set(gamc_handle h, int64_t n, const double* u_sched, const
 
 gamc_status gamc_tape_generate(gamc_handle h, int64_t n, uint64_t seed) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->dX, GAMC_NOT_READY, "no target");
+  REQUIRE(h, h->dX || h->cb, GAMC_NOT_READY, "no target");
   REQUIRE(h, n >= 1, GAMC_INVALID_ARG, "gamc_tape_generate: n < 1");
   cudaSetDevice(h->device);
   gamc_status s = ensure_tape(h, n);
@@ -1046,7 +1088,7 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
         CUDA_TRY(h, cudaEventRecord(h->ev_side, h->side));
         h->dp_grid_now = std::max(1, h->dp_grid - 2);                                    // leave two SMs to the speculative CTAs
       }
-      const bool local_sum = !h->comm || h->p2p_ready;
+      const bool local_sum = (!h->comm || h->p2p_ready) && !h->cb;
       const int nparts_post = local_sum ? (h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid) : 0;
       PeerArgs pa{};
       if (h->comm && h->p2p_ready) { pa.peers = h->d_peers; pa.nranks = h->nranks; pa.rank = h->rank; pa.seq = ++h->p2p_seq; }

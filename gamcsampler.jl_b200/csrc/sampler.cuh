@@ -77,6 +77,7 @@ __device__ inline double log_prior(const double* theta, int p, double lambda, do
   double s = 0.0;
   for (int i = threadIdx.x; i < p; i += blockDim.x) s = fma(theta[i], theta[i], s);
   s = block_sum(s, red);
+  if (!(lambda > 0.0)) return 0.0;          // generic (callback) target: the host's values already contain the prior
   return -0.5 * (s / lambda + p * log(2.0 * 3.14159265358979323846 * lambda));
 }
 
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(LAND_THREADS) k_land(Bufs B, TuneCfg T, int mo
   const double* Gc = B.Gs + (size_t)cur * B.Gstride + (size_t)j * p;
   double* Gd = B.Gs + (size_t)slot * B.Gstride + (size_t)j * p;
   double* U = B.U + (size_t)slot * B.Ustride + (size_t)j * p;
-  const double ilam = 1.0 / T.lambda;
+  const double ilam = T.lambda > 0.0 ? 1.0 / T.lambda : 0.0;   // lambda <= 0: generic target, prior already included
   double nf = 0.0, q1 = 0.0, q2 = 0.0;
   for (int i = threadIdx.x; i < p; i += LAND_THREADS) {
     double v;
@@ -778,7 +779,7 @@ __global__ void __launch_bounds__(256) k_mala_init(Bufs B, TuneCfg T) {
   const double lp = log_prior(B.theta, p, T.lambda, red);
   double bad = 0.0;
   for (int i = threadIdx.x; i < p; i += blockDim.x) {
-    const double g = B.R[1 + i] - B.theta[i] / T.lambda;
+    const double g = B.R[1 + i] - (T.lambda > 0.0 ? B.theta[i] / T.lambda : 0.0);
     B.gs[i] = g;
     B.lastmean[i] = B.theta[i];
     if (!isfinite(g)) bad = 1.0;
@@ -814,7 +815,7 @@ __global__ void __launch_bounds__(256) k_mala_post(Bufs B, TuneCfg T, long long 
   const double lt_p = B.R[0] + log_prior(B.theta_prop, p, T.lambda, red);
   double q1 = 0.0, q2 = 0.0, bad = 0.0;
   for (int i = threadIdx.x; i < p; i += blockDim.x) {
-    const double gp = B.R[1 + i] - B.theta_prop[i] / T.lambda;
+    const double gp = B.R[1 + i] - (T.lambda > 0.0 ? B.theta_prop[i] / T.lambda : 0.0);
     B.gs[p + i] = gp;                                     // proposal-slot gradient
     if (!isfinite(gp)) bad = 1.0;
     const double d1 = B.theta_prop[i] - B.mu[i];

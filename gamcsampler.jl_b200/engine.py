@@ -69,6 +69,30 @@ class Engine:
         self._ck(self.lib.gamc_target_logistic_synth(self.h, int(seed), int(row0), int(nrows), int(p), L.dptr(tt), float(lam)))
         self.N, self.p = int(nrows), int(p)
 
+    def target_callback(self, p, fn):
+        """Generic target: `fn(theta, level) -> (logtarget, grad | None, G | None)` evaluated on the host for
+        levels 0 (log-target), 1 (+ gradient), 2 (+ metric tensor, already transformed).  The wrapper is kept alive here."""
+        p = int(p)
+
+        def _cb(theta_ptr, p_, level, lt_ptr, grad_ptr, G_ptr, _user):
+            try:
+                theta = np.ctypeslib.as_array(theta_ptr, shape=(p_,)).copy()
+                lt, grad, G = fn(theta, int(level))
+                lt_ptr[0] = float(lt)
+                if level >= 1:
+                    np.ctypeslib.as_array(grad_ptr, shape=(p_,))[:] = np.asarray(grad, dtype=np.float64).ravel()
+                if level >= 2:
+                    np.ctypeslib.as_array(G_ptr, shape=(p_ * p_,))[:] = np.asarray(G, dtype=np.float64).ravel(order="F")
+                return 0
+            except Exception:   # noqa: BLE001 -- an exception must not unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._target_cb = L.TARGET_FN(_cb)
+        self._ck(self.lib.gamc_target_callback(self.h, p, C.cast(self._target_cb, C.c_void_p), None))
+        self.N, self.p = 0, p
+
     def read_rows(self, r0, n):
         X = np.empty((n, self.p), dtype=np.float64, order="F")
         y = np.empty(n, dtype=np.float64)

@@ -28,7 +28,7 @@ __all__ = [
     "rand_lin_decay_update", "rand_pow_decay_update", "rand_quad_decay_update",
     "exp_decay", "lin_decay", "pow_decay", "quad_decay",
     "BasicMCRange", "LogisticModel", "BasicMCJob", "Chain", "run", "output", "acceptance", "RandomTape",
-    "synth_theta_true", "softabs", "Softabs", "MvTModel", "RVModel", "BatchedMCJob", "BatchedRandomTape",
+    "synth_theta_true", "softabs", "Softabs", "MvTModel", "RVModel", "BatchedMCJob", "BatchedRandomTape", "GenericModel",
 ]
 
 
@@ -167,9 +167,9 @@ class GAMC:
         assert 0 < minorscale, f"Constant minorscale must be positive, got {minorscale}"
         assert 0 <= c, "Constant c must be non-negative"
         assert t0 > 0, "t0 is not positive"
-        if transform is not None and not isinstance(transform, Softabs):
-            raise NotImplementedError("only transform=softabs(alpha) (Klara softabs, examples/t_distribution/src/GAMC/simulations.jl:39) "
-                                      "is available on the device; arbitrary host callbacks are not")
+        if transform is not None and not isinstance(transform, Softabs) and not callable(transform):
+            raise TypeError("transform must be softabs(alpha) or a callable H -> H' (the latter only with a GenericModel, whose "
+                            "metric is evaluated on the host)")
         self.update = update if update is not None else rand_update()
         self.transform = transform
         self.driftstep, self.minorscale, self.c, self.t0 = float(driftstep), float(minorscale), float(c), int(t0)
@@ -207,6 +207,26 @@ class LogisticModel:
     y: Optional[np.ndarray] = None
     lam: float = 100.0
     synth: Optional[dict] = None   # {"seed":..., "N":..., "p":..., "theta_true":..., "row0": 0, "nrows": N}
+
+
+@dataclass
+class GenericModel:
+    """An arbitrary model given by its Klara-style closures: `uptotensorlogtarget(theta) -> (logtarget, grad,
+    tensor)` (what `parameter.uptotensorlogtarget!` leaves in `pstate`, src/samplers/iterate/GAMC.jl:20,37) and, optionally,
+    `logtarget(theta)` (`parameter.logtarget!`, :148; defaults to the first component of `uptotensorlogtarget`).  The host
+    evaluates the model -- and the sampler's `transform` -- once per evaluation; the dense algebra, proposal, accept/reject,
+    means, tuner and chain run on the device (`gamc_target_callback`)."""
+    p: int
+    uptotensorlogtarget: object
+    logtarget: object = None
+
+
+def _softabs_host(H, alpha):
+    """Klara `softabs(H, alpha)` = Q diag(lambda coth(alpha lambda)) Q' (examples/t_distribution/src/GAMC/simulations.jl:39)."""
+    lam, Q = np.linalg.eigh(0.5 * (H + H.T))
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        s = np.where(np.abs(alpha * lam) < 1e-8, 1.0 / alpha, lam / np.tanh(alpha * lam))
+    return (Q * s) @ Q.T
 
 
 def synth_theta_true(seed, p):
@@ -319,7 +339,21 @@ class BasicMCJob:
         self.outopts = outopts or {"monitor": ["value"], "diagnostics": ["accept"]}
         self.engine = engine if engine is not None else Engine(device)
         eng = self.engine
-        if engine is None:
+        if isinstance(model, GenericModel):
+            tr = getattr(sampler, "transform", None)
+
+            def _eval(theta, level, _m=model, _tr=tr):
+                if level == 0 and _m.logtarget is not None:
+                    return float(_m.logtarget(theta)), None, None
+                lt, grad, G = _m.uptotensorlogtarget(theta)
+                if level >= 2 and _tr is not None:
+                    G = _softabs_host(np.asarray(G, dtype=np.float64), _tr.alpha) if isinstance(_tr, Softabs) else _tr(G)
+                return lt, grad, G
+
+            eng.target_callback(model.p, _eval)
+        elif callable(getattr(sampler, "transform", None)) and not isinstance(sampler.transform, Softabs):
+            raise NotImplementedError("a callable transform needs a GenericModel (the metric of the built-in targets never leaves the device)")
+        elif engine is None:
             if model.synth is not None:
                 s = model.synth
                 eng.target_logistic_synth(s["seed"], s.get("row0", 0), s.get("nrows", s["N"]), s["p"], s["theta_true"], model.lam)

@@ -155,6 +155,19 @@ gamc_status gamc_eval_upto_tensor(gamc_handle h, const double* theta, double* lo
  * (what the rank contributes to the reduction): ll, g_lik[p], G_lik[p x p]. */
 gamc_status gamc_eval_partials(gamc_handle h, const double* theta, double* ll, double* g_lik, double* G_lik);
 
+/* ---- generic target ----------------------------------------------------------------
+ * Replaces, for an arbitrary model, the Klara closures `parameter.logtarget!(pstate)` and
+ * `parameter.uptotensorlogtarget!(pstate)` called at src/samplers/iterate/GAMC.jl:20,37,148 and
+ * src/samplers/GAMC.jl:163: the HOST evaluates the model, the sampler's dense algebra, proposal, accept/reject,
+ * running means, tuner and chain stay on the device.  One host round trip per evaluation -- meant for the
+ * small-p examples and for checking models, not for the data-parallel path.
+ * fn(theta[p], p, level, &logtarget, grad[p], G[p*p], user): level 0 = log-target only, 1 = + gradient,
+ * 2 = + metric tensor (column-major, full symmetric, AFTER any `sampler.transform`, iterate/GAMC.jl:22-24,39-41).
+ * All values are those of the full log-target (prior included).  Return 0; anything else aborts the run with
+ * GAMC_INVALID_ARG.  Non-finite values at a proposal reject it, at the initial point raise GAMC_NONFINITE_INIT. */
+typedef int32_t (*gamc_target_fn)(const double* theta, int32_t p, int32_t level, double* logtarget, double* grad, double* G, void* user);
+gamc_status gamc_target_callback(gamc_handle h, int32_t p, gamc_target_fn fn, void* user);
+
 /* ---- multi-GPU: observations row-sharded, one process per GPU -------------------------
  * gamc_comm_unique_id fills a 128-byte NCCL unique id on one rank; the host side (torch.distributed /
  * MPI / Julia Distributed) broadcasts it; every rank then calls gamc_comm_init.  After that, every

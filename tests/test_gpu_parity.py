@@ -236,3 +236,53 @@ def test_speculative_am_is_bitwise_identical(gamc, engine):
     assert np.array_equal(out[0][0].diagnosticvalues, out[1][0].diagnosticvalues)
     assert out[0][1:4] == out[1][1:4]
     assert np.array_equal(out[0][4], out[1][4])
+
+
+@pytest.mark.parametrize("am_mode", [0, 2])
+def test_generic_target_callback_parity(gamc, engine, am_mode):
+    """an arbitrary model through `gamc_target_callback` -- the host evaluates the Klara-style closures
+    (here the t example with `transform = softabs(1000)`, examples/t_distribution/src/GAMC/simulations.jl:17-39), the
+    device runs everything else.  Step-for-step agreement with the oracle on the same tape."""
+    o = _oracle()
+    from oracle import targets as T
+    n, nsteps, burnin = 9, 1200, 200
+    tgt = T.TTarget(n, 30.0, 0.9)
+    theta0 = 0.3 * np.random.default_rng(7).standard_normal(n)
+    sampler = gamc.GAMC(update=gamc.rand_exp_decay_update(10.0), transform=gamc.softabs(1000.0), driftstep=0.02, minorscale=0.001, c=0.01,
+                        am_mode=am_mode)
+    tuner = gamc.GAMCTuner(gamc.VanillaMCTuner(), gamc.VanillaMCTuner(), gamc.AcceptanceRateMCTuner(0.35))
+    tape = gamc.RandomTape(nsteps, n, seed=11)
+    model = gamc.GenericModel(n, tgt.uptotensorlogtarget, tgt.logtarget)
+    job = gamc.BasicMCJob(model, sampler, gamc.BasicMCRange(nsteps, burnin), {"p": theta0}, tuner=tuner, tape=tape, engine=engine)
+    job.run()
+    chain = job.output()
+    otuner = o.GAMCTuner(o.VanillaMCTuner(), o.VanillaMCTuner(), o.AcceptanceRateMCTuner(0.35))
+    osam = o.GAMCOracle(tgt, theta0, nsteps, burnin, update="rand_exp_decay_update!", update_params=(10.0, 0.0),
+                        transform=lambda H: T.softabs(H, 1000.0), driftstep=0.02, minorscale=0.001, c=0.01, tuner=otuner)
+    v, a, k = osam.run(o.RandomTape(nsteps, n, seed=11))
+    assert np.array_equal(chain.diagnosticvalues.ravel(), a), "accept/reject decisions diverged"
+    assert relerr(chain.value, v) <= 1e-8
+    st = job.engine.state()
+    assert st.updatetensorcount == osam.updatetensorcount
+    # a callable transform is applied on the host as well
+    sampler2 = gamc.GAMC(update=gamc.smmala_only_update(), transform=lambda H: T.softabs(H, 1000.0), driftstep=0.02, minorscale=0.001, c=0.01)
+    job2 = gamc.BasicMCJob(model, sampler2, gamc.BasicMCRange(50, 0), {"p": theta0}, tuner=tuner, tape=gamc.RandomTape(50, n, seed=12), engine=engine)
+    job2.run()
+    osam2 = o.GAMCOracle(tgt, theta0, 50, 0, update="smmala_only_update!", update_params=(), transform=lambda H: T.softabs(H, 1000.0),
+                         driftstep=0.02, minorscale=0.001, c=0.01, tuner=o.GAMCTuner(o.VanillaMCTuner(), o.VanillaMCTuner(), o.AcceptanceRateMCTuner(0.35)))
+    v2, a2, _ = osam2.run(o.RandomTape(50, n, seed=12))
+    assert np.array_equal(job2.output().diagnosticvalues.ravel(), a2)
+    assert relerr(job2.output().value, v2) <= 1e-8
+
+
+def test_generic_target_callback_errors(gamc, engine):
+    """A non-finite initial point raises the reference's initialisation error; a failing callback aborts the call."""
+    sampler, tuner, rng_ = example_config(gamc, 10, 0)
+    bad = gamc.GenericModel(3, lambda th: (float("nan"), np.zeros(3), np.eye(3)))
+    with pytest.raises(gamc._lib.NonFiniteInitError):
+        gamc.BasicMCJob(bad, sampler, rng_, {"p": np.zeros(3)}, tuner=tuner, tape=gamc.RandomTape(10, 3, seed=1), engine=engine)
+
+    def boom(th):
+        raise RuntimeError("model failure")
+    with pytest.raises(AssertionError, match="callback"):
+        gamc.BasicMCJob(gamc.GenericModel(3, boom), sampler, rng_, {"p": np.zeros(3)}, tuner=tuner, tape=gamc.RandomTape(10, 3, seed=1), engine=engine)
