@@ -29,6 +29,7 @@ __all__ = [
     "exp_decay", "lin_decay", "pow_decay", "quad_decay",
     "BasicMCRange", "LogisticModel", "BasicMCJob", "Chain", "run", "output", "acceptance", "RandomTape",
     "synth_theta_true", "softabs", "Softabs", "MvTModel", "RVModel", "BatchedMCJob", "BatchedRandomTape", "GenericModel",
+    "make_param_true_ex1", "make_param_true_ex2", "rv_model_velocity",
 ]
 
 
@@ -432,6 +433,71 @@ class RVModel:
     obs: np.ndarray
     sigma_obs: np.ndarray
     nplanets: int = 1
+
+    @classmethod
+    def from_csv(cls, path, nplanets=1):
+        """The reference's data files (`examples/radial_velocity/data/one_planet.csv`: rows `time,obs,sigma_obs`, written by
+        `writedlm(..., zip(times, obs, sigma_obs), ',')`, one_planet/data_generation.jl:30-34)."""
+        d = np.loadtxt(path, delimiter=",", ndmin=2)
+        return cls(d[:, 0].copy(), d[:, 1].copy(), d[:, 2].copy(), nplanets)
+
+    def to_csv(self, path):
+        np.savetxt(path, np.column_stack([self.times, self.obs, self.sigma_obs]), delimiter=",", fmt="%.17g")
+
+    @classmethod
+    def simulate(cls, param_true, num_obs=50, observation_timespan=2 * 365.25, sigma_obs_scalar=2.0, seed=42):
+        """`data_generation.jl` of the one- and two-planet examples (:13-28): epochs = timespan * sort(rand(num_obs)), observations =
+        true model + sigma * randn (the jitter term is switched off in the reference, `num_jitters = 0`, rv_model_param.jl:5).
+        Julia's `srand(42)` stream is not reproducible here; NumPy PCG64(seed) stands in."""
+        rng = np.random.Generator(np.random.PCG64(seed))
+        param_true = np.asarray(param_true, dtype=np.float64)
+        times = observation_timespan * np.sort(rng.random(num_obs))
+        sigma = sigma_obs_scalar * np.ones(num_obs)
+        obs = rv_model_velocity(param_true, times) + sigma_obs_scalar * rng.standard_normal(num_obs)
+        return cls(times, obs, sigma, len(param_true) // 5)
+
+
+def make_param_true_ex1():
+    """One-planet truth of utils_ex.jl:48-57 packed as rv_model_param.jl:19-44: [log1p(P), log1p(K), e cos w, e sin w, w + M0, C]."""
+    P, K, e, w, M0, C = 50.0, 20.0, 0.2, math.pi / 4, math.pi / 4, 1.0
+    return np.array([math.log1p(P), math.log1p(K), e * math.cos(w), e * math.sin(w), w + M0, C])
+
+
+def make_param_true_ex2():
+    """Two-planet truth of utils_ex.jl:59-68."""
+    out = []
+    for P, K in ((40.0, 30.0), (80.8, 30.0)):
+        e, w, M0 = 0.2, math.pi / 4, math.pi / 4
+        out += [math.log1p(P), math.log1p(K), e * math.cos(w), e * math.sin(w), w + M0]
+    return np.array(out + [0.0])
+
+
+def rv_model_velocity(theta, times):
+    """`calc_model_rv` (rv_model_keplerian.jl:9-51) on the host, for data generation only: sum over planets of the Keplerian
+    velocity K j / (1 - e cos E) [cos(w + M + e sin E) - k e cos E / (1 + j)], j = sqrt(1 - e^2), plus the offset; Kepler's
+    equation by Newton iterations from the Danby guess (kepler_eqn.jl:18-23) to machine precision."""
+    theta = np.asarray(theta, dtype=np.float64)
+    t = np.asarray(times, dtype=np.float64)
+    npl = len(theta) // 5
+    z = np.zeros_like(t)
+    for pl in range(npl):
+        P, K = math.expm1(theta[5 * pl]), math.expm1(theta[5 * pl + 1])
+        h, k = theta[5 * pl + 2], theta[5 * pl + 3]
+        ecc, w = math.hypot(h, k), math.atan2(k, h)
+        if not ecc < 1.0:
+            raise ValueError("eccentricity must be below one (rv_model_param.jl:83-96)")
+        M = t * (2.0 * math.pi / P) - (theta[5 * pl + 4] - w)
+        Mr = np.mod(M, 2.0 * math.pi)
+        E = np.where(Mr < math.pi, Mr + 0.85 * ecc, Mr - 0.85 * ecc)
+        for _ in range(60):
+            dE = (E - ecc * np.sin(E) - Mr) / (1.0 - ecc * np.cos(E))
+            E = E - dE
+            if np.max(np.abs(dE)) < 1e-15:
+                break
+        j = math.sqrt((1.0 - ecc) * (1.0 + ecc))
+        q = ecc * np.cos(E)
+        z = z + K * j / (1.0 - q) * (np.cos(w + M + ecc * np.sin(E)) - k * q / (1.0 + j))
+    return z + theta[5 * npl]
 
 
 class BatchedRandomTape:

@@ -154,3 +154,24 @@ def test_csv_pipeline_roundtrip(gamc, tmp_path):
     assert np.array_equal(np.loadtxt(os.path.join(d, "chain02.csv"), delimiter=","), chains[1])
     assert open(os.path.join(d, "diagnostics01.csv")).readline().strip() in ("true", "false")
     assert len(open(os.path.join(d, "summary.txt")).read().split(" & ")) == 1 + 4 + 2
+
+
+def test_rv_data_generation_and_csv(tmp_path):
+    """the front-end's host-side Keplerian forward model (data generation only), the reference's truth vectors
+    (utils_ex.jl:48-68) and its `time,obs,sigma` CSV format, against the oracle and the reference's shipped data file."""
+    import gamc_b200 as g
+    from oracle import targets as T
+    for mine, ref in ((g.make_param_true_ex1(), T.make_param_true_ex1()), (g.make_param_true_ex2(), T.make_param_true_ex2())):
+        assert np.array_equal(mine, ref)
+        m = g.RVModel.simulate(mine, num_obs=300, seed=5)
+        assert m.nplanets == len(mine) // 5 and np.all(np.diff(m.times) >= 0) and m.times.max() <= 730.5
+        v = g.rv_model_velocity(mine, m.times)
+        assert np.max(np.abs(v - T.RVModel(m.times, m.obs, m.sigma_obs).model_rv(ref))) <= 1e-12
+        resid = (m.obs - v) / m.sigma_obs
+        assert 0.85 < resid.std() < 1.15 and abs(resid.mean()) < 0.2          # obs = model + sigma * N(0, 1)
+        path = tmp_path / "rv.csv"
+        m.to_csv(path)
+        back = g.RVModel.from_csv(path, m.nplanets)
+        assert np.array_equal(back.times, m.times) and np.array_equal(back.obs, m.obs) and np.array_equal(back.sigma_obs, m.sigma_obs)
+    with pytest.raises(ValueError):
+        g.rv_model_velocity(np.array([3.0, 3.0, 0.8, 0.8, 1.0, 0.0]), np.array([1.0]))
