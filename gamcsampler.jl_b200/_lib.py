@@ -59,6 +59,7 @@ class Config(C.Structure):
         ("total_tuner_kind", C.c_int32), ("targetrate", C.c_double), ("score_k", C.c_double),
         ("period", C.c_int32), ("verbose_total", C.c_int32), ("verbose_smmala", C.c_int32), ("verbose_am", C.c_int32),
         ("nsteps", C.c_int64), ("burnin", C.c_int64), ("am_mode", C.c_int32), ("sampler_kind", C.c_int32),
+        ("reuse_tensor", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

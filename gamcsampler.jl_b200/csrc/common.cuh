@@ -52,6 +52,7 @@ struct DevState {
   double mix_scratch;
   int lcur;           // which of the three AM factor buffers holds chol(C) (am_mode 2 rotates them; otherwise 0)
   int spec_err[2];    // speculative factor update of outcome 0 (accept) / 1 (reject) failed
+  int tensor_valid;   // slot `cur` (gradient, metric, factor, G^-1 grad) belongs to the current point: no AM accept since it was filled
 };
 
 // Tuner / range constants handed to the step kernels by value.
@@ -67,6 +68,7 @@ struct TuneCfg {
   double lambda;     // prior variance of the logistic target
   int p;
   int am_mode;
+  int reuse_tensor;  // gamc_config.reuse_tensor
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -40,7 +40,8 @@ template <int NU, int RPL, bool GRAD>
 __global__ void __launch_bounds__(DP_THREADS, 1)
 k_datapass(const __grid_constant__ CUtensorMap mapX, const double* __restrict__ y,
            const double* __restrict__ theta, int p, long long N, double* __restrict__ w_out,
-           double* __restrict__ part_ll, double* __restrict__ part_g, int part_g_stride) {
+           double* __restrict__ part_ll, double* __restrict__ part_g, int part_g_stride, const int* skip_flag) {
+  if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;   // gamc_config.reuse_tensor: nothing to recompute
   constexpr int RB = 32 * RPL;
   constexpr int CU = 64 / RPL;
   constexpr int CPW = CU / DP_CONSUMER_WARPS;  // columns per warp per unit

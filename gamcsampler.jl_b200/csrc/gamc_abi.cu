@@ -353,54 +353,54 @@ void apply_l2_policy(gamc_ctx* h) {
 
 // ---- data-pass dispatch -----------------------------------------------------------------------------
 template <int NU, int RPL, bool GRAD>
-gamc_status launch_dp_t(gamc_ctx* h, const double* theta) {
+gamc_status launch_dp_t(gamc_ctx* h, const double* theta, const int* skip) {
   const int grid = h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid;
   auto kern = k_datapass<NU, RPL, GRAD>;
   { gamc_status s = ensure_attr(h, (const void*)kern, sizeof(DataPassSmem)); if (s != GAMC_OK) return s; }
   ProfScope ps(h, GRAD ? GAMC_K_LOGLIK_GRAD : GAMC_K_LOGLIK);
   DEBUG_POINT(h, "before datapass");
   kern<<<grid, DP_THREADS, sizeof(DataPassSmem), h->stream>>>(h->mapXA, h->dy, theta, h->p, h->N, h->dw, h->part_ll,
-                                                                    h->part_g, h->part_g_stride);
+                                                                    h->part_g, h->part_g_stride, skip);
   CUDA_TRY(h, cudaGetLastError());
   DEBUG_POINT(h, "after datapass");
   return GAMC_OK;
 }
 
 template <int RPL, bool GRAD>
-gamc_status launch_dp_nu(gamc_ctx* h, const double* theta) {
+gamc_status launch_dp_nu(gamc_ctx* h, const double* theta, const int* skip) {
   switch (h->dp_nu) {
-    case 1: return launch_dp_t<1, RPL, GRAD>(h, theta);
-    case 2: return launch_dp_t<2, RPL, GRAD>(h, theta);
-    case 3: return launch_dp_t<3, RPL, GRAD>(h, theta);
-    case 4: return launch_dp_t<4, RPL, GRAD>(h, theta);
-    case 5: return launch_dp_t<5, RPL, GRAD>(h, theta);
-    case 6: return launch_dp_t<6, RPL, GRAD>(h, theta);
-    case 7: return launch_dp_t<7, RPL, GRAD>(h, theta);
-    case 8: return launch_dp_t<8, RPL, GRAD>(h, theta);
+    case 1: return launch_dp_t<1, RPL, GRAD>(h, theta, skip);
+    case 2: return launch_dp_t<2, RPL, GRAD>(h, theta, skip);
+    case 3: return launch_dp_t<3, RPL, GRAD>(h, theta, skip);
+    case 4: return launch_dp_t<4, RPL, GRAD>(h, theta, skip);
+    case 5: return launch_dp_t<5, RPL, GRAD>(h, theta, skip);
+    case 6: return launch_dp_t<6, RPL, GRAD>(h, theta, skip);
+    case 7: return launch_dp_t<7, RPL, GRAD>(h, theta, skip);
+    case 8: return launch_dp_t<8, RPL, GRAD>(h, theta, skip);
     default: h->err = "unsupported number of column units"; return GAMC_UNSUPPORTED_SHAPE;
   }
 }
 
-gamc_status launch_datapass(gamc_ctx* h, const double* theta, bool grad) {
-  if (h->dp_rpl == 2) return grad ? launch_dp_nu<2, true>(h, theta) : launch_dp_nu<2, false>(h, theta);
-  return grad ? launch_dp_nu<1, true>(h, theta) : launch_dp_nu<1, false>(h, theta);
+gamc_status launch_datapass(gamc_ctx* h, const double* theta, bool grad, const int* skip = nullptr) {
+  if (h->dp_rpl == 2) return grad ? launch_dp_nu<2, true>(h, theta, skip) : launch_dp_nu<2, false>(h, theta, skip);
+  return grad ? launch_dp_nu<1, true>(h, theta, skip) : launch_dp_nu<1, false>(h, theta, skip);
 }
 
-gamc_status launch_metric(gamc_ctx* h) {
+gamc_status launch_metric(gamc_ctx* h, const int* skip = nullptr) {
   { gamc_status s = ensure_attr(h, (const void*)k_metric, sizeof(MetricSmem)); if (s != GAMC_OK) return s; }
   ProfScope ps(h, GAMC_K_METRIC);
   k_metric<<<h->metric_grid, MT_THREADS, sizeof(MetricSmem), h->stream>>>(h->mapXB, h->mapW, h->d_plans, h->d_cta_kind, h->d_cta_split,
-                                                                        h->d_kind_nsplit, h->nslabs, h->ws, h->layout.max_nsplit);
+                                                                        h->d_kind_nsplit, h->nslabs, h->ws, h->layout.max_nsplit, skip);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
 }
 
 // level: 0 = ll, 1 = ll + grad, 2 = ll + grad + metric
-gamc_status launch_reduce(gamc_ctx* h, int level, double* E = nullptr) {
+gamc_status launch_reduce(gamc_ctx* h, int level, double* E = nullptr, const int* skip = nullptr) {
   ProfScope ps(h, GAMC_K_REDUCE);
   const int nblk = (level >= 2 ? h->ntasks * 4 : 0) + 1;
   k_reduce<<<nblk, 256, 0, h->stream>>>(E ? E : h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid, level >= 1,
-                                        level >= 2 ? h->ws : nullptr, h->d_coords, h->ntasks, h->d_task_nsplit, h->layout.max_nsplit);
+                                        level >= 2 ? h->ws : nullptr, h->d_coords, h->ntasks, h->d_task_nsplit, h->layout.max_nsplit, skip);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
 }
@@ -575,6 +575,18 @@ gamc_status launch_land(gamc_ctx* h, int mode) {
 // Level-2 evaluation at a device-resident theta, landed into its slot.  With peer landing the reduced buffers stay where
 // they are and k_land adds them up over NVLink; otherwise NCCL all-reduces R first.
 gamc_status eval_and_land(gamc_ctx* h, const double* d_theta, int mode) {
+  if (mode == 1 && h->tune.reuse_tensor && !h->comm && !h->cb) {
+    // gamc_config.reuse_tensor: every kernel of the re-evaluation returns at once if no AM proposal was accepted since the
+    // slot was filled (device flag; the host never synchronises)
+    const int* skip = &h->d_state->tensor_valid;
+    gamc_status s = launch_datapass(h, d_theta, true, skip);
+    if (s != GAMC_OK) return s;
+    s = launch_metric(h, skip);
+    if (s != GAMC_OK) return s;
+    s = launch_reduce(h, 2, nullptr, skip);
+    if (s != GAMC_OK) return s;
+    return launch_land(h, mode);
+  }
   if (!h->land_p2p) {
     gamc_status s = eval_device(h, d_theta, 2, true);
     if (s != GAMC_OK) return s;
@@ -912,6 +924,7 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   T.targetrate = cfg->targetrate; T.score_k = cfg->score_k;
   T.minorscale = cfg->minorscale; T.sqrtminorscale = sqrt(cfg->minorscale); T.c = cfg->c;
   T.lambda = h->lambda; T.p = p; T.am_mode = cfg->am_mode;
+  T.reuse_tensor = (cfg->reuse_tensor && !h->comm && !h->cb) ? 1 : 0;
 
   Bufs& B = h->B;
   B = Bufs{};

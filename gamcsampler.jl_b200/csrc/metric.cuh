@@ -71,7 +71,8 @@ __device__ __forceinline__ void metric_slab(const double* __restrict__ A, const 
 __global__ void __launch_bounds__(MT_THREADS, 1)
 k_metric(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
          const MetricPlan* __restrict__ plans, const int* __restrict__ cta_kind, const int* __restrict__ cta_split,
-         const int* __restrict__ kind_nsplit, long long nslabs, double* __restrict__ ws, int max_nsplit) {
+         const int* __restrict__ kind_nsplit, long long nslabs, double* __restrict__ ws, int max_nsplit, const int* skip_flag) {
+  if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;   // gamc_config.reuse_tensor
   extern __shared__ __align__(128) unsigned char smem_raw[];
   MetricSmem& S = *reinterpret_cast<MetricSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -153,7 +154,8 @@ __global__ void __launch_bounds__(256)
 k_reduce(double* __restrict__ E, int p, int goff,
          const double* __restrict__ part_ll, const double* __restrict__ part_g, int part_g_stride, int nparts,
          int want_grad, const double* __restrict__ ws, const TaskCoord* __restrict__ coords, int ntasks,
-         const int* __restrict__ task_nsplit, int max_nsplit) {
+         const int* __restrict__ task_nsplit, int max_nsplit, const int* skip_flag) {
+  if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;
   const int nblk_tensor = ws ? ntasks * 4 : 0;  // 256 threads per block, 1024 elements per task
   if ((int)blockIdx.x < nblk_tensor) {
     const int task = blockIdx.x >> 2;

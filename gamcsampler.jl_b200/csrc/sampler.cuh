@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(LAND_THREADS) k_land(Bufs B, TuneCfg T, int mo
   __shared__ double red[40];
   DevState* st = B.st;
   if (st->error_flag) return;
+  if (mode == 1 && T.reuse_tensor && st->tensor_valid) return;   // the evaluation was skipped: slot `cur` is still current
   const int p = T.p, j = blockIdx.x;
   const int nr = lp.nranks > 1 ? lp.nranks : 1;
   if (nr > 1) {
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_sampler_init(Bufs B, TuneCfg 
   const int bad = factor_slot(B, 0, p, S);
   if (bad) { raise_error(st, 3 /*GAMC_NOT_POSDEF*/, p + 1 - bad); return; }
   for (int i = threadIdx.x; i < p; i += blockDim.x) B.lastmean[i] = B.theta[i];   // GAMC.jl:218
-  if (threadIdx.x == 0) { st->logtarget = lt; st->cur = 0; }
+  if (threadIdx.x == 0) { st->logtarget = lt; st->cur = 0; st->tensor_valid = 1; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -298,10 +299,13 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_smmala_pre(Bufs B, TuneCfg T,
     if (T.verbose_sm) st->sm_prop += 1;               // :15-17
   }
   GAMC_PHASE_BEGIN();
-  if (refactor) {                                     // :19-31 (previous step was AM: grad/metric stale)
+  const int still_valid = T.reuse_tensor && st->tensor_valid;   // gamc_config.reuse_tensor: the re-evaluation was skipped on the device
+  __syncthreads();
+  if (refactor && !still_valid) {                     // :19-31 (previous step was AM: grad/metric stale)
     if (threadIdx.x == 0) st->logtarget = B.land[3 * p];   // k_land(mode 1) ran on the re-evaluation at theta
     const int bad = factor_slot(B, cur, p, S);
     if (bad) { raise_error(st, 3, p + 1 - bad); return; }
+    if (threadIdx.x == 0) st->tensor_valid = 1;
   }
   __syncthreads();
   GAMC_PHASE(refactor ? 32 : 33);
@@ -738,6 +742,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, lo
     st->ratio = ratio;
     if (accept) {
       st->logtarget = lt_p;                                                             // :161
+      st->tensor_valid = 0;                    // gradient / metric of the slot now belong to an older point
       if (T.count_total) st->tot_acc += 1;
       if (T.verbose_am) st->am_acc += 1;
     }

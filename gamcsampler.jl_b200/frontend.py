@@ -163,7 +163,7 @@ class GAMC:
     """`GAMC(; update=rand_update!, transform=nothing, driftstep=1., minorscale=1., c=0.05, t0=3)`."""
 
     def __init__(self, update: Optional[Schedule] = None, transform=None, driftstep=1.0, minorscale=1.0, c=0.05, t0=3,
-                 am_mode=0):
+                 am_mode=0, reuse_tensor=False):
         assert driftstep > 0, "Drift step is not positive"
         assert 0 < minorscale, f"Constant minorscale must be positive, got {minorscale}"
         assert 0 <= c, "Constant c must be non-negative"
@@ -175,6 +175,7 @@ class GAMC:
         self.transform = transform
         self.driftstep, self.minorscale, self.c, self.t0 = float(driftstep), float(minorscale), float(c), int(t0)
         self.am_mode = int(am_mode)
+        self.reuse_tensor = bool(reuse_tensor)    # skip the re-evaluation at an unchanged current point (gamc_config.reuse_tensor)
 
     def __repr__(self):
         return (f"GAMC sampler: drift step = {self.driftstep}, scaling of stabilizing covariance = {self.minorscale}, "
@@ -278,6 +279,7 @@ def make_config(sampler, tuner, mcrange: BasicMCRange) -> L.Config:
     cfg.verbose_am = int(bool(tuner.amtuner.verbose))
     cfg.nsteps, cfg.burnin = int(mcrange.nsteps), int(mcrange.burnin)
     cfg.am_mode = sampler.am_mode
+    cfg.reuse_tensor = int(getattr(sampler, "reuse_tensor", False))
     return cfg
 
 

@@ -113,6 +113,7 @@ struct CConfig
   period::Int32; verbose_total::Int32; verbose_smmala::Int32; verbose_am::Int32
   nsteps::Int64; burnin::Int64
   am_mode::Int32; sampler_kind::Int32
+  reuse_tensor::Int32; reserved_::Int32
 end
 struct CState
   count::Int64; updatetensorcount::Int64; step::Cdouble; sqrttunestep::Cdouble
@@ -129,7 +130,7 @@ function cconfig(s::GAMC, t::GAMCTuner, r::BasicMCRange; am_mode::Integer=1)
   isacc = tt isa AcceptanceRateMCTuner
   CConfig(s.driftstep, s.minorscale, s.c, s.t0, s.update!.kind, s.update!.params, isacc ? 1 : 0,
           isacc ? tt.targetrate : NaN, isacc ? tt.score_k : 7., tt.period, tt.verbose, t.smmalatuner.verbose, t.amtuner.verbose,
-          r.nsteps, r.burnin, am_mode, 0)
+          r.nsteps, r.burnin, am_mode, 0, 0, 0)
 end
 
 # ---- model + job (examples/logistic_regression/src/GAMC/simulations.jl:39-48,71-77) --------------------------------

@@ -76,6 +76,13 @@ typedef struct {
                                   the data pass runs (bit-identical chain, shorter critical path)  */
   int32_t sampler_kind;    /* 0 = GAMC, 1 = MALA (Klara's comparison sampler, examples/logistic_regression/src/MALA/simulations.jl:37;
                               identity metric: only driftstep, the total tuner and the range are used)          */
+  int32_t reuse_tensor;    /* 0 = literal: an SMMALA step that follows an AM step always re-evaluates gradient and metric at
+                              the current point (src/samplers/iterate/GAMC.jl:19-31);
+                              1 = skip that re-evaluation (on the device, no host round trip) when no AM proposal has been
+                                  accepted since they were last computed: same inputs, deterministic kernels, so the chain is
+                                  bit-identical (tested) -- an optimisation the reference does not have; off by default and
+                                  never part of bench.py's headline value; single-GPU jobs only                      */
+  int32_t reserved_;       /* keep zero */
 } gamc_config;
 
 /* Snapshot of the scalar sampler state: fields of MuvGAMCState / GAMCTune that the reference exposes

@@ -286,3 +286,25 @@ def test_generic_target_callback_errors(gamc, engine):
         raise RuntimeError("model failure")
     with pytest.raises(AssertionError, match="callback"):
         gamc.BasicMCJob(gamc.GenericModel(3, boom), sampler, rng_, {"p": np.zeros(3)}, tuner=tuner, tape=gamc.RandomTape(10, 3, seed=1), engine=engine)
+
+
+def test_reuse_tensor_is_bitwise_identical(gamc, engine):
+    """gamc_config.reuse_tensor: skipping the re-evaluation of gradient and metric at a current point that no AM step has
+    moved (src/samplers/iterate/GAMC.jl:19-31 always re-evaluates) must not change a single bit of the chain."""
+    o = _oracle()
+    N, p, nsteps = 3000, 40, 900
+    X, y, tt = o.synth_logistic(5, N, p)
+    theta0 = tt + 0.05 * np.random.default_rng(2).standard_normal(p)
+    engine.target_logistic(X, y, 100.0)
+    out = []
+    for reuse in (False, True):
+        sampler = gamc.GAMC(update=gamc.rand_exp_decay_update(10.0), driftstep=0.02, minorscale=0.001, c=0.01, am_mode=2, reuse_tensor=reuse)
+        tuner = gamc.GAMCTuner(gamc.VanillaMCTuner(), gamc.VanillaMCTuner(), gamc.AcceptanceRateMCTuner(0.35))
+        job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, gamc.BasicMCRange(nsteps, 0), {"p": theta0}, tuner=tuner,
+                              tape=gamc.RandomTape(nsteps, p, seed=8), engine=engine)
+        job.run()
+        c = job.output()
+        st = job.engine.state()
+        out.append((c.value.copy(), c.diagnosticvalues.copy(), st.logtarget, st.step, st.updatetensorcount))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[0][2:] == out[1][2:]
