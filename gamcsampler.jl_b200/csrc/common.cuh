@@ -71,6 +71,10 @@ struct TuneCfg {
   int reuse_tensor;  // gamc_config.reuse_tensor
 };
 
+// Warm the L1 line of a global address this CTA will read later in the kernel (the single-CTA step kernels are chains of
+// dependent L2 round trips; issuing them together at the top collapses them into one).
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // ---------------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------------

@@ -692,6 +692,12 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, lo
   DevState* st = B.st;
   const int p = T.p;
   if (st->error_flag) return;
+  // everything this kernel reads later, requested now: one L2 round trip instead of five dependent ones
+  for (int i = threadIdx.x * 16; i < p; i += blockDim.x * 16) {      // one request per 128-byte line
+    prefetch_l1(B.theta_prop + i); prefetch_l1(B.theta + i); prefetch_l1(B.lastmean + i);
+    if (next_spec) { prefetch_l1(B.accbuf + i); prefetch_l1(B.accbuf + p + i); prefetch_l1(B.tape_z + (size_t)(tape_idx + 1) * p + i); }
+  }
+  if (threadIdx.x == 0) { prefetch_l1(B.tape_uacc + tape_idx); if (next_spec) prefetch_l1(B.tape_umix + tape_idx + 1); }
   if (nparts > 0) {
     if (threadIdx.x < 32) {
       double s = 0.0;
