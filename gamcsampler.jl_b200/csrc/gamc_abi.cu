@@ -280,6 +280,8 @@ void setup_peer_landing(gamc_ctx* h) {
 // ncclAllGather; the gather also orders every rank's zero-fill before any peer write.  GAMC_NO_P2P=1 disables the path.
 void setup_peer_mailboxes(gamc_ctx* h) {
   h->p2p_ready = false;
+  for (int r = 0; r < 32; ++r) { if (h->peer_ptr[r] && h->peer_ptr[r] != (void*)h->mbox) cudaIpcCloseMemHandle(h->peer_ptr[r]); h->peer_ptr[r] = nullptr; }
+  cudaFree(h->mbox); cudaFree(h->d_peers); h->mbox = nullptr; h->d_peers = nullptr;      // a second gamc_comm_init starts afresh
   if (getenv("GAMC_NO_P2P") || h->nranks < 2 || h->nranks > 32 || !g_nccl.AllGather) return;
   const int n = h->nranks;
   unsigned char* d_handles = nullptr;
@@ -877,6 +879,12 @@ gamc_status gamc_comm_init(gamc_handle h, const uint8_t id[128], int32_t nranks,
   REQUIRE(h, id && nranks >= 1 && rank >= 0 && rank < nranks, GAMC_INVALID_ARG, "gamc_comm_init: bad argument");
   if (!g_nccl.load(h->err)) return GAMC_NCCL_ERROR;
   cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->comm) {                     // re-initialisation: drop the previous communicator and its peer mappings
+    free_peer_landing(h);
+    if (g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
   NcclUniqueId uid;
   memcpy(uid.internal, id, 128);
   int r = g_nccl.CommInitRank(&h->comm, nranks, uid, rank);
