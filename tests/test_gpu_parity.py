@@ -140,7 +140,7 @@ def test_state_arrays_parity(gamc, engine):
     assert relerr(eng.array(1), osam.grad) <= 1e-10
 
 
-@pytest.mark.parametrize("N,p,nsteps", [(400, 12, 25), (3000, 130, 12), (6000, 256, 9)])
+@pytest.mark.parametrize("N,p,nsteps", [(400, 12, 25), (1500, 95, 10), (3000, 130, 12), (6000, 256, 9), (5000, 257, 6), (6000, 479, 4)])
 def test_smmala_ratio_parity(gamc, engine, N, p, nsteps):
     """sstate.ratio of the last SMMALA transition (iterate/GAMC.jl:45-67).  The device forms the proposal-side quadratic
     form as a'G*a - eps a'grad* + eps^2/4 f*'grad* (a = theta - theta*, f* = G*^-1 grad*) from the column partials of
@@ -288,7 +288,8 @@ def test_generic_target_callback_errors(gamc, engine):
         gamc.BasicMCJob(gamc.GenericModel(3, boom), sampler, rng_, {"p": np.zeros(3)}, tuner=tuner, tape=gamc.RandomTape(10, 3, seed=1), engine=engine)
 
 
-def test_reuse_tensor_is_bitwise_identical(gamc, engine):
+@pytest.mark.parametrize("am_mode", [0, 2])
+def test_reuse_tensor_is_bitwise_identical(gamc, engine, am_mode):
     """gamc_config.reuse_tensor: skipping the re-evaluation of gradient and metric at a current point that no AM step has
     moved (src/samplers/iterate/GAMC.jl:19-31 always re-evaluates) must not change a single bit of the chain."""
     o = _oracle()
@@ -298,7 +299,7 @@ def test_reuse_tensor_is_bitwise_identical(gamc, engine):
     engine.target_logistic(X, y, 100.0)
     out = []
     for reuse in (False, True):
-        sampler = gamc.GAMC(update=gamc.rand_exp_decay_update(10.0), driftstep=0.02, minorscale=0.001, c=0.01, am_mode=2, reuse_tensor=reuse)
+        sampler = gamc.GAMC(update=gamc.rand_exp_decay_update(10.0), driftstep=0.02, minorscale=0.001, c=0.01, am_mode=am_mode, reuse_tensor=reuse)
         tuner = gamc.GAMCTuner(gamc.VanillaMCTuner(), gamc.VanillaMCTuner(), gamc.AcceptanceRateMCTuner(0.35))
         job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, gamc.BasicMCRange(nsteps, 0), {"p": theta0}, tuner=tuner,
                               tape=gamc.RandomTape(nsteps, p, seed=8), engine=engine)
