@@ -416,8 +416,18 @@ __device__ void trsv_lower_t(MatView<REV> L, const double* invd, double* b, LaSc
 #pragma unroll
       for (int i = 0; i < LA_NB; ++i) reg[i] = gB[i * LA_NB + lane];
     } else if (tid < kb) {
+      // the 32 entries of column `tid` in this block row are contiguous in memory: 16-byte loads halve the number of
+      // sector requests of this uncoalesced (one line per lane) access -- the LSU, not latency, bounds this loop
+      if (REV && nb == LA_NB && (p & 1) == 0 && L.ld == p) {
 #pragma unroll
-      for (int c = 0; c < LA_NB; ++c) reg[c] = (c < nb) ? L(kb + c, tid) : 0.0;
+        for (int c = 0; c < LA_NB; c += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(&L(kb + c + 1, tid));   // reversed view: (kb+c+1, tid) sits just below (kb+c, tid)
+          reg[c + 1] = v.x; reg[c] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < LA_NB; ++c) reg[c] = (c < nb) ? L(kb + c, tid) : 0.0;
+      }
     }
   };
   prefetch(nblk - 1);
