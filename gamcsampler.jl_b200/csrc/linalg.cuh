@@ -152,12 +152,14 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaSc
         for (int c = 0; c < LA_NB; ++c) a[c] = S.D[r * LA_DLD + c];
         int bad = 0;
         double myrd = 0.0;
+        // software-pipelined: the pivot broadcast and rsqrt of column j+1 are issued before the bulk update of column j,
+        // so the long-latency part of the next column overlaps the (issue-bound) FMAs of this one
+        double djj = __shfl_sync(0xffffffffu, a[0], 0);
+        double rdv = rsqrt(djj);
 #pragma unroll
         for (int j = 0; j < LA_NB; ++j) {
           if (j < nbn) {
-            const double djj = __shfl_sync(0xffffffffu, a[j], j);
             if (!(djj > 0.0) || !isfinite(djj)) { if (!bad) bad = kn + j + 1; }
-            const double rdv = rsqrt(djj);
             const double l = a[j] * rdv;             // lane j: sqrt(d_jj); lanes > j: l_ij; lanes < j: 0
             a[j] = l;
             if (r == j) { myrd = rdv; S.rd[j] = rdv; }
@@ -165,6 +167,8 @@ __device__ double chol_blocked(MatView<REV> A, double* rdiag, double* invd, LaSc
             if (j + 1 < LA_NB) {                     // next pivot column first, through a shuffle (shortest dependent path)
               const double ln = __shfl_sync(0xffffffffu, l, j + 1);
               a[j + 1] = fma(-l, ln, a[j + 1]);
+              djj = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+              rdv = rsqrt(djj);
             }
             __syncwarp();
             if (r == 0) vflag[1] = it * LA_NB + j + 1;   // column j visible to the inverter (shared stores of a warp retire in order)
