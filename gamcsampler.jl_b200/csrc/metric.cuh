@@ -19,12 +19,18 @@
 
 namespace gamc {
 
-constexpr int MT_SLAB = 36;                  // rows per slab (K-extent per stage)
+#ifndef GAMC_MT_SLAB
+#define GAMC_MT_SLAB 36
+#endif
+#ifndef GAMC_MT_NSTAGE
+#define GAMC_MT_NSTAGE 3
+#endif
+constexpr int MT_SLAB = GAMC_MT_SLAB;          // rows per slab (K-extent per stage); 4 mod 16 keeps the fragment loads conflict-free
 constexpr int MT_BLK = 32;                   // columns per block
 constexpr int MT_MAXS = 8;                   // max column blocks resident per CTA
 constexpr int MT_MAXT = 12;                  // tasks (consumer warps) per CTA
 constexpr int MT_THREADS = (MT_MAXT + 1) * 32;
-constexpr int MT_NSTAGE = 3;
+constexpr int MT_NSTAGE = GAMC_MT_NSTAGE;
 constexpr int MT_SLOT_DOUBLES = MT_SLAB * MT_BLK;  // 1152 doubles = 9216 B
 
 struct MetricPlan {
@@ -39,7 +45,7 @@ struct MetricPlan {
 
 struct MetricSmem {
   alignas(128) double slab[MT_NSTAGE][MT_MAXS][MT_SLOT_DOUBLES];
-  alignas(128) double w[MT_NSTAGE][48];
+  alignas(128) double w[MT_NSTAGE][(MT_SLAB + 15) / 16 * 16];
   alignas(8) uint64_t full_bar[MT_NSTAGE];
   alignas(8) uint64_t empty_bar[MT_NSTAGE];
   MetricPlan plan;
