@@ -175,3 +175,13 @@ def test_rv_data_generation_and_csv(tmp_path):
         assert np.array_equal(back.times, m.times) and np.array_equal(back.obs, m.obs) and np.array_equal(back.sigma_obs, m.sigma_obs)
     with pytest.raises(ValueError):
         g.rv_model_velocity(np.array([3.0, 3.0, 0.8, 0.8, 1.0, 0.0]), np.array([1.0]))
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps every entry point of include/gamc_b200.h to the reference interface it replaces."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "gamc_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = sorted(set(re.findall(r"\b(gamc_[a-z_0-9]+)\s*\(", header)))
+    assert len(names) >= 37
+    assert [n for n in names if n not in doc] == []
