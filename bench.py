@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--am-mode", type=int, default=int(os.environ.get("GAMC_AM_MODE", "2")),
                     help="2 = rank-one Cholesky update, computed speculatively for both outcomes while the data pass runs (default; bit-identical to 1); "
                          "1 = rank-one update on the critical path; 0 = literal covariance recursion + Cholesky")
+    ap.add_argument("--clock-interval-ms", type=int, default=250, help="nvidia-smi sampling period during the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ess-steps", type=int, default=30000, help="length of the separate long chain used for ESS/sec (0 = skip; 1 GPU only)")
@@ -64,8 +65,9 @@ def measured_peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=250):
         self.index = index
+        self.interval_ms = int(interval_ms)
         self.proc = None
         self.lines = []
 
@@ -73,7 +75,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -255,7 +257,7 @@ def run_ours(args):
     eng.tape_set(tape.u_sched, tape.u_mix, tape.z, tape.u_acc)     # untimed upload: inputs resident in HBM
     kinds = eng.peek_kinds(K)
     launches0 = eng.launch_count()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, args.clock_interval_ms)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     clocks.start()
