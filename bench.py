@@ -86,6 +86,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_running(self, timeout=3.0):
+        """Block until nvidia-smi has delivered its first sample (its start-up, NVML initialisation included, then lies outside
+        the timed region), and forget what was sampled so far: only samples taken DURING the timed region are reported."""
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
+        self.lines.clear()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -259,8 +267,9 @@ def run_ours(args):
     launches0 = eng.launch_count()
     clocks = ClockSampler(local, args.clock_interval_ms)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     clocks.start()
+    clocks.wait_running()
+    barrier()
     e0.record(stream)
     eng.run(K)
     e1.record(stream)
