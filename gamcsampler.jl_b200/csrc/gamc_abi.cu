@@ -84,7 +84,8 @@ struct gamc_ctx {
   double* dw = nullptr;
   // data-pass configuration
   int dp_rpl = 1, dp_nu = 0, dp_grid = 0, dp_grid_now = 0, part_g_stride = 0;   // dp_grid_now: grid of the current evaluation (am_mode 2 leaves SMs free)
-  CUtensorMap mapXA{}, mapXB{}, mapW{};
+  CUtensorMap mapXA{}, mapXB{}, mapW{}, mapY{};
+  bool metric_fused = false; MetricPlan* d_plans_fused = nullptr;   // level-2 evaluation in one pass (k_metric_fused), p <= 256
   double* part_ll = nullptr; double* part_g = nullptr;
   // metric
   MetricLayout layout; MetricPlan* d_plans = nullptr; TaskCoord* d_coords = nullptr;
@@ -213,6 +214,7 @@ void free_target(gamc_ctx* h) {
   h->dX = h->dy = nullptr; h->own_data = false;
   cudaFree(h->dw); h->dw = nullptr;
   cudaFree(h->part_ll); cudaFree(h->part_g); h->part_ll = h->part_g = nullptr;
+  cudaFree(h->d_plans_fused); h->d_plans_fused = nullptr; h->metric_fused = false;
   cudaFree(h->d_plans); cudaFree(h->d_coords); cudaFree(h->ws); cudaFree(h->d_ints); h->d_plans = nullptr; h->d_coords = nullptr; h->ws = nullptr; h->d_ints = nullptr;
   cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0; h->R = nullptr; h->vecs = h->mats = nullptr; h->d_state = nullptr;
   cudaFree(h->theta_eval); h->theta_eval = nullptr;
@@ -397,11 +399,22 @@ gamc_status launch_metric(gamc_ctx* h, const int* skip = nullptr) {
   return GAMC_OK;
 }
 
+// Level-2 evaluation in one pass over X (k_metric_fused): log-likelihood and gradient partials per metric CTA, metric tiles.
+gamc_status launch_metric_fused(gamc_ctx* h, const double* theta, const int* skip = nullptr) {
+  { gamc_status s = ensure_attr(h, (const void*)k_metric_fused, sizeof(MetricSmemF)); if (s != GAMC_OK) return s; }
+  ProfScope ps(h, GAMC_K_METRIC);
+  k_metric_fused<<<h->metric_grid, MTF_THREADS, sizeof(MetricSmemF), h->stream>>>(h->mapXB, h->mapY, h->d_plans_fused, h->d_cta_kind, h->d_cta_split,
+      h->d_kind_nsplit, h->nslabs, h->ws, h->layout.max_nsplit, theta, h->p, h->N, h->part_ll, h->part_g, h->part_g_stride, h->nkinds, skip);
+  CUDA_TRY(h, cudaGetLastError());
+  return GAMC_OK;
+}
+
 // level: 0 = ll, 1 = ll + grad, 2 = ll + grad + metric
 gamc_status launch_reduce(gamc_ctx* h, int level, double* E = nullptr, const int* skip = nullptr) {
   ProfScope ps(h, GAMC_K_REDUCE);
   const int nblk = (level >= 2 ? h->ntasks * 4 : 0) + 1;
-  k_reduce<<<nblk, 256, 0, h->stream>>>(E ? E : h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid, level >= 1,
+  const int nparts = (level >= 2 && h->metric_fused) ? h->metric_grid : (h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid);
+  k_reduce<<<nblk, 256, 0, h->stream>>>(E ? E : h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, nparts, level >= 1,
                                         level >= 2 ? h->ws : nullptr, h->d_coords, h->ntasks, h->d_task_nsplit, h->layout.max_nsplit, skip);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
@@ -423,13 +436,21 @@ gamc_status eval_callback(gamc_ctx* h, const double* d_theta, int level) {
   return GAMC_OK;
 }
 
+// The kernels of a level-2 evaluation before the reduction: one fused pass when every CTA can hold complete rows (p <= 256),
+// otherwise the gradient pass followed by the metric pass.
+gamc_status launch_level2(gamc_ctx* h, const double* d_theta, const int* skip = nullptr) {
+  if (h->metric_fused) return launch_metric_fused(h, d_theta, skip);
+  gamc_status s = launch_datapass(h, d_theta, true, skip);
+  if (s != GAMC_OK) return s;
+  return launch_metric(h, skip);
+}
+
 // skip_reduce (level 0, single GPU only): leave the per-CTA partials for k_am_post to sum.
 gamc_status eval_device(gamc_ctx* h, const double* d_theta, int level, bool allreduce, bool skip_reduce = false) {
   if (h->cb) return eval_callback(h, d_theta, level);
-  gamc_status s = launch_datapass(h, d_theta, level >= 1);
+  gamc_status s = level >= 2 ? launch_level2(h, d_theta) : launch_datapass(h, d_theta, level >= 1);
   if (s != GAMC_OK) return s;
   if (skip_reduce && level == 0 && (!h->comm || h->p2p_ready)) return GAMC_OK;
-  if (level >= 2) { s = launch_metric(h); if (s != GAMC_OK) return s; }
   s = launch_reduce(h, level);
   if (s != GAMC_OK) return s;
   if (allreduce && h->comm) {
@@ -500,8 +521,11 @@ gamc_status setup_target(gamc_ctx* h) {
   CUDA_TRY(h, cudaMemsetAsync(h->dw, 0, sizeof(double) * (size_t)(h->N + 64), h->stream));
   s = make_map_1d(h, &h->mapW, h->dw, h->N, MT_SLAB);
   if (s != GAMC_OK) return s;
-  CUDA_TRY(h, cudaMalloc(&h->part_ll, sizeof(double) * h->dp_grid));
-  CUDA_TRY(h, cudaMalloc(&h->part_g, sizeof(double) * (size_t)h->dp_grid * h->part_g_stride));
+  {
+    const int rows = std::max(h->dp_grid, h->num_sms + 8);   // the fused level-2 kernel writes one row per metric CTA
+    CUDA_TRY(h, cudaMalloc(&h->part_ll, sizeof(double) * rows));
+    CUDA_TRY(h, cudaMalloc(&h->part_g, sizeof(double) * (size_t)rows * h->part_g_stride));
+  }
   // metric layout
   h->layout = build_metric_layout(p);
   h->nkinds = (int)h->layout.plans.size();
@@ -520,6 +544,26 @@ gamc_status setup_target(gamc_ctx* h) {
   }
   CUDA_TRY(h, cudaMalloc(&h->d_plans, sizeof(MetricPlan) * h->nkinds));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_plans, h->layout.plans.data(), sizeof(MetricPlan) * h->nkinds, cudaMemcpyHostToDevice, h->stream));
+  {
+    // fused level-2 evaluation: every kind keeps ALL column blocks resident (the ones its tasks do not use are appended), so
+    // each CTA can form eta = X theta for its slab itself.  Opt-in (GAMC_FUSED_METRIC=1) until it beats the two-pass route.
+    const int nblk = (p + MT_BLK - 1) / MT_BLK;
+    h->metric_fused = nblk <= MT_MAXS && h->metric_grid <= h->num_sms + 8 && h->part_g_stride >= nblk * MT_BLK && getenv("GAMC_FUSED_METRIC");
+    if (h->metric_fused) {
+      std::vector<MetricPlan> fp = h->layout.plans;
+      for (auto& pl : fp)
+        for (int b = 0; b < nblk; ++b) {
+          bool have = false;
+          for (int sl = 0; sl < pl.nslots; ++sl) have = have || pl.slot_block[sl] == b;
+          if (!have) pl.slot_block[pl.nslots++] = b;
+        }
+      CUDA_TRY(h, cudaMalloc(&h->d_plans_fused, sizeof(MetricPlan) * h->nkinds));
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_plans_fused, fp.data(), sizeof(MetricPlan) * h->nkinds, cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      gamc_status sy = make_map_1d(h, &h->mapY, h->dy, h->N, MT_SLAB);
+      if (sy != GAMC_OK) return sy;
+    }
+  }
   CUDA_TRY(h, cudaMalloc(&h->d_coords, sizeof(TaskCoord) * h->ntasks));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_coords, h->layout.coords.data(), sizeof(TaskCoord) * h->ntasks, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMalloc(&h->ws, sizeof(double) * (size_t)h->layout.max_nsplit * h->ntasks * MT_BLK * MT_BLK));
@@ -581,9 +625,7 @@ gamc_status eval_and_land(gamc_ctx* h, const double* d_theta, int mode) {
     // gamc_config.reuse_tensor: every kernel of the re-evaluation returns at once if no AM proposal was accepted since the
     // slot was filled (device flag; the host never synchronises)
     const int* skip = &h->d_state->tensor_valid;
-    gamc_status s = launch_datapass(h, d_theta, true, skip);
-    if (s != GAMC_OK) return s;
-    s = launch_metric(h, skip);
+    gamc_status s = launch_level2(h, d_theta, skip);
     if (s != GAMC_OK) return s;
     s = launch_reduce(h, 2, nullptr, skip);
     if (s != GAMC_OK) return s;
@@ -594,9 +636,7 @@ gamc_status eval_and_land(gamc_ctx* h, const double* d_theta, int mode) {
     if (s != GAMC_OK) return s;
     return launch_land(h, mode);
   }
-  gamc_status s = launch_datapass(h, d_theta, true);
-  if (s != GAMC_OK) return s;
-  s = launch_metric(h);
+  gamc_status s = launch_level2(h, d_theta);
   if (s != GAMC_OK) return s;
   const unsigned long long seq = ++h->land_seq;
   const size_t roff = (size_t)(seq & 1ull) * h->xR_stride;

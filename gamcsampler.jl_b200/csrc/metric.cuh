@@ -149,6 +149,229 @@ k_metric(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
 }
 
 // ---------------------------------------------------------------------------------------------------
+// k_metric_fused: the whole level-2 evaluation (log-likelihood, gradient, metric) in ONE pass, for p <= 8 column blocks.
+// Every CTA keeps all column blocks of its slab resident (blocks a kind's tasks do not use are loaded as well), so four
+// "weight warps" -- three, on different scheduler partitions, because the FP64 pipe is saturated by the DMMAs and side work
+// must be spread -- can form eta = X theta (two or three column blocks each), sigma, the metric weights sigma (1 - sigma) and the residual
+// y - sigma for the 36 rows of the slab as soon as it lands, one stage ahead of the DMMA warps, which wait for the weights
+// instead of for the TMA.  The gradient X'(y - sigma) rides along in the warps that own a DIAGONAL task: their A fragments are
+// exactly the 32 columns of one block, they issue 10 instead of 16 DMMAs per k-step, and each column block has exactly one
+// diagonal task in the whole plan.  The separate gradient pass over X (k_datapass<GRAD>) disappears.
+// Per-CTA partials (fixed order, deterministic): part_ll[cta] (slab s is accounted for by the CTA of kind s mod nkinds that
+// sweeps it), part_g[cta][column].
+// ---------------------------------------------------------------------------------------------------
+constexpr int MTF_NW = 3;                                     // weight warps: warps 13, 14, 15 = scheduler partitions 1, 2, 3 (16 warps in all:
+                                                              // a 17th would put five warps on one partition and cap the kernel at 96 registers)
+constexpr int MTF_THREADS = (MT_MAXT + 1 + MTF_NW) * 32;      // task warps, producer, weight warps
+constexpr int MTF_PAD = (MT_SLAB + 15) / 16 * 16;
+constexpr int MTF_RPW = (MT_SLAB + MTF_NW - 1) / MTF_NW;      // rows whose sigmoid each weight warp evaluates
+
+struct MetricSmemF {
+  alignas(128) double slab[MT_NSTAGE][MT_MAXS][MT_SLOT_DOUBLES];
+  alignas(128) double yv[MT_NSTAGE][MTF_PAD];
+  alignas(128) double w[MT_NSTAGE][MTF_PAD];
+  alignas(128) double r[MT_NSTAGE][MTF_PAD];
+  alignas(128) double eta[MTF_NW][MTF_PAD];
+  double theta[MT_MAXS * MT_BLK];
+  double llpart[MTF_NW];
+  alignas(8) uint64_t full_bar[MT_NSTAGE];
+  alignas(8) uint64_t ready_bar[MT_NSTAGE];
+  alignas(8) uint64_t empty_bar[MT_NSTAGE];
+  int slot_of_block[MT_MAXS];
+  MetricPlan plan;
+};
+
+template <bool DIAG>
+__device__ __forceinline__ void metric_slab_fused(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ wv,
+                                                  const double* __restrict__ rv, int lane, double (&acc)[4][4][2], double (&ga)[4]) {
+  const int g = lane >> 2, c = lane & 3;
+  const double* ap = A + g * MT_SLAB + c;
+  const double* bp = B + g * MT_SLAB + c;
+#pragma unroll
+  for (int k4 = 0; k4 < MT_SLAB / 4; ++k4) {
+    const double wk = wv[k4 * 4 + c];
+    double a[4], b[4];
+    if (DIAG) {
+      const double rk = rv[k4 * 4 + c];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const double x = ap[t * 8 * MT_SLAB + k4 * 4];
+        ga[t] = fma(x, rk, ga[t]);                       // gradient of column t*8+g, rows k = c (mod 4)
+        a[t] = x * wk;
+        b[t] = bp[t * 8 * MT_SLAB + k4 * 4];
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        a[t] = ap[t * 8 * MT_SLAB + k4 * 4] * wk;
+        b[t] = bp[t * 8 * MT_SLAB + k4 * 4];
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        if (!DIAG || mt >= nt) dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+  }
+}
+
+__global__ void __launch_bounds__(MTF_THREADS, 1)
+k_metric_fused(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+               const MetricPlan* __restrict__ plans, const int* __restrict__ cta_kind, const int* __restrict__ cta_split,
+               const int* __restrict__ kind_nsplit, long long nslabs, double* __restrict__ ws, int max_nsplit,
+               const double* __restrict__ theta, int p, long long N, double* __restrict__ part_ll, double* __restrict__ part_g,
+               int part_g_stride, int nkinds, const int* skip_flag) {
+  if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;   // gamc_config.reuse_tensor
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MetricSmemF& S = *reinterpret_cast<MetricSmemF*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kind = cta_kind[blockIdx.x], split = cta_split[blockIdx.x], nsplit = kind_nsplit[kind];
+  const int nblk = (p + MT_BLK - 1) / MT_BLK;
+
+  {
+    const int* src = reinterpret_cast<const int*>(&plans[kind]);
+    int* dst = reinterpret_cast<int*>(&S.plan);
+    for (int i = tid; i < (int)(sizeof(MetricPlan) / sizeof(int)); i += MTF_THREADS) dst[i] = src[i];
+  }
+  for (int j = tid; j < MT_MAXS * MT_BLK; j += MTF_THREADS) S.theta[j] = (j < p) ? theta[j] : 0.0;
+  for (int j = tid; j < part_g_stride; j += MTF_THREADS) part_g[(size_t)blockIdx.x * part_g_stride + j] = 0.0;
+  if (tid == 0) {
+    const int nt = plans[kind].ntasks;
+    for (int s = 0; s < MT_NSTAGE; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.ready_bar[s], MTF_NW); mbar_init(&S.empty_bar[s], nt + MTF_NW); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int nslots = S.plan.nslots, ntasks = S.plan.ntasks;
+  if (tid < MT_MAXS) {
+    int sl = 0;
+    for (int s = 0; s < nslots; ++s) if (S.plan.slot_block[s] == tid) sl = s;
+    S.slot_of_block[tid] = sl;
+  }
+  __syncthreads();
+
+  if (warp == MT_MAXT) {
+    // ===== producer: X blocks + the y slab
+    if (lane == 0) {
+      tma_prefetch_desc(&mapX);
+      tma_prefetch_desc(&mapY);
+      unsigned it = 0;
+      for (long long slab = split; slab < nslabs; slab += nsplit, ++it) {
+        const unsigned st = it % MT_NSTAGE, round = it / MT_NSTAGE;
+        mbar_wait(&S.empty_bar[st], (round & 1) ^ 1);
+        mbar_arrive_expect_tx(&S.full_bar[st], (uint32_t)(nslots * MT_SLOT_DOUBLES * 8 + MT_SLAB * 8));
+        for (int s = 0; s < nslots; ++s)
+          tma_load_2d(S.slab[st][s], &mapX, &S.full_bar[st], (int)(slab * MT_SLAB), S.plan.slot_block[s] * MT_BLK);
+        tma_load_1d(S.yv[st], &mapY, &S.full_bar[st], (int)(slab * MT_SLAB));
+      }
+    }
+    return;
+  }
+
+  if (warp > MT_MAXT) {
+    // ===== weight warps: q handles column blocks q, q+3, q+6 of eta = X theta (lane = row; rows 32..35 spread over the
+    //       lanes), then the sigmoid of rows q*12 .. q*12+11
+    const int q = warp - MT_MAXT - 1;
+    const int lo = lane & 3, hi = lane >> 2;
+    double ll = 0.0;
+    unsigned it = 0;
+    for (long long slab = split; slab < nslabs; slab += nsplit, ++it) {
+      const unsigned st = it % MT_NSTAGE, round = it / MT_NSTAGE;
+      mbar_wait(&S.full_bar[st], round & 1);
+      double e0[4] = {0.0, 0.0, 0.0, 0.0}, e1 = 0.0;
+      for (int b = q; b < nblk; b += MTF_NW) {
+        const double* sl = S.slab[st][S.slot_of_block[b]];
+        const double* th = S.theta + b * MT_BLK;
+#pragma unroll 8
+        for (int jj = 0; jj < MT_BLK; ++jj) e0[jj & 3] = fma(sl[jj * MT_SLAB + lane], th[jj], e0[jj & 3]);
+#pragma unroll
+        for (int m = 0; m < MT_BLK / 8; ++m) e1 = fma(sl[(hi + 8 * m) * MT_SLAB + 32 + lo], th[hi + 8 * m], e1);   // row 32+lo, columns hi+8m
+      }
+      e1 += __shfl_xor_sync(0xffffffffu, e1, 4);
+      e1 += __shfl_xor_sync(0xffffffffu, e1, 8);
+      e1 += __shfl_xor_sync(0xffffffffu, e1, 16);
+      S.eta[q][lane] = (e0[0] + e0[1]) + (e0[2] + e0[3]);
+      if (lane < MT_SLAB - 32) S.eta[q][32 + lane] = e1;
+      asm volatile("bar.sync 2, %0;" ::"n"(MTF_NW * 32) : "memory");
+      // every slab is swept by one CTA of each kind: the kind with index slab % nkinds adds its log-likelihood terms, the
+      // others skip the log1p (the FP64 instructions of these warps queue behind the DMMAs: every one saved counts)
+      const bool need_ll = (int)(slab % nkinds) == kind;
+      if (lane < MTF_RPW) {
+        const int k = q * MTF_RPW + lane;
+        if (k < MT_SLAB) {
+          double eta = 0.0;
+#pragma unroll
+          for (int qq = 0; qq < MTF_NW; ++qq) eta += S.eta[qq][k];
+          const double e = exp(-fabs(eta));
+          const double inv = 1.0 / (1.0 + e);
+          const double sig = (eta >= 0.0) ? inv : e * inv;
+          const bool valid = slab * MT_SLAB + k < N;
+          const double y = S.yv[st][k];
+          S.w[st][k] = valid ? sig * (1.0 - sig) : 0.0;
+          S.r[st][k] = valid ? (y - sig) : 0.0;
+          if (need_ll && valid) ll += y * eta - (fmax(eta, 0.0) + log1p(e));
+        }
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(MTF_NW * 32) : "memory");   // eta scratch free again; w, r of this warp written
+      if (lane == 0) { mbar_arrive(&S.ready_bar[st]); mbar_arrive(&S.empty_bar[st]); }
+    }
+    ll = warp_sum(ll);
+    if (lane == 0) S.llpart[q] = ll;
+    asm volatile("bar.sync 2, %0;" ::"n"(MTF_NW * 32) : "memory");
+    if (q == 0 && lane == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int qq = 0; qq < MTF_NW; ++qq) t += S.llpart[qq];
+      part_ll[blockIdx.x] = t;
+    }
+    return;
+  }
+
+  // ===== DMMA warps (one task each); surplus warps of a partially filled kind retire
+  if (warp >= ntasks) return;
+  const int sa = S.plan.task_sa[warp], sb = S.plan.task_sb[warp];
+  const bool diag = S.plan.task_diag[warp] != 0;
+  double acc[4][4][2];
+  double ga[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  unsigned it = 0;
+  for (long long slab = split; slab < nslabs; slab += nsplit, ++it) {
+    const unsigned st = it % MT_NSTAGE, round = it / MT_NSTAGE;
+    mbar_wait(&S.ready_bar[st], round & 1);
+    if (diag) metric_slab_fused<true>(S.slab[st][sa], S.slab[st][sb], S.w[st], S.r[st], lane, acc, ga);
+    else      metric_slab_fused<false>(S.slab[st][sa], S.slab[st][sb], S.w[st], S.r[st], lane, acc, ga);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.empty_bar[st]);
+  }
+
+  {
+    double* out = ws + ((size_t)S.plan.task_id[warp] * max_nsplit + split) * (MT_BLK * MT_BLK);
+    const int g = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        double2 v = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        *reinterpret_cast<double2*>(&out[(mt * 8 + g) * MT_BLK + nt * 8 + 2 * c]) = v;
+      }
+    if (diag) {
+      const int blk = S.plan.slot_block[sa];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        double v = ga[t];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        const int col = blk * MT_BLK + t * 8 + g;
+        if (c == 0 && col < part_g_stride) part_g[(size_t)blockIdx.x * part_g_stride + col] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // k_reduce: deterministic second stage.  Sums per-CTA log-likelihood / gradient partials of Kernel A and
 // the per-split metric tiles of Kernel B in a fixed order into the packed evaluation buffer
 //   E = [ ll, g(0..p-1), pad, G(p x p column-major, both triangles written, exactly symmetric) ]

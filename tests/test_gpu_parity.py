@@ -309,3 +309,22 @@ def test_reuse_tensor_is_bitwise_identical(gamc, engine, am_mode):
         out.append((c.value.copy(), c.diagnosticvalues.copy(), st.logtarget, st.step, st.updatetensorcount))
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     assert out[0][2:] == out[1][2:]
+
+
+@pytest.mark.parametrize("N,p", [(777, 33), (6000, 256), (5000, 130)])
+def test_fused_level2_kernel_parity(gamc, engine, N, p, monkeypatch):
+    """GAMC_FUSED_METRIC=1 (experimental, off by default): log-likelihood, gradient and metric from ONE pass over X
+    (k_metric_fused) against the oracle and against the default two-pass route."""
+    o = _oracle()
+    X, y, tt = o.synth_logistic(77, N, p)
+    theta = tt + 0.05 * np.random.default_rng(3).standard_normal(p)
+    engine.target_logistic(X, y, 100.0)
+    lt0, g0, G0 = engine.eval_upto_tensor(theta)
+    monkeypatch.setenv("GAMC_FUSED_METRIC", "1")
+    engine.target_logistic(X, y, 100.0)
+    lt1, g1, G1 = engine.eval_upto_tensor(theta)
+    monkeypatch.delenv("GAMC_FUSED_METRIC")
+    ltr, gr, Gr = o.LogisticTarget(X, y, 100.0).uptotensorlogtarget(theta)
+    assert abs(lt1 - ltr) <= 1e-10 * abs(ltr) and relerr(g1, gr) <= 1e-10 and relerr(G1, Gr) <= 1e-10
+    assert abs(lt1 - lt0) <= 1e-12 * abs(lt0) and relerr(g1, g0) <= 1e-11 and relerr(G1, G0) <= 1e-12
+    engine.target_logistic(X, y, 100.0)      # leave the engine on the default route
