@@ -185,3 +185,19 @@ def test_integration_doc_names_every_entry_point():
     names = sorted(set(re.findall(r"\b(gamc_[a-z_0-9]+)\s*\(", header)))
     assert len(names) >= 37
     assert [n for n in names if n not in doc] == []
+
+
+def test_metric_planner_invariants(tmp_path):
+    """Host planner of the metric kernel (metric_plan.h) for every p in 1..512: each lower-triangle block pair is exactly one task,
+    each column block has exactly one diagonal task, slot / task / CTA tables are consistent (tests/cpp/plan_check.cu; only host
+    code runs, so no GPU is needed)."""
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "plan_check")
+    subprocess.run(["nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(root, "gamcsampler.jl_b200", "csrc"),
+                    os.path.join(root, "tests", "cpp", "plan_check.cu"), "-o", exe], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:]
