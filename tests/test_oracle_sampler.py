@@ -158,3 +158,22 @@ def test_ess_on_ar1():
 def test_notposdef_is_raised_like_chol():
     with pytest.raises(osamp.NotPosDef):
         osamp._chol_lower(np.array([[1.0, 2.0], [2.0, 1.0]]))
+
+
+def test_smmala_ratio_expansion_identity():
+    """The device evaluates the proposal-side quadratic form of the SMMALA ratio (iterate/GAMC.jl:58-67) as
+    a'G*a - eps a'grad* + eps^2/4 f*'grad* with a = theta - theta*, f* = G*^-1 grad* (DESIGN.md 3C); here the identity itself,
+    against the literal (theta - mu*)' G* (theta - mu*), mu* = theta* + eps/2 f*, on random well- and ill-conditioned metrics."""
+    rng = np.random.default_rng(0)
+    for p, cond in ((5, 1e1), (40, 1e4), (120, 1e7)):
+        Q, _ = np.linalg.qr(rng.standard_normal((p, p)))
+        G = (Q * np.geomspace(1.0, cond, p)) @ Q.T
+        G = 0.5 * (G + G.T)
+        theta, theta_p, grad = rng.standard_normal(p), rng.standard_normal(p), rng.standard_normal(p)
+        eps = 0.02
+        f = np.linalg.solve(G, grad)
+        d2 = theta - (theta_p + 0.5 * eps * f)
+        literal = d2 @ G @ d2
+        a = theta - theta_p
+        expanded = a @ G @ a - eps * (a @ grad) + 0.25 * eps * eps * (f @ grad)
+        assert abs(expanded - literal) <= 1e-12 * abs(literal) * max(1.0, cond * 1e-6)
