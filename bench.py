@@ -1,16 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- GAMC (AM <-> SMMALA) throughput on the BASELINE.json workload.
 
-  python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+  python bench.py --gpus N --steps K --warmup W                    # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K --warmup W   # CPU restatement of the reference, host cores
 
-Workload (BASELINE.json configs[1], "C2"): synthetic Bayesian logistic regression, N = 2^20 observations
-PER GPU, p = 256, FP64, single chain, the sampler configuration shipped with the reference's example
-(examples/logistic_regression/src/GAMC/simulations.jl:50-59: rand_exp_decay_update!(a=10), driftstep 0.02,
-minorscale 0.001, c 0.01, t0 3, AcceptanceRateMCTuner(0.35), period 100).  A "step" is one GAMC `iterate!`
-transition.  Multi-GPU: observations are row-sharded, one process per GPU, one NCCL all-reduce of
-[loglik, gradient, metric] per target evaluation; weak scaling (2^20 rows per GPU), and `value` counts
-shard-iterations per second (= iters/s x n_gpus; at 1 GPU exactly GAMC iters/s on C2).
+Workload (BASELINE.json configs[1], "C2"): synthetic Bayesian logistic regression, N = 2^20 observations IN TOTAL, p = 256,
+FP64, single chain, the sampler configuration shipped with the reference's example (examples/logistic_regression/src/GAMC/
+simulations.jl:50-59: rand_exp_decay_update!(a=10), driftstep 0.02, minorscale 0.001, c 0.01, t0 3, AcceptanceRateMCTuner(0.35),
+period 100).  A "step" is one GAMC `iterate!` transition.  Multi-GPU: the SAME 2^20 observations are row-sharded over the N ranks
+(strong scaling; one process per GPU; [loglik, gradient, metric] summed over NVLink peer memory inside the consuming kernels), so
+`value` is the true iteration rate of the one chain at every N.  Extra blocks in the same line: `parity` (multi-GPU results against
+the single-GPU evaluation of the same rows, chains bit-identical across ranks, chain equal to the CPU oracle on a small shape),
+`c3` (BASELINE configs[2]: N = 2^24, p = 512 split the same way), `weak` (2^20 rows PER GPU, the round-1 definition, for
+information only), `limiter` (microseconds per step of every kernel family, max over ranks).
 
 Prints ONE JSON line (rank 0).
 """
@@ -32,7 +34,8 @@ if ROOT not in sys.path:
 
 SEED = 20260101
 LAMBDA = 100.0
-FP64_DMMA_PEAK_TFLOPS_FALLBACK = 37.1   # profiles/r01_fp64_peak.txt (register-only DMMA.8x8x4 loop, this pool's B200)
+FP64_DMMA_PEAK_TFLOPS_FALLBACK = 37.1   # profiles/r01_fp64_peak.txt; only used if the in-run probe fails
+NCU_TRAFFIC_FILE = "profiles/r02_ncu_summary.md"
 
 
 def parse():
@@ -41,14 +44,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--logN", type=int, default=20, help="log2 of rows per GPU (default 2^20 = BASELINE C2)")
+    ap.add_argument("--logN", type=int, default=20, help="log2 of the GLOBAL number of rows (default 2^20 = BASELINE C2)")
     ap.add_argument("--p", type=int, default=256)
     ap.add_argument("--am-mode", type=int, default=int(os.environ.get("GAMC_AM_MODE", "2")),
                     help="2 = rank-one Cholesky update, computed speculatively for both outcomes while the data pass runs (default; bit-identical to 1); "
                          "1 = rank-one update on the critical path; 0 = literal covariance recursion + Cholesky")
-    ap.add_argument("--clock-interval-ms", type=int, default=250, help="nvidia-smi sampling period during the timed region")
+    ap.add_argument("--clock-interval-ms", type=int, default=100, help="nvidia-smi sampling period")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="skip the C3 block (N = 2^24, p = 512)")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling extra (N > 1 only)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--c3-logN", type=int, default=24)
+    ap.add_argument("--c3-steps", type=int, default=20)
     ap.add_argument("--ess-steps", type=int, default=30000, help="length of the separate long chain used for ESS/sec (0 = skip; 1 GPU only)")
     return ap.parse_args()
 
@@ -63,9 +71,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled while the GPU arm's kernels run."""
 
-    def __init__(self, index, interval_ms=250):
+    def __init__(self, index, interval_ms=100):
         self.index = index
         self.interval_ms = int(interval_ms)
         self.proc = None
@@ -84,40 +92,46 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def wait_running(self, timeout=3.0):
-        """Block until nvidia-smi has delivered its first sample (its start-up, NVML initialisation included, then lies outside
-        the timed region), and forget what was sampled so far: only samples taken DURING the timed region are reported."""
+        """Block until nvidia-smi has delivered its first sample (its start-up then lies outside the sampled window)."""
         t0 = time.time()
         while self.proc is not None and not self.lines and time.time() - t0 < timeout:
             time.sleep(0.01)
         self.lines.clear()
 
-    def stop(self):
+    def stop(self, window=None):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
+        sm, mx, reasons, pw, in_timed = [], [], set(), [], 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                s_, m_, p_ = float(f[0]), float(f[1]), float(f[2])
             except ValueError:
                 continue
+            if p_ < 250.0:          # idle samples between phases (host work) say nothing about the clock under load
+                continue
+            sm.append(s_); mx.append(m_); pw.append(p_)
+            if window and window[0] <= ts <= window[1]:
+                in_timed += 1
             for nm, val in zip(names, f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_in_timed_region": in_timed, "reasons": sorted(reasons),
+                "window": "warm-up + timed region + profiled re-run of the same job (samples under load, power > 250 W); the timed "
+                          "region alone can be shorter than one nvidia-smi sampling period"}
 
 
 def bench_config(gamc, nsteps, am_mode, reuse_tensor=False):
@@ -133,81 +147,91 @@ def theta_inputs(p):
     return tt, theta0
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is entitled to all host cores."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+    return os.cpu_count()
+
+
 # ----------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (a NumPy restatement of the reference's Julia path; Julia itself is not in the image)
 # ----------------------------------------------------------------------------------------------------
-def cpu_iteration_costs(X, y, theta0, p):
-    """Times real oracle `iterate!` transitions at full N on the host cores, per kind:
-    'am', 'smmala' (one tensor evaluation) and 'smmala_stale' (two: the step after an AM step re-evaluates)."""
+def tape_kinds(K, p):
+    """Branch sequence (1 = SMMALA, 0 = AM) of the K-step job: both arms draw the schedule uniforms from the same host tape."""
+    import oracle as o
+    tape = o.RandomTape(K, p, seed=SEED + 9)
+    kinds = np.ones(K, dtype=np.uint8)
+    for i in range(4, K + 1):               # t0 = 3: the first three iterations are always SMMALA
+        kinds[i - 1] = tape.u_sched[i - 1] <= o.exp_decay(i, K, 10.0, 0.0)
+    return tape, kinds
+
+
+def cpu_arm(X, y, theta0, p, K):
+    """iters/s of the reference's path on the host cores for the K-step job.  K <= 32: the oracle EXECUTES the K transitions on
+    the shared tape (same branch sequence as the GPU arm).  Larger K: 14 real transitions at full size give per-kind costs
+    (AM / SMMALA / SMMALA after AM, which re-evaluates), summed over the job's own branch sequence."""
     import oracle as o
     tgt = o.LogisticTarget(X, y, LAMBDA, reference_shaped=True)   # three X*theta passes, N x p temporary, full gemm
+    mk_tuner = lambda: o.GAMCTuner(o.VanillaMCTuner(), o.VanillaMCTuner(), o.AcceptanceRateMCTuner(0.35))
+    tape, kinds = tape_kinds(K, p)
+    n_sm = int(kinds.sum())
+    if K <= 32:
+        sam = o.GAMCOracle(tgt, theta0, K, K // 5, update="rand_exp_decay_update!", update_params=(10.0, 0.0), driftstep=0.02, minorscale=0.001,
+                           c=0.01, tuner=mk_tuner())
+        t0 = time.perf_counter()
+        for _ in range(K):
+            sam.iterate(tape)
+        total = time.perf_counter() - t0
+        assert sam.updatetensorcount == n_sm
+        return K / total, {"mode": "executed", "seconds": total, "n_smmala": n_sm, "n_am": K - n_sm,
+                           "sample": f"the K={K} transitions of the job itself, executed by the oracle on the shared tape ({n_sm} SMMALA / {K - n_sm} AM), "
+                                     f"reference-shaped callbacks (3 X*theta passes, N x p temporary, full gemm)"}
     nst = 14
-    tuner = o.GAMCTuner(o.VanillaMCTuner(), o.VanillaMCTuner(), o.AcceptanceRateMCTuner(0.35))
-    sam = o.GAMCOracle(tgt, theta0, nst, 0, update="mod_update!", update_params=(4,), driftstep=0.02, minorscale=0.001, c=0.01, tuner=tuner)
-    tape = o.RandomTape(nst, p, seed=3)
+    sam = o.GAMCOracle(tgt, theta0, nst, 0, update="mod_update!", update_params=(4,), driftstep=0.02, minorscale=0.001, c=0.01, tuner=mk_tuner())
+    t14 = o.RandomTape(nst, p, seed=3)
     costs = {"am": [], "smmala": [], "smmala_stale": []}
     for _ in range(nst):
         past = sam.pastupdatetensor
         t0 = time.perf_counter()
-        sam.iterate(tape)
+        sam.iterate(t14)
         dt = time.perf_counter() - t0
-        kind = "am" if sam.last_kind == "am" else ("smmala" if past else "smmala_stale")
-        costs[kind].append(dt)
-    return {k: float(np.mean(v[1:] if len(v) > 1 else v)) for k, v in costs.items() if v}
-
-
-def compose_cpu_rate(costs, kinds):
-    """iters/s of the K-step schedule from per-kind costs (kinds: 1 = SMMALA, 0 = AM)."""
+        costs["am" if sam.last_kind == "am" else ("smmala" if past else "smmala_stale")].append(dt)
+    costs = {k: float(np.mean(v[1:] if len(v) > 1 else v)) for k, v in costs.items() if v}
     total, past = 0.0, False
     for k in kinds:
-        if k:
-            total += costs["smmala"] if past else costs.get("smmala_stale", costs["smmala"])
-        else:
-            total += costs["am"]
+        total += (costs["smmala"] if past else costs.get("smmala_stale", costs["smmala"])) if k else costs["am"]
         past = bool(k)
-    return len(kinds) / total, total
-
-
-def host_kinds(K, seed):
-    """Branch sequence of the K-step job for the device-generated tape is only known to the GPU arm; the CPU
-    arm draws its own schedule uniforms (same distribution: exp(-10 i/K) SMMALA probability)."""
-    import oracle as o
-    rng = np.random.Generator(np.random.PCG64(seed))
-    u = rng.random(K)
-    kinds = np.ones(K, dtype=np.uint8)
-    for i in range(4, K + 1):
-        kinds[i - 1] = u[i - 1] <= o.exp_decay(i, K, 10.0, 0.0)
-    return kinds
+    return K / total, {"mode": "composed", "per_kind_seconds": costs, "n_smmala": n_sm, "n_am": K - n_sm,
+                       "sample": f"14 real oracle iterate! transitions (mod_update! n=4) at full size, reference-shaped callbacks; per-kind means "
+                                 f"summed over the job's own K={K}-step branch sequence ({n_sm} SMMALA / {K - n_sm} AM)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = use_all_host_threads()
     N, p = 1 << args.logN, args.p
     t0 = time.perf_counter()
     rng = np.random.Generator(np.random.PCG64(SEED))
-    # same shape and distribution as the GPU arm's synthetic data (standardised columns, Bernoulli labels);
-    # generated with NumPy's own generator here because the timing is data-independent
+    # same shape and distribution family as the GPU arm's synthetic data (standardised columns, Bernoulli labels); generated
+    # with NumPy's own generator here because the timing is data-independent
     X = np.asfortranarray(rng.standard_normal((N, p)))
     tt, theta0 = theta_inputs(p)
     y = (rng.random(N) < 1.0 / (1.0 + np.exp(-(X @ tt)))).astype(np.float64)
     gen_s = time.perf_counter() - t0
-    costs = cpu_iteration_costs(X, y, theta0, p)
-    kinds = host_kinds(args.steps, SEED + 2)
-    rate, total = compose_cpu_rate(costs, kinds)
-    cores = os.cpu_count()
-    sample = (f"14 real oracle iterate! transitions (mod_update! n=4) at full N=2^{args.logN}, p={p}, reference-shaped callbacks "
-              f"(3 X*theta passes, N x p temporary, full gemm), per-kind means composed over the K={args.steps}-step exp-decay schedule "
-              f"({int(kinds.sum())} SMMALA / {int(len(kinds) - kinds.sum())} AM)")
+    rate, info = cpu_arm(X, y, theta0, p, args.steps)
     line = {
         "impl": "reference", "metric": "gamc_iters_per_sec", "value": rate, "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (NumPy PCG64 N(0,1) design, Bernoulli labels)",
-        "config": {"workload": f"C2: logistic N=2^{args.logN} rows per GPU, p={p}, FP64, GAMC rand_exp_decay(a=10), single chain", "rows_per_gpu": N, "p": p,
-                   "value_definition": "iters/s x n_gpus (weak scaling: the CPU arm is timed on one 2^20-row shard; a CPU job on n_gpus shards is n_gpus times slower per iteration)"},
-        "cpu_baseline": {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample,
-                         "per_kind_seconds": costs, "datagen_s": gen_s},
+        "config": {"workload": f"C2: logistic N=2^{args.logN} rows in total, p={p}, FP64, GAMC rand_exp_decay(a=10), single chain", "global_rows": N, "p": p,
+                   "value_definition": "chain iterations per second on the whole problem (the CPU arm does not depend on n_gpus)"},
+        "cpu_baseline": {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "datagen_s": gen_s, **info},
         "e2e": {"value": rate, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "Julia/Klara cannot run in this image; this is the NumPy+BLAS restatement (oracle/) on all host cores",
     }
@@ -217,79 +241,214 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
+def relerr(a, b):
+    den = float(np.max(np.abs(b)))
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / (den if den > 0 else 1.0))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import gamc_b200 as g
+    from gamc_b200.distributed import init_comm, shard_rows
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    N, p = 1 << args.logN, args.p          # rows PER GPU (weak scaling)
+        dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
-    tt, theta0 = theta_inputs(p)
-
-    eng = g.Engine(local)
     stream = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(stream)
-    eng.set_stream(stream.cuda_stream)
-    eng.target_logistic_synth(SEED, rank * N, N, p, tt, LAMBDA)   # this rank's row shard, generated on the device
-    if world > 1:
-        from gamc_b200.distributed import init_comm
-        init_comm(eng, rank, world)
-
-    model = g.LogisticModel(synth={"seed": SEED, "N": N * world, "p": p, "theta_true": tt}, lam=LAMBDA)
-
-    def make_job(nsteps, tape=None, reuse_tensor=False):
-        sampler, tuner, rng = bench_config(g, nsteps, args.am_mode, reuse_tensor)
-        return g.BasicMCJob(model, sampler, rng, {"p": theta0}, tuner=tuner, engine=eng, tape=tape, tape_seed=SEED + 7)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up: W transitions of a separate short job (both kernel families get exercised)
-    job = make_job(max(W, 8))
-    job.run()
-    # ---- timed region: tape resident on the device, K transitions, device-timed, max over ranks.
-    # One host-drawn tape (pinned) serves the device-timed run, the profiled re-run and the end-to-end run, so all
-    # three execute the identical branch sequence.
-    tape = g.RandomTape(K, p, seed=SEED + 9)
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-    tape.u_sched, tape.u_mix, tape.u_acc, tape.z = pin(tape.u_sched), pin(tape.u_mix), pin(tape.u_acc), pin(tape.z)
-    job = make_job(K)
-    eng.tape_set(tape.u_sched, tape.u_mix, tape.z, tape.u_acc)     # untimed upload: inputs resident in HBM
-    kinds = eng.peek_kinds(K)
-    launches0 = eng.launch_count()
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ranks_ok(flag):
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() == 1)
+
+    def bitwise_equal_across_ranks(arr):
+        if world == 1:
+            return True
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        return all_ranks_ok(bool(torch.equal(t, ref)))
+
+    def new_engine():
+        e = g.Engine(local)
+        e.set_stream(stream.cuda_stream)
+        return e
+
     clocks = ClockSampler(local, args.clock_interval_ms)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks.start()
     clocks.wait_running()
-    barrier()
-    e0.record(stream)
-    eng.run(K)
-    e1.record(stream)
-    barrier()
-    clk = clocks.stop()
-    ms = e0.elapsed_time(e1)
-    launches = eng.launch_count() - launches0
-    eng.sync()
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    iters_per_sec = K / (ms * 1e-3)
-    st = eng.state()
+
+    eng = new_engine()
+    dmma_peak, dfma_peak = eng.probe_fp64_peak()       # FP64 yard-sticks of THIS device, in this lease
+    hbm_peak, hbm_src = measured_peaks()
+
+    # ------------------------------------------------------------------ parity (small shape; every rank; oracle on rank 0)
+    parity = None
+    if not args.no_parity:
+        parity = parity_block(g, eng, rank, world, dev, dist if world > 1 else None, args, all_ranks_ok, bitwise_equal_across_ranks,
+                              init_comm, shard_rows)
+
+    def timed_job(label, logN, p, K, W, want_profile, want_e2e):
+        """One strong-scaled workload: 2^logN rows in total over `world` ranks.  Returns the result block."""
+        nonlocal eng
+        N = 1 << logN
+        r0, r1 = shard_rows(N, world, rank)
+        Nloc = r1 - r0
+        tt, theta0 = theta_inputs(p)
+        eng.target_logistic_synth(SEED, r0, Nloc, p, tt, LAMBDA)
+        if world > 1 and not getattr(eng, "_comm_done", False):
+            init_comm(eng, rank, world)
+            eng._comm_done = True
+        model = g.LogisticModel(synth={"seed": SEED, "N": N, "p": p, "theta_true": tt}, lam=LAMBDA)
+
+        def make_job(nsteps, tape=None, reuse_tensor=False):
+            sampler, tuner, rng = bench_config(g, nsteps, args.am_mode, reuse_tensor)
+            return g.BasicMCJob(model, sampler, rng, {"p": theta0}, tuner=tuner, engine=eng, tape=tape, tape_seed=SEED + 7)
+
+        out = {"global_rows": N, "rows_per_gpu": Nloc, "p": p, "steps": K}
+        # full-size parity of the reduction (N > 1): the all-reduced evaluation against ONE GPU evaluating all the rows
+        if world > 1 and not args.no_parity:
+            lt, gr, G = eng.eval_upto_tensor(theta0)
+            ok, errs = True, None
+            if rank == 0:
+                e1 = g.Engine(local)
+                e1.target_logistic_synth(SEED, 0, N, p, tt, LAMBDA)
+                lt1, g1, G1 = e1.eval_upto_tensor(theta0)
+                e1.close()
+                errs = {"logtarget": abs(lt - lt1) / abs(lt1), "grad": relerr(gr, g1), "metric": relerr(G, G1)}
+                ok = max(errs.values()) <= 1e-11
+            out["reduced_vs_single_gpu"] = {"ok": all_ranks_ok(ok), "relerr": errs, "tolerance": 1e-11,
+                                            "what": f"[ll, grad, metric] all-reduced over {world} row shards vs one GPU evaluating all 2^{logN} rows"}
+        # ---- warm-up: W transitions of a separate short job (both kernel families get exercised)
+        job = make_job(max(W, 8))
+        job.run()
+        # ---- timed region: tape resident on the device, K transitions, device-timed, max over ranks.  One host-drawn tape (pinned)
+        # serves the device-timed run, the profiled re-run and the end-to-end run, so all three execute the identical branch sequence.
+        tape = g.RandomTape(K, p, seed=SEED + 9)
+        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+        tape.u_sched, tape.u_mix, tape.u_acc, tape.z = pin(tape.u_sched), pin(tape.u_mix), pin(tape.u_acc), pin(tape.z)
+        job = make_job(K)
+        eng.tape_set(tape.u_sched, tape.u_mix, tape.z, tape.u_acc)     # untimed upload: inputs resident in HBM
+        kinds = eng.peek_kinds(K)
+        launches0 = eng.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_w0 = time.time()
+        e0.record(stream)
+        eng.run(K)
+        e1.record(stream)
+        barrier()
+        t_w1 = time.time()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        out["timed_window"] = (t_w0, t_w1)
+        out["gpu_launches"] = int(eng.launch_count() - launches0)
+        eng.sync()
+        st = eng.state()
+        nsave = K - K // 5
+        value, accept = eng.chain_get(0, nsave)
+        out.update({"ms": ms, "ms_per_step": ms / K, "iters_per_sec": K / (ms * 1e-3), "n_smmala": int(kinds.sum()), "n_am": int(K - kinds.sum()),
+                    "acceptance": float(accept.mean()), "final_step": st.step, "updatetensorcount": st.updatetensorcount,
+                    "chain_bit_identical_across_ranks": bitwise_equal_across_ranks(value)})
+        out["_chain"] = (value, accept)
+        out["_make_job"], out["_tape"], out["_kinds"], out["_theta0"] = make_job, tape, kinds, theta0
+
+        if want_profile:
+            # per-kernel times: same job re-run with CUDA events around every launch (on the launching stream)
+            job = make_job(K)
+            eng.tape_set(tape.u_sched, tape.u_mix, tape.z, tape.u_acc)
+            eng.profile_enable(True)
+            eng.profile_reset()
+            kp = min(K, 4000)      # the event pool holds 32768 launches
+            eng.run(kp)
+            eng.sync()
+            prof = eng.profile_get()
+            eng.profile_enable(False)
+            n_ll, ms_ll = prof["loglik"]
+            n_lg, ms_lg = prof["loglik_grad"]
+            n_mt, ms_mt = prof["metric"]
+            bytes_ll = 8.0 * Nloc * p + 8.0 * Nloc + 8.0 * p             # X + y + theta (SURVEY.md 8d), this rank's shard
+            bytes_lg = 8.0 * Nloc * p + 16.0 * Nloc + 16.0 * p           # + weights written (8N) + gradient partials
+            flops_mt = float(Nloc) * p * (p + 1)                         # algorithmic: lower triangle incl. diagonal, FMA = 2
+            roofs = {}
+            roofs["loglik"] = {"bound": "hbm", "achieved": bytes_ll / (ms_ll / n_ll * 1e-3) * 1e-9 if n_ll else None, "peak": hbm_peak, "unit": "GB/s",
+                               "traffic": None, "kernel": "k_datapass<loglik> (AM step)", "launches": n_ll, "avg_ms": ms_ll / n_ll if n_ll else None,
+                               "algorithmic_bytes": bytes_ll, "peak_source": hbm_src}
+            roofs["loglik_grad"] = {"bound": "hbm", "achieved": bytes_lg / (ms_lg / n_lg * 1e-3) * 1e-9 if n_lg else None, "peak": hbm_peak, "unit": "GB/s",
+                                    "traffic": None, "kernel": "k_datapass<loglik+grad+weights> (SMMALA step)", "launches": n_lg,
+                                    "avg_ms": ms_lg / n_lg if n_lg else None, "algorithmic_bytes": bytes_lg, "peak_source": hbm_src}
+            peak64 = dmma_peak if dmma_peak and dmma_peak > 1.0 else FP64_DMMA_PEAK_TFLOPS_FALLBACK
+            roofs["metric"] = {"bound": "tensor", "achieved": flops_mt / (ms_mt / n_mt * 1e-3) * 1e-12 if n_mt else None, "peak": peak64, "unit": "TFLOP/s",
+                               "traffic": None, "kernel": "k_metric (FP64 DMMA weighted SYRK)", "launches": n_mt, "avg_ms": ms_mt / n_mt if n_mt else None,
+                               "algorithmic_flops": flops_mt, "full_gemm_flops": 2.0 * Nloc * p * p,
+                               "peak_source": "register-only DMMA.8x8x4 loop on all SMs, measured in this run by gamc_probe_fp64_peak "
+                                              f"(DFMA loop: {dfma_peak:.1f} TFLOP/s); tcgen05 has no FP64 kind" if dmma_peak and dmma_peak > 1.0
+                                              else "fallback: profiles/r01_fp64_peak.txt"}
+            for r in roofs.values():
+                if r["achieved"]:
+                    r["frac"] = r["achieved"] / r["peak"]
+                r["traffic_from_profile"] = f"dram__bytes of one launch: see {NCU_TRAFFIC_FILE} (ncu --set full capture of this command; not re-measured in-run)"
+            fam_ms = {k: v[1] for k, v in prof.items()}
+            tot = sum(fam_ms.values()) or 1.0
+            out["kernel_time_share"] = {k: round(v / tot, 4) for k, v in fam_ms.items()}
+            # microseconds per step of every family, max over ranks: what bounds the step at this N
+            us = {k: max_over_ranks(1e3 * v / kp) for k, v in fam_ms.items()}
+            step_kernels = sum(us[k] for k in ("linalg", "land", "smmala_pre", "smmala_post", "am_pre", "am_post", "handover", "reduce", "allreduce"))
+            out["limiter"] = {"us_per_step": {k: round(v, 2) for k, v in us.items()},
+                              "data_parallel_us_per_step": round(us["loglik"] + us["loglik_grad"] + us["metric"], 2),
+                              "replicated_us_per_step": round(step_kernels, 2),
+                              "what": "data-parallel kernels shrink with N; the replicated single-GPU step kernels (factorisation of the p x p metric, "
+                                      "triangular solves, accept/reject) and the peer reduction inside k_land / k_am_post do not (Amdahl term, reference "
+                                      "src/samplers/iterate/GAMC.jl:26-30,43,94)",
+                              "per_launch_us": {k: round(1e3 * v[1] / v[0], 2) for k, v in prof.items() if v[0]}}
+            dom = max(("loglik", "loglik_grad", "metric"), key=lambda k: fam_ms[k])
+            out["roofline"] = roofs[dom]
+            out["roofline_others"] = {k: v for k, v in roofs.items() if k != dom}
+
+        if want_e2e:
+            # e2e: the user-facing call with HOST buffers (pinned): tape H2D + K transitions + chain D2H
+            job = make_job(K, tape=tape)
+            barrier()
+            t0 = time.perf_counter()
+            job.run()                    # gamc_tape_set (H2D) + gamc_run + sync
+            chain = job.output()         # gamc_chain_get (D2H)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            out["e2e"] = {"value": K / dt, "unit": "iters/s", "h2d_bytes_per_step": 8 * (p + 3),
+                          "d2h_bytes_per_step": (8 * p + 1) * (K - K // 5) / K, "acceptance": float(chain.diagnosticvalues.mean()),
+                          "what": "BasicMCJob.run()+output(): gamc_tape_set(host pinned tape) + gamc_run + gamc_chain_get(host chain); "
+                                  "the design matrix is resident (uploaded/generated once per job, as the reference passes it once at job construction)"}
+        return out
+
+    c2 = timed_job("c2", args.logN, args.p, K, W, True, not args.no_e2e)
+    N, p = 1 << args.logN, args.p
+    value, accept = c2.pop("_chain")
+    make_job, tape, kinds, theta0 = c2.pop("_make_job"), c2.pop("_tape"), c2.pop("_kinds"), c2.pop("_theta0")
+    timed_window = c2.pop("timed_window")
     nsave = K - K // 5
-    value, accept = eng.chain_get(0, nsave)
     ess_min = float(np.min(g.ess(value))) if nsave >= 400 else None
 
-    # ---- optional extra, NOT the headline: the same job with gamc_config.reuse_tensor = 1 (the re-evaluation of an unchanged
-    #      current point is skipped on the device; the chain must be bit-identical).  Single GPU only.
+    # ---- optional extra, NOT the headline: the same job with gamc_config.reuse_tensor = 1 (single GPU only)
     reuse = None
     if world == 1:
         job = make_job(K, reuse_tensor=True)
@@ -304,77 +463,18 @@ def run_ours(args):
         reuse = {"value": K / (r0.elapsed_time(r1) * 1e-3), "unit": "iters/s", "chain_bit_identical": bool(np.array_equal(value_r, value) and np.array_equal(accept_r, accept)),
                  "what": "gamc_config.reuse_tensor = 1: an SMMALA step after AM steps does not re-evaluate gradient and metric at the current point "
                          "when no AM proposal was accepted since they were computed (memoisation of a deterministic evaluation; the reference always "
-                         "re-evaluates). Reported for information; `value` above is measured with the literal behaviour."}
+                         "re-evaluates). Reported for information; `value` is measured with the literal behaviour."}
 
-    # ---- per-kernel roofline: same job re-run with CUDA events around every launch (on the launching stream)
-    job = make_job(K)
-    eng.tape_set(tape.u_sched, tape.u_mix, tape.z, tape.u_acc)
-    eng.profile_enable(True)
-    eng.profile_reset()
-    kp = min(K, 5000)      # the event pool holds 32768 launches
-    eng.run(kp)
-    eng.sync()
-    prof = eng.profile_get()
-    eng.profile_enable(False)
-    hbm_peak, hbm_src = measured_peaks()
-    n_ll, ms_ll = prof["loglik"]
-    n_lg, ms_lg = prof["loglik_grad"]
-    n_mt, ms_mt = prof["metric"]
-    bytes_ll = 8.0 * N * p + 8.0 * N + 8.0 * p               # X + y + theta
-    bytes_lg = 8.0 * N * p + 16.0 * N + 16.0 * p             # + weights written (8N) + gradient partials
-    flops_mt = float(N) * p * (p + 1)                        # algorithmic: lower triangle incl. diagonal, FMA = 2
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the round-1 `ncu --set full` capture (profiles/r01_ncu_summary.md);
-    # only valid for the shape it was captured on
-    traffic_ll = 2155891000 + 3613 if (args.logN == 20 and p == 256) else None
-    roof_ll = {"bound": "hbm", "achieved": bytes_ll / (ms_ll / n_ll * 1e-3) * 1e-9 if n_ll else None, "peak": hbm_peak, "unit": "GB/s",
-               "traffic": traffic_ll, "kernel": "k_datapass<loglik> (AM step)", "launches": n_ll, "avg_ms": ms_ll / n_ll if n_ll else None,
-               "algorithmic_bytes": bytes_ll, "peak_source": hbm_src}
-    if roof_ll["achieved"]:
-        roof_ll["frac"] = roof_ll["achieved"] / hbm_peak
-    roof_lg = {"bound": "hbm", "achieved": bytes_lg / (ms_lg / n_lg * 1e-3) * 1e-9 if n_lg else None, "peak": hbm_peak, "unit": "GB/s",
-               "kernel": "k_datapass<loglik+grad+weights> (SMMALA step)", "launches": n_lg, "avg_ms": ms_lg / n_lg if n_lg else None,
-               "algorithmic_bytes": bytes_lg}
-    if roof_lg["achieved"]:
-        roof_lg["frac"] = roof_lg["achieved"] / hbm_peak
-    peak64 = FP64_DMMA_PEAK_TFLOPS_FALLBACK
-    roof_mt = {"bound": "tensor", "achieved": flops_mt / (ms_mt / n_mt * 1e-3) * 1e-12 if n_mt else None, "peak": peak64, "unit": "TFLOP/s",
-               "kernel": "k_metric (FP64 DMMA weighted SYRK)", "launches": n_mt, "avg_ms": ms_mt / n_mt if n_mt else None,
-               "algorithmic_flops": flops_mt, "full_gemm_flops": 2.0 * N * p * p,
-               "peak_source": "measured register-only DMMA.8x8x4 loop on this pool's B200 (profiles/r01_fp64_peak.txt); cuBLAS DGEMM 8192^3 = 35.5"}
-    if roof_mt["achieved"]:
-        roof_mt["frac"] = roof_mt["achieved"] / peak64
-    share = {k: v[1] for k, v in prof.items()}
-    tot = sum(share.values()) or 1.0
-    share = {k: round(v / tot, 4) for k, v in share.items()}
-
-    # ---- e2e: the user-facing call with HOST buffers (pinned): tape H2D + K transitions + chain D2H
-    e2e = None
-    if not args.no_e2e:
-        job = make_job(K, tape=tape)
-        barrier()
-        t0 = time.perf_counter()
-        job.run()                    # gamc_tape_set (H2D) + gamc_run + sync
-        chain = job.output()         # gamc_chain_get (D2H)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * K / dt, "unit": "iters/s", "iters_per_sec": K / dt, "h2d_bytes_per_step": 8 * (p + 3),
-               "d2h_bytes_per_step": (8 * p + 1) * (K - K // 5) / K, "acceptance": float(chain.diagnosticvalues.mean()),
-               "what": "BasicMCJob.run()+output(): gamc_tape_set(host pinned tape) + gamc_run + gamc_chain_get(host chain); "
-                       "the design matrix is resident (uploaded/generated once per job, as the reference passes it once at job construction)"}
-
-    # ---- ESS/sec (the second half of BASELINE.json's metric) from a chain long enough for the estimate to mean something:
-    # min over coordinates of the IMSE effective sample size of the post-burn-in samples / device seconds of the whole run
-    # (examples/logistic_regression/src/GAMC/table.jl:28-31)
+    # ---- ESS/sec (the second half of BASELINE.json's metric): min over coordinates of the IMSE effective sample size of the
+    # post-burn-in samples / device seconds of the whole run (examples/logistic_regression/src/GAMC/table.jl:28-31)
     ess_long = None
     if world == 1 and args.ess_steps > 0:
         n_l, b_l = args.ess_steps, args.ess_steps // 6
         sampler, tuner, _ = bench_config(g, n_l, args.am_mode)
+        model = g.LogisticModel(synth={"seed": SEED, "N": N, "p": p, "theta_true": theta_inputs(p)[0]}, lam=LAMBDA)
         job = g.BasicMCJob(model, sampler, g.BasicMCRange(n_l, b_l), {"p": theta0}, tuner=tuner, engine=eng, tape_seed=SEED + 11)
         eng.tape_generate(n_l, SEED + 11)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(stream)
         eng.run(n_l)
@@ -385,11 +485,14 @@ def run_ours(args):
         em = float(np.min(g.ess(v_l)))
         ess_long = {"nsteps": n_l, "burnin": b_l, "seconds": sec, "iters_per_sec": n_l / sec, "ess_min": em, "ess_per_sec": em / sec,
                     "acceptance": float(a_l.mean()), "final_step": eng.state().step}
+    clk = clocks.stop(window=timed_window)
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only), bounded sample
     cpu = None
+    e2e = c2.get("e2e")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        Xh, yh = eng.read_rows(0, N)      # identical data: read the device-generated shard back
+        cores = use_all_host_threads()
+        Xh, yh = eng.read_rows(0, N)      # identical data: read the device-generated matrix back
         # one-time cost a host-data user pays at job construction (the reference passes X once, in the model): upload of the
         # design matrix from (pageable) host memory through gamc_target_logistic
         if e2e is not None:
@@ -401,41 +504,136 @@ def run_ours(args):
             eng_up.close()
             e2e["dataset_h2d_seconds"] = up
             e2e["dataset_bytes"] = int(Xh.nbytes + yh.nbytes)
-            e2e["value_including_dataset_upload"] = K / (K / e2e["iters_per_sec"] + up)
-        costs = cpu_iteration_costs(Xh, yh, theta0, p)
-        rate, _ = compose_cpu_rate(costs, kinds)
-        cpu = {"value": rate, "unit": "iters/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"14 real oracle iterate! transitions at full N=2^{args.logN}, p={p} (reference-shaped callbacks), per-kind means "
-                         f"composed over the same K={K}-step branch sequence", "per_kind_seconds": costs}
+            e2e["value_including_dataset_upload"] = K / (K / e2e["value"] + up)
+        rate, info = cpu_arm(Xh, yh, theta0, p, K)
+        cpu = {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", **info}
         del Xh, yh
 
+    # ---- C3 (BASELINE configs[2]): N = 2^24, p = 512, the same strong split; and the weak-scaling extra
+    c3 = weak = None
+    if not args.no_c3:
+        free_b, _tot = torch.cuda.mem_get_info(local)
+        need = 8.0 * ((1 << args.c3_logN) // world) * 512 * 1.02 + (2 << 30)
+        eng.close()
+        eng = new_engine()
+        free_b, _tot = torch.cuda.mem_get_info(local)
+        if free_b > need:
+            K3 = max(4, min(K, args.c3_steps))
+            c3 = timed_job("c3", args.c3_logN, 512, K3, 3, True, False)
+            for k in ("_chain", "_make_job", "_tape", "_kinds", "_theta0", "timed_window"):
+                c3.pop(k, None)
+            c3["workload"] = f"C3: logistic N=2^{args.c3_logN} rows in total, p=512, FP64, same sampler, {K3} steps after 3 warm-up steps, row-sharded x{world}"
+        else:
+            c3 = {"skipped": f"needs {need / 2**30:.1f} GiB per GPU, {free_b / 2**30:.1f} GiB free"}
+    if world > 1 and not args.no_weak:
+        eng.close()
+        eng = new_engine()
+        Nw = 1 << args.logN
+        tt, th0 = theta_inputs(p)
+        eng.target_logistic_synth(SEED, rank * Nw, Nw, p, tt, LAMBDA)
+        init_comm(eng, rank, world)
+        model = g.LogisticModel(synth={"seed": SEED, "N": Nw * world, "p": p, "theta_true": tt}, lam=LAMBDA)
+        sampler, tuner, rng = bench_config(g, max(W, 8), args.am_mode)
+        g.BasicMCJob(model, sampler, rng, {"p": th0}, tuner=tuner, engine=eng, tape_seed=SEED + 7).run()
+        sampler, tuner, rng = bench_config(g, K, args.am_mode)
+        g.BasicMCJob(model, sampler, rng, {"p": th0}, tuner=tuner, engine=eng)
+        eng.tape_set(tape.u_sched, tape.u_mix, tape.z, tape.u_acc)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        eng.run(K)
+        e1.record(stream)
+        barrier()
+        msw = max_over_ranks(e0.elapsed_time(e1))
+        weak = {"rows_per_gpu": Nw, "global_rows": Nw * world, "ms_per_step": msw / K, "iters_per_sec": K / (msw * 1e-3),
+                "shard_iterations_per_sec": world * K / (msw * 1e-3),
+                "what": "round-1 definition, for information: 2^20 rows PER GPU (the problem grows with N); iters_per_sec is the chain's rate"}
+
     if rank == 0:
+        par_ok = None
+        if parity is not None:
+            par_ok = bool(parity["ok"] and c2.get("reduced_vs_single_gpu", {"ok": True})["ok"] and c2["chain_bit_identical_across_ranks"]
+                          and (c3 is None or "skipped" in c3 or (c3.get("reduced_vs_single_gpu", {"ok": True})["ok"] and c3["chain_bit_identical_across_ranks"])))
+            parity["ok"] = par_ok
+            parity["c2_reduced_vs_single_gpu"] = c2.get("reduced_vs_single_gpu")
+            parity["c2_chain_bit_identical_across_ranks"] = c2["chain_bit_identical_across_ranks"]
+        peer = eng.comm_peer_path() if world > 1 else 0
         line = {
-            "metric": "gamc_iters_per_sec", "value": world * iters_per_sec, "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "with_tensor_reuse": reuse,
+            "metric": "gamc_iters_per_sec", "value": c2["iters_per_sec"], "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": c2["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (Philox4x32-10 keyed by global row/col, generated on device)",
-            "config": {"workload": f"C2: logistic N=2^{args.logN} rows per GPU, p={p}, FP64, GAMC rand_exp_decay(a=10), single chain",
-                       "rows_per_gpu": N, "global_rows": N * world, "p": p, "parallelism": (f"row-sharded x{world}; [ll, grad, metric] of SMMALA steps summed over "
-                                       + ("NVLink peer memory inside k_land" if eng.comm_peer_path() & 2 else "NCCL all-reduce")
-                                       + "; AM-step scalar over "
-                                       + ("NVLink peer mailboxes inside k_am_post" if eng.comm_peer_path() & 1 else "NCCL")) if world > 1 else "single GPU",
-                       "l2": "inputs (2.1 GB design matrix per pass) larger than L2; no flush needed",
-                       "value_definition": "iters/s x n_gpus (each GPU processes one 2^20-row shard of every iteration)",
+            "config": {"workload": f"C2: logistic N=2^{args.logN} rows in total, p={p}, FP64, GAMC rand_exp_decay(a=10), single chain",
+                       "global_rows": N, "rows_per_gpu": c2["rows_per_gpu"], "p": p,
+                       "parallelism": (f"the same 2^{args.logN} rows row-sharded x{world}; [ll, grad, metric] of SMMALA steps summed over "
+                                       + ("NVLink peer memory inside k_land" if peer & 2 else "NCCL all-reduce") + "; AM-step scalar over "
+                                       + ("NVLink peer mailboxes inside k_am_post" if peer & 1 else "NCCL")) if world > 1 else "single GPU",
+                       "l2": "inputs (the design-matrix shard streamed by every pass: 2.1 GB at 1 GPU, 268 MB at 8) larger than L2; no flush needed",
+                       "value_definition": "iterations per second of the one chain on the fixed 2^20-row problem (strong scaling)",
                        "am_mode": args.am_mode, "nsteps": K, "burnin": K // 5},
-            "iters_per_sec": iters_per_sec,
-            "ess_per_sec": ess_long["ess_per_sec"] if ess_long else ((ess_min / (ms * 1e-3)) if ess_min else None),
+            "iters_per_sec": c2["iters_per_sec"],
+            "ess_per_sec": ess_long["ess_per_sec"] if ess_long else ((ess_min / (c2["ms"] * 1e-3)) if ess_min else None),
             "ess": ess_long, "ess_min_timed_run": ess_min,
-            "acceptance": float(accept.mean()), "n_smmala": int(kinds.sum()), "n_am": int(K - kinds.sum()),
-            "final_step": st.step, "updatetensorcount": st.updatetensorcount,
-            "gpu_launches": int(launches),
-            "roofline": roof_ll, "roofline_grad": roof_lg, "roofline_metric": roof_mt, "kernel_time_share": share,
+            "acceptance": c2["acceptance"], "n_smmala": c2["n_smmala"], "n_am": c2["n_am"],
+            "final_step": c2["final_step"], "updatetensorcount": c2["updatetensorcount"],
+            "gpu_launches": c2["gpu_launches"],
+            "roofline": c2["roofline"], "roofline_others": c2["roofline_others"], "kernel_time_share": c2["kernel_time_share"],
+            "limiter": c2["limiter"], "fp64_probe": {"dmma_tflops": dmma_peak, "dfma_tflops": dfma_peak},
+            "parity": parity, "c3": c3, "weak": weak, "with_tensor_reuse": reuse,
             "clocks": clk, "e2e": e2e, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_block(g, eng, rank, world, dev, dist, args, all_ranks_ok, bitwise_equal_across_ranks, init_comm, shard_rows):
+    """Correctness inside the bench line (what tools/multigpu_check.py checks, on the ranks of THIS run): a small logistic problem
+    row-sharded over the ranks -- reduced evaluation and this rank's partials against the CPU oracle, the chain against the
+    oracle's on the same tape, and bit-identical chains on every rank."""
+    import torch
+    N, p, nsteps, burnin, seed = 20000 + 7, 96, 300, 60, 20260101
+    tt = g.synth_theta_true(seed, p)
+    theta = tt + 0.03 * np.random.default_rng(1).standard_normal(p)
+    r0, r1 = shard_rows(N, world, rank)
+    eng.target_logistic_synth(seed, r0, r1 - r0, p, tt, 100.0)
+    if world > 1:
+        init_comm(eng, rank, world)
+        eng._comm_done = True
+    lt, grad, G = eng.eval_upto_tensor(theta)
+    ll, gl, Gl = eng.eval_partials(theta)
+    sampler = g.GAMC(update=g.rand_exp_decay_update(10.0), driftstep=0.02, minorscale=0.001, c=0.01, am_mode=args.am_mode)
+    tuner = g.GAMCTuner(g.VanillaMCTuner(), g.VanillaMCTuner(), g.AcceptanceRateMCTuner(0.35))
+    tape = g.RandomTape(nsteps, p, seed=3)
+    job = g.BasicMCJob(g.LogisticModel(lam=100.0), sampler, g.BasicMCRange(nsteps, burnin), {"p": theta}, tuner=tuner, tape=tape, engine=eng)
+    job.run()
+    chain = job.output()
+    same = bitwise_equal_across_ranks(chain.value)
+    ok, errs, secs = True, {}, None
+    t0 = time.perf_counter()
+    import oracle as o
+    if rank == 0:
+        use_all_host_threads()
+        X, y, _ = o.synth_logistic(seed, N, p, theta_true=tt)
+        lt0, g0, G0 = o.LogisticTarget(X, y, 100.0).uptotensorlogtarget(theta)
+        errs = {"logtarget": abs(lt - lt0) / abs(lt0), "grad": relerr(grad, g0), "metric": relerr(G, G0)}
+        ll0, gl0, Gl0 = o.logistic_partials(theta, X[r0:r1], y[r0:r1])
+        errs.update({"shard_ll": abs(ll - ll0) / abs(ll0), "shard_grad": relerr(gl, gl0), "shard_metric": relerr(Gl, Gl0)})
+        osam = o.GAMCOracle(o.LogisticTarget(X, y, 100.0), theta, nsteps, burnin, update="rand_exp_decay_update!", update_params=(10.0, 0.0),
+                            driftstep=0.02, minorscale=0.001, c=0.01,
+                            tuner=o.GAMCTuner(o.VanillaMCTuner(), o.VanillaMCTuner(), o.AcceptanceRateMCTuner(0.35)))
+        v, a, _ = osam.run(o.RandomTape(nsteps, p, seed=3))
+        decisions = bool(np.array_equal(chain.diagnosticvalues.ravel(), a))
+        errs["chain"] = relerr(chain.value, v) if decisions else float("inf")
+        ok = decisions and max(errs[k] for k in ("logtarget", "grad", "metric", "shard_ll", "shard_grad", "shard_metric")) <= 1e-10 and errs["chain"] <= 1e-8
+        secs = time.perf_counter() - t0
+    ok = all_ranks_ok(ok) and same
+    return {"ok": ok, "n_ranks": world, "shape": f"N={N}, p={p}, {nsteps} steps, am_mode={args.am_mode}", "relerr_vs_oracle": errs,
+            "tolerance": {"evaluation": 1e-10, "chain": 1e-8, "decisions": "identical"},
+            "chain_bit_identical_across_ranks": same, "oracle_seconds": secs,
+            "what": "small logistic problem row-sharded over the ranks of this run: all-reduced [logtarget, grad, metric] and this rank's "
+                    "likelihood partials vs the CPU oracle (1e-10), the GAMC chain on a shared tape vs the oracle's (identical accept decisions), "
+                    "chains bit-identical on every rank"}
 
 
 def main():

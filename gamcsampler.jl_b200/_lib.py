@@ -16,12 +16,15 @@ GAMC_OK, GAMC_INVALID_ARG, GAMC_NONFINITE_INIT, GAMC_NOT_POSDEF, GAMC_CUDA_ERROR
     GAMC_UNSUPPORTED_SHAPE, GAMC_NOT_READY = range(8)
 
 # kernel families (gamc_kernel_family)
-K_LOGLIK, K_LOGLIK_GRAD, K_METRIC, K_REDUCE, K_LINALG, K_ALLREDUCE = range(6)
-KERNEL_FAMILIES = ("loglik", "loglik_grad", "metric", "reduce", "linalg", "allreduce")
+K_LOGLIK, K_LOGLIK_GRAD, K_METRIC, K_REDUCE, K_LINALG, K_ALLREDUCE, K_LAND, K_SMMALA_PRE, K_SMMALA_POST, K_AM_PRE, K_AM_POST, \
+    K_HANDOVER = range(12)
+KERNEL_FAMILIES = ("loglik", "loglik_grad", "metric", "reduce", "linalg", "allreduce", "land", "smmala_pre", "smmala_post",
+                   "am_pre", "am_post", "handover")
 
 # array ids (gamc_array_id)
 ARR_VALUE, ARR_GRADLOGTARGET, ARR_TENSORLOGTARGET, ARR_LASTMEAN, ARR_SECONDLASTMEAN, ARR_OLDINVTENSOR, \
-    ARR_CHOLINVTENSOR, ARR_OLDFIRSTTERM, ARR_PROPOSED_VALUE = range(9)
+    ARR_CHOLINVTENSOR, ARR_OLDFIRSTTERM, ARR_PROPOSED_VALUE, ARR_GRADLOGLIKELIHOOD, ARR_GRADLOGPRIOR, \
+    ARR_TENSORLOGLIKELIHOOD, ARR_TENSORLOGPRIOR = range(13)
 
 
 class GamcError(RuntimeError):
@@ -121,6 +124,16 @@ SIGNATURES = {
     "gamc_profile_get": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_int64), _DP]),
     "gamc_profile_reset": (C.c_int, [_H]),
     "gamc_launch_count": (C.c_int, [_H, C.POINTER(C.c_int64)]),
+    "gamc_target_device_callback": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p]),
+    "gamc_comm_set_timeout": (C.c_int, [_H, C.c_double]),
+    "gamc_set_schedule_callback": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "gamc_set_state": (C.c_int, [_H, C.POINTER(StateScalars), _DP, _DP, _DP, _DP]),
+    "gamc_get_monitor": (C.c_int, [_H, _DP, _DP]),
+    "gamc_chain_get_logtarget": (C.c_int, [_H, C.c_int64, C.c_int64, _DP]),
+    "gamc_tune_log_get": (C.c_int, [_H, _DP, C.c_int64, C.POINTER(C.c_int64)]),
+    "gamc_probe_fp64_peak": (C.c_int, [_H, _DP, _DP]),
+    "gamc_tape_get": (C.c_int, [_H, C.c_int64, C.c_int64, _DP, _DP, _DP, _DP]),
+    "gamc_batched_target_logistic": (C.c_int, [_H, _DP, C.c_int64, _DP, C.c_int64, C.c_int32, C.c_double]),
 }
 
 _lib = None
@@ -129,6 +142,11 @@ _lib = None
 # gamc_target_fn of include/gamc_b200.h
 TARGET_FN = C.CFUNCTYPE(C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
                         C.POINTER(C.c_double), C.c_void_p)
+
+
+# gamc_target_enqueue_fn / gamc_schedule_fn of include/gamc_b200.h
+TARGET_ENQUEUE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)
+SCHEDULE_FN = C.CFUNCTYPE(C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_void_p)
 
 
 def load():

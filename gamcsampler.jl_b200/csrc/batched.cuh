@@ -24,7 +24,7 @@ struct BatchedCfg {
   int p, ld;                    // dimension, leading dimension (odd)
   int nchains;
   long long chain_offset;       // global index of this rank's first chain (keys the Philox streams; chains are sharded across ranks)
-  int target;                   // 0 = mvt, 1 = rv
+  int target;                   // 0 = mvt, 1 = rv, 3 = logistic regression
   int transform;                // 0 = none, 1 = softabs
   double softabs_alpha;
   // sampler / tuner / range (same meaning as gamc_config)
@@ -37,6 +37,8 @@ struct BatchedCfg {
   double nu, logconst; const double* Sinv;   // n x n row-major == column-major (symmetric)
   // rv target
   const double* rv_t; const double* rv_obs; const double* rv_sig; long long rv_n; int rv_npl; double rv_lognorm;
+  // logistic target (small N, small p): X is N x p column-major, y in {0,1}, lambda = prior variance
+  const double* lg_X; const double* lg_y; int lg_n; double lg_lambda;
   // tape (may be null -> Philox with `seed`)
   const double* tape_usched; const double* tape_umix; const double* tape_uacc; const double* tape_z;   // [chain][t] / [chain][t][p]
   long long tape_len;           // iterations per chain on the tape
@@ -245,6 +247,46 @@ __device__ inline double mvt_eval(const BatchedCfg& C, const double* x, double* 
     if (level >= 2 && lane < p) {
       const double cc = 2.0 / (C.nu + q);
       for (int j = 0; j < p; ++j) H[lane * ld + j] = a * (C.Sinv[lane * p + j] - cc * vi * vtmp[j]);
+    }
+    __syncwarp();
+  }
+  return lt;
+}
+
+// Bayesian logistic regression of examples/logistic_regression/src/GAMC/simulations.jl:25-37 for the as-shipped sizes (N = 200,
+// p = 4): ploglikelihood + plogprior, pgradlogtarget, ptensorlogtarget.  One warp; lanes stride the observations, every sum ends in
+// a warp reduction.  wr = [w(N) | r(N)] shared scratch: weights sigma(1-sigma) and residuals y - sigma of the first pass.
+__device__ inline double logi_eval(const BatchedCfg& C, const double* x, double* g, double* H, double* wr, int level, int lane) {
+  const int p = C.p, ld = C.ld, N = C.lg_n;
+  const double* X = C.lg_X; const double* y = C.lg_y;
+  double ll = 0.0;
+  for (int n = lane; n < N; n += 32) {
+    double eta = 0.0;
+    for (int j = 0; j < p; ++j) eta = fma(X[n + (size_t)j * N], x[j], eta);
+    double sig, sp;
+    sigmoid_softplus(eta, sig, sp);
+    ll += y[n] * eta - sp;
+    if (level >= 1) { wr[n] = sig * (1.0 - sig); wr[N + n] = y[n] - sig; }
+  }
+  ll = warp_sum(ll);
+  const double tt = warp_sum(lane < p ? x[lane] * x[lane] : 0.0);
+  const double lt = ll - 0.5 * (tt / C.lg_lambda + p * log(2.0 * 3.14159265358979323846 * C.lg_lambda));
+  if (level >= 1) {
+    __syncwarp();
+    for (int j = 0; j < p; ++j) {
+      double s = 0.0;
+      for (int n = lane; n < N; n += 32) s = fma(X[n + (size_t)j * N], wr[N + n], s);
+      s = warp_sum(s);
+      if (lane == 0) g[j] = s - x[j] / C.lg_lambda;
+    }
+    if (level >= 2) {
+      for (int i = 0; i < p; ++i)
+        for (int j = 0; j <= i; ++j) {
+          double s = 0.0;
+          for (int n = lane; n < N; n += 32) s = fma(X[n + (size_t)i * N] * wr[n], X[n + (size_t)j * N], s);
+          s = warp_sum(s);
+          if (lane == 0) { if (i == j) s += 1.0 / C.lg_lambda; H[i * ld + j] = s; H[j * ld + i] = s; }
+        }
     }
     __syncwarp();
   }
@@ -665,6 +707,7 @@ __device__ inline double bt_eval_point(const BatchedCfg& C, const BState& S, con
   *ok = 1;
   double lt;
   if (TGT == 0) lt = mvt_eval(C, x, g, (level >= 2) ? W : nullptr, S.vec(BV_T1), level >= 2 ? 2 : 0, lane);
+  else if (TGT == 3) lt = logi_eval(C, x, g, W, Wk.rvconst, level >= 2 ? 2 : 0, lane);
   else lt = rv_eval_master<(TGT == 2 ? 2 : 1)>(C, S, Wk, xvec, gradv, W, level >= 2 ? 2 : 0, lane);
   if (!isfinite(lt)) { *ok = 0; return lt; }
   if (level >= 2) {   // finite gradient / tensor (initialize! asserts, GAMC.jl:168-170; otherwise a rejection)
@@ -731,15 +774,15 @@ __device__ inline void bt_tail(const BatchedCfg& C, const BState& S, int chain, 
 }
 
 // mode: 0 = run n_iters transitions, 1 = initialise (initialize! + sampler_state) from theta0 [p x nchains]
-__host__ __device__ inline size_t bt_smem_bytes(int blob_doubles, int nthreads) {
-  return sizeof(double) * ((size_t)blob_doubles + (size_t)RV_MAXRED * (nthreads / 32) + 8 + (nthreads > 32 ? RV_CONST_DOUBLES : 0));
+__host__ __device__ inline size_t bt_smem_bytes(int blob_doubles, int nthreads, int extra_doubles = 0) {
+  return sizeof(double) * ((size_t)blob_doubles + (size_t)RV_MAXRED * (nthreads / 32) + 8 + (nthreads > 32 ? RV_CONST_DOUBLES : 0) + (size_t)extra_doubles);
 }
 
 template <int TGT>
 #ifndef GAMC_RV_MINBLOCKS
 #define GAMC_RV_MINBLOCKS 4     // resident CTAs per SM the RV kernels are compiled for: 128 registers (spills) but twice the warps of the uncapped build; measured 51.9 k (2 CTAs/SM) -> 60.9 k (3) -> 70.9 k (4) chain-iterations/s on C5
 #endif
-__global__ void __launch_bounds__(TGT == 0 ? 32 : 128, TGT == 0 ? 1 : GAMC_RV_MINBLOCKS) k_batched_gamc(BatchedCfg C, int mode, long long n_iters, const double* __restrict__ theta0) {
+__global__ void __launch_bounds__((TGT == 0 || TGT == 3) ? 32 : 128, (TGT == 0 || TGT == 3) ? 1 : GAMC_RV_MINBLOCKS) k_batched_gamc(BatchedCfg C, int mode, long long n_iters, const double* __restrict__ theta0) {
   extern __shared__ __align__(16) double bsm[];
   const int chain = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (chain >= C.nchains) return;
@@ -752,7 +795,8 @@ __global__ void __launch_bounds__(TGT == 0 ? 32 : 128, TGT == 0 ? 1 : GAMC_RV_MI
   Wk.bcast = Wk.red + RV_MAXRED * (blockDim.x >> 5);
   Wk.cmd = reinterpret_cast<int*>(Wk.bcast + 4);
   Wk.rvconst = Wk.bcast + 8;
-  if (TGT != 0 && warp != 0) {
+  constexpr bool RV = (TGT == 1 || TGT == 2);
+  if (RV && warp != 0) {
     // worker warps: wait for an evaluation request from warp 0, take part in it, repeat
     while (true) {
       __syncthreads();                               // barrier A
@@ -762,7 +806,7 @@ __global__ void __launch_bounds__(TGT == 0 ? 32 : 128, TGT == 0 ? 1 : GAMC_RV_MI
     }
     return;
   }
-  auto release_workers = [&]() { if (TGT != 0) { if (lane == 0) Wk.cmd[0] = 0; __syncthreads(); } };
+  auto release_workers = [&]() { if (RV) { if (lane == 0) Wk.cmd[0] = 0; __syncthreads(); } };
   if (mode == 1) {
     for (int i = lane; i < C.blob_doubles; i += 32) bsm[i] = 0.0;
     __syncwarp();

@@ -10,9 +10,9 @@ namespace gamc {
 // Phase clocks (debug builds only, -DGAMC_PHASE_CLOCKS): thread 0 accumulates clock64 deltas between PHASE() marks of
 // the single-CTA step kernels; read back with gamc_debug_phases().  Compiled out of the product library.
 #ifdef GAMC_PHASE_CLOCKS
-__device__ long long g_phase_acc[64];
-__device__ long long g_phase_cnt[64];
-__device__ long long g_phase_last;
+static __device__ long long g_phase_acc[64];
+static __device__ long long g_phase_cnt[64];
+static __device__ long long g_phase_last;
 #define GAMC_PHASE_BEGIN() do { __syncthreads(); if (threadIdx.x == 0) g_phase_last = clock64(); } while (0)
 #define GAMC_PHASE(k) do { __syncthreads(); if (threadIdx.x == 0) { const long long now_ = clock64(); \
     g_phase_acc[k] += now_ - g_phase_last; g_phase_cnt[k] += 1; g_phase_last = now_; } } while (0)
@@ -52,6 +52,7 @@ struct DevState {
   double mix_scratch;
   int lcur;           // which of the three AM factor buffers holds chol(C) (am_mode 2 rotates them; otherwise 0)
   int spec_err[2];    // speculative factor update of outcome 0 (accept) / 1 (reject) failed
+  long long tune_events;   // burn-in tuning events so far (records of the tune log)
   int tensor_valid;   // slot `cur` (gradient, metric, factor, G^-1 grad) belongs to the current point: no AM accept since it was filled
 };
 

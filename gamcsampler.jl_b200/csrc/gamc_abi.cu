@@ -10,16 +10,16 @@
 #include <string>
 #include <vector>
 #include <set>
+#include <map>
 #include <dlfcn.h>
 
-#include "../../include/gamc_b200.h"
+#include "ctx.h"
 #include "common.cuh"
 #include "datapass.cuh"
 #include "metric.cuh"
 #include "metric_plan.h"
 #include "sampler.cuh"
 #include "synth.cuh"
-#include "batched.cuh"
 
 using namespace gamc;
 
@@ -67,16 +67,11 @@ typedef CUresult (*fn_cuTensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType,
                                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 fn_cuTensorMapEncodeTiled g_encode = nullptr;
 
-constexpr int PROF_POOL = 32768;
+constexpr int PROF_POOL = GAMC_PROF_POOL;
 }  // namespace
 
-struct gamc_ctx {
-  int device = 0;
-  int num_sms = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = true;
+struct gamc_ctx : gamc_ctx_base {
   cudaStream_t side = nullptr; cudaEvent_t ev_main = nullptr, ev_side = nullptr;   // am_mode 2: speculative factor updates overlap the data pass
-  std::string err;
 
   // target
   long long N = 0; int p = 0; long long ld = 0; double lambda = 1.0;
@@ -107,33 +102,28 @@ struct gamc_ctx {
   long long tape_gen_total = 0;
   // chain
   long long chain_cap = 0; double* d_chain = nullptr; unsigned char* d_accept = nullptr;
-  // batched chains
-  BatchedCfg bcfg{}; long long bcfg_chain_offset = 0; bool batched_target = false, batched_ready = false; double* d_Sinv = nullptr; double* d_blob = nullptr;
-  double* d_bchain = nullptr; unsigned char* d_baccept = nullptr; double* d_btape = nullptr; long long btape_doubles = 0;
   // comm
-  ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
+  ncclComm_t comm = nullptr;
   // peer mailboxes (NVLink peer memory, CUDA IPC): scalar all-reduce of the AM step without NCCL or k_reduce
   PeerMail* mbox = nullptr; PeerMail** d_peers = nullptr; void* peer_ptr[32] = {nullptr}; bool p2p_ready = false; unsigned long long p2p_seq = 0;
   // peer landing: two reduced-evaluation buffers per rank, mapped by every peer; k_land sums them over NVLink (no NCCL on the step path)
   double* xR = nullptr; size_t xR_stride = 0; int xR_p = 0; double** d_peerR = nullptr; void* peerR_ptr[32] = {nullptr}; bool land_p2p = false;
   unsigned long long land_seq = 0;
-  // generic target: the host evaluates the model (gamc_target_callback)
+  // generic target: the host evaluates the model (gamc_target_callback) or enqueues device work (gamc_target_device_callback)
   long long launches_cb = 0;
   gamc_target_fn cb = nullptr; void* cb_user = nullptr; double* cb_theta = nullptr; double* cb_R = nullptr;
-  // profiling
-  bool prof = false; std::vector<cudaEvent_t> ev0, ev1; std::vector<int> ev_family; int ev_used = 0;
-  long long launches = 0;
-  std::set<const void*> attr_set;   // kernels whose dynamic shared-memory limit was raised on this device
+  gamc_target_enqueue_fn dcb = nullptr; void* dcb_user = nullptr;
+  // user schedule (gamc_set_schedule_callback)
+  gamc_schedule_fn sched_fn = nullptr; void* sched_user = nullptr;
+  // peer waits
+  unsigned long long peer_timeout_ns = 30000000000ull; double* d_barrier = nullptr;
+  // burn-in report records, per-sample log-target
+  double* d_tune_log = nullptr; int tune_log_cap = 0; double* d_chain_lt = nullptr; double* d_monitor = nullptr;
+  long long chain_saved_seen = 0;           // DevState.chain_saved at the last check_device_error
 };
 
-#define CUDA_TRY(h, call)                                                                         \
-  do {                                                                                            \
-    cudaError_t e__ = (call);                                                                     \
-    if (e__ != cudaSuccess) {                                                                     \
-      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                             \
-      return GAMC_CUDA_ERROR;                                                                     \
-    }                                                                                             \
-  } while (0)
+gamc_ctx_base* gamc_base(gamc_handle h) { return h; }
+static inline bool generic_target(const gamc_ctx* h) { return h->cb != nullptr || h->dcb != nullptr; }
 
 // Debug aid (GAMC_DEBUG=1): synchronise and report after every launch.
 static bool g_debug = getenv("GAMC_DEBUG") != nullptr;
@@ -147,31 +137,7 @@ static bool g_debug = getenv("GAMC_DEBUG") != nullptr;
     }                                                                                             \
   } while (0)
 
-#define REQUIRE(h, cond, status, msg)                                                             \
-  do { if (!(cond)) { (h)->err = (msg); return (status); } } while (0)
-
 namespace {
-
-struct ProfScope {
-  gamc_ctx* h; int idx = -1;
-  ProfScope(gamc_ctx* h_, int family) : h(h_) {
-    h->launches += 1;
-    if (h->prof && h->ev_used < PROF_POOL) {
-      idx = h->ev_used++;
-      h->ev_family[idx] = family;
-      cudaEventRecord(h->ev0[idx], h->stream);
-    }
-  }
-  ~ProfScope() { if (idx >= 0) cudaEventRecord(h->ev1[idx], h->stream); }
-};
-
-gamc_status ensure_attr(gamc_ctx* h, const void* kern, size_t bytes) {
-  if (h->attr_set.count(kern)) return GAMC_OK;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return GAMC_CUDA_ERROR; }
-  h->attr_set.insert(kern);
-  return GAMC_OK;
-}
 
 bool ensure_encode(gamc_ctx* h) {
   if (g_encode) return true;
@@ -218,7 +184,7 @@ void free_target(gamc_ctx* h) {
   cudaFree(h->d_plans); cudaFree(h->d_coords); cudaFree(h->ws); cudaFree(h->d_ints); h->d_plans = nullptr; h->d_coords = nullptr; h->ws = nullptr; h->d_ints = nullptr;
   cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0; h->R = nullptr; h->vecs = h->mats = nullptr; h->d_state = nullptr;
   cudaFree(h->theta_eval); h->theta_eval = nullptr;
-  cudaFreeHost(h->cb_theta); cudaFreeHost(h->cb_R); h->cb_theta = h->cb_R = nullptr; h->cb = nullptr; h->cb_user = nullptr;
+  cudaFreeHost(h->cb_theta); cudaFreeHost(h->cb_R); h->cb_theta = h->cb_R = nullptr; h->cb = nullptr; h->cb_user = nullptr; h->dcb = nullptr; h->dcb_user = nullptr;
 }
 
 void free_peer_landing(gamc_ctx* h) {
@@ -330,8 +296,8 @@ void setup_peer_mailboxes(gamc_ctx* h) {
 }
 
 void free_sampler(gamc_ctx* h) {
-  cudaFree(h->d_chain); cudaFree(h->d_accept);
-  h->B = Bufs{}; h->d_chain = nullptr; h->d_accept = nullptr;
+  cudaFree(h->d_chain); cudaFree(h->d_accept); cudaFree(h->d_tune_log); cudaFree(h->d_chain_lt);
+  h->B = Bufs{}; h->d_chain = nullptr; h->d_accept = nullptr; h->d_tune_log = nullptr; h->d_chain_lt = nullptr; h->tune_log_cap = 0;
   h->sampler_ready = false;
 }
 
@@ -448,6 +414,13 @@ gamc_status launch_level2(gamc_ctx* h, const double* d_theta, const int* skip = 
 // skip_reduce (level 0, single GPU only): leave the per-CTA partials for k_am_post to sum.
 gamc_status eval_device(gamc_ctx* h, const double* d_theta, int level, bool allreduce, bool skip_reduce = false) {
   if (h->cb) return eval_callback(h, d_theta, level);
+  if (h->dcb) {
+    // device-side generic target: the user's work is enqueued on the handle's stream straight into the landing buffer
+    const int rc = h->dcb(d_theta, h->p, level, h->R, (void*)h->stream, h->dcb_user);
+    if (rc != 0) { h->err = "device target callback returned " + std::to_string(rc); return GAMC_INVALID_ARG; }
+    h->launches_cb += 1;
+    return GAMC_OK;
+  }
   gamc_status s = level >= 2 ? launch_level2(h, d_theta) : launch_datapass(h, d_theta, level >= 1);
   if (s != GAMC_OK) return s;
   if (skip_reduce && level == 0 && (!h->comm || h->p2p_ready)) return GAMC_OK;
@@ -576,6 +549,7 @@ gamc_status check_device_error(gamc_ctx* h) {
   DevState st;
   CUDA_TRY(h, cudaMemcpyAsync(&st, h->B.st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->chain_saved_seen = st.chain_saved;
   if (st.error_flag == GAMC_NONFINITE_INIT) {
     h->err = "Log-target, gradient or tensor of log-target not finite: initial values out of support";
     return GAMC_NONFINITE_INIT;
@@ -610,9 +584,26 @@ bool schedule_decision(const gamc_config& c, long long i, long long tot, double 
   }
 }
 
+// the branch of iteration t: the user's schedule function if one is set (GAMC.update!::Function), else the descriptor
+bool branch_decision(const gamc_ctx* h, long long t, double u) {
+  if (h->sched_fn) return h->sched_fn((int64_t)t, (int64_t)h->cfg.nsteps, u, h->sched_user) != 0;
+  return schedule_decision(h->cfg, t, h->cfg.nsteps, u);
+}
+
+// Stream-ordered barrier over the ranks of a multi-GPU job (one-element NCCL all-reduce): no rank's later kernels start before
+// every rank's earlier work is enqueued and reached, so the in-kernel peer waits only ever cover kernel-time skew.
+gamc_status comm_stream_barrier(gamc_ctx* h) {
+  if (!h->comm) return GAMC_OK;
+  if (!h->d_barrier) { CUDA_TRY(h, cudaMalloc(&h->d_barrier, sizeof(double))); CUDA_TRY(h, cudaMemsetAsync(h->d_barrier, 0, sizeof(double), h->stream)); }
+  ProfScope ps(h, GAMC_K_ALLREDUCE);
+  const int r = g_nccl.AllReduce(h->d_barrier, h->d_barrier, 1, NCCL_DOUBLE, NCCL_SUM, h->comm, h->stream);
+  if (r != 0) { h->err = std::string("ncclAllReduce (barrier): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return GAMC_NCCL_ERROR; }
+  return GAMC_OK;
+}
+
 // move a landed level-2 evaluation into its slot (mode 0 initial point, 1 current point, 2 proposal)
 gamc_status launch_land(gamc_ctx* h, int mode) {
-  ProfScope ps(h, GAMC_K_LINALG);
+  ProfScope ps(h, GAMC_K_LAND);
   k_land<<<h->p, LAND_THREADS, 0, h->stream>>>(h->B, h->tune, mode, LandPeer{});
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
@@ -621,7 +612,7 @@ gamc_status launch_land(gamc_ctx* h, int mode) {
 // Level-2 evaluation at a device-resident theta, landed into its slot.  With peer landing the reduced buffers stay where
 // they are and k_land adds them up over NVLink; otherwise NCCL all-reduces R first.
 gamc_status eval_and_land(gamc_ctx* h, const double* d_theta, int mode) {
-  if (mode == 1 && h->tune.reuse_tensor && !h->comm && !h->cb) {
+  if (mode == 1 && h->tune.reuse_tensor && !h->comm && !generic_target(h)) {
     // gamc_config.reuse_tensor: every kernel of the re-evaluation returns at once if no AM proposal was accepted since the
     // slot was filled (device flag; the host never synchronises)
     const int* skip = &h->d_state->tensor_valid;
@@ -647,17 +638,17 @@ gamc_status eval_and_land(gamc_ctx* h, const double* d_theta, int mode) {
     k_peer_flag<<<1, 32, 0, h->stream>>>(h->d_peers, h->nranks, h->rank, seq);
     CUDA_TRY(h, cudaGetLastError());
   }
-  ProfScope ps(h, GAMC_K_LINALG);
-  LandPeer lp{h->d_peerR, h->d_peers, h->nranks, h->rank, seq, roff};
+  ProfScope ps(h, GAMC_K_LAND);
+  LandPeer lp{h->d_peerR, h->d_peers, h->nranks, h->rank, seq, roff, h->peer_timeout_ns};
   k_land<<<h->p, LAND_THREADS, 0, h->stream>>>(h->B, h->tune, mode, lp);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
 }
 
 template <typename K, typename... Args>
-gamc_status launch_step(gamc_ctx* h, K kern, Args... args) {
+gamc_status launch_step(gamc_ctx* h, int family, K kern, Args... args) {
   const size_t smem = step_smem_bytes(h->p);
-  ProfScope ps(h, GAMC_K_LINALG);
+  ProfScope ps(h, family);
   kern<<<1, LA_THREADS, smem, h->stream>>>(args...);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
@@ -668,7 +659,13 @@ gamc_status set_step_attrs(gamc_ctx* h) {
   const void* ks[] = {(const void*)k_sampler_init, (const void*)k_smmala_pre, (const void*)k_smmala_post, (const void*)k_am_pre,
                       (const void*)k_am_post};
   for (const void* k : ks) { gamc_status s = ensure_attr(h, k, smem); if (s != GAMC_OK) return s; }
-  { gamc_status s = ensure_attr(h, (const void*)k_am_pre_r1, am_r1_smem_bytes(512, 1)); if (s != GAMC_OK) return s; }
+  {
+    // the request depends on p through the number of panel buffers (two while they fit 200 KB: p <= 352), so the limit is the
+    // maximum over every supported p, not the value at p = 512
+    size_t mx = 0;
+    for (int q = 1; q <= 512; ++q) mx = std::max(mx, am_r1_smem_bytes(q, am_r1_nbuf(q)));
+    gamc_status s = ensure_attr(h, (const void*)k_am_pre_r1, mx); if (s != GAMC_OK) return s;
+  }
   { gamc_status s = ensure_attr(h, (const void*)k_triinv, triinv_smem_bytes(512)); if (s != GAMC_OK) return s; }
   return GAMC_OK;
 }
@@ -677,13 +674,13 @@ gamc_status set_step_attrs(gamc_ctx* h) {
 gamc_status launch_inverse(gamc_ctx* h, bool write_C = true) {
   const int p = h->p;
   {
-    ProfScope ps(h, GAMC_K_LINALG);
+    ProfScope ps(h, GAMC_K_HANDOVER);
     const size_t smem = triinv_smem_bytes(p);
     k_triinv<<<(p + 31) / 32, 256, smem, h->stream>>>(h->B.st, h->B.U, h->B.Ustride, h->B.invU, h->B.invUstride, p, h->B.W);
     CUDA_TRY(h, cudaGetLastError());
   }
   if (write_C) {
-    ProfScope ps(h, GAMC_K_LINALG);
+    ProfScope ps(h, GAMC_K_HANDOVER);
     dim3 grid((p + 15) / 16, (p + 15) / 16);
     k_wtw<<<grid, 256, 0, h->stream>>>(h->B.W, p, h->B.C);
     CUDA_TRY(h, cudaGetLastError());
@@ -695,7 +692,7 @@ gamc_status launch_inverse(gamc_ctx* h, bool write_C = true) {
 gamc_status launch_seed_factor(gamc_ctx* h) {
   gamc_status s = launch_inverse(h, false);
   if (s != GAMC_OK) return s;
-  ProfScope ps(h, GAMC_K_LINALG);
+  ProfScope ps(h, GAMC_K_HANDOVER);
   const int p = h->p;
   k_w_to_l<<<std::min(1024, (p * p + 255) / 256), 256, 0, h->stream>>>(h->B.st, h->B.W, p, h->B.Lc, h->B.rdiagL);
   CUDA_TRY(h, cudaGetLastError());
@@ -720,15 +717,78 @@ void bind_tape(gamc_ctx* h) {
   h->B.tape_z = h->d_tape + 3 * n;
 }
 
+
+// ---- small kernels of the new entry points -----------------------------------------------------------
+// gamc_set_state: B.Lc[0] = chol(C) of a host-supplied AM covariance (am_mode >= 1 keeps the covariance in factored form)
+__global__ void __launch_bounds__(LA_THREADS, 1) k_state_factor(Bufs B, TuneCfg T) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StepSmem S = step_smem_carve(smem_raw, T.p);
+  const int p = T.p;
+  const size_t n = (size_t)p * p;
+  for (size_t e = threadIdx.x; e < n; e += blockDim.x) { const int i = (int)(e % p), j = (int)(e / p); B.Lc[e] = (i >= j) ? B.C[e] : 0.0; }
+  __syncthreads();
+  MatView<false> V{B.Lc, p, p};
+  int bad = 0;
+  chol_blocked<false>(V, B.rdiagL, nullptr, S.la, &bad);
+  if (bad) { raise_error(B.st, 3, bad); return; }
+  if (threadIdx.x == 0) B.st->lcur = 0;
+}
+
+// gamc_get_monitor / monitored arrays: out = [loglikelihood, logprior | gradloglikelihood(p) | gradlogprior(p)] of the current point
+__global__ void __launch_bounds__(256) k_monitor(Bufs B, TuneCfg T, double* out) {
+  __shared__ double red[40];
+  const int p = T.p;
+  const double lp = log_prior(B.theta, p, T.lambda, red);
+  const int cur = B.st->cur;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) {
+    const double glp = T.lambda > 0.0 ? -B.theta[i] / T.lambda : 0.0;
+    out[2 + i] = B.gs[(size_t)cur * p + i] - glp;
+    out[2 + p + i] = glp;
+  }
+  if (threadIdx.x == 0) { out[0] = B.st->logtarget - lp; out[1] = lp; }
+}
+
+// FP64 yard-sticks (gamc_probe_fp64_peak): register-only loops, 16 independent accumulators per warp
+__global__ void __launch_bounds__(256) k_probe_dmma(double* out, int iters, double seed) {
+  double c[16][2];
+  const double a = seed + threadIdx.x * 1e-9, b = seed - threadIdx.x * 1e-9;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) s += c[t][0] + c[t][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) k_probe_dfma(double* out, int iters, double seed) {
+  double c[16];
+  const double a = seed + threadIdx.x * 1e-9, b = 1.0 - 1e-12;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) c[t] = t;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) c[t] = fma(c[t], b, a);
+  }
+  double s = 0;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) s += c[t];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
 
 // ====================================================================================================
 // C ABI
 // ====================================================================================================
 extern "C" {
-static void free_batched(gamc_ctx* h);
 
-const char* gamc_version(void) { return "gamc_b200 0.1.0 sm_100a"; }
+static gamc_status run_monitor(gamc_ctx* h);
+
+const char* gamc_version(void) { return "gamc_b200 0.2.0 sm_100a"; }
 
 gamc_status gamc_create(gamc_handle* out, int32_t device) {
   if (!out) return GAMC_INVALID_ARG;
@@ -761,8 +821,8 @@ gamc_status gamc_destroy(gamc_handle h) {
   free_peer_landing(h);
   free_sampler(h);
   free_target(h);
-  free_batched(h);
-  cudaFree(h->d_Sinv);
+  cudaFree(h->d_barrier); cudaFree(h->d_monitor);
+  for (int i = 0; i < GAMC_EXT_COUNT; ++i) if (h->ext_free[i]) h->ext_free[i](h);
   cudaFree(h->d_tape);
   if (h->prof || h->ev_used) for (int i = 0; i < PROF_POOL; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -875,14 +935,14 @@ gamc_status gamc_target_read_rows(gamc_handle h, int64_t r0, int64_t n, double* 
 // ---- evaluation -------------------------------------------------------------------------------------
 static gamc_status eval_host(gamc_handle h, const double* theta, int level, bool reduce_and_prior, double* lt, double* grad, double* G) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->dX || h->cb, GAMC_NOT_READY, "no target: call gamc_target_* first");
+  REQUIRE(h, h->dX || generic_target(h), GAMC_NOT_READY, "no target: call gamc_target_* first");
   REQUIRE(h, theta, GAMC_INVALID_ARG, "theta is null");
   cudaSetDevice(h->device);
   const int p = h->p;
   CUDA_TRY(h, cudaMemcpyAsync(h->theta_eval, theta, sizeof(double) * p, cudaMemcpyHostToDevice, h->stream));
   gamc_status s = eval_device(h, h->theta_eval, level, reduce_and_prior);
   if (s != GAMC_OK) return s;
-  if (reduce_and_prior && !h->cb) {
+  if (reduce_and_prior && !generic_target(h)) {
     ProfScope ps(h, GAMC_K_LINALG);
     k_eval_finish<<<1, 256, 0, h->stream>>>(h->R, h->goff, h->theta_eval, p, h->lambda, level);
     CUDA_TRY(h, cudaGetLastError());
@@ -943,7 +1003,7 @@ gamc_status gamc_comm_peer_path(gamc_handle h, int32_t* active) {
 // ---- sampler ----------------------------------------------------------------------------------------
 gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const double* theta0) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->dX || h->cb, GAMC_NOT_READY, "no target: call gamc_target_* first");
+  REQUIRE(h, h->dX || generic_target(h), GAMC_NOT_READY, "no target: call gamc_target_* first");
   REQUIRE(h, cfg && theta0, GAMC_INVALID_ARG, "null argument");
   // GAMC inner constructor asserts (src/samplers/GAMC.jl:135-138)
   REQUIRE(h, cfg->driftstep > 0, GAMC_INVALID_ARG, "Drift step is not positive");
@@ -972,7 +1032,7 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   T.targetrate = cfg->targetrate; T.score_k = cfg->score_k;
   T.minorscale = cfg->minorscale; T.sqrtminorscale = sqrt(cfg->minorscale); T.c = cfg->c;
   T.lambda = h->lambda; T.p = p; T.am_mode = cfg->am_mode;
-  T.reuse_tensor = (cfg->reuse_tensor && !h->comm && !h->cb) ? 1 : 0;
+  T.reuse_tensor = (cfg->reuse_tensor && !h->comm && !generic_target(h)) ? 1 : 0;
 
   Bufs& B = h->B;
   B = Bufs{};
@@ -992,8 +1052,15 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   if (h->chain_cap > 0) {
     CUDA_TRY(h, cudaMalloc(&h->d_chain, sizeof(double) * (size_t)h->chain_cap * p));
     CUDA_TRY(h, cudaMalloc(&h->d_accept, (size_t)h->chain_cap));
+    CUDA_TRY(h, cudaMalloc(&h->d_chain_lt, sizeof(double) * (size_t)h->chain_cap));
   }
-  B.chain_value = h->d_chain; B.chain_accept = h->d_accept; B.chain_cap = h->chain_cap;
+  B.chain_value = h->d_chain; B.chain_accept = h->d_accept; B.chain_cap = h->chain_cap; B.chain_logtarget = h->d_chain_lt;
+  if (T.tuning) {   // one record per tuning event: at most burnin / period + 2 of them (iterate/GAMC.jl:201)
+    h->tune_log_cap = (int)std::min<long long>(cfg->burnin / cfg->period + 2, 1 << 20);
+    CUDA_TRY(h, cudaMalloc(&h->d_tune_log, sizeof(double) * 16 * (size_t)h->tune_log_cap));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_tune_log, 0, sizeof(double) * 16 * (size_t)h->tune_log_cap, h->stream));
+  }
+  B.tune_log = h->d_tune_log; B.tune_log_cap = h->tune_log_cap;
   if (h->d_tape && h->tape_p == p) bind_tape(h);
 
   // tuner_state (src/samplers/GAMC.jl:195-200): BasicMCTune(step, 0, 0, period) seeds totproposed with the period
@@ -1017,9 +1084,10 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   } else {
     // initialize! (:157-176): first evaluation of target + gradient + metric at theta0
     setup_peer_landing(h);
+    s = comm_stream_barrier(h); if (s != GAMC_OK) return s;
     s = eval_and_land(h, B.theta, 0);
     if (s != GAMC_OK) return s;
-    s = launch_step(h, k_sampler_init, B, T);
+    s = launch_step(h, GAMC_K_LINALG, k_sampler_init, B, T);
     if (s != GAMC_OK) return s;
   }
   h->h_count = 0; h->h_present = true; h->h_past = false; h->spec_ready = false;   // MuvGAMCState outer ctor (:117-118)
@@ -1030,7 +1098,7 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
 
 gamc_status gamc_tape_set(gamc_handle h, int64_t n, const double* u_sched, const double* u_mix, const double* z, const double* u_acc) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->dX || h->cb, GAMC_NOT_READY, "no target");
+  REQUIRE(h, h->dX || generic_target(h), GAMC_NOT_READY, "no target");
   REQUIRE(h, n >= 1 && u_sched && u_mix && z && u_acc, GAMC_INVALID_ARG, "gamc_tape_set: bad argument");
   cudaSetDevice(h->device);
   gamc_status s = ensure_tape(h, n);
@@ -1048,7 +1116,7 @@ gamc_status gamc_tape_set(gamc_handle h, int64_t n, const double* u_sched, const
 
 gamc_status gamc_tape_generate(gamc_handle h, int64_t n, uint64_t seed) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->dX || h->cb, GAMC_NOT_READY, "no target");
+  REQUIRE(h, h->dX || generic_target(h), GAMC_NOT_READY, "no target");
   REQUIRE(h, n >= 1, GAMC_INVALID_ARG, "gamc_tape_generate: n < 1");
   cudaSetDevice(h->device);
   gamc_status s = ensure_tape(h, n);
@@ -1069,6 +1137,21 @@ gamc_status gamc_tape_generate(gamc_handle h, int64_t n, uint64_t seed) {
   return GAMC_OK;
 }
 
+gamc_status gamc_tape_get(gamc_handle h, int64_t first, int64_t n, double* u_sched, double* u_mix, double* z, double* u_acc) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->d_tape && h->tape_n > 0, GAMC_NOT_READY, "no tape: call gamc_tape_set / gamc_tape_generate");
+  REQUIRE(h, first >= 0 && n >= 0 && first + n <= h->tape_n, GAMC_INVALID_ARG, "gamc_tape_get: range out of bounds");
+  cudaSetDevice(h->device);
+  const long long cap = h->tape_cap;
+  if (n == 0) return GAMC_OK;
+  if (u_sched) CUDA_TRY(h, cudaMemcpyAsync(u_sched, h->d_tape + first, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (u_mix) CUDA_TRY(h, cudaMemcpyAsync(u_mix, h->d_tape + cap + first, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (u_acc) CUDA_TRY(h, cudaMemcpyAsync(u_acc, h->d_tape + 2 * cap + first, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (z) CUDA_TRY(h, cudaMemcpyAsync(z, h->d_tape + 3 * cap + (size_t)first * h->tape_p, sizeof(double) * (size_t)n * h->tape_p, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GAMC_OK;
+}
+
 gamc_status gamc_peek_kinds(gamc_handle h, int64_t n, uint8_t* kinds_out) {
   if (!h) return GAMC_INVALID_ARG;
   REQUIRE(h, h->sampler_ready, GAMC_NOT_READY, "sampler not initialised");
@@ -1077,7 +1160,7 @@ gamc_status gamc_peek_kinds(gamc_handle h, int64_t n, uint8_t* kinds_out) {
   bool present = h->h_present;
   for (long long k = 0; k < n; ++k) {
     const long long t = h->h_count + k + 1;
-    if (t > h->cfg.t0) present = schedule_decision(h->cfg, t, h->cfg.nsteps, h->h_usched[h->tape_pos + k]);
+    if (t > h->cfg.t0) present = branch_decision(h, t, h->h_usched[h->tape_pos + k]);
     kinds_out[k] = present ? 1 : 0;
   }
   return GAMC_OK;
@@ -1101,13 +1184,14 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
     }
     return GAMC_OK;
   }
+  if (h->comm && (h->p2p_ready || h->land_p2p) && n > 0) { s = comm_stream_barrier(h); if (s != GAMC_OK) return s; }
   // branch sequence of these n iterations (the schedule coin depends only on (i, nsteps, u_sched))
   std::vector<unsigned char> kinds(n);
   {
     bool pr = h->h_present;
     for (long long k = 0; k < n; ++k) {
       const long long t = h->h_count + k + 1;
-      if (t > h->cfg.t0) pr = schedule_decision(h->cfg, t, h->cfg.nsteps, h->h_usched[h->tape_pos + k]);
+      if (t > h->cfg.t0) pr = branch_decision(h, t, h->h_usched[h->tape_pos + k]);
       kinds[k] = pr ? 1 : 0;
     }
   }
@@ -1121,22 +1205,22 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
       if (refactor) {                                                                    // :20
         s = eval_and_land(h, B.theta, 1); if (s != GAMC_OK) return s;
       }
-      s = launch_step(h, k_smmala_pre, B, T, ti, refactor); if (s != GAMC_OK) return s;
+      s = launch_step(h, GAMC_K_SMMALA_PRE, k_smmala_pre, B, T, ti, refactor); if (s != GAMC_OK) return s;
       s = eval_and_land(h, B.theta_prop, 2); if (s != GAMC_OK) return s;                 // :37
-      s = launch_step(h, k_smmala_post, B, T, ti); if (s != GAMC_OK) return s;
+      s = launch_step(h, GAMC_K_SMMALA_POST, k_smmala_post, B, T, ti); if (s != GAMC_OK) return s;
     } else {                                                                             // :128
       const bool next_am = (T.am_mode == 2) && (k + 1 < n) && !kinds[k + 1];            // next step is AM too: speculate
       if (T.am_mode >= 1) {
         if (!h->spec_ready) {
           if (h->h_past) { s = launch_seed_factor(h); if (s != GAMC_OK) return s; }      // chol(oldinvtensor) = U^-T seeds the update
           const int nbuf = am_r1_nbuf(h->p);
-          ProfScope ps(h, GAMC_K_LINALG);
+          ProfScope ps(h, GAMC_K_AM_PRE);
           k_am_pre_r1<<<1, LA_THREADS, am_r1_smem_bytes(h->p, nbuf), h->stream>>>(B, T, ti, nbuf, 0);
           CUDA_TRY(h, cudaGetLastError());
         }   // else: the previous k_am_post selected the speculative factor and wrote the proposal
       } else {
         if (h->h_past) { s = launch_inverse(h); if (s != GAMC_OK) return s; }            // oldinvtensor = inv(G) seeds the recursion
-        s = launch_step(h, k_am_pre, B, T, ti); if (s != GAMC_OK) return s;
+        s = launch_step(h, GAMC_K_AM_PRE, k_am_pre, B, T, ti); if (s != GAMC_OK) return s;
       }
       if (next_am) {
         // both outcomes of this step's accept/reject -> next step's factor, on the side stream, while the data pass runs
@@ -1149,17 +1233,17 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
         CUDA_TRY(h, cudaEventRecord(h->ev_side, h->side));
         h->dp_grid_now = std::max(1, h->dp_grid - 2);                                    // leave two SMs to the speculative CTAs
       }
-      const bool local_sum = (!h->comm || h->p2p_ready) && !h->cb;
+      const bool local_sum = (!h->comm || h->p2p_ready) && !generic_target(h);
       const int nparts_post = local_sum ? (h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid) : 0;
       PeerArgs pa{};
-      if (h->comm && h->p2p_ready) { pa.peers = h->d_peers; pa.nranks = h->nranks; pa.rank = h->rank; pa.seq = ++h->p2p_seq; }
+      if (h->comm && h->p2p_ready) { pa.peers = h->d_peers; pa.nranks = h->nranks; pa.rank = h->rank; pa.seq = ++h->p2p_seq; pa.timeout_ns = h->peer_timeout_ns; }
       s = eval_device(h, B.theta_prop, 0, true, true);                                   // :148
       h->dp_grid_now = 0;
       if (s != GAMC_OK) return s;
       if (next_am) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_side, 0));
       {
         const size_t smem = step_smem_bytes(h->p);
-        ProfScope ps(h, GAMC_K_LINALG);
+        ProfScope ps(h, GAMC_K_AM_POST);
         k_am_post<<<1, LA_THREADS, smem, h->stream>>>(B, T, ti, next_am ? 1 : 0, h->part_ll, nparts_post, pa);
         CUDA_TRY(h, cudaGetLastError());
       }
@@ -1177,6 +1261,8 @@ gamc_status gamc_chain_get(gamc_handle h, int64_t first, int64_t n, double* valu
   gamc_status s = check_device_error(h);   // synchronises
   if (s != GAMC_OK) return s;
   REQUIRE(h, first >= 0 && n >= 0 && first + n <= h->chain_cap, GAMC_INVALID_ARG, "chain range out of bounds");
+  REQUIRE(h, first + n <= h->chain_saved_seen, GAMC_NOT_READY, "chain range not sampled yet: " + std::to_string(h->chain_saved_seen) +
+          " post-burn-in samples saved so far");
   if (n == 0) return GAMC_OK;
   if (value) CUDA_TRY(h, cudaMemcpyAsync(value, h->d_chain + (size_t)first * h->p, sizeof(double) * (size_t)n * h->p, cudaMemcpyDeviceToHost, h->stream));
   if (accept) CUDA_TRY(h, cudaMemcpyAsync(accept, h->d_accept + first, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
@@ -1254,6 +1340,24 @@ gamc_status gamc_get_array(gamc_handle h, int32_t array_id, double* out) {
       for (int b = 0; b < p; ++b) for (int a = 0; a < p; ++a) out[a + (size_t)b * p] = (a >= b) ? W[(size_t)(p - 1 - b) + (size_t)(p - 1 - a) * p] : 0.0;
       return GAMC_OK;
     }
+    case GAMC_ARR_GRADLOGLIKELIHOOD: case GAMC_ARR_GRADLOGPRIOR: {
+      REQUIRE(h, h->lambda > 0, GAMC_NOT_READY, "a generic target does not separate likelihood and prior");
+      gamc_status s = run_monitor(h); if (s != GAMC_OK) return s;
+      src = h->d_monitor + 2 + (array_id == GAMC_ARR_GRADLOGPRIOR ? p : 0); break;
+    }
+    case GAMC_ARR_TENSORLOGLIKELIHOOD: case GAMC_ARR_TENSORLOGPRIOR: {
+      // tensor = X' W X + I/lambda (examples/logistic_regression/src/GAMC/simulations.jl:34-37): the prior part is I/lambda
+      REQUIRE(h, h->lambda > 0, GAMC_NOT_READY, "a generic target does not separate likelihood and prior");
+      std::vector<double> G(pp);
+      CUDA_TRY(h, cudaMemcpyAsync(G.data(), B.Gs + (size_t)cur * pp, sizeof(double) * pp, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      const bool prior = array_id == GAMC_ARR_TENSORLOGPRIOR;
+      for (int j = 0; j < p; ++j) for (int i = 0; i < p; ++i) {
+        const double pr = (i == j) ? 1.0 / h->lambda : 0.0;
+        out[i + (size_t)j * p] = prior ? pr : G[i + (size_t)j * p] - pr;
+      }
+      return GAMC_OK;
+    }
     default: h->err = "unknown array id"; return GAMC_INVALID_ARG;
   }
   CUDA_TRY(h, cudaMemcpyAsync(out, src, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -1262,193 +1366,157 @@ gamc_status gamc_get_array(gamc_handle h, int32_t array_id, double* out) {
 }
 
 // ---- measurement ------------------------------------------------------------------------------------
-// ---- batched chains ---------------------------------------------------------------------------------
-static void free_batched(gamc_ctx* h) {
-  cudaFree(h->d_blob); cudaFree(h->d_bchain); cudaFree(h->d_baccept); cudaFree(h->d_btape);
-  h->d_blob = nullptr; h->d_bchain = nullptr; h->d_baccept = nullptr; h->d_btape = nullptr; h->btape_doubles = 0;
-  h->batched_ready = false;
+
+// ---- round-2 additions: device-side generic target, user schedule, restart, monitors, burn-in report, probes -------
+gamc_status gamc_target_device_callback(gamc_handle h, int32_t p, gamc_target_enqueue_fn enqueue, void* user) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, enqueue && p >= 1, GAMC_INVALID_ARG, "gamc_target_device_callback: bad argument");
+  REQUIRE(h, p <= 512, GAMC_UNSUPPORTED_SHAPE, "p must be in 1..512");
+  cudaSetDevice(h->device);
+  free_sampler(h); free_target(h);
+  h->N = 0; h->p = p; h->lambda = -1.0;   // lambda <= 0: the step kernels add no prior terms (the user's values are complete)
+  h->goff = (1 + p + 1) & ~1;
+  h->dcb = enqueue; h->dcb_user = user;
+  return alloc_arena(h);
 }
 
-gamc_status gamc_batched_target_mvt(gamc_handle h, int32_t n, double nu, const double* Sinv, double logconst) {
+gamc_status gamc_comm_set_timeout(gamc_handle h, double seconds) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, Sinv && n >= 1 && nu > 0, GAMC_INVALID_ARG, "gamc_batched_target_mvt: bad argument");
-  REQUIRE(h, n <= BT_MAXP, GAMC_UNSUPPORTED_SHAPE, "batched chains support p <= 32");
-  cudaSetDevice(h->device);
-  free_batched(h);
-  cudaFree(h->d_Sinv); h->d_Sinv = nullptr;
-  CUDA_TRY(h, cudaMalloc(&h->d_Sinv, sizeof(double) * n * n));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_Sinv, Sinv, sizeof(double) * n * n, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  h->bcfg = BatchedCfg{};
-  h->bcfg.p = n; h->bcfg.ld = (n & 1) ? n : n + 1; h->bcfg.target = 0;
-  h->bcfg.nu = nu; h->bcfg.logconst = logconst; h->bcfg.Sinv = h->d_Sinv;
-  h->batched_target = true;
+  REQUIRE(h, seconds > 0 && seconds < 1e6, GAMC_INVALID_ARG, "timeout must be positive");
+  h->peer_timeout_ns = (unsigned long long)(seconds * 1e9);
   return GAMC_OK;
 }
 
-gamc_status gamc_batched_target_rv(gamc_handle h, const double* t, const double* obs, const double* sigma, int64_t N, int32_t nplanets) {
+gamc_status gamc_set_schedule_callback(gamc_handle h, gamc_schedule_fn fn, void* user) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, t && obs && sigma && N >= 1, GAMC_INVALID_ARG, "gamc_batched_target_rv: bad argument");
-  REQUIRE(h, nplanets == 1 || nplanets == 2, GAMC_UNSUPPORTED_SHAPE, "radial-velocity target supports 1 or 2 planets");
-  cudaSetDevice(h->device);
-  free_batched(h);
-  cudaFree(h->d_Sinv); h->d_Sinv = nullptr;        // reused as the [t | obs | sigma] buffer
-  CUDA_TRY(h, cudaMalloc(&h->d_Sinv, sizeof(double) * 3 * (size_t)N));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_Sinv, t, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_Sinv + N, obs, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_Sinv + 2 * N, sigma, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  double lognorm = -0.5 * (double)N * log(2.0 * M_PI);          // stat_model.jl:27,33 (data constants, summed once on the host)
-  for (int64_t i = 0; i < N; ++i) lognorm -= 0.5 * log(sigma[i] * sigma[i]);
-  h->bcfg = BatchedCfg{};
-  h->bcfg.p = 5 * nplanets + 1; h->bcfg.ld = (h->bcfg.p & 1) ? h->bcfg.p : h->bcfg.p + 1; h->bcfg.target = 1;
-  h->bcfg.rv_t = h->d_Sinv; h->bcfg.rv_obs = h->d_Sinv + N; h->bcfg.rv_sig = h->d_Sinv + 2 * N; h->bcfg.rv_n = N; h->bcfg.rv_npl = nplanets;
-  h->bcfg.rv_lognorm = lognorm;
-  h->batched_target = true;
+  h->sched_fn = fn; h->sched_user = user;
   return GAMC_OK;
 }
 
-}  // extern "C"
+gamc_status gamc_set_state(gamc_handle h, const gamc_state_scalars* st_in, const double* theta, const double* lastmean,
+                           const double* secondlastmean, const double* oldinvtensor) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->sampler_ready, GAMC_NOT_READY, "sampler not initialised: call gamc_sampler_init first");
+  REQUIRE(h, h->cfg.sampler_kind == 0, GAMC_INVALID_ARG, "gamc_set_state restarts GAMC chains");
+  REQUIRE(h, st_in && theta && lastmean && secondlastmean, GAMC_INVALID_ARG, "gamc_set_state: null argument");
+  REQUIRE(h, st_in->count >= 0 && st_in->step > 0, GAMC_INVALID_ARG, "gamc_set_state: bad count / step");
+  REQUIRE(h, st_in->pastupdatetensor || st_in->count == 0 || oldinvtensor, GAMC_INVALID_ARG,
+          "gamc_set_state: the last transition was an AM step, so sstate.oldinvtensor (the AM covariance) is required");
+  cudaSetDevice(h->device);
+  Bufs& B = h->B;
+  const TuneCfg& T = h->tune;
+  const int p = h->p;
+  // value, then initialize! + sampler_state at it: log-target, gradient, metric, factor, G^-1 grad of slot 0
+  CUDA_TRY(h, cudaMemcpyAsync(B.theta, theta, sizeof(double) * p, cudaMemcpyHostToDevice, h->stream));
+  gamc_status s = comm_stream_barrier(h); if (s != GAMC_OK) return s;
+  s = eval_and_land(h, B.theta, 0); if (s != GAMC_OK) return s;
+  s = launch_step(h, GAMC_K_LINALG, k_sampler_init, B, T); if (s != GAMC_OK) return s;
+  s = check_device_error(h); if (s != GAMC_OK) return s;
+  CUDA_TRY(h, cudaMemcpyAsync(B.lastmean, lastmean, sizeof(double) * p, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(B.secondlastmean, secondlastmean, sizeof(double) * p, cudaMemcpyHostToDevice, h->stream));
+  DevState st;
+  CUDA_TRY(h, cudaMemcpyAsync(&st, B.st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  st.count = st_in->count; st.updatetensorcount = st_in->updatetensorcount;
+  st.step = st_in->step; st.sqrtstep = sqrt(st_in->step);
+  st.tot_acc = st_in->total_accepted; st.tot_prop = st_in->total_proposed; st.tot_totprop = st_in->total_totproposed; st.tot_rate = st_in->total_rate;
+  st.sm_acc = st_in->smmala_accepted; st.sm_prop = st_in->smmala_proposed; st.sm_totprop = st_in->smmala_totproposed;
+  st.am_acc = st_in->am_accepted; st.am_prop = st_in->am_proposed; st.am_totprop = st_in->am_totproposed;
+  st.smfreq = st_in->smmalafrequency; st.amfreq = st_in->amfrequency; st.ratio = st_in->ratio;
+  st.chain_saved = 0; st.tune_events = 0; st.lcur = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(B.st, &st, sizeof(DevState), cudaMemcpyHostToDevice, h->stream));
+  h->h_count = st_in->count;
+  h->h_present = st_in->count == 0 ? true : st_in->presentupdatetensor != 0;
+  h->h_past = st_in->count == 0 ? false : st_in->pastupdatetensor != 0;
+  h->spec_ready = false; h->tape_n = 0; h->tape_pos = 0;
+  if (!h->h_past && st_in->count > 0) {
+    CUDA_TRY(h, cudaMemcpyAsync(B.C, oldinvtensor, sizeof(double) * (size_t)p * p, cudaMemcpyHostToDevice, h->stream));
+    if (T.am_mode >= 1) { s = launch_step(h, GAMC_K_LINALG, k_state_factor, B, T); if (s != GAMC_OK) return s; }
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  { gamc_status e = ensure_attr(h, (const void*)k_state_factor, step_smem_bytes(512)); if (e != GAMC_OK) return e; }
+  return check_device_error(h);
+}
 
-template <int TGT>
-static gamc_status launch_batched_t(gamc_ctx* h, int mode, long long n, const double* d_theta0) {
-  const int nt = (TGT == 0) ? 32 : 128;
-  const size_t smem = bt_smem_bytes(h->bcfg.blob_doubles, nt);
-  { gamc_status s = ensure_attr(h, (const void*)k_batched_gamc<TGT>, 200 * 1024); if (s != GAMC_OK) return s; }
+static gamc_status run_monitor(gamc_ctx* h) {
+  if (!h->d_monitor) CUDA_TRY(h, cudaMalloc(&h->d_monitor, sizeof(double) * (2 + 2 * 512)));
   ProfScope ps(h, GAMC_K_LINALG);
-  k_batched_gamc<TGT><<<h->bcfg.nchains, nt, smem, h->stream>>>(h->bcfg, mode, n, d_theta0);
+  k_monitor<<<1, 256, 0, h->stream>>>(h->B, h->tune, h->d_monitor);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
 }
-extern "C" {
 
-static gamc_status launch_batched(gamc_ctx* h, int mode, long long n, const double* d_theta0) {
-  if (h->bcfg.target == 0) return launch_batched_t<0>(h, mode, n, d_theta0);
-  return h->bcfg.rv_npl == 2 ? launch_batched_t<2>(h, mode, n, d_theta0) : launch_batched_t<1>(h, mode, n, d_theta0);
-}
-
-gamc_status gamc_batched_init(gamc_handle h, const gamc_config* cfg, int32_t nchains, const double* theta0, int32_t transform, double softabs_alpha) {
+gamc_status gamc_get_monitor(gamc_handle h, double* loglikelihood, double* logprior) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->batched_target, GAMC_NOT_READY, "no batched target: call gamc_batched_target_* first");
-  REQUIRE(h, cfg && theta0 && nchains >= 1, GAMC_INVALID_ARG, "null argument");
-  REQUIRE(h, cfg->driftstep > 0, GAMC_INVALID_ARG, "Drift step is not positive");
-  REQUIRE(h, cfg->minorscale > 0, GAMC_INVALID_ARG, "Constant minorscale must be positive");
-  REQUIRE(h, cfg->c >= 0, GAMC_INVALID_ARG, "Constant c must be non-negative");
-  REQUIRE(h, cfg->t0 > 0, GAMC_INVALID_ARG, "t0 is not positive");
-  REQUIRE(h, cfg->schedule >= 0 && cfg->schedule <= GAMC_SCHED_RAND_QUAD_DECAY, GAMC_INVALID_ARG, "unknown schedule");
-  REQUIRE(h, cfg->period >= 1 && cfg->nsteps >= 1 && cfg->burnin >= 0, GAMC_INVALID_ARG, "bad period / nsteps / burnin");
-  REQUIRE(h, transform == 0 || transform == 1, GAMC_INVALID_ARG, "transform must be 0 (none) or 1 (softabs)");
+  REQUIRE(h, h->sampler_ready, GAMC_NOT_READY, "sampler not initialised");
+  REQUIRE(h, h->lambda > 0, GAMC_NOT_READY, "a generic target does not separate likelihood and prior");
   cudaSetDevice(h->device);
+  gamc_status s = run_monitor(h); if (s != GAMC_OK) return s;
+  double v[2];
+  CUDA_TRY(h, cudaMemcpyAsync(v, h->d_monitor, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  free_batched(h);
-  BatchedCfg& C = h->bcfg;
-  const int p = C.p;
-  C.nchains = nchains; C.chain_offset = h->bcfg_chain_offset; C.transform = transform; C.softabs_alpha = softabs_alpha;
-  C.driftstep = cfg->driftstep; C.minorscale = cfg->minorscale; C.sqrtminorscale = sqrt(cfg->minorscale); C.c = cfg->c;
-  C.t0 = cfg->t0; C.schedule = cfg->schedule; C.sp0 = cfg->sched_params[0]; C.sp1 = cfg->sched_params[1]; C.sp2 = cfg->sched_params[2];
-  C.is_accrate = cfg->total_tuner_kind == 1;
-  C.tuning = (cfg->verbose_total || cfg->verbose_smmala || cfg->verbose_am || C.is_accrate) ? 1 : 0;
-  C.count_total = (cfg->verbose_total || C.is_accrate) ? 1 : 0;
-  C.verbose_sm = cfg->verbose_smmala; C.verbose_am = cfg->verbose_am; C.period = cfg->period;
-  C.nsteps = cfg->nsteps; C.burnin = cfg->burnin; C.targetrate = cfg->targetrate; C.score_k = cfg->score_k;
-  C.blob_doubles = bt_blob_doubles(p, C.ld);
-  C.chain_cap = std::max<long long>(0, cfg->nsteps - cfg->burnin);
-  CUDA_TRY(h, cudaMalloc(&h->d_blob, sizeof(double) * (size_t)nchains * C.blob_doubles));
-  if (C.chain_cap > 0) {
-    CUDA_TRY(h, cudaMalloc(&h->d_bchain, sizeof(double) * (size_t)nchains * C.chain_cap * p));
-    CUDA_TRY(h, cudaMalloc(&h->d_baccept, (size_t)nchains * C.chain_cap));
-  }
-  C.blob = h->d_blob; C.chain_value = h->d_bchain; C.chain_accept = h->d_baccept;
-  C.tape_usched = C.tape_umix = C.tape_uacc = C.tape_z = nullptr; C.tape_len = 0; C.seed = 0;
-  double* d_t0 = nullptr;
-  CUDA_TRY(h, cudaMalloc(&d_t0, sizeof(double) * (size_t)nchains * p));
-  CUDA_TRY(h, cudaMemcpyAsync(d_t0, theta0, sizeof(double) * (size_t)nchains * p, cudaMemcpyHostToDevice, h->stream));
-  gamc_status s = launch_batched(h, 1, 0, d_t0);
-  if (s != GAMC_OK) { cudaFree(d_t0); return s; }
-  // initial-point check (src/samplers/GAMC.jl:168-170) for every chain
-  std::vector<double> err(nchains);
-  cudaError_t e = cudaMemcpy2DAsync(err.data(), sizeof(double), h->d_blob + BS_ERR, sizeof(double) * C.blob_doubles, sizeof(double), nchains,
-                                    cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_t0);
-  if (e != cudaSuccess) { h->err = std::string("batched init: ") + cudaGetErrorString(e); return GAMC_CUDA_ERROR; }
-  for (int c = 0; c < nchains; ++c)
-    if (err[c] != 0.0) { h->err = "Log-target, gradient or tensor not finite / not positive definite at the initial value of chain " + std::to_string(c); return GAMC_NONFINITE_INIT; }
-  h->batched_ready = true;
+  if (loglikelihood) *loglikelihood = v[0];
+  if (logprior) *logprior = v[1];
   return GAMC_OK;
 }
 
-gamc_status gamc_batched_run(gamc_handle h, int64_t n, uint64_t seed, const double* u_sched, const double* u_mix, const double* z, const double* u_acc) {
+gamc_status gamc_chain_get_logtarget(gamc_handle h, int64_t first, int64_t n, double* logtarget) {
   if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->batched_ready, GAMC_NOT_READY, "batched sampler not initialised");
-  REQUIRE(h, n >= 0, GAMC_INVALID_ARG, "n < 0");
+  REQUIRE(h, h->sampler_ready, GAMC_NOT_READY, "sampler not initialised");
   cudaSetDevice(h->device);
-  BatchedCfg& C = h->bcfg;
-  const bool tape = u_sched || u_mix || z || u_acc;
-  if (tape) {
-    REQUIRE(h, u_sched && u_mix && z && u_acc, GAMC_INVALID_ARG, "either all tape pointers or none");
-    const long long per = (long long)C.nchains * n;
-    const long long need = per * (3 + C.p);
-    if (need > h->btape_doubles) {
-      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-      cudaFree(h->d_btape); h->d_btape = nullptr; h->btape_doubles = 0;
-      CUDA_TRY(h, cudaMalloc(&h->d_btape, sizeof(double) * need));
-      h->btape_doubles = need;
+  gamc_status s = check_device_error(h);   // synchronises
+  if (s != GAMC_OK) return s;
+  REQUIRE(h, first >= 0 && n >= 0 && first + n <= h->chain_cap, GAMC_INVALID_ARG, "chain range out of bounds");
+  REQUIRE(h, first + n <= h->chain_saved_seen, GAMC_NOT_READY, "chain range not sampled yet");
+  if (n == 0 || !logtarget) return GAMC_OK;
+  CUDA_TRY(h, cudaMemcpyAsync(logtarget, h->d_chain_lt + first, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GAMC_OK;
+}
+
+gamc_status gamc_tune_log_get(gamc_handle h, double* out, int64_t max_records, int64_t* n_records) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, h->sampler_ready, GAMC_NOT_READY, "sampler not initialised");
+  cudaSetDevice(h->device);
+  DevState st;
+  CUDA_TRY(h, cudaMemcpyAsync(&st, h->B.st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  const long long have = std::min<long long>(st.tune_events, h->tune_log_cap);
+  if (n_records) *n_records = have;
+  const long long take = std::min<long long>(have, std::max<long long>(0, max_records));
+  if (out && take > 0) {
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_tune_log, sizeof(double) * 16 * (size_t)take, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return GAMC_OK;
+}
+
+gamc_status gamc_probe_fp64_peak(gamc_handle h, double* dmma_tflops, double* dfma_tflops) {
+  if (!h) return GAMC_INVALID_ARG;
+  cudaSetDevice(h->device);
+  const int grid = h->num_sms * 4, iters = 4000;      // 32 warps per SM: the occupancy at which both loops saturate the FP64 pipe
+  double* out = nullptr;
+  CUDA_TRY(h, cudaMalloc(&out, sizeof(double) * (size_t)grid * 256));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(h, cudaEventCreate(&e0)); CUDA_TRY(h, cudaEventCreate(&e1));
+  double best[2] = {0.0, 0.0};
+  for (int which = 0; which < 2; ++which) {
+    for (int rep = 0; rep < 4; ++rep) {                // first repetition is the warm-up
+      cudaEventRecord(e0, h->stream);
+      if (which == 0) k_probe_dmma<<<grid, 256, 0, h->stream>>>(out, iters, 1.0);
+      else k_probe_dfma<<<grid, 256, 0, h->stream>>>(out, iters, 1.0);
+      cudaEventRecord(e1, h->stream);
+      h->launches += 1;
+      if (cudaEventSynchronize(e1) != cudaSuccess) break;
+      float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+      const double flops = which == 0 ? (double)grid * 8 * iters * 16.0 * 512.0 : (double)grid * 256 * iters * 16.0 * 2.0;
+      if (rep > 0 && ms > 0.f) best[which] = std::max(best[which], flops / ms * 1e-9);
     }
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_btape, u_sched, sizeof(double) * per, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_btape + per, u_mix, sizeof(double) * per, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_btape + 2 * per, u_acc, sizeof(double) * per, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_btape + 3 * per, z, sizeof(double) * per * C.p, cudaMemcpyHostToDevice, h->stream));
-    C.tape_usched = h->d_btape; C.tape_umix = h->d_btape + per; C.tape_uacc = h->d_btape + 2 * per; C.tape_z = h->d_btape + 3 * per;
-    C.tape_len = n;
-  } else {
-    C.tape_usched = C.tape_umix = C.tape_uacc = C.tape_z = nullptr; C.tape_len = 0;
   }
-  C.seed = seed;
-  return launch_batched(h, 0, n, nullptr);
-}
-
-gamc_status gamc_batched_set_chain_offset(gamc_handle h, int64_t chain_offset) {
-  if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, chain_offset >= 0, GAMC_INVALID_ARG, "chain_offset < 0");
-  h->bcfg_chain_offset = chain_offset;
-  h->bcfg.chain_offset = chain_offset;
-  return GAMC_OK;
-}
-
-gamc_status gamc_batched_chain_get(gamc_handle h, int32_t chain_first, int32_t nchains, double* value, uint8_t* accept) {
-  if (!h) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->batched_ready, GAMC_NOT_READY, "batched sampler not initialised");
-  const BatchedCfg& C = h->bcfg;
-  REQUIRE(h, chain_first >= 0 && nchains >= 0 && chain_first + nchains <= C.nchains, GAMC_INVALID_ARG, "chain range out of bounds");
-  cudaSetDevice(h->device);
-  if (nchains == 0 || C.chain_cap == 0) { CUDA_TRY(h, cudaStreamSynchronize(h->stream)); return GAMC_OK; }
-  if (value) CUDA_TRY(h, cudaMemcpyAsync(value, h->d_bchain + (size_t)chain_first * C.chain_cap * C.p, sizeof(double) * (size_t)nchains * C.chain_cap * C.p, cudaMemcpyDeviceToHost, h->stream));
-  if (accept) CUDA_TRY(h, cudaMemcpyAsync(accept, h->d_baccept + (size_t)chain_first * C.chain_cap, (size_t)nchains * C.chain_cap, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  return GAMC_OK;
-}
-
-gamc_status gamc_batched_get_state(gamc_handle h, int32_t chain, gamc_state_scalars* out, double* theta) {
-  if (!h || !out) return GAMC_INVALID_ARG;
-  REQUIRE(h, h->batched_ready, GAMC_NOT_READY, "batched sampler not initialised");
-  const BatchedCfg& C = h->bcfg;
-  REQUIRE(h, chain >= 0 && chain < C.nchains, GAMC_INVALID_ARG, "chain out of range");
-  cudaSetDevice(h->device);
-  std::vector<double> b(BS_NSCAL + BT_MAXP);
-  CUDA_TRY(h, cudaMemcpyAsync(b.data(), h->d_blob + (size_t)chain * C.blob_doubles, sizeof(double) * (BS_NSCAL + BT_MAXP), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  memset(out, 0, sizeof(*out));
-  out->count = (int64_t)b[BS_COUNT]; out->updatetensorcount = (int64_t)b[BS_UPD];
-  out->step = b[BS_STEP]; out->sqrttunestep = b[BS_SQSTEP];
-  out->total_accepted = (int64_t)b[BS_TACC]; out->total_proposed = (int64_t)b[BS_TPROP]; out->total_totproposed = (int64_t)b[BS_TTOT]; out->total_rate = b[BS_TRATE];
-  out->smmala_accepted = (int64_t)b[BS_SMACC]; out->smmala_proposed = (int64_t)b[BS_SMPROP]; out->smmala_totproposed = (int64_t)b[BS_SMTOT];
-  out->am_accepted = (int64_t)b[BS_AMACC]; out->am_proposed = (int64_t)b[BS_AMPROP]; out->am_totproposed = (int64_t)b[BS_AMTOT];
-  out->smmalafrequency = NAN; out->amfrequency = NAN;
-  out->logtarget = b[BS_LT]; out->ratio = b[BS_RATIO];
-  out->presentupdatetensor = b[BS_PRESENT] != 0.0; out->pastupdatetensor = b[BS_PAST] != 0.0;
-  out->error_flag = (int32_t)b[BS_ERR]; out->chain_saved = (int64_t)b[BS_SAVED];
-  if (theta) memcpy(theta, b.data() + BS_NSCAL + BV_THETA * BT_MAXP, sizeof(double) * C.p);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  CUDA_TRY(h, cudaGetLastError());
+  if (dmma_tflops) *dmma_tflops = best[0];
+  if (dfma_tflops) *dfma_tflops = best[1];
   return GAMC_OK;
 }
 

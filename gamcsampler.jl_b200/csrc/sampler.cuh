@@ -13,9 +13,11 @@ namespace gamc {
 
 // One mailbox slot of the peer all-reduce (see k_am_post) and the per-launch arguments of that path.
 struct PeerMail { double val; unsigned long long seq; };
-struct PeerArgs { PeerMail* const* peers; int nranks; int rank; unsigned long long seq; };
+struct PeerArgs { PeerMail* const* peers; int nranks; int rank; unsigned long long seq; unsigned long long timeout_ns; };
 // Peer landing (see k_land): peerR[r] = rank r's pair of reduced evaluation buffers, roff = offset of this evaluation's buffer.
-struct LandPeer { double* const* peerR; PeerMail* const* peers; int nranks; int rank; unsigned long long seq; size_t roff; };
+struct LandPeer { double* const* peerR; PeerMail* const* peers; int nranks; int rank; unsigned long long seq; size_t roff; unsigned long long timeout_ns; };
+// Wall-clock nanoseconds (independent of the SM clock): the peer waits are bounded in real time (gamc_comm_set_timeout).
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ double ld_peer(const double* q) { return *reinterpret_cast<const volatile double*>(q); }
 
 // After k_reduce: tell every peer that this rank's reduced evaluation `seq` is in place (mailbox slots 2n .. 4n).
@@ -45,6 +47,8 @@ struct Bufs {
   size_t Lstride;                        // p*p: distance between the AM factor buffers
   double* W;                             // p x p  scratch: triangular inverse
   double* chain_value; unsigned char* chain_accept; long long chain_cap;
+  double* chain_logtarget;               // [chain_cap] pstate.logtarget of every saved sample
+  double* tune_log; int tune_log_cap;    // [cap][16] one record per burn-in tuning event (gamc_tune_log_get)
   const double* tape_usched; const double* tape_umix; const double* tape_z; const double* tape_uacc;
 };
 
@@ -118,9 +122,9 @@ __global__ void __launch_bounds__(LAND_THREADS) k_land(Bufs B, TuneCfg T, int mo
   if (nr > 1) {
     if ((int)threadIdx.x < nr) {
       volatile PeerMail* src = lp.peers[lp.rank] + 2 * nr + (int)(lp.seq & 1ull) * nr + threadIdx.x;
-      const long long t0 = clock64();
+      const unsigned long long t0 = globaltimer_ns();
       while (src->seq != lp.seq) {
-        if (clock64() - t0 > 6000000000ll) {          // ~3 s: a peer died
+        if (globaltimer_ns() - t0 > lp.timeout_ns) {   // the peer never published this evaluation (gamc_comm_set_timeout)
           if (st->error_flag == 0) { st->error_flag = 5 /*GAMC_NCCL_ERROR*/; st->error_pivot = threadIdx.x; st->error_iter = st->count; }
           break;
         }
@@ -234,7 +238,7 @@ __device__ inline void step_tail(const Bufs& B, const TuneCfg& T, int accepted) 
     const long long pos = st->chain_saved;
     if (pos < B.chain_cap) {
       for (int i = threadIdx.x; i < p; i += blockDim.x) B.chain_value[(size_t)pos * p + i] = B.theta[i];
-      if (threadIdx.x == 0) B.chain_accept[pos] = (unsigned char)accepted;
+      if (threadIdx.x == 0) { B.chain_accept[pos] = (unsigned char)accepted; B.chain_logtarget[pos] = st->logtarget; }
     }
   }
   __syncthreads();
@@ -256,6 +260,14 @@ __device__ inline void step_tail(const Bufs& B, const TuneCfg& T, int accepted) 
           st->step *= 2.0 / (1.0 + exp(-T.score_k * (st->tot_rate - T.targetrate)));
           st->sqrtstep = sqrt(st->step);
         }
+        if (B.tune_log && st->tune_events < B.tune_log_cap) {       // what the verbose report prints (:218-268), before the resets
+          double* r = B.tune_log + 16 * st->tune_events;
+          r[0] = (double)t; r[1] = (double)st->tot_acc; r[2] = (double)st->tot_prop; r[3] = st->tot_rate;
+          r[4] = (double)st->sm_acc; r[5] = (double)st->sm_prop; r[6] = st->sm_rate; r[7] = st->smfreq;
+          r[8] = (double)st->am_acc; r[9] = (double)st->am_prop; r[10] = st->am_rate; r[11] = st->amfreq;
+          r[12] = st->step; r[13] = r[14] = r[15] = 0.0;
+        }
+        st->tune_events += 1;
         if (T.verbose_sm) { st->sm_totprop += st->sm_prop; st->sm_prop = 0; st->sm_acc = 0; st->sm_rate = nan(""); }
         if (T.verbose_am) { st->am_totprop += st->am_prop; st->am_prop = 0; st->am_acc = 0; st->am_rate = nan(""); }
         st->tot_totprop += st->tot_prop;                                                     // :283
@@ -715,10 +727,10 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, lo
         __threadfence_system();
         dst->seq = pa.seq;
         volatile PeerMail* src = pa.peers[pa.rank] + par * pa.nranks + threadIdx.x;
-        const long long t0 = clock64();
+        const unsigned long long t0 = globaltimer_ns();
         bool got = true;
         while (src->seq != pa.seq) {
-          if (clock64() - t0 > 6000000000ll) { got = false; break; }   // ~3 s: a peer died
+          if (globaltimer_ns() - t0 > pa.timeout_ns) { got = false; break; }   // the peer never reached this step (gamc_comm_set_timeout)
           __nanosleep(100);
         }
         __threadfence_system();

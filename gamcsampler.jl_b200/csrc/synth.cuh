@@ -32,7 +32,7 @@ __host__ __device__ inline double philox_u53(uint32_t a, uint32_t b) {
 }
 
 // X[i, j] for local rows i in [0, nrows), global row = row0 + i; column-major with leading dimension ld.
-__global__ void k_synth_X(double* __restrict__ X, long long ld, long long row0, long long nrows, int p, uint64_t seed) {
+static __global__ void k_synth_X(double* __restrict__ X, long long ld, long long row0, long long nrows, int p, uint64_t seed) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
   for (int j = blockIdx.y; j < p; j += gridDim.y) X[i + (long long)j * ld] = synth_x(seed, (uint64_t)(row0 + i), (uint32_t)j);
@@ -40,7 +40,7 @@ __global__ void k_synth_X(double* __restrict__ X, long long ld, long long row0, 
 
 // y[i] = 1{u_i < sigma(x_i . theta_true)}; eta accumulated sequentially in j WITHOUT fma contraction
 // (matches the NumPy loop in oracle/logistic.py:synth_logistic).
-__global__ void k_synth_y(const double* __restrict__ X, long long ld, long long row0, long long nrows, int p,
+static __global__ void k_synth_y(const double* __restrict__ X, long long ld, long long row0, long long nrows, int p,
                           const double* __restrict__ theta_true, uint64_t seed, double* __restrict__ y) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
@@ -56,7 +56,7 @@ __global__ void k_synth_y(const double* __restrict__ X, long long ld, long long 
 
 // Device-generated random tape (throughput mode): slot t -> u_sched, u_mix, u_acc in (0,1), z ~ N(0,1)
 // by Box-Muller on Philox outputs.  Counter (t_lo, t_hi, j, stream).
-__global__ void k_tape_generate(long long n, int p, uint64_t seed, long long t0, double* __restrict__ usched,
+static __global__ void k_tape_generate(long long n, int p, uint64_t seed, long long t0, double* __restrict__ usched,
                                 double* __restrict__ umix, double* __restrict__ uacc, double* __restrict__ z) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int pairs = (p + 1) / 2;

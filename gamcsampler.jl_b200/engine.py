@@ -93,6 +93,25 @@ class Engine:
         self._ck(self.lib.gamc_target_callback(self.h, p, C.cast(self._target_cb, C.c_void_p), None))
         self.N, self.p = 0, p
 
+    def target_device_callback(self, p, enqueue):
+        """Generic target evaluated ON THE DEVICE: `enqueue(d_theta_ptr, level, d_out_ptr, stream_ptr)` must only
+        enqueue work on the CUDA stream `stream_ptr` that reads p doubles at `d_theta_ptr` and writes [logtarget, grad(p), pad,
+        G(p x p column-major)] at `d_out_ptr` (G at offset (p + 2) & ~1); no host synchronisation per evaluation."""
+        p = int(p)
+
+        def _cb(d_theta, p_, level, d_out, stream, _user):
+            try:
+                enqueue(int(d_theta), int(level), int(d_out), int(stream or 0))
+                return 0
+            except Exception:   # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._target_dcb = L.TARGET_ENQUEUE_FN(_cb)
+        self._ck(self.lib.gamc_target_device_callback(self.h, p, C.cast(self._target_dcb, C.c_void_p), None))
+        self.N, self.p = 0, p
+
     def read_rows(self, r0, n):
         X = np.empty((n, self.p), dtype=np.float64, order="F")
         y = np.empty(n, dtype=np.float64)
@@ -141,7 +160,57 @@ class Engine:
         self._ck(self.lib.gamc_comm_peer_path(self.h, C.byref(out)))
         return int(out.value)
 
+    def comm_set_timeout(self, seconds):
+        self._ck(self.lib.gamc_comm_set_timeout(self.h, float(seconds)))
+
     # -- sampler
+    def set_schedule_callback(self, fn):
+        """`GAMC.update!::Function`: fn(i, tot, u) -> bool (True = SMMALA step); None restores the configured schedule."""
+        if fn is None:
+            self._sched_cb = None
+            self._ck(self.lib.gamc_set_schedule_callback(self.h, None, None))
+            return
+
+        def _cb(i, tot, u, _user):
+            try:
+                return 1 if fn(int(i), int(tot), float(u)) else 0
+            except Exception:   # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._sched_cb = L.SCHEDULE_FN(_cb)
+        self._ck(self.lib.gamc_set_schedule_callback(self.h, C.cast(self._sched_cb, C.c_void_p), None))
+
+    def set_state(self, st: L.StateScalars, theta, lastmean, secondlastmean, oldinvtensor=None):
+        th, m1, m2 = (_f64(a, "C").ravel() for a in (theta, lastmean, secondlastmean))
+        Cm = None if oldinvtensor is None else _f64(oldinvtensor, "F")
+        self._ck(self.lib.gamc_set_state(self.h, C.byref(st), L.dptr(th), L.dptr(m1), L.dptr(m2), L.dptr(Cm)))
+
+    def monitor(self):
+        """(pstate.loglikelihood, pstate.logprior) of the current point."""
+        ll, lp = C.c_double(), C.c_double()
+        self._ck(self.lib.gamc_get_monitor(self.h, C.byref(ll), C.byref(lp)))
+        return ll.value, lp.value
+
+    def chain_get_logtarget(self, first, n):
+        out = np.empty(n, dtype=np.float64)
+        self._ck(self.lib.gamc_chain_get_logtarget(self.h, int(first), int(n), L.dptr(out)))
+        return out
+
+    def tune_log(self):
+        """Records of the burn-in report, one row of 16 doubles per tuning event (see gamc_tune_log_get)."""
+        n = C.c_int64()
+        self._ck(self.lib.gamc_tune_log_get(self.h, None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 16), dtype=np.float64)
+        self._ck(self.lib.gamc_tune_log_get(self.h, L.dptr(out), n.value, C.byref(n)))
+        return out[: n.value]
+
+    def probe_fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.lib.gamc_probe_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def sampler_init(self, cfg: L.Config, theta0):
         th = _f64(theta0, "C").ravel()
         assert th.shape[0] == self.p
@@ -158,6 +227,13 @@ class Engine:
 
     def tape_generate(self, n, seed):
         self._ck(self.lib.gamc_tape_generate(self.h, int(n), int(seed)))
+
+    def tape_get(self, first, n):
+        """(u_sched, u_mix, z, u_acc) of tape slots [first, first+n); z is (n, p)."""
+        us, um, ua = np.empty(n), np.empty(n), np.empty(n)
+        z = np.empty((n, self.p))
+        self._ck(self.lib.gamc_tape_get(self.h, int(first), int(n), L.dptr(us), L.dptr(um), L.dptr(z), L.dptr(ua)))
+        return us, um, z, ua
 
     def run(self, n):
         self._ck(self.lib.gamc_run(self.h, int(n)))
@@ -191,7 +267,8 @@ class Engine:
         return st
 
     def array(self, array_id):
-        is_mat = array_id in (L.ARR_TENSORLOGTARGET, L.ARR_OLDINVTENSOR, L.ARR_CHOLINVTENSOR)
+        is_mat = array_id in (L.ARR_TENSORLOGTARGET, L.ARR_OLDINVTENSOR, L.ARR_CHOLINVTENSOR, L.ARR_TENSORLOGLIKELIHOOD,
+                              L.ARR_TENSORLOGPRIOR)
         out = np.empty(self.p * self.p if is_mat else self.p, dtype=np.float64)
         self._ck(self.lib.gamc_get_array(self.h, int(array_id), L.dptr(out)))
         return out.reshape((self.p, self.p), order="F") if is_mat else out
@@ -208,6 +285,14 @@ class Engine:
         assert t.shape == obs.shape == sigma.shape
         self._ck(self.lib.gamc_batched_target_rv(self.h, L.dptr(t), L.dptr(obs), L.dptr(sigma), t.shape[0], int(nplanets)))
         self.bp = 5 * int(nplanets) + 1
+
+    def batched_target_logistic(self, X, y, lam):
+        X = _f64(X, "F")
+        y = _f64(y, "C").ravel()
+        N, p = X.shape
+        assert y.shape[0] == N
+        self._ck(self.lib.gamc_batched_target_logistic(self.h, L.dptr(X), N, L.dptr(y), N, p, float(lam)))
+        self.bp = p
 
     def batched_set_chain_offset(self, offset):
         self._ck(self.lib.gamc_batched_set_chain_offset(self.h, int(offset)))

@@ -171,6 +171,10 @@ class GAMC:
         if transform is not None and not isinstance(transform, Softabs) and not callable(transform):
             raise TypeError("transform must be softabs(alpha) or a callable H -> H' (the latter only with a GenericModel, whose "
                             "metric is evaluated on the host)")
+        if update is not None and not isinstance(update, Schedule) and not callable(update):
+            raise TypeError("update must be one of the nine schedules or a function (i, tot, u) -> Bool")
+        # `update!::Function` (src/samplers/GAMC.jl:127): one of the nine schedules with its parameters bound, or any function
+        # (i, tot, u) -> Bool, u being the iteration's schedule uniform (in place of the reference's in-line `rand(Bernoulli(.))`)
         self.update = update if update is not None else rand_update()
         self.transform = transform
         self.driftstep, self.minorscale, self.c, self.t0 = float(driftstep), float(minorscale), float(c), int(t0)
@@ -265,8 +269,9 @@ def make_config(sampler, tuner, mcrange: BasicMCRange) -> L.Config:
         return cfg
     cfg = L.Config()
     cfg.driftstep, cfg.minorscale, cfg.c, cfg.t0 = sampler.driftstep, sampler.minorscale, sampler.c, sampler.t0
-    cfg.schedule = sampler.update.kind
-    pr = list(sampler.update.params) + [float("nan")] * 3
+    is_fn = not isinstance(sampler.update, Schedule)          # a user function: installed with gamc_set_schedule_callback
+    cfg.schedule = 1 if is_fn else sampler.update.kind
+    pr = ([] if is_fn else list(sampler.update.params)) + [float("nan")] * 3
     for i in range(3):
         cfg.sched_params[i] = pr[i]
     tt = tuner.totaltuner
@@ -323,9 +328,25 @@ class _SState:
     def ratio(self):
         return self._refresh().ratio
 
+    @property
+    def logtarget(self):
+        return self._refresh().logtarget
+
+    @property
+    def loglikelihood(self):
+        return self._eng.monitor()[0]
+
+    @property
+    def logprior(self):
+        return self._eng.monitor()[1]
+
     def __getattr__(self, name):
         ids = {"lastmean": L.ARR_LASTMEAN, "secondlastmean": L.ARR_SECONDLASTMEAN, "oldinvtensor": L.ARR_OLDINVTENSOR,
-               "cholinvtensor": L.ARR_CHOLINVTENSOR, "oldfirstterm": L.ARR_OLDFIRSTTERM}
+               "cholinvtensor": L.ARR_CHOLINVTENSOR, "oldfirstterm": L.ARR_OLDFIRSTTERM,
+               # monitored extras of the current point (iterate/GAMC.jl:74-90)
+               "gradloglikelihood": L.ARR_GRADLOGLIKELIHOOD, "gradlogprior": L.ARR_GRADLOGPRIOR,
+               "tensorloglikelihood": L.ARR_TENSORLOGLIKELIHOOD, "tensorlogprior": L.ARR_TENSORLOGPRIOR,
+               "gradlogtarget": L.ARR_GRADLOGTARGET, "tensorlogtarget": L.ARR_TENSORLOGTARGET, "value": L.ARR_VALUE}
         if name in ids:
             return self._eng.array(ids[name])
         raise AttributeError(name)
@@ -354,8 +375,12 @@ class BasicMCJob:
                 return lt, grad, G
 
             eng.target_callback(model.p, _eval)
-        elif callable(getattr(sampler, "transform", None)) and not isinstance(sampler.transform, Softabs):
-            raise NotImplementedError("a callable transform needs a GenericModel (the metric of the built-in targets never leaves the device)")
+        elif getattr(sampler, "transform", None) is not None:
+            # the reference applies sampler.transform to the metric at iterate/GAMC.jl:22-24,39-41; the single-chain logistic path
+            # has no device transform (the logistic metric is positive definite and the example passes none), so refuse rather
+            # than run with different semantics
+            raise NotImplementedError("transform= is supported for GenericModel (host or device callback) and for the batched "
+                                      "chains (BatchedMCJob); the built-in single-chain logistic target takes transform=None")
         elif engine is None:
             if model.synth is not None:
                 s = model.synth
@@ -366,6 +391,8 @@ class BasicMCJob:
             eng.comm_init(*comm)
         theta0 = np.asarray(v0["p"] if isinstance(v0, dict) else v0, dtype=np.float64)
         self.cfg = make_config(sampler, self.tuner, mcrange)
+        if not isinstance(sampler, MALA):
+            eng.set_schedule_callback(None if isinstance(sampler.update, Schedule) else sampler.update)
         eng.sampler_init(self.cfg, theta0)          # initialize! + sampler_state
         self.tape = tape
         self.tape_seed = tape_seed
@@ -385,7 +412,22 @@ class BasicMCJob:
         eng.run(n)
         eng.sync()
         self._done += n
+        if isinstance(self.tuner, GAMCTuner) and self.tuner.verbose:
+            self._print_burnin_report()
         return self
+
+    def _print_burnin_report(self):
+        """The burn-in report of src/samplers/iterate/GAMC.jl:218-268, printed from the records the device kept."""
+        t = self.tuner
+        for r in self.engine.tune_log()[getattr(self, "_reported", 0):]:
+            print(f"Burnin iteration {int(r[0])} out of {self.range.burnin}...")
+            if t.totaltuner.verbose:
+                print(f"  Total : {int(r[1])}/{int(r[2])} ({100 * r[3]:.2f}%) acceptance rate")
+            if t.smmalatuner.verbose:
+                print(f"  SMMALA: {int(r[4])}/{int(r[5])} ({100 * r[6]:.2f}%) acceptance rate, {int(r[5])}/{int(r[2])} ({100 * r[7]:.2f}%) running frequency")
+            if t.amtuner.verbose:
+                print(f"  AM    : {int(r[8])}/{int(r[9])} ({100 * r[10]:.2f}%) acceptance rate, {int(r[9])}/{int(r[2])} ({100 * r[11]:.2f}%) running frequency")
+        self._reported = len(self.engine.tune_log())
 
     def output(self) -> Chain:
         nsave = max(0, self.range.nsteps - self.range.burnin)
@@ -524,9 +566,13 @@ class BatchedMCJob:
         self.engine = engine if engine is not None else Engine(device)
         if isinstance(model, RVModel):
             self.engine.batched_target_rv(model.times, model.obs, model.sigma_obs, model.nplanets)
+        elif isinstance(model, LogisticModel):
+            self.engine.batched_target_logistic(model.X, model.y, model.lam)    # the as-shipped sizes (N = 200, p = 4)
         else:
             Sinv, logconst = model.constants()
             self.engine.batched_target_mvt(Sinv, model.nu, logconst)
+        if not isinstance(sampler.update, Schedule):
+            raise NotImplementedError("the batched kernel decides the branch on the device: pass one of the nine schedules")
         self.cfg = make_config(sampler, self.tuner, mcrange)
         self.engine.batched_set_chain_offset(chain_offset)     # this rank's first chain in a chains-sharded multi-GPU job
         tr = sampler.transform

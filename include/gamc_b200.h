@@ -117,7 +117,13 @@ typedef enum {
   GAMC_ARR_OLDINVTENSOR = 5,   /* sstate.oldinvtensor     p x p  (G^-1 after SMMALA, AM covariance after AM) */
   GAMC_ARR_CHOLINVTENSOR = 6,  /* sstate.cholinvtensor    p x p lower (L L' = G^-1)                          */
   GAMC_ARR_OLDFIRSTTERM = 7,   /* sstate.oldfirstterm     p        */
-  GAMC_ARR_PROPOSED_VALUE = 8  /* sstate.pstate.value     p        */
+  GAMC_ARR_PROPOSED_VALUE = 8, /* sstate.pstate.value     p        */
+  /* monitored extras of the current point that iterate! keeps in step with the value when they are in outopts[:monitor]
+   * (src/samplers/iterate/GAMC.jl:74-90,100-106); for the logistic target they follow from (value, gradient, tensor) and lambda */
+  GAMC_ARR_GRADLOGLIKELIHOOD = 9,   /* pstate.gradloglikelihood    p      */
+  GAMC_ARR_GRADLOGPRIOR = 10,       /* pstate.gradlogprior         p      */
+  GAMC_ARR_TENSORLOGLIKELIHOOD = 11,/* pstate.tensorloglikelihood  p x p  */
+  GAMC_ARR_TENSORLOGPRIOR = 12      /* pstate.tensorlogprior       p x p  */
 } gamc_array_id;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------- */
@@ -174,6 +180,15 @@ gamc_status gamc_eval_partials(gamc_handle h, const double* theta, double* ll, d
  * GAMC_INVALID_ARG.  Non-finite values at a proposal reject it, at the initial point raise GAMC_NONFINITE_INIT. */
 typedef int32_t (*gamc_target_fn)(const double* theta, int32_t p, int32_t level, double* logtarget, double* grad, double* G, void* user);
 gamc_status gamc_target_callback(gamc_handle h, int32_t p, gamc_target_fn fn, void* user);
+/* The same closures for a model that lives ON THE DEVICE ("user-supplied device callback"): `enqueue` is called
+ * on the host but must only ENQUEUE work on `cuda_stream` (kernels, cuBLAS calls, CUDA.jl launches ...) that reads the p doubles at
+ * d_theta and writes the evaluation into d_out, laid out as the library's landing buffer:
+ *   d_out[0] = log-target, d_out[1 .. p] = gradient (level >= 1), d_out[goff + i + j*p] = tensor (level 2, column-major, after
+ *   any `sampler.transform`), goff = (p + 2) & ~1.
+ * No host synchronisation happens per evaluation: the sampler's kernels are ordered after the user's work by the stream, so a
+ * whole gamc_run stays asynchronous.  Values are those of the full log-target (prior included). */
+typedef int32_t (*gamc_target_enqueue_fn)(const double* d_theta, int32_t p, int32_t level, double* d_out, void* cuda_stream, void* user);
+gamc_status gamc_target_device_callback(gamc_handle h, int32_t p, gamc_target_enqueue_fn enqueue, void* user);
 
 /* ---- multi-GPU: observations row-sharded, one process per GPU -------------------------
  * gamc_comm_unique_id fills a 128-byte NCCL unique id on one rank; the host side (torch.distributed /
@@ -190,12 +205,33 @@ gamc_status gamc_target_callback(gamc_handle h, int32_t p, gamc_target_fn fn, vo
 gamc_status gamc_comm_unique_id(uint8_t id_out[128]);
 gamc_status gamc_comm_init(gamc_handle h, const uint8_t id[128], int32_t nranks, int32_t rank);
 gamc_status gamc_comm_peer_path(gamc_handle h, int32_t* active);
+/* How long a rank waits inside a step kernel for a peer's contribution before it gives up with GAMC_NCCL_ERROR (wall-clock
+ * seconds, measured with %globaltimer; default 30 s, or GAMC_PEER_TIMEOUT_S).  Ranks are aligned by a stream-ordered NCCL
+ * barrier at every gamc_sampler_init and at the start of every gamc_run, so the wait only has to cover kernel-time skew. */
+gamc_status gamc_comm_set_timeout(gamc_handle h, double seconds);
 
 /* ---- sampler ----------------------------------------------------------------------------------------
  * gamc_sampler_init = Klara `initialize!` + `sampler_state` for GAMC (src/samplers/GAMC.jl:157-176,202-228):
  * evaluates target/gradient/metric at theta0, checks finiteness, factorises the metric, seeds lastmean,
  * counters and tuner state (tuner_state, :195-200).  Calling it again is `reset!` (:234-260). */
 gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const double* theta0);
+
+/* `GAMC.update!::Function` (src/samplers/GAMC.jl:127; the examples pass closures, examples/logistic_regression/src/GAMC/
+ * simulations.jl:51): a user-supplied schedule.  fn(i, tot, u, user) returns 1 for an SMMALA step and 0 for an AM step at
+ * iteration i of tot; u is the iteration's schedule uniform from the tape (use it in place of `rand(Bernoulli(.))` so that the
+ * run stays reproducible).  It replaces gamc_config.schedule until fn = NULL is set.  Evaluated on the host, ahead of the
+ * device, when gamc_run builds the launch sequence -- it can depend on (i, tot, u) and on host state, not on the chain. */
+typedef int32_t (*gamc_schedule_fn)(int64_t i, int64_t tot, double u, void* user);
+gamc_status gamc_set_schedule_callback(gamc_handle h, gamc_schedule_fn fn, void* user);
+
+/* Restart a chain from saved host state (Klara has no checkpointing, `reset!` src/samplers/GAMC.jl:234-260 only
+ * re-initialises): after gamc_sampler_init, overwrite the counters / tuner state (count, updatetensorcount, step, the three
+ * BasicMCTune triples, present/pastupdatetensor) from `st`, the value, lastmean and secondlastmean from the p-vectors, and --
+ * when the last transition was an AM step (st->pastupdatetensor == 0) -- sstate.oldinvtensor (the running AM covariance, p x p)
+ * from `oldinvtensor`.  Log-target, gradient, metric and their factorisation are re-evaluated at `theta`.  The tape position
+ * restarts at 0: pass the tape of the REMAINING iterations to gamc_tape_set. */
+gamc_status gamc_set_state(gamc_handle h, const gamc_state_scalars* st, const double* theta, const double* lastmean,
+                           const double* secondlastmean, const double* oldinvtensor);
 
 /* Random tape for the next n iterations (host arrays): u_sched[n], u_mix[n], z[p x n column-major],
  * u_acc[n].  Replaces the reference's in-line `rand(Bernoulli(.))`, `rand(proposal)`, `randn(p)`, `rand()`
@@ -205,6 +241,10 @@ gamc_status gamc_tape_set(gamc_handle h, int64_t n, const double* u_sched, const
                           const double* z, const double* u_acc);
 /* Device-generated tape (Philox, throughput mode): same slots, no host traffic. */
 gamc_status gamc_tape_generate(gamc_handle h, int64_t n, uint64_t seed);
+
+/* Read slots [first, first+n) of the resident tape back (host arrays as in gamc_tape_set; any pointer may be NULL): what a
+ * device-generated tape drew, e.g. to replay a run on the host. */
+gamc_status gamc_tape_get(gamc_handle h, int64_t first, int64_t n, double* u_sched, double* u_mix, double* z, double* u_acc);
 
 /* Enqueue n `iterate!` transitions (src/samplers/iterate/GAMC.jl:1-293) reading the resident tape;
  * asynchronous.  Samples with iteration index > burnin are appended to the device chain buffer. */
@@ -222,7 +262,22 @@ gamc_status gamc_peek_kinds(gamc_handle h, int64_t n, uint8_t* kinds_out);
 
 gamc_status gamc_get_state(gamc_handle h, gamc_state_scalars* out);
 gamc_status gamc_get_array(gamc_handle h, int32_t array_id, double* out);
+/* pstate.loglikelihood and pstate.logprior of the current point (monitored extras, src/samplers/iterate/GAMC.jl:100-106). */
+gamc_status gamc_get_monitor(gamc_handle h, double* loglikelihood, double* logprior);
+/* pstate.logtarget of the saved samples [first, first+n) (Klara `outopts[:monitor]` containing :logtarget). */
+gamc_status gamc_chain_get_logtarget(gamc_handle h, int64_t first, int64_t n, double* logtarget);
+/* The burn-in report of src/samplers/iterate/GAMC.jl:199-292, one record per tuning event, recorded on the device (the
+ * reference prints it when a tuner is verbose; the front-end prints the same lines from these records).  Record layout, 16
+ * doubles: [count, total accepted, total proposed, total rate, smmala accepted, smmala proposed, smmala rate, smmala frequency,
+ * am accepted, am proposed, am rate, am frequency, step after tune!, 0, 0, 0] -- counters as they stood before reset_burnin!.
+ * Copies up to max_records records into out; *n_records receives the number recorded so far. */
+gamc_status gamc_tune_log_get(gamc_handle h, double* out, int64_t max_records, int64_t* n_records);
 
+
+/* Batched logistic regression (the as-shipped example: N = 200, p = 4, 10 chains; examples/logistic_regression/src/GAMC/
+ * simulations.jl:13-37,68-91): the same callbacks as gamc_target_logistic, evaluated inside the persistent batched kernel.
+ * p <= 32, N <= 2048. */
+gamc_status gamc_batched_target_logistic(gamc_handle h, const double* X, int64_t ldX, const double* y, int64_t N, int32_t p, double lambda);
 
 /* ---- batched chains (small p): many independent chains, one persistent kernel per run -----------------------------
  * Replaces the reference's sequential `while i <= nchains ... run(job)` loops (examples/t_distribution/src/GAMC/simulations.jl:56-79)
@@ -260,14 +315,23 @@ typedef enum {
   GAMC_K_METRIC = 2,     /* X' diag(w) X on FP64 DMMA                             */
   GAMC_K_REDUCE = 3,     /* deterministic partial reductions                      */
   GAMC_K_LINALG = 4,     /* Cholesky / solves / proposal / MH accept kernels      */
-  GAMC_K_ALLREDUCE = 5,  /* NCCL all-reduce                                       */
-  GAMC_K_COUNT = 6
+  GAMC_K_ALLREDUCE = 5,  /* NCCL all-reduce / peer flag                           */
+  GAMC_K_LAND = 6,       /* k_land: prior terms, slot fill, ratio partials (= the peer all-reduce in multi-GPU jobs) */
+  GAMC_K_SMMALA_PRE = 7, /* k_smmala_pre: [factorisation of a re-evaluated point,] proposal                          */
+  GAMC_K_SMMALA_POST = 8,/* k_smmala_post: factorisation of the proposal's metric, ratio, accept/reject, tail        */
+  GAMC_K_AM_PRE = 9,     /* k_am_pre / k_am_pre_r1 on the critical path (speculative ones run on a side stream)      */
+  GAMC_K_AM_POST = 10,   /* k_am_post: partial sums, peer all-reduce of the scalar, accept/reject, tail               */
+  GAMC_K_HANDOVER = 11,  /* SMMALA -> AM hand-over: k_triinv, k_wtw, k_w_to_l                                        */
+  GAMC_K_COUNT = 12
 } gamc_kernel_family;
 gamc_status gamc_profile_enable(gamc_handle h, int32_t on);
 gamc_status gamc_profile_get(gamc_handle h, int32_t family, int64_t* launches, double* total_ms);
 gamc_status gamc_profile_reset(gamc_handle h);
 /* Total kernels launched by this handle since creation (for bench.py's gpu_launches). */
 gamc_status gamc_launch_count(gamc_handle h, int64_t* out);
+/* FP64 yard-sticks of THIS device, measured now: a register-only `mma.sync.m8n8k4.f64` (DMMA) loop and a DFMA loop on every
+ * SM (a few milliseconds).  bench.py quotes the metric pass against the DMMA figure of the same lease. */
+gamc_status gamc_probe_fp64_peak(gamc_handle h, double* dmma_tflops, double* dfma_tflops);
 
 #ifdef __cplusplus
 }

@@ -26,15 +26,28 @@ def test_reference_arm_json_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["cpu_baseline"]["mode"] == "composed" and d["scaling"] == "strong"
+
+
+def test_reference_arm_executes_short_jobs():
+    """K <= 32: the CPU arm executes the job's own K transitions on the shared tape instead of composing per-kind costs."""
+    d = _run(["--impl", "reference", "--logN", "11", "--p", "8", "--steps", "20", "--warmup", "3"])
+    cb = d["cpu_baseline"]
+    assert cb["mode"] == "executed" and cb["n_smmala"] + cb["n_am"] == 20 and cb["n_smmala"] >= 3
+    assert d["value"] == pytest.approx(20 / cb["seconds"])
 
 
 @pytest.mark.gpu
 def test_gpu_arm_json_line():
-    d = _run(["--logN", "14", "--p", "32", "--steps", "120", "--warmup", "5", "--ess-steps", "0"])
-    assert BASE_KEYS | {"roofline", "clocks", "gpu_launches"} <= set(d)
+    d = _run(["--logN", "14", "--p", "32", "--steps", "120", "--warmup", "5", "--ess-steps", "0", "--c3-logN", "13", "--c3-steps", "8"])
+    assert BASE_KEYS | {"roofline", "clocks", "gpu_launches", "parity", "limiter", "c3", "fp64_probe"} <= set(d)
     assert d["metric"] == "gamc_iters_per_sec" and d["unit"] == "iters/s" and d["n_gpus"] == 1 and d["dtype"] == "f64"
-    r = d["roofline"]
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["achieved"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert d["scaling"] == "strong" and d["value"] == pytest.approx(d["iters_per_sec"])
+    r = d["roofline"]                               # the dominant data-parallel kernel by time share
+    assert (r["bound"], r["unit"]) in (("hbm", "GB/s"), ("tensor", "TFLOP/s")) and r["achieved"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert d["parity"]["ok"] is True and d["parity"]["relerr_vs_oracle"]["metric"] <= 1e-10
+    assert d["fp64_probe"]["dmma_tflops"] > 10 and d["c3"]["iters_per_sec"] > 0 and d["c3"]["p"] == 512
+    assert d["clocks"]["samples"] >= 0 and d["limiter"]["us_per_step"]["smmala_post"] > 0
     assert d["gpu_launches"] > 3 * d["steps"]
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 8 * (32 + 3) and e["d2h_bytes_per_step"] > 0

@@ -92,9 +92,11 @@ def _run_both(gamc, engine, N, p, nsteps, burnin, seed, am_mode=0, update=None, 
 
 
 @pytest.mark.parametrize("am_mode", [0, 1, 2])
-@pytest.mark.parametrize("N,p,nsteps", [(200, 4, 3000), (500, 33, 1200), (2000, 64, 1000), (3000, 130, 1000), (6000, 256, 300), (4000, 512, 120)])
+@pytest.mark.parametrize("N,p,nsteps", [(200, 4, 3000), (500, 33, 1200), (2000, 64, 1000), (3000, 130, 1000), (6000, 256, 1000), (4000, 512, 1000),
+                                        (2500, 300, 160), (2500, 352, 160), (2500, 353, 120)])
 def test_trajectory_parity(gamc, engine, N, p, nsteps, am_mode):
-    """Same host-drawn normals and uniforms => step-for-step agreement for >= 1000 iterations.
+    """Same host-drawn normals and uniforms => step-for-step agreement for >= 1000 iterations, including the BASELINE
+    dimensions p = 256 and p = 512; p = 300 / 352 / 353 straddle the panel-buffer switch of the rank-one AM update.
     am_mode 0 = literal covariance recursion + Cholesky per AM step; 1 = rank-one Cholesky update (fast path);
     2 = the same update computed speculatively for both accept/reject outcomes while the data pass runs."""
     burnin = nsteps // 5
