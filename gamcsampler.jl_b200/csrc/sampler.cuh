@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, 
     }
     __syncthreads();
     if (warp == b && i < p) acc += accd[lane];
-    if (nbuf == 1 && b + 1 < nblk) issue_panel(b + 1, tid, LA_THREADS);
+    if (nbuf == 1 && b + 1 < nblk) { issue_panel(b + 1, tid, LA_THREADS); cp_async_commit(); }   // committed here: wait_group at the loop top only covers committed groups
   }
   const int fin = isfinite(sigma) ? 0 : 1;
   if (__syncthreads_or(fin)) {

@@ -201,3 +201,27 @@ def test_metric_planner_invariants(tmp_path):
                     os.path.join(root, "tests", "cpp", "plan_check.cu"), "-o", exe], check=True, capture_output=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:]
+
+
+def test_julia_binding_covers_every_entry_point():
+    """The Julia `ccall` front-end (not executable in this image) binds every symbol include/gamc_b200.h declares, and its C
+    structs list the same fields, in the same order, as the header."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "gamc_b200.h")).read()
+    jl = open(os.path.join(root, "gamcsampler.jl_b200", "julia", "GAMCSamplerB200.jl")).read()
+    names = sorted(set(re.findall(r"\b(gamc_[a-z_0-9]+)\s*\(", header)))
+    bound = set(re.findall(r"\(:(gamc_[a-z_0-9]+), libgamc\)", jl))
+    assert [n for n in names if n not in bound] == []
+    for cname, jname in (("gamc_config", "CConfig"), ("gamc_state_scalars", "CState")):
+        body = [c for c in header.split("typedef struct {") if re.search(r"\} " + cname + ";", c)][-1].split("} " + cname + ";")[0]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        cfields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(",")[0:1] + decl.split(",")[1:]:
+                cfields.append(re.sub(r"\[.*?\]", "", part.strip().split()[-1]))
+        jbody = re.search(r"struct " + jname + r"\n(.*?)\nend", jl, re.S).group(1)
+        jfields = re.findall(r"([A-Za-z_0-9]+)::", jbody)
+        assert jfields == cfields, (jname, jfields, cfields)
