@@ -132,6 +132,12 @@ SIGNATURES = {
     "gamc_chain_get_logtarget": (C.c_int, [_H, C.c_int64, C.c_int64, _DP]),
     "gamc_tune_log_get": (C.c_int, [_H, _DP, C.c_int64, C.POINTER(C.c_int64)]),
     "gamc_probe_fp64_peak": (C.c_int, [_H, _DP, _DP]),
+    "gamc_bigd_target_mvt": (C.c_int, [_H, C.c_int32, C.c_double, _DP, _DP]),
+    "gamc_bigd_set_chain_offset": (C.c_int, [_H, C.c_int64]),
+    "gamc_bigd_init": (C.c_int, [_H, C.POINTER(Config), C.c_int32, _DP, C.c_int32, C.c_double, C.c_int32]),
+    "gamc_bigd_run": (C.c_int, [_H, C.c_int64, C.c_uint64, _DP, _DP, _DP, _DP]),
+    "gamc_bigd_chain_get": (C.c_int, [_H, C.c_int32, C.c_int32, _DP, _U8P]),
+    "gamc_bigd_get_state": (C.c_int, [_H, C.c_int32, C.POINTER(StateScalars), _DP]),
     "gamc_tape_get": (C.c_int, [_H, C.c_int64, C.c_int64, _DP, _DP, _DP, _DP]),
     "gamc_batched_target_logistic": (C.c_int, [_H, _DP, C.c_int64, _DP, C.c_int64, C.c_int32, C.c_double]),
 }

@@ -1,0 +1,807 @@
+// bigd.cuh -- batched GAMC chains of the multivariate-t target in LARGE dimension (33 <= d <= 1024; BASELINE config 4: d = 1024,
+// 4096 chains per GPU).  Reference: examples/t_distribution/src/GAMC/simulations.jl:17-39 (target, `transform = softabs(H, 1000)`),
+// :56-79 (the sequential chain loop), and the transition src/samplers/iterate/GAMC.jl:1-293.
+//
+// The reference handles this target densely: ForwardDiff Hessian (O(d^2) duals), `eig` inside softabs, `inv`, `chol`, two `logdet`s
+// per SMMALA step -- O(d^3) per chain and step, hopeless at d = 1024 x 4096 chains.  Here the STRUCTURE of the target carries the
+// SMMALA branch (tests/bigd_ref.py states the algebra in NumPy; tests/test_bigd_math.py checks it against the dense oracle):
+//   * T = inv(Sigma_t) is tridiagonal; tensor = -Hessian = a (T - beta v v'), v = T x           (rank-one modification)
+//   * softabs changes only the eigenvalues below 21/alpha: G = a T + V S V', V = [lowest eigenvectors ..., v]. The eigenvalues
+//     come from bisection on the inertia count of the LDL' recurrence of T - mu plus the sign of the secular function, the
+//     eigenvectors from (T - mu)^-1 v: O(d) per sweep, no dense matrix, no eigen-decomposition
+//   * reverse Cholesky factor of G in product form  Lm = sqrt(a) L_T K_1 ... K_m,  K = chol(I + W S W') from a row sweep with a
+//     32 x 32 state held in the registers of one warp (lane = row of the state)
+//   * G^-1 grad, chol(G^-1) z, logdet and the quadratic forms of the acceptance ratio are recurrences over the d rows
+// ONE WARP PER CHAIN runs all of that: 4096 chains = 4096 warps, all resident at once.
+// The AM branch needs the dense Cholesky factor of the proposal covariance (d x d per chain, 8 MB at d = 1024: the HBM-resident
+// part of the state, 32 GB for 4096 chains): seeded from the structure at the SMMALA -> AM hand-over (bd_handover), then updated
+// by the same closed-form rank-one sweep as the single-chain path (sampler.cuh k_am_pre_r1), one CTA per chain.
+#pragma once
+#include "common.cuh"
+#include "synth.cuh"
+
+namespace gamc {
+
+constexpr int BD_CH = 32;        // columns per product factor (= warp width: lane <-> column)
+constexpr int BD_WPB = 4;        // chains (warps) per CTA in the warp-per-chain kernels
+constexpr int BD_MAXD = 1024;
+constexpr int BD_NBISECT = 60;
+
+enum { BDV_THETA = 0, BDV_PROP, BDV_MU, BDV_M1, BDV_M2, BDV_G0, BDV_G1, BDV_F0, BDV_F1, BDV_V0, BDV_V1, BDV_N };   // G/F/V: per evaluation slot
+enum { BDS_LT = 0, BDS_LTP, BDS_A0, BDS_A1, BDS_BETA0, BDS_BETA1, BDS_SL0, BDS_SL1, BDS_NCH0, BDS_NCH1, BDS_OK1, BDS_CUR, BDS_STEP, BDS_SQSTEP,
+       BDS_RATIO, BDS_COUNT, BDS_UPD, BDS_TACC, BDS_TPROP, BDS_TTOT, BDS_TRATE, BDS_SMACC, BDS_SMPROP, BDS_SMTOT, BDS_AMACC, BDS_AMPROP,
+       BDS_AMTOT, BDS_PAST, BDS_PRESENT, BDS_ERR, BDS_SAVED, BDS_US, BDS_UM, BDS_UA, BDS_R0, BDS_R1, BDS_N = 40 };
+
+struct BdCfg {
+  int d, nchains, ncmax;
+  long long chain_offset;
+  int transform; double alpha;
+  // target: natural-order tridiagonal T = inv(Sigma_t) (td, te), bidiagonal Cholesky factor of the index-reversed T (ld, le, 1/ld)
+  const double* td; const double* te; const double* ld; const double* le; const double* rld;
+  double nu, logconst, sumlog_ld, gersh_lo, gersh_hi;
+  // sampler / tuner / range (same meaning as gamc_config)
+  double driftstep, minorscale, sqrtminorscale, c;
+  int t0, schedule; double sp0, sp1, sp2;
+  int tuning, count_total, is_accrate, verbose_sm, verbose_am, period;
+  long long nsteps, burnin;
+  double targetrate, score_k;
+  // tape (null -> Philox with `seed`): [chain][t], z [chain][t][d]
+  const double* tape_usched; const double* tape_umix; const double* tape_uacc; const double* tape_z;
+  long long tape_len; unsigned long long seed;
+  // state
+  double* vecs;                  // [nchains][BDV_N][d]
+  double* scal;                  // [nchains][BDS_N]
+  double* W; double* B;          // [nchains][2][ncmax][d][32]   product-factor generators of the two evaluation slots
+  double* delta;                 // [nchains][2][ncmax][d]
+  double* S;                     // [nchains][2][ncmax][32]
+  double* L; double* rdiagL;     // [nchains][d*d] dense AM factor (natural order, column-major, lower), [nchains][d]
+  double* chain_value; unsigned char* chain_accept; long long chain_cap;   // [chain][cap][d], [chain][cap]
+};
+
+struct BdChain {                 // per-warp view of one chain
+  const BdCfg* C; int chain, lane, d;
+  double* s;
+  __device__ double* vec(int k) const { return C->vecs + ((size_t)chain * BDV_N + k) * d; }
+  __device__ size_t slot_chunk(int slot, int k) const { return ((size_t)chain * 2 + slot) * C->ncmax + k; }
+  __device__ double* Wc(int slot, int k) const { return C->W + slot_chunk(slot, k) * (size_t)d * BD_CH; }
+  __device__ double* Bc(int slot, int k) const { return C->B + slot_chunk(slot, k) * (size_t)d * BD_CH; }
+  __device__ double* Dc(int slot, int k) const { return C->delta + slot_chunk(slot, k) * (size_t)d; }
+  __device__ double* Sc(int slot, int k) const { return C->S + slot_chunk(slot, k) * BD_CH; }
+};
+
+// index-reversed ("M space") view of the tridiagonal T: row i' = d-1-i
+__device__ __forceinline__ double bd_tdm(const BdCfg& C, int i) { return C.td[C.d - 1 - i]; }
+__device__ __forceinline__ double bd_tem(const BdCfg& C, int i) { return C.te[C.d - 2 - i]; }   // between rows i and i+1 of M space
+
+// s(lam) - lam for Klara's softabs s(lam) = lam coth(alpha lam) (1/alpha at 0), accurate for every sign and size of lam
+__device__ inline double bd_softabs_gap(double lam, double alpha) {
+  const double x = alpha * lam;
+  if (fabs(x) < 1e-8) return 1.0 / alpha - lam;
+  if (x > 0.0) return x < 350.0 ? 2.0 * lam / expm1(2.0 * x) : 0.0;
+  return -2.0 * lam + (x > -350.0 ? (-2.0 * lam) / expm1(-2.0 * x) : 0.0);
+}
+
+// ---- random numbers of (chain, iteration): same conventions as the small-p batched kernel (batched.cuh bt_draw) ----------------
+__device__ inline void bd_uniforms(const BdCfg& C, int chain, long long t, long long tape_pos, double& us, double& um, double& ua) {
+  if (C.tape_z) {
+    const size_t o = (size_t)chain * C.tape_len + tape_pos;
+    us = C.tape_usched[o]; um = C.tape_umix[o]; ua = C.tape_uacc[o];
+    return;
+  }
+  const uint32_t gchain = (uint32_t)(C.chain_offset + chain);
+  const Philox4 r = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 0x51u, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
+  const Philox4 r2 = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 0x52u, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
+  us = philox_u53(r.x, r.y); um = philox_u53(r.z, r.w); ua = philox_u53(r2.x, r2.y);
+  if (ua <= 0.0) ua = 1.0 / 9007199254740992.0;
+}
+__device__ inline double bd_normal(const BdCfg& C, int chain, long long t, long long tape_pos, int i) {
+  if (C.tape_z) return C.tape_z[((size_t)chain * C.tape_len + tape_pos) * C.d + i];
+  const uint32_t gchain = (uint32_t)(C.chain_offset + chain);
+  const Philox4 q = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 0x100u + (uint32_t)i, (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
+  double u1 = philox_u53(q.x, q.y); const double u2 = philox_u53(q.z, q.w);
+  if (u1 <= 0.0) u1 = 1.0 / 9007199254740992.0;
+  double sn, cs; sincospi(2.0 * u2, &sn, &cs);
+  return sqrt(-2.0 * log(u1)) * cs;
+}
+
+__device__ inline bool bd_schedule(const BdCfg& C, long long i, double u) {       // src/samplers/GAMC.jl:264-337
+  const double di = (double)i, dt = (double)C.nsteps;
+  auto par = [](double v, double d) { return isnan(v) ? d : v; };
+  switch (C.schedule) {
+    case 0: return false;
+    case 1: return true;
+    case 2: { const long long n = (long long)par(C.sp0, 10.0); return n > 0 && (i % n) == 0; }
+    case 3: return u <= par(C.sp0, 0.5);
+    case 4: return u <= par(C.sp1, 0.2) * cos(par(C.sp0, 10.0) * di * 3.14159265358979323846 / dt) + par(C.sp2, 0.2);
+    case 5: { const double b = par(C.sp1, 0.0); return u <= (1 - b) * exp(-par(C.sp0, 10.0) * di / dt) + b; }
+    case 6: { const double b = par(C.sp1, 0.0); return u <= (1 - b) * (1 / (1 + par(C.sp0, 1e-2) * di)) + b; }
+    case 7: { const double b = par(C.sp1, 0.0); return u <= (1 - b) * pow(par(C.sp0, 1e-3), di / dt) + b; }
+    case 8: { const double b = par(C.sp1, 0.0); return u <= (1 - b) * (1 / (1 + par(C.sp0, 1e-5) * (di * di))) + b; }
+    default: return true;
+  }
+}
+
+// =====================================================================================================
+// warp-level pieces (all 32 lanes call; xs / vm are per-warp shared-memory vectors of length d in M-space order)
+// =====================================================================================================
+// y = T x in natural order (global vectors), returns q = x'y to every lane
+__device__ inline double bd_tmatvec(const BdCfg& C, const double* x, double* y, int lane) {
+  const int d = C.d;
+  double q = 0.0;
+  for (int i = lane; i < d; i += 32) {
+    double v = C.td[i] * x[i];
+    if (i > 0) v = fma(C.te[i - 1], x[i - 1], v);
+    if (i + 1 < d) v = fma(C.te[i], x[i + 1], v);
+    y[i] = v;
+    q = fma(x[i], v, q);
+  }
+  return warp_sum(q);
+}
+
+// One LDL' sweep of T' - mu (each lane its own mu): number of eigenvalues of A = T' - beta v v' below mu = negative pivots +
+// [f(mu) < 0], f the secular function 1 - beta v'(T'-mu)^-1 v.
+__device__ inline int bd_count(const BdCfg& C, const double* vm, double beta, double mu) {
+  const int d = C.d;
+  const double pivmin = 1e-290;
+  double D = bd_tdm(C, 0) - mu;
+  if (fabs(D) < pivmin) D = -pivmin;
+  double rD = 1.0 / D, z = vm[0];
+  int neg = D < 0.0;
+  double acc = z * z * rD;
+  for (int i = 1; i < d; ++i) {
+    const double e = bd_tem(C, i - 1);
+    const double l = e * rD;
+    D = (bd_tdm(C, i) - mu) - l * e;
+    if (fabs(D) < pivmin) D = -pivmin;
+    rD = 1.0 / D;
+    z = fma(-l, z, vm[i]);
+    neg += D < 0.0;
+    acc = fma(z * z, rD, acc);
+  }
+  return neg + ((1.0 - beta * acc) < 0.0 ? 1 : 0);
+}
+
+// (sqrt(a) L_T) u = b in place on the warp's vector (first-order recurrence; every lane runs it, lane 0 stores)
+__device__ inline void bd_bidiag_solve(const BdCfg& C, double sa, double* xs, int lane) {
+  const int d = C.d;
+  const double rsa = 1.0 / sa;
+  __syncwarp();
+  if (lane == 0) {
+    double u = xs[0] * rsa * C.rld[0];
+    xs[0] = u;
+    for (int i = 1; i < d; ++i) { u = (xs[i] * rsa - C.le[i - 1] * u) * C.rld[i]; xs[i] = u; }
+  }
+  __syncwarp();
+}
+// (sqrt(a) L_T)' y = b
+__device__ inline void bd_bidiag_solve_t(const BdCfg& C, double sa, double* xs, int lane) {
+  const int d = C.d;
+  const double rsa = 1.0 / sa;
+  __syncwarp();
+  if (lane == 0) {
+    double y = xs[d - 1] * rsa * C.rld[d - 1];
+    xs[d - 1] = y;
+    for (int i = d - 2; i >= 0; --i) { y = (xs[i] * rsa - C.le[i] * y) * C.rld[i]; xs[i] = y; }
+  }
+  __syncwarp();
+}
+// y = (sqrt(a) L_T)' x (no recurrence)
+__device__ inline void bd_bidiag_mult_t(const BdCfg& C, double sa, double* xs, int lane) {
+  const int d = C.d;
+  __syncwarp();
+  double mine[BD_MAXD / 32];
+#pragma unroll
+  for (int k = 0; k < BD_MAXD / 32; ++k) {
+    const int i = lane + 32 * k;
+    mine[k] = (i < d) ? sa * (C.ld[i] * xs[i] + (i + 1 < d ? C.le[i] * xs[i + 1] : 0.0)) : 0.0;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < BD_MAXD / 32; ++k) { const int i = lane + 32 * k; if (i < d) xs[i] = mine[k]; }
+  __syncwarp();
+}
+
+// K y = u in place: y_i = (u_i - w_i'sigma)/sqrt(delta_i), sigma += b_i y_i   (lane <-> component of sigma)
+__device__ inline void bd_k_solve(const double* __restrict__ W, const double* __restrict__ B, const double* __restrict__ dl, int d, double* xs, int lane) {
+  double sig = 0.0;
+  for (int i0 = 0; i0 < d; i0 += 4) {
+    double w[4], b[4], rs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = min(i0 + u, d - 1);
+      w[u] = W[(size_t)i * BD_CH + lane]; b[u] = B[(size_t)i * BD_CH + lane]; rs[u] = rsqrt(dl[i]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u < d) {
+        const double dot = warp_sum(w[u] * sig);
+        const double y = (xs[i0 + u] - dot) * rs[u];
+        sig = fma(b[u], y, sig);
+        if (lane == 0) xs[i0 + u] = y;
+      }
+    }
+  }
+  __syncwarp();
+}
+// K' w = b in place (backward): w_j = (b_j - b_j'tau)/sqrt(delta_j), tau += w_j (generator row) w_j
+__device__ inline void bd_k_solve_t(const double* __restrict__ W, const double* __restrict__ B, const double* __restrict__ dl, int d, double* xs, int lane) {
+  double tau = 0.0;
+  for (int j0 = d - 1; j0 >= 0; j0 -= 4) {
+    double w[4], b[4], rs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = max(j0 - u, 0);
+      w[u] = W[(size_t)j * BD_CH + lane]; b[u] = B[(size_t)j * BD_CH + lane]; rs[u] = rsqrt(dl[j]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (j0 - u >= 0) {
+        const double dot = warp_sum(b[u] * tau);
+        const double y = (xs[j0 - u] - dot) * rs[u];
+        tau = fma(w[u], y, tau);
+        if (lane == 0) xs[j0 - u] = y;
+      }
+    }
+  }
+  __syncwarp();
+}
+// out = K' w in place (backward): out_j = sqrt(delta_j) w_j + b_j'tau, tau += w_j (generator row) w_j
+__device__ inline void bd_k_mult_t(const double* __restrict__ W, const double* __restrict__ B, const double* __restrict__ dl, int d, double* xs, int lane) {
+  double tau = 0.0;
+  for (int j = d - 1; j >= 0; --j) {
+    const double w = W[(size_t)j * BD_CH + lane], b = B[(size_t)j * BD_CH + lane];
+    const double x = xs[j];
+    const double dot = warp_sum(b * tau);
+    tau = fma(w, x, tau);
+    __syncwarp();
+    if (lane == 0) xs[j] = fma(sqrt(dl[j]), x, dot);
+  }
+  __syncwarp();
+}
+
+// Lm y = b, Lm' y = b, y = Lm' x for the product-form factor of `slot` (nch factors); xs in M-space order
+__device__ inline void bd_solve(const BdChain& Q, int slot, int nch, double sa, double* xs) {
+  bd_bidiag_solve(*Q.C, sa, xs, Q.lane);
+  for (int k = 0; k < nch; ++k) bd_k_solve(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+}
+__device__ inline void bd_solve_t(const BdChain& Q, int slot, int nch, double sa, double* xs) {
+  for (int k = nch - 1; k >= 0; --k) bd_k_solve_t(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+  bd_bidiag_solve_t(*Q.C, sa, xs, Q.lane);
+}
+__device__ inline void bd_mult_t(const BdChain& Q, int slot, int nch, double sa, double* xs) {
+  bd_bidiag_mult_t(*Q.C, sa, xs, Q.lane);
+  for (int k = 0; k < nch; ++k) bd_k_mult_t(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+}
+// NOTE on bd_mult_t: Lm' = K_m' ... K_1' (sqrt(a) L_T)'  -- the bidiagonal factor is applied first, then K_1', ..., K_m'.
+
+// =====================================================================================================
+// Level-2 evaluation at x = vec(xv) into evaluation slot `slot`: log-target, gradient, v, product-form factor of the softabs metric,
+// G^-1 grad ("firstterm"), sum log diag.  Returns the log-target; *ok = 0 if anything is non-finite / not positive definite /
+// (*ok = -1: needs more than ncmax product factors).  vm, xs: per-warp shared vectors (length d); bc: per-warp 2 x 32 broadcast rows.
+// =====================================================================================================
+__device__ inline double bd_eval2(const BdChain& Q, int xv, int slot, double* vm, double* xs, double* bc, int* ok) {
+  const BdCfg& C = *Q.C;
+  const int d = Q.d, lane = Q.lane;
+  const double* x = Q.vec(xv);
+  double* v = Q.vec(BDV_V0 + slot);
+  double* g = Q.vec(BDV_G0 + slot);
+  *ok = 1;
+  const double q = bd_tmatvec(C, x, v, lane);
+  const double lt = C.logconst - 0.5 * (C.nu + d) * log1p(q / C.nu);
+  const double a = (C.nu + d) / (C.nu + q), beta = 2.0 / (C.nu + q);
+  if (!isfinite(lt) || !(a > 0.0)) { *ok = 0; return lt; }
+  __syncwarp();
+  double vv = 0.0;
+  for (int i = lane; i < d; i += 32) { const double vi = v[i]; g[i] = -a * vi; vm[d - 1 - i] = vi; vv = fma(vi, vi, vv); }
+  vv = warp_sum(vv);
+  __syncwarp();
+  // ---- how many eigenvalues of the tensor a (T - beta v v') does softabs change?  (none without the transform)
+  const double thr = 21.0 / C.alpha;
+  int r = 0;
+  if (C.transform == 1) r = bd_count(C, vm, beta, thr / a);
+  const int ncol = r + 1;                                  // + the column v itself (the rank-one part of the tensor)
+  const int nch = (ncol + BD_CH - 1) / BD_CH;
+  if (nch > C.ncmax) { *ok = -1; return lt; }              // more product factors than allocated (gamc_bigd_init max_factors)
+  const double sa = sqrt(a);
+  double sumlog = 0.5 * d * log(a) + C.sumlog_ld;
+  const double lo0 = C.gersh_lo - beta * vv - 1e-3 * fmax(1.0, fabs(C.gersh_lo));
+  for (int k = 0; k < nch; ++k) {
+    double* W = Q.Wc(slot, k); double* B = Q.Bc(slot, k); double* dl = Q.Dc(slot, k);
+    const int col = k * BD_CH + lane;                      // this lane's column of V
+    const bool is_root = col < r, is_v = col == r;
+    double Sj = 0.0, scale = 1.0;
+    // ---- root col+1 of the secular equation by bisection on the count (every lane its own root, in lockstep)
+    double mu = 0.0;
+    const bool any_root = k * BD_CH < r;                   // the last factor may hold the column v only
+    if (any_root) {
+      double lo = lo0, hi = fmin(thr / a, C.gersh_hi);
+      const int want = col + 1;
+      for (int it = 0; it < BD_NBISECT; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        const int cnt = bd_count(C, vm, beta, mid);        // lanes without a root run along (uniform control flow)
+        if (cnt >= want) hi = mid; else lo = mid;
+      }
+      mu = 0.5 * (lo + hi);
+    }
+    // ---- eigenvector x = (T' - mu)^-1 v' (unnormalised) by the LDL' recurrence: forward sweep parks y and the multipliers in the
+    //      chunk's own W / B storage, backward sweep overwrites W with x
+    if (!any_root) {
+      for (int i = 0; i < d; ++i) W[(size_t)i * BD_CH + lane] = is_v ? vm[i] : 0.0;
+      if (is_v) Sj = -a * beta;
+      __syncwarp();
+    } else {
+      const double pivmin = 1e-290;
+      double D = bd_tdm(C, 0) - mu;
+      if (fabs(D) < pivmin) D = -pivmin;
+      double rD = 1.0 / D, z = vm[0];
+      if (is_root) { W[lane] = z * rD; B[lane] = 0.0; }
+      for (int i = 1; i < d; ++i) {
+        const double e = bd_tem(C, i - 1);
+        const double l = e * rD;
+        D = (bd_tdm(C, i) - mu) - l * e;
+        if (fabs(D) < pivmin) D = -pivmin;
+        rD = 1.0 / D;
+        z = fma(-l, z, vm[i]);
+        if (is_root) { W[(size_t)i * BD_CH + lane] = z * rD; B[(size_t)i * BD_CH + lane] = l; }
+      }
+      __syncwarp();
+      double xn = 0.0, amax = 0.0, ssq = 0.0;
+      for (int i = d - 1; i >= 0; --i) {
+        if (is_root) {
+          const double y = W[(size_t)i * BD_CH + lane];
+          const double lnext = (i + 1 < d) ? B[(size_t)(i + 1) * BD_CH + lane] : 0.0;
+          xn = fma(-lnext, xn, y);
+          W[(size_t)i * BD_CH + lane] = xn;
+          amax = fmax(amax, fabs(xn)); ssq = fma(xn, xn, ssq);
+        } else {
+          W[(size_t)i * BD_CH + lane] = is_v ? vm[i] : 0.0;
+        }
+      }
+      if (is_root) {
+        int ex; frexp(amax, &ex);
+        scale = ldexp(1.0, -ex);                           // power of two: the column is used as x * scale (exact)
+        Sj = bd_softabs_gap(a * mu, C.alpha) / (ssq * scale * scale);
+        if (!isfinite(Sj) || !(ssq > 0.0)) Sj = nan("");
+      } else if (is_v) {
+        Sj = -a * beta;
+      }
+      __syncwarp();
+    }
+    if (lane < BD_CH) Q.Sc(slot, k)[lane] = Sj;
+    // ---- W <- (sqrt(a) L_T)^-1 (x scale): bidiagonal recurrence, lane <-> column
+    {
+      const double rsa = 1.0 / sa;
+      double u = W[lane] * scale * rsa * C.rld[0];
+      W[lane] = u;
+      for (int i = 1; i < d; ++i) {
+        u = (W[(size_t)i * BD_CH + lane] * scale * rsa - C.le[i - 1] * u) * C.rld[i];
+        W[(size_t)i * BD_CH + lane] = u;
+      }
+      __syncwarp();
+    }
+    // ---- W <- K_{k-1}^-1 ... K_0^-1 W: lane <-> column, every lane carries its own sigma (32 doubles); generator rows of the
+    //      earlier factor are broadcast through shared memory
+    for (int c = 0; c < k; ++c) {
+      const double* Wp = Q.Wc(slot, c); const double* Bp = Q.Bc(slot, c); const double* dp = Q.Dc(slot, c);
+      double sig[BD_CH];
+#pragma unroll
+      for (int m = 0; m < BD_CH; ++m) sig[m] = 0.0;
+      for (int i = 0; i < d; ++i) {
+        bc[lane] = Wp[(size_t)i * BD_CH + lane]; bc[BD_CH + lane] = Bp[(size_t)i * BD_CH + lane];
+        __syncwarp();
+        double dot = 0.0;
+#pragma unroll
+        for (int m = 0; m < BD_CH; ++m) dot = fma(bc[m], sig[m], dot);
+        const double y = (W[(size_t)i * BD_CH + lane] - dot) * rsqrt(dp[i]);
+#pragma unroll
+        for (int m = 0; m < BD_CH; ++m) sig[m] = fma(bc[BD_CH + m], y, sig[m]);
+        W[(size_t)i * BD_CH + lane] = y;
+        __syncwarp();
+      }
+    }
+    // ---- row sweep: chol(I + W S W'), state M (32 x 32) in registers, lane <-> row of M
+    {
+      double M[BD_CH];
+#pragma unroll
+      for (int m = 0; m < BD_CH; ++m) M[m] = (m == lane) ? Sj : 0.0;
+      int bad = 0;
+      double slog = 0.0;
+      for (int i = 0; i < d; ++i) {
+        const double w = W[(size_t)i * BD_CH + lane];
+        bc[lane] = w;
+        __syncwarp();
+        double t = 0.0;
+#pragma unroll
+        for (int m = 0; m < BD_CH; ++m) t = fma(M[m], bc[m], t);
+        const double dlt = 1.0 + warp_sum(w * t);
+        if (!(dlt > 0.0) || !isfinite(dlt)) { bad = 1; break; }     // uniform: dlt is the same on every lane
+        const double rs = rsqrt(dlt);
+        B[(size_t)i * BD_CH + lane] = t * rs;
+        bc[BD_CH + lane] = t;
+        __syncwarp();
+        const double tr = t * (rs * rs);
+#pragma unroll
+        for (int m = 0; m < BD_CH; ++m) M[m] = fma(-tr, bc[BD_CH + m], M[m]);
+        if (lane == 0) dl[i] = dlt;
+        slog += log(dlt);
+        __syncwarp();
+      }
+      if (bad) { *ok = 0; return lt; }
+      sumlog += 0.5 * slog;
+    }
+    __syncwarp();
+  }
+  // ---- firstterm = G^-1 grad = P Lm^-T Lm^-1 P grad
+  for (int i = lane; i < d; i += 32) xs[d - 1 - i] = g[i];
+  __syncwarp();
+  bd_solve(Q, slot, nch, sa, xs);
+  bd_solve_t(Q, slot, nch, sa, xs);
+  double* f = Q.vec(BDV_F0 + slot);
+  double bad = 0.0;
+  for (int i = lane; i < d; i += 32) { const double fi = xs[d - 1 - i]; f[i] = fi; if (!isfinite(fi)) bad = 1.0; }
+  if (warp_sum(bad) != 0.0 || !isfinite(sumlog)) { *ok = 0; return lt; }
+  if (lane == 0) { Q.s[BDS_A0 + slot] = a; Q.s[BDS_BETA0 + slot] = beta; Q.s[BDS_SL0 + slot] = sumlog; Q.s[BDS_NCH0 + slot] = (double)nch; Q.s[BDS_R0 + slot] = (double)r; }
+  __syncwarp();
+  return lt;
+}
+
+// running means, chain output, burn-in tuning (iterate/GAMC.jl:193-292): warp version of step_tail
+__device__ inline void bd_tail(const BdChain& Q, int accepted) {
+  const BdCfg& C = *Q.C;
+  const int d = Q.d, lane = Q.lane;
+  double* s = Q.s;
+  const long long t = (long long)s[BDS_COUNT];
+  const double* th = Q.vec(BDV_THETA);
+  double* m1 = Q.vec(BDV_M1); double* m2 = Q.vec(BDV_M2);
+  for (int i = lane; i < d; i += 32) { const double lm = m1[i]; m2[i] = lm; m1[i] = ((double)(t - 1) * lm + th[i]) / (double)t; }
+  if (t > C.burnin) {
+    const long long pos = (long long)s[BDS_SAVED];
+    if (pos < C.chain_cap) {
+      double* out = C.chain_value + ((size_t)Q.chain * C.chain_cap + pos) * d;
+      for (int i = lane; i < d; i += 32) out[i] = th[i];
+      if (lane == 0) C.chain_accept[(size_t)Q.chain * C.chain_cap + pos] = (unsigned char)accepted;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    if (t > C.burnin && s[BDS_SAVED] < (double)C.chain_cap) s[BDS_SAVED] += 1.0;
+    if (C.tuning) {
+      if ((long long)s[BDS_TTOT] <= C.burnin && ((long long)s[BDS_TPROP] % C.period) == 0) {
+        if (C.count_total) s[BDS_TRATE] = s[BDS_TACC] / s[BDS_TPROP];
+        if (C.is_accrate) { s[BDS_STEP] *= 2.0 / (1.0 + exp(-C.score_k * (s[BDS_TRATE] - C.targetrate))); s[BDS_SQSTEP] = sqrt(s[BDS_STEP]); }
+        if (C.verbose_sm) { s[BDS_SMTOT] += s[BDS_SMPROP]; s[BDS_SMPROP] = 0; s[BDS_SMACC] = 0; }
+        if (C.verbose_am) { s[BDS_AMTOT] += s[BDS_AMPROP]; s[BDS_AMPROP] = 0; s[BDS_AMACC] = 0; }
+        s[BDS_TTOT] += s[BDS_TPROP]; s[BDS_TPROP] = 0;
+        if (C.count_total) { s[BDS_TACC] = 0; s[BDS_TRATE] = nan(""); }
+      }
+    }
+    s[BDS_PAST] = s[BDS_PRESENT];                                                   // :197
+  }
+  __syncwarp();
+}
+
+// =====================================================================================================
+// kernels.  Warp-per-chain kernels: blockDim = 32 * BD_WPB, dynamic shared memory = BD_WPB * (2 d + 64) doubles.
+// =====================================================================================================
+__host__ __device__ inline size_t bd_warp_smem_bytes(int d) { return sizeof(double) * (size_t)BD_WPB * (2 * (size_t)d + 2 * BD_CH); }
+
+struct BdWarp { BdChain Q; double* vm; double* xs; double* bc; bool active; };
+__device__ inline BdWarp bd_warp_setup(const BdCfg& C, double* smem) {
+  BdWarp w;
+  const int warp = threadIdx.x >> 5;
+  w.Q.C = &C; w.Q.lane = threadIdx.x & 31; w.Q.d = C.d;
+  w.Q.chain = blockIdx.x * BD_WPB + warp;
+  w.active = w.Q.chain < C.nchains;
+  w.Q.s = C.scal + (size_t)(w.active ? w.Q.chain : 0) * BDS_N;
+  double* base = smem + (size_t)warp * (2 * (size_t)C.d + 2 * BD_CH);
+  w.vm = base; w.xs = base + C.d; w.bc = base + 2 * (size_t)C.d;
+  return w;
+}
+
+// initialize! + sampler_state (src/samplers/GAMC.jl:157-228) for every chain; theta0 [chain][d]
+__global__ void __launch_bounds__(32 * BD_WPB) k_bd_init(BdCfg C, const double* __restrict__ theta0) {
+  extern __shared__ __align__(16) double bd_smem[];
+  BdWarp w = bd_warp_setup(C, bd_smem);
+  if (!w.active) return;
+  const BdChain& Q = w.Q;
+  const int d = C.d, lane = Q.lane;
+  double* s = Q.s;
+  for (int i = lane; i < BDS_N; i += 32) s[i] = 0.0;
+  double* th = Q.vec(BDV_THETA); double* m1 = Q.vec(BDV_M1);
+  for (int i = lane; i < d; i += 32) { const double v = theta0[(size_t)Q.chain * d + i]; th[i] = v; m1[i] = v; Q.vec(BDV_M2)[i] = 0.0; }
+  __syncwarp();
+  int ok;
+  const double lt = bd_eval2(Q, BDV_THETA, 0, w.vm, w.xs, w.bc, &ok);
+  if (lane == 0) {
+    s[BDS_LT] = lt; s[BDS_CUR] = 0.0; s[BDS_STEP] = C.driftstep; s[BDS_SQSTEP] = sqrt(C.driftstep);
+    s[BDS_TTOT] = C.period; s[BDS_SMTOT] = C.period; s[BDS_AMTOT] = C.period; s[BDS_TRATE] = nan("");
+    s[BDS_PRESENT] = 1.0; s[BDS_PAST] = 0.0;
+    if (ok != 1) s[BDS_ERR] = ok < 0 ? 6.0 : 2.0;           // more factors needed than allocated / GAMC_NONFINITE_INIT (or not PD) at the initial point
+  }
+}
+
+// head of iterate! (:2-10): counters, the iteration's uniforms, the schedule coin.  One thread per chain.
+__global__ void __launch_bounds__(128) k_bd_begin(BdCfg C, long long tape_pos) {
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= C.nchains) return;
+  double* s = C.scal + (size_t)chain * BDS_N;
+  if (s[BDS_ERR] != 0.0) return;
+  const long long t = (long long)s[BDS_COUNT] + 1;
+  double us, um, ua;
+  bd_uniforms(C, chain, t, tape_pos, us, um, ua);
+  bool present = s[BDS_PRESENT] != 0.0;
+  if (t > C.t0) present = bd_schedule(C, t, us);
+  s[BDS_COUNT] = (double)t;
+  if (C.tuning) s[BDS_TPROP] += 1.0;
+  s[BDS_PRESENT] = present ? 1.0 : 0.0;
+  s[BDS_US] = us; s[BDS_UM] = um; s[BDS_UA] = ua;
+  if (present) { s[BDS_UPD] += 1.0; if (C.verbose_sm) s[BDS_SMPROP] += 1.0; }
+  else if (C.verbose_am) s[BDS_AMPROP] += 1.0;
+}
+
+// SMMALA branch, first half (:19-35): re-evaluation at theta if the previous step was AM, then the proposal
+__global__ void __launch_bounds__(32 * BD_WPB) k_bd_smmala_pre(BdCfg C, long long tape_pos) {
+  extern __shared__ __align__(16) double bd_smem[];
+  BdWarp w = bd_warp_setup(C, bd_smem);
+  if (!w.active) return;
+  const BdChain& Q = w.Q;
+  double* s = Q.s;
+  if (s[BDS_ERR] != 0.0 || s[BDS_PRESENT] == 0.0) return;
+  const int d = C.d, lane = Q.lane;
+  const int cur = (int)s[BDS_CUR];
+  if (s[BDS_PAST] == 0.0) {                                                         // :19-31
+    int ok;
+    const double lt = bd_eval2(Q, BDV_THETA, cur, w.vm, w.xs, w.bc, &ok);
+    if (ok != 1) { if (lane == 0) s[BDS_ERR] = ok < 0 ? 6.0 : 3.0; return; }        // capacity / PosDefException analogue
+    if (lane == 0) s[BDS_LT] = lt;
+    __syncwarp();
+  }
+  const double eps = s[BDS_STEP], sq = s[BDS_SQSTEP];
+  const long long t = (long long)s[BDS_COUNT];
+  // theta* = mu + sqrt(eps) chol(inv(G)) z,  chol(inv(G)) z = P Lm^-T P z                                   (:33-35)
+  for (int i = lane; i < d; i += 32) w.xs[d - 1 - i] = bd_normal(C, Q.chain, t, tape_pos, i);
+  __syncwarp();
+  bd_solve_t(Q, cur, (int)s[BDS_NCH0 + cur], sqrt(s[BDS_A0 + cur]), w.xs);
+  const double* th = Q.vec(BDV_THETA); const double* f = Q.vec(BDV_F0 + cur);
+  double* mu = Q.vec(BDV_MU); double* prop = Q.vec(BDV_PROP);
+  for (int i = lane; i < d; i += 32) { const double m = th[i] + 0.5 * eps * f[i]; mu[i] = m; prop[i] = m + sq * w.xs[d - 1 - i]; }
+}
+
+// SMMALA branch, second half (:37-127): evaluation at the proposal, ratio, accept/reject, tail
+__global__ void __launch_bounds__(32 * BD_WPB) k_bd_smmala_post(BdCfg C) {
+  extern __shared__ __align__(16) double bd_smem[];
+  BdWarp w = bd_warp_setup(C, bd_smem);
+  if (!w.active) return;
+  const BdChain& Q = w.Q;
+  double* s = Q.s;
+  if (s[BDS_ERR] != 0.0 || s[BDS_PRESENT] == 0.0) return;
+  const int d = C.d, lane = Q.lane;
+  const int cur = (int)s[BDS_CUR], prp = 1 - cur;
+  const double eps = s[BDS_STEP];
+  int ok;
+  const double lt_p = bd_eval2(Q, BDV_PROP, prp, w.vm, w.xs, w.bc, &ok);             // :37-43,56
+  if (ok < 0) { if (lane == 0) s[BDS_ERR] = 6.0; return; }                          // more product factors needed than allocated
+  double ratio = -INFINITY;
+  double* th = Q.vec(BDV_THETA); const double* prop = Q.vec(BDV_PROP); const double* mu = Q.vec(BDV_MU);
+  if (ok == 1) {
+    // q1 = d'G d = |Lm' P d|^2, d = theta* - mu                                                              (:47-54)
+    for (int i = lane; i < d; i += 32) w.xs[d - 1 - i] = prop[i] - mu[i];
+    __syncwarp();
+    bd_mult_t(Q, cur, (int)s[BDS_NCH0 + cur], sqrt(s[BDS_A0 + cur]), w.xs);
+    double q1 = 0.0;
+    for (int i = lane; i < d; i += 32) q1 = fma(w.xs[i], w.xs[i], q1);
+    q1 = warp_sum(q1);
+    __syncwarp();
+    // q2 = (theta - mu*)'G*(theta - mu*), mu* = theta* + eps/2 G*^-1 grad*                                   (:58-67)
+    const double* fp = Q.vec(BDV_F0 + prp);
+    for (int i = lane; i < d; i += 32) w.xs[d - 1 - i] = th[i] - (prop[i] + 0.5 * eps * fp[i]);
+    __syncwarp();
+    bd_mult_t(Q, prp, (int)s[BDS_NCH0 + prp], sqrt(s[BDS_A0 + prp]), w.xs);
+    double q2 = 0.0;
+    for (int i = lane; i < d; i += 32) q2 = fma(w.xs[i], w.xs[i], q2);
+    q2 = warp_sum(q2);
+    const double plog = d * log(eps);
+    const double ld_old = plog - 2.0 * s[BDS_SL0 + cur], ld_new = plog - 2.0 * s[BDS_SL0 + prp];   // logdet(eps inv(G))
+    ratio = lt_p - s[BDS_LT];
+    ratio += 0.5 * (ld_old + q1 / eps);
+    ratio -= 0.5 * (ld_new + q2 / eps);
+  }
+  const int accept = (ratio > 0.0) || (ratio > log(s[BDS_UA]));                     // :69
+  __syncwarp();
+  if (accept) for (int i = lane; i < d; i += 32) th[i] = prop[i];
+  __syncwarp();
+  if (lane == 0) {
+    s[BDS_RATIO] = ratio;
+    if (accept) { s[BDS_LT] = lt_p; s[BDS_CUR] = (double)prp; if (C.count_total) s[BDS_TACC] += 1.0; if (C.verbose_sm) s[BDS_SMACC] += 1.0; }
+  }
+  __syncwarp();
+  bd_tail(Q, accept);
+}
+
+// AM branch, second half (:148-191 + tail): log-target at the proposal, accept/reject.  The two GMM log-densities cancel exactly.
+__global__ void __launch_bounds__(32 * BD_WPB) k_bd_am_post(BdCfg C) {
+  extern __shared__ __align__(16) double bd_smem[];
+  BdWarp w = bd_warp_setup(C, bd_smem);
+  if (!w.active) return;
+  const BdChain& Q = w.Q;
+  double* s = Q.s;
+  if (s[BDS_ERR] != 0.0 || s[BDS_PRESENT] != 0.0) return;
+  const int d = C.d, lane = Q.lane;
+  double* th = Q.vec(BDV_THETA); const double* prop = Q.vec(BDV_PROP);
+  const double q = bd_tmatvec(C, prop, w.xs, lane);
+  const double lt_p = C.logconst - 0.5 * (C.nu + d) * log1p(q / C.nu);
+  const double ratio = isfinite(lt_p) ? (lt_p - s[BDS_LT]) : -INFINITY;             // :150-156
+  const int accept = (ratio > 0.0) || (ratio > log(s[BDS_UA]));                     // :158
+  __syncwarp();
+  if (accept) for (int i = lane; i < d; i += 32) th[i] = prop[i];
+  __syncwarp();
+  if (lane == 0) {
+    s[BDS_RATIO] = ratio;
+    if (accept) { s[BDS_LT] = lt_p; if (C.count_total) s[BDS_TACC] += 1.0; if (C.verbose_am) s[BDS_AMACC] += 1.0; }
+  }
+  __syncwarp();
+  bd_tail(Q, accept);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SMMALA -> AM hand-over (:26,92,133): sstate.oldinvtensor = inv(G) seeds the AM covariance; its lower Cholesky factor
+// chol(inv(G)) = U^-T is the index reversal of Lm^-1.  One CTA per chain, thread c = column c of X = Lm^-1 (forward solves on the
+// unit vectors, all columns in lockstep over the rows so that every store is coalesced), one pass per product factor.
+// X(j, c) lands at L[(d-1-c) + (d-1-j) d].
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BD_MAXD) k_bd_handover(BdCfg C) {
+  __shared__ double rows[16][2 * BD_CH + 2];
+  const int chain = blockIdx.x, c = threadIdx.x, d = C.d;
+  double* s = C.scal + (size_t)chain * BDS_N;
+  if (s[BDS_ERR] != 0.0 || s[BDS_PRESENT] != 0.0 || s[BDS_PAST] == 0.0) return;
+  const int cur = (int)s[BDS_CUR];
+  const int nch = (int)s[BDS_NCH0 + cur];
+  const double rsa = 1.0 / sqrt(s[BDS_A0 + cur]);
+  double* L = C.L + (size_t)chain * d * d;
+  double* rdiag = C.rdiagL + (size_t)chain * d;
+  const size_t sc0 = ((size_t)chain * 2 + cur) * C.ncmax;
+  for (int k = 0; k < nch; ++k) {
+    const double* W = C.W + (sc0 + k) * (size_t)d * BD_CH;
+    const double* B = C.B + (sc0 + k) * (size_t)d * BD_CH;
+    const double* dl = C.delta + (sc0 + k) * (size_t)d;
+    double sig[BD_CH];
+#pragma unroll
+    for (int m = 0; m < BD_CH; ++m) sig[m] = 0.0;
+    double u = 0.0;                                    // bidiagonal recurrence of pass 0
+    for (int i0 = 0; i0 < d; i0 += 16) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < 16 * (2 * BD_CH + 1); e += blockDim.x) {
+        const int rr = e / (2 * BD_CH + 1), m = e % (2 * BD_CH + 1), i = i0 + rr;
+        if (i < d) rows[rr][m] = m < BD_CH ? W[(size_t)i * BD_CH + m] : (m < 2 * BD_CH ? B[(size_t)i * BD_CH + (m - BD_CH)] : rsqrt(dl[i]));
+      }
+      __syncthreads();
+      if (c >= d) continue;
+      for (int rr = 0; rr < 16 && i0 + rr < d; ++rr) {
+        const int i = i0 + rr;
+        if (i < c) continue;                           // X is lower triangular: rows above the diagonal are zero and stay zero
+        const size_t addr = (size_t)(d - 1 - c) + (size_t)(d - 1 - i) * d;
+        double x;
+        if (k == 0) { u = ((i == c ? rsa : 0.0) - C.le[i > 0 ? i - 1 : 0] * (i > c ? u : 0.0)) * C.rld[i]; x = u; }
+        else x = L[addr];
+        double dot = 0.0;
+#pragma unroll
+        for (int m = 0; m < BD_CH; ++m) dot = fma(rows[rr][m], sig[m], dot);
+        const double y = (x - dot) * rows[rr][2 * BD_CH];
+#pragma unroll
+        for (int m = 0; m < BD_CH; ++m) sig[m] = fma(rows[rr][BD_CH + m], y, sig[m]);
+        L[addr] = y;
+        if (k == nch - 1 && i == c) rdiag[d - 1 - c] = 1.0 / y;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AM branch, first half (:128-146): rank-one update of the dense factor + proposal.  The same closed form as the single-chain
+// path (sampler.cuh k_am_pre_r1: C_k = ((k-1)/k) C_{k-1} + u u', chol(I + w w') in closed form, one ascending sweep over
+// 32-column blocks), one CTA per chain, thread = row, the factor streamed from / to HBM in place.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BD_MAXD) k_bd_am_pre(BdCfg C, long long tape_pos) {
+  __shared__ double zs[BD_MAXD];
+  __shared__ double bw[4 * 32];
+  __shared__ double Ls[32 * 33];
+  __shared__ double Ts[32 * 33];
+  __shared__ double accd[32];
+  const int chain = blockIdx.x, d = C.d;
+  double* s = C.scal + (size_t)chain * BDS_N;
+  if (s[BDS_ERR] != 0.0 || s[BDS_PRESENT] != 0.0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+  double* L = C.L + (size_t)chain * d * d;
+  double* rd = C.rdiagL + (size_t)chain * d;
+  const double* theta = C.vecs + ((size_t)chain * BDV_N + BDV_THETA) * d;
+  const double* m2 = C.vecs + ((size_t)chain * BDV_N + BDV_M2) * d;
+  double* prop = C.vecs + ((size_t)chain * BDV_N + BDV_PROP) * d;
+  const long long t = (long long)s[BDS_COUNT];
+  const double k = (double)(t - 2);
+  if (!(k > 1.0)) { __syncthreads(); if (tid == 0) s[BDS_ERR] = 3.0; return; }        // C_1 has rank one: the reference's chol throws
+  const double alpha = sqrt((k - 1.0) / k), beta = 1.0 / sqrt(k + 1.0), ralpha = 1.0 / alpha;
+  const int i = tid;
+  double th = 0.0, ui = 0.0, P = 0.0, acc = 0.0, rdv = 0.0;
+  if (i < d) {
+    th = theta[i];
+    ui = (th - m2[i]) * beta;
+    rdv = rd[i] * ralpha;
+    zs[i] = bd_normal(C, chain, t, tape_pos, i);
+  }
+  double sigma = 1.0;
+  const int nblk = (d + 31) >> 5;
+  for (int b = 0; b < nblk; ++b) {
+    const int j0 = b << 5, nb = min(32, d - j0);
+    __syncthreads();
+    if (warp == b) {
+      double lrow[32];
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        lrow[jj] = (jj <= lane && jj < nb && i < d) ? alpha * L[(size_t)(j0 + lane) + (size_t)(j0 + jj) * d] : 0.0;
+        Ls[jj * 33 + lane] = lrow[jj];
+      }
+      double res = ui - P, wmine = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        if (jj < nb) {
+          const double wj = __shfl_sync(0xffffffffu, res * rdv, jj);
+          if (lane == jj) wmine = wj;
+          res = fma(-lrow[jj], wj, res);
+          Ts[jj * 33 + lane] = res;
+        }
+      }
+      P = ui - res;
+      double sc = wmine * wmine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const double n = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += n; }
+      const double incl = sigma + sc, excl = incl - wmine * wmine;
+      const double rs = rsqrt(excl * incl);
+      bw[lane] = wmine; bw[32 + lane] = incl * rs; bw[64 + lane] = wmine * rs;
+      const double snew = __shfl_sync(0xffffffffu, incl, nb - 1);
+      if (lane == 0) bw[96] = snew;
+    }
+    __syncthreads();
+    sigma = bw[96];
+    if (i >= j0 + 32 && i < d) {
+      double lv[32];
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) lv[jj] = (jj < nb) ? L[(size_t)i + (size_t)(j0 + jj) * d] : 0.0;
+      double res = ui - P, a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        if (jj < nb) {
+          const double l = alpha * lv[jj];
+          res = fma(-l, bw[jj], res);
+          const double ln = fma(l, bw[32 + jj], bw[64 + jj] * res);
+          L[(size_t)i + (size_t)(j0 + jj) * d] = ln;
+          if (jj & 1) a1 = fma(ln, zs[j0 + jj], a1); else a0 = fma(ln, zs[j0 + jj], a0);
+        }
+      }
+      P = ui - res;
+      acc += a0 + a1;
+    }
+    for (int r = warp; r < nb; r += nwarps) {
+      const int gi = j0 + r;
+      double contrib = 0.0;
+      if (lane <= r && lane < nb) {
+        const double ln = fma(Ls[lane * 33 + r], bw[32 + lane], bw[64 + lane] * Ts[lane * 33 + r]);
+        L[(size_t)gi + (size_t)(j0 + lane) * d] = ln;
+        contrib = ln * zs[j0 + lane];
+        if (lane == r) rd[gi] = 1.0 / ln;
+      }
+      contrib = warp_sum(contrib);
+      if (lane == 0) accd[r] = contrib;
+    }
+    __syncthreads();
+    if (warp == b && i < d) acc += accd[lane];
+  }
+  const int fin = isfinite(sigma) ? 0 : 1;
+  if (__syncthreads_or(fin)) { if (tid == 0) s[BDS_ERR] = 3.0; return; }
+  if (i < d) {
+    if (s[BDS_UM] <= 1.0 - C.c) prop[i] = th + s[BDS_SQSTEP] * acc;                 // core component  N(theta, eps C)   (:146)
+    else prop[i] = th + C.sqrtminorscale * zs[i];                                   // stabilising component
+  }
+}
+
+}  // namespace gamc

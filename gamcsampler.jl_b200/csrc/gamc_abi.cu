@@ -378,7 +378,7 @@ gamc_status launch_metric_fused(gamc_ctx* h, const double* theta, const int* ski
 // level: 0 = ll, 1 = ll + grad, 2 = ll + grad + metric
 gamc_status launch_reduce(gamc_ctx* h, int level, double* E = nullptr, const int* skip = nullptr) {
   ProfScope ps(h, GAMC_K_REDUCE);
-  const int nblk = (level >= 2 ? h->ntasks * 4 : 0) + 1;
+  const int nblk = (level >= 2 ? h->ntasks * 4 : 0) + (level >= 1 ? (h->p + 31) / 32 : 0) + 1;   // tensor tiles | gradient column blocks | scalar
   const int nparts = (level >= 2 && h->metric_fused) ? h->metric_grid : (h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid);
   k_reduce<<<nblk, 256, 0, h->stream>>>(E ? E : h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, nparts, level >= 1,
                                         level >= 2 ? h->ws : nullptr, h->d_coords, h->ntasks, h->d_task_nsplit, h->layout.max_nsplit, skip);

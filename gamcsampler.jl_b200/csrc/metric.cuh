@@ -398,39 +398,59 @@ k_reduce(double* __restrict__ E, int p, int goff,
     const double* src = ws + (size_t)task * max_nsplit * (MT_BLK * MT_BLK) + e;
     const int nsplit = task_nsplit[task];
     int k = 0;
-    for (; k + 4 <= nsplit; k += 4) {           // four independent loads in flight, added in split order (deterministic)
-      const double v0 = src[(size_t)k * (MT_BLK * MT_BLK)], v1 = src[(size_t)(k + 1) * (MT_BLK * MT_BLK)];
-      const double v2 = src[(size_t)(k + 2) * (MT_BLK * MT_BLK)], v3 = src[(size_t)(k + 3) * (MT_BLK * MT_BLK)];
-      s += v0; s += v1; s += v2; s += v3;
+    for (; k + 16 <= nsplit; k += 16) {         // sixteen independent loads in flight (the kernel is bound by L2 latency), added in split order
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = src[(size_t)(k + u) * (MT_BLK * MT_BLK)];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) s += v[u];
     }
-    for (; k < nsplit; ++k) s += src[(size_t)k * (MT_BLK * MT_BLK)];
+    {
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = (k + u < nsplit) ? src[(size_t)(k + u) * (MT_BLK * MT_BLK)] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) if (k + u < nsplit) s += v[u];
+    }
     double* G = E + goff;
     G[gi + (size_t)gj * p] = s;
     G[gj + (size_t)gi * p] = s;
     return;
   }
-  // last block: scalar + gradient
+  // gradient blocks (32 columns each): thread (column, group) adds every RG_GROUPS-th per-CTA partial with all its loads in flight,
+  // the groups are then combined in a fixed order -- deterministic, and one L2 round trip deep instead of nparts / 8
+  constexpr int RG_GROUPS = 8;
+  __shared__ double gsum[RG_GROUPS][33];
+  const int gb = (int)blockIdx.x - nblk_tensor;       // 0 .. ceil(p / 32): the last one only sums the scalar
+  const int ngb = (p + 31) / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp == 0) {
-    double s = 0.0;
-    for (int k = lane; k < nparts; k += 32) s += part_ll[k];
-    s = warp_sum(s);
-    if (lane == 0) E[0] = s;
-  }
-  if (want_grad) {
-    for (int j = threadIdx.x; j < p; j += blockDim.x) {
+  if (gb == ngb || !want_grad) {
+    if (warp == 0 && (gb == ngb || gb == 0)) {
       double s = 0.0;
-      int k = 0;
-      for (; k + 8 <= nparts; k += 8) {         // eight independent loads in flight, added in CTA order (deterministic)
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = part_g[(size_t)(k + u) * part_g_stride + j];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
-      }
-      for (; k < nparts; ++k) s += part_g[(size_t)k * part_g_stride + j];
-      E[1 + j] = s;
+      for (int k = lane; k < nparts; k += 32) s += part_ll[k];
+      s = warp_sum(s);
+      if (lane == 0) E[0] = s;
     }
+    return;
+  }
+  const int j = gb * 32 + lane;
+  double s = 0.0;
+  if (j < p) {
+    for (int k0 = warp; k0 < nparts; k0 += RG_GROUPS * 24) {
+      double v[24];
+#pragma unroll
+      for (int u = 0; u < 24; ++u) { const int k = k0 + u * RG_GROUPS; v[u] = (k < nparts) ? part_g[(size_t)k * part_g_stride + j] : 0.0; }
+#pragma unroll
+      for (int u = 0; u < 24; ++u) s += v[u];
+    }
+  }
+  gsum[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && j < p) {
+    double t = 0.0;
+#pragma unroll
+    for (int g = 0; g < RG_GROUPS; ++g) t += gsum[g][lane];
+    E[1 + j] = t;
   }
 }
 

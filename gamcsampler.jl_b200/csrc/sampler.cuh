@@ -19,6 +19,19 @@ struct LandPeer { double* const* peerR; PeerMail* const* peers; int nranks; int 
 // Wall-clock nanoseconds (independent of the SM clock): the peer waits are bounded in real time (gamc_comm_set_timeout).
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ double ld_peer(const double* q) { return *reinterpret_cast<const volatile double*>(q); }
+// Element `off` of every rank's reduced buffer, added in rank order (identical bits on every rank).  The loads of up to eight
+// ranks are issued together -- one NVLink round trip per batch instead of one per rank -- and only the additions are ordered.
+__device__ __forceinline__ double peer_sum(double* const* peerR, int nr, size_t off) {
+  double s = 0.0;
+  for (int r0 = 0; r0 < nr; r0 += 8) {
+    double t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = (r0 + u < nr) ? ld_peer(peerR[r0 + u] + off) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (r0 + u < nr) s += t[u];
+  }
+  return s;
+}
 
 // After k_reduce: tell every peer that this rank's reduced evaluation `seq` is in place (mailbox slots 2n .. 4n).
 __global__ void k_peer_flag(PeerMail* const* peers, int nranks, int rank, unsigned long long seq) {
@@ -145,7 +158,7 @@ __global__ void __launch_bounds__(LAND_THREADS) k_land(Bufs B, TuneCfg T, int mo
   double nf = 0.0, q1 = 0.0, q2 = 0.0;
   for (int i = threadIdx.x; i < p; i += LAND_THREADS) {
     double v;
-    if (nr > 1) { v = 0.0; for (int r = 0; r < nr; ++r) v += ld_peer(lp.peerR[r] + poff + i); }
+    if (nr > 1) v = peer_sum(lp.peerR, nr, poff + i);
     else v = G[i];
     if (i == j) v += ilam;
     Gd[i] = v;
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(LAND_THREADS) k_land(Bufs B, TuneCfg T, int mo
     double gnf = 0.0;
     for (int i = threadIdx.x; i < p; i += LAND_THREADS) {
       double gl;
-      if (nr > 1) { gl = 0.0; for (int r = 0; r < nr; ++r) gl += ld_peer(lp.peerR[r] + lp.roff + 1 + i); }
+      if (nr > 1) gl = peer_sum(lp.peerR, nr, lp.roff + 1 + i);
       else gl = B.R[1 + i];
       const double g = gl - th[i] * ilam;
       B.gs[(size_t)slot * p + i] = g;

@@ -327,6 +327,45 @@ class Engine:
         self._ck(self.lib.gamc_batched_get_state(self.h, int(chain), C.byref(st), L.dptr(th)))
         return st, th
 
+    # -- batched chains, large dimension (structured t target)
+    def bigd_target_mvt(self, tdiag, toff, nu):
+        td, te = _f64(tdiag, "C").ravel(), _f64(toff, "C").ravel()
+        n = td.shape[0]
+        assert te.shape[0] == max(n - 1, 0)
+        self._ck(self.lib.gamc_bigd_target_mvt(self.h, n, float(nu), L.dptr(td), L.dptr(te) if n > 1 else None))
+        self.bp = n
+
+    def bigd_set_chain_offset(self, offset):
+        self._ck(self.lib.gamc_bigd_set_chain_offset(self.h, int(offset)))
+
+    def bigd_init(self, cfg: L.Config, theta0, transform=1, softabs_alpha=1000.0, max_factors=0):
+        th = _f64(theta0, "C")
+        assert th.ndim == 2 and th.shape[1] == self.bp
+        self.bn = th.shape[0]
+        self.bcap = max(0, int(cfg.nsteps) - int(cfg.burnin))
+        self._ck(self.lib.gamc_bigd_init(self.h, C.byref(cfg), self.bn, L.dptr(th), int(transform), float(softabs_alpha), int(max_factors)))
+
+    def bigd_run(self, n, seed=0, tape=None):
+        if tape is None:
+            self._ck(self.lib.gamc_bigd_run(self.h, int(n), int(seed), None, None, None, None))
+        else:
+            us, um, ua, z = (_f64(tape[k], "C") for k in ("u_sched", "u_mix", "u_acc", "z"))
+            assert us.shape == (self.bn, n) and z.shape == (self.bn, n, self.bp)
+            self._ck(self.lib.gamc_bigd_run(self.h, int(n), int(seed), L.dptr(us), L.dptr(um), L.dptr(z), L.dptr(ua)))
+
+    def bigd_chain_get(self, first=0, nchains=None):
+        nchains = self.bn - first if nchains is None else nchains
+        value = np.empty((nchains, self.bcap, self.bp), dtype=np.float64)
+        accept = np.empty((nchains, self.bcap), dtype=np.uint8)
+        self._ck(self.lib.gamc_bigd_chain_get(self.h, int(first), int(nchains), L.dptr(value), L.u8ptr(accept)))
+        return value, accept.astype(bool)
+
+    def bigd_state(self, chain):
+        st = L.StateScalars()
+        th = np.empty(self.bp)
+        self._ck(self.lib.gamc_bigd_get_state(self.h, int(chain), C.byref(st), L.dptr(th)))
+        return st, th
+
     # -- measurement
     def profile_enable(self, on=True):
         self._ck(self.lib.gamc_profile_enable(self.h, 1 if on else 0))

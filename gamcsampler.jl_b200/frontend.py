@@ -459,6 +459,16 @@ class MvTModel:
     nu: float = 30.0
     c: float = 0.9
 
+    def tridiagonal(self):
+        """Diagonal and off-diagonal of the inverse scale matrix T = inv(Sigma_t): for Sigma_ij = c^|i-j| it is tridiagonal,
+        T = nu / ((nu - 2)(1 - c^2)) tridiag(-c; 1, 1 + c^2, ..., 1 + c^2, 1; -c) -- what the large-dimension path works from."""
+        n, s = self.n, self.nu / ((self.nu - 2.0) * (1.0 - self.c * self.c))
+        td = np.full(n, s * (1.0 + self.c * self.c))
+        td[0] = td[-1] = s
+        if n == 1:
+            td[0] = self.nu / (self.nu - 2.0)
+        return td, np.full(max(n - 1, 0), -s * self.c)
+
     def constants(self):
         idx = np.arange(self.n)
         Sigma_t = (self.nu - 2.0) * (self.c ** np.abs(idx[:, None] - idx[None, :])) / self.nu
@@ -557,13 +567,30 @@ class BatchedRandomTape:
 
 class BatchedMCJob:
     """The reference's `while i <= nchains ... BasicMCJob(...); run(job)` loop (examples/t_distribution/src/GAMC/simulations.jl:56-79)
-    as ONE persistent kernel: every chain is an independent GAMC job with its own initial value v0s[c]."""
+    as ONE persistent kernel: every chain is an independent GAMC job with its own initial value v0s[c].
+    A t target of dimension n > 32 runs on the structured large-dimension path (gamc_bigd_*; n <= 1024)."""
 
     def __init__(self, model, sampler: GAMC, mcrange: BasicMCRange, v0s, tuner: Optional[GAMCTuner] = None, device=0,
-                 tape: Optional[BatchedRandomTape] = None, seed=0, engine: Optional[Engine] = None, chain_offset=0):
+                 tape: Optional[BatchedRandomTape] = None, seed=0, engine: Optional[Engine] = None, chain_offset=0, max_factors=0):
         self.model, self.sampler, self.range = model, sampler, mcrange
         self.tuner = tuner if tuner is not None else GAMCTuner()
         self.engine = engine if engine is not None else Engine(device)
+        self.bigd = isinstance(model, MvTModel) and model.n > 32
+        if self.bigd:
+            if not isinstance(sampler.update, Schedule):
+                raise NotImplementedError("the batched kernels decide the branch on the device: pass one of the nine schedules")
+            tr = sampler.transform
+            if tr is not None and not isinstance(tr, Softabs):
+                raise NotImplementedError("the large-dimension t target supports transform=None or softabs(alpha)")
+            td, te = model.tridiagonal()
+            self.engine.bigd_target_mvt(td, te, model.nu)
+            self.cfg = make_config(sampler, self.tuner, mcrange)
+            self.engine.bigd_set_chain_offset(chain_offset)
+            self.engine.bigd_init(self.cfg, np.asarray(v0s, dtype=np.float64), 1 if isinstance(tr, Softabs) else 0,
+                                  tr.alpha if isinstance(tr, Softabs) else 0.0, max_factors)
+            self.tape, self.seed = tape, seed
+            self._done = 0
+            return
         if isinstance(model, RVModel):
             self.engine.batched_target_rv(model.times, model.obs, model.sigma_obs, model.nplanets)
         elif isinstance(model, LogisticModel):
@@ -583,18 +610,18 @@ class BatchedMCJob:
 
     def run(self):
         n = self.range.nsteps - self._done
+        runner = self.engine.bigd_run if self.bigd else self.engine.batched_run
         if self.tape is not None:
             lo, hi = self._done, self._done + n
             t = self.tape
-            self.engine.batched_run(n, self.seed, {"u_sched": t.u_sched[:, lo:hi], "u_mix": t.u_mix[:, lo:hi], "u_acc": t.u_acc[:, lo:hi],
-                                                   "z": t.z[:, lo:hi]})
+            runner(n, self.seed, {"u_sched": t.u_sched[:, lo:hi], "u_mix": t.u_mix[:, lo:hi], "u_acc": t.u_acc[:, lo:hi], "z": t.z[:, lo:hi]})
         else:
-            self.engine.batched_run(n, self.seed)
+            runner(n, self.seed)
         self.engine.sync()
         self._done += n
         return self
 
     def output(self):
         """List of Chain objects (value p x nsamples, as `chain.value` of the reference)."""
-        value, accept = self.engine.batched_chain_get()
+        value, accept = self.engine.bigd_chain_get() if self.bigd else self.engine.batched_chain_get()
         return [Chain(np.ascontiguousarray(value[c].T), accept[c].reshape(1, -1)) for c in range(value.shape[0])]

@@ -306,6 +306,28 @@ gamc_status gamc_batched_set_chain_offset(gamc_handle h, int64_t chain_offset);
 gamc_status gamc_batched_chain_get(gamc_handle h, int32_t chain_first, int32_t nchains, double* value, uint8_t* accept);
 gamc_status gamc_batched_get_state(gamc_handle h, int32_t chain, gamc_state_scalars* out, double* theta);
 
+/* ---- batched chains, LARGE dimension: the t target at d up to 1024 (BASELINE config: d = 1024, 4096 chains per GPU) ----------
+ * The same experiment as gamc_batched_target_mvt (examples/t_distribution/src/GAMC/simulations.jl:17-39,56-79) for dimensions
+ * where the reference's dense route (ForwardDiff Hessian, `eig` inside softabs, `inv`, `chol`) is O(d^3) per chain and step.  The
+ * inverse scale matrix T = inv(Sigma_t) must be symmetric TRIDIAGONAL -- it is for the reference's Sigma_ij = c^|i-j| -- and is given
+ * by its diagonal tdiag[n] and off-diagonal toff[n-1]:
+ *   logpdf(MvTDist(nu, 0, Sigma_t), x) = lgamma((nu+n)/2) - lgamma(nu/2) - n/2 log(nu pi) + 1/2 logdet T - (nu+n)/2 log1p(x'Tx/nu).
+ * SMMALA steps use the structure (tensor = a (T - beta v v'); softabs changes only its few eigenvalues below 21/alpha, found by
+ * bisection on the LDL' inertia count; reverse Cholesky factor in product form): O(d) memory and O(d r^2) work per evaluation
+ * instead of O(d^3).  AM steps keep the dense d x d Cholesky factor of the proposal covariance per chain in HBM (8 MB at d = 1024)
+ * and update it in one streamed O(d^2) sweep.  One warp per chain (SMMALA) / one CTA per chain (AM).
+ * max_factors: product factors of 32 columns allocated per evaluation (0 = default 5: up to 159 eigenvalues below 21/alpha, enough
+ * for the reference's N(0, 2^2) initial values at d = 1024); a chain that needs more raises GAMC_UNSUPPORTED_SHAPE.
+ * theta0: [nchains][n] (row c = initial value of chain c).  Tape / chain layouts as for gamc_batched_run / gamc_batched_chain_get. */
+gamc_status gamc_bigd_target_mvt(gamc_handle h, int32_t n, double nu, const double* tdiag, const double* toff);
+gamc_status gamc_bigd_set_chain_offset(gamc_handle h, int64_t chain_offset);
+gamc_status gamc_bigd_init(gamc_handle h, const gamc_config* cfg, int32_t nchains, const double* theta0, int32_t transform, double softabs_alpha,
+                           int32_t max_factors);
+gamc_status gamc_bigd_run(gamc_handle h, int64_t n, uint64_t seed, const double* u_sched, const double* u_mix, const double* z, const double* u_acc);
+gamc_status gamc_bigd_chain_get(gamc_handle h, int32_t chain_first, int32_t nchains, double* value, uint8_t* accept);
+/* out->error_pivot reports how many eigenvalues softabs changed at the chain's current point (diagnostic). */
+gamc_status gamc_bigd_get_state(gamc_handle h, int32_t chain, gamc_state_scalars* out, double* theta);
+
 /* ---- measurement hooks ------------------------------------------------------------------------------
  * With profiling on, every kernel launched by gamc_run / gamc_eval_* is bracketed by CUDA events on the
  * handle's stream; gamc_profile_get returns launches and summed milliseconds per kernel family. */
