@@ -201,22 +201,35 @@ __device__ inline void bd_bidiag_mult_t(const BdCfg& C, double sa, double* xs, i
   __syncwarp();
 }
 
+// The generator rows of a factor stream from HBM (256 B per row and matrix, one row per lane-wide load), and every recurrence
+// below walks the d rows in order: to keep the walks off the memory latency, rows are fetched in blocks of BD_PF and the NEXT
+// block's loads are issued before the current block is consumed (register double buffering).
+constexpr int BD_PF = 8;
+struct BdRows { double w[BD_PF], b[BD_PF], rs[BD_PF]; };
+// rows i0 .. i0+BD_PF-1 (ascending, dir = +1) or i0 .. i0-BD_PF+1 (descending, dir = -1), clamped to [0, d)
+__device__ __forceinline__ void bd_fetch(BdRows& R, const double* __restrict__ W, const double* __restrict__ B, const double* __restrict__ dl,
+                                         int d, int i0, int dir, int lane) {
+#pragma unroll
+  for (int u = 0; u < BD_PF; ++u) {
+    const int i = min(max(i0 + dir * u, 0), d - 1);
+    R.w[u] = W[(size_t)i * BD_CH + lane]; R.b[u] = B[(size_t)i * BD_CH + lane]; R.rs[u] = dl[i];
+  }
+}
+
 // K y = u in place: y_i = (u_i - w_i'sigma)/sqrt(delta_i), sigma += b_i y_i   (lane <-> component of sigma)
 __device__ inline void bd_k_solve(const double* __restrict__ W, const double* __restrict__ B, const double* __restrict__ dl, int d, double* xs, int lane) {
   double sig = 0.0;
-  for (int i0 = 0; i0 < d; i0 += 4) {
-    double w[4], b[4], rs[4];
+  BdRows nxt;
+  bd_fetch(nxt, W, B, dl, d, 0, 1, lane);
+  for (int i0 = 0; i0 < d; i0 += BD_PF) {
+    const BdRows cur = nxt;
+    if (i0 + BD_PF < d) bd_fetch(nxt, W, B, dl, d, i0 + BD_PF, 1, lane);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = min(i0 + u, d - 1);
-      w[u] = W[(size_t)i * BD_CH + lane]; b[u] = B[(size_t)i * BD_CH + lane]; rs[u] = rsqrt(dl[i]);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < BD_PF; ++u) {
       if (i0 + u < d) {
-        const double dot = warp_sum(w[u] * sig);
-        const double y = (xs[i0 + u] - dot) * rs[u];
-        sig = fma(b[u], y, sig);
+        const double dot = warp_sum(cur.w[u] * sig);
+        const double y = (xs[i0 + u] - dot) * rsqrt(cur.rs[u]);
+        sig = fma(cur.b[u], y, sig);
         if (lane == 0) xs[i0 + u] = y;
       }
     }
@@ -226,19 +239,17 @@ __device__ inline void bd_k_solve(const double* __restrict__ W, const double* __
 // K' w = b in place (backward): w_j = (b_j - b_j'tau)/sqrt(delta_j), tau += w_j (generator row) w_j
 __device__ inline void bd_k_solve_t(const double* __restrict__ W, const double* __restrict__ B, const double* __restrict__ dl, int d, double* xs, int lane) {
   double tau = 0.0;
-  for (int j0 = d - 1; j0 >= 0; j0 -= 4) {
-    double w[4], b[4], rs[4];
+  BdRows nxt;
+  bd_fetch(nxt, W, B, dl, d, d - 1, -1, lane);
+  for (int j0 = d - 1; j0 >= 0; j0 -= BD_PF) {
+    const BdRows cur = nxt;
+    if (j0 - BD_PF >= 0) bd_fetch(nxt, W, B, dl, d, j0 - BD_PF, -1, lane);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = max(j0 - u, 0);
-      w[u] = W[(size_t)j * BD_CH + lane]; b[u] = B[(size_t)j * BD_CH + lane]; rs[u] = rsqrt(dl[j]);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < BD_PF; ++u) {
       if (j0 - u >= 0) {
-        const double dot = warp_sum(b[u] * tau);
-        const double y = (xs[j0 - u] - dot) * rs[u];
-        tau = fma(w[u], y, tau);
+        const double dot = warp_sum(cur.b[u] * tau);
+        const double y = (xs[j0 - u] - dot) * rsqrt(cur.rs[u]);
+        tau = fma(cur.w[u], y, tau);
         if (lane == 0) xs[j0 - u] = y;
       }
     }
@@ -248,13 +259,20 @@ __device__ inline void bd_k_solve_t(const double* __restrict__ W, const double* 
 // out = K' w in place (backward): out_j = sqrt(delta_j) w_j + b_j'tau, tau += w_j (generator row) w_j
 __device__ inline void bd_k_mult_t(const double* __restrict__ W, const double* __restrict__ B, const double* __restrict__ dl, int d, double* xs, int lane) {
   double tau = 0.0;
-  for (int j = d - 1; j >= 0; --j) {
-    const double w = W[(size_t)j * BD_CH + lane], b = B[(size_t)j * BD_CH + lane];
-    const double x = xs[j];
-    const double dot = warp_sum(b * tau);
-    tau = fma(w, x, tau);
-    __syncwarp();
-    if (lane == 0) xs[j] = fma(sqrt(dl[j]), x, dot);
+  BdRows nxt;
+  bd_fetch(nxt, W, B, dl, d, d - 1, -1, lane);
+  for (int j0 = d - 1; j0 >= 0; j0 -= BD_PF) {
+    const BdRows cur = nxt;
+    if (j0 - BD_PF >= 0) bd_fetch(nxt, W, B, dl, d, j0 - BD_PF, -1, lane);
+#pragma unroll
+    for (int u = 0; u < BD_PF; ++u) {
+      if (j0 - u >= 0) {
+        const double x = xs[j0 - u];
+        const double dot = warp_sum(cur.b[u] * tau);
+        tau = fma(cur.w[u], x, tau);
+        if (lane == 0) xs[j0 - u] = fma(sqrt(cur.rs[u]), x, dot);
+      }
+    }
   }
   __syncwarp();
 }
@@ -310,18 +328,35 @@ __device__ inline double bd_eval2(const BdChain& Q, int xv, int slot, double* vm
     const int col = k * BD_CH + lane;                      // this lane's column of V
     const bool is_root = col < r, is_v = col == r;
     double Sj = 0.0, scale = 1.0;
-    // ---- root col+1 of the secular equation by bisection on the count (every lane its own root, in lockstep)
+    // ---- roots of the secular equation: eigenvalue number col+1 of A = T' - beta v v' for the column of lane `lane`
     double mu = 0.0;
     const bool any_root = k * BD_CH < r;                   // the last factor may hold the column v only
     if (any_root) {
+      // (g+1)-section on the count: the nr roots of this factor share the warp, g = 32 / nr lanes each.  Every step evaluates the
+      // count at g interior points of the root's bracket at once (one lane each) and keeps the sub-interval in which the count
+      // reaches the root's index: log2(g+1) bits per sweep instead of one -- 12 sweeps instead of 60 when softabs changes a single
+      // eigenvalue (the regime a chain lives in once it has reached the typical set).
+      const int nr = min(BD_CH, r - k * BD_CH);
+      const int g = 32 / nr;
+      const int grp = lane / g, sub = lane - grp * g;
+      const bool act = grp < nr;
+      const int want = k * BD_CH + grp + 1;
+      const unsigned gmask = (g == 32 ? 0xffffffffu : ((1u << g) - 1u)) << (act ? grp * g : 0);
       double lo = lo0, hi = fmin(thr / a, C.gersh_hi);
-      const int want = col + 1;
-      for (int it = 0; it < BD_NBISECT; ++it) {
-        const double mid = 0.5 * (lo + hi);
-        const int cnt = bd_count(C, vm, beta, mid);        // lanes without a root run along (uniform control flow)
-        if (cnt >= want) hi = mid; else lo = mid;
+      const int nit = (int)ceil((double)BD_NBISECT / log2((double)(g + 1)));
+      for (int it = 0; it < nit; ++it) {
+        const double hstep = (hi - lo) / (double)(g + 1);
+        const double mid = fma((double)(sub + 1), hstep, lo);
+        const int cnt = bd_count(C, vm, beta, mid);        // idle lanes run along (uniform control flow)
+        const unsigned hit = __ballot_sync(0xffffffffu, act && cnt >= want);
+        const unsigned bits = act ? (hit & gmask) >> (grp * g) : 0u;
+        const int f = bits ? (__ffs(bits) - 1) : g;        // first interior point at which the count has reached `want`
+        const double nlo = fma((double)f, hstep, lo);
+        hi = (f < g) ? fma((double)(f + 1), hstep, lo) : hi;
+        lo = nlo;
       }
-      mu = 0.5 * (lo + hi);
+      const double mu_grp = 0.5 * (lo + hi);
+      mu = __shfl_sync(0xffffffffu, mu_grp, min(lane, nr - 1) * g);    // lane j <-> column j of this factor
     }
     // ---- eigenvector x = (T' - mu)^-1 v' (unnormalised) by the LDL' recurrence: forward sweep parks y and the multipliers in the
     //      chunk's own W / B storage, backward sweep overwrites W with x
@@ -346,15 +381,26 @@ __device__ inline double bd_eval2(const BdChain& Q, int xv, int slot, double* vm
       }
       __syncwarp();
       double xn = 0.0, amax = 0.0, ssq = 0.0;
-      for (int i = d - 1; i >= 0; --i) {
-        if (is_root) {
-          const double y = W[(size_t)i * BD_CH + lane];
-          const double lnext = (i + 1 < d) ? B[(size_t)(i + 1) * BD_CH + lane] : 0.0;
-          xn = fma(-lnext, xn, y);
-          W[(size_t)i * BD_CH + lane] = xn;
-          amax = fmax(amax, fabs(xn)); ssq = fma(xn, xn, ssq);
-        } else {
-          W[(size_t)i * BD_CH + lane] = is_v ? vm[i] : 0.0;
+      for (int i0 = d - 1; i0 >= 0; i0 -= BD_PF) {
+        double yv[BD_PF], lv[BD_PF];
+#pragma unroll
+        for (int u = 0; u < BD_PF; ++u) {
+          const int i = max(i0 - u, 0);
+          yv[u] = W[(size_t)i * BD_CH + lane];
+          lv[u] = (i + 1 < d) ? B[(size_t)(i + 1) * BD_CH + lane] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < BD_PF; ++u) {
+          const int i = i0 - u;
+          if (i >= 0) {
+            if (is_root) {
+              xn = fma(-lv[u], xn, yv[u]);
+              W[(size_t)i * BD_CH + lane] = xn;
+              amax = fmax(amax, fabs(xn)); ssq = fma(xn, xn, ssq);
+            } else {
+              W[(size_t)i * BD_CH + lane] = is_v ? vm[i] : 0.0;
+            }
+          }
         }
       }
       if (is_root) {
@@ -370,12 +416,20 @@ __device__ inline double bd_eval2(const BdChain& Q, int xv, int slot, double* vm
     if (lane < BD_CH) Q.Sc(slot, k)[lane] = Sj;
     // ---- W <- (sqrt(a) L_T)^-1 (x scale): bidiagonal recurrence, lane <-> column
     {
-      const double rsa = 1.0 / sa;
-      double u = W[lane] * scale * rsa * C.rld[0];
-      W[lane] = u;
-      for (int i = 1; i < d; ++i) {
-        u = (W[(size_t)i * BD_CH + lane] * scale * rsa - C.le[i - 1] * u) * C.rld[i];
-        W[(size_t)i * BD_CH + lane] = u;
+      const double rsa = scale / sa;
+      double u = 0.0;
+      for (int i0 = 0; i0 < d; i0 += BD_PF) {
+        double wv[BD_PF];
+#pragma unroll
+        for (int q2 = 0; q2 < BD_PF; ++q2) wv[q2] = W[(size_t)min(i0 + q2, d - 1) * BD_CH + lane];
+#pragma unroll
+        for (int q2 = 0; q2 < BD_PF; ++q2) {
+          const int i = i0 + q2;
+          if (i < d) {
+            u = (wv[q2] * rsa - (i > 0 ? C.le[i - 1] : 0.0) * u) * C.rld[i];
+            W[(size_t)i * BD_CH + lane] = u;
+          }
+        }
       }
       __syncwarp();
     }
@@ -386,17 +440,29 @@ __device__ inline double bd_eval2(const BdChain& Q, int xv, int slot, double* vm
       double sig[BD_CH];
 #pragma unroll
       for (int m = 0; m < BD_CH; ++m) sig[m] = 0.0;
-      for (int i = 0; i < d; ++i) {
-        bc[lane] = Wp[(size_t)i * BD_CH + lane]; bc[BD_CH + lane] = Bp[(size_t)i * BD_CH + lane];
-        __syncwarp();
-        double dot = 0.0;
+      for (int i0 = 0; i0 < d; i0 += 4) {
+        double wp[4], bp[4], dv[4], wo[4];
 #pragma unroll
-        for (int m = 0; m < BD_CH; ++m) dot = fma(bc[m], sig[m], dot);
-        const double y = (W[(size_t)i * BD_CH + lane] - dot) * rsqrt(dp[i]);
+        for (int q2 = 0; q2 < 4; ++q2) {
+          const int i = min(i0 + q2, d - 1);
+          wp[q2] = Wp[(size_t)i * BD_CH + lane]; bp[q2] = Bp[(size_t)i * BD_CH + lane]; dv[q2] = dp[i]; wo[q2] = W[(size_t)i * BD_CH + lane];
+        }
 #pragma unroll
-        for (int m = 0; m < BD_CH; ++m) sig[m] = fma(bc[BD_CH + m], y, sig[m]);
-        W[(size_t)i * BD_CH + lane] = y;
-        __syncwarp();
+        for (int q2 = 0; q2 < 4; ++q2) {
+          const int i = i0 + q2;
+          if (i < d) {
+            bc[lane] = wp[q2]; bc[BD_CH + lane] = bp[q2];
+            __syncwarp();
+            double dot = 0.0;
+#pragma unroll
+            for (int m = 0; m < BD_CH; ++m) dot = fma(bc[m], sig[m], dot);
+            const double y = (wo[q2] - dot) * rsqrt(dv[q2]);
+#pragma unroll
+            for (int m = 0; m < BD_CH; ++m) sig[m] = fma(bc[BD_CH + m], y, sig[m]);
+            W[(size_t)i * BD_CH + lane] = y;
+            __syncwarp();
+          }
+        }
       }
     }
     // ---- row sweep: chol(I + W S W'), state M (32 x 32) in registers, lane <-> row of M
@@ -406,25 +472,44 @@ __device__ inline double bd_eval2(const BdChain& Q, int xv, int slot, double* vm
       for (int m = 0; m < BD_CH; ++m) M[m] = (m == lane) ? Sj : 0.0;
       int bad = 0;
       double slog = 0.0;
-      for (int i = 0; i < d; ++i) {
-        const double w = W[(size_t)i * BD_CH + lane];
-        bc[lane] = w;
-        __syncwarp();
-        double t = 0.0;
+      double wnext[BD_PF];
 #pragma unroll
-        for (int m = 0; m < BD_CH; ++m) t = fma(M[m], bc[m], t);
-        const double dlt = 1.0 + warp_sum(w * t);
-        if (!(dlt > 0.0) || !isfinite(dlt)) { bad = 1; break; }     // uniform: dlt is the same on every lane
-        const double rs = rsqrt(dlt);
-        B[(size_t)i * BD_CH + lane] = t * rs;
-        bc[BD_CH + lane] = t;
-        __syncwarp();
-        const double tr = t * (rs * rs);
+      for (int q2 = 0; q2 < BD_PF; ++q2) wnext[q2] = W[(size_t)min(q2, d - 1) * BD_CH + lane];
+      for (int i0 = 0; i0 < d && !bad; i0 += BD_PF) {
+        double wcur[BD_PF];
 #pragma unroll
-        for (int m = 0; m < BD_CH; ++m) M[m] = fma(-tr, bc[BD_CH + m], M[m]);
-        if (lane == 0) dl[i] = dlt;
-        slog += log(dlt);
-        __syncwarp();
+        for (int q2 = 0; q2 < BD_PF; ++q2) wcur[q2] = wnext[q2];
+        if (i0 + BD_PF < d) {             // next block's rows in flight while this block is swept
+#pragma unroll
+          for (int q2 = 0; q2 < BD_PF; ++q2) wnext[q2] = W[(size_t)min(i0 + BD_PF + q2, d - 1) * BD_CH + lane];
+        }
+#pragma unroll
+        for (int q2 = 0; q2 < BD_PF; ++q2) {
+          const int i = i0 + q2;
+          if (i < d && !bad) {
+            const double w = wcur[q2];
+            bc[lane] = w;
+            __syncwarp();
+            double t = 0.0;
+#pragma unroll
+            for (int m = 0; m < BD_CH; ++m) t = fma(M[m], bc[m], t);
+            const double dlt = 1.0 + warp_sum(w * t);
+            if (!(dlt > 0.0) || !isfinite(dlt)) {          // uniform: dlt is the same on every lane
+              bad = 1;
+            } else {
+              const double rs = rsqrt(dlt);
+              B[(size_t)i * BD_CH + lane] = t * rs;
+              bc[BD_CH + lane] = t;
+              __syncwarp();
+              const double tr = t * (rs * rs);
+#pragma unroll
+              for (int m = 0; m < BD_CH; ++m) M[m] = fma(-tr, bc[BD_CH + m], M[m]);
+              if (lane == 0) dl[i] = dlt;
+              slog += log(dlt);
+            }
+            __syncwarp();
+          }
+        }
       }
       if (bad) { *ok = 0; return lt; }
       sumlog += 0.5 * slog;

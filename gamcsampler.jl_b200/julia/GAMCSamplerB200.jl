@@ -452,6 +452,14 @@ mutable struct BatchedMCJob
   p::Int
   nchains::Int
   range::BasicMCRange
+  bigd::Bool                 # t target of dimension n > 32: the structured large-dimension path (gamc_bigd_*)
+end
+# diagonal / off-diagonal of the tridiagonal inverse scale matrix inv((ν-2)Σ/ν), Σ_ij = c^|i-j|
+function mvt_tridiagonal(m::MvTModel)
+  s = m.ν / ((m.ν - 2) * (1 - m.c^2))
+  td = fill(s * (1 + m.c^2), m.n); td[1] = td[end] = s
+  m.n == 1 && (td[1] = m.ν / (m.ν - 2))
+  td, fill(-s * m.c, max(m.n - 1, 0))
 end
 function mvt_constants(m::MvTModel)
   Σt = [(m.ν - 2) * m.c^abs(i - j) / m.ν for i in 1:m.n, j in 1:m.n]
@@ -462,9 +470,21 @@ function mvt_constants(m::MvTModel)
 end
 lgamma_(x) = first(Base.Math.lgamma_r(x))     # SpecialFunctions.loggamma where available
 function BatchedMCJob(model, sampler::GAMC, range::BasicMCRange, v0s::Matrix{Float64}; tuner::GAMCTuner=GAMCTuner(), device::Integer=0,
-                      chain_offset::Integer=0)
+                      chain_offset::Integer=0, max_factors::Integer=0)
   sampler.update! isa Schedule || error("the batched kernel decides the branch on the device: pass one of the nine schedules")
   h = create(device)
+  if model isa MvTModel && model.n > 32
+    td, te = mvt_tridiagonal(model)
+    check(h, ccall((:gamc_bigd_target_mvt, libgamc), Cint, (Handle, Int32, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}), h, model.n, model.ν, td, te))
+    check(h, ccall((:gamc_bigd_set_chain_offset, libgamc), Cint, (Handle, Int64), h, chain_offset))
+    cfg = Ref(cconfig(sampler, tuner, range))
+    tr = sampler.transform
+    check(h, ccall((:gamc_bigd_init, libgamc), Cint, (Handle, Ref{CConfig}, Int32, Ptr{Cdouble}, Int32, Cdouble, Int32),
+                   h, cfg, size(v0s, 2), v0s, tr isa Softabs ? 1 : 0, tr isa Softabs ? tr.alpha : 0., max_factors))
+    job = BatchedMCJob(h, model.n, size(v0s, 2), range, true)
+    finalizer(j -> ccall((:gamc_destroy, libgamc), Cint, (Handle,), j.handle), job)
+    return job
+  end
   if model isa RVModel
     p = 5 * model.nplanets + 1
     check(h, ccall((:gamc_batched_target_rv, libgamc), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Int32),
@@ -484,11 +504,17 @@ function BatchedMCJob(model, sampler::GAMC, range::BasicMCRange, v0s::Matrix{Flo
   tr = sampler.transform
   check(h, ccall((:gamc_batched_init, libgamc), Cint, (Handle, Ref{CConfig}, Int32, Ptr{Cdouble}, Int32, Cdouble),
                  h, cfg, nchains, v0s, tr isa Softabs ? 1 : 0, tr isa Softabs ? tr.alpha : 0.))
-  job = BatchedMCJob(h, p, nchains, range)
+  job = BatchedMCJob(h, p, nchains, range, false)
   finalizer(j -> ccall((:gamc_destroy, libgamc), Cint, (Handle,), j.handle), job)
   job
 end
 function run!(job::BatchedMCJob; seed::Integer=0, n::Integer=job.range.nsteps)     # device Philox streams keyed by (seed, chain, iteration)
+  if job.bigd
+    check(job.handle, ccall((:gamc_bigd_run, libgamc), Cint, (Handle, Int64, UInt64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                            job.handle, n, seed, C_NULL, C_NULL, C_NULL, C_NULL))
+    check(job.handle, ccall((:gamc_sync, libgamc), Cint, (Handle,), job.handle))
+    return job
+  end
   check(job.handle, ccall((:gamc_batched_run, libgamc), Cint, (Handle, Int64, UInt64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
                           job.handle, n, seed, C_NULL, C_NULL, C_NULL, C_NULL))
   check(job.handle, ccall((:gamc_sync, libgamc), Cint, (Handle,), job.handle))
@@ -498,11 +524,19 @@ function output(job::BatchedMCJob)
   cap = max(0, job.range.nsteps - job.range.burnin)
   value = Array{Float64}(undef, job.p, cap, job.nchains)          # [p][cap][chain] in column-major = the ABI's [chain][cap][p]
   acc = Matrix{UInt8}(undef, cap, job.nchains)
-  check(job.handle, ccall((:gamc_batched_chain_get, libgamc), Cint, (Handle, Int32, Int32, Ptr{Cdouble}, Ptr{UInt8}), job.handle, 0, job.nchains, value, acc))
+  if job.bigd
+    check(job.handle, ccall((:gamc_bigd_chain_get, libgamc), Cint, (Handle, Int32, Int32, Ptr{Cdouble}, Ptr{UInt8}), job.handle, 0, job.nchains, value, acc))
+  else
+    check(job.handle, ccall((:gamc_batched_chain_get, libgamc), Cint, (Handle, Int32, Int32, Ptr{Cdouble}, Ptr{UInt8}), job.handle, 0, job.nchains, value, acc))
+  end
   [Chain(value[:, :, c], reshape(acc[:, c] .!= 0, 1, cap), Float64[]) for c in 1:job.nchains]
 end
 function state(job::BatchedMCJob, chain::Integer)
   st = Ref{CState}(); θ = Vector{Float64}(undef, job.p)
+  if job.bigd
+    check(job.handle, ccall((:gamc_bigd_get_state, libgamc), Cint, (Handle, Int32, Ref{CState}, Ptr{Cdouble}), job.handle, chain - 1, st, θ))
+    return st[], θ
+  end
   check(job.handle, ccall((:gamc_batched_get_state, libgamc), Cint, (Handle, Int32, Ref{CState}, Ptr{Cdouble}), job.handle, chain - 1, st, θ))
   st[], θ
 end
