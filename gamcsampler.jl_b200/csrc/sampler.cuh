@@ -698,8 +698,10 @@ __global__ void __launch_bounds__(256) k_llt(const double* __restrict__ L, int p
 // ---------------------------------------------------------------------------------------------------
 // AM branch, part 2 (iterate/GAMC.jl:148-191 + tail).  The two GMM log-densities (:152,156) use the same
 // covariance with the roles of theta and theta* exchanged; d -> -d gives bit-identical quadratic forms and
-// log-sum-exp, so they cancel exactly and the device omits them (the oracle evaluates both literally and
-// tests/test_oracle_sampler.py asserts the cancellation is exact).
+// log-sum-exp, so the two terms are the same number a and the device omits them.  The reference forms
+// (r - a) + a, which equals r up to ONE rounding of the ratio (not bit for bit); accept decisions agree in
+// every tested run (the oracle evaluates both terms literally; tests/test_oracle_sampler.py asserts a is
+// bit-identical on both sides).
 // ---------------------------------------------------------------------------------------------------
 // next_spec = 1 (am_mode 2): the next step is an AM step whose factor update was computed speculatively for both outcomes
 // while the data pass ran; after the decision this kernel selects the factor buffer of the outcome that happened and

@@ -105,6 +105,34 @@ def test_batched_rv_target_parity(gamc, engine, name, npl, nchains, nsteps):
         assert st.updatetensorcount == sam.updatetensorcount and st.count == nsteps
 
 
+def test_batched_rv_c5_size_parity(gamc, engine):
+    """BASELINE config 5 at its full size (N = 2^18 epochs, one planet): three SMMALA transitions (second-order duals in the kernel,
+    block-cooperative reduction over 262 144 epochs) against the oracle's accept decisions, values and final log-target."""
+    import oracle as o
+    from oracle import targets as T
+    rng = np.random.default_rng(11)
+    N = 1 << 18
+    t = np.sort(rng.uniform(0.0, 730.5, N))
+    truth = T.make_param_true_ex1()
+    sig = 2.0 * np.ones(N)
+    obs = T.RVModel(t, np.zeros(N), sig).model_rv(truth) + 2.0 * rng.standard_normal(N)
+    nsteps = 3
+    sampler = gamc.GAMC(update=gamc.smmala_only_update(), transform=gamc.softabs(1000.0), driftstep=0.02, minorscale=0.001, c=0.01)
+    tuner = gamc.GAMCTuner(gamc.VanillaMCTuner(), gamc.VanillaMCTuner(), gamc.AcceptanceRateMCTuner(0.35))
+    v0s = truth + 3e-6 * _rv_perturb_scale(1) * rng.standard_normal((1, 6))
+    tape = gamc.BatchedRandomTape(1, nsteps, 6, seed=19)
+    job = gamc.BatchedMCJob(gamc.RVModel(t, obs, sig, 1), sampler, gamc.BasicMCRange(nsteps, 0), v0s, tuner=tuner, tape=tape, engine=engine)
+    job.run()
+    chains = job.output()
+    sam = o.GAMCOracle(T.RVModel(t, obs, sig), v0s[0], nsteps, 0, update="smmala_only_update!", transform=lambda H: T.softabs(H, 1000.0), driftstep=0.02,
+                       minorscale=0.001, c=0.01, tuner=o.GAMCTuner(o.VanillaMCTuner(), o.VanillaMCTuner(), o.AcceptanceRateMCTuner(0.35)))
+    v, a, _ = sam.run(o.RandomTape(nsteps, 6, seed=19))
+    assert np.array_equal(chains[0].diagnosticvalues.ravel(), a)
+    assert relerr(chains[0].value, v) <= 1e-6
+    st, _ = engine.batched_state(0)
+    assert abs(st.logtarget - sam.logtarget) <= 1e-9 * abs(sam.logtarget)
+
+
 def test_batched_rv_many_epochs_derivatives(gamc, engine):
     """Synthetic epochs (N = 20000, data_generation.jl:11-33 recipe): one SMMALA step from the truth must reproduce the
     oracle's log-target after the step, i.e. the block-cooperative reduction over epochs is exact to FP64 rounding."""
