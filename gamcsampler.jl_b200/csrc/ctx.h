@@ -9,6 +9,7 @@
 #include <map>
 #include <cuda_runtime.h>
 #include "../../include/gamc_b200.h"
+#include "guard.h"
 
 constexpr int GAMC_PROF_POOL = 32768;
 enum { GAMC_EXT_BATCHED = 0, GAMC_EXT_BIGD = 1, GAMC_EXT_COUNT = 4 };

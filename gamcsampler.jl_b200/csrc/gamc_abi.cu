@@ -1560,6 +1560,59 @@ gamc_status gamc_launch_count(gamc_handle h, int64_t* out) {
   return GAMC_OK;
 }
 
+#ifdef GAMC_GUARD
+}  // extern "C"
+#undef cudaMalloc
+#undef cudaFree
+namespace {
+constexpr size_t GUARD_BYTES = 4096;
+constexpr unsigned char GUARD_PATTERN = 0xA5;
+struct GuardRec { unsigned char* base; size_t bytes; };
+std::vector<GuardRec> g_guard;
+__global__ void k_guard_scan(const unsigned char* z, size_t n, unsigned long long* bad) {
+  unsigned long long c = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c += z[i] != GUARD_PATTERN;
+  if (c) atomicAdd(bad, c);
+}
+}  // namespace
+cudaError_t gamc_guard_malloc(void** p, size_t bytes) {
+  unsigned char* base = nullptr;
+  const size_t padded = (bytes + 255) & ~(size_t)255;
+  cudaError_t e = cudaMalloc(&base, padded + 2 * GUARD_BYTES);
+  if (e != cudaSuccess) return e;
+  cudaMemset(base, GUARD_PATTERN, GUARD_BYTES);
+  cudaMemset(base + GUARD_BYTES + bytes, GUARD_PATTERN, padded - bytes + GUARD_BYTES);
+  g_guard.push_back(GuardRec{base, bytes});
+  *p = base + GUARD_BYTES;
+  return cudaSuccess;
+}
+cudaError_t gamc_guard_free(void* p) {
+  if (!p) return cudaSuccess;
+  unsigned char* base = static_cast<unsigned char*>(p) - GUARD_BYTES;
+  for (size_t i = 0; i < g_guard.size(); ++i)
+    if (g_guard[i].base == base) { g_guard.erase(g_guard.begin() + i); return cudaFree(base); }
+  return cudaFree(p);     // not one of ours (e.g. an IPC mapping)
+}
+extern "C" {
+// Number of guard bytes overwritten next to any live allocation (0 = no out-of-bounds write), and the number of live allocations.
+long long gamc_debug_guard_check(long long* n_allocations) {
+  cudaDeviceSynchronize();
+  unsigned long long* d_bad = nullptr;
+  cudaMalloc(&d_bad, sizeof(unsigned long long));
+  cudaMemset(d_bad, 0, sizeof(unsigned long long));
+  for (const GuardRec& r : g_guard) {
+    const size_t padded = (r.bytes + 255) & ~(size_t)255;
+    k_guard_scan<<<8, 256>>>(r.base, GUARD_BYTES, d_bad);
+    k_guard_scan<<<8, 256>>>(r.base + GUARD_BYTES + r.bytes, padded - r.bytes + GUARD_BYTES, d_bad);
+  }
+  unsigned long long bad = 0;
+  cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+  cudaFree(d_bad);
+  if (n_allocations) *n_allocations = (long long)g_guard.size();
+  return (long long)bad;
+}
+#endif
+
 #ifdef GAMC_PHASE_CLOCKS
 // Debug build only (make dbg): accumulated clock64 deltas / hit counts of the PHASE() marks; reset = 1 clears them.
 int gamc_debug_phases(long long* acc, long long* cnt, int reset) {
