@@ -820,19 +820,18 @@ __global__ void __launch_bounds__(BD_MAXD) k_bd_am_pre(BdCfg C, long long tape_p
     const int j0 = b << 5, nb = min(32, d - j0);
     __syncthreads();
     if (warp == b) {
-      double lrow[32];
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        lrow[jj] = (jj <= lane && jj < nb && i < d) ? alpha * L[(size_t)(j0 + lane) + (size_t)(j0 + jj) * d] : 0.0;
-        Ls[jj * 33 + lane] = lrow[jj];
-      }
+      // diagonal block: the lane's row of a L goes to shared memory (the register budget at 1024 threads per CTA is 64)
+#pragma unroll 8
+      for (int jj = 0; jj < 32; ++jj)
+        Ls[jj * 33 + lane] = (jj <= lane && jj < nb && i < d) ? alpha * L[(size_t)(j0 + lane) + (size_t)(j0 + jj) * d] : 0.0;
+      __syncwarp();
       double res = ui - P, wmine = 0.0;
-#pragma unroll
+#pragma unroll 8
       for (int jj = 0; jj < 32; ++jj) {
         if (jj < nb) {
           const double wj = __shfl_sync(0xffffffffu, res * rdv, jj);
           if (lane == jj) wmine = wj;
-          res = fma(-lrow[jj], wj, res);
+          res = fma(-Ls[jj * 33 + lane], wj, res);
           Ts[jj * 33 + lane] = res;
         }
       }
@@ -849,18 +848,22 @@ __global__ void __launch_bounds__(BD_MAXD) k_bd_am_pre(BdCfg C, long long tape_p
     __syncthreads();
     sigma = bw[96];
     if (i >= j0 + 32 && i < d) {
-      double lv[32];
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) lv[jj] = (jj < nb) ? L[(size_t)i + (size_t)(j0 + jj) * d] : 0.0;
       double res = ui - P, a0 = 0.0, a1 = 0.0;
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        if (jj < nb) {
-          const double l = alpha * lv[jj];
-          res = fma(-l, bw[jj], res);
-          const double ln = fma(l, bw[32 + jj], bw[64 + jj] * res);
-          L[(size_t)i + (size_t)(j0 + jj) * d] = ln;
-          if (jj & 1) a1 = fma(ln, zs[j0 + jj], a1); else a0 = fma(ln, zs[j0 + jj], a0);
+      for (int h0 = 0; h0 < 32; h0 += 16) {              // 16 columns at a time: their loads are in flight together
+        double lv[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) lv[jj] = (h0 + jj < nb) ? L[(size_t)i + (size_t)(j0 + h0 + jj) * d] : 0.0;
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          if (h0 + jj < nb) {
+            const int c = h0 + jj;
+            const double l = alpha * lv[jj];
+            res = fma(-l, bw[c], res);
+            const double ln = fma(l, bw[32 + c], bw[64 + c] * res);
+            L[(size_t)i + (size_t)(j0 + c) * d] = ln;
+            if (jj & 1) a1 = fma(ln, zs[j0 + c], a1); else a0 = fma(ln, zs[j0 + c], a0);
+          }
         }
       }
       P = ui - res;

@@ -654,10 +654,12 @@ gamc_status launch_step(gamc_ctx* h, int family, K kern, Args... args) {
   return GAMC_OK;
 }
 
+__global__ void k_state_factor(Bufs B, TuneCfg T);   // defined with the other small kernels of the round-2 entry points below
+
 gamc_status set_step_attrs(gamc_ctx* h) {
   const int smem = (int)step_smem_bytes(512);   // sized for the largest supported p so the attribute is set once
   const void* ks[] = {(const void*)k_sampler_init, (const void*)k_smmala_pre, (const void*)k_smmala_post, (const void*)k_am_pre,
-                      (const void*)k_am_post};
+                      (const void*)k_am_post, (const void*)k_state_factor};
   for (const void* k : ks) { gamc_status s = ensure_attr(h, k, smem); if (s != GAMC_OK) return s; }
   {
     // the request depends on p through the number of panel buffers (two while they fit 200 KB: p <= 352), so the limit is the
@@ -807,6 +809,7 @@ gamc_status gamc_create(gamc_handle* out, int32_t device) {
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess) { delete h; return GAMC_CUDA_ERROR; }
   h->ev0.resize(PROF_POOL); h->ev1.resize(PROF_POOL); h->ev_family.resize(PROF_POOL);
+  if (const char* ts = getenv("GAMC_PEER_TIMEOUT_S")) { const double v = atof(ts); if (v > 0.0 && v < 1e6) h->peer_timeout_ns = (unsigned long long)(v * 1e9); }
   *out = h;
   return GAMC_OK;
 }
@@ -1434,7 +1437,6 @@ gamc_status gamc_set_state(gamc_handle h, const gamc_state_scalars* st_in, const
     if (T.am_mode >= 1) { s = launch_step(h, GAMC_K_LINALG, k_state_factor, B, T); if (s != GAMC_OK) return s; }
   }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  { gamc_status e = ensure_attr(h, (const void*)k_state_factor, step_smem_bytes(512)); if (e != GAMC_OK) return e; }
   return check_device_error(h);
 }
 

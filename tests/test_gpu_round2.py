@@ -59,6 +59,35 @@ def test_user_schedule_function(gamc, engine):
     assert job.sstate.updatetensorcount == want
 
 
+def test_set_state_restart_large_p(gamc, engine):
+    """The same at p = 300 (the step kernels then need more than the default 48 KB of dynamic shared memory)."""
+    N, p, nsteps, split = 2500, 300, 60, 42
+    X, y, tt = _problem(N, p)
+    theta0 = tt + 0.02 * np.random.default_rng(9).standard_normal(p)
+    tape = gamc.RandomTape(nsteps, p, seed=13)
+    engine.target_logistic(X, y, 100.0)
+    sampler, tuner, rng_ = example_config(gamc, nsteps, 0, am_mode=1, update=gamc.mod_update(5))
+    job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, rng_, {"p": theta0}, tuner=tuner, tape=tape, engine=engine)
+    job.run()
+    full = job.output()
+    job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, rng_, {"p": theta0}, tuner=tuner, engine=engine)
+    engine.tape_set(tape.u_sched[:split], tape.u_mix[:split], tape.z[:split], tape.u_acc[:split])
+    engine.run(split)
+    engine.sync()
+    st = engine.state()
+    assert st.pastupdatetensor == 0            # iterations 41, 42 of mod_update(5) are AM steps: the restart must carry the AM covariance
+    saved = dict(theta=engine.array(0), m1=engine.array(3), m2=engine.array(4), C=engine.array(5))
+    part1, acc1 = engine.chain_get(0, split)
+    job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, rng_, {"p": theta0}, tuner=tuner, engine=engine)
+    engine.set_state(st, saved["theta"], saved["m1"], saved["m2"], saved["C"])
+    engine.tape_set(tape.u_sched[split:], tape.u_mix[split:], tape.z[split:], tape.u_acc[split:])
+    engine.run(nsteps - split)
+    engine.sync()
+    part2, acc2 = engine.chain_get(0, nsteps - split)
+    assert np.array_equal(np.concatenate([acc1, acc2]), full.diagnosticvalues.ravel())
+    assert relerr(np.concatenate([part1, part2], axis=1), full.value) <= 1e-9
+
+
 @pytest.mark.parametrize("am_mode", [0, 1, 2])
 @pytest.mark.parametrize("split", [137, 150])
 def test_set_state_restart(gamc, engine, am_mode, split):
