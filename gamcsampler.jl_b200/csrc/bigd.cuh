@@ -69,6 +69,8 @@ struct BdChain {                 // per-warp view of one chain
   __device__ double* Sc(int slot, int k) const { return C->S + slot_chunk(slot, k) * BD_CH; }
 };
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // index-reversed ("M space") view of the tridiagonal T: row i' = d-1-i
 __device__ __forceinline__ double bd_tdm(const BdCfg& C, int i) { return C.td[C.d - 1 - i]; }
 __device__ __forceinline__ double bd_tem(const BdCfg& C, int i) { return C.te[C.d - 2 - i]; }   // between rows i and i+1 of M space
@@ -277,18 +279,124 @@ __device__ inline void bd_k_mult_t(const double* __restrict__ W, const double* _
   __syncwarp();
 }
 
-// Lm y = b, Lm' y = b, y = Lm' x for the product-form factor of `slot` (nch factors); xs in M-space order
-__device__ inline void bd_solve(const BdChain& Q, int slot, int nch, double sa, double* xs) {
-  bd_bidiag_solve(*Q.C, sa, xs, Q.lane);
-  for (int k = 0; k < nch; ++k) bd_k_solve(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+// The same three recurrences for a factor with at most NC live generator columns (NC = 4: the typical-set regime, where a factor
+// holds the lowest eigenvector and v).  Every lane carries the whole NC-vector and reads the generator rows as broadcasts, so a
+// row step is a short chain of FMAs with no shuffle reduction on it (about four times shorter than the 32-column version).
+template <int NC>
+__device__ inline void bd_k_solve_nc(const double* __restrict__ W, const double* __restrict__ B, const double* __restrict__ dl, int d, double* xs, int lane) {
+  double sig[NC];
+#pragma unroll
+  for (int m = 0; m < NC; ++m) sig[m] = 0.0;
+  __syncwarp();
+  for (int i0 = 0; i0 < d; i0 += 4) {
+    double w[4][NC], b[4][NC], rs[4], xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = min(i0 + u, d - 1);
+#pragma unroll
+      for (int m = 0; m < NC; ++m) { w[u][m] = W[(size_t)i * BD_CH + m]; b[u][m] = B[(size_t)i * BD_CH + m]; }
+      rs[u] = rsqrt(dl[i]); xv[u] = xs[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u < d) {
+        double dot = 0.0;
+#pragma unroll
+        for (int m = 0; m < NC; ++m) dot = fma(w[u][m], sig[m], dot);
+        const double y = (xv[u] - dot) * rs[u];
+#pragma unroll
+        for (int m = 0; m < NC; ++m) sig[m] = fma(b[u][m], y, sig[m]);
+        if (lane == 0) xs[i0 + u] = y;
+      }
+    }
+  }
+  __syncwarp();
 }
-__device__ inline void bd_solve_t(const BdChain& Q, int slot, int nch, double sa, double* xs) {
-  for (int k = nch - 1; k >= 0; --k) bd_k_solve_t(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+template <int NC>
+__device__ inline void bd_k_solve_t_nc(const double* __restrict__ W, const double* __restrict__ B, const double* __restrict__ dl, int d, double* xs, int lane) {
+  double tau[NC];
+#pragma unroll
+  for (int m = 0; m < NC; ++m) tau[m] = 0.0;
+  __syncwarp();
+  for (int j0 = d - 1; j0 >= 0; j0 -= 4) {
+    double w[4][NC], b[4][NC], rs[4], xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = max(j0 - u, 0);
+#pragma unroll
+      for (int m = 0; m < NC; ++m) { w[u][m] = W[(size_t)j * BD_CH + m]; b[u][m] = B[(size_t)j * BD_CH + m]; }
+      rs[u] = rsqrt(dl[j]); xv[u] = xs[j];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (j0 - u >= 0) {
+        double dot = 0.0;
+#pragma unroll
+        for (int m = 0; m < NC; ++m) dot = fma(b[u][m], tau[m], dot);
+        const double y = (xv[u] - dot) * rs[u];
+#pragma unroll
+        for (int m = 0; m < NC; ++m) tau[m] = fma(w[u][m], y, tau[m]);
+        if (lane == 0) xs[j0 - u] = y;
+      }
+    }
+  }
+  __syncwarp();
+}
+template <int NC>
+__device__ inline void bd_k_mult_t_nc(const double* __restrict__ W, const double* __restrict__ B, const double* __restrict__ dl, int d, double* xs, int lane) {
+  double tau[NC];
+#pragma unroll
+  for (int m = 0; m < NC; ++m) tau[m] = 0.0;
+  __syncwarp();
+  for (int j0 = d - 1; j0 >= 0; j0 -= 4) {
+    double w[4][NC], b[4][NC], sd[4], xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = max(j0 - u, 0);
+#pragma unroll
+      for (int m = 0; m < NC; ++m) { w[u][m] = W[(size_t)j * BD_CH + m]; b[u][m] = B[(size_t)j * BD_CH + m]; }
+      sd[u] = sqrt(dl[j]); xv[u] = xs[j];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (j0 - u >= 0) {
+        double dot = 0.0;
+#pragma unroll
+        for (int m = 0; m < NC; ++m) dot = fma(b[u][m], tau[m], dot);
+#pragma unroll
+        for (int m = 0; m < NC; ++m) tau[m] = fma(w[u][m], xv[u], tau[m]);
+        if (lane == 0) xs[j0 - u] = fma(sd[u], xv[u], dot);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Lm y = b, Lm' y = b, y = Lm' x for the product-form factor of `slot` (nch factors, ncol live columns in all); xs in M-space order
+__device__ __forceinline__ bool bd_small(int ncol, int k) { return ncol - k * BD_CH <= 4; }
+__device__ inline void bd_solve(const BdChain& Q, int slot, int nch, int ncol, double sa, double* xs) {
+  bd_bidiag_solve(*Q.C, sa, xs, Q.lane);
+  for (int k = 0; k < nch; ++k) {
+    if (bd_small(ncol, k)) bd_k_solve_nc<4>(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+    else bd_k_solve(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+  }
+}
+__device__ inline void bd_solve_t(const BdChain& Q, int slot, int nch, int ncol, double sa, double* xs) {
+  for (int k = nch - 1; k >= 0; --k) {
+    if (bd_small(ncol, k)) bd_k_solve_t_nc<4>(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+    else bd_k_solve_t(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+  }
   bd_bidiag_solve_t(*Q.C, sa, xs, Q.lane);
 }
-__device__ inline void bd_mult_t(const BdChain& Q, int slot, int nch, double sa, double* xs) {
+__device__ inline void bd_mult_t(const BdChain& Q, int slot, int nch, int ncol, double sa, double* xs) {
   bd_bidiag_mult_t(*Q.C, sa, xs, Q.lane);
-  for (int k = 0; k < nch; ++k) bd_k_mult_t(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+  for (int k = 0; k < nch; ++k) {
+    if (bd_small(ncol, k)) bd_k_mult_t_nc<4>(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+    else bd_k_mult_t(Q.Wc(slot, k), Q.Bc(slot, k), Q.Dc(slot, k), Q.d, xs, Q.lane);
+  }
 }
 // NOTE on bd_mult_t: Lm' = K_m' ... K_1' (sqrt(a) L_T)'  -- the bidiagonal factor is applied first, then K_1', ..., K_m'.
 
@@ -465,8 +573,60 @@ __device__ inline double bd_eval2(const BdChain& Q, int xv, int slot, double* vm
         }
       }
     }
-    // ---- row sweep: chol(I + W S W'), state M (32 x 32) in registers, lane <-> row of M
-    {
+    // ---- row sweep: chol(I + W S W').  With at most four live columns (the typical-set regime) every lane carries the whole 4 x 4
+    //      state and reads the generator rows as broadcasts: no shared-memory broadcast, no shuffle reduction on the row's chain.
+    const int live = min(BD_CH, ncol - k * BD_CH);
+    if (live <= 4) {
+      constexpr int NC = 4;
+      double M[NC][NC];
+#pragma unroll
+      for (int p2 = 0; p2 < NC; ++p2)
+#pragma unroll
+        for (int q2 = 0; q2 < NC; ++q2) M[p2][q2] = 0.0;
+#pragma unroll
+      for (int p2 = 0; p2 < NC; ++p2) M[p2][p2] = __shfl_sync(0xffffffffu, Sj, p2);
+      int bad = 0;
+      double slog = 0.0, prod = 1.0;
+      for (int i0 = 0; i0 < d && !bad; i0 += 4) {
+        double wv[4][NC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int m = 0; m < NC; ++m) wv[u][m] = W[(size_t)min(i0 + u, d - 1) * BD_CH + m];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u;
+          if (i < d && !bad) {
+            double t[NC];
+            double dlt = 1.0;
+#pragma unroll
+            for (int p2 = 0; p2 < NC; ++p2) {
+              double a2 = 0.0;
+#pragma unroll
+              for (int q2 = 0; q2 < NC; ++q2) a2 = fma(M[p2][q2], wv[u][q2], a2);
+              t[p2] = a2;
+              dlt = fma(wv[u][p2], a2, dlt);
+            }
+            if (!(dlt > 0.0) || !isfinite(dlt)) {
+              bad = 1;
+            } else {
+              const double rs = rsqrt(dlt), rr = rs * rs;
+              if (lane < NC) B[(size_t)i * BD_CH + lane] = (lane == 0 ? t[0] : lane == 1 ? t[1] : lane == 2 ? t[2] : t[3]) * rs;
+              else B[(size_t)i * BD_CH + lane] = 0.0;
+#pragma unroll
+              for (int p2 = 0; p2 < NC; ++p2)
+#pragma unroll
+                for (int q2 = 0; q2 < NC; ++q2) M[p2][q2] = fma(-t[p2] * rr, t[q2], M[p2][q2]);
+              if (lane == 0) dl[i] = dlt;
+              prod *= dlt;
+              if ((i & 7) == 7) { slog += log(prod); prod = 1.0; }      // one logarithm per eight rows
+            }
+          }
+        }
+      }
+      if (bad) { *ok = 0; return lt; }
+      sumlog += 0.5 * (slog + log(prod));
+    } else {
       double M[BD_CH];
 #pragma unroll
       for (int m = 0; m < BD_CH; ++m) M[m] = (m == lane) ? Sj : 0.0;
@@ -519,8 +679,8 @@ __device__ inline double bd_eval2(const BdChain& Q, int xv, int slot, double* vm
   // ---- firstterm = G^-1 grad = P Lm^-T Lm^-1 P grad
   for (int i = lane; i < d; i += 32) xs[d - 1 - i] = g[i];
   __syncwarp();
-  bd_solve(Q, slot, nch, sa, xs);
-  bd_solve_t(Q, slot, nch, sa, xs);
+  bd_solve(Q, slot, nch, ncol, sa, xs);
+  bd_solve_t(Q, slot, nch, ncol, sa, xs);
   double* f = Q.vec(BDV_F0 + slot);
   double bad = 0.0;
   for (int i = lane; i < d; i += 32) { const double fi = xs[d - 1 - i]; f[i] = fi; if (!isfinite(fi)) bad = 1.0; }
@@ -646,7 +806,7 @@ __global__ void __launch_bounds__(32 * BD_WPB) k_bd_smmala_pre(BdCfg C, long lon
   // theta* = mu + sqrt(eps) chol(inv(G)) z,  chol(inv(G)) z = P Lm^-T P z                                   (:33-35)
   for (int i = lane; i < d; i += 32) w.xs[d - 1 - i] = bd_normal(C, Q.chain, t, tape_pos, i);
   __syncwarp();
-  bd_solve_t(Q, cur, (int)s[BDS_NCH0 + cur], sqrt(s[BDS_A0 + cur]), w.xs);
+  bd_solve_t(Q, cur, (int)s[BDS_NCH0 + cur], (int)s[BDS_R0 + cur] + 1, sqrt(s[BDS_A0 + cur]), w.xs);
   const double* th = Q.vec(BDV_THETA); const double* f = Q.vec(BDV_F0 + cur);
   double* mu = Q.vec(BDV_MU); double* prop = Q.vec(BDV_PROP);
   for (int i = lane; i < d; i += 32) { const double m = th[i] + 0.5 * eps * f[i]; mu[i] = m; prop[i] = m + sq * w.xs[d - 1 - i]; }
@@ -672,7 +832,7 @@ __global__ void __launch_bounds__(32 * BD_WPB) k_bd_smmala_post(BdCfg C) {
     // q1 = d'G d = |Lm' P d|^2, d = theta* - mu                                                              (:47-54)
     for (int i = lane; i < d; i += 32) w.xs[d - 1 - i] = prop[i] - mu[i];
     __syncwarp();
-    bd_mult_t(Q, cur, (int)s[BDS_NCH0 + cur], sqrt(s[BDS_A0 + cur]), w.xs);
+    bd_mult_t(Q, cur, (int)s[BDS_NCH0 + cur], (int)s[BDS_R0 + cur] + 1, sqrt(s[BDS_A0 + cur]), w.xs);
     double q1 = 0.0;
     for (int i = lane; i < d; i += 32) q1 = fma(w.xs[i], w.xs[i], q1);
     q1 = warp_sum(q1);
@@ -681,7 +841,7 @@ __global__ void __launch_bounds__(32 * BD_WPB) k_bd_smmala_post(BdCfg C) {
     const double* fp = Q.vec(BDV_F0 + prp);
     for (int i = lane; i < d; i += 32) w.xs[d - 1 - i] = th[i] - (prop[i] + 0.5 * eps * fp[i]);
     __syncwarp();
-    bd_mult_t(Q, prp, (int)s[BDS_NCH0 + prp], sqrt(s[BDS_A0 + prp]), w.xs);
+    bd_mult_t(Q, prp, (int)s[BDS_NCH0 + prp], (int)s[BDS_R0 + prp] + 1, sqrt(s[BDS_A0 + prp]), w.xs);
     double q2 = 0.0;
     for (int i = lane; i < d; i += 32) q2 = fma(w.xs[i], w.xs[i], q2);
     q2 = warp_sum(q2);
@@ -734,13 +894,51 @@ __global__ void __launch_bounds__(32 * BD_WPB) k_bd_am_post(BdCfg C) {
 // unit vectors, all columns in lockstep over the rows so that every store is coalesced), one pass per product factor.
 // X(j, c) lands at L[(d-1-c) + (d-1-j) d].
 // ---------------------------------------------------------------------------------------------------
+// One pass of the hand-over for one product factor with NC live columns (NC = 4 covers the typical-set regime, where a factor
+// holds the lowest eigenvector and v: the other 30 generator columns are zero and are skipped).
+template <int NC>
+__device__ __forceinline__ void bd_handover_pass(const BdCfg& C, const double* __restrict__ W, const double* __restrict__ B, const double* __restrict__ dl,
+                                                 double* __restrict__ L, double* __restrict__ rdiag, int k, bool last, double rsa, double (*rows)[2 * BD_CH + 2]) {
+  const int c = threadIdx.x, d = C.d;
+  double sig[NC];
+#pragma unroll
+  for (int m = 0; m < NC; ++m) sig[m] = 0.0;
+  double u = 0.0;                                      // bidiagonal recurrence of pass 0
+  for (int i0 = 0; i0 < d; i0 += 16) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 16 * (2 * NC + 1); e += blockDim.x) {
+      const int rr = e / (2 * NC + 1), m = e % (2 * NC + 1), i = i0 + rr;
+      if (i < d) rows[rr][m] = m < NC ? W[(size_t)i * BD_CH + m] : (m < 2 * NC ? B[(size_t)i * BD_CH + (m - NC)] : rsqrt(dl[i]));
+    }
+    __syncthreads();
+    if (c >= d) continue;
+    for (int rr = 0; rr < 16 && i0 + rr < d; ++rr) {
+      const int i = i0 + rr;
+      if (i < c) continue;                             // X is lower triangular: rows above the diagonal are zero and stay zero
+      const size_t addr = (size_t)(d - 1 - c) + (size_t)(d - 1 - i) * d;
+      double x;
+      if (k == 0) { u = ((i == c ? rsa : 0.0) - C.le[i > 0 ? i - 1 : 0] * (i > c ? u : 0.0)) * C.rld[i]; x = u; }
+      else x = L[addr];
+      double dot = 0.0;
+#pragma unroll
+      for (int m = 0; m < NC; ++m) dot = fma(rows[rr][m], sig[m], dot);
+      const double y = (x - dot) * rows[rr][2 * NC];
+#pragma unroll
+      for (int m = 0; m < NC; ++m) sig[m] = fma(rows[rr][NC + m], y, sig[m]);
+      L[addr] = y;
+      if (last && i == c) rdiag[d - 1 - c] = 1.0 / y;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(BD_MAXD) k_bd_handover(BdCfg C) {
   __shared__ double rows[16][2 * BD_CH + 2];
-  const int chain = blockIdx.x, c = threadIdx.x, d = C.d;
+  const int chain = blockIdx.x, d = C.d;
   double* s = C.scal + (size_t)chain * BDS_N;
   if (s[BDS_ERR] != 0.0 || s[BDS_PRESENT] != 0.0 || s[BDS_PAST] == 0.0) return;
   const int cur = (int)s[BDS_CUR];
   const int nch = (int)s[BDS_NCH0 + cur];
+  const int ncol = (int)s[BDS_R0 + cur] + 1;           // live columns over all factors (the eigenvectors softabs changed, then v)
   const double rsa = 1.0 / sqrt(s[BDS_A0 + cur]);
   double* L = C.L + (size_t)chain * d * d;
   double* rdiag = C.rdiagL + (size_t)chain * d;
@@ -749,35 +947,9 @@ __global__ void __launch_bounds__(BD_MAXD) k_bd_handover(BdCfg C) {
     const double* W = C.W + (sc0 + k) * (size_t)d * BD_CH;
     const double* B = C.B + (sc0 + k) * (size_t)d * BD_CH;
     const double* dl = C.delta + (sc0 + k) * (size_t)d;
-    double sig[BD_CH];
-#pragma unroll
-    for (int m = 0; m < BD_CH; ++m) sig[m] = 0.0;
-    double u = 0.0;                                    // bidiagonal recurrence of pass 0
-    for (int i0 = 0; i0 < d; i0 += 16) {
-      __syncthreads();
-      for (int e = threadIdx.x; e < 16 * (2 * BD_CH + 1); e += blockDim.x) {
-        const int rr = e / (2 * BD_CH + 1), m = e % (2 * BD_CH + 1), i = i0 + rr;
-        if (i < d) rows[rr][m] = m < BD_CH ? W[(size_t)i * BD_CH + m] : (m < 2 * BD_CH ? B[(size_t)i * BD_CH + (m - BD_CH)] : rsqrt(dl[i]));
-      }
-      __syncthreads();
-      if (c >= d) continue;
-      for (int rr = 0; rr < 16 && i0 + rr < d; ++rr) {
-        const int i = i0 + rr;
-        if (i < c) continue;                           // X is lower triangular: rows above the diagonal are zero and stay zero
-        const size_t addr = (size_t)(d - 1 - c) + (size_t)(d - 1 - i) * d;
-        double x;
-        if (k == 0) { u = ((i == c ? rsa : 0.0) - C.le[i > 0 ? i - 1 : 0] * (i > c ? u : 0.0)) * C.rld[i]; x = u; }
-        else x = L[addr];
-        double dot = 0.0;
-#pragma unroll
-        for (int m = 0; m < BD_CH; ++m) dot = fma(rows[rr][m], sig[m], dot);
-        const double y = (x - dot) * rows[rr][2 * BD_CH];
-#pragma unroll
-        for (int m = 0; m < BD_CH; ++m) sig[m] = fma(rows[rr][BD_CH + m], y, sig[m]);
-        L[addr] = y;
-        if (k == nch - 1 && i == c) rdiag[d - 1 - c] = 1.0 / y;
-      }
-    }
+    const int live = min(BD_CH, ncol - k * BD_CH);
+    if (live <= 4) bd_handover_pass<4>(C, W, B, dl, L, rdiag, k, k == nch - 1, rsa, rows);
+    else bd_handover_pass<BD_CH>(C, W, B, dl, L, rdiag, k, k == nch - 1, rsa, rows);
   }
 }
 
@@ -816,8 +988,19 @@ __global__ void __launch_bounds__(BD_MAXD) k_bd_am_pre(BdCfg C, long long tape_p
   }
   double sigma = 1.0;
   const int nblk = (d + 31) >> 5;
+  // the first diagonal block, towards L2
+  if (warp == 0 && i < d) for (int jj = 0; jj <= lane && jj < 32; ++jj) prefetch_l2(&L[(size_t)lane + (size_t)jj * d]);
   for (int b = 0; b < nblk; ++b) {
     const int j0 = b << 5, nb = min(32, d - j0);
+    // While the diagonal warp runs its serial chain, the rows below fetch their 32 columns of this block (and the next diagonal
+    // block) into L2: the loads after the barrier then see L2 latency instead of HBM latency.  One request per 32-byte sector.
+    if (i >= j0 + 32 && i < d) {
+      if ((lane & 3) == 0) {
+#pragma unroll 8
+        for (int jj = 0; jj < 32; ++jj) if (jj < nb) prefetch_l2(&L[(size_t)i + (size_t)(j0 + jj) * d]);
+      }
+      if (warp == b + 1) for (int jj = 0; jj <= lane && jj < 32 && j0 + 32 + jj < d; ++jj) prefetch_l2(&L[(size_t)i + (size_t)(j0 + 32 + jj) * d]);
+    }
     __syncthreads();
     if (warp == b) {
       // diagonal block: the lane's row of a L goes to shared memory (the register budget at 1024 threads per CTA is 64)

@@ -13,7 +13,11 @@ def _run(gamc, n, nchains, nsteps, burnin, init_scale, seed, update=None, max_fa
     import oracle as o
     from oracle import targets as T
     rng = np.random.default_rng(seed)
-    v0 = init_scale * rng.standard_normal((nchains, n))
+    if init_scale is None:          # the typical set of the target: x ~ N(0, Sigma) -- softabs then changes a single eigenvalue
+        idx = np.arange(n)
+        v0 = rng.multivariate_normal(np.zeros(n), 0.9 ** np.abs(idx[:, None] - idx[None, :]), size=nchains)
+    else:
+        v0 = init_scale * rng.standard_normal((nchains, n))
     sampler = gamc.GAMC(update=update if update is not None else gamc.rand_exp_decay_update(10.0), transform=gamc.softabs(1000.0),
                         driftstep=0.02, minorscale=0.001, c=0.01)
     tuner = gamc.GAMCTuner(gamc.VanillaMCTuner(), gamc.VanillaMCTuner(), gamc.AcceptanceRateMCTuner(0.35))
@@ -33,7 +37,7 @@ def _run(gamc, n, nchains, nsteps, burnin, init_scale, seed, update=None, max_fa
     return job, chains, outs
 
 
-@pytest.mark.parametrize("n,nsteps,init_scale", [(40, 600, 2.0), (64, 500, 1.0), (130, 400, 2.0), (256, 300, 1.0)])
+@pytest.mark.parametrize("n,nsteps,init_scale", [(40, 600, 2.0), (64, 500, 1.0), (130, 400, 2.0), (256, 300, 1.0), (96, 500, None), (300, 250, None)])
 def test_bigd_trajectory_parity(gamc, n, nsteps, init_scale):
     """Step-for-step agreement with the dense oracle; N(0, 2^2) initial values (the reference's, simulations.jl:57) put many
     eigenvalues of the tensor below 21/alpha, so the softabs correction has tens of columns (several product factors at n = 130)."""
@@ -42,6 +46,8 @@ def test_bigd_trajectory_parity(gamc, n, nsteps, init_scale):
         assert np.array_equal(chains[c].diagnosticvalues.ravel(), a), f"chain {c}: accept/reject decisions diverged"
         assert relerr(chains[c].value, v) <= 1e-6
         st, th = job.engine.bigd_state(c)
+        if init_scale is None:
+            assert st.error_pivot <= 3          # few eigenvalues changed by softabs: the four-column code paths ran
         assert st.count == nsteps and st.updatetensorcount == osam.updatetensorcount
         assert abs(st.step - osam.tune.totaltune.step) <= 1e-12 * osam.tune.totaltune.step
         assert abs(st.logtarget - osam.logtarget) <= 1e-8 * abs(osam.logtarget)

@@ -39,3 +39,18 @@ def test_all_ranks_parity():
         pytest.skip("needs four or more GPUs")
     out = _torchrun(n, "parity", 29534)
     assert out.returncode == 0 and "PASS" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
+
+
+def test_chains_sharded_across_ranks():
+    """SURVEY 8e, independent chains: every rank owns a block of chains, no collective; the device random streams are keyed by the
+    GLOBAL chain index, so ranks draw distinct numbers (tools/bench_c4.py asserts it) and the aggregate rate is the sum."""
+    import json
+    if _ngpus() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29535",
+           os.path.join(ROOT, "tools", "bench_c4.py"), "--dim", "64", "--chains", "16", "--steps", "40", "--cpu-steps", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["n_gpus"] == 2 and d["value"] > 0 and "chains sharded x2" in d["config"]["parallelism"]
