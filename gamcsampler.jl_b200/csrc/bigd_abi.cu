@@ -14,7 +14,7 @@ using namespace gamc;
 namespace {
 struct BigdExt {
   BdCfg cfg{}; long long chain_offset = 0; bool target = false, ready = false;
-  double* d_const = nullptr;     // [td | te | ld | le | rld]
+  double* d_const = nullptr;     // [td | te | ld | le | rld | poles]
   double* d_vecs = nullptr; double* d_scal = nullptr; double* d_W = nullptr; double* d_B = nullptr; double* d_delta = nullptr; double* d_S = nullptr;
   double* d_L = nullptr; double* d_rdiag = nullptr; double* d_chain = nullptr; unsigned char* d_accept = nullptr;
   double* d_tape = nullptr; long long tape_doubles = 0;
@@ -76,8 +76,8 @@ gamc_status gamc_bigd_target_mvt(gamc_handle hh, int32_t n, double nu, const dou
   free_run_state(x);
   cudaFree(x->d_const); x->d_const = nullptr; x->target = false;
   // bidiagonal Cholesky factor of the index-reversed tridiagonal (host, O(n), once)
-  std::vector<double> c(5 * (size_t)n, 0.0);
-  double* td = c.data(); double* te = td + n; double* ld = te + n; double* le = ld + n; double* rld = le + n;
+  std::vector<double> c(6 * (size_t)n, 0.0);
+  double* td = c.data(); double* te = td + n; double* ld = te + n; double* le = ld + n; double* rld = le + n; double* poles = rld + n;
   for (int i = 0; i < n; ++i) td[i] = tdiag[i];
   for (int i = 0; i + 1 < n; ++i) te[i] = toff[i];
   auto tdm = [&](int i) { return td[n - 1 - i]; };
@@ -92,13 +92,37 @@ gamc_status gamc_bigd_target_mvt(gamc_handle hh, int32_t n, double nu, const dou
     const double off = (i > 0 ? fabs(te[i - 1]) : 0.0) + (i + 1 < n ? fabs(te[i]) : 0.0);
     glo = std::min(glo, td[i] - off); ghi = std::max(ghi, td[i] + off);
   }
+  // eigenvalues of T, ascending, by bisection on the Sturm count (host, O(n^2), once): the poles of the secular function
+  {
+    auto count_below = [&](double mu) {
+      int neg = 0;
+      double D = td[0] - mu;
+      if (fabs(D) < 1e-290) D = -1e-290;
+      neg += D < 0.0;
+      for (int i = 1; i < n; ++i) {
+        D = (td[i] - mu) - te[i - 1] * te[i - 1] / D;
+        if (fabs(D) < 1e-290) D = -1e-290;
+        neg += D < 0.0;
+      }
+      return neg;
+    };
+    for (int k = 0; k < n; ++k) {
+      double lo = glo - 1e-3 * std::max(1.0, fabs(glo)), hi = ghi + 1e-3 * std::max(1.0, fabs(ghi));
+      if (k > 0) lo = poles[k - 1];
+      for (int it = 0; it < 200 && hi - lo > 2e-16 * std::max(fabs(lo), fabs(hi)); ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (count_below(mid) >= k + 1) hi = mid; else lo = mid;
+      }
+      poles[k] = 0.5 * (lo + hi);
+    }
+  }
   CUDA_TRY(h, cudaMalloc(&x->d_const, sizeof(double) * c.size()));
   CUDA_TRY(h, cudaMemcpyAsync(x->d_const, c.data(), sizeof(double) * c.size(), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   BdCfg& C = x->cfg;
   C = BdCfg{};
   C.d = n; C.nu = nu;
-  C.td = x->d_const; C.te = C.td + n; C.ld = C.te + n; C.le = C.ld + n; C.rld = C.le + n;
+  C.td = x->d_const; C.te = C.td + n; C.ld = C.te + n; C.le = C.ld + n; C.rld = C.le + n; C.poles = C.rld + n;
   C.sumlog_ld = sumlog; C.gersh_lo = glo; C.gersh_hi = ghi;
   // logpdf(MvTDist(nu, 0, Sigma_t), x) = logconst - (nu+n)/2 log1p(x'Tx/nu);  -1/2 logdet Sigma_t = +1/2 logdet T = sum log ld
   C.logconst = lgamma((nu + n) / 2.0) - lgamma(nu / 2.0) - 0.5 * n * log(nu * M_PI) + sumlog;
