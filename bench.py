@@ -397,12 +397,23 @@ def run_ours(args):
             roofs["loglik_grad"] = {"bound": "hbm", "achieved": bytes_lg / (ms_lg / n_lg * 1e-3) * 1e-9 if n_lg else None, "peak": hbm_peak, "unit": "GB/s",
                                     "traffic": None, "kernel": "k_datapass<loglik+grad+weights> (SMMALA step)", "launches": n_lg,
                                     "avg_ms": ms_lg / n_lg if n_lg else None, "algorithmic_bytes": bytes_lg, "peak_source": hbm_src}
-            peak64 = dmma_peak if dmma_peak and dmma_peak > 1.0 else FP64_DMMA_PEAK_TFLOPS_FALLBACK
+            # DMMA and DFMA run on the same FP64 pipe at the same 32 flop / cycle / partition: the larger of the two register-only probes is
+            # the pipe's rate on this device (on some boxes the DMMA loop alone is clipped by the power cap and reads ~30 instead of 37)
+            probe = max(dmma_peak or 0.0, dfma_peak or 0.0)
+            peak64 = probe if probe > 1.0 else FP64_DMMA_PEAK_TFLOPS_FALLBACK
+            # p <= 256: the level-2 evaluation is ONE profiling scope -- k_datapass_co (log-lik + gradient + weights) runs at the same time as
+            # the metric kernel on the same SMs (one pass over X out of HBM); its 4 N p flops (eta and gradient) are part of the scope
+            co_pair = (n_lg == 0 and n_mt > 0)
+            if co_pair:
+                flops_mt += 4.0 * Nloc * p
             roofs["metric"] = {"bound": "tensor", "achieved": flops_mt / (ms_mt / n_mt * 1e-3) * 1e-12 if n_mt else None, "peak": peak64, "unit": "TFLOP/s",
-                               "traffic": None, "kernel": "k_metric (FP64 DMMA weighted SYRK)", "launches": n_mt, "avg_ms": ms_mt / n_mt if n_mt else None,
+                               "traffic": None,
+                               "kernel": ("k_datapass_co || k_metric_t<2,true>: whole level-2 evaluation (log-lik, gradient, weights + FP64 DMMA weighted SYRK), "
+                                          "the two kernels co-scheduled on every SM" if co_pair else "k_metric (FP64 DMMA weighted SYRK)"),
+                               "launches": n_mt, "avg_ms": ms_mt / n_mt if n_mt else None,
                                "algorithmic_flops": flops_mt, "full_gemm_flops": 2.0 * Nloc * p * p,
-                               "peak_source": "register-only DMMA.8x8x4 loop on all SMs, measured in this run by gamc_probe_fp64_peak "
-                                              f"(DFMA loop: {dfma_peak:.1f} TFLOP/s); tcgen05 has no FP64 kind" if dmma_peak and dmma_peak > 1.0
+                               "peak_source": "FP64 pipe rate measured in this run by gamc_probe_fp64_peak = max of the register-only DMMA.8x8x4 loop "
+                                              f"({dmma_peak:.1f}) and the DFMA loop ({dfma_peak:.1f} TFLOP/s) on all SMs; tcgen05 has no FP64 kind" if probe > 1.0
                                               else "fallback: profiles/r01_fp64_peak.txt"}
             for r in roofs.values():
                 if r["achieved"]:
@@ -442,6 +453,36 @@ def run_ours(args):
 
     c2 = timed_job("c2", args.logN, args.p, K, W, True, not args.no_e2e)
     N, p = 1 << args.logN, args.p
+    # ---- the two kernels of the level-2 evaluation one after the other (GAMC_LEVEL2_CO=0), for the record: what the co-scheduled pair is
+    # measured against, and the metric kernel's own roofline fraction when it has the SM to itself
+    level2_serial = None
+    if p <= 256 and c2.get("roofline", {}).get("launches"):
+        try:
+            os.environ["GAMC_LEVEL2_CO"] = "0"
+            r0_, r1_ = shard_rows(N, world, rank)
+            tt_, th0_ = theta_inputs(p)
+            eng.target_logistic_synth(SEED, r0_, r1_ - r0_, p, tt_, LAMBDA)
+            for _ in range(2):
+                eng.eval_partials(th0_)
+            eng.profile_enable(True)
+            eng.profile_reset()
+            for i in range(6):
+                eng.eval_partials(th0_ + 1e-3 * i)
+            eng.sync()
+            prof_s = eng.profile_get()
+            eng.profile_enable(False)
+            ms_dp = prof_s["loglik_grad"][1] / max(prof_s["loglik_grad"][0], 1)
+            ms_mt = prof_s["metric"][1] / max(prof_s["metric"][0], 1)
+            pk = c2["roofline"]["peak"]
+            fl = float(r1_ - r0_) * p * (p + 1)
+            level2_serial = {"ms_datapass_grad": ms_dp, "ms_metric": ms_mt, "ms_level2": ms_dp + ms_mt, "ms_level2_co_scheduled": c2["roofline"]["avg_ms"],
+                             "metric_alone_tflops": fl / (ms_mt * 1e-3) * 1e-12, "metric_alone_frac": fl / (ms_mt * 1e-3) * 1e-12 / pk,
+                             "what": "k_datapass<grad> then k_metric_t<3,false> (GAMC_LEVEL2_CO=0), 6 evaluations of this rank's shard, CUDA events per launch"}
+        finally:
+            os.environ.pop("GAMC_LEVEL2_CO", None)
+            r0_, r1_ = shard_rows(N, world, rank)
+            tt_, th0_ = theta_inputs(p)
+            eng.target_logistic_synth(SEED, r0_, r1_ - r0_, p, tt_, LAMBDA)
     value, accept = c2.pop("_chain")
     make_job, tape, kinds, theta0 = c2.pop("_make_job"), c2.pop("_tape"), c2.pop("_kinds"), c2.pop("_theta0")
     timed_window = c2.pop("timed_window")
@@ -577,7 +618,7 @@ def run_ours(args):
             "final_step": c2["final_step"], "updatetensorcount": c2["updatetensorcount"],
             "gpu_launches": c2["gpu_launches"],
             "roofline": c2["roofline"], "roofline_others": c2["roofline_others"], "kernel_time_share": c2["kernel_time_share"],
-            "limiter": c2["limiter"], "fp64_probe": {"dmma_tflops": dmma_peak, "dfma_tflops": dfma_peak},
+            "limiter": c2["limiter"], "fp64_probe": {"dmma_tflops": dmma_peak, "dfma_tflops": dfma_peak}, "level2_serial": level2_serial,
             "parity": parity, "c3": c3, "weak": weak, "with_tensor_reuse": reuse,
             "clocks": clk, "e2e": e2e, "cpu_baseline": cpu,
         }

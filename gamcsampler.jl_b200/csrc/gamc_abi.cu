@@ -81,6 +81,9 @@ struct gamc_ctx : gamc_ctx_base {
   int dp_rpl = 1, dp_nu = 0, dp_grid = 0, dp_grid_now = 0, part_g_stride = 0;   // dp_grid_now: grid of the current evaluation (am_mode 2 leaves SMs free)
   CUtensorMap mapXA{}, mapXB{}, mapW{}, mapY{};
   bool metric_fused = false; MetricPlan* d_plans_fused = nullptr;   // level-2 evaluation in one pass (k_metric_fused), p <= 256
+  // level-2 evaluation as ONE pass over X out of HBM: k_datapass_co and the metric kernel run at the same time (p <= 256)
+  bool level2_co = false; unsigned long long* d_co_flags = nullptr; unsigned co_epoch = 0; long long co_lag_rows = 0;
+  unsigned long long* d_co_dbg = nullptr;   // GAMC_CO_DEBUG=1: time stamps and CTA placement of the pair, printed by gamc_eval_upto_tensor
   double* part_ll = nullptr; double* part_g = nullptr;
   // metric
   MetricLayout layout; MetricPlan* d_plans = nullptr; TaskCoord* d_coords = nullptr;
@@ -181,6 +184,8 @@ void free_target(gamc_ctx* h) {
   cudaFree(h->dw); h->dw = nullptr;
   cudaFree(h->part_ll); cudaFree(h->part_g); h->part_ll = h->part_g = nullptr;
   cudaFree(h->d_plans_fused); h->d_plans_fused = nullptr; h->metric_fused = false;
+  cudaFree(h->d_co_flags); h->d_co_flags = nullptr; h->level2_co = false;
+  cudaFree(h->d_co_dbg); h->d_co_dbg = nullptr;
   cudaFree(h->d_plans); cudaFree(h->d_coords); cudaFree(h->ws); cudaFree(h->d_ints); h->d_plans = nullptr; h->d_coords = nullptr; h->ws = nullptr; h->d_ints = nullptr;
   cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0; h->R = nullptr; h->vecs = h->mats = nullptr; h->d_state = nullptr;
   cudaFree(h->theta_eval); h->theta_eval = nullptr;
@@ -357,12 +362,61 @@ gamc_status launch_datapass(gamc_ctx* h, const double* theta, bool grad, const i
 }
 
 gamc_status launch_metric(gamc_ctx* h, const int* skip = nullptr) {
-  { gamc_status s = ensure_attr(h, (const void*)k_metric, sizeof(MetricSmem)); if (s != GAMC_OK) return s; }
+  auto kern = k_metric_t<MT_NSTAGE, false>;
+  { gamc_status s = ensure_attr(h, (const void*)kern, sizeof(MetricSmem)); if (s != GAMC_OK) return s; }
   ProfScope ps(h, GAMC_K_METRIC);
-  k_metric<<<h->metric_grid, MT_THREADS, sizeof(MetricSmem), h->stream>>>(h->mapXB, h->mapW, h->d_plans, h->d_cta_kind, h->d_cta_split,
-                                                                        h->d_kind_nsplit, h->nslabs, h->ws, h->layout.max_nsplit, skip);
+  kern<<<h->metric_grid, MT_THREADS, sizeof(MetricSmem), h->stream>>>(h->mapXB, h->mapW, h->d_plans, h->d_cta_kind, h->d_cta_split,
+                                                                    h->d_kind_nsplit, h->nslabs, h->ws, h->layout.max_nsplit, skip, MetricCo{});
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
+}
+
+// Level-2 evaluation with ONE pass over X out of HBM: the data pass (log-likelihood, gradient, weights; HBM-bound, ~2 % of the FP64
+// pipe) and the metric pass (FP64-tensor-bound, HBM nearly idle) run at the same time, one CTA of each per SM; the metric kernel
+// is launched with programmatic stream serialisation so that it starts as soon as every data-pass CTA is resident, takes the
+// weights of a slab when the data pass has published them, and re-reads the slab's rows of X from L2 (the data pass is throttled
+// to stay co_lag_rows ahead at most).  One profiling scope for the pair (events between the two launches would serialise them).
+template <int NU>
+gamc_status launch_level2_co_t(gamc_ctx* h, const double* theta, const int* skip) {
+  auto kd = k_datapass_co<NU>;
+  auto km = k_metric_t<MT_NSTAGE_CO, true>;
+  if (h->attr_set.find((const void*)kd) == h->attr_set.end()) {
+    // both kernels must fit one SM together: let each ask for the largest shared-memory carve-out
+    cudaFuncSetAttribute(kd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(km, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
+  { gamc_status s = ensure_attr(h, (const void*)kd, sizeof(DataPassCoSmem<NU>)); if (s != GAMC_OK) return s; }
+  { gamc_status s = ensure_attr(h, (const void*)km, sizeof(MetricSmemT<MT_NSTAGE_CO>)); if (s != GAMC_OK) return s; }
+  ProfScope ps(h, GAMC_K_METRIC);
+  h->launches += 1;   // two kernels in this scope
+  h->co_epoch += 1;
+  unsigned long long* progress = h->d_co_flags + 8;
+  unsigned long long* front = h->d_co_flags;
+  const int dgrid = h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid;
+  kd<<<dgrid, DPC_THREADS, sizeof(DataPassCoSmem<NU>), h->stream>>>(h->mapXA, h->dy, theta, h->p, h->N, h->dw, h->part_ll, h->part_g,
+      h->part_g_stride, skip, progress, h->co_lag_rows > 0 ? front : nullptr, h->co_epoch, h->co_lag_rows, h->d_co_dbg);
+  CUDA_TRY(h, cudaGetLastError());
+  MetricCo co{h->dw, progress, front, h->N, dgrid, h->co_epoch, h->d_co_dbg};
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)h->metric_grid); cfg.blockDim = dim3(MT_THREADS);
+  cfg.dynamicSmemBytes = sizeof(MetricSmemT<MT_NSTAGE_CO>); cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CUDA_TRY(h, cudaLaunchKernelEx(&cfg, km, h->mapXB, h->mapW, (const MetricPlan*)h->d_plans, (const int*)h->d_cta_kind, (const int*)h->d_cta_split,
+                                 (const int*)h->d_kind_nsplit, h->nslabs, h->ws, h->layout.max_nsplit, skip, co));
+  return GAMC_OK;
+}
+
+gamc_status launch_level2_co(gamc_ctx* h, const double* theta, const int* skip) {
+  switch (h->dp_nu) {
+    case 1: return launch_level2_co_t<1>(h, theta, skip);
+    case 2: return launch_level2_co_t<2>(h, theta, skip);
+    case 3: return launch_level2_co_t<3>(h, theta, skip);
+    case 4: return launch_level2_co_t<4>(h, theta, skip);
+    default: h->err = "co-scheduled level-2 evaluation needs p <= 256"; return GAMC_UNSUPPORTED_SHAPE;
+  }
 }
 
 // Level-2 evaluation in one pass over X (k_metric_fused): log-likelihood and gradient partials per metric CTA, metric tiles.
@@ -406,6 +460,7 @@ gamc_status eval_callback(gamc_ctx* h, const double* d_theta, int level) {
 // otherwise the gradient pass followed by the metric pass.
 gamc_status launch_level2(gamc_ctx* h, const double* d_theta, const int* skip = nullptr) {
   if (h->metric_fused) return launch_metric_fused(h, d_theta, skip);
+  if (h->level2_co) return launch_level2_co(h, d_theta, skip);
   gamc_status s = launch_datapass(h, d_theta, true, skip);
   if (s != GAMC_OK) return s;
   return launch_metric(h, skip);
@@ -537,6 +592,28 @@ gamc_status setup_target(gamc_ctx* h) {
       if (sy != GAMC_OK) return sy;
     }
   }
+  {
+    // co-scheduled level-2 evaluation (default for p <= 256; GAMC_LEVEL2_CO=0 keeps the two passes one after the other).
+    // GAMC_CO_LAG_MB: how far (in bytes of X) the data pass may run ahead of the metric sweep; 0 = no throttle.
+    const char* e = getenv("GAMC_LEVEL2_CO");
+    h->level2_co = !h->metric_fused && h->dp_rpl == 1 && h->dp_nu <= 4 && !(e && atoi(e) == 0);
+    if (h->level2_co) {
+      const char* lg = getenv("GAMC_CO_LAG_MB");
+      const double lag_mb = lg ? atof(lg) : 48.0;
+      h->co_lag_rows = (long long)(lag_mb * 1048576.0 / (8.0 * p));
+      // a metric CTA sweeps every nsplit-th slab, so the frontier moves in steps of nsplit slabs: a smaller lag would make the two kernels wait for each other
+      if (h->co_lag_rows > 0) h->co_lag_rows = std::max<long long>(h->co_lag_rows, (long long)MT_SLAB * (h->layout.max_nsplit + 1) + 64);
+      CUDA_TRY(h, cudaMalloc(&h->d_co_flags, sizeof(unsigned long long) * (8 + h->num_sms)));
+      CUDA_TRY(h, cudaMemsetAsync(h->d_co_flags, 0, sizeof(unsigned long long) * (8 + h->num_sms), h->stream));
+      h->co_epoch = 0;
+      if (getenv("GAMC_CO_DEBUG")) {
+        CUDA_TRY(h, cudaMalloc(&h->d_co_dbg, sizeof(unsigned long long) * 1024));
+        std::vector<unsigned long long> z(1024, 0ull);
+        z[0] = ~0ull; z[2] = ~0ull;
+        CUDA_TRY(h, cudaMemcpy(h->d_co_dbg, z.data(), sizeof(unsigned long long) * 1024, cudaMemcpyHostToDevice));
+      }
+    }
+  }
   CUDA_TRY(h, cudaMalloc(&h->d_coords, sizeof(TaskCoord) * h->ntasks));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_coords, h->layout.coords.data(), sizeof(TaskCoord) * h->ntasks, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMalloc(&h->ws, sizeof(double) * (size_t)h->layout.max_nsplit * h->ntasks * MT_BLK * MT_BLK));
@@ -544,11 +621,49 @@ gamc_status setup_target(gamc_ctx* h) {
 }
 
 
+// hand-over error word of the co-scheduled level-2 evaluation (after a stream synchronisation)
+gamc_status check_co_error(gamc_ctx* h) {
+  if (!h->level2_co || !h->d_co_flags) return GAMC_OK;
+  unsigned long long w = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&w, h->d_co_flags + 1, sizeof(w), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (w) { h->err = "co-scheduled level-2 evaluation: the metric kernel timed out waiting for the data pass"; return GAMC_CUDA_ERROR; }
+  return GAMC_OK;
+}
+
+// GAMC_CO_DEBUG=1: when and where the CTAs of the last co-scheduled pair ran (stderr), then re-arm the stamps
+void co_debug_report(gamc_ctx* h) {
+  std::vector<unsigned long long> d(1024);
+  cudaMemcpy(d.data(), h->d_co_dbg, sizeof(unsigned long long) * 1024, cudaMemcpyDeviceToHost);
+  if (d[0] != ~0ull && d[2] != ~0ull) {
+    int max_dp = 0, max_mt = 0, both = 0, sms = 0;
+    for (int i = 0; i < 512; ++i) {
+      const int ndp = (int)(d[8 + i] & 0xffffffffull), nmt = (int)(d[8 + i] >> 32);
+      max_dp = std::max(max_dp, ndp); max_mt = std::max(max_mt, nmt); both += (ndp > 0 && nmt > 0); sms += (ndp > 0 || nmt > 0);
+    }
+    int occ_dp = -1, occ_mt = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dp, k_datapass_co<4>, DPC_THREADS, sizeof(DataPassCoSmem<4>));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mt, k_metric_t<MT_NSTAGE_CO, true>, MT_THREADS, sizeof(MetricSmemT<MT_NSTAGE_CO>));
+    fprintf(stderr, "[co] data pass runs %.1f us; first metric CTA starts %+.1f us after the first data-pass CTA; SMs used %d, with both kernels %d, "
+                    "max CTAs per SM: data pass %d, metric %d; occupancy alone: %d / %d\n",
+            (d[1] - d[0]) * 1e-3, ((double)d[2] - (double)d[0]) * 1e-3, sms, both, max_dp, max_mt, occ_dp, occ_mt);
+    if (d[4] && d[5] && d[6])
+      fprintf(stderr, "[co] data-pass CTA 0 reaches 25 / 50 / 75 %% of its row blocks at +%.0f / +%.0f / +%.0f us\n",
+              ((double)d[4] - (double)d[0]) * 1e-3, ((double)d[5] - (double)d[0]) * 1e-3, ((double)d[6] - (double)d[0]) * 1e-3);
+  }
+  std::vector<unsigned long long> z(1024, 0ull);
+  z[0] = ~0ull; z[2] = ~0ull;
+  cudaMemcpy(h->d_co_dbg, z.data(), sizeof(unsigned long long) * 1024, cudaMemcpyHostToDevice);
+}
+
 gamc_status check_device_error(gamc_ctx* h) {
-  if (!h->B.st) return GAMC_OK;
+  if (!h->B.st) return check_co_error(h);
   DevState st;
+  unsigned long long co_word = 0;
+  if (h->level2_co && h->d_co_flags) CUDA_TRY(h, cudaMemcpyAsync(&co_word, h->d_co_flags + 1, sizeof(co_word), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(&st, h->B.st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (co_word) { h->err = "co-scheduled level-2 evaluation: the metric kernel timed out waiting for the data pass"; return GAMC_CUDA_ERROR; }
   h->chain_saved_seen = st.chain_saved;
   if (st.error_flag == GAMC_NONFINITE_INIT) {
     h->err = "Log-target, gradient or tensor of log-target not finite: initial values out of support";
@@ -954,7 +1069,8 @@ static gamc_status eval_host(gamc_handle h, const double* theta, int level, bool
   if (grad && level >= 1) CUDA_TRY(h, cudaMemcpyAsync(grad, h->R + 1, sizeof(double) * p, cudaMemcpyDeviceToHost, h->stream));
   if (G && level >= 2) CUDA_TRY(h, cudaMemcpyAsync(G, h->R + h->goff, sizeof(double) * (size_t)p * p, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  return GAMC_OK;
+  if (level >= 2 && h->d_co_dbg) co_debug_report(h);
+  return level >= 2 ? check_co_error(h) : GAMC_OK;
 }
 
 gamc_status gamc_eval_logtarget(gamc_handle h, const double* theta, double* logtarget) {

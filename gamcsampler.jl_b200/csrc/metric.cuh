@@ -43,13 +43,17 @@ struct MetricPlan {
   int task_diag[MT_MAXT];
 };
 
-struct MetricSmem {
-  alignas(128) double slab[MT_NSTAGE][MT_MAXS][MT_SLOT_DOUBLES];
-  alignas(128) double w[MT_NSTAGE][(MT_SLAB + 15) / 16 * 16];
-  alignas(8) uint64_t full_bar[MT_NSTAGE];
-  alignas(8) uint64_t empty_bar[MT_NSTAGE];
+constexpr int MT_WPAD = (MT_SLAB + 15) / 16 * 16;
+template <int NS>
+struct MetricSmemT {
+  alignas(128) double slab[NS][MT_MAXS][MT_SLOT_DOUBLES];
+  alignas(128) double w[NS][MT_WPAD];
+  alignas(8) uint64_t full_bar[NS];
+  alignas(8) uint64_t empty_bar[NS];
   MetricPlan plan;
 };
+using MetricSmem = MetricSmemT<MT_NSTAGE>;
+constexpr int MT_NSTAGE_CO = 2;              // stages of the co-scheduled variant (shares the SM with k_datapass_co)
 
 template <bool DIAG>
 __device__ __forceinline__ void metric_slab(const double* __restrict__ A, const double* __restrict__ B,
@@ -74,15 +78,38 @@ __device__ __forceinline__ void metric_slab(const double* __restrict__ A, const 
   }
 }
 
+// Hand-over block of the co-scheduled variant (CO): the weights of a slab come from k_datapass_co, which runs at the same time.
+struct MetricCo {
+  const double* w;                         // weights sigma (1 - sigma), written by k_datapass_co during this kernel
+  const unsigned long long* dp_progress;   // [dp_grid] (epoch << 32 | 32-row blocks finished by data-pass CTA c; it owns blocks c, c + dp_grid, ...)
+  unsigned long long* mt_front;            // (epoch << 32 | first row not yet swept by the most advanced metric CTA): the data pass throttles on it; [1] = hand-over error word
+  long long N;
+  int dp_grid;
+  unsigned epoch;
+  unsigned long long* dbg;                 // GAMC_CO_DEBUG: time stamps / CTA placement (else null)
+};
+
+// NS = pipeline stages.  CO = false: the weights are a finished vector (TMA, mapW).  CO = true: launched with programmatic
+// stream serialisation right after k_datapass_co and running next to it; the producer warp waits until the data pass has
+// published the row blocks of a slab, copies the slab's weights to shared memory itself (L2 loads: they were written by other
+// SMs during this kernel) and then issues the TMA loads of X; the kernel ends with griddepcontrol.wait, so it cannot complete
+// before the data pass has.
+template <int NS, bool CO>
 __global__ void __launch_bounds__(MT_THREADS, 1)
-k_metric(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
-         const MetricPlan* __restrict__ plans, const int* __restrict__ cta_kind, const int* __restrict__ cta_split,
-         const int* __restrict__ kind_nsplit, long long nslabs, double* __restrict__ ws, int max_nsplit, const int* skip_flag) {
+k_metric_t(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+           const MetricPlan* __restrict__ plans, const int* __restrict__ cta_kind, const int* __restrict__ cta_split,
+           const int* __restrict__ kind_nsplit, long long nslabs, double* __restrict__ ws, int max_nsplit, const int* skip_flag,
+           const MetricCo co) {
   if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;   // gamc_config.reuse_tensor
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  MetricSmem& S = *reinterpret_cast<MetricSmem*>(smem_raw);
+  MetricSmemT<NS>& S = *reinterpret_cast<MetricSmemT<NS>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kind = cta_kind[blockIdx.x], split = cta_split[blockIdx.x], nsplit = kind_nsplit[kind];
+  if (CO && co.dbg && tid == 0) {
+    unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    atomicMin(&co.dbg[2], global_timer_ns());
+    atomicAdd(&co.dbg[8 + smid], 1ull << 32);
+  }
 
   {
     const int* src = reinterpret_cast<const int*>(&plans[kind]);
@@ -91,31 +118,66 @@ k_metric(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
   }
   if (tid == 0) {
     const int nt = plans[kind].ntasks;   // only warps that own a task take part in the empty-barrier protocol
-    for (int s = 0; s < MT_NSTAGE; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], nt); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], nt); }
     mbar_fence_init();
   }
   __syncthreads();
   const int nslots = S.plan.nslots, ntasks = S.plan.ntasks;
 
   if (warp == MT_MAXT) {
-    if (lane == 0) {
-      tma_prefetch_desc(&mapX);
-      tma_prefetch_desc(&mapW);
+    if (!CO) {
+      if (lane == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapW);
+        unsigned it = 0;
+        for (long long slab = split; slab < nslabs; slab += nsplit, ++it) {
+          const unsigned st = it % NS, round = it / NS;
+          mbar_wait(&S.empty_bar[st], (round & 1) ^ 1);
+          mbar_arrive_expect_tx(&S.full_bar[st], (uint32_t)(nslots * MT_SLOT_DOUBLES * 8 + MT_SLAB * 8));
+          for (int s = 0; s < nslots; ++s)
+            tma_load_2d(S.slab[st][s], &mapX, &S.full_bar[st], (int)(slab * MT_SLAB), S.plan.slot_block[s] * MT_BLK);
+          tma_load_1d(S.w[st], &mapW, &S.full_bar[st], (int)(slab * MT_SLAB));
+        }
+      }
+    } else {
+      if (lane == 0) tma_prefetch_desc(&mapX);
       unsigned it = 0;
       for (long long slab = split; slab < nslabs; slab += nsplit, ++it) {
-        const unsigned st = it % MT_NSTAGE, round = it / MT_NSTAGE;
-        mbar_wait(&S.empty_bar[st], (round & 1) ^ 1);
-        mbar_arrive_expect_tx(&S.full_bar[st], (uint32_t)(nslots * MT_SLOT_DOUBLES * 8 + MT_SLAB * 8));
-        for (int s = 0; s < nslots; ++s)
-          tma_load_2d(S.slab[st][s], &mapX, &S.full_bar[st], (int)(slab * MT_SLAB), S.plan.slot_block[s] * MT_BLK);
-        tma_load_1d(S.w[st], &mapW, &S.full_bar[st], (int)(slab * MT_SLAB));
+        const unsigned st = it % NS, round = it / NS;
+        if (lane == 0) mbar_wait(&S.empty_bar[st], (round & 1) ^ 1);
+        __syncwarp();
+        const long long r0 = slab * MT_SLAB;
+        const long long r1 = (r0 + MT_SLAB < co.N ? r0 + MT_SLAB : co.N) - 1;
+        // the 32-row blocks of the data pass that cover rows r0..r1 (at most three): one lane polls each
+        for (long long rb = (r0 >> 5) + lane; rb <= (r1 >> 5); rb += 32) {
+          const unsigned long long need = ((unsigned long long)co.epoch << 32) | (unsigned long long)(rb / co.dp_grid + 1);
+          const unsigned long long* flag = co.dp_progress + (rb % co.dp_grid);
+          if (ld_acquire_u64(flag) < need) {
+            // bounded (the data pass is resident before this kernel starts and never waits for it without a time limit, so this
+            // only trips on a programming error): raise the hand-over error word instead of hanging the device
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_u64(flag) < need) {
+              if (global_timer_ns() - t0 > 4000000000ull) { co.mt_front[1] = 1ull; break; }
+              __nanosleep(64);
+            }
+          }
+        }
+        __syncwarp();
+        for (int i = lane; i < MT_WPAD; i += 32) S.w[st][i] = (i < MT_SLAB && r0 + i < co.N) ? __ldcg(&co.w[r0 + i]) : 0.0;
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&S.full_bar[st], (uint32_t)(nslots * MT_SLOT_DOUBLES * 8));
+          for (int s = 0; s < nslots; ++s)
+            tma_load_2d(S.slab[st][s], &mapX, &S.full_bar[st], (int)(slab * MT_SLAB), S.plan.slot_block[s] * MT_BLK);
+        }
       }
+      asm volatile("griddepcontrol.wait;" ::: "memory");
     }
     return;
   }
 
   // consumer warps (one task each); surplus warps of a partially filled kind retire
-  if (warp >= ntasks) return;
+  if (warp >= ntasks) { if (CO) asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
   const int sa = S.plan.task_sa[warp], sb = S.plan.task_sb[warp];
   const bool diag = S.plan.task_diag[warp] != 0;
   double acc[4][4][2];
@@ -126,12 +188,18 @@ k_metric(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
 
   unsigned it = 0;
   for (long long slab = split; slab < nslabs; slab += nsplit, ++it) {
-    const unsigned st = it % MT_NSTAGE, round = it / MT_NSTAGE;
+    const unsigned st = it % NS, round = it / NS;
     mbar_wait(&S.full_bar[st], round & 1);
     if (diag) metric_slab<true>(S.slab[st][sa], S.slab[st][sb], S.w[st], lane, acc);
     else      metric_slab<false>(S.slab[st][sa], S.slab[st][sb], S.w[st], lane, acc);
     __syncwarp();
-    if (lane == 0) mbar_arrive(&S.empty_bar[st]);
+    if (lane == 0) {
+      mbar_arrive(&S.empty_bar[st]);
+      if (CO && warp == 0) {   // sweep frontier (the most advanced metric CTA) for the data pass's throttle
+        const long long fr = (slab + 1) * MT_SLAB;
+        atomicMax(co.mt_front, ((unsigned long long)co.epoch << 32) | (unsigned long long)(fr < 0xffffffffll ? fr : 0xffffffffll));
+      }
+    }
   }
 
   {
@@ -146,6 +214,7 @@ k_metric(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         *reinterpret_cast<double2*>(&out[(mt * 8 + g) * MT_BLK + nt * 8 + 2 * c]) = v;
       }
   }
+  if (CO) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -330,3 +330,42 @@ def test_fused_level2_kernel_parity(gamc, engine, N, p, monkeypatch):
     assert abs(lt1 - ltr) <= 1e-10 * abs(ltr) and relerr(g1, gr) <= 1e-10 and relerr(G1, Gr) <= 1e-10
     assert abs(lt1 - lt0) <= 1e-12 * abs(lt0) and relerr(g1, g0) <= 1e-11 and relerr(G1, G0) <= 1e-12
     engine.target_logistic(X, y, 100.0)      # leave the engine on the default route
+
+
+@pytest.mark.parametrize("N,p", [(200, 4), (777, 33), (6000, 256), (5000, 130), (40000, 200), (31, 64), (36 * 148 * 3 + 5, 256), (100001, 96)])
+def test_coscheduled_level2_parity(gamc, engine, N, p, monkeypatch):
+    """Default level-2 evaluation for p <= 256: k_datapass_co and the metric kernel run at the same time (one pass over X out of
+    HBM, weights handed over through progress flags).  Against the oracle (1e-10), and against the two kernels run one after the
+    other (GAMC_LEVEL2_CO=0): equal to rounding (1e-13; the data pass that shares the SM with the metric kernel sums eta and the gradient in
+    a different order).  Repeated evaluations must give identical bits (deterministic); they also exercise the epoch
+    counter of the flags; GAMC_CO_LAG_MB=0.01 forces the data pass to throttle on the metric frontier, =0 switches the throttle off."""
+    o = _oracle()
+    X, y, tt = o.synth_logistic(78, N, p)
+    rng = np.random.default_rng(5)
+    thetas = [tt + 0.05 * rng.standard_normal(p) for _ in range(3)]
+    monkeypatch.setenv("GAMC_LEVEL2_CO", "0")
+    engine.target_logistic(X, y, 100.0)
+    serial = [engine.eval_upto_tensor(t) for t in thetas]
+    monkeypatch.delenv("GAMC_LEVEL2_CO")
+    tgt = o.LogisticTarget(X, y, 100.0)
+    for lag in (None, "0.01", "0"):
+        if lag is None:
+            monkeypatch.delenv("GAMC_CO_LAG_MB", raising=False)
+        else:
+            monkeypatch.setenv("GAMC_CO_LAG_MB", lag)
+        engine.target_logistic(X, y, 100.0)
+        first = {}
+        for rep in range(2):
+            for it, (t, (lt0, g0, G0)) in enumerate(zip(thetas, serial)):
+                lt1, g1, G1 = engine.eval_upto_tensor(t)
+                if rep == 0:
+                    first[it] = (lt1, g1, G1)
+                else:
+                    assert lt1 == first[it][0] and np.array_equal(g1, first[it][1]) and np.array_equal(G1, first[it][2])
+                assert abs(lt1 - lt0) <= 1e-13 * abs(lt0) and relerr(G1, G0) <= 1e-13 and np.array_equal(G1, G1.T)
+                assert relerr(g1, g0) <= 1e-13
+                if rep == 0 and lag is None:
+                    ltr, gr, Gr = tgt.uptotensorlogtarget(t)
+                    assert abs(lt1 - ltr) <= 1e-10 * abs(ltr) and relerr(g1, gr) <= 1e-10 and relerr(G1, Gr) <= 1e-10
+    monkeypatch.delenv("GAMC_CO_LAG_MB", raising=False)
+    engine.target_logistic(X, y, 100.0)      # leave the engine on the default route
