@@ -18,6 +18,7 @@
 #include "datapass.cuh"
 #include "metric.cuh"
 #include "metric_plan.h"
+#include "metric_i8_plan.h"
 #include "sampler.cuh"
 #include "synth.cuh"
 
@@ -85,6 +86,12 @@ struct gamc_ctx : gamc_ctx_base {
   bool level2_co = false; unsigned long long* d_co_flags = nullptr; unsigned co_epoch = 0; long long co_lag_rows = 0;
   unsigned long long* d_co_dbg = nullptr;   // GAMC_CO_DEBUG=1: time stamps and CTA placement of the pair, printed by gamc_eval_upto_tensor
   double* part_ll = nullptr; double* part_g = nullptr;
+  // metric on the integer tensor cores (metric_i8.cuh): digit planes of diag(sqrt w) X, column exponents, per-CTA partial tiles
+  bool metric_i8 = false; int i8_k = 0, i8_smax = 0, i8_grid = 0, i8_nchunks = 0, i8_ntiles = 0; long long i8_ldn = 0;
+  int8_t* d_i8S = nullptr; double *d_i8cs = nullptr, *d_i8cg = nullptr, *d_i8part = nullptr; unsigned long long* d_i8cmax = nullptr;
+  I8Kind* d_i8kinds = nullptr; int* d_i8ints = nullptr; CUtensorMap mapS{};
+  int *d_i8cta_kind = nullptr, *d_i8cta_split = nullptr, *d_i8kind_nsplit = nullptr, *d_i8tile_bi = nullptr, *d_i8tile_bj = nullptr,
+      *d_i8tile_off = nullptr, *d_i8tile_n = nullptr, *d_i8tile_ctas = nullptr;
   // metric
   MetricLayout layout; MetricPlan* d_plans = nullptr; TaskCoord* d_coords = nullptr;
   int nkinds = 0, ntasks = 0, metric_grid = 0; long long nslabs = 0; double* ws = nullptr; int* d_ints = nullptr;
@@ -186,6 +193,8 @@ void free_target(gamc_ctx* h) {
   cudaFree(h->d_plans_fused); h->d_plans_fused = nullptr; h->metric_fused = false;
   cudaFree(h->d_co_flags); h->d_co_flags = nullptr; h->level2_co = false;
   cudaFree(h->d_co_dbg); h->d_co_dbg = nullptr;
+  cudaFree(h->d_i8S); cudaFree(h->d_i8cs); cudaFree(h->d_i8cg); cudaFree(h->d_i8part); cudaFree(h->d_i8cmax); cudaFree(h->d_i8kinds); cudaFree(h->d_i8ints);
+  h->d_i8S = nullptr; h->d_i8cs = h->d_i8cg = h->d_i8part = nullptr; h->d_i8cmax = nullptr; h->d_i8kinds = nullptr; h->d_i8ints = nullptr; h->metric_i8 = false;
   cudaFree(h->d_plans); cudaFree(h->d_coords); cudaFree(h->ws); cudaFree(h->d_ints); h->d_plans = nullptr; h->d_coords = nullptr; h->ws = nullptr; h->d_ints = nullptr;
   cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0; h->R = nullptr; h->vecs = h->mats = nullptr; h->d_state = nullptr;
   cudaFree(h->theta_eval); h->theta_eval = nullptr;
@@ -429,11 +438,39 @@ gamc_status launch_metric_fused(gamc_ctx* h, const double* theta, const int* ski
   return GAMC_OK;
 }
 
+// Metric on the integer tensor cores: digit planes of diag(sqrt w) X (k_i8_slice, after the gradient pass has written w), then the
+// int8 GEMMs (k_metric_i8: TMA -> tcgen05.mma kind::i8 -> TMEM), partial tiles summed by k_reduce_i8 inside launch_reduce.
+gamc_status launch_metric_i8(gamc_ctx* h, const int* skip = nullptr) {
+  { gamc_status s = ensure_attr(h, (const void*)k_metric_i8, I8_SMEM_BYTES); if (s != GAMC_OK) return s; }
+  ProfScope ps(h, GAMC_K_METRIC);
+  h->launches += 1;   // two kernels in this scope
+  const dim3 sgrid((unsigned)((h->N + I8_SLICE_ROWS - 1) / I8_SLICE_ROWS), (unsigned)((h->p + I8_SLICE_COLS - 1) / I8_SLICE_COLS));
+  double bias = 0.0;
+  for (int i = 0; i + 1 < h->i8_k; ++i) bias += ldexp(128.0, 8 * i);
+  k_i8_slice<<<sgrid, 256, 0, h->stream>>>(h->dX, h->ld, h->dw, h->N, h->p, h->d_i8cs, h->i8_k, h->i8_ldn, h->d_i8S, bias, skip);
+  CUDA_TRY(h, cudaGetLastError());
+  k_metric_i8<<<h->i8_grid, I8_THREADS, I8_SMEM_BYTES, h->stream>>>(h->mapS, h->d_i8kinds, h->d_i8cta_kind, h->d_i8cta_split, h->d_i8kind_nsplit,
+                                                                    h->i8_nchunks, h->d_i8part, skip);
+  CUDA_TRY(h, cudaGetLastError());
+  return GAMC_OK;
+}
+
 // level: 0 = ll, 1 = ll + grad, 2 = ll + grad + metric
 gamc_status launch_reduce(gamc_ctx* h, int level, double* E = nullptr, const int* skip = nullptr) {
   ProfScope ps(h, GAMC_K_REDUCE);
   const int nblk = (level >= 2 ? h->ntasks * 4 : 0) + (level >= 1 ? (h->p + 31) / 32 : 0) + 1;   // tensor tiles | gradient column blocks | scalar
   const int nparts = (level >= 2 && h->metric_fused) ? h->metric_grid : (h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid);
+  if (level >= 2 && h->metric_i8) {
+    const int nb1 = (h->p + 31) / 32 + 1;
+    k_reduce<<<nb1, 256, 0, h->stream>>>(E ? E : h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, nparts, 1,
+                                         nullptr, h->d_coords, h->ntasks, h->d_task_nsplit, h->layout.max_nsplit, skip);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    k_reduce_i8<<<h->i8_ntiles * (I8_TILE * I8_TILE / 256), 256, 0, h->stream>>>(E ? E : h->R, h->p, h->goff, h->d_i8part, h->d_i8tile_bi, h->d_i8tile_bj,
+        h->d_i8tile_off, h->d_i8tile_n, h->d_i8tile_ctas, h->d_i8cg, skip);
+    CUDA_TRY(h, cudaGetLastError());
+    return GAMC_OK;
+  }
   k_reduce<<<nblk, 256, 0, h->stream>>>(E ? E : h->R, h->p, h->goff, h->part_ll, h->part_g, h->part_g_stride, nparts, level >= 1,
                                         level >= 2 ? h->ws : nullptr, h->d_coords, h->ntasks, h->d_task_nsplit, h->layout.max_nsplit, skip);
   CUDA_TRY(h, cudaGetLastError());
@@ -459,6 +496,11 @@ gamc_status eval_callback(gamc_ctx* h, const double* d_theta, int level) {
 // The kernels of a level-2 evaluation before the reduction: one fused pass when every CTA can hold complete rows (p <= 256),
 // otherwise the gradient pass followed by the metric pass.
 gamc_status launch_level2(gamc_ctx* h, const double* d_theta, const int* skip = nullptr) {
+  if (h->metric_i8) {
+    gamc_status s8 = launch_datapass(h, d_theta, true, skip);
+    if (s8 != GAMC_OK) return s8;
+    return launch_metric_i8(h, skip);
+  }
   if (h->metric_fused) return launch_metric_fused(h, d_theta, skip);
   if (h->level2_co) return launch_level2_co(h, d_theta, skip);
   gamc_status s = launch_datapass(h, d_theta, true, skip);
@@ -528,6 +570,8 @@ gamc_status alloc_arena(gamc_ctx* h) {
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return GAMC_OK;
 }
+
+gamc_status setup_metric_i8(gamc_ctx* h, int k, int smax);
 
 gamc_status setup_target(gamc_ctx* h) {
   const int p = h->p;
@@ -617,9 +661,66 @@ gamc_status setup_target(gamc_ctx* h) {
   CUDA_TRY(h, cudaMalloc(&h->d_coords, sizeof(TaskCoord) * h->ntasks));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_coords, h->layout.coords.data(), sizeof(TaskCoord) * h->ntasks, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMalloc(&h->ws, sizeof(double) * (size_t)h->layout.max_nsplit * h->ntasks * MT_BLK * MT_BLK));
+  if (const char* e8 = getenv("GAMC_METRIC_I8")) {
+    // GAMC_METRIC_I8 = "1" (6 digit planes, digit products with a + b <= 7) or "k,smax"
+    int k = 6, smax = 7;
+    if (sscanf(e8, "%d,%d", &k, &smax) < 2) { k = 6; smax = 7; }
+    if (atoi(e8) != 0) { gamc_status s8 = setup_metric_i8(h, k, smax); if (s8 != GAMC_OK) return s8; }
+  }
   return alloc_arena(h);
 }
 
+
+// Integer-tensor-core metric: column exponents of X (once), digit-plane buffer, tensor map, work plan.
+gamc_status setup_metric_i8(gamc_ctx* h, int k, int smax) {
+  const int p = h->p;
+  REQUIRE(h, k >= 2 && k <= I8_MAXK && smax >= 2 && smax <= 2 * k, GAMC_INVALID_ARG, "metric_i8: 2 <= slices <= 7, 2 <= smax <= 2 slices");
+  REQUIRE(h, h->N < (1ll << 31) - 256, GAMC_UNSUPPORTED_SHAPE, "metric_i8: too many rows for one rank");
+  h->i8_k = k; h->i8_smax = smax;
+  h->i8_ldn = (h->N + I8_KC - 1) / I8_KC * I8_KC;
+  h->i8_nchunks = (int)(h->i8_ldn / I8_KC);
+  CUDA_TRY(h, cudaMalloc(&h->d_i8S, (size_t)k * p * h->i8_ldn));
+  CUDA_TRY(h, cudaMalloc(&h->d_i8cs, sizeof(double) * p));
+  CUDA_TRY(h, cudaMalloc(&h->d_i8cg, sizeof(double) * p));
+  CUDA_TRY(h, cudaMalloc(&h->d_i8cmax, sizeof(unsigned long long) * p));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_i8cmax, 0, sizeof(unsigned long long) * p, h->stream));
+  {
+    const int ny = (int)std::max<long long>(1, std::min<long long>(64, (h->N + 4095) / 4096));
+    k_i8_colmax<<<dim3((unsigned)p, (unsigned)ny), 256, 0, h->stream>>>(h->dX, h->ld, h->N, p, h->d_i8cmax);
+    CUDA_TRY(h, cudaGetLastError());
+    k_i8_scales<<<(p + 127) / 128, 128, 0, h->stream>>>(h->d_i8cmax, p, 8 * k - 2, h->d_i8cs, h->d_i8cg);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  {
+    if (!ensure_encode(h)) return GAMC_CUDA_ERROR;
+    cuuint64_t dims[3] = {(cuuint64_t)h->N, (cuuint64_t)p, (cuuint64_t)k};
+    cuuint64_t strides[2] = {(cuuint64_t)h->i8_ldn, (cuuint64_t)h->i8_ldn * (cuuint64_t)p};
+    cuuint32_t box[3] = {(cuuint32_t)I8_KC, (cuuint32_t)I8_TILE, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = g_encode(&h->mapS, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)h->d_i8S, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled(digit planes) failed with code " + std::to_string((int)r); return GAMC_CUDA_ERROR; }
+  }
+  const I8Layout L = build_i8_layout(p, k, smax, h->num_sms, h->i8_nchunks);
+  h->i8_grid = (int)L.cta_kind.size();
+  h->i8_ntiles = (int)L.tile_bi.size();
+  {
+    std::vector<int> ints;
+    auto push = [&](const std::vector<int>& v) { size_t off = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); return off; };
+    const size_t o1 = push(L.cta_kind), o2 = push(L.cta_split), o3 = push(L.kind_nsplit), o4 = push(L.tile_bi), o5 = push(L.tile_bj),
+                 o6 = push(L.tile_off), o7 = push(L.tile_n), o8 = push(L.tile_ctas);
+    CUDA_TRY(h, cudaMalloc(&h->d_i8ints, sizeof(int) * ints.size()));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_i8ints, ints.data(), sizeof(int) * ints.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMalloc(&h->d_i8kinds, sizeof(I8Kind) * L.kinds.size()));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_i8kinds, L.kinds.data(), sizeof(I8Kind) * L.kinds.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->d_i8cta_kind = h->d_i8ints + o1; h->d_i8cta_split = h->d_i8ints + o2; h->d_i8kind_nsplit = h->d_i8ints + o3; h->d_i8tile_bi = h->d_i8ints + o4;
+    h->d_i8tile_bj = h->d_i8ints + o5; h->d_i8tile_off = h->d_i8ints + o6; h->d_i8tile_n = h->d_i8ints + o7; h->d_i8tile_ctas = h->d_i8ints + o8;
+  }
+  CUDA_TRY(h, cudaMalloc(&h->d_i8part, sizeof(double) * (size_t)h->i8_grid * I8_TILE * I8_TILE));
+  h->metric_i8 = true;
+  return GAMC_OK;
+}
 
 // hand-over error word of the co-scheduled level-2 evaluation (after a stream synchronisation)
 gamc_status check_co_error(gamc_ctx* h) {
@@ -1730,6 +1831,29 @@ long long gamc_debug_guard_check(long long* n_allocations) {
   return (long long)bad;
 }
 #endif
+
+// Debug read-out of the integer-tensor-core metric (tests/test_gpu_i8.py): what = 0: digit planes [k][p][ldn] int8 (as written by the last
+// level-2 evaluation), 1: column scales cg[p] (double), 2: {k, smax, ldn, grid} as four int64.  Not part of the public header.
+int gamc_debug_i8_read(gamc_handle h, int what, void* out, long long bytes) {
+  if (!h || !h->metric_i8) return 1;
+  cudaStreamSynchronize(h->stream);
+  if (what == 0) {
+    const long long need = (long long)h->i8_k * h->p * h->i8_ldn;
+    if (bytes < need) return 2;
+    return cudaMemcpy(out, h->d_i8S, (size_t)need, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 3;
+  }
+  if (what == 1) {
+    if (bytes < (long long)sizeof(double) * h->p) return 2;
+    return cudaMemcpy(out, h->d_i8cg, sizeof(double) * h->p, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 3;
+  }
+  if (what == 2) {
+    if (bytes < 32) return 2;
+    long long* o = reinterpret_cast<long long*>(out);
+    o[0] = h->i8_k; o[1] = h->i8_smax; o[2] = h->i8_ldn; o[3] = h->i8_grid;
+    return 0;
+  }
+  return 4;
+}
 
 #ifdef GAMC_PHASE_CLOCKS
 // Debug build only (make dbg): accumulated clock64 deltas / hit counts of the PHASE() marks; reset = 1 clears them.

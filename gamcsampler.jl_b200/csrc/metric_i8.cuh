@@ -1,0 +1,337 @@
+// metric_i8.cuh -- the Fisher metric  G_lik = X' diag(w) X  on the INTEGER tensor cores (tcgen05.mma kind::i8, TMEM
+// accumulators, TMA-fed), an error-free-transformation ("Ozaki") alternative to the FP64 DMMA kernel of metric.cuh.
+//
+// Replaces `broadcast(*, r.*(1-r), X)' * X` of examples/logistic_regression/src/GAMC/simulations.jl:36.
+//
+// FP64 has no tcgen05 kind, and the DMMA pipe bounds metric.cuh at 37 TFLOP/s.  Here S = diag(sqrt w) X is brought to
+// fixed point per column, S_nj = q_nj 2^(e_j - E) (E = 8 k - 2 bits, 2^e_j >= max_n |x_nj| / 2 >= max_n |S_nj| because
+// w = sigma (1 - sigma) <= 1/4), and q is cut into k signed base-256 digits d_1 (most significant) .. d_k in [-128, 127],
+// one int8 plane per digit.  Then, EXACTLY in integers,
+//     (S'S)_ij = 2^(e_i + e_j - 2E) sum_{a, b} 256^(2k - a - b) (D_a' D_b)_ij ,
+// and the products with a + b > smax are dropped (their weight is 2^(4 - 8 (a + b))).  With k = 6, smax = 7 (21 digit
+// products) the result agrees with the FP64 evaluation to 1e-13 of the largest entry (tests/test_gpu_i8.py, numpy
+// statement of the scheme in tests/i8_ref.py); the products themselves are exact, so the result does not depend on the
+// order of summation inside the tensor core.
+//
+// Kernels: k_i8_colmax / k_i8_scales (once per target: column exponents), k_i8_slice (per evaluation: digit planes of
+// diag(sqrt w) X, HBM-bound), k_metric_i8 (the int8 GEMMs: warp-specialised TMA producer / single-thread tcgen05.mma
+// issuer / TMEM epilogue), k_reduce_i8 (deterministic sum of the per-CTA partial tiles into the landing buffer).
+#pragma once
+#include "common.cuh"
+
+namespace gamc {
+
+constexpr int I8_TILE = 128;                       // columns of X per operand tile = edge of an output tile
+constexpr int I8_KC = 128;                         // rows (the contraction index) per chunk = one 128-byte swizzle row
+constexpr int I8_TILE_BYTES = I8_TILE * I8_KC;     // 16 KB
+constexpr int I8_MAXT = 6;                         // operand tiles per stage
+constexpr int I8_MAXP = 12;                        // digit products per kind
+constexpr int I8_MAXACC = 4;                       // accumulators of 128 TMEM columns: all 512 columns of the SM
+constexpr int I8_MAXK = 7;                         // digit planes
+constexpr int I8_SMEM_TILES = 13;                  // operand tiles resident per CTA (208 KB), cut into stages of the kind's ntiles
+constexpr int I8_MAXSTAGE = 8;
+constexpr int I8_THREADS = 192;                    // warps 0-3: epilogue (TMEM lane quarters 0-3); warp 4: TMA producer; warp 5: MMA issuer, TMEM allocator
+constexpr int I8_SLICE_ROWS = 128, I8_SLICE_COLS = 64;
+
+struct I8Kind {
+  int bi, bj;                  // output tile (column blocks of X), bi >= bj
+  int ntiles;                  // operand tiles per chunk
+  int tile_slice[I8_MAXT];     // digit plane (0 = most significant)
+  int tile_blk[I8_MAXT];       // column block
+  int npairs;
+  int pair_a[I8_MAXP], pair_b[I8_MAXP], pair_acc[I8_MAXP];   // operand tiles and accumulator of each digit product
+  int nacc;
+  int acc_sum[I8_MAXACC];      // a + b (1-based digits) of the products of accumulator g: weight 2^(4 - 8 (a + b))
+  int flush_chunks;            // chunks between two flushes of the int32 accumulators (head room of 2^31)
+};
+
+struct I8Ctl {
+  alignas(8) uint64_t full[I8_MAXSTAGE];
+  alignas(8) uint64_t empty[I8_MAXSTAGE];
+  alignas(8) uint64_t tmem_full, tmem_empty;
+  uint32_t tmem_base;
+  I8Kind kind;
+};
+constexpr size_t I8_SMEM_BYTES = (size_t)I8_SMEM_TILES * I8_TILE_BYTES + 1024 + sizeof(I8Ctl);
+
+// ---- tcgen05 / TMEM wrappers (SASS: UTCIMMA / UTCBAR / LDTM) ------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc_512(uint32_t* dst_smem) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(512u) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {    // whole warp (the allocating one)
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(512u) : "memory");
+}
+// mbarrier arrive once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]', int8 x int8 -> int32, M = 128, N = 128, K = 32 per instruction
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor of a K-major operand tile written by TMA with the 128-byte swizzle: rows of 128 bytes,
+// 8-row groups 1024 bytes apart (stride byte offset), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t tc_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed 8 bit (bits 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0),
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28
+__device__ __forceinline__ constexpr uint32_t tc_idesc_i8(int m, int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// ---- column exponents (once per target) ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_i8_colmax(const double* __restrict__ X, long long ld, long long N, int p,
+                                                   unsigned long long* __restrict__ cmax) {
+  const int j = blockIdx.x;
+  double m = 0.0;
+  for (long long r = (long long)blockIdx.y * 256 + threadIdx.x; r < N; r += (long long)gridDim.y * 256) m = fmax(m, fabs(X[r + (size_t)j * ld]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&cmax[j], (unsigned long long)__double_as_longlong(m));   // non-negative doubles order like their bit patterns
+}
+
+// cs[j] = 2^(E - e_j) (fixed-point scale of column j), cg[j] = 2^e_j, 2^e_j >= max|x_j| / 2
+__global__ void k_i8_scales(const unsigned long long* __restrict__ cmax, int p, int ebits, double* __restrict__ cs, double* __restrict__ cg) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p) return;
+  const double m = __longlong_as_double((long long)cmax[j]);
+  int e = 0;
+  if (m > 0.0 && isfinite(m)) { frexp(m, &e); e -= 1; }       // m = f 2^(e+1), f in [0.5, 1)  =>  2^e >= m / 2
+  cs[j] = ldexp(1.0, ebits - e);
+  cg[j] = ldexp(1.0, e);
+}
+
+// ---- digit planes of diag(sqrt w) X (per evaluation) -----------------------------------------------------------------------
+// Block = 128 rows x 64 columns; warp = 8 columns; lane = 4 consecutive rows: 1 KB coalesced loads of X per warp and column,
+// 128-byte coalesced stores per warp, column and plane.  q' = rint(x sqrt(w) 2^(E - e_j)) + B with B = sum_{i < k-1} 128 256^i:
+// the bytes of q' are the digits, offset by 128 except the top one (balanced digits without a carry chain).
+__global__ void __launch_bounds__(256)
+k_i8_slice(const double* __restrict__ X, long long ld, const double* __restrict__ w, long long N, int p, const double* __restrict__ cs,
+           int k, long long ldn, int8_t* __restrict__ S, double bias, const int* skip_flag) {
+  if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const long long r = (long long)blockIdx.x * I8_SLICE_ROWS + 4 * lane;
+  double sw[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) sw[u] = (r + u < N) ? sqrt(w[r + u]) : 0.0;
+  const int j0 = blockIdx.y * I8_SLICE_COLS + wq * 8;
+#pragma unroll 2
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = j0 + jj;
+    if (j >= p) break;
+    const double* col = X + (size_t)j * ld + r;
+    double x[4];
+    if (r + 3 < N) {
+      const double2 v0 = *reinterpret_cast<const double2*>(col), v1 = *reinterpret_cast<const double2*>(col + 2);
+      x[0] = v0.x; x[1] = v0.y; x[2] = v1.x; x[3] = v1.y;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = (r + u < N) ? col[u] : 0.0;
+    }
+    const double c = cs[j];
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long q = __double2ll_rn(fma(x[u] * sw[u], c, bias));
+      lo[u] = (uint32_t)q; hi[u] = (uint32_t)((unsigned long long)q >> 32);
+    }
+    for (int s = 0; s < k; ++s) {
+      const int b = k - 1 - s;                       // byte of q' that holds digit s + 1
+      const uint32_t sel = (uint32_t)(b & 3) | ((uint32_t)(4 + (b & 3)) << 4);
+      uint32_t t01, t23;
+      if (b < 4) { t01 = __byte_perm(lo[0], lo[1], sel); t23 = __byte_perm(lo[2], lo[3], sel); }
+      else       { t01 = __byte_perm(hi[0], hi[1], sel); t23 = __byte_perm(hi[2], hi[3], sel); }
+      uint32_t word = __byte_perm(t01, t23, 0x5410);
+      if (s > 0) word ^= 0x80808080u;
+      *reinterpret_cast<uint32_t*>(S + ((size_t)s * p + j) * ldn + r) = word;
+    }
+  }
+}
+
+// ---- the int8 GEMMs ---------------------------------------------------------------------------------------------------------
+// grid = CTAs of all kinds; CTA (kind, split) takes the chunks split, split + nsplit, ... of the kind's tile.
+// part[cta][j][i] (FP64, i contiguous): sum over the CTA's chunks of sum_g 2^(4 - 8 s_g) acc_g(i, j).
+__global__ void __launch_bounds__(I8_THREADS, 1)
+k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__ kinds, const int* __restrict__ cta_kind,
+            const int* __restrict__ cta_split, const int* __restrict__ kind_nsplit, int nchunks, double* __restrict__ part,
+            const int* skip_flag) {
+  if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;
+  extern __shared__ unsigned char i8_smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t pad = (1024u - (smem_u32(i8_smem_raw) & 1023u)) & 1023u;      // SWIZZLE_128B tiles: 1024-byte aligned
+  unsigned char* tiles = i8_smem_raw + pad;
+  I8Ctl& C = *reinterpret_cast<I8Ctl*>(tiles + (size_t)I8_SMEM_TILES * I8_TILE_BYTES);
+  const int kind = cta_kind[blockIdx.x], split = cta_split[blockIdx.x], nsplit = kind_nsplit[kind];
+  const int n_my = split < nchunks ? (nchunks - split + nsplit - 1) / nsplit : 0;
+  double* mypart = part + (size_t)blockIdx.x * (I8_TILE * I8_TILE);
+  if (n_my == 0) {                                   // fewer chunks than CTAs of this kind: an all-zero partial
+    for (int e = tid; e < I8_TILE * I8_TILE; e += I8_THREADS) mypart[e] = 0.0;
+    return;
+  }
+  {
+    const int* src = reinterpret_cast<const int*>(&kinds[kind]);
+    int* dst = reinterpret_cast<int*>(&C.kind);
+    for (int i = tid; i < (int)(sizeof(I8Kind) / sizeof(int)); i += I8_THREADS) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < I8_MAXSTAGE; ++s) { mbar_init(&C.full[s], 1); mbar_init(&C.empty[s], 1); }
+    mbar_init(&C.tmem_full, 1);
+    mbar_init(&C.tmem_empty, 4);
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc_512(&C.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = C.tmem_base;
+  const int ntiles = C.kind.ntiles;
+  const int nst = min(I8_MAXSTAGE, I8_SMEM_TILES / ntiles);
+  const uint32_t stage_bytes = (uint32_t)ntiles * I8_TILE_BYTES;
+  const int flush_chunks = C.kind.flush_chunks;
+
+  if (warp == 4) {
+    // ===== TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&mapS);
+      for (int i = 0; i < n_my; ++i) {
+        const int st = i % nst, round = i / nst;
+        mbar_wait(&C.empty[st], (round & 1) ^ 1);
+        mbar_arrive_expect_tx(&C.full[st], stage_bytes);
+        const int row0 = (split + i * nsplit) * I8_KC;
+        unsigned char* dst = tiles + (size_t)st * stage_bytes;
+        for (int t = 0; t < ntiles; ++t)
+          tma_load_3d(dst + (size_t)t * I8_TILE_BYTES, &mapS, &C.full[st], row0, C.kind.tile_blk[t] * I8_TILE, C.kind.tile_slice[t]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===== MMA issuer: one thread
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc_idesc_i8(I8_TILE, I8_TILE);
+      const int npairs = C.kind.npairs;
+      int period = 0, fl = 0;
+      uint32_t started = 0;                          // accumulators already written in this flush period
+      for (int i = 0; i < n_my; ++i) {
+        const int st = i % nst, round = i / nst;
+        mbar_wait(&C.full[st], round & 1);
+        tc_fence_after();
+        const uint32_t sbase = smem_u32(tiles + (size_t)st * stage_bytes);
+        for (int q = 0; q < npairs; ++q) {
+          const uint32_t g = (uint32_t)C.kind.pair_acc[q];
+          const uint64_t da = tc_desc_sw128(sbase + (uint32_t)C.kind.pair_a[q] * I8_TILE_BYTES);
+          const uint64_t db = tc_desc_sw128(sbase + (uint32_t)C.kind.pair_b[q] * I8_TILE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < I8_KC / 32; ++kk)    // 32 bytes of K per instruction: advance the start address by 32 B (>> 4 = 2)
+            tc_mma_i8(tmem + g * I8_TILE, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (kk > 0 || ((started >> g) & 1u)) ? 1u : 0u);
+          started |= 1u << g;
+        }
+        tc_commit(&C.empty[st]);                     // the stage is free once these MMAs have read it
+        ++period;
+        if (period == flush_chunks || i == n_my - 1) {
+          tc_commit(&C.tmem_full);
+          mbar_wait(&C.tmem_empty, fl & 1);
+          tc_fence_after();
+          period = 0; started = 0; ++fl;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warp q reads TMEM lanes 32 q .. 32 q + 31 (= rows i of the output tile), thread = row
+    const int nacc = C.kind.nacc;
+    double scale[I8_MAXACC];
+#pragma unroll
+    for (int g = 0; g < I8_MAXACC; ++g) scale[g] = (g < nacc) ? ldexp(1.0, 4 - 8 * C.kind.acc_sum[g]) : 0.0;
+    const int nfl = (n_my + flush_chunks - 1) / flush_chunks;
+    const int i = warp * 32 + lane;
+    for (int fl = 0; fl < nfl; ++fl) {
+      mbar_wait(&C.tmem_full, fl & 1);
+      tc_fence_after();
+      for (int cb = 0; cb < I8_TILE / 32; ++cb) {
+        double v[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = 0.0;
+        for (int g = 0; g < nacc; ++g) {
+          uint32_t r[32];
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * I8_TILE + cb * 32), r);
+          const double sc = scale[g];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = fma((double)(int)r[c], sc, v[c]);
+        }
+        double* out = mypart + (size_t)(cb * 32) * I8_TILE + i;
+        if (fl == 0) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) out[(size_t)c * I8_TILE] = v[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) out[(size_t)c * I8_TILE] += v[c];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&C.tmem_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) { tc_fence_after(); tmem_dealloc_512(tmem); }
+}
+
+// ---- deterministic sum of the per-CTA partial tiles -> landing buffer (both triangles, exactly symmetric) ------------------
+__global__ void __launch_bounds__(256)
+k_reduce_i8(double* __restrict__ E, int p, int goff, const double* __restrict__ part, const int* __restrict__ tile_bi,
+            const int* __restrict__ tile_bj, const int* __restrict__ tile_off, const int* __restrict__ tile_n,
+            const int* __restrict__ tile_ctas, const double* __restrict__ cg, const int* skip_flag) {
+  if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;
+  constexpr int BPT = I8_TILE * I8_TILE / 256;       // blocks per tile
+  const int t = blockIdx.x / BPT;
+  const int e = (blockIdx.x % BPT) * 256 + threadIdx.x;
+  const int i = e & (I8_TILE - 1), j = e >> 7;
+  const int bi = tile_bi[t], bj = tile_bj[t];
+  const int gi = bi * I8_TILE + i, gj = bj * I8_TILE + j;
+  if (gi >= p || gj >= p || (bi == bj && i < j)) return;
+  const int* list = tile_ctas + tile_off[t];
+  const int n = tile_n[t];
+  double s = 0.0;
+  int k = 0;
+  for (; k + 8 <= n; k += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = part[(size_t)list[k + u] * (I8_TILE * I8_TILE) + e];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; k < n; ++k) s += part[(size_t)list[k] * (I8_TILE * I8_TILE) + e];
+  s *= cg[gi] * cg[gj];
+  double* G = E + goff;
+  G[gi + (size_t)gj * p] = s;
+  G[gj + (size_t)gi * p] = s;
+}
+
+}  // namespace gamc
