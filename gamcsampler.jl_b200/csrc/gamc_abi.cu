@@ -87,11 +87,11 @@ struct gamc_ctx : gamc_ctx_base {
   unsigned long long* d_co_dbg = nullptr;   // GAMC_CO_DEBUG=1: time stamps and CTA placement of the pair, printed by gamc_eval_upto_tensor
   double* part_ll = nullptr; double* part_g = nullptr;
   // metric on the integer tensor cores (metric_i8.cuh): digit planes of diag(sqrt w) X, column exponents, per-CTA partial tiles
-  bool metric_i8 = false; int i8_k = 0, i8_smax = 0, i8_grid = 0, i8_nchunks = 0, i8_ntiles = 0; long long i8_ldn = 0;
-  int8_t* d_i8S = nullptr; double *d_i8cs = nullptr, *d_i8cg = nullptr, *d_i8part = nullptr; unsigned long long* d_i8cmax = nullptr;
-  I8Kind* d_i8kinds = nullptr; int* d_i8ints = nullptr; CUtensorMap mapS{};
-  int *d_i8cta_kind = nullptr, *d_i8cta_split = nullptr, *d_i8kind_nsplit = nullptr, *d_i8tile_bi = nullptr, *d_i8tile_bj = nullptr,
-      *d_i8tile_off = nullptr, *d_i8tile_n = nullptr, *d_i8tile_ctas = nullptr;
+  bool metric_i8 = false; int i8_k = 0, i8_smax = 0, i8_grid = 0, i8_nitems = 0, i8_ntiles = 0, i8_nslots = 0; long long i8_ldn = 0;
+  int8_t* d_i8S = nullptr; double *d_i8cs = nullptr, *d_i8cg = nullptr; unsigned long long* d_i8cmax = nullptr;
+  long long* d_i8acc = nullptr; size_t i8_acc_bytes = 0;   // [item counter (16 bytes) | int64 group sums [tile][slot][128 x 128]]
+  I8Kind* d_i8kinds = nullptr; I8Item* d_i8items = nullptr; int* d_i8ints = nullptr; CUtensorMap mapS{};
+  int *d_i8tile_bi = nullptr, *d_i8tile_bj = nullptr;
   // metric
   MetricLayout layout; MetricPlan* d_plans = nullptr; TaskCoord* d_coords = nullptr;
   int nkinds = 0, ntasks = 0, metric_grid = 0; long long nslabs = 0; double* ws = nullptr; int* d_ints = nullptr;
@@ -193,8 +193,8 @@ void free_target(gamc_ctx* h) {
   cudaFree(h->d_plans_fused); h->d_plans_fused = nullptr; h->metric_fused = false;
   cudaFree(h->d_co_flags); h->d_co_flags = nullptr; h->level2_co = false;
   cudaFree(h->d_co_dbg); h->d_co_dbg = nullptr;
-  cudaFree(h->d_i8S); cudaFree(h->d_i8cs); cudaFree(h->d_i8cg); cudaFree(h->d_i8part); cudaFree(h->d_i8cmax); cudaFree(h->d_i8kinds); cudaFree(h->d_i8ints);
-  h->d_i8S = nullptr; h->d_i8cs = h->d_i8cg = h->d_i8part = nullptr; h->d_i8cmax = nullptr; h->d_i8kinds = nullptr; h->d_i8ints = nullptr; h->metric_i8 = false;
+  cudaFree(h->d_i8S); cudaFree(h->d_i8cs); cudaFree(h->d_i8cg); cudaFree(h->d_i8acc); cudaFree(h->d_i8cmax); cudaFree(h->d_i8kinds); cudaFree(h->d_i8items); cudaFree(h->d_i8ints);
+  h->d_i8S = nullptr; h->d_i8cs = h->d_i8cg = nullptr; h->d_i8acc = nullptr; h->d_i8cmax = nullptr; h->d_i8kinds = nullptr; h->d_i8items = nullptr; h->d_i8ints = nullptr; h->metric_i8 = false;
   cudaFree(h->d_plans); cudaFree(h->d_coords); cudaFree(h->ws); cudaFree(h->d_ints); h->d_plans = nullptr; h->d_coords = nullptr; h->ws = nullptr; h->d_ints = nullptr;
   cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0; h->R = nullptr; h->vecs = h->mats = nullptr; h->d_state = nullptr;
   cudaFree(h->theta_eval); h->theta_eval = nullptr;
@@ -449,8 +449,9 @@ gamc_status launch_metric_i8(gamc_ctx* h, const int* skip = nullptr) {
   for (int i = 0; i + 1 < h->i8_k; ++i) bias += ldexp(128.0, 8 * i);
   k_i8_slice<<<sgrid, 256, 0, h->stream>>>(h->dX, h->ld, h->dw, h->N, h->p, h->d_i8cs, h->i8_k, h->i8_ldn, h->d_i8S, bias, skip);
   CUDA_TRY(h, cudaGetLastError());
-  k_metric_i8<<<h->i8_grid, I8_THREADS, I8_SMEM_BYTES, h->stream>>>(h->mapS, h->d_i8kinds, h->d_i8cta_kind, h->d_i8cta_split, h->d_i8kind_nsplit,
-                                                                    h->i8_nchunks, h->d_i8part, skip);
+  CUDA_TRY(h, cudaMemsetAsync(h->d_i8acc, 0, h->i8_acc_bytes, h->stream));   // item counter and int64 group sums
+  k_metric_i8<<<h->i8_grid, I8_THREADS, I8_SMEM_BYTES, h->stream>>>(h->mapS, h->d_i8kinds, h->d_i8items, h->i8_nitems, reinterpret_cast<int*>(h->d_i8acc),
+                                                                    h->d_i8acc + 2, h->i8_nslots, skip);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
 }
@@ -466,8 +467,8 @@ gamc_status launch_reduce(gamc_ctx* h, int level, double* E = nullptr, const int
                                          nullptr, h->d_coords, h->ntasks, h->d_task_nsplit, h->layout.max_nsplit, skip);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
-    k_reduce_i8<<<h->i8_ntiles * (I8_TILE * I8_TILE / 256), 256, 0, h->stream>>>(E ? E : h->R, h->p, h->goff, h->d_i8part, h->d_i8tile_bi, h->d_i8tile_bj,
-        h->d_i8tile_off, h->d_i8tile_n, h->d_i8tile_ctas, h->d_i8cg, skip);
+    k_reduce_i8<<<h->i8_ntiles * (I8_TILE * I8_TILE / 256), 256, 0, h->stream>>>(E ? E : h->R, h->p, h->goff, h->d_i8acc + 2, h->i8_smax, h->d_i8tile_bi,
+        h->d_i8tile_bj, h->d_i8cg, skip);
     CUDA_TRY(h, cudaGetLastError());
     return GAMC_OK;
   }
@@ -678,7 +679,7 @@ gamc_status setup_metric_i8(gamc_ctx* h, int k, int smax) {
   REQUIRE(h, h->N < (1ll << 31) - 256, GAMC_UNSUPPORTED_SHAPE, "metric_i8: too many rows for one rank");
   h->i8_k = k; h->i8_smax = smax;
   h->i8_ldn = (h->N + I8_KC - 1) / I8_KC * I8_KC;
-  h->i8_nchunks = (int)(h->i8_ldn / I8_KC);
+  const long long nchunks = h->i8_ldn / I8_KC;
   CUDA_TRY(h, cudaMalloc(&h->d_i8S, (size_t)k * p * h->i8_ldn));
   CUDA_TRY(h, cudaMalloc(&h->d_i8cs, sizeof(double) * p));
   CUDA_TRY(h, cudaMalloc(&h->d_i8cg, sizeof(double) * p));
@@ -701,23 +702,28 @@ gamc_status setup_metric_i8(gamc_ctx* h, int k, int smax) {
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled(digit planes) failed with code " + std::to_string((int)r); return GAMC_CUDA_ERROR; }
   }
-  const I8Layout L = build_i8_layout(p, k, smax, h->num_sms, h->i8_nchunks);
-  h->i8_grid = (int)L.cta_kind.size();
+  int block_chunks = 0;
+  if (const char* eb = getenv("GAMC_I8_BLOCK")) { const int v = atoi(eb); if (v >= 1 && v <= 4096) block_chunks = v; }
+  const I8Layout L = build_i8_layout(p, k, smax, h->num_sms, nchunks, block_chunks);
+  h->i8_nitems = (int)L.items.size();
+  h->i8_grid = std::min(h->num_sms, h->i8_nitems);
   h->i8_ntiles = (int)L.tile_bi.size();
+  h->i8_nslots = L.nslots;
   {
     std::vector<int> ints;
     auto push = [&](const std::vector<int>& v) { size_t off = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); return off; };
-    const size_t o1 = push(L.cta_kind), o2 = push(L.cta_split), o3 = push(L.kind_nsplit), o4 = push(L.tile_bi), o5 = push(L.tile_bj),
-                 o6 = push(L.tile_off), o7 = push(L.tile_n), o8 = push(L.tile_ctas);
+    const size_t o4 = push(L.tile_bi), o5 = push(L.tile_bj);
     CUDA_TRY(h, cudaMalloc(&h->d_i8ints, sizeof(int) * ints.size()));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_i8ints, ints.data(), sizeof(int) * ints.size(), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMalloc(&h->d_i8kinds, sizeof(I8Kind) * L.kinds.size()));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_i8kinds, L.kinds.data(), sizeof(I8Kind) * L.kinds.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMalloc(&h->d_i8items, sizeof(I8Item) * L.items.size()));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_i8items, L.items.data(), sizeof(I8Item) * L.items.size(), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    h->d_i8cta_kind = h->d_i8ints + o1; h->d_i8cta_split = h->d_i8ints + o2; h->d_i8kind_nsplit = h->d_i8ints + o3; h->d_i8tile_bi = h->d_i8ints + o4;
-    h->d_i8tile_bj = h->d_i8ints + o5; h->d_i8tile_off = h->d_i8ints + o6; h->d_i8tile_n = h->d_i8ints + o7; h->d_i8tile_ctas = h->d_i8ints + o8;
+    h->d_i8tile_bi = h->d_i8ints + o4; h->d_i8tile_bj = h->d_i8ints + o5;
   }
-  CUDA_TRY(h, cudaMalloc(&h->d_i8part, sizeof(double) * (size_t)h->i8_grid * I8_TILE * I8_TILE));
+  h->i8_acc_bytes = 16 + sizeof(long long) * (size_t)h->i8_ntiles * h->i8_nslots * I8_TILE * I8_TILE;
+  CUDA_TRY(h, cudaMalloc(&h->d_i8acc, h->i8_acc_bytes));
   h->metric_i8 = true;
   return GAMC_OK;
 }
@@ -1849,7 +1855,7 @@ int gamc_debug_i8_read(gamc_handle h, int what, void* out, long long bytes) {
   if (what == 2) {
     if (bytes < 32) return 2;
     long long* o = reinterpret_cast<long long*>(out);
-    o[0] = h->i8_k; o[1] = h->i8_smax; o[2] = h->i8_ldn; o[3] = h->i8_grid;
+    o[0] = h->i8_k; o[1] = h->i8_smax; o[2] = h->i8_ldn; o[3] = h->i8_nitems;
     return 0;
   }
   return 4;

@@ -15,7 +15,7 @@
 //
 // Kernels: k_i8_colmax / k_i8_scales (once per target: column exponents), k_i8_slice (per evaluation: digit planes of
 // diag(sqrt w) X, HBM-bound), k_metric_i8 (the int8 GEMMs: warp-specialised TMA producer / single-thread tcgen05.mma
-// issuer / TMEM epilogue), k_reduce_i8 (deterministic sum of the per-CTA partial tiles into the landing buffer).
+// issuer / TMEM epilogue with exact int64 atomics), k_reduce_i8 (weights, column scales, landing buffer).
 #pragma once
 #include "common.cuh"
 
@@ -28,31 +28,38 @@ constexpr int I8_MAXT = 6;                         // operand tiles per stage
 constexpr int I8_MAXP = 12;                        // digit products per kind
 constexpr int I8_MAXACC = 4;                       // accumulators of 128 TMEM columns: all 512 columns of the SM
 constexpr int I8_MAXK = 7;                         // digit planes
-constexpr int I8_SMEM_TILES = 13;                  // operand tiles resident per CTA (208 KB), cut into stages of the kind's ntiles
-constexpr int I8_MAXSTAGE = 8;
 constexpr int I8_THREADS = 192;                    // warps 0-3: epilogue (TMEM lane quarters 0-3); warp 4: TMA producer; warp 5: MMA issuer, TMEM allocator
 constexpr int I8_SLICE_ROWS = 128, I8_SLICE_COLS = 64;
 
 struct I8Kind {
   int bi, bj;                  // output tile (column blocks of X), bi >= bj
+  int tile;                    // index of the output tile (position of its accumulators in the int64 buffer)
   int ntiles;                  // operand tiles per chunk
   int tile_slice[I8_MAXT];     // digit plane (0 = most significant)
   int tile_blk[I8_MAXT];       // column block
   int npairs;
   int pair_a[I8_MAXP], pair_b[I8_MAXP], pair_acc[I8_MAXP];   // operand tiles and accumulator of each digit product
   int nacc;
-  int acc_sum[I8_MAXACC];      // a + b (1-based digits) of the products of accumulator g: weight 2^(4 - 8 (a + b))
-  int flush_chunks;            // chunks between two flushes of the int32 accumulators (head room of 2^31)
+  int acc_slot[I8_MAXACC];     // group slot of accumulator g inside the tile's block of the int64 buffer (see below)
+  int max_chunks;              // chunks one int32 accumulation may span (head room of 2^31)
 };
+// Group slots of an output tile in the int64 buffer: slot s - 2 holds sum_{a + b = s} D_a' D_b over the ORDERED digit pairs the
+// planner issued with that weight; for a diagonal tile only a <= b is issued and the a < b products go to slot (smax - 1) + s - 2,
+// which the reduction adds together with its transpose (D_a' D_b + D_b' D_a).
+struct I8Item { int kind, chunk0, nchunks; };
 
+constexpr int I8_RING = 13;                        // operand tile slots of 16 KB (ring; a chunk takes the kind's ntiles consecutive slots)
+constexpr int I8_IQ = 4;                           // items in flight between the producer and the other roles
 struct I8Ctl {
-  alignas(8) uint64_t full[I8_MAXSTAGE];
-  alignas(8) uint64_t empty[I8_MAXSTAGE];
+  alignas(8) uint64_t full[I8_RING];
+  alignas(8) uint64_t empty[I8_RING];
+  alignas(8) uint64_t item_full[I8_IQ], item_empty[I8_IQ];
   alignas(8) uint64_t tmem_full, tmem_empty;
   uint32_t tmem_base;
-  I8Kind kind;
+  int item[I8_IQ];
+  I8Kind kind;                                     // the MMA issuer's copy of the current item's kind
 };
-constexpr size_t I8_SMEM_BYTES = (size_t)I8_SMEM_TILES * I8_TILE_BYTES + 1024 + sizeof(I8Ctl);
+constexpr size_t I8_SMEM_BYTES = (size_t)I8_RING * I8_TILE_BYTES + 1024 + sizeof(I8Ctl);
 
 // ---- tcgen05 / TMEM wrappers (SASS: UTCIMMA / UTCBAR / LDTM) ------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -175,32 +182,25 @@ k_i8_slice(const double* __restrict__ X, long long ld, const double* __restrict_
 }
 
 // ---- the int8 GEMMs ---------------------------------------------------------------------------------------------------------
-// grid = CTAs of all kinds; CTA (kind, split) takes the chunks split, split + nsplit, ... of the kind's tile.
-// part[cta][j][i] (FP64, i contiguous): sum over the CTA's chunks of sum_g 2^(4 - 8 s_g) acc_g(i, j).
+// Persistent grid (one CTA per SM).  Work items (kind, block of consecutive 128-row chunks), ordered by rows so that all CTAs sweep
+// the digit planes together (the L2 serves the re-reads), are claimed from a global counter by the producer warp and handed to the
+// MMA issuer and the epilogue warps through a small ring.  Operand tiles travel through a ring of I8_RING 16 KB slots with one
+// full / empty mbarrier pair each, so the pipeline depth adapts to the kind's number of tiles and runs on across item boundaries.
+// An item accumulates in int32 in tensor memory; its epilogue adds the accumulators to the tile's int64 group slots in global
+// memory with integer atomics: exact, hence independent of which CTA took which item and in which order -- the evaluation is
+// bit-reproducible although the schedule is dynamic.
 __global__ void __launch_bounds__(I8_THREADS, 1)
-k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__ kinds, const int* __restrict__ cta_kind,
-            const int* __restrict__ cta_split, const int* __restrict__ kind_nsplit, int nchunks, double* __restrict__ part,
-            const int* skip_flag) {
+k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__ kinds, const I8Item* __restrict__ items, int nitems,
+            int* __restrict__ counter, long long* __restrict__ acc64, int nslots, const int* skip_flag) {
   if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;
   extern __shared__ unsigned char i8_smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t pad = (1024u - (smem_u32(i8_smem_raw) & 1023u)) & 1023u;      // SWIZZLE_128B tiles: 1024-byte aligned
   unsigned char* tiles = i8_smem_raw + pad;
-  I8Ctl& C = *reinterpret_cast<I8Ctl*>(tiles + (size_t)I8_SMEM_TILES * I8_TILE_BYTES);
-  const int kind = cta_kind[blockIdx.x], split = cta_split[blockIdx.x], nsplit = kind_nsplit[kind];
-  const int n_my = split < nchunks ? (nchunks - split + nsplit - 1) / nsplit : 0;
-  double* mypart = part + (size_t)blockIdx.x * (I8_TILE * I8_TILE);
-  if (n_my == 0) {                                   // fewer chunks than CTAs of this kind: an all-zero partial
-    for (int e = tid; e < I8_TILE * I8_TILE; e += I8_THREADS) mypart[e] = 0.0;
-    return;
-  }
-  {
-    const int* src = reinterpret_cast<const int*>(&kinds[kind]);
-    int* dst = reinterpret_cast<int*>(&C.kind);
-    for (int i = tid; i < (int)(sizeof(I8Kind) / sizeof(int)); i += I8_THREADS) dst[i] = src[i];
-  }
+  I8Ctl& C = *reinterpret_cast<I8Ctl*>(tiles + (size_t)I8_RING * I8_TILE_BYTES);
   if (tid == 0) {
-    for (int s = 0; s < I8_MAXSTAGE; ++s) { mbar_init(&C.full[s], 1); mbar_init(&C.empty[s], 1); }
+    for (int s = 0; s < I8_RING; ++s) { mbar_init(&C.full[s], 1); mbar_init(&C.empty[s], 1); }
+    for (int s = 0; s < I8_IQ; ++s) { mbar_init(&C.item_full[s], 1); mbar_init(&C.item_empty[s], 5); }   // consumers: MMA issuer + 4 epilogue warps
     mbar_init(&C.tmem_full, 1);
     mbar_init(&C.tmem_empty, 4);
     mbar_fence_init();
@@ -210,92 +210,117 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = C.tmem_base;
-  const int ntiles = C.kind.ntiles;
-  const int nst = min(I8_MAXSTAGE, I8_SMEM_TILES / ntiles);
-  const uint32_t stage_bytes = (uint32_t)ntiles * I8_TILE_BYTES;
-  const int flush_chunks = C.kind.flush_chunks;
 
   if (warp == 4) {
-    // ===== TMA producer
+    // ===== producer: claims items, feeds the tile ring
     if (lane == 0) {
       tma_prefetch_desc(&mapS);
-      for (int i = 0; i < n_my; ++i) {
-        const int st = i % nst, round = i / nst;
-        mbar_wait(&C.empty[st], (round & 1) ^ 1);
-        mbar_arrive_expect_tx(&C.full[st], stage_bytes);
-        const int row0 = (split + i * nsplit) * I8_KC;
-        unsigned char* dst = tiles + (size_t)st * stage_bytes;
-        for (int t = 0; t < ntiles; ++t)
-          tma_load_3d(dst + (size_t)t * I8_TILE_BYTES, &mapS, &C.full[st], row0, C.kind.tile_blk[t] * I8_TILE, C.kind.tile_slice[t]);
+      unsigned n = 0;                                // tile slots handed out so far
+      for (unsigned iq = 0;; ++iq) {
+        const int e = iq % I8_IQ;
+        mbar_wait(&C.item_empty[e], ((iq / I8_IQ) & 1) ^ 1);
+        const int it = atomicAdd(counter, 1);
+        C.item[e] = it < nitems ? it : -1;
+        mbar_arrive(&C.item_full[e]);                // (mbarrier arrive has release semantics: the item index is visible to the waiters)
+        if (it >= nitems) break;
+        const I8Item im = items[it];
+        const I8Kind* kd = kinds + im.kind;
+        const int ntiles = kd->ntiles;
+        int tsl[I8_MAXT], tbk[I8_MAXT];
+#pragma unroll
+        for (int t = 0; t < I8_MAXT; ++t) { tsl[t] = t < ntiles ? kd->tile_slice[t] : 0; tbk[t] = t < ntiles ? kd->tile_blk[t] * I8_TILE : 0; }
+        for (int c = 0; c < im.nchunks; ++c) {
+          const int row0 = (im.chunk0 + c) * I8_KC;
+#pragma unroll
+          for (int t = 0; t < I8_MAXT; ++t) {
+            if (t < ntiles) {
+              const unsigned sl = n % I8_RING, round = n / I8_RING;
+              mbar_wait(&C.empty[sl], (round & 1) ^ 1);
+              mbar_arrive_expect_tx(&C.full[sl], I8_TILE_BYTES);
+              tma_load_3d(tiles + (size_t)sl * I8_TILE_BYTES, &mapS, &C.full[sl], row0, tbk[t], tsl[t]);
+              ++n;
+            }
+          }
+        }
       }
     }
     __syncwarp();
   } else if (warp == 5) {
-    // ===== MMA issuer: one thread
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc_idesc_i8(I8_TILE, I8_TILE);
-      const int npairs = C.kind.npairs;
-      int period = 0, fl = 0;
-      uint32_t started = 0;                          // accumulators already written in this flush period
-      for (int i = 0; i < n_my; ++i) {
-        const int st = i % nst, round = i / nst;
-        mbar_wait(&C.full[st], round & 1);
-        tc_fence_after();
-        const uint32_t sbase = smem_u32(tiles + (size_t)st * stage_bytes);
-        for (int q = 0; q < npairs; ++q) {
-          const uint32_t g = (uint32_t)C.kind.pair_acc[q];
-          const uint64_t da = tc_desc_sw128(sbase + (uint32_t)C.kind.pair_a[q] * I8_TILE_BYTES);
-          const uint64_t db = tc_desc_sw128(sbase + (uint32_t)C.kind.pair_b[q] * I8_TILE_BYTES);
-#pragma unroll
-          for (int kk = 0; kk < I8_KC / 32; ++kk)    // 32 bytes of K per instruction: advance the start address by 32 B (>> 4 = 2)
-            tc_mma_i8(tmem + g * I8_TILE, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (kk > 0 || ((started >> g) & 1u)) ? 1u : 0u);
-          started |= 1u << g;
-        }
-        tc_commit(&C.empty[st]);                     // the stage is free once these MMAs have read it
-        ++period;
-        if (period == flush_chunks || i == n_my - 1) {
-          tc_commit(&C.tmem_full);
-          mbar_wait(&C.tmem_empty, fl & 1);
-          tc_fence_after();
-          period = 0; started = 0; ++fl;
-        }
+    // ===== MMA issuer (one thread issues; the warp copies the kind of each item to shared memory together)
+    constexpr uint32_t idesc = tc_idesc_i8(I8_TILE, I8_TILE);
+    unsigned n = 0, nitem = 0;
+    for (unsigned iq = 0;; ++iq) {
+      const int e = iq % I8_IQ;
+      mbar_wait(&C.item_full[e], (iq / I8_IQ) & 1);
+      const int it = C.item[e];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&C.item_empty[e]);
+      if (it < 0) break;
+      const I8Item im = items[it];
+      {
+        const int* src = reinterpret_cast<const int*>(kinds + im.kind);
+        int* dst = reinterpret_cast<int*>(&C.kind);
+        for (int i = lane; i < (int)(sizeof(I8Kind) / sizeof(int)); i += 32) dst[i] = src[i];
       }
+      __syncwarp();
+      if (lane == 0) {
+        const int ntiles = C.kind.ntiles, npairs = C.kind.npairs;
+        if (nitem > 0) { mbar_wait(&C.tmem_empty, (nitem - 1) & 1); tc_fence_after(); }   // the previous item's accumulators have been read
+        uint32_t started = 0;
+        for (int c = 0; c < im.nchunks; ++c) {
+          for (int t = 0; t < ntiles; ++t) { const unsigned m = n + t; mbar_wait(&C.full[m % I8_RING], (m / I8_RING) & 1); }
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(tiles);
+          for (int q = 0; q < npairs; ++q) {
+            const uint32_t g = (uint32_t)C.kind.pair_acc[q];
+            const uint64_t da = tc_desc_sw128(sbase + ((n + (unsigned)C.kind.pair_a[q]) % I8_RING) * I8_TILE_BYTES);
+            const uint64_t db = tc_desc_sw128(sbase + ((n + (unsigned)C.kind.pair_b[q]) % I8_RING) * I8_TILE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < I8_KC / 32; ++kk)    // 32 bytes of K per instruction: advance the start address by 32 B (>> 4 = 2)
+              tc_mma_i8(tmem + g * I8_TILE, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (kk > 0 || ((started >> g) & 1u)) ? 1u : 0u);
+            started |= 1u << g;
+          }
+          for (int t = 0; t < ntiles; ++t) tc_commit(&C.empty[(n + t) % I8_RING]);   // the slots are free once these MMAs have read them
+          n += ntiles;
+        }
+        tc_commit(&C.tmem_full);
+      }
+      ++nitem;
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===== epilogue: warp q reads TMEM lanes 32 q .. 32 q + 31 (= rows i of the output tile), thread = row
-    const int nacc = C.kind.nacc;
-    double scale[I8_MAXACC];
-#pragma unroll
-    for (int g = 0; g < I8_MAXACC; ++g) scale[g] = (g < nacc) ? ldexp(1.0, 4 - 8 * C.kind.acc_sum[g]) : 0.0;
-    const int nfl = (n_my + flush_chunks - 1) / flush_chunks;
     const int i = warp * 32 + lane;
-    for (int fl = 0; fl < nfl; ++fl) {
-      mbar_wait(&C.tmem_full, fl & 1);
-      tc_fence_after();
-      for (int cb = 0; cb < I8_TILE / 32; ++cb) {
-        double v[32];
+    unsigned nitem = 0;
+    for (unsigned iq = 0;; ++iq) {
+      const int e = iq % I8_IQ;
+      mbar_wait(&C.item_full[e], (iq / I8_IQ) & 1);
+      const int it = C.item[e];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&C.item_empty[e]);
+      if (it < 0) break;
+      const I8Kind* kd = kinds + items[it].kind;
+      const int nacc = kd->nacc;
+      long long* tbase = acc64 + (size_t)kd->tile * nslots * (I8_TILE * I8_TILE);
+      int slot[I8_MAXACC];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = 0.0;
-        for (int g = 0; g < nacc; ++g) {
+      for (int g = 0; g < I8_MAXACC; ++g) slot[g] = g < nacc ? kd->acc_slot[g] : 0;
+      mbar_wait(&C.tmem_full, nitem & 1);
+      tc_fence_after();
+      for (int g = 0; g < nacc; ++g) {
+        unsigned long long* out = reinterpret_cast<unsigned long long*>(tbase + (size_t)slot[g] * (I8_TILE * I8_TILE)) + i;
+        for (int cb = 0; cb < I8_TILE / 32; ++cb) {
           uint32_t r[32];
           tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * I8_TILE + cb * 32), r);
-          const double sc = scale[g];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] = fma((double)(int)r[c], sc, v[c]);
-        }
-        double* out = mypart + (size_t)(cb * 32) * I8_TILE + i;
-        if (fl == 0) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) out[(size_t)c * I8_TILE] = v[c];
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) out[(size_t)c * I8_TILE] += v[c];
+          for (int c = 0; c < 32; ++c)
+            if (r[c]) atomicAdd(out + (size_t)(cb * 32 + c) * I8_TILE, (unsigned long long)(long long)(int)r[c]);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&C.tmem_empty);
+      ++nitem;
     }
   }
   tc_fence_before();
@@ -303,11 +328,12 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
   if (warp == 5) { tc_fence_after(); tmem_dealloc_512(tmem); }
 }
 
-// ---- deterministic sum of the per-CTA partial tiles -> landing buffer (both triangles, exactly symmetric) ------------------
+// ---- exact int64 group sums -> landing buffer (both triangles, exactly symmetric).
+//      G_ij = 2^(e_i + e_j) sum_s 2^(4 - 8 s) [slot_s(i, j) (+ slotA_s(i, j) + slotA_s(j, i) on diagonal tiles)].
+//      (The sums and the item counter are cleared by a memset node before the next evaluation.)
 __global__ void __launch_bounds__(256)
-k_reduce_i8(double* __restrict__ E, int p, int goff, const double* __restrict__ part, const int* __restrict__ tile_bi,
-            const int* __restrict__ tile_bj, const int* __restrict__ tile_off, const int* __restrict__ tile_n,
-            const int* __restrict__ tile_ctas, const double* __restrict__ cg, const int* skip_flag) {
+k_reduce_i8(double* __restrict__ E, int p, int goff, const long long* __restrict__ acc64, int smax, const int* __restrict__ tile_bi,
+            const int* __restrict__ tile_bj, const double* __restrict__ cg, const int* skip_flag) {
   if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;
   constexpr int BPT = I8_TILE * I8_TILE / 256;       // blocks per tile
   const int t = blockIdx.x / BPT;
@@ -315,19 +341,17 @@ k_reduce_i8(double* __restrict__ E, int p, int goff, const double* __restrict__ 
   const int i = e & (I8_TILE - 1), j = e >> 7;
   const int bi = tile_bi[t], bj = tile_bj[t];
   const int gi = bi * I8_TILE + i, gj = bj * I8_TILE + j;
-  if (gi >= p || gj >= p || (bi == bj && i < j)) return;
-  const int* list = tile_ctas + tile_off[t];
-  const int n = tile_n[t];
+  const bool diag = bi == bj;
+  if (gi >= p || gj >= p || (diag && i < j)) return;
+  const int ng = smax - 1, nslots = 2 * ng;
+  const long long* tb = acc64 + (size_t)t * nslots * (I8_TILE * I8_TILE);
+  const int et = i * I8_TILE + j;                    // the transposed element of the tile
   double s = 0.0;
-  int k = 0;
-  for (; k + 8 <= n; k += 8) {
-    double v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = part[(size_t)list[k + u] * (I8_TILE * I8_TILE) + e];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) s += v[u];
+  for (int q = ng - 1; q >= 0; --q) {                // smallest weights first
+    long long v = tb[(size_t)q * (I8_TILE * I8_TILE) + e];
+    if (diag) v += tb[(size_t)(ng + q) * (I8_TILE * I8_TILE) + e] + tb[(size_t)(ng + q) * (I8_TILE * I8_TILE) + et];
+    s = fma((double)v, ldexp(1.0, 4 - 8 * (q + 2)), s);
   }
-  for (; k < n; ++k) s += part[(size_t)list[k] * (I8_TILE * I8_TILE) + e];
   s *= cg[gi] * cg[gj];
   double* G = E + goff;
   G[gi + (size_t)gj * p] = s;
