@@ -447,7 +447,7 @@ gamc_status launch_metric_i8(gamc_ctx* h, const int* skip = nullptr) {
   const dim3 sgrid((unsigned)((h->N + I8_SLICE_ROWS - 1) / I8_SLICE_ROWS), (unsigned)((h->p + I8_SLICE_COLS - 1) / I8_SLICE_COLS));
   double bias = 0.0;
   for (int i = 0; i + 1 < h->i8_k; ++i) bias += ldexp(128.0, 8 * i);
-  k_i8_slice<<<sgrid, 256, 0, h->stream>>>(h->dX, h->ld, h->dw, h->N, h->p, h->d_i8cs, h->i8_k, h->i8_ldn, h->d_i8S, bias, skip);
+  k_i8_slice<<<sgrid, 256, 0, h->stream>>>(h->dX, h->ld, h->dw, h->N, h->p, h->d_i8cs, h->i8_k, h->d_i8S, bias, skip);
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaMemsetAsync(h->d_i8acc, 0, h->i8_acc_bytes, h->stream));   // item counter and int64 group sums
   k_metric_i8<<<h->i8_grid, I8_THREADS, I8_SMEM_BYTES, h->stream>>>(h->mapS, h->d_i8kinds, h->d_i8items, h->i8_nitems, reinterpret_cast<int*>(h->d_i8acc),
@@ -694,11 +694,11 @@ gamc_status setup_metric_i8(gamc_ctx* h, int k, int smax) {
   }
   {
     if (!ensure_encode(h)) return GAMC_CUDA_ERROR;
-    cuuint64_t dims[3] = {(cuuint64_t)h->N, (cuuint64_t)p, (cuuint64_t)k};
-    cuuint64_t strides[2] = {(cuuint64_t)h->i8_ldn, (cuuint64_t)h->i8_ldn * (cuuint64_t)p};
-    cuuint32_t box[3] = {(cuuint32_t)I8_KC, (cuuint32_t)I8_TILE, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = g_encode(&h->mapS, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)h->d_i8S, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t dims[4] = {(cuuint64_t)I8_KC, (cuuint64_t)p, (cuuint64_t)k, (cuuint64_t)nchunks};
+    cuuint64_t strides[3] = {(cuuint64_t)I8_KC, (cuuint64_t)I8_KC * (cuuint64_t)p, (cuuint64_t)I8_KC * (cuuint64_t)p * (cuuint64_t)k};
+    cuuint32_t box[4] = {(cuuint32_t)I8_KC, (cuuint32_t)I8_TILE, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(&h->mapS, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)h->d_i8S, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled(digit planes) failed with code " + std::to_string((int)r); return GAMC_CUDA_ERROR; }
   }
@@ -1838,7 +1838,7 @@ long long gamc_debug_guard_check(long long* n_allocations) {
 }
 #endif
 
-// Debug read-out of the integer-tensor-core metric (tests/test_gpu_i8.py): what = 0: digit planes [k][p][ldn] int8 (as written by the last
+// Debug read-out of the integer-tensor-core metric (tests/test_gpu_i8.py): what = 0: digit planes [chunk][k][p][128] int8 (as written by the last
 // level-2 evaluation), 1: column scales cg[p] (double), 2: {k, smax, ldn, grid} as four int64.  Not part of the public header.
 int gamc_debug_i8_read(gamc_handle h, int what, void* out, long long bytes) {
   if (!h || !h->metric_i8) return 1;

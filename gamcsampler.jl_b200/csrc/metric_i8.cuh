@@ -64,6 +64,19 @@ constexpr size_t I8_SMEM_BYTES = (size_t)I8_RING * I8_TILE_BYTES + 1024 + sizeof
 // ---- tcgen05 / TMEM wrappers (SASS: UTCIMMA / UTCBAR / LDTM) ------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// One lane of a CONVERGED warp (the form ptxas recognises as a single-thread region: operands of the tcgen05 / TMA instructions
+// issued under it move to uniform registers once instead of through a per-lane waterfall loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_alloc_512(uint32_t* dst_smem) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(512u) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -75,24 +88,42 @@ __device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {    // whole w
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]', int8 x int8 -> int32, M = 128, N = 128, K = 32 per instruction
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]', int8 x int8 -> int32, M = 128, N = 128, K = 32 per instruction.
+// ptxas serves every thread that executes tcgen05.mma through a loop (ELECT, operands to uniform registers with R2UR, UTCIMMA),
+// and the R2UR moves are what limits the issue rate of a 64-cycle instruction: only the two 32-bit words that really vary -- the
+// low words of the shared-memory descriptors -- are passed in registers; the high words (stride byte offset 1024 B, version 1,
+// SWIZZLE_128B), the instruction descriptor and the accumulator column are immediates (the CTA owns all 512 TMEM columns, so
+// its allocation starts at column 0, lane 0: checked at kernel start).
+//   shared-memory matrix descriptor of a K-major operand tile written by TMA with the 128-byte swizzle: rows of 128 bytes, 8-row
+//   groups 1024 bytes apart (bits 32-45 = 64), leading byte offset 1 (unused), version 1 (bits 46-47), layout 2 (bits 61-63);
+//   instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed 8 bit (bits 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0),
+//   N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__device__ __forceinline__ constexpr uint32_t tc_idesc_i8(int m, int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+constexpr uint32_t TC_DESC_HI_SW128 = 64u | (1u << 14) | (2u << 29);      // bits 32-63 of the descriptor
+__device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+template <int ACC>
+__device__ __forceinline__ void tc_mma_i8(uint32_t desc_a_lo, uint32_t desc_b_lo, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 td, id;\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "mov.b64 da, {%0, %3};\n\t"
+      "mov.b64 db, {%1, %3};\n\t"
+      "mov.b32 td, %4;\n\t"
+      "mov.b32 id, %5;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [td], da, db, id, p;\n\t"
+      "}" ::"r"(desc_a_lo), "r"(desc_b_lo), "r"(accumulate), "n"(TC_DESC_HI_SW128), "n"(ACC * I8_TILE), "n"(tc_idesc_i8(I8_TILE, I8_TILE)) : "memory");
 }
-// shared-memory matrix descriptor of a K-major operand tile written by TMA with the 128-byte swizzle: rows of 128 bytes,
-// 8-row groups 1024 bytes apart (stride byte offset), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t tc_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed 8 bit (bits 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0),
-// N >> 3 at bits 17-22, M >> 4 at bits 24-28
-__device__ __forceinline__ constexpr uint32_t tc_idesc_i8(int m, int n) {
-  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// the four K = 32 steps of one digit product on one 128-row chunk into accumulator ACC
+template <int ACC>
+__device__ __forceinline__ void tc_product(uint32_t da_lo, uint32_t db_lo, uint32_t accumulate) {
+  tc_mma_i8<ACC>(da_lo, db_lo, accumulate);
+#pragma unroll
+  for (int kk = 1; kk < I8_KC / 32; ++kk) tc_mma_i8<ACC>(da_lo + 2 * kk, db_lo + 2 * kk, 1u);   // 32 bytes of K further: start address + 32 B (>> 4 = 2)
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -106,10 +137,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 // ---- column exponents (once per target) ----------------------------------------------------------------------------------
@@ -135,12 +166,14 @@ __global__ void k_i8_scales(const unsigned long long* __restrict__ cmax, int p, 
 }
 
 // ---- digit planes of diag(sqrt w) X (per evaluation) -----------------------------------------------------------------------
-// Block = 128 rows x 64 columns; warp = 8 columns; lane = 4 consecutive rows: 1 KB coalesced loads of X per warp and column,
-// 128-byte coalesced stores per warp, column and plane.  q' = rint(x sqrt(w) 2^(E - e_j)) + B with B = sum_{i < k-1} 128 256^i:
+// Digit-plane layout in HBM: [chunk of 128 rows][plane][column][128 bytes], so that an operand tile of the GEMM (one plane, 128
+// columns, one chunk) is 16 KB of CONTIGUOUS memory (one DRAM page run instead of 128 segments a column apart).
+// Block = 128 rows (one chunk) x 64 columns; warp = 8 columns; lane = 4 consecutive rows: 1 KB coalesced loads of X per warp and
+// column, 128-byte coalesced stores per warp, column and plane; rows past N are written as zeros.  q' = rint(x sqrt(w) 2^(E - e_j)) + B with B = sum_{i < k-1} 128 256^i:
 // the bytes of q' are the digits, offset by 128 except the top one (balanced digits without a carry chain).
 __global__ void __launch_bounds__(256)
 k_i8_slice(const double* __restrict__ X, long long ld, const double* __restrict__ w, long long N, int p, const double* __restrict__ cs,
-           int k, long long ldn, int8_t* __restrict__ S, double bias, const int* skip_flag) {
+           int k, int8_t* __restrict__ S, double bias, const int* skip_flag) {
   if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const long long r = (long long)blockIdx.x * I8_SLICE_ROWS + 4 * lane;
@@ -176,7 +209,7 @@ k_i8_slice(const double* __restrict__ X, long long ld, const double* __restrict_
       else       { t01 = __byte_perm(hi[0], hi[1], sel); t23 = __byte_perm(hi[2], hi[3], sel); }
       uint32_t word = __byte_perm(t01, t23, 0x5410);
       if (s > 0) word ^= 0x80808080u;
-      *reinterpret_cast<uint32_t*>(S + ((size_t)s * p + j) * ldn + r) = word;
+      *reinterpret_cast<uint32_t*>(S + (((size_t)blockIdx.x * k + s) * p + j) * I8_KC + 4 * lane) = word;
     }
   }
 }
@@ -210,36 +243,38 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = C.tmem_base;
+  if (tmem != 0) __trap();                           // all 512 columns are ours: the MMA issue path hard-codes the base
 
   if (warp == 4) {
-    // ===== producer: claims items, feeds the tile ring
-    if (lane == 0) {
-      tma_prefetch_desc(&mapS);
-      unsigned n = 0;                                // tile slots handed out so far
-      for (unsigned iq = 0;; ++iq) {
-        const int e = iq % I8_IQ;
-        mbar_wait(&C.item_empty[e], ((iq / I8_IQ) & 1) ^ 1);
-        const int it = atomicAdd(counter, 1);
-        C.item[e] = it < nitems ? it : -1;
-        mbar_arrive(&C.item_full[e]);                // (mbarrier arrive has release semantics: the item index is visible to the waiters)
-        if (it >= nitems) break;
-        const I8Item im = items[it];
-        const I8Kind* kd = kinds + im.kind;
-        const int ntiles = kd->ntiles;
-        int tsl[I8_MAXT], tbk[I8_MAXT];
+    // ===== producer: claims items, feeds the tile ring (the warp stays converged; one elected lane issues)
+    if (elect_one()) tma_prefetch_desc(&mapS);
+    unsigned n = 0;                                  // tile slots handed out so far
+    for (unsigned iq = 0;; ++iq) {
+      const int e = iq % I8_IQ;
+      mbar_wait(&C.item_empty[e], ((iq / I8_IQ) & 1) ^ 1);
+      int it = 0;
+      if (lane == 0) it = atomicAdd(counter, 1);
+      it = __shfl_sync(0xffffffffu, it, 0);
+      if (lane == 0) { C.item[e] = it < nitems ? it : -1; mbar_arrive(&C.item_full[e]); }   // (arrive = release: the item index is visible to the waiters)
+      if (it >= nitems) break;
+      const I8Item im = items[it];
+      const I8Kind* kd = kinds + im.kind;
+      const int ntiles = kd->ntiles;
+      int tsl[I8_MAXT], tbk[I8_MAXT];
 #pragma unroll
-        for (int t = 0; t < I8_MAXT; ++t) { tsl[t] = t < ntiles ? kd->tile_slice[t] : 0; tbk[t] = t < ntiles ? kd->tile_blk[t] * I8_TILE : 0; }
-        for (int c = 0; c < im.nchunks; ++c) {
-          const int row0 = (im.chunk0 + c) * I8_KC;
+      for (int t = 0; t < I8_MAXT; ++t) { tsl[t] = t < ntiles ? kd->tile_slice[t] : 0; tbk[t] = t < ntiles ? kd->tile_blk[t] * I8_TILE : 0; }
+      for (int c = 0; c < im.nchunks; ++c) {
 #pragma unroll
-          for (int t = 0; t < I8_MAXT; ++t) {
-            if (t < ntiles) {
-              const unsigned sl = n % I8_RING, round = n / I8_RING;
-              mbar_wait(&C.empty[sl], (round & 1) ^ 1);
+        for (int t = 0; t < I8_MAXT; ++t) {
+          if (t < ntiles) {
+            const unsigned sl = n % I8_RING, round = n / I8_RING;
+            mbar_wait(&C.empty[sl], (round & 1) ^ 1);
+            if (elect_one()) {
               mbar_arrive_expect_tx(&C.full[sl], I8_TILE_BYTES);
-              tma_load_3d(tiles + (size_t)sl * I8_TILE_BYTES, &mapS, &C.full[sl], row0, tbk[t], tsl[t]);
-              ++n;
+              tma_load_4d(tiles + (size_t)sl * I8_TILE_BYTES, &mapS, &C.full[sl], 0, tbk[t], tsl[t], im.chunk0 + c);
             }
+            __syncwarp();
+            ++n;
           }
         }
       }
@@ -247,7 +282,6 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
     __syncwarp();
   } else if (warp == 5) {
     // ===== MMA issuer (one thread issues; the warp copies the kind of each item to shared memory together)
-    constexpr uint32_t idesc = tc_idesc_i8(I8_TILE, I8_TILE);
     unsigned n = 0, nitem = 0;
     for (unsigned iq = 0;; ++iq) {
       const int e = iq % I8_IQ;
@@ -263,27 +297,34 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
         for (int i = lane; i < (int)(sizeof(I8Kind) / sizeof(int)); i += 32) dst[i] = src[i];
       }
       __syncwarp();
-      if (lane == 0) {
+      {
         const int ntiles = C.kind.ntiles, npairs = C.kind.npairs;
         if (nitem > 0) { mbar_wait(&C.tmem_empty, (nitem - 1) & 1); tc_fence_after(); }   // the previous item's accumulators have been read
         uint32_t started = 0;
+        const uint32_t sbase = smem_u32(tiles);
         for (int c = 0; c < im.nchunks; ++c) {
           for (int t = 0; t < ntiles; ++t) { const unsigned m = n + t; mbar_wait(&C.full[m % I8_RING], (m / I8_RING) & 1); }
           tc_fence_after();
-          const uint32_t sbase = smem_u32(tiles);
-          for (int q = 0; q < npairs; ++q) {
-            const uint32_t g = (uint32_t)C.kind.pair_acc[q];
-            const uint64_t da = tc_desc_sw128(sbase + ((n + (unsigned)C.kind.pair_a[q]) % I8_RING) * I8_TILE_BYTES);
-            const uint64_t db = tc_desc_sw128(sbase + ((n + (unsigned)C.kind.pair_b[q]) % I8_RING) * I8_TILE_BYTES);
-#pragma unroll
-            for (int kk = 0; kk < I8_KC / 32; ++kk)    // 32 bytes of K per instruction: advance the start address by 32 B (>> 4 = 2)
-              tc_mma_i8(tmem + g * I8_TILE, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (kk > 0 || ((started >> g) & 1u)) ? 1u : 0u);
-            started |= 1u << g;
+          if (elect_one()) {
+            for (int q = 0; q < npairs; ++q) {
+              const uint32_t g = (uint32_t)C.kind.pair_acc[q];
+              const uint32_t da = tc_desc_lo(sbase + ((n + (unsigned)C.kind.pair_a[q]) % I8_RING) * I8_TILE_BYTES);
+              const uint32_t db = tc_desc_lo(sbase + ((n + (unsigned)C.kind.pair_b[q]) % I8_RING) * I8_TILE_BYTES);
+              const uint32_t accum = (started >> g) & 1u;
+              if (g == 0) tc_product<0>(da, db, accum);
+              else if (g == 1) tc_product<1>(da, db, accum);
+              else if (g == 2) tc_product<2>(da, db, accum);
+              else tc_product<3>(da, db, accum);
+              started |= 1u << g;
+            }
+            for (int t = 0; t < ntiles; ++t) tc_commit(&C.empty[(n + t) % I8_RING]);   // the slots are free once these MMAs have read them
+            if (c == im.nchunks - 1) tc_commit(&C.tmem_full);
           }
-          for (int t = 0; t < ntiles; ++t) tc_commit(&C.empty[(n + t) % I8_RING]);   // the slots are free once these MMAs have read them
+          __syncwarp();
+          // `started` is per lane: after the first chunk every accumulator of the kind has been written
+          started = 0xFu;
           n += ntiles;
         }
-        tc_commit(&C.tmem_full);
       }
       ++nitem;
       __syncwarp();
