@@ -87,7 +87,7 @@ struct gamc_ctx : gamc_ctx_base {
   unsigned long long* d_co_dbg = nullptr;   // GAMC_CO_DEBUG=1: time stamps and CTA placement of the pair, printed by gamc_eval_upto_tensor
   double* part_ll = nullptr; double* part_g = nullptr;
   // metric on the integer tensor cores (metric_i8.cuh): digit planes of diag(sqrt w) X, column exponents, per-CTA partial tiles
-  bool metric_i8 = false; int i8_k = 0, i8_smax = 0, i8_grid = 0, i8_nitems = 0, i8_ntiles = 0, i8_nslots = 0; long long i8_ldn = 0;
+  bool metric_i8 = false, i8_fused = false; int i8_k = 0, i8_smax = 0, i8_grid = 0, i8_nitems = 0, i8_ntiles = 0, i8_nslots = 0; long long i8_ldn = 0;
   int8_t* d_i8S = nullptr; double *d_i8cs = nullptr, *d_i8cg = nullptr; unsigned long long* d_i8cmax = nullptr;
   long long* d_i8acc = nullptr; size_t i8_acc_bytes = 0;   // [item counter (16 bytes) | int64 group sums [tile][slot][128 x 128]]
   I8Kind* d_i8kinds = nullptr; I8Item* d_i8items = nullptr; int* d_i8ints = nullptr; CUtensorMap mapS{};
@@ -440,15 +440,43 @@ gamc_status launch_metric_fused(gamc_ctx* h, const double* theta, const int* ski
 
 // Metric on the integer tensor cores: digit planes of diag(sqrt w) X (k_i8_slice, after the gradient pass has written w), then the
 // int8 GEMMs (k_metric_i8: TMA -> tcgen05.mma kind::i8 -> TMEM), partial tiles summed by k_reduce_i8 inside launch_reduce.
+static double i8_bias(int k) { double b = 0.0; for (int i = 0; i + 1 < k; ++i) b += ldexp(128.0, 8 * i); return b; }
+
+// gradient pass that also writes the digit planes (one read of X for the whole level-2 evaluation of the integer route)
+template <int NU>
+gamc_status launch_dp_i8_t(gamc_ctx* h, const double* theta, const int* skip) {
+  const int grid = h->dp_grid_now > 0 ? h->dp_grid_now : h->dp_grid;
+  auto kern = k_datapass_i8<NU>;
+  { gamc_status s = ensure_attr(h, (const void*)kern, sizeof(DataPassI8Smem)); if (s != GAMC_OK) return s; }
+  ProfScope ps(h, GAMC_K_LOGLIK_GRAD);
+  kern<<<grid, DP_THREADS, sizeof(DataPassI8Smem), h->stream>>>(h->mapXA, h->dy, theta, h->p, h->N, h->dw, h->part_ll, h->part_g, h->part_g_stride,
+                                                                   h->d_i8cs, h->i8_k, h->d_i8S, i8_bias(h->i8_k), skip);
+  CUDA_TRY(h, cudaGetLastError());
+  return GAMC_OK;
+}
+gamc_status launch_dp_i8(gamc_ctx* h, const double* theta, const int* skip) {
+  switch (h->dp_nu) {
+    case 1: return launch_dp_i8_t<1>(h, theta, skip);
+    case 2: return launch_dp_i8_t<2>(h, theta, skip);
+    case 3: return launch_dp_i8_t<3>(h, theta, skip);
+    case 4: return launch_dp_i8_t<4>(h, theta, skip);
+    case 5: return launch_dp_i8_t<5>(h, theta, skip);
+    case 6: return launch_dp_i8_t<6>(h, theta, skip);
+    case 7: return launch_dp_i8_t<7>(h, theta, skip);
+    case 8: return launch_dp_i8_t<8>(h, theta, skip);
+    default: h->err = "unsupported number of column units"; return GAMC_UNSUPPORTED_SHAPE;
+  }
+}
+
 gamc_status launch_metric_i8(gamc_ctx* h, const int* skip = nullptr) {
   { gamc_status s = ensure_attr(h, (const void*)k_metric_i8, I8_SMEM_BYTES); if (s != GAMC_OK) return s; }
   ProfScope ps(h, GAMC_K_METRIC);
-  h->launches += 1;   // two kernels in this scope
-  const dim3 sgrid((unsigned)((h->N + I8_SLICE_ROWS - 1) / I8_SLICE_ROWS), (unsigned)((h->p + I8_SLICE_COLS - 1) / I8_SLICE_COLS));
-  double bias = 0.0;
-  for (int i = 0; i + 1 < h->i8_k; ++i) bias += ldexp(128.0, 8 * i);
-  k_i8_slice<<<sgrid, 256, 0, h->stream>>>(h->dX, h->ld, h->dw, h->N, h->p, h->d_i8cs, h->i8_k, h->d_i8S, bias, skip);
-  CUDA_TRY(h, cudaGetLastError());
+  if (!h->i8_fused) {
+    h->launches += 1;   // two kernels in this scope
+    const dim3 sgrid((unsigned)((h->N + I8_SLICE_ROWS - 1) / I8_SLICE_ROWS), (unsigned)((h->p + I8_SLICE_COLS - 1) / I8_SLICE_COLS));
+    k_i8_slice<<<sgrid, 256, 0, h->stream>>>(h->dX, h->ld, h->dw, h->N, h->p, h->d_i8cs, h->i8_k, h->d_i8S, i8_bias(h->i8_k), skip);
+    CUDA_TRY(h, cudaGetLastError());
+  }
   CUDA_TRY(h, cudaMemsetAsync(h->d_i8acc, 0, h->i8_acc_bytes, h->stream));   // item counter and int64 group sums
   k_metric_i8<<<h->i8_grid, I8_THREADS, I8_SMEM_BYTES, h->stream>>>(h->mapS, h->d_i8kinds, h->d_i8items, h->i8_nitems, reinterpret_cast<int*>(h->d_i8acc),
                                                                     h->d_i8acc + 2, h->i8_nslots, skip);
@@ -498,7 +526,7 @@ gamc_status eval_callback(gamc_ctx* h, const double* d_theta, int level) {
 // otherwise the gradient pass followed by the metric pass.
 gamc_status launch_level2(gamc_ctx* h, const double* d_theta, const int* skip = nullptr) {
   if (h->metric_i8) {
-    gamc_status s8 = launch_datapass(h, d_theta, true, skip);
+    gamc_status s8 = h->i8_fused ? launch_dp_i8(h, d_theta, skip) : launch_datapass(h, d_theta, true, skip);
     if (s8 != GAMC_OK) return s8;
     return launch_metric_i8(h, skip);
   }
@@ -678,9 +706,11 @@ gamc_status setup_metric_i8(gamc_ctx* h, int k, int smax) {
   REQUIRE(h, k >= 2 && k <= I8_MAXK && smax >= 2 && smax <= 2 * k, GAMC_INVALID_ARG, "metric_i8: 2 <= slices <= 7, 2 <= smax <= 2 slices");
   REQUIRE(h, h->N < (1ll << 31) - 256, GAMC_UNSUPPORTED_SHAPE, "metric_i8: too many rows for one rank");
   h->i8_k = k; h->i8_smax = smax;
-  h->i8_ldn = (h->N + I8_KC - 1) / I8_KC * I8_KC;
+  h->i8_ldn = (h->N + I8_SLICE_ROWS - 1) / I8_SLICE_ROWS * I8_SLICE_ROWS;
   const long long nchunks = h->i8_ldn / I8_KC;
   CUDA_TRY(h, cudaMalloc(&h->d_i8S, (size_t)k * p * h->i8_ldn));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_i8S, 0, (size_t)k * p * h->i8_ldn, h->stream));   // rows between N and the end of the last chunk stay zero
+  { const char* ef = getenv("GAMC_I8_FUSED"); h->i8_fused = h->dp_rpl == 1 && !(ef && atoi(ef) == 0); }
   CUDA_TRY(h, cudaMalloc(&h->d_i8cs, sizeof(double) * p));
   CUDA_TRY(h, cudaMalloc(&h->d_i8cg, sizeof(double) * p));
   CUDA_TRY(h, cudaMalloc(&h->d_i8cmax, sizeof(unsigned long long) * p));
@@ -699,7 +729,7 @@ gamc_status setup_metric_i8(gamc_ctx* h, int k, int smax) {
     cuuint32_t box[4] = {(cuuint32_t)I8_KC, (cuuint32_t)I8_TILE, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = g_encode(&h->mapS, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)h->d_i8S, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          I8_KC == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled(digit planes) failed with code " + std::to_string((int)r); return GAMC_CUDA_ERROR; }
   }
   int block_chunks = 0;
@@ -1838,7 +1868,7 @@ long long gamc_debug_guard_check(long long* n_allocations) {
 }
 #endif
 
-// Debug read-out of the integer-tensor-core metric (tests/test_gpu_i8.py): what = 0: digit planes [chunk][k][p][128] int8 (as written by the last
+// Debug read-out of the integer-tensor-core metric (tests/test_gpu_i8.py): what = 0: digit planes [chunk][k][p][I8_KC] int8 (as written by the last
 // level-2 evaluation), 1: column scales cg[p] (double), 2: {k, smax, ldn, grid} as four int64.  Not part of the public header.
 int gamc_debug_i8_read(gamc_handle h, int what, void* out, long long bytes) {
   if (!h || !h->metric_i8) return 1;
@@ -1855,7 +1885,7 @@ int gamc_debug_i8_read(gamc_handle h, int what, void* out, long long bytes) {
   if (what == 2) {
     if (bytes < 32) return 2;
     long long* o = reinterpret_cast<long long*>(out);
-    o[0] = h->i8_k; o[1] = h->i8_smax; o[2] = h->i8_ldn; o[3] = h->i8_nitems;
+    o[0] = h->i8_k; o[1] = h->i8_smax; o[2] = h->i8_ldn; o[3] = I8_KC;
     return 0;
   }
   return 4;

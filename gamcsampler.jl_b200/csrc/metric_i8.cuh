@@ -18,12 +18,29 @@
 // issuer / TMEM epilogue with exact int64 atomics), k_reduce_i8 (weights, column scales, landing buffer).
 #pragma once
 #include "common.cuh"
+#include "datapass.cuh"
 
 namespace gamc {
 
+#ifdef GAMC_PHASE_CLOCKS
+#define I8_CLK_DECL(v) long long v = 0
+#define I8_CLK_T(t) const long long t = clock64()
+#define I8_CLK_ADD(v, t0) v += clock64() - (t0)
+#define I8_CLK_OUT(k, v) do { if ((threadIdx.x & 31) == 0) { atomicAdd((unsigned long long*)&g_phase_acc[k], (unsigned long long)(v)); atomicAdd((unsigned long long*)&g_phase_cnt[k], 1ull); } } while (0)
+#else
+#define I8_CLK_DECL(v) do { } while (0)
+#define I8_CLK_T(t) do { } while (0)
+#define I8_CLK_ADD(v, t0) do { } while (0)
+#define I8_CLK_OUT(k, v) do { } while (0)
+#endif
+
 constexpr int I8_TILE = 128;                       // columns of X per operand tile = edge of an output tile
-constexpr int I8_KC = 128;                         // rows (the contraction index) per chunk = one 128-byte swizzle row
-constexpr int I8_TILE_BYTES = I8_TILE * I8_KC;     // 16 KB
+#ifndef GAMC_I8_KC
+#define GAMC_I8_KC 128
+#endif
+constexpr int I8_KC = GAMC_I8_KC;                  // rows (the contraction index) per chunk = one swizzle row of 64 or 128 bytes
+static_assert(I8_KC == 64 || I8_KC == 128, "chunk = one SWIZZLE_64B or SWIZZLE_128B row");
+constexpr int I8_TILE_BYTES = I8_TILE * I8_KC;     // 8 KB (16 KB): finer tiles leave more of the ring in flight while a chunk is consumed
 constexpr int I8_MAXT = 6;                         // operand tiles per stage
 constexpr int I8_MAXP = 12;                        // digit products per kind
 constexpr int I8_MAXACC = 4;                       // accumulators of 128 TMEM columns: all 512 columns of the SM
@@ -48,7 +65,7 @@ struct I8Kind {
 // which the reduction adds together with its transpose (D_a' D_b + D_b' D_a).
 struct I8Item { int kind, chunk0, nchunks; };
 
-constexpr int I8_RING = 13;                        // operand tile slots of 16 KB (ring; a chunk takes the kind's ntiles consecutive slots)
+constexpr int I8_RING = 13 * 16384 / I8_TILE_BYTES;   // operand tile slots (208 KB ring; a chunk takes the kind's ntiles consecutive slots)
 constexpr int I8_IQ = 4;                           // items in flight between the producer and the other roles
 struct I8Ctl {
   alignas(8) uint64_t full[I8_RING];
@@ -58,6 +75,7 @@ struct I8Ctl {
   uint32_t tmem_base;
   int item[I8_IQ];
   I8Kind kind;                                     // the MMA issuer's copy of the current item's kind
+  uint32_t pk[I8_MAXP];                            // its digit products, packed: A tile | B tile << 8 | accumulator << 16
 };
 constexpr size_t I8_SMEM_BYTES = (size_t)I8_RING * I8_TILE_BYTES + 1024 + sizeof(I8Ctl);
 
@@ -94,14 +112,15 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 // low words of the shared-memory descriptors -- are passed in registers; the high words (stride byte offset 1024 B, version 1,
 // SWIZZLE_128B), the instruction descriptor and the accumulator column are immediates (the CTA owns all 512 TMEM columns, so
 // its allocation starts at column 0, lane 0: checked at kernel start).
-//   shared-memory matrix descriptor of a K-major operand tile written by TMA with the 128-byte swizzle: rows of 128 bytes, 8-row
-//   groups 1024 bytes apart (bits 32-45 = 64), leading byte offset 1 (unused), version 1 (bits 46-47), layout 2 (bits 61-63);
+//   shared-memory matrix descriptor of a K-major operand tile written by TMA with the 128-byte (64-byte) swizzle: rows of I8_KC
+//   bytes, 8-row groups 8 I8_KC bytes apart (stride byte offset, bits 32-45), leading byte offset 1 (unused), version 1 (bits 46-47),
+//   layout 2 = SWIZZLE_128B or 4 = SWIZZLE_64B (bits 61-63);
 //   instruction descriptor: D = s32 (bits 4-5 = 2), A and B signed 8 bit (bits 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0),
 //   N >> 3 at bits 17-22, M >> 4 at bits 24-28.
 __device__ __forceinline__ constexpr uint32_t tc_idesc_i8(int m, int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-constexpr uint32_t TC_DESC_HI_SW128 = 64u | (1u << 14) | (2u << 29);      // bits 32-63 of the descriptor
+constexpr uint32_t TC_DESC_HI_SW128 = (uint32_t)(8 * I8_KC / 16) | (1u << 14) | ((I8_KC == 128 ? 2u : 4u) << 29);   // bits 32-63 of the descriptor (layout 4 = SWIZZLE_64B)
 __device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 template <int ACC>
 __device__ __forceinline__ void tc_mma_i8(uint32_t desc_a_lo, uint32_t desc_b_lo, uint32_t accumulate) {
@@ -116,7 +135,7 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t desc_a_lo, uint32_t desc_b_lo
       "mov.b32 td, %4;\n\t"
       "mov.b32 id, %5;\n\t"
       "tcgen05.mma.cta_group::1.kind::i8 [td], da, db, id, p;\n\t"
-      "}" ::"r"(desc_a_lo), "r"(desc_b_lo), "r"(accumulate), "n"(TC_DESC_HI_SW128), "n"(ACC * I8_TILE), "n"(tc_idesc_i8(I8_TILE, I8_TILE)) : "memory");
+      "}" ::"r"(desc_a_lo), "r"(desc_b_lo), "r"(accumulate), "n"(TC_DESC_HI_SW128), "n"(ACC * I8_TILE), "n"(tc_idesc_i8(I8_TILE, I8_TILE)));
 }
 // the four K = 32 steps of one digit product on one 128-row chunk into accumulator ACC
 template <int ACC>
@@ -166,8 +185,8 @@ __global__ void k_i8_scales(const unsigned long long* __restrict__ cmax, int p, 
 }
 
 // ---- digit planes of diag(sqrt w) X (per evaluation) -----------------------------------------------------------------------
-// Digit-plane layout in HBM: [chunk of 128 rows][plane][column][128 bytes], so that an operand tile of the GEMM (one plane, 128
-// columns, one chunk) is 16 KB of CONTIGUOUS memory (one DRAM page run instead of 128 segments a column apart).
+// Digit-plane layout in HBM: [chunk of I8_KC rows][plane][column][I8_KC bytes], so that an operand tile of the GEMM (one plane, 128
+// columns, one chunk) is 8 KB (16 KB) of CONTIGUOUS memory (one DRAM page run instead of 128 segments a column apart).
 // Block = 128 rows (one chunk) x 64 columns; warp = 8 columns; lane = 4 consecutive rows: 1 KB coalesced loads of X per warp and
 // column, 128-byte coalesced stores per warp, column and plane; rows past N are written as zeros.  q' = rint(x sqrt(w) 2^(E - e_j)) + B with B = sum_{i < k-1} 128 256^i:
 // the bytes of q' are the digits, offset by 128 except the top one (balanced digits without a carry chain).
@@ -177,6 +196,8 @@ k_i8_slice(const double* __restrict__ X, long long ld, const double* __restrict_
   if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const long long r = (long long)blockIdx.x * I8_SLICE_ROWS + 4 * lane;
+  const size_t chunk = (size_t)(r / I8_KC);
+  const int coff = (int)(r % I8_KC);
   double sw[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) sw[u] = (r + u < N) ? sqrt(w[r + u]) : 0.0;
@@ -209,7 +230,160 @@ k_i8_slice(const double* __restrict__ X, long long ld, const double* __restrict_
       else       { t01 = __byte_perm(hi[0], hi[1], sel); t23 = __byte_perm(hi[2], hi[3], sel); }
       uint32_t word = __byte_perm(t01, t23, 0x5410);
       if (s > 0) word ^= 0x80808080u;
-      *reinterpret_cast<uint32_t*>(S + (((size_t)blockIdx.x * k + s) * p + j) * I8_KC + 4 * lane) = word;
+      *reinterpret_cast<uint32_t*>(S + ((chunk * k + s) * p + j) * I8_KC + coff) = word;
+    }
+  }
+}
+
+// ---- gradient pass + digit planes in ONE read of X ------------------------------------------------------------------------
+// k_datapass_i8<NU>: k_datapass<NU, 1, true> (log-likelihood, gradient, weights; same TMA ring, same phase 1, so the scalar is
+// bit-identical) whose phase 2 also cuts diag(sqrt w) X into digit planes while the row block is still resident in shared memory:
+// the level-2 evaluation of the integer route reads X once (k_i8_slice would read it a second time).  Phase 2 mapping: lane =
+// 4 consecutive rows (lane & 7) x 2 of the warp's 8 columns per unit (lane >> 3, + 4): 32-byte shared loads without bank
+// conflicts, and the four digits of one plane and column go out as one 32-bit store (a quarter-warp writes one 32-byte sector).
+struct DataPassI8Smem {
+  alignas(128) double ring[DP_NSLOT][DP_UNIT_DOUBLES];
+  double theta[512];
+  double cs[512];
+  double red[2][DP_CONSUMER_WARPS][32];
+  alignas(8) uint64_t full_bar[DP_NSLOT];
+  alignas(8) uint64_t empty_bar[DP_NSLOT];
+};
+
+template <int NU>
+__global__ void __launch_bounds__(DP_THREADS, 1)
+k_datapass_i8(const __grid_constant__ CUtensorMap mapX, const double* __restrict__ y, const double* __restrict__ theta, int p, long long N,
+              double* __restrict__ w_out, double* __restrict__ part_ll, double* __restrict__ part_g, int part_g_stride,
+              const double* __restrict__ cs, int k, int8_t* __restrict__ S8, double bias, const int* skip_flag) {
+  if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;
+  constexpr int RB = 32, CU = 64, CPW = CU / DP_CONSUMER_WARPS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  DataPassI8Smem& S = *reinterpret_cast<DataPassI8Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long nrb = (N + RB - 1) / RB;
+
+  for (int c = tid; c < NU * CU; c += DP_THREADS) { S.theta[c] = (c < p) ? theta[c] : 0.0; S.cs[c] = (c < p) ? cs[c] : 0.0; }
+  if (tid == 0) {
+    for (int s = 0; s < DP_NSLOT; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], DP_CONSUMER_WARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == DP_CONSUMER_WARPS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&mapX);
+      unsigned q = 0;
+      for (long long rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+#pragma unroll 1
+        for (int u = 0; u < NU; ++u, ++q) {
+          const unsigned slot = q % DP_NSLOT, round = q / DP_NSLOT;
+          mbar_wait(&S.empty_bar[slot], (round & 1) ^ 1);
+          mbar_arrive_expect_tx(&S.full_bar[slot], DP_UNIT_DOUBLES * 8);
+          tma_load_2d(S.ring[slot], &mapX, &S.full_bar[slot], (int)(rb * RB), u * CU);
+        }
+      }
+    }
+    return;
+  }
+
+  const int rg = lane & 7, cg = lane >> 3;
+  // bytes 0 .. k-2 of q' carry digit + 128: one XOR turns them into the signed digits
+  unsigned long long xmask = 0;
+  for (int b = 0; b + 1 < k; ++b) xmask |= 0x80ull << (8 * b);
+  const uint32_t xlo = (uint32_t)xmask, xhi = (uint32_t)(xmask >> 32);
+  const size_t plane_stride = (size_t)p * I8_KC;
+  double gacc[NU * 2];
+#pragma unroll
+  for (int i = 0; i < NU * 2; ++i) gacc[i] = 0.0;
+  double ll = 0.0;
+  unsigned q = 0;
+  int it = 0;
+  for (long long rb = blockIdx.x; rb < nrb; rb += gridDim.x, ++it) {
+    const long long row0 = rb * RB + lane;
+    const double yv = (row0 < N) ? __ldg(&y[row0]) : 0.0;
+    // ---- phase 1 (as k_datapass): eta partial over this warp's columns, lane = row
+    double eta = 0.0;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const unsigned qq = q + u, slot = qq % DP_NSLOT, round = qq / DP_NSLOT;
+      mbar_wait(&S.full_bar[slot], round & 1);
+      const double* base = &S.ring[slot][(warp * CPW) * RB + lane];
+      const double* th = &S.theta[u * CU + warp * CPW];
+#pragma unroll
+      for (int jj = 0; jj < CPW; ++jj) eta = fma(base[jj * RB], th[jj], eta);
+    }
+    double* red = &S.red[it & 1][0][0];
+    red[warp * 32 + lane] = eta;
+    asm volatile("bar.sync 1, %0;" ::"n"(DP_CONSUMER_WARPS * 32) : "memory");
+    double e = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < DP_CONSUMER_WARPS; ++w2) e += red[w2 * 32 + lane];
+    double sig, sp;
+    sigmoid_softplus(e, sig, sp);
+    const bool valid = row0 < N;
+    const double rres = valid ? (yv - sig) : 0.0;
+    const double wv = valid ? sig * (1.0 - sig) : 0.0;
+    if (warp == 0) {
+      ll += valid ? (yv * e - sp) : 0.0;
+      if (valid) w_out[row0] = wv;
+    }
+    const double sw = sqrt(wv);
+    // ---- phase 2: gradient partials and digit planes from the still-resident units; lane = rows 4 rg .. 4 rg + 3
+    double rr[4], ss[4];
+#pragma unroll
+    for (int u4 = 0; u4 < 4; ++u4) { rr[u4] = __shfl_sync(0xffffffffu, rres, 4 * rg + u4); ss[u4] = __shfl_sync(0xffffffffu, sw, 4 * rg + u4); }
+    const long long row = rb * RB + 4 * rg;
+    int8_t* out0 = S8 + ((size_t)(row / I8_KC) * k + (size_t)(k - 1)) * plane_stride + (size_t)(row % I8_KC);   // plane k-1 = byte 0 of q'
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const unsigned qq = q + u, slot = qq % DP_NSLOT;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int cl = warp * CPW + cg + 4 * jj;
+        const double2 xa = *reinterpret_cast<const double2*>(&S.ring[slot][cl * RB + 4 * rg]);
+        const double2 xb = *reinterpret_cast<const double2*>(&S.ring[slot][cl * RB + 4 * rg + 2]);
+        double a = gacc[u * 2 + jj];
+        a = fma(xa.x, rr[0], a); a = fma(xa.y, rr[1], a); a = fma(xb.x, rr[2], a); a = fma(xb.y, rr[3], a);
+        gacc[u * 2 + jj] = a;
+        const int j = u * CU + cl;
+        if (j < p) {
+          const double c = S.cs[j];
+          const long long q0 = __double2ll_rn(fma(xa.x * ss[0], c, bias)), q1 = __double2ll_rn(fma(xa.y * ss[1], c, bias));
+          const long long q2 = __double2ll_rn(fma(xb.x * ss[2], c, bias)), q3 = __double2ll_rn(fma(xb.y * ss[3], c, bias));
+          const uint32_t l0 = (uint32_t)q0 ^ xlo, l1 = (uint32_t)q1 ^ xlo, l2 = (uint32_t)q2 ^ xlo, l3 = (uint32_t)q3 ^ xlo;
+          const uint32_t h0 = (uint32_t)((unsigned long long)q0 >> 32) ^ xhi, h1 = (uint32_t)((unsigned long long)q1 >> 32) ^ xhi;
+          const uint32_t h2 = (uint32_t)((unsigned long long)q2 >> 32) ^ xhi, h3 = (uint32_t)((unsigned long long)q3 >> 32) ^ xhi;
+          int8_t* o = out0 + (size_t)j * I8_KC;
+#pragma unroll
+          for (int b = 0; b < I8_MAXK; ++b) {
+            if (b < k) {
+              const uint32_t sel = (uint32_t)(b & 3) | ((uint32_t)(4 + (b & 3)) << 4);
+              const uint32_t t01 = b < 4 ? __byte_perm(l0, l1, sel) : __byte_perm(h0, h1, sel);
+              const uint32_t t23 = b < 4 ? __byte_perm(l2, l3, sel) : __byte_perm(h2, h3, sel);
+              *reinterpret_cast<uint32_t*>(o - (size_t)b * plane_stride) = __byte_perm(t01, t23, 0x5410);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.empty_bar[slot]);
+    }
+    q += NU;
+  }
+
+  if (warp == 0) {
+    ll = warp_sum(ll);
+    if (lane == 0) part_ll[blockIdx.x] = ll;
+  }
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      double v = gacc[u * 2 + jj];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (rg == 0) part_g[(size_t)blockIdx.x * part_g_stride + u * CU + warp * CPW + cg + 4 * jj] = v;
     }
   }
 }
@@ -249,6 +423,7 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
     // ===== producer: claims items, feeds the tile ring (the warp stays converged; one elected lane issues)
     if (elect_one()) tma_prefetch_desc(&mapS);
     unsigned n = 0;                                  // tile slots handed out so far
+    I8_CLK_DECL(clk_pw); I8_CLK_DECL(clk_pt); I8_CLK_T(tp0);
     for (unsigned iq = 0;; ++iq) {
       const int e = iq % I8_IQ;
       mbar_wait(&C.item_empty[e], ((iq / I8_IQ) & 1) ^ 1);
@@ -268,7 +443,7 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
         for (int t = 0; t < I8_MAXT; ++t) {
           if (t < ntiles) {
             const unsigned sl = n % I8_RING, round = n / I8_RING;
-            mbar_wait(&C.empty[sl], (round & 1) ^ 1);
+            { I8_CLK_T(tw); mbar_wait(&C.empty[sl], (round & 1) ^ 1); I8_CLK_ADD(clk_pw, tw); }
             if (elect_one()) {
               mbar_arrive_expect_tx(&C.full[sl], I8_TILE_BYTES);
               tma_load_4d(tiles + (size_t)sl * I8_TILE_BYTES, &mapS, &C.full[sl], 0, tbk[t], tsl[t], im.chunk0 + c);
@@ -279,10 +454,12 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
         }
       }
     }
+    I8_CLK_ADD(clk_pt, tp0); I8_CLK_OUT(62, clk_pw); I8_CLK_OUT(63, clk_pt);
     __syncwarp();
   } else if (warp == 5) {
     // ===== MMA issuer (one thread issues; the warp copies the kind of each item to shared memory together)
     unsigned n = 0, nitem = 0;
+    I8_CLK_DECL(clk_wf); I8_CLK_DECL(clk_wt); I8_CLK_DECL(clk_is); I8_CLK_DECL(clk_tot); I8_CLK_T(tm0);
     for (unsigned iq = 0;; ++iq) {
       const int e = iq % I8_IQ;
       mbar_wait(&C.item_full[e], (iq / I8_IQ) & 1);
@@ -295,21 +472,29 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
         const int* src = reinterpret_cast<const int*>(kinds + im.kind);
         int* dst = reinterpret_cast<int*>(&C.kind);
         for (int i = lane; i < (int)(sizeof(I8Kind) / sizeof(int)); i += 32) dst[i] = src[i];
+        if (lane < I8_MAXP) C.pk[lane] = (uint32_t)kinds[im.kind].pair_a[lane] | ((uint32_t)kinds[im.kind].pair_b[lane] << 8) | ((uint32_t)kinds[im.kind].pair_acc[lane] << 16);
       }
       __syncwarp();
       {
         const int ntiles = C.kind.ntiles, npairs = C.kind.npairs;
-        if (nitem > 0) { mbar_wait(&C.tmem_empty, (nitem - 1) & 1); tc_fence_after(); }   // the previous item's accumulators have been read
+        if (nitem > 0) { I8_CLK_T(tw); mbar_wait(&C.tmem_empty, (nitem - 1) & 1); tc_fence_after(); I8_CLK_ADD(clk_wt, tw); }   // the previous item's accumulators have been read
         uint32_t started = 0;
         const uint32_t sbase = smem_u32(tiles);
+        const uint32_t d0 = tc_desc_lo(sbase);
         for (int c = 0; c < im.nchunks; ++c) {
-          for (int t = 0; t < ntiles; ++t) { const unsigned m = n + t; mbar_wait(&C.full[m % I8_RING], (m / I8_RING) & 1); }
+          const unsigned base = n % I8_RING, par = (n / I8_RING) & 1;
+          { I8_CLK_T(tw);
+            for (int t = 0; t < ntiles; ++t) { const unsigned m = base + t; if (m < I8_RING) mbar_wait(&C.full[m], par); else mbar_wait(&C.full[m - I8_RING], par ^ 1); }
+            I8_CLK_ADD(clk_wf, tw); }
           tc_fence_after();
+          I8_CLK_T(ti);
           if (elect_one()) {
             for (int q = 0; q < npairs; ++q) {
-              const uint32_t g = (uint32_t)C.kind.pair_acc[q];
-              const uint32_t da = tc_desc_lo(sbase + ((n + (unsigned)C.kind.pair_a[q]) % I8_RING) * I8_TILE_BYTES);
-              const uint32_t db = tc_desc_lo(sbase + ((n + (unsigned)C.kind.pair_b[q]) % I8_RING) * I8_TILE_BYTES);
+              const uint32_t pk = C.pk[q];
+              unsigned sa = base + (pk & 0xFFu), sb = base + ((pk >> 8) & 0xFFu);
+              sa -= sa >= I8_RING ? I8_RING : 0; sb -= sb >= I8_RING ? I8_RING : 0;
+              const uint32_t da = d0 + sa * (I8_TILE_BYTES >> 4), db = d0 + sb * (I8_TILE_BYTES >> 4);
+              const uint32_t g = pk >> 16;
               const uint32_t accum = (started >> g) & 1u;
               if (g == 0) tc_product<0>(da, db, accum);
               else if (g == 1) tc_product<1>(da, db, accum);
@@ -317,10 +502,11 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
               else tc_product<3>(da, db, accum);
               started |= 1u << g;
             }
-            for (int t = 0; t < ntiles; ++t) tc_commit(&C.empty[(n + t) % I8_RING]);   // the slots are free once these MMAs have read them
+            for (int t = 0; t < ntiles; ++t) { unsigned m = base + t; m -= m >= I8_RING ? I8_RING : 0; tc_commit(&C.empty[m]); }   // the slots are free once these MMAs have read them
             if (c == im.nchunks - 1) tc_commit(&C.tmem_full);
           }
           __syncwarp();
+          I8_CLK_ADD(clk_is, ti);
           // `started` is per lane: after the first chunk every accumulator of the kind has been written
           started = 0xFu;
           n += ntiles;
@@ -329,6 +515,7 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
       ++nitem;
       __syncwarp();
     }
+    I8_CLK_ADD(clk_tot, tm0); I8_CLK_OUT(58, clk_wf); I8_CLK_OUT(59, clk_wt); I8_CLK_OUT(60, clk_is); I8_CLK_OUT(61, clk_tot);
   } else {
     // ===== epilogue: warp q reads TMEM lanes 32 q .. 32 q + 31 (= rows i of the output tile), thread = row
     const int i = warp * 32 + lane;

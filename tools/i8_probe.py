@@ -46,7 +46,8 @@ def main():
     ldn = int(info[2])
     buf = np.empty(k * a.p * ldn, dtype=np.int8)
     assert lib.gamc_debug_i8_read(eng.h, 0, buf.ctypes.data_as(C.c_void_p), buf.nbytes) == 0
-    planes_dev = buf.reshape(ldn // 128, k, a.p, 128).transpose(1, 2, 0, 3).reshape(k, a.p, ldn)[:, :, :a.N]
+    kc = int(info[3])
+    planes_dev = buf.reshape(ldn // kc, k, a.p, kc).transpose(1, 2, 0, 3).reshape(k, a.p, ldn)[:, :, :a.N]
     w = sig * (1.0 - sig)
     planes_ref, e = i8_ref.digit_planes(X, w, k)
     ndiff = int(np.count_nonzero(planes_dev != planes_ref))
