@@ -87,6 +87,7 @@ struct gamc_ctx : gamc_ctx_base {
   unsigned long long* d_co_dbg = nullptr;   // GAMC_CO_DEBUG=1: time stamps and CTA placement of the pair, printed by gamc_eval_upto_tensor
   double* part_ll = nullptr; double* part_g = nullptr;
   // metric on the integer tensor cores (metric_i8.cuh): digit planes of diag(sqrt w) X, column exponents, per-CTA partial tiles
+  int metric_route = 0, route_slices = 0, route_smax = 0;   // gamc_set_metric_route
   bool metric_i8 = false, i8_fused = false; int i8_k = 0, i8_smax = 0, i8_grid = 0, i8_nitems = 0, i8_ntiles = 0, i8_nslots = 0; long long i8_ldn = 0;
   int8_t* d_i8S = nullptr; double *d_i8cs = nullptr, *d_i8cg = nullptr; unsigned long long* d_i8cmax = nullptr;
   long long* d_i8acc = nullptr; size_t i8_acc_bytes = 0;   // [item counter (16 bytes) | int64 group sums [tile][slot][128 x 128]]
@@ -449,7 +450,7 @@ gamc_status launch_dp_i8_t(gamc_ctx* h, const double* theta, const int* skip) {
   auto kern = k_datapass_i8<NU>;
   { gamc_status s = ensure_attr(h, (const void*)kern, sizeof(DataPassI8Smem)); if (s != GAMC_OK) return s; }
   ProfScope ps(h, GAMC_K_LOGLIK_GRAD);
-  kern<<<grid, DP_THREADS, sizeof(DataPassI8Smem), h->stream>>>(h->mapXA, h->dy, theta, h->p, h->N, h->dw, h->part_ll, h->part_g, h->part_g_stride,
+  kern<<<grid, DPI_THREADS, sizeof(DataPassI8Smem), h->stream>>>(h->mapXA, h->dy, theta, h->p, h->N, h->dw, h->part_ll, h->part_g, h->part_g_stride,
                                                                    h->d_i8cs, h->i8_k, h->d_i8S, i8_bias(h->i8_k), skip);
   CUDA_TRY(h, cudaGetLastError());
   return GAMC_OK;
@@ -690,11 +691,16 @@ gamc_status setup_target(gamc_ctx* h) {
   CUDA_TRY(h, cudaMalloc(&h->d_coords, sizeof(TaskCoord) * h->ntasks));
   CUDA_TRY(h, cudaMemcpyAsync(h->d_coords, h->layout.coords.data(), sizeof(TaskCoord) * h->ntasks, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMalloc(&h->ws, sizeof(double) * (size_t)h->layout.max_nsplit * h->ntasks * MT_BLK * MT_BLK));
-  if (const char* e8 = getenv("GAMC_METRIC_I8")) {
-    // GAMC_METRIC_I8 = "1" (6 digit planes, digit products with a + b <= 7) or "k,smax"
-    int k = 6, smax = 7;
-    if (sscanf(e8, "%d,%d", &k, &smax) < 2) { k = 6; smax = 7; }
-    if (atoi(e8) != 0) { gamc_status s8 = setup_metric_i8(h, k, smax); if (s8 != GAMC_OK) return s8; }
+  {
+    // metric route (gamc_set_metric_route; GAMC_METRIC_I8 = "0" | "1" | "slices,smax" overrides it)
+    int route = h->metric_route, k = h->route_slices > 0 ? h->route_slices : 6, smax = h->route_smax > 0 ? h->route_smax : k + 1;
+    if (const char* e8 = getenv("GAMC_METRIC_I8")) {
+      int ek = 0, es = 0;
+      if (sscanf(e8, "%d,%d", &ek, &es) == 2) { route = GAMC_METRIC_I8; k = ek; smax = es; }
+      else route = atoi(e8) != 0 ? GAMC_METRIC_I8 : GAMC_METRIC_F64;
+    }
+    if (route == GAMC_METRIC_AUTO) route = ((double)h->N * (double)p >= 4194304.0) ? GAMC_METRIC_I8 : GAMC_METRIC_F64;
+    if (route == GAMC_METRIC_I8) { gamc_status s8 = setup_metric_i8(h, k, smax); if (s8 != GAMC_OK) return s8; }
   }
   return alloc_arena(h);
 }
@@ -1634,6 +1640,15 @@ gamc_status gamc_target_device_callback(gamc_handle h, int32_t p, gamc_target_en
   h->goff = (1 + p + 1) & ~1;
   h->dcb = enqueue; h->dcb_user = user;
   return alloc_arena(h);
+}
+
+gamc_status gamc_set_metric_route(gamc_handle h, int32_t route, int32_t slices, int32_t smax) {
+  if (!h) return GAMC_INVALID_ARG;
+  REQUIRE(h, route >= GAMC_METRIC_AUTO && route <= GAMC_METRIC_I8, GAMC_INVALID_ARG, "metric route must be GAMC_METRIC_AUTO, _F64 or _I8");
+  REQUIRE(h, slices == 0 || (slices >= 2 && slices <= I8_MAXK), GAMC_INVALID_ARG, "slices must be 0 (default) or 2..7");
+  REQUIRE(h, smax == 0 || (smax >= 2 && smax <= 2 * (slices ? slices : 6)), GAMC_INVALID_ARG, "smax must be 0 (default) or 2..2*slices");
+  h->metric_route = route; h->route_slices = slices; h->route_smax = smax;
+  return GAMC_OK;
 }
 
 gamc_status gamc_comm_set_timeout(gamc_handle h, double seconds) {

@@ -241,35 +241,37 @@ k_i8_slice(const double* __restrict__ X, long long ld, const double* __restrict_
 // the level-2 evaluation of the integer route reads X once (k_i8_slice would read it a second time).  Phase 2 mapping: lane =
 // 4 consecutive rows (lane & 7) x 2 of the warp's 8 columns per unit (lane >> 3, + 4): 32-byte shared loads without bank
 // conflicts, and the four digits of one plane and column go out as one 32-bit store (a quarter-warp writes one 32-byte sector).
+constexpr int DPI_WARPS = 16;                      // consumer warps: the digit extraction is latency-bound, so twice the warps of k_datapass
+constexpr int DPI_THREADS = (DPI_WARPS + 1) * 32;
 struct DataPassI8Smem {
   alignas(128) double ring[DP_NSLOT][DP_UNIT_DOUBLES];
   double theta[512];
   double cs[512];
-  double red[2][DP_CONSUMER_WARPS][32];
+  double red[2][DPI_WARPS][32];
   alignas(8) uint64_t full_bar[DP_NSLOT];
   alignas(8) uint64_t empty_bar[DP_NSLOT];
 };
 
 template <int NU>
-__global__ void __launch_bounds__(DP_THREADS, 1)
+__global__ void __launch_bounds__(DPI_THREADS, 1)
 k_datapass_i8(const __grid_constant__ CUtensorMap mapX, const double* __restrict__ y, const double* __restrict__ theta, int p, long long N,
               double* __restrict__ w_out, double* __restrict__ part_ll, double* __restrict__ part_g, int part_g_stride,
               const double* __restrict__ cs, int k, int8_t* __restrict__ S8, double bias, const int* skip_flag) {
   if (skip_flag && *reinterpret_cast<const volatile int*>(skip_flag)) return;
-  constexpr int RB = 32, CU = 64, CPW = CU / DP_CONSUMER_WARPS;
+  constexpr int RB = 32, CU = 64, CPW = CU / DPI_WARPS, CPL = CPW / 4;   // columns per warp and unit; per lane
   extern __shared__ __align__(128) unsigned char smem_raw[];
   DataPassI8Smem& S = *reinterpret_cast<DataPassI8Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long nrb = (N + RB - 1) / RB;
 
-  for (int c = tid; c < NU * CU; c += DP_THREADS) { S.theta[c] = (c < p) ? theta[c] : 0.0; S.cs[c] = (c < p) ? cs[c] : 0.0; }
+  for (int c = tid; c < NU * CU; c += DPI_THREADS) { S.theta[c] = (c < p) ? theta[c] : 0.0; S.cs[c] = (c < p) ? cs[c] : 0.0; }
   if (tid == 0) {
-    for (int s = 0; s < DP_NSLOT; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], DP_CONSUMER_WARPS); }
+    for (int s = 0; s < DP_NSLOT; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], DPI_WARPS); }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == DP_CONSUMER_WARPS) {
+  if (warp == DPI_WARPS) {
     if (lane == 0) {
       tma_prefetch_desc(&mapX);
       unsigned q = 0;
@@ -292,9 +294,9 @@ k_datapass_i8(const __grid_constant__ CUtensorMap mapX, const double* __restrict
   for (int b = 0; b + 1 < k; ++b) xmask |= 0x80ull << (8 * b);
   const uint32_t xlo = (uint32_t)xmask, xhi = (uint32_t)(xmask >> 32);
   const size_t plane_stride = (size_t)p * I8_KC;
-  double gacc[NU * 2];
+  double gacc[NU * CPL];
 #pragma unroll
-  for (int i = 0; i < NU * 2; ++i) gacc[i] = 0.0;
+  for (int i = 0; i < NU * CPL; ++i) gacc[i] = 0.0;
   double ll = 0.0;
   unsigned q = 0;
   int it = 0;
@@ -314,10 +316,10 @@ k_datapass_i8(const __grid_constant__ CUtensorMap mapX, const double* __restrict
     }
     double* red = &S.red[it & 1][0][0];
     red[warp * 32 + lane] = eta;
-    asm volatile("bar.sync 1, %0;" ::"n"(DP_CONSUMER_WARPS * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(DPI_WARPS * 32) : "memory");
     double e = 0.0;
 #pragma unroll
-    for (int w2 = 0; w2 < DP_CONSUMER_WARPS; ++w2) e += red[w2 * 32 + lane];
+    for (int w2 = 0; w2 < DPI_WARPS; ++w2) e += red[w2 * 32 + lane];
     double sig, sp;
     sigmoid_softplus(e, sig, sp);
     const bool valid = row0 < N;
@@ -338,13 +340,13 @@ k_datapass_i8(const __grid_constant__ CUtensorMap mapX, const double* __restrict
     for (int u = 0; u < NU; ++u) {
       const unsigned qq = q + u, slot = qq % DP_NSLOT;
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
+      for (int jj = 0; jj < CPL; ++jj) {
         const int cl = warp * CPW + cg + 4 * jj;
         const double2 xa = *reinterpret_cast<const double2*>(&S.ring[slot][cl * RB + 4 * rg]);
         const double2 xb = *reinterpret_cast<const double2*>(&S.ring[slot][cl * RB + 4 * rg + 2]);
-        double a = gacc[u * 2 + jj];
+        double a = gacc[u * CPL + jj];
         a = fma(xa.x, rr[0], a); a = fma(xa.y, rr[1], a); a = fma(xb.x, rr[2], a); a = fma(xb.y, rr[3], a);
-        gacc[u * 2 + jj] = a;
+        gacc[u * CPL + jj] = a;
         const int j = u * CU + cl;
         if (j < p) {
           const double c = S.cs[j];
@@ -378,8 +380,8 @@ k_datapass_i8(const __grid_constant__ CUtensorMap mapX, const double* __restrict
 #pragma unroll
   for (int u = 0; u < NU; ++u) {
 #pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-      double v = gacc[u * 2 + jj];
+    for (int jj = 0; jj < CPL; ++jj) {
+      double v = gacc[u * CPL + jj];
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);

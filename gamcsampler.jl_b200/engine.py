@@ -160,6 +160,12 @@ class Engine:
         self._ck(self.lib.gamc_comm_peer_path(self.h, C.byref(out)))
         return int(out.value)
 
+    def set_metric_route(self, route="auto", slices=0, smax=0):
+        """Route of the logistic metric for targets set up after this call: "auto", "f64" (FP64 DMMA) or "i8" (exact int8 digit
+        products on tcgen05; `slices` digit planes, products with a + b <= smax)."""
+        code = {"auto": 0, "f64": 1, "i8": 2}[route] if isinstance(route, str) else int(route)
+        self._ck(self.lib.gamc_set_metric_route(self.h, code, int(slices), int(smax)))
+
     def comm_set_timeout(self, seconds):
         self._ck(self.lib.gamc_comm_set_timeout(self.h, float(seconds)))
 

@@ -445,6 +445,9 @@ function comm_peer_path(h::Handle)
   a[]                                  # bit 0: AM scalar over NVLink mailboxes, bit 1: SMMALA payload summed inside k_land
 end
 comm_set_timeout!(h::Handle, seconds::Real) = check(h, ccall((:gamc_comm_set_timeout, libgamc), Cint, (Handle, Cdouble), h, seconds))
+# metric route of the logistic targets set up afterwards: 0 = auto, 1 = FP64 DMMA, 2 = exact int8 digit products on tcgen05
+set_metric_route!(h::Handle, route::Integer; slices::Integer = 0, smax::Integer = 0) =
+  check(h, ccall((:gamc_set_metric_route, libgamc), Cint, (Handle, Int32, Int32, Int32), h, route, slices, smax))
 
 # ---- batched chains: the examples' `while i <= nchains ... run(job)` loop as one persistent kernel -------------------
 mutable struct BatchedMCJob

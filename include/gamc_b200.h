@@ -153,6 +153,18 @@ gamc_status gamc_target_logistic_device(gamc_handle h, const double* dX, int64_t
  * Bit-identical to oracle/logistic.py:synth_logistic for any sharding. */
 gamc_status gamc_target_logistic_synth(gamc_handle h, uint64_t seed, int64_t row0, int64_t nrows, int32_t p,
                                        const double* theta_true, double lambda);
+/* Route of the metric  X' diag(sigma (1 - sigma)) X  (`ptensorlogtarget`, simulations.jl:35-36) for the logistic targets set up
+ * AFTER this call:
+ *   GAMC_METRIC_AUTO: the integer route when the shard of the design matrix has at least 2^22 entries, else FP64;
+ *   GAMC_METRIC_F64:  weighted SYRK on the FP64 tensor cores (DMMA), elementwise accurate to rounding;
+ *   GAMC_METRIC_I8:   error-free int8 digit products on the 5th-generation tensor cores (tcgen05, TMEM accumulators): diag(sqrt w) X
+ *                     is cut into `slices` signed base-256 digit planes (2..7; 0 = 6) and the digit products D_a' D_b with
+ *                     a + b <= smax (0 = slices + 1) are summed exactly in integers; with the defaults the result agrees with the
+ *                     FP64 evaluation to 1e-13 of the largest entry of the metric, deterministically (no dependence on
+ *                     scheduling).  Needs slices/8 times the memory of X for the digit planes.
+ * The environment variable GAMC_METRIC_I8 ("0", "1" or "slices,smax") overrides the route at target set-up. */
+typedef enum { GAMC_METRIC_AUTO = 0, GAMC_METRIC_F64 = 1, GAMC_METRIC_I8 = 2 } gamc_metric_route;
+gamc_status gamc_set_metric_route(gamc_handle h, int32_t route, int32_t slices, int32_t smax);
 /* Copy rows [r0, r0+n) of the device-resident design matrix / labels back (n x p column-major, ld = n). */
 gamc_status gamc_target_read_rows(gamc_handle h, int64_t r0, int64_t n, double* X_out, double* y_out);
 

@@ -3,6 +3,7 @@ builds the right config, product-side statistics agree with the oracle, and the 
 sharding path reduces to the single-process result."""
 import ctypes
 import os
+import sys
 import re
 
 import numpy as np
@@ -201,6 +202,47 @@ def test_metric_planner_invariants(tmp_path):
                     os.path.join(root, "tests", "cpp", "plan_check.cu"), "-o", exe], check=True, capture_output=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:]
+
+
+def test_i8_planner_invariants(tmp_path):
+    """Host planner of the integer-tensor-core metric (metric_i8_plan.h): every digit product of every output tile is issued exactly
+    once into the right group slot, the int32 head room bounds the item length, every kind covers every row chunk exactly once in
+    row order (tests/cpp/i8_plan_check.cu; only host code runs)."""
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "i8_plan_check")
+    subprocess.run(["nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(root, "gamcsampler.jl_b200", "csrc"),
+                    os.path.join(root, "tests", "cpp", "i8_plan_check.cu"), "-o", exe], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:]
+
+
+def test_i8_scheme_accuracy_numpy():
+    """NumPy statement of the integer route (tests/i8_ref.py) against extended precision: 6 digit planes with the digit products
+    a + b <= 7 reproduce the logistic metric to 1e-13 of its largest entry; the balanced digits reconstruct the fixed-point value
+    exactly; the error grows as advertised with fewer planes."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import i8_ref
+    import oracle as o
+    X, y, tt = o.synth_logistic(20260101, 3000, 48)
+    sig = 1.0 / (1.0 + np.exp(-(X @ tt)))
+    w = sig * (1.0 - sig)
+    Xl = X.astype(np.longdouble)
+    G0 = np.array((Xl.T * w.astype(np.longdouble)) @ Xl, dtype=np.float64)
+    rel = lambda A: float(np.max(np.abs(A - G0)) / np.max(np.abs(G0)))
+    assert rel(i8_ref.metric_i8(X, w, 6, 7)) <= 3e-13
+    assert rel(i8_ref.metric_i8(X, w, 6, 8)) <= 1e-14
+    assert 1e-13 < rel(i8_ref.metric_i8(X, w, 5, 6)) <= 1e-11
+    assert rel(i8_ref.metric_i8(X, w, 4, 5)) <= 2e-8
+    planes, e = i8_ref.digit_planes(X, w, 6)
+    q = sum(planes[s].astype(np.int64) << (8 * (5 - s)) for s in range(6))          # sum_a d_a 256^(k - a)
+    S = np.sqrt(w)[:, None] * X
+    d = q.T - np.rint(S * np.ldexp(1.0, (46 - e).astype(np.int64))[None, :]).astype(np.int64)
+    assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= 1e-3 * d.size       # (the bias is added before the rounding: a tie can go the other way)
+    assert np.abs(planes[0]).max() <= 65 and planes.min() >= -128 and planes.max() <= 127
 
 
 def test_julia_binding_covers_every_entry_point():
