@@ -61,6 +61,17 @@ def parse():
     return ap.parse_args()
 
 
+def _load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
+PEAKS = _load_peaks()
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -390,6 +401,7 @@ def run_ours(args):
             bytes_ll = 8.0 * Nloc * p + 8.0 * Nloc + 8.0 * p             # X + y + theta, this rank's shard
             bytes_lg = 8.0 * Nloc * p + 16.0 * Nloc + 16.0 * p           # + weights written (8N) + gradient partials
             flops_mt = float(Nloc) * p * (p + 1)                         # algorithmic: lower triangle incl. diagonal, FMA = 2
+            route, i8_k, i8_smax = eng.metric_route()
             roofs = {}
             roofs["loglik"] = {"bound": "hbm", "achieved": bytes_ll / (ms_ll / n_ll * 1e-3) * 1e-9 if n_ll else None, "peak": hbm_peak, "unit": "GB/s",
                                "traffic": None, "kernel": "k_datapass<loglik> (AM step)", "launches": n_ll, "avg_ms": ms_ll / n_ll if n_ll else None,
@@ -415,6 +427,26 @@ def run_ours(args):
                                "peak_source": "FP64 pipe rate measured in this run by gamc_probe_fp64_peak = max of the register-only DMMA.8x8x4 loop "
                                               f"({dmma_peak:.1f}) and the DFMA loop ({dfma_peak:.1f} TFLOP/s) on all SMs; tcgen05 has no FP64 kind" if probe > 1.0
                                               else "fallback: profiles/r01_fp64_peak.txt"}
+            if route == "i8":
+                # integer route: the gradient pass also writes the digit planes (k bytes per matrix entry); the metric is a batch of exact
+                # int8 GEMMs on tcgen05 (one 128 x 128 x N product per digit pair and output tile)
+                bytes_lg += float(i8_k) * Nloc * p
+                roofs["loglik_grad"].update({"achieved": bytes_lg / (ms_lg / n_lg * 1e-3) * 1e-9 if n_lg else None, "algorithmic_bytes": bytes_lg,
+                                             "kernel": "k_datapass_i8<loglik+grad+weights+digit planes> (SMMALA step)"})
+                nb = (p + 127) // 128
+                ordered = sum(1 for a in range(1, i8_k + 1) for b in range(1, i8_k + 1) if a + b <= i8_smax)
+                unordered = sum(1 for a in range(1, i8_k + 1) for b in range(a, i8_k + 1) if a + b <= i8_smax)
+                tile_products = nb * unordered + nb * (nb - 1) // 2 * ordered
+                ops = 2.0 * Nloc * 128.0 * 128.0 * tile_products
+                peak_i8 = 2.0 * (PEAKS.get("bf16_tflops_sustained") or PEAKS.get("bf16_tflops") or 1590.0)
+                roofs["metric"] = {"bound": "tensor", "achieved": ops / (ms_mt / n_mt * 1e-3) * 1e-12 if n_mt else None, "peak": peak_i8, "unit": "TOP/s (int8)",
+                                   "traffic": None, "kernel": f"k_metric_i8 (tcgen05.mma kind::i8, TMEM accumulators, TMA-fed): {tile_products} digit products of "
+                                                              f"128 x 128 x N per evaluation ({i8_k} digit planes, a + b <= {i8_smax})",
+                                   "launches": n_mt, "avg_ms": ms_mt / n_mt if n_mt else None, "algorithmic_ops": ops,
+                                   "fp64_equivalent_tflops": flops_mt / (ms_mt / n_mt * 1e-3) * 1e-12 if n_mt else None,
+                                   "fp64_pipe_peak_tflops": peak64,
+                                   "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (a kernel timed inside a step; the int8 tensor rate of "
+                                                  "B200 is twice the bf16 rate: nominal 4.5 POP/s dense)"}
             for r in roofs.values():
                 if r["achieved"]:
                     r["frac"] = r["achieved"] / r["peak"]
@@ -456,7 +488,37 @@ def run_ours(args):
     # ---- the two kernels of the level-2 evaluation one after the other (GAMC_LEVEL2_CO=0), for the record: what the co-scheduled pair is
     # measured against, and the metric kernel's own roofline fraction when it has the SM to itself
     level2_serial = None
-    if p <= 256 and c2.get("roofline", {}).get("launches"):
+    level2_routes = None
+    if eng.metric_route()[0] == "i8" and c2.get("roofline", {}).get("launches"):
+        # for the record: the same evaluation through the FP64 DMMA route (what the integer route replaces)
+        def level2_ms(route):
+            eng.set_metric_route(route)
+            r0_, r1_ = shard_rows(N, world, rank)
+            tt_, th0_ = theta_inputs(p)
+            eng.target_logistic_synth(SEED, r0_, r1_ - r0_, p, tt_, LAMBDA)
+            for _ in range(2):
+                eng.eval_partials(th0_)
+            eng.profile_enable(True)
+            eng.profile_reset()
+            for i in range(6):
+                eng.eval_partials(th0_ + 1e-3 * i)
+            eng.sync()
+            pr = eng.profile_get()
+            eng.profile_enable(False)
+            return sum(pr[k][1] for k in ("loglik_grad", "metric", "reduce")) / 6.0, eng.eval_partials(th0_)[2]
+        try:
+            ms_f64, G_f64 = level2_ms("f64")
+            ms_i8, G_i8 = level2_ms("i8")
+            level2_routes = {"ms_level2_f64_route": ms_f64, "ms_level2_i8_route": ms_i8, "speedup": ms_f64 / ms_i8,
+                             "metric_relerr_between_routes": relerr(G_i8, G_f64),
+                             "what": "one level-2 evaluation (log-lik, gradient, metric, reduction) of this rank's shard, mean of 6, CUDA events per launch: "
+                                     "FP64 route = k_datapass_co || k_metric (DMMA) co-scheduled, integer route = k_datapass_i8 + k_metric_i8 (tcgen05 int8)"}
+        finally:
+            eng.set_metric_route("auto")
+            r0_, r1_ = shard_rows(N, world, rank)
+            tt_, th0_ = theta_inputs(p)
+            eng.target_logistic_synth(SEED, r0_, r1_ - r0_, p, tt_, LAMBDA)
+    elif p <= 256 and c2.get("roofline", {}).get("launches"):
         try:
             os.environ["GAMC_LEVEL2_CO"] = "0"
             r0_, r1_ = shard_rows(N, world, rank)
@@ -618,7 +680,7 @@ def run_ours(args):
             "final_step": c2["final_step"], "updatetensorcount": c2["updatetensorcount"],
             "gpu_launches": c2["gpu_launches"],
             "roofline": c2["roofline"], "roofline_others": c2["roofline_others"], "kernel_time_share": c2["kernel_time_share"],
-            "limiter": c2["limiter"], "fp64_probe": {"dmma_tflops": dmma_peak, "dfma_tflops": dfma_peak}, "level2_serial": level2_serial,
+            "limiter": c2["limiter"], "fp64_probe": {"dmma_tflops": dmma_peak, "dfma_tflops": dfma_peak}, "level2_serial": level2_serial, "level2_routes": level2_routes,
             "parity": parity, "c3": c3, "weak": weak, "with_tensor_reuse": reuse,
             "clocks": clk, "e2e": e2e, "cpu_baseline": cpu,
         }

@@ -127,6 +127,7 @@ SIGNATURES = {
     "gamc_target_device_callback": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p]),
     "gamc_comm_set_timeout": (C.c_int, [_H, C.c_double]),
     "gamc_set_metric_route": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32]),
+    "gamc_get_metric_route": (C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gamc_set_schedule_callback": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "gamc_set_state": (C.c_int, [_H, C.POINTER(StateScalars), _DP, _DP, _DP, _DP]),
     "gamc_get_monitor": (C.c_int, [_H, _DP, _DP]),

@@ -1651,6 +1651,14 @@ gamc_status gamc_set_metric_route(gamc_handle h, int32_t route, int32_t slices, 
   return GAMC_OK;
 }
 
+gamc_status gamc_get_metric_route(gamc_handle h, int32_t* route, int32_t* slices, int32_t* smax) {
+  if (!h) return GAMC_INVALID_ARG;
+  if (route) *route = h->metric_i8 ? GAMC_METRIC_I8 : GAMC_METRIC_F64;
+  if (slices) *slices = h->metric_i8 ? h->i8_k : 0;
+  if (smax) *smax = h->metric_i8 ? h->i8_smax : 0;
+  return GAMC_OK;
+}
+
 gamc_status gamc_comm_set_timeout(gamc_handle h, double seconds) {
   if (!h) return GAMC_INVALID_ARG;
   REQUIRE(h, seconds > 0 && seconds < 1e6, GAMC_INVALID_ARG, "timeout must be positive");

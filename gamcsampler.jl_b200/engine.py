@@ -166,6 +166,12 @@ class Engine:
         code = {"auto": 0, "f64": 1, "i8": 2}[route] if isinstance(route, str) else int(route)
         self._ck(self.lib.gamc_set_metric_route(self.h, code, int(slices), int(smax)))
 
+    def metric_route(self):
+        """("f64" | "i8", slices, smax) of the current target."""
+        r, k, s = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.gamc_get_metric_route(self.h, C.byref(r), C.byref(k), C.byref(s)))
+        return ("i8" if r.value == 2 else "f64"), int(k.value), int(s.value)
+
     def comm_set_timeout(self, seconds):
         self._ck(self.lib.gamc_comm_set_timeout(self.h, float(seconds)))
 

@@ -449,6 +449,12 @@ comm_set_timeout!(h::Handle, seconds::Real) = check(h, ccall((:gamc_comm_set_tim
 set_metric_route!(h::Handle, route::Integer; slices::Integer = 0, smax::Integer = 0) =
   check(h, ccall((:gamc_set_metric_route, libgamc), Cint, (Handle, Int32, Int32, Int32), h, route, slices, smax))
 
+function metric_route(h::Handle)
+  r = Ref{Int32}(0); k = Ref{Int32}(0); s = Ref{Int32}(0)
+  check(h, ccall((:gamc_get_metric_route, libgamc), Cint, (Handle, Ref{Int32}, Ref{Int32}, Ref{Int32}), h, r, k, s))
+  (r[], k[], s[])                      # route (1 = FP64 DMMA, 2 = int8 digit products), digit planes, smax
+end
+
 # ---- batched chains: the examples' `while i <= nchains ... run(job)` loop as one persistent kernel -------------------
 mutable struct BatchedMCJob
   handle::Handle

@@ -165,6 +165,8 @@ gamc_status gamc_target_logistic_synth(gamc_handle h, uint64_t seed, int64_t row
  * The environment variable GAMC_METRIC_I8 ("0", "1" or "slices,smax") overrides the route at target set-up. */
 typedef enum { GAMC_METRIC_AUTO = 0, GAMC_METRIC_F64 = 1, GAMC_METRIC_I8 = 2 } gamc_metric_route;
 gamc_status gamc_set_metric_route(gamc_handle h, int32_t route, int32_t slices, int32_t smax);
+/* The route the CURRENT target uses (GAMC_METRIC_F64 or GAMC_METRIC_I8) and, for the integer route, its digit planes and smax. */
+gamc_status gamc_get_metric_route(gamc_handle h, int32_t* route, int32_t* slices, int32_t* smax);
 /* Copy rows [r0, r0+n) of the device-resident design matrix / labels back (n x p column-major, ld = n). */
 gamc_status gamc_target_read_rows(gamc_handle h, int64_t r0, int64_t n, double* X_out, double* y_out);
 

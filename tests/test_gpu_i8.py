@@ -137,6 +137,7 @@ def test_i8_reuse_tensor_chain_identical(gamc, i8_engine):
     for reuse in (False, True):
         sampler, tuner, rng_ = example_config(gamc, 300, 0, am_mode=2)
         sampler.reuse_tensor = reuse
+        i8_engine.target_logistic(X, y, 100.0)
         job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, rng_, {"p": tt.copy()}, tuner=tuner, tape=gamc.RandomTape(300, 40, seed=8),
                               engine=i8_engine)
         job.run()
