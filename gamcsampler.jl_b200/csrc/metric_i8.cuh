@@ -67,9 +67,11 @@ struct I8Item { int kind, chunk0, nchunks; };
 
 constexpr int I8_RING = 13 * 16384 / I8_TILE_BYTES;   // operand tile slots (208 KB ring; a chunk takes the kind's ntiles consecutive slots)
 constexpr int I8_IQ = 4;                           // items in flight between the producer and the other roles
+constexpr int I8_CQ = 16;                          // chunk barriers (more than the I8_RING chunks that can be in flight)
 struct I8Ctl {
-  alignas(8) uint64_t full[I8_RING];
-  alignas(8) uint64_t empty[I8_RING];
+  alignas(8) uint64_t full[I8_CQ];                 // chunk cs: all its operand tiles have landed
+  alignas(8) uint64_t done[I8_CQ];                 // chunk cs: its MMAs have read the tiles (tcgen05.commit)
+  int nt_of[I8_CQ];                                // producer: tiles of the chunks in flight
   alignas(8) uint64_t item_full[I8_IQ], item_empty[I8_IQ];
   alignas(8) uint64_t tmem_full, tmem_empty;
   uint32_t tmem_base;
@@ -320,12 +322,15 @@ k_datapass_i8(const __grid_constant__ CUtensorMap mapX, const double* __restrict
     double e = 0.0;
 #pragma unroll
     for (int w2 = 0; w2 < DPI_WARPS; ++w2) e += red[w2 * 32 + lane];
-    double sig, sp;
-    sigmoid_softplus(e, sig, sp);
+    // sigma as in sigmoid_softplus (common.cuh); the softplus is needed for the scalar only: warp 0
+    const double ex = exp(-fabs(e));
+    const double inv = 1.0 / (1.0 + ex);
+    const double sig = (e >= 0.0) ? inv : ex * inv;
     const bool valid = row0 < N;
     const double rres = valid ? (yv - sig) : 0.0;
     const double wv = valid ? sig * (1.0 - sig) : 0.0;
     if (warp == 0) {
+      const double sp = fmax(e, 0.0) + log1p(ex);
       ll += valid ? (yv * e - sp) : 0.0;
       if (valid) w_out[row0] = wv;
     }
@@ -367,8 +372,12 @@ k_datapass_i8(const __grid_constant__ CUtensorMap mapX, const double* __restrict
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&S.empty_bar[slot]);
+    }
+    // the units of the row block are released together (no barrier between the units: their work interleaves)
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mbar_arrive(&S.empty_bar[(q + u) % DP_NSLOT]);
     }
     q += NU;
   }
@@ -393,8 +402,8 @@ k_datapass_i8(const __grid_constant__ CUtensorMap mapX, const double* __restrict
 // ---- the int8 GEMMs ---------------------------------------------------------------------------------------------------------
 // Persistent grid (one CTA per SM).  Work items (kind, block of consecutive 128-row chunks), ordered by rows so that all CTAs sweep
 // the digit planes together (the L2 serves the re-reads), are claimed from a global counter by the producer warp and handed to the
-// MMA issuer and the epilogue warps through a small ring.  Operand tiles travel through a ring of I8_RING 16 KB slots with one
-// full / empty mbarrier pair each, so the pipeline depth adapts to the kind's number of tiles and runs on across item boundaries.
+// MMA issuer and the epilogue warps through a small ring.  Operand tiles travel through a ring of I8_RING 16 KB slots with a
+// full / done mbarrier pair per chunk in flight, so the pipeline depth adapts to the kind's number of tiles and runs on across item boundaries.
 // An item accumulates in int32 in tensor memory; its epilogue adds the accumulators to the tile's int64 group slots in global
 // memory with integer atomics: exact, hence independent of which CTA took which item and in which order -- the evaluation is
 // bit-reproducible although the schedule is dynamic.
@@ -408,7 +417,7 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
   unsigned char* tiles = i8_smem_raw + pad;
   I8Ctl& C = *reinterpret_cast<I8Ctl*>(tiles + (size_t)I8_RING * I8_TILE_BYTES);
   if (tid == 0) {
-    for (int s = 0; s < I8_RING; ++s) { mbar_init(&C.full[s], 1); mbar_init(&C.empty[s], 1); }
+    for (int s = 0; s < I8_CQ; ++s) { mbar_init(&C.full[s], 1); mbar_init(&C.done[s], 1); }
     for (int s = 0; s < I8_IQ; ++s) { mbar_init(&C.item_full[s], 1); mbar_init(&C.item_empty[s], 5); }   // consumers: MMA issuer + 4 epilogue warps
     mbar_init(&C.tmem_full, 1);
     mbar_init(&C.tmem_empty, 4);
@@ -425,6 +434,8 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
     // ===== producer: claims items, feeds the tile ring (the warp stays converged; one elected lane issues)
     if (elect_one()) tma_prefetch_desc(&mapS);
     unsigned n = 0;                                  // tile slots handed out so far
+    unsigned cs = 0, head = 0;                       // chunks issued / chunks whose slots have been taken back
+    int nfree = I8_RING;
     I8_CLK_DECL(clk_pw); I8_CLK_DECL(clk_pt); I8_CLK_T(tp0);
     for (unsigned iq = 0;; ++iq) {
       const int e = iq % I8_IQ;
@@ -440,27 +451,36 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
       int tsl[I8_MAXT], tbk[I8_MAXT];
 #pragma unroll
       for (int t = 0; t < I8_MAXT; ++t) { tsl[t] = t < ntiles ? kd->tile_slice[t] : 0; tbk[t] = t < ntiles ? kd->tile_blk[t] * I8_TILE : 0; }
-      for (int c = 0; c < im.nchunks; ++c) {
+      for (int c = 0; c < im.nchunks; ++c, ++cs) {
+        { I8_CLK_T(tw);
+          while (nfree < ntiles) {                   // take back the slots of the oldest chunks in flight
+            mbar_wait(&C.done[head % I8_CQ], (head / I8_CQ) & 1);
+            nfree += C.nt_of[head % I8_CQ];
+            ++head;
+          }
+          I8_CLK_ADD(clk_pw, tw); }
+        nfree -= ntiles;
+        if (elect_one()) {
+          C.nt_of[cs % I8_CQ] = ntiles;
+          uint64_t* fb = &C.full[cs % I8_CQ];
+          mbar_arrive_expect_tx(fb, (uint32_t)ntiles * I8_TILE_BYTES);
 #pragma unroll
-        for (int t = 0; t < I8_MAXT; ++t) {
-          if (t < ntiles) {
-            const unsigned sl = n % I8_RING, round = n / I8_RING;
-            { I8_CLK_T(tw); mbar_wait(&C.empty[sl], (round & 1) ^ 1); I8_CLK_ADD(clk_pw, tw); }
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&C.full[sl], I8_TILE_BYTES);
-              tma_load_4d(tiles + (size_t)sl * I8_TILE_BYTES, &mapS, &C.full[sl], 0, tbk[t], tsl[t], im.chunk0 + c);
+          for (int t = 0; t < I8_MAXT; ++t) {
+            if (t < ntiles) {
+              unsigned sl = n % I8_RING + t; sl -= sl >= I8_RING ? I8_RING : 0;
+              tma_load_4d(tiles + (size_t)sl * I8_TILE_BYTES, &mapS, fb, 0, tbk[t], tsl[t], im.chunk0 + c);
             }
-            __syncwarp();
-            ++n;
           }
         }
+        __syncwarp();
+        n += ntiles;
       }
     }
     I8_CLK_ADD(clk_pt, tp0); I8_CLK_OUT(62, clk_pw); I8_CLK_OUT(63, clk_pt);
     __syncwarp();
   } else if (warp == 5) {
     // ===== MMA issuer (one thread issues; the warp copies the kind of each item to shared memory together)
-    unsigned n = 0, nitem = 0;
+    unsigned n = 0, nitem = 0, cs = 0;
     I8_CLK_DECL(clk_wf); I8_CLK_DECL(clk_wt); I8_CLK_DECL(clk_is); I8_CLK_DECL(clk_tot); I8_CLK_T(tm0);
     for (unsigned iq = 0;; ++iq) {
       const int e = iq % I8_IQ;
@@ -484,10 +504,8 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
         const uint32_t sbase = smem_u32(tiles);
         const uint32_t d0 = tc_desc_lo(sbase);
         for (int c = 0; c < im.nchunks; ++c) {
-          const unsigned base = n % I8_RING, par = (n / I8_RING) & 1;
-          { I8_CLK_T(tw);
-            for (int t = 0; t < ntiles; ++t) { const unsigned m = base + t; if (m < I8_RING) mbar_wait(&C.full[m], par); else mbar_wait(&C.full[m - I8_RING], par ^ 1); }
-            I8_CLK_ADD(clk_wf, tw); }
+          const unsigned base = n % I8_RING;
+          { I8_CLK_T(tw); mbar_wait(&C.full[cs % I8_CQ], (cs / I8_CQ) & 1); I8_CLK_ADD(clk_wf, tw); }
           tc_fence_after();
           I8_CLK_T(ti);
           if (elect_one()) {
@@ -504,14 +522,14 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
               else tc_product<3>(da, db, accum);
               started |= 1u << g;
             }
-            for (int t = 0; t < ntiles; ++t) { unsigned m = base + t; m -= m >= I8_RING ? I8_RING : 0; tc_commit(&C.empty[m]); }   // the slots are free once these MMAs have read them
+            tc_commit(&C.done[cs % I8_CQ]);          // the chunk's slots are free once these MMAs have read them
             if (c == im.nchunks - 1) tc_commit(&C.tmem_full);
           }
           __syncwarp();
           I8_CLK_ADD(clk_is, ti);
           // `started` is per lane: after the first chunk every accumulator of the kind has been written
           started = 0xFu;
-          n += ntiles;
+          n += ntiles; ++cs;
         }
       }
       ++nitem;
@@ -537,14 +555,18 @@ k_metric_i8(const __grid_constant__ CUtensorMap mapS, const I8Kind* __restrict__
       for (int g = 0; g < I8_MAXACC; ++g) slot[g] = g < nacc ? kd->acc_slot[g] : 0;
       mbar_wait(&C.tmem_full, nitem & 1);
       tc_fence_after();
+      const bool diag = kd->bi == kd->bj;
       for (int g = 0; g < nacc; ++g) {
         unsigned long long* out = reinterpret_cast<unsigned long long*>(tbase + (size_t)slot[g] * (I8_TILE * I8_TILE)) + i;
+        // a + b products with a = b on a diagonal tile are symmetric: only i >= j is read by the reduction
+        const bool lower_only = diag && slot[g] < nslots / 2;
         for (int cb = 0; cb < I8_TILE / 32; ++cb) {
+          if (lower_only && cb > warp) break;
           uint32_t r[32];
           tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * I8_TILE + cb * 32), r);
 #pragma unroll
           for (int c = 0; c < 32; ++c)
-            if (r[c]) atomicAdd(out + (size_t)(cb * 32 + c) * I8_TILE, (unsigned long long)(long long)(int)r[c]);
+            if (r[c] && !(lower_only && cb * 32 + c > i)) atomicAdd(out + (size_t)(cb * 32 + c) * I8_TILE, (unsigned long long)(long long)(int)r[c]);
         }
       }
       tc_fence_before();

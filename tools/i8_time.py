@@ -26,7 +26,7 @@ def main():
     for _ in range(a.evals):
         lt, gr, G = eng.eval_upto_tensor(tt)
     dt = (time.perf_counter() - t0) / a.evals
-    print(f"route {'i8 ' + os.environ['GAMC_METRIC_I8'] if os.environ.get('GAMC_METRIC_I8') else 'f64'}: {dt * 1e3:.3f} ms per evaluation (host loop), logtarget {lt:.6f}")
+    print(f"route {eng.metric_route()}: {dt * 1e3:.3f} ms per evaluation (host loop), logtarget {lt:.6f}")
     for k, (n, ms) in eng.profile_get().items():
         if n:
             print(f"  {k:12s} {n:4d} launches  {ms / n:8.4f} ms each")
