@@ -372,12 +372,17 @@ k_datapass_i8(const __grid_constant__ CUtensorMap mapX, const double* __restrict
           }
         }
       }
+      if (NU > 4) {                                  // wide rows: the ring holds less than two row blocks, give every unit back at once
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.empty_bar[slot]);
+      }
     }
-    // the units of the row block are released together (no barrier between the units: their work interleaves)
-    __syncwarp();
-    if (lane == 0) {
+    if (NU <= 4) {                                   // released together (no barrier between the units: their work interleaves)
+      __syncwarp();
+      if (lane == 0) {
 #pragma unroll
-      for (int u = 0; u < NU; ++u) mbar_arrive(&S.empty_bar[(q + u) % DP_NSLOT]);
+        for (int u = 0; u < NU; ++u) mbar_arrive(&S.empty_bar[(q + u) % DP_NSLOT]);
+      }
     }
     q += NU;
   }
