@@ -19,10 +19,10 @@ def _ngpus():
         return 0
 
 
-def _torchrun(n, mode, port):
+def _torchrun(n, mode, port, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tools", "multigpu_check.py"), mode]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, **(env or {})))
 
 
 @pytest.mark.parametrize("mode,port", [("parity", 29531), ("fallback", 29532), ("timeout", 29533)])
@@ -30,6 +30,16 @@ def test_two_ranks(mode, port):
     if _ngpus() < 2:
         pytest.skip("needs two GPUs")
     out = _torchrun(2, mode, port)
+    assert out.returncode == 0 and "PASS" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
+
+
+def test_two_ranks_integer_metric_route():
+    """The same parity job with the metric forced onto the integer tensor cores on every rank (GAMC_METRIC_I8=1; the test sizes are
+    below the automatic threshold): every rank cuts its own row shard into digit planes with its own column exponents, and the
+    reduced metric still equals the single-GPU evaluation of all rows and the oracle."""
+    if _ngpus() < 2:
+        pytest.skip("needs two GPUs")
+    out = _torchrun(2, "parity", 29536, env={"GAMC_METRIC_I8": "1"})
     assert out.returncode == 0 and "PASS" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
 
 

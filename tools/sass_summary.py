@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel SASS mnemonic counts of libgamc_b200.so (cuobjdump -sass): the instructions that prove which hardware paths the
-kernels use -- DMMA (FP64 tensor cores), UTMALDG (TMA bulk tensor loads), SYNCS (mbarrier), LDGSTS (cp.async), and that no
-tcgen05 (UTC*MMA / LDTM) or HMMA/IMMA instructions are present (tcgen05 has no FP64 kind).  Usage: tools/sass_summary.py > profiles/rNN_sass_summary.md"""
+kernels use -- DMMA (FP64 tensor cores), UTCIMMA / UTCBAR / LDTM (tcgen05.mma kind::i8, tcgen05.commit, tcgen05.ld: the integer
+route of the metric), UTMALDG (TMA bulk tensor loads), SYNCS (mbarrier), LDGSTS (cp.async); no legacy HMMA / IMMA.  Usage: tools/sass_summary.py > profiles/rNN_sass_summary.md"""
 import os
 import re
 import subprocess
@@ -10,7 +10,7 @@ from collections import Counter, OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "gamcsampler.jl_b200", "libgamc_b200.so")
-WATCH = ["DMMA", "DFMA", "UTMALDG", "SYNCS", "LDGSTS", "UTCMMA", "UTCHMMA", "UTCIMMA", "LDTM", "HMMA", "IMMA", "MUFU", "SHFL", "BAR", "LDG", "STG", "LDS", "STS"]
+WATCH = ["DMMA", "DFMA", "UTCIMMA", "UTCBAR", "LDTM", "UTCATOMSWS", "UTMALDG", "SYNCS", "LDGSTS", "UTCHMMA", "HMMA", "IMMA", "REDG", "ATOMG", "MUFU", "SHFL", "BAR", "LDG", "STG", "LDS", "STS"]
 
 
 def demangle(names):
@@ -43,8 +43,9 @@ def main():
     for c in kernels.values():
         tot.update(c)
     print("Totals: " + ", ".join(f"{w} {tot[w]}" for w in WATCH) + f"; instructions {tot['_total']}.\n")
-    print("`UTC*MMA` / `LDTM` (tcgen05) = 0 by design: tcgen05 has no FP64 kind; the FP64 tensor path on sm_100a is `DMMA.8x8x4`.\n")
-    cols = ["DMMA", "DFMA", "UTMALDG", "SYNCS", "LDGSTS", "MUFU", "SHFL", "BAR"]
+    print("tcgen05 (`UTCIMMA`, `UTCBAR` = tcgen05.commit, `LDTM` = tcgen05.ld, `UTCATOMSWS` = TMEM allocation) appears in `k_metric_i8` only: tcgen05 has no "
+          "FP64 kind, so the FP64 tensor path is `DMMA.8x8x4` and the metric reaches the 5th-generation tensor cores through exact int8 digit products.\n")
+    cols = ["DMMA", "DFMA", "UTCIMMA", "UTCBAR", "LDTM", "UTMALDG", "SYNCS", "LDGSTS", "REDG", "MUFU", "SHFL", "BAR"]
     print("| kernel | instructions | " + " | ".join(cols) + " |")
     print("|---|---|" + "---|" * len(cols))
     for (mangled, c), name in zip(kernels.items(), names):
