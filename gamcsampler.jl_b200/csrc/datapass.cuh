@@ -180,6 +180,98 @@ k_datapass(const __grid_constant__ CUtensorMap mapX, const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// k_datapass_ll3<NU>: the log-likelihood at THREE parameter vectors in one read of X (am_mode 3: the proposal of an AM step and
+// the two candidate proposals of the NEXT AM step -- one per accept/reject outcome -- so that two consecutive AM steps cost one
+// HBM pass).  Same TMA ring and the same order of summation per vector as k_datapass<NU, 1, false>.
+// part_ll[v * part_stride + cta]: per-CTA partial of vector v.
+// ---------------------------------------------------------------------------------------------------
+constexpr int DP3_NSLOT = 12;                  // ring depth (192 KB: three parameter vectors and three scratch sets need room)
+struct DataPassLL3Smem {
+  alignas(128) double ring[DP3_NSLOT][DP_UNIT_DOUBLES];
+  double theta[3][512];
+  double red[2][3][DP_CONSUMER_WARPS][32];
+  alignas(8) uint64_t full_bar[DP3_NSLOT];
+  alignas(8) uint64_t empty_bar[DP3_NSLOT];
+};
+
+template <int NU>
+__global__ void __launch_bounds__(DP_THREADS, 1)
+k_datapass_ll3(const __grid_constant__ CUtensorMap mapX, const double* __restrict__ y, const double* __restrict__ th0,
+               const double* __restrict__ th1, const double* __restrict__ th2, int p, long long N, double* __restrict__ part_ll, int part_stride) {
+  constexpr int RB = 32, CU = 64, CPW = CU / DP_CONSUMER_WARPS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  DataPassLL3Smem& S = *reinterpret_cast<DataPassLL3Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long nrb = (N + RB - 1) / RB;
+  for (int c = tid; c < NU * CU; c += DP_THREADS) {
+    S.theta[0][c] = (c < p) ? th0[c] : 0.0; S.theta[1][c] = (c < p) ? th1[c] : 0.0; S.theta[2][c] = (c < p) ? th2[c] : 0.0;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < DP3_NSLOT; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], DP_CONSUMER_WARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (warp == DP_CONSUMER_WARPS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&mapX);
+      unsigned q = 0;
+      for (long long rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+#pragma unroll 1
+        for (int u = 0; u < NU; ++u, ++q) {
+          const unsigned slot = q % DP3_NSLOT, round = q / DP3_NSLOT;
+          mbar_wait(&S.empty_bar[slot], (round & 1) ^ 1);
+          mbar_arrive_expect_tx(&S.full_bar[slot], DP_UNIT_DOUBLES * 8);
+          tma_load_2d(S.ring[slot], &mapX, &S.full_bar[slot], (int)(rb * RB), u * CU);
+        }
+      }
+    }
+    return;
+  }
+  double ll0 = 0.0;                              // warp v < 3: the scalar of vector v
+  unsigned q = 0;
+  int it = 0;
+  for (long long rb = blockIdx.x; rb < nrb; rb += gridDim.x, ++it) {
+    const long long row0 = rb * RB + lane;
+    const double yv = (row0 < N) ? __ldg(&y[row0]) : 0.0;
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const unsigned qq = q + u, slot = qq % DP3_NSLOT, round = qq / DP3_NSLOT;
+      mbar_wait(&S.full_bar[slot], round & 1);
+      const double* base = &S.ring[slot][(warp * CPW) * RB + lane];
+      const int c0 = u * CU + warp * CPW;
+#pragma unroll
+      for (int jj = 0; jj < CPW; ++jj) {
+        const double x = base[jj * RB];
+        e0 = fma(x, S.theta[0][c0 + jj], e0);
+        e1 = fma(x, S.theta[1][c0 + jj], e1);
+        e2 = fma(x, S.theta[2][c0 + jj], e2);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.empty_bar[slot]);
+    }
+    double* red = &S.red[it & 1][0][0][0];
+    red[(0 * DP_CONSUMER_WARPS + warp) * 32 + lane] = e0;
+    red[(1 * DP_CONSUMER_WARPS + warp) * 32 + lane] = e1;
+    red[(2 * DP_CONSUMER_WARPS + warp) * 32 + lane] = e2;
+    asm volatile("bar.sync 1, %0;" ::"n"(DP_CONSUMER_WARPS * 32) : "memory");
+    if (warp < 3) {                              // warp v finishes vector v
+      double e = 0.0;
+#pragma unroll
+      for (int w2 = 0; w2 < DP_CONSUMER_WARPS; ++w2) e += red[(warp * DP_CONSUMER_WARPS + w2) * 32 + lane];
+      double sig, sp;
+      sigmoid_softplus(e, sig, sp);
+      ll0 += (row0 < N) ? (yv * e - sp) : 0.0;
+    }
+    q += NU;
+  }
+  if (warp < 3) {
+    const double v = warp_sum(ll0);
+    if (lane == 0) part_ll[(size_t)warp * part_stride + blockIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // k_datapass_co<NU>: the log-likelihood + gradient + weights pass of a level-2 evaluation, built to run CONCURRENTLY with the
 // metric kernel on the same SMs (one pass over X out of HBM for the whole evaluation: the metric kernel follows a bounded
 // number of rows behind and finds its slabs in L2).  The metric pass is bound by the FP64 tensor pipe and leaves HBM idle; this

@@ -107,6 +107,8 @@ struct gamc_ctx : gamc_ctx_base {
   double* vecs = nullptr; double* mats = nullptr; DevState* d_state = nullptr;
   unsigned char* arena = nullptr; size_t arena_bytes = 0;   // [state | vecs | R | mats]: the L2-persisting working set of the step kernels
   long long h_count = 0; bool h_present = true, h_past = false, spec_ready = false;
+  long long h_tot_prop = 0, h_tot_totprop = 0;   // host mirror of the tuner's proposal counters: which steps are burn-in tuning events (am_mode 3)
+  double* part_ll3 = nullptr; int part_ll3_stride = 0;   // per-CTA partials of the three-vector log-likelihood pass (am_mode 3)
   // tape
   long long tape_n = 0, tape_pos = 0, tape_cap = 0; int tape_p = 0;
   double* d_tape = nullptr; std::vector<double> h_usched;
@@ -190,7 +192,7 @@ void free_target(gamc_ctx* h) {
   if (h->own_data) { cudaFree(h->dX); cudaFree(h->dy); }
   h->dX = h->dy = nullptr; h->own_data = false;
   cudaFree(h->dw); h->dw = nullptr;
-  cudaFree(h->part_ll); cudaFree(h->part_g); h->part_ll = h->part_g = nullptr;
+  cudaFree(h->part_ll); cudaFree(h->part_g); cudaFree(h->part_ll3); h->part_ll = h->part_g = h->part_ll3 = nullptr;
   cudaFree(h->d_plans_fused); h->d_plans_fused = nullptr; h->metric_fused = false;
   cudaFree(h->d_co_flags); h->d_co_flags = nullptr; h->level2_co = false;
   cudaFree(h->d_co_dbg); h->d_co_dbg = nullptr;
@@ -369,6 +371,30 @@ gamc_status launch_dp_nu(gamc_ctx* h, const double* theta, const int* skip) {
 gamc_status launch_datapass(gamc_ctx* h, const double* theta, bool grad, const int* skip = nullptr) {
   if (h->dp_rpl == 2) return grad ? launch_dp_nu<2, true>(h, theta, skip) : launch_dp_nu<2, false>(h, theta, skip);
   return grad ? launch_dp_nu<1, true>(h, theta, skip) : launch_dp_nu<1, false>(h, theta, skip);
+}
+
+// log-likelihood at three parameter vectors in one pass (am_mode 3)
+template <int NU>
+gamc_status launch_ll3_t(gamc_ctx* h, const double* t0, const double* t1, const double* t2) {
+  auto kern = k_datapass_ll3<NU>;
+  { gamc_status s = ensure_attr(h, (const void*)kern, sizeof(DataPassLL3Smem)); if (s != GAMC_OK) return s; }
+  ProfScope ps(h, GAMC_K_LOGLIK);
+  kern<<<h->dp_grid, DP_THREADS, sizeof(DataPassLL3Smem), h->stream>>>(h->mapXA, h->dy, t0, t1, t2, h->p, h->N, h->part_ll3, h->part_ll3_stride);
+  CUDA_TRY(h, cudaGetLastError());
+  return GAMC_OK;
+}
+gamc_status launch_ll3(gamc_ctx* h, const double* t0, const double* t1, const double* t2) {
+  switch (h->dp_nu) {
+    case 1: return launch_ll3_t<1>(h, t0, t1, t2);
+    case 2: return launch_ll3_t<2>(h, t0, t1, t2);
+    case 3: return launch_ll3_t<3>(h, t0, t1, t2);
+    case 4: return launch_ll3_t<4>(h, t0, t1, t2);
+    case 5: return launch_ll3_t<5>(h, t0, t1, t2);
+    case 6: return launch_ll3_t<6>(h, t0, t1, t2);
+    case 7: return launch_ll3_t<7>(h, t0, t1, t2);
+    case 8: return launch_ll3_t<8>(h, t0, t1, t2);
+    default: h->err = "unsupported number of column units"; return GAMC_UNSUPPORTED_SHAPE;
+  }
 }
 
 gamc_status launch_metric(gamc_ctx* h, const int* skip = nullptr) {
@@ -584,7 +610,7 @@ gamc_status alloc_arena(gamc_ctx* h) {
   h->goff = (1 + p + 1) & ~1;  // G starts 16-byte aligned
   {
     const size_t pp = (size_t)p * p;
-    const size_t n_state = 64, n_vecs = ((size_t)20 * p + 16 + 15) & ~(size_t)15, n_R = ((size_t)h->goff + pp + 15) & ~(size_t)15, n_mats = 9 * pp + 2 * la_invd_doubles(p);
+    const size_t n_state = 64, n_vecs = ((size_t)22 * p + 16 + 15) & ~(size_t)15, n_R = ((size_t)h->goff + pp + 15) & ~(size_t)15, n_mats = 9 * pp + 2 * la_invd_doubles(p);
     h->arena_bytes = sizeof(double) * (n_state + n_vecs + n_R + n_mats);
     CUDA_TRY(h, cudaMalloc(&h->arena, h->arena_bytes));
     CUDA_TRY(h, cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
@@ -626,6 +652,8 @@ gamc_status setup_target(gamc_ctx* h) {
   {
     const int rows = std::max(h->dp_grid, h->num_sms + 8);   // the fused level-2 kernel writes one row per metric CTA
     CUDA_TRY(h, cudaMalloc(&h->part_ll, sizeof(double) * rows));
+    CUDA_TRY(h, cudaMalloc(&h->part_ll3, sizeof(double) * 3 * rows));
+    h->part_ll3_stride = rows;
     CUDA_TRY(h, cudaMalloc(&h->part_g, sizeof(double) * (size_t)rows * h->part_g_stride));
   }
   // metric layout
@@ -816,6 +844,10 @@ gamc_status check_device_error(gamc_ctx* h) {
     h->err = "matrix is not positive definite; Cholesky factorization failed at pivot " + std::to_string(st.error_pivot) +
              " (iteration " + std::to_string(st.error_iter) + ")";
     return GAMC_NOT_POSDEF;
+  }
+  if (st.error_flag == GAMC_CUDA_ERROR) {
+    h->err = "internal: a paired AM step (am_mode 3) found a stale candidate proposal (iteration " + std::to_string(st.error_iter) + ")";
+    return GAMC_CUDA_ERROR;
   }
   if (st.error_flag == GAMC_NCCL_ERROR) {
     h->err = "peer all-reduce timed out waiting for rank " + std::to_string(st.error_pivot) + " (iteration " + std::to_string(st.error_iter) + ")";
@@ -1274,7 +1306,7 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   REQUIRE(h, cfg->t0 > 0, GAMC_INVALID_ARG, "t0 is not positive");
   REQUIRE(h, cfg->schedule >= 0 && cfg->schedule <= GAMC_SCHED_RAND_QUAD_DECAY, GAMC_INVALID_ARG, "unknown schedule");
   REQUIRE(h, cfg->period >= 1 && cfg->nsteps >= 1 && cfg->burnin >= 0, GAMC_INVALID_ARG, "bad period / nsteps / burnin");
-  REQUIRE(h, cfg->am_mode >= 0 && cfg->am_mode <= 2, GAMC_INVALID_ARG, "am_mode must be 0, 1 or 2");
+  REQUIRE(h, cfg->am_mode >= 0 && cfg->am_mode <= 3, GAMC_INVALID_ARG, "am_mode must be 0, 1, 2 or 3");
   REQUIRE(h, cfg->sampler_kind == 0 || cfg->sampler_kind == 1, GAMC_INVALID_ARG, "sampler_kind must be 0 (GAMC) or 1 (MALA)");
   cudaSetDevice(h->device);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1305,10 +1337,10 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
   B.U = h->mats + 2 * pp; B.Ustride = pp;
   B.invU = h->mats + 9 * pp; B.invUstride = la_invd_doubles(p);
   B.C = h->mats + 4 * pp; B.W = h->mats + 5 * pp; B.Lc = h->mats + 6 * pp; B.Lstride = pp;   // Lc: three buffers (am_mode 2 rotates them)
-  CUDA_TRY(h, cudaMemsetAsync(h->vecs, 0, sizeof(double) * ((size_t)p * 20 + 16), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->vecs, 0, sizeof(double) * ((size_t)p * 22 + 16), h->stream));
   double* v = h->vecs;
   B.gs = v; v += 2 * p; B.rdiagU = v; v += 2 * p; B.fterm = v; v += 2 * p;
-  B.theta = v; v += p; B.theta_prop = v; v += p; B.mu = v; v += p; B.lastmean = v; v += p; B.secondlastmean = v; v += p; B.rdiagL = v; v += 3 * p; B.accbuf = v; v += 2 * p; B.land = v;
+  B.theta = v; v += p; B.theta_prop = v; v += p; B.mu = v; v += p; B.lastmean = v; v += p; B.secondlastmean = v; v += p; B.rdiagL = v; v += 3 * p; B.accbuf = v; v += 2 * p; B.cand = v; v += 2 * p; B.land = v;
   B.R = h->R; B.goff = h->goff;
   h->chain_cap = std::max<long long>(0, cfg->nsteps - cfg->burnin);
   if (h->chain_cap > 0) {
@@ -1353,6 +1385,7 @@ gamc_status gamc_sampler_init(gamc_handle h, const gamc_config* cfg, const doubl
     if (s != GAMC_OK) return s;
   }
   h->h_count = 0; h->h_present = true; h->h_past = false; h->spec_ready = false;   // MuvGAMCState outer ctor (:117-118)
+  h->h_tot_prop = 0; h->h_tot_totprop = cfg->period;
   h->tape_n = 0; h->tape_pos = 0;
   h->sampler_ready = true;
   return check_device_error(h);
@@ -1448,15 +1481,25 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
   }
   if (h->comm && (h->p2p_ready || h->land_p2p) && n > 0) { s = comm_stream_barrier(h); if (s != GAMC_OK) return s; }
   // branch sequence of these n iterations (the schedule coin depends only on (i, nsteps, u_sched))
-  std::vector<unsigned char> kinds(n);
+  std::vector<unsigned char> kinds(n), events(n);
   {
     bool pr = h->h_present;
+    long long tp = h->h_tot_prop, ttp = h->h_tot_totprop;
     for (long long k = 0; k < n; ++k) {
       const long long t = h->h_count + k + 1;
       if (t > h->cfg.t0) pr = branch_decision(h, t, h->h_usched[h->tape_pos + k]);
       kinds[k] = pr ? 1 : 0;
+      // burn-in tuning events (step_tail: tot_prop counts every transition while the tuner is on and restarts at every event)
+      events[k] = 0;
+      if (T.tuning) {
+        ++tp;
+        if (ttp <= T.burnin && (tp % T.period) == 0) { events[k] = 1; ttp += tp; tp = 0; }
+      }
     }
+    h->h_tot_prop = tp; h->h_tot_totprop = ttp;
   }
+  // am_mode 3: two consecutive AM steps share one data pass (needs the partial sums to be added on this rank's device)
+  const bool can_pair = T.am_mode == 3 && h->dp_rpl == 1 && !generic_target(h) && (!h->comm || h->p2p_ready);
   for (long long k = 0; k < n; ++k) {
     ++h->h_count;                                                                        // iterate/GAMC.jl:2
     const long long ti = h->tape_pos++;
@@ -1472,6 +1515,42 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
       s = launch_step(h, GAMC_K_SMMALA_POST, k_smmala_post, B, T, ti); if (s != GAMC_OK) return s;
     } else {                                                                             // :128
       const bool next_am = (T.am_mode == 2) && (k + 1 < n) && !kinds[k + 1];            // next step is AM too: speculate
+      const bool pair = can_pair && (k + 1 < n) && !kinds[k + 1] && !events[k];          // ... and share this step's data pass
+      if (pair) {
+        // ---- am_mode 3: steps k and k + 1 in one data pass.  This step's factor and proposal; both candidate factors and proposals of
+        //      the next step (one per outcome of this one); the log-likelihood at all three; the two accept/reject kernels.
+        if (!h->spec_ready) {
+          if (h->h_past) { s = launch_seed_factor(h); if (s != GAMC_OK) return s; }
+          const int nbuf = am_r1_nbuf(h->p);
+          ProfScope ps(h, GAMC_K_AM_PRE);
+          k_am_pre_r1<<<1, LA_THREADS, am_r1_smem_bytes(h->p, nbuf), h->stream>>>(B, T, ti, nbuf, 0);
+          CUDA_TRY(h, cudaGetLastError());
+        }
+        {
+          const int nbuf = am_r1_nbuf(h->p);
+          ProfScope ps(h, GAMC_K_AM_PRE);
+          k_am_pre_r1<<<2, LA_THREADS, am_r1_smem_bytes(h->p, nbuf), h->stream>>>(B, T, ti + 1, nbuf, 2);
+          CUDA_TRY(h, cudaGetLastError());
+        }
+        s = launch_ll3(h, B.theta_prop, B.cand, B.cand + h->p); if (s != GAMC_OK) return s;    // :148 of both steps
+        const size_t smem = step_smem_bytes(h->p);
+        for (int half = 0; half < 2; ++half) {
+          PeerArgs pa{};
+          if (h->comm && h->p2p_ready) { pa.peers = h->d_peers; pa.nranks = h->nranks; pa.rank = h->rank; pa.seq = ++h->p2p_seq; pa.timeout_ns = h->peer_timeout_ns; }
+          ProfScope ps(h, GAMC_K_AM_POST);
+          if (half == 0)
+            k_am_post<<<1, LA_THREADS, smem, h->stream>>>(B, T, ti, 1, h->part_ll3, h->dp_grid, pa, nullptr, 0);
+          else
+            k_am_post<<<1, LA_THREADS, smem, h->stream>>>(B, T, ti + 1, 0, h->part_ll3 + h->part_ll3_stride, h->dp_grid, pa,
+                                                          h->part_ll3 + 2 * (size_t)h->part_ll3_stride, 1);
+          CUDA_TRY(h, cudaGetLastError());
+        }
+        // host bookkeeping of the second step (iterate/GAMC.jl:2,8-10,197)
+        ++h->h_count; ++h->tape_pos; ++k;
+        h->spec_ready = false;
+        h->h_past = false;
+        continue;
+      }
       if (T.am_mode >= 1) {
         if (!h->spec_ready) {
           if (h->h_past) { s = launch_seed_factor(h); if (s != GAMC_OK) return s; }      // chol(oldinvtensor) = U^-T seeds the update
@@ -1506,7 +1585,7 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
       {
         const size_t smem = step_smem_bytes(h->p);
         ProfScope ps(h, GAMC_K_AM_POST);
-        k_am_post<<<1, LA_THREADS, smem, h->stream>>>(B, T, ti, next_am ? 1 : 0, h->part_ll, nparts_post, pa);
+        k_am_post<<<1, LA_THREADS, smem, h->stream>>>(B, T, ti, next_am ? 1 : 0, h->part_ll, nparts_post, pa, nullptr, 0);
         CUDA_TRY(h, cudaGetLastError());
       }
       h->spec_ready = next_am;
@@ -1705,6 +1784,7 @@ gamc_status gamc_set_state(gamc_handle h, const gamc_state_scalars* st_in, const
   st.chain_saved = 0; st.tune_events = 0; st.lcur = 0;
   CUDA_TRY(h, cudaMemcpyAsync(B.st, &st, sizeof(DevState), cudaMemcpyHostToDevice, h->stream));
   h->h_count = st_in->count;
+  h->h_tot_prop = st_in->total_proposed; h->h_tot_totprop = st_in->total_totproposed;
   h->h_present = st_in->count == 0 ? true : st_in->presentupdatetensor != 0;
   h->h_past = st_in->count == 0 ? false : st_in->pastupdatetensor != 0;
   h->spec_ready = false; h->tape_n = 0; h->tape_pos = 0;

@@ -57,6 +57,7 @@ struct Bufs {
   double* Lc;                            // p x p  lower Cholesky factor of eps*C (am_mode 0) / of C (am_mode 1)
   double* rdiagL;                        // p  (am_mode 2: three buffers of p, like Lc)
   double* accbuf;                        // [2][p] unscaled proposal products L' z of the two speculative outcomes (am_mode 2)
+  double* cand;                          // [2][p] candidate proposals of the NEXT AM step, one per outcome of this one (am_mode 3)
   size_t Lstride;                        // p*p: distance between the AM factor buffers
   double* W;                             // p x p  scratch: triangular inverse
   double* chain_value; unsigned char* chain_accept; long long chain_cap;
@@ -501,6 +502,8 @@ __host__ __device__ inline int am_r1_nbuf(int p) { return am_r1_smem_bytes(p, 2)
 // current step runs: CTA o in {0, 1} assumes the current proposal is accepted (o = 0) or rejected (o = 1), reads the
 // current factor, writes the updated factor to buffer (lcur + 1 + o) % 3 and the unscaled product L' z to accbuf[o];
 // k_am_post picks the outcome that happened.  Same arithmetic as spec = 0, so the chain is bit-identical.
+// spec = 2 (am_mode 3): as spec = 1, on the main stream BEFORE the data pass, and also writes the two candidate proposals of the next
+// step (B.cand) so that the pass can evaluate the log-likelihood at them together with this step's proposal.
 __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, long long tape_idx, int nbuf, int spec) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   DevState* st = B.st;
@@ -660,14 +663,22 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_pre_r1(Bufs B, TuneCfg T, 
     return;
   }
   if (spec) {
-    if (i < p) B.accbuf[(size_t)outcome * p + i] = acc;                     // scaled by sqrt(eps) once the outcome is known
+    if (i < p) {
+      B.accbuf[(size_t)outcome * p + i] = acc;                              // scaled by sqrt(eps) once the outcome is known
+      if (spec == 2) {
+        // am_mode 3: the candidate proposal itself, exactly as k_am_post will form it after the decision (the host pairs two AM
+        // steps only when the first is not a tuning event, so sqrt(eps) is the one the next iterate! sees)
+        const double umix = B.tape_umix[tape_idx];
+        B.cand[(size_t)outcome * p + i] = (umix <= 1.0 - T.c) ? fma(st->sqrtstep, acc, th) : fma(T.sqrtminorscale, zs[i], th);   // (explicit fma: the three places that form an AM proposal must round alike)
+      }
+    }
     if (tid == 0) st->spec_err[outcome] = 0;
     return;
   }
   if (i < p) {
     const double umix = B.tape_umix[tape_idx];
-    if (umix <= 1.0 - T.c) B.theta_prop[i] = th + st->sqrtstep * acc;       // core component  N(theta, eps C)
-    else B.theta_prop[i] = th + T.sqrtminorscale * zs[i];                   // stabilising component
+    if (umix <= 1.0 - T.c) B.theta_prop[i] = fma(st->sqrtstep, acc, th);    // core component  N(theta, eps C)
+    else B.theta_prop[i] = fma(T.sqrtminorscale, zs[i], th);                // stabilising component
   }
 }
 
@@ -712,13 +723,25 @@ __global__ void __launch_bounds__(256) k_llt(const double* __restrict__ L, int p
 // into its slot of every peer's mailbox, waits until its own mailbox holds this step's sequence number from every rank,
 // and adds the values in rank order: the same bits on every rank.  Slots alternate with the parity of the sequence
 // number (a rank can be at most one step ahead of the slowest one).
+// pair_second = 1 (am_mode 3): second AM step of a pair.  Its proposal was written by the first step's k_am_post; the data pass
+// of the pair has already evaluated the log-likelihood at both candidates: part_ll belongs to the candidate of an ACCEPTED first
+// step, part_alt to the candidate of a rejected one (st->last_accept tells which).  The candidate is compared with the proposal
+// bit for bit: a difference (the host paired across a tuning event) raises an error instead of using a stale value.
 __global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, long long tape_idx, int next_spec,
-                                                           const double* __restrict__ part_ll, int nparts, PeerArgs pa) {
+                                                           const double* __restrict__ part_ll, int nparts, PeerArgs pa,
+                                                           const double* __restrict__ part_alt, int pair_second) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StepSmem S = step_smem_carve(smem_raw, T.p);
   DevState* st = B.st;
   const int p = T.p;
   if (st->error_flag) return;
+  if (pair_second) {
+    const int o = st->last_accept ? 0 : 1;
+    if (o) part_ll = part_alt;
+    int bad = 0;
+    for (int i = threadIdx.x; i < p; i += blockDim.x) bad |= (B.theta_prop[i] != B.cand[(size_t)o * p + i]);
+    if (__syncthreads_or(bad)) { raise_error(st, 4 /*GAMC_CUDA_ERROR: internal*/, 0); return; }
+  }
   // everything this kernel reads later, requested now: one L2 round trip instead of five dependent ones
   for (int i = threadIdx.x * 16; i < p; i += blockDim.x * 16) {      // one request per 128-byte line
     prefetch_l1(B.theta_prop + i); prefetch_l1(B.theta + i); prefetch_l1(B.lastmean + i);
@@ -792,7 +815,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_am_post(Bufs B, TuneCfg T, lo
     const double sq = st->sqrtstep;                                           // after this step's tuning, as the next iterate! sees it
     for (int i = threadIdx.x; i < p; i += blockDim.x) {
       const double th = B.theta[i];
-      B.theta_prop[i] = (umix <= 1.0 - T.c) ? th + sq * B.accbuf[(size_t)o * p + i] : th + T.sqrtminorscale * z[i];
+      B.theta_prop[i] = (umix <= 1.0 - T.c) ? fma(sq, B.accbuf[(size_t)o * p + i], th) : fma(T.sqrtminorscale, z[i], th);
     }
     if (threadIdx.x == 0) {
       st->lcur = (st->lcur + 1 + o) % 3;

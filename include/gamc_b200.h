@@ -73,7 +73,10 @@ typedef struct {
   int32_t am_mode;         /* 0 = literal covariance recursion + Cholesky each AM step,
                               1 = rank-one Cholesky update of the same recursion (fast path),
                               2 = as 1, computed for both accept/reject outcomes on a side stream while
-                                  the data pass runs (bit-identical chain, shorter critical path)  */
+                                  the data pass runs (bit-identical chain, shorter critical path),
+                              3 = two consecutive AM steps share ONE pass over X: the pass evaluates the log-likelihood at this
+                                  step's proposal and at both candidate proposals of the next step (same arithmetic per
+                                  vector; steps that are burn-in tuning events are not paired)                       */
   int32_t sampler_kind;    /* 0 = GAMC, 1 = MALA (Klara's comparison sampler, examples/logistic_regression/src/MALA/simulations.jl:37;
                               identity metric: only driftstep, the total tuner and the range are used)          */
   int32_t reuse_tensor;    /* 0 = literal: an SMMALA step that follows an AM step always re-evaluates gradient and metric at

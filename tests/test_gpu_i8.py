@@ -116,7 +116,7 @@ def test_i8_deterministic_and_routes_agree(engine):
         engine.set_metric_route("auto")
 
 
-@pytest.mark.parametrize("am_mode", [0, 2])
+@pytest.mark.parametrize("am_mode", [0, 2, 3])
 @pytest.mark.parametrize("N,p,nsteps", [(200, 4, 2000), (2000, 64, 1000), (6000, 256, 1000), (4000, 512, 400)])
 def test_i8_trajectory_parity(gamc, i8_engine, N, p, nsteps, am_mode):
     """GAMC chains whose SMMALA steps use the integer-route metric: step for step against the oracle on a shared tape (identical

@@ -91,14 +91,15 @@ def _run_both(gamc, engine, N, p, nsteps, burnin, seed, am_mode=0, update=None, 
     return job, chain, osam, v, a, k
 
 
-@pytest.mark.parametrize("am_mode", [0, 1, 2])
+@pytest.mark.parametrize("am_mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("N,p,nsteps", [(200, 4, 3000), (500, 33, 1200), (2000, 64, 1000), (3000, 130, 1000), (6000, 256, 1000), (4000, 512, 1000),
                                         (2500, 300, 160), (2500, 352, 160), (2500, 353, 120)])
 def test_trajectory_parity(gamc, engine, N, p, nsteps, am_mode):
     """Same host-drawn normals and uniforms => step-for-step agreement for >= 1000 iterations, including the BASELINE
     dimensions p = 256 and p = 512; p = 300 / 352 / 353 straddle the panel-buffer switch of the rank-one AM update.
     am_mode 0 = literal covariance recursion + Cholesky per AM step; 1 = rank-one Cholesky update (fast path);
-    2 = the same update computed speculatively for both accept/reject outcomes while the data pass runs."""
+    2 = the same update computed speculatively for both accept/reject outcomes while the data pass runs;
+    3 = two consecutive AM steps share one pass over X (log-likelihood at the proposal and at both candidates of the next step)."""
     burnin = nsteps // 5
     job, chain, osam, v, a, k = _run_both(gamc, engine, N, p, nsteps, burnin, seed=42, am_mode=am_mode)
     assert chain.value.shape == v.shape
@@ -155,7 +156,7 @@ def test_smmala_ratio_parity(gamc, engine, N, p, nsteps):
     assert abs(st.logtarget - osam.logtarget) <= 1e-10 * abs(osam.logtarget)
 
 
-@pytest.mark.parametrize("am_mode", [0, 1, 2])
+@pytest.mark.parametrize("am_mode", [0, 1, 2, 3])
 def test_am_covariance_readout(gamc, engine, am_mode):
     """sstate.oldinvtensor after a run that ends in AM steps = the Haario covariance recursion seeded with inv(G)."""
     job, chain, osam, v, a, k = _run_both(gamc, engine, 400, 9, 60, 0, seed=4, am_mode=am_mode, update=gamc.mod_update(7))
@@ -177,7 +178,7 @@ def test_errors(gamc, engine):
         engine.target_logistic(np.zeros((10, 513)), np.zeros(10), 100.0)
 
 
-@pytest.mark.parametrize("am_mode", [0, 1, 2])
+@pytest.mark.parametrize("am_mode", [0, 1, 2, 3])
 def test_am_before_enough_history_raises_posdef(gamc, engine, am_mode):
     """t0 = 1 lets an AM step run at t = 2/3, where Klara's covariance recursion has k = 0/1 and the proposal covariance
     is not positive definite: the reference throws from the MvNormal constructor (set_gmm, GAMC.jl:188); here the device
@@ -221,23 +222,25 @@ def test_mala_trajectory_parity(gamc, engine, N, p, nsteps):
 
 
 def test_speculative_am_is_bitwise_identical(gamc, engine):
-    """am_mode 2 overlaps the factor update with the data pass; it must not change a single bit of the chain."""
+    """am_mode 2 overlaps the factor update with the data pass, am_mode 3 evaluates two AM steps in one data pass (including across
+    burn-in tuning events, which must not be paired); neither may change a single bit of the chain."""
     import oracle as o
     X, y, tt = o.synth_logistic(5, 5000, 96)
     theta0 = tt + 0.05 * np.random.default_rng(2).standard_normal(96)
     nsteps = 700
     engine.target_logistic(X, y, 100.0)
     out = []
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         sampler, tuner, rng_ = example_config(gamc, nsteps, 100, am_mode=mode, verbose=True)
         job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, rng_, {"p": theta0}, tuner=tuner, tape=gamc.RandomTape(nsteps, 96, seed=4), engine=engine)
         job.run()
         st = engine.state()
         out.append((job.output(), st.step, st.am_totproposed, st.total_totproposed, engine.array(5)))
-    assert np.array_equal(out[0][0].value, out[1][0].value)
-    assert np.array_equal(out[0][0].diagnosticvalues, out[1][0].diagnosticvalues)
-    assert out[0][1:4] == out[1][1:4]
-    assert np.array_equal(out[0][4], out[1][4])
+    for other in out[1:]:
+        assert np.array_equal(out[0][0].value, other[0].value)
+        assert np.array_equal(out[0][0].diagnosticvalues, other[0].diagnosticvalues)
+        assert out[0][1:4] == other[1:4]
+        assert np.array_equal(out[0][4], other[4])
 
 
 @pytest.mark.parametrize("am_mode", [0, 2])

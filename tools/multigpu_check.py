@@ -125,7 +125,7 @@ def main():
     ok = ok and abs(ll - ll0) <= 1e-10 * abs(ll0) and relerr(gl, gl0) <= 1e-10 and relerr(Gl, Gl0) <= 1e-10
     # trajectory: identical on every rank and equal to the oracle
     nsteps = 600
-    for am_mode in (0, 1, 2):
+    for am_mode in (0, 1, 2, 3):
         sampler = g.GAMC(update=g.rand_exp_decay_update(10.0), driftstep=0.02, minorscale=0.001, c=0.01, am_mode=am_mode)
         tuner = g.GAMCTuner(g.VanillaMCTuner(), g.VanillaMCTuner(), g.AcceptanceRateMCTuner(0.35))
         tape = g.RandomTape(nsteps, p, seed=3)
