@@ -46,9 +46,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--logN", type=int, default=20, help="log2 of the GLOBAL number of rows (default 2^20 = BASELINE C2)")
     ap.add_argument("--p", type=int, default=256)
-    ap.add_argument("--am-mode", type=int, default=int(os.environ.get("GAMC_AM_MODE", "2")),
-                    help="2 = rank-one Cholesky update, computed speculatively for both outcomes while the data pass runs (default; bit-identical to 1); "
-                         "1 = rank-one update on the critical path; 0 = literal covariance recursion + Cholesky")
+    ap.add_argument("--am-mode", type=int, default=int(os.environ.get("GAMC_AM_MODE", "3")),
+                    help="3 = two consecutive AM steps share one pass over X (default; bit-identical chain); 2 = rank-one Cholesky update, computed "
+                         "speculatively for both outcomes while the data pass runs; 1 = rank-one update on the critical path; 0 = literal covariance "
+                         "recursion + Cholesky")
     ap.add_argument("--clock-interval-ms", type=int, default=100, help="nvidia-smi sampling period")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

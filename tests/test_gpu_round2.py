@@ -88,7 +88,7 @@ def test_set_state_restart_large_p(gamc, engine):
     assert relerr(np.concatenate([part1, part2], axis=1), full.value) <= 1e-9
 
 
-@pytest.mark.parametrize("am_mode", [0, 1, 2])
+@pytest.mark.parametrize("am_mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("split", [137, 150])
 def test_set_state_restart(gamc, engine, am_mode, split):
     """gamc_set_state: stop a chain after `split` transitions, carry the state over the host, restart on a fresh sampler and
