@@ -1499,7 +1499,13 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
     h->h_tot_prop = tp; h->h_tot_totprop = ttp;
   }
   // am_mode 3: two consecutive AM steps share one data pass (needs the partial sums to be added on this rank's device)
-  const bool can_pair = T.am_mode == 3 && h->dp_rpl == 1 && !generic_target(h) && (!h->comm || h->p2p_ready);
+  // Pairing puts both factor updates (~2 x 58 us at p = 256) on the critical path and saves one data pass: it pays when the pass over
+  // this rank's shard takes longer than ~100 us (0.65 GB); below that (small shards of a many-GPU job) am_mode 3 runs as am_mode 2.
+  double pair_min_bytes = 6.5e8;
+  if (const char* e = getenv("GAMC_AM_PAIR_MIN_BYTES")) pair_min_bytes = atof(e);   // tests: 0 pairs at any size
+  const bool pass_is_long = 8.0 * (double)h->N * (double)h->p >= pair_min_bytes;
+  const bool can_pair = T.am_mode == 3 && pass_is_long && h->dp_rpl == 1 && !generic_target(h) && (!h->comm || h->p2p_ready);
+  const bool spec_mode = T.am_mode == 2 || (T.am_mode == 3 && !can_pair);
   for (long long k = 0; k < n; ++k) {
     ++h->h_count;                                                                        // iterate/GAMC.jl:2
     const long long ti = h->tape_pos++;
@@ -1514,7 +1520,7 @@ gamc_status gamc_run(gamc_handle h, int64_t n) {
       s = eval_and_land(h, B.theta_prop, 2); if (s != GAMC_OK) return s;                 // :37
       s = launch_step(h, GAMC_K_SMMALA_POST, k_smmala_post, B, T, ti); if (s != GAMC_OK) return s;
     } else {                                                                             // :128
-      const bool next_am = (T.am_mode == 2) && (k + 1 < n) && !kinds[k + 1];            // next step is AM too: speculate
+      const bool next_am = spec_mode && (k + 1 < n) && !kinds[k + 1];                  // next step is AM too: speculate
       const bool pair = can_pair && (k + 1 < n) && !kinds[k + 1] && !events[k];          // ... and share this step's data pass
       if (pair) {
         // ---- am_mode 3: steps k and k + 1 in one data pass.  This step's factor and proposal; both candidate factors and proposals of

@@ -243,6 +243,23 @@ def test_speculative_am_is_bitwise_identical(gamc, engine):
         assert np.array_equal(out[0][4], other[4])
 
 
+def test_am_mode3_unpaired_fallback_is_bitwise_identical(gamc, engine, monkeypatch):
+    """Below the size threshold am_mode 3 runs as am_mode 2 (speculative factor update on the side stream, one data pass per AM step):
+    the same chain, bit for bit, as with the pairing forced on."""
+    import oracle as o
+    X, y, tt = o.synth_logistic(6, 4000, 48)
+    theta0 = tt + 0.05 * np.random.default_rng(3).standard_normal(48)
+    engine.target_logistic(X, y, 100.0)
+    out = []
+    for thr in ("0", "1e18"):
+        monkeypatch.setenv("GAMC_AM_PAIR_MIN_BYTES", thr)
+        sampler, tuner, rng_ = example_config(gamc, 400, 100, am_mode=3)
+        job = gamc.BasicMCJob(gamc.LogisticModel(X, y, 100.0), sampler, rng_, {"p": theta0}, tuner=tuner, tape=gamc.RandomTape(400, 48, seed=5), engine=engine)
+        job.run()
+        out.append((job.output().value.copy(), engine.launch_count()))
+    assert np.array_equal(out[0][0], out[1][0])
+
+
 @pytest.mark.parametrize("am_mode", [0, 2])
 def test_generic_target_callback_parity(gamc, engine, am_mode):
     """an arbitrary model through `gamc_target_callback` -- the host evaluates the Klara-style closures
