@@ -727,8 +727,19 @@ gamc_status setup_target(gamc_ctx* h) {
       if (sscanf(e8, "%d,%d", &ek, &es) == 2) { route = GAMC_METRIC_I8; k = ek; smax = es; }
       else route = atoi(e8) != 0 ? GAMC_METRIC_I8 : GAMC_METRIC_F64;
     }
-    if (route == GAMC_METRIC_AUTO) route = ((double)h->N * (double)p >= 4194304.0) ? GAMC_METRIC_I8 : GAMC_METRIC_F64;
-    if (route == GAMC_METRIC_I8) { gamc_status s8 = setup_metric_i8(h, k, smax); if (s8 != GAMC_OK) return s8; }
+    const bool automatic = route == GAMC_METRIC_AUTO;
+    if (automatic) route = ((double)h->N * (double)p >= 4194304.0) ? GAMC_METRIC_I8 : GAMC_METRIC_F64;
+    if (route == GAMC_METRIC_I8) {
+      gamc_status s8 = setup_metric_i8(h, k, smax);
+      if (s8 != GAMC_OK) {
+        if (!automatic) return s8;
+        // automatic route: the digit planes (slices / 8 of the size of X) did not fit beside X -- evaluate the metric on the FP64 route
+        cudaGetLastError();
+        cudaFree(h->d_i8S); cudaFree(h->d_i8cs); cudaFree(h->d_i8cg); cudaFree(h->d_i8acc); cudaFree(h->d_i8cmax); cudaFree(h->d_i8kinds); cudaFree(h->d_i8items); cudaFree(h->d_i8ints);
+        h->d_i8S = nullptr; h->d_i8cs = h->d_i8cg = nullptr; h->d_i8acc = nullptr; h->d_i8cmax = nullptr; h->d_i8kinds = nullptr; h->d_i8items = nullptr; h->d_i8ints = nullptr;
+        h->metric_i8 = false; h->err.clear();
+      }
+    }
   }
   return alloc_arena(h);
 }
