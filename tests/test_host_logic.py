@@ -220,6 +220,30 @@ def test_i8_planner_invariants(tmp_path):
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:]
 
 
+def test_integer_metric_kernel_uses_tcgen05_without_issue_loops():
+    """SASS of the built library (cuobjdump, no GPU needed): k_metric_i8 issues tcgen05.mma kind::i8 (UTCIMMA), commits to mbarriers
+    (UTCBAR), reads TMEM (LDTM), is fed by TMA (UTMALDG) and adds its results with 64-bit integer reductions (REDG ... .64); and the MMA /
+    TMA issue compiles to straight-line code -- no per-lane `BRA.U.ANY` loop around the uniform-register moves (what `if (lane == 0)`
+    instead of `elect.sync` produced: three times slower issue than the tensor pipe needs)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "gamcsampler.jl_b200", "libgamc_b200.so")
+    if shutil.which("cuobjdump") is None or not os.path.exists(lib):
+        pytest.skip("cuobjdump or the built library not available")
+    txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    body, on = [], False
+    for line in txt.splitlines():
+        if "Function :" in line:
+            on = "k_metric_i8" in line
+        elif on:
+            body.append(line)
+    sass = "\n".join(body)
+    assert sass.count("UTCIMMA") >= 16 and sass.count("UTCBAR") >= 2 and sass.count("LDTM") >= 1 and sass.count("UTMALDG") >= 1
+    assert "REDG.E.ADD.64" in sass
+    assert sass.count("BRA.U.ANY") == 0
+
+
 def test_i8_scheme_accuracy_numpy():
     """NumPy statement of the integer route (tests/i8_ref.py) against extended precision: 6 digit planes with the digit products
     a + b <= 7 reproduce the logistic metric to 1e-13 of its largest entry; the balanced digits reconstruct the fixed-point value
