@@ -244,6 +244,24 @@ def test_integer_metric_kernel_uses_tcgen05_without_issue_loops():
     assert sass.count("BRA.U.ANY") == 0
 
 
+def test_i8_scheme_golden():
+    """The committed fixture of the integer metric route (tests/golden/i8_scheme.json, made by make_golden.py): the NumPy statement
+    still produces the same column exponents, digit planes (bit for bit) and metric, and that metric is the FP64 oracle's to 1e-12."""
+    import json
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import i8_ref
+    import oracle as o
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "i8_scheme.json")))
+    X, y, tt = o.synth_logistic(d["seed"], d["N"], d["p"])
+    planes, e = i8_ref.digit_planes(X, np.array(d["w"]), d["slices"])
+    assert np.array_equal(e, np.array(d["column_exponents"]))
+    assert np.array_equal(planes, np.array(d["planes"], dtype=np.int8))
+    G = i8_ref.metric_from_planes(planes, e, d["smax"])
+    assert np.array_equal(G, np.array(d["G_lik"]))
+    Gl = o.logistic_partials(np.array(d["theta"]), X, y)[2]
+    assert np.max(np.abs(G - Gl)) <= 1e-12 * np.max(np.abs(Gl))
+
+
 def test_i8_scheme_accuracy_numpy():
     """NumPy statement of the integer route (tests/i8_ref.py) against extended precision: 6 digit planes with the digit products
     a + b <= 7 reproduce the logistic metric to 1e-13 of its largest entry; the balanced digits reconstruct the fixed-point value
