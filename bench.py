@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 SEED = 20260101
 LAMBDA = 100.0
 FP64_DMMA_PEAK_TFLOPS_FALLBACK = 37.1   # profiles/r01_fp64_peak.txt; only used if the in-run probe fails
-NCU_TRAFFIC_FILE = "profiles/r02_ncu_summary.md"
+NCU_TRAFFIC_FILE = "profiles/r02b_ncu_i8_summary.md (integer route, k_datapass_ll3) and profiles/r02_ncu_summary.md (FP64 route, k_datapass)"
 
 
 def parse():
@@ -448,6 +448,10 @@ def run_ours(args):
                                    "fp64_pipe_peak_tflops": peak64,
                                    "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (a kernel timed inside a step; the int8 tensor rate of "
                                                   "B200 is twice the bf16 rate: nominal 4.5 POP/s dense)"}
+            if route == "i8" and Nloc == (1 << 20) and p == 256 and i8_k == 6:
+                # DRAM bytes per launch from the committed ncu capture of this very configuration (profiles/r02b_ncu_i8_summary.md): recorded, not re-measured
+                roofs["loglik_grad"]["traffic"] = 2.155968e9 + 1.572147e9
+                roofs["metric"]["traffic"] = 2.311153e9 + 0.021818e9
             for r in roofs.values():
                 if r["achieved"]:
                     r["frac"] = r["achieved"] / r["peak"]
